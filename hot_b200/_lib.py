@@ -1,0 +1,74 @@
+"""ctypes binding of include/hot_b200.h (the reference-side binding a maintainer would add is in INTEGRATION.md)."""
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhot_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "hot_b200.h")
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+_lib = None
+
+_c_double_p = C.POINTER(C.c_double)
+_c_int_p = C.POINTER(C.c_int)
+_c_u64_p = C.POINTER(C.c_ulonglong)
+_c_i64_p = C.POINTER(C.c_longlong)
+
+
+def declared_symbols(header=HEADER_PATH):
+    """Every function name declared in the C header (used by the ABI test)."""
+    text = open(header).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hot_[a-z0-9_]+)\s*\(", text)))
+
+
+def load_library(path=LIB_PATH):
+    """Load the CUDA library; raise loudly (no CPU fallback exists) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise LibraryMissing(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(hot_b200 has no CPU fallback)")
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    sig = {
+        "hot_create": (vp, [C.c_double, C.c_double, C.c_double, C.c_int]),
+        "hot_destroy": (None, [vp]),
+        "hot_last_error": (C.c_char_p, [vp]),
+        "hot_set_stream": (C.c_int, [vp, vp]),
+        "hot_synchronize": (C.c_int, [vp]),
+        "hot_launch_count": (C.c_longlong, [vp]),
+        "hot_linear_offset": (C.c_int, [vp, C.c_long, _c_int_p, _c_u64_p]),
+        "hot_linear_to_coord": (C.c_int, [vp, C.c_long, _c_u64_p, _c_int_p]),
+        "hot_packed_add": (C.c_int, [vp, C.c_long, _c_u64_p, _c_u64_p, _c_u64_p]),
+        "hot_set_particles": (C.c_int, [vp, C.c_long] + [vp] * 8),
+        "hot_get_particles": (C.c_int, [vp] + [vp] * 5),
+        "hot_num_particles": (C.c_long, [vp]),
+        "hot_sort_and_activate": (C.c_int, [vp]),
+        "hot_num_groups": (C.c_long, [vp]),
+        "hot_num_pages": (C.c_long, [vp]),
+        "hot_get_sort": (C.c_int, [vp, vp, vp, vp]),
+        "hot_get_groups": (C.c_int, [vp, vp, vp, vp]),
+        "hot_get_pages": (C.c_int, [vp, vp]),
+        "hot_p2g": (C.c_int, [vp, _c_int_p]),
+        "hot_num_nodes": (C.c_int, [vp]),
+        "hot_get_grid": (C.c_int, [vp, vp, vp, vp]),
+        "hot_get_id2coord": (C.c_int, [vp, vp]),
+        "hot_get_mass_matrix": (C.c_int, [vp, vp]),
+        "hot_set_dv": (C.c_int, [vp, vp]),
+        "hot_g2p": (C.c_int, [vp, C.c_double, _c_int_p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib._hot_signatures = sig
+    _lib = lib
+    return lib

@@ -1,0 +1,336 @@
+// extern "C" entry points of include/hot_b200.h: argument checking, host<->device marshalling, dispatch.
+#include "../../include/hot_b200.h"
+#include "sim.h"
+
+using namespace hot;
+
+struct hot_sim : public hot::Sim {
+    DevBuf<double> stage; // AoS staging for host<->device particle marshalling
+    DevBuf<unsigned long long> stage_u;
+    DevBuf<int> stage_i;
+};
+
+namespace {
+
+constexpr int TPB = 256;
+inline int nblk(long n) { return (int)((n + TPB - 1) / TPB); }
+
+thread_local std::string g_create_error;
+
+// AoS (n x comps, original order) -> component-major SoA rows
+__global__ void k_aos_to_soa(long n, int comps, const double* __restrict__ aos, size_t stride, double* __restrict__ soa)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * comps) return;
+    long i = t / comps;
+    int c = (int)(t - i * comps);
+    soa[c * stride + i] = aos[t];
+}
+// SoA rows in sorted order -> AoS in original order
+__global__ void k_soa_to_aos(long n, int comps, const double* __restrict__ soa, size_t stride, const int* __restrict__ orig_id,
+    double* __restrict__ aos)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * comps) return;
+    long s = t / comps;
+    int c = (int)(t - s * comps);
+    aos[(size_t)orig_id[s] * comps + c] = soa[c * stride + s];
+}
+__global__ void k_iota_i(long n, int* v)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) v[t] = (int)t;
+}
+__global__ void k_mask_ops(int op, long n, const int* __restrict__ ijk_in, const unsigned long long* __restrict__ a,
+    const unsigned long long* __restrict__ b, unsigned long long* __restrict__ out, int* __restrict__ ijk_out)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    if (op == 0) out[t] = linear_offset(ijk_in[3 * t], ijk_in[3 * t + 1], ijk_in[3 * t + 2]);
+    else if (op == 1) {
+        ijk_out[3 * t] = (int)bit_pack(a[t], Geo::xmask);
+        ijk_out[3 * t + 1] = (int)bit_pack(a[t], Geo::ymask);
+        ijk_out[3 * t + 2] = (int)bit_pack(a[t], Geo::zmask);
+    }
+    else out[t] = packed_add(a[t], b[t]);
+}
+// particle_sorter / particle_order / particle_base_offset views of the device state
+__global__ void k_export_sort(long n, const uint64_t* __restrict__ keys, int* __restrict__ order, unsigned long long* __restrict__ base_offset)
+{
+    long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint64_t key = keys[s];
+    int o = (int)(key & ((1ull << Geo::index_bits) - 1));
+    order[s] = o;
+    base_offset[o] = (key >> Geo::index_bits) << Geo::data_bits;
+}
+__global__ void k_export_groups(long G, const int* __restrict__ group_first, int* __restrict__ first, int* __restrict__ last)
+{
+    long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    first[g] = group_first[g];
+    last[g] = group_first[g + 1] - 1;
+}
+__global__ void k_export_pages(long NP, const uint32_t* __restrict__ page_id, unsigned long long* __restrict__ out)
+{
+    long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < NP) out[p] = (unsigned long long)page_id[p] << 12;
+}
+__global__ void k_export_grid(long n, size_t gs, const int* __restrict__ idx, const double* __restrict__ v, long long* __restrict__ idx64,
+    double* __restrict__ v_aos)
+{
+    long a = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    idx64[a] = idx[a];
+    v_aos[3 * a] = v[a];
+    v_aos[3 * a + 1] = v[gs + a];
+    v_aos[3 * a + 2] = v[2 * gs + a];
+}
+__global__ void k_id2coord(int n_nodes, const int* __restrict__ dof_slot, const uint32_t* __restrict__ page_id, int* __restrict__ coord)
+{
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_nodes) return;
+    int a = dof_slot[id];
+    uint64_t off = ((uint64_t)page_id[a / Geo::E] << 12) | ((uint64_t)(a % Geo::E) << Geo::data_bits);
+    coord[3 * id] = (int)bit_pack(off, Geo::xmask);
+    coord[3 * id + 1] = (int)bit_pack(off, Geo::ymask);
+    coord[3 * id + 2] = (int)bit_pack(off, Geo::zmask);
+}
+
+template <class T>
+int d2h(hot_sim* s, T* host, const T* dev, size_t n)
+{
+    HOT_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+hot_sim* hot_create(double dx, double apic_rpic_ratio, double cfl, int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        fprintf(stderr, "hot_create: no usable CUDA device (%s); hot_b200 has no CPU fallback\n", cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) {
+        fprintf(stderr, "hot_create: cudaSetDevice(%d) failed\n", device);
+        return nullptr;
+    }
+    if (!(dx > 0)) {
+        fprintf(stderr, "hot_create: dx must be positive\n");
+        return nullptr;
+    }
+    hot_sim* s = new hot_sim;
+    cudaGetDevice(&s->device);
+    s->dx = dx;
+    s->apic_rpic_ratio = apic_rpic_ratio;
+    s->cfl = cfl;
+    return s;
+}
+
+void hot_destroy(hot_sim* s)
+{
+    if (!s) return;
+    if (s->hcount) cudaFreeHost(s->hcount);
+    delete s;
+}
+
+const char* hot_last_error(hot_sim* s) { return s ? s->err.c_str() : "null handle"; }
+
+int hot_set_stream(hot_sim* s, void* cuda_stream)
+{
+    s->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+int hot_synchronize(hot_sim* s)
+{
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+long long hot_launch_count(hot_sim* s) { return s->launches; }
+
+static int mask_op(hot_sim* s, int op, long n, const int* ijk_in, const unsigned long long* a, const unsigned long long* b,
+    unsigned long long* out, int* ijk_out)
+{
+    if (n <= 0) return 0;
+    HOT_CUDA(s->stage_u.reserve(3 * n));
+    HOT_CUDA(s->stage_i.reserve(3 * n));
+    unsigned long long *da = s->stage_u.p, *db = s->stage_u.p + n, *dout = s->stage_u.p + 2 * n;
+    if (ijk_in) HOT_CUDA(cudaMemcpyAsync(s->stage_i.p, ijk_in, 3 * n * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    if (a) HOT_CUDA(cudaMemcpyAsync(da, a, n * sizeof(*a), cudaMemcpyHostToDevice, s->stream));
+    if (b) HOT_CUDA(cudaMemcpyAsync(db, b, n * sizeof(*b), cudaMemcpyHostToDevice, s->stream));
+    k_mask_ops<<<nblk(n), TPB, 0, s->stream>>>(op, n, s->stage_i.p, da, db, dout, s->stage_i.p);
+    HOT_LAUNCHED(s);
+    if (out) return d2h(s, out, dout, n);
+    return d2h(s, ijk_out, s->stage_i.p, 3 * n);
+}
+int hot_linear_offset(hot_sim* s, long n, const int* ijk, unsigned long long* out) { return mask_op(s, 0, n, ijk, nullptr, nullptr, out, nullptr); }
+int hot_linear_to_coord(hot_sim* s, long n, const unsigned long long* off, int* ijk) { return mask_op(s, 1, n, nullptr, off, nullptr, nullptr, ijk); }
+int hot_packed_add(hot_sim* s, long n, const unsigned long long* a, const unsigned long long* b, unsigned long long* out)
+{
+    return mask_op(s, 2, n, nullptr, a, b, out, nullptr);
+}
+
+int hot_set_particles(hot_sim* s, long n, const double* X, const double* V, const double* mass, const double* C, const double* F,
+    const double* vol, const double* mu, const double* lambda)
+{
+    if (n <= 0) return fail(s, "hot_set_particles: n must be positive");
+    if (!X || !V || !mass || !C || !F || !vol || !mu || !lambda) return fail(s, "hot_set_particles: null attribute array");
+    HOT_CUDA(s->P.reserve(n));
+    HOT_CUDA(s->stage.reserve(28 * (size_t)n));
+    s->N = n;
+    cudaStream_t st = s->stream;
+    struct Item { const double* h; int comps; double* soa; };
+    Item items[] = {{X, 3, s->P.X.p}, {V, 3, s->P.V.p}, {mass, 1, s->P.M.p}, {C, 9, s->P.C.p}, {F, 9, s->P.F.p}, {vol, 1, s->P.vol.p},
+        {mu, 1, s->P.mu.p}, {lambda, 1, s->P.lam.p}};
+    size_t off = 0;
+    for (const Item& it : items) {
+        double* d = s->stage.p + off;
+        HOT_CUDA(cudaMemcpyAsync(d, it.h, (size_t)n * it.comps * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (it.comps == 1)
+            HOT_CUDA(cudaMemcpyAsync(it.soa, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        else {
+            k_aos_to_soa<<<nblk(n * it.comps), TPB, 0, st>>>(n, it.comps, d, s->P.stride, it.soa);
+            HOT_LAUNCHED(s);
+        }
+        off += (size_t)n * it.comps;
+    }
+    k_iota_i<<<nblk(n), TPB, 0, st>>>(n, s->P.orig_id.p);
+    HOT_LAUNCHED(s);
+    s->sorted = false;
+    s->p2g_done = false;
+    return 0;
+}
+
+int hot_get_particles(hot_sim* s, double* X, double* V, double* C, double* F, double* gradV)
+{
+    const long n = s->N;
+    if (n <= 0) return fail(s, "hot_get_particles: no particles");
+    if (gradV && s->P.gradV.cap < 9 * s->P.stride) return fail(s, "hot_get_particles: gradV is only defined after hot_g2p");
+    HOT_CUDA(s->stage.reserve(28 * (size_t)n));
+    cudaStream_t st = s->stream;
+    struct Item { double* h; int comps; const double* soa; };
+    Item items[] = {{X, 3, s->P.X.p}, {V, 3, s->P.V.p}, {C, 9, s->P.C.p}, {F, 9, s->P.F.p}, {gradV, 9, s->P.gradV.p}};
+    size_t off = 0;
+    for (const Item& it : items) {
+        if (!it.h) continue;
+        if (off + (size_t)n * it.comps > 28 * (size_t)n) { // staging holds 28 doubles per particle
+            HOT_CUDA(cudaStreamSynchronize(st));
+            off = 0;
+        }
+        double* d = s->stage.p + off;
+        k_soa_to_aos<<<nblk(n * it.comps), TPB, 0, st>>>(n, it.comps, it.soa, s->P.stride, s->P.orig_id.p, d);
+        HOT_LAUNCHED(s);
+        HOT_CUDA(cudaMemcpyAsync(it.h, d, (size_t)n * it.comps * sizeof(double), cudaMemcpyDeviceToHost, st));
+        off += (size_t)n * it.comps;
+    }
+    HOT_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+long hot_num_particles(hot_sim* s) { return s->N; }
+
+int hot_sort_and_activate(hot_sim* s) { return sort_and_activate(s); }
+long hot_num_groups(hot_sim* s) { return s->n_groups; }
+long hot_num_pages(hot_sim* s) { return s->n_pages; }
+
+int hot_get_sort(hot_sim* s, unsigned long long* sorter, int* order, unsigned long long* base_offset)
+{
+    if (!s->sorted) return fail(s, "hot_get_sort: call hot_sort_and_activate first");
+    const long n = s->N;
+    if (sorter) {
+        int rc = d2h(s, sorter, (const unsigned long long*)s->keys.p, n);
+        if (rc) return rc;
+    }
+    if (order || base_offset) {
+        HOT_CUDA(s->stage_i.reserve(n));
+        HOT_CUDA(s->stage_u.reserve(n));
+        k_export_sort<<<nblk(n), TPB, 0, s->stream>>>(n, s->keys.p, s->stage_i.p, s->stage_u.p);
+        HOT_LAUNCHED(s);
+        if (order) {
+            int rc = d2h(s, order, s->stage_i.p, n);
+            if (rc) return rc;
+        }
+        if (base_offset) return d2h(s, base_offset, s->stage_u.p, n);
+    }
+    return 0;
+}
+
+int hot_get_groups(hot_sim* s, int* first, int* last, unsigned long long* block_offset)
+{
+    if (!s->sorted) return fail(s, "hot_get_groups: call hot_sort_and_activate first");
+    const long G = s->n_groups;
+    HOT_CUDA(s->stage_i.reserve(2 * G));
+    k_export_groups<<<nblk(G), TPB, 0, s->stream>>>(G, s->group_first.p, s->stage_i.p, s->stage_i.p + G);
+    HOT_LAUNCHED(s);
+    int rc = 0;
+    if (first) rc = d2h(s, first, s->stage_i.p, G);
+    if (!rc && last) rc = d2h(s, last, s->stage_i.p + G, G);
+    if (!rc && block_offset) rc = d2h(s, block_offset, (const unsigned long long*)s->group_block.p, G);
+    return rc;
+}
+
+int hot_get_pages(hot_sim* s, unsigned long long* offsets)
+{
+    if (!s->sorted) return fail(s, "hot_get_pages: call hot_sort_and_activate first");
+    HOT_CUDA(s->stage_u.reserve(s->n_pages));
+    k_export_pages<<<nblk(s->n_pages), TPB, 0, s->stream>>>(s->n_pages, s->page_id.p, s->stage_u.p);
+    HOT_LAUNCHED(s);
+    return d2h(s, offsets, s->stage_u.p, s->n_pages);
+}
+
+int hot_p2g(hot_sim* s, int* n_nodes)
+{
+    int rc = p2g(s);
+    if (rc) return rc;
+    if (n_nodes) *n_nodes = s->num_nodes;
+    return 0;
+}
+int hot_num_nodes(hot_sim* s) { return s->num_nodes; }
+
+int hot_get_grid(hot_sim* s, long long* idx, double* m, double* v)
+{
+    if (!s->p2g_done) return fail(s, "hot_get_grid: call hot_p2g first");
+    const long gn = (long)s->g_stride;
+    HOT_CUDA(s->stage.reserve(3 * gn));
+    HOT_CUDA(s->stage_u.reserve(gn));
+    k_export_grid<<<nblk(gn), TPB, 0, s->stream>>>(gn, s->g_stride, s->g_idx.p, s->g_v.p, (long long*)s->stage_u.p, s->stage.p);
+    HOT_LAUNCHED(s);
+    int rc = 0;
+    if (idx) rc = d2h(s, idx, (const long long*)s->stage_u.p, gn);
+    if (!rc && m) rc = d2h(s, m, s->g_m.p, gn);
+    if (!rc && v) rc = d2h(s, v, s->stage.p, 3 * gn);
+    return rc;
+}
+
+int hot_get_id2coord(hot_sim* s, int* coord)
+{
+    if (!s->p2g_done) return fail(s, "hot_get_id2coord: call hot_p2g first");
+    const int n = s->num_nodes;
+    if (n == 0) return 0;
+    HOT_CUDA(s->stage_i.reserve(3 * (size_t)n));
+    k_id2coord<<<nblk(n), TPB, 0, s->stream>>>(n, s->dof_slot.p, s->page_id.p, s->stage_i.p);
+    HOT_LAUNCHED(s);
+    return d2h(s, coord, s->stage_i.p, 3 * (size_t)n);
+}
+
+int hot_get_mass_matrix(hot_sim* s, double* mass)
+{
+    if (!s->p2g_done) return fail(s, "hot_get_mass_matrix: call hot_p2g first");
+    return d2h(s, mass, s->mass_matrix.p, s->num_nodes);
+}
+
+int hot_set_dv(hot_sim* s, const double* dv)
+{
+    if (!s->p2g_done) return fail(s, "hot_set_dv: call hot_p2g first");
+    HOT_CUDA(cudaMemcpyAsync(s->dv.p, dv, 3 * (size_t)s->num_nodes * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    return 0;
+}
+
+int hot_g2p(hot_sim* s, double dt, int* flags) { return g2p(s, dt, flags); }
+
+} // extern "C"

@@ -1,0 +1,200 @@
+// hot_b200 internal state shared by the .cu translation units (not part of the C ABI).
+//
+// HBM layout (all device memory, SURVEY 8a rows a2/a3 re-designed for the GPU):
+//  * particles: component-major SoA in SORTED order (key order of a5), so that a page group is one
+//    contiguous run in every attribute array and CTA loads are fully coalesced.  `orig_id[s]` maps
+//    a sorted slot back to the reference's original particle index (== particle_order).
+//  * grid: the SPGrid virtual-memory trick (mmap of 4096^3 x 128 B, SPGrid_Allocator_Base.h:35-41) is
+//    replaced by a compact page table: pages are stored in the reference's first-Set order
+//    (SPGrid_Page_Map.h:61-70), `slot*E + e` addresses node e (in-page memory order, z fastest) of
+//    page `slot`; the 128-byte AoS GridState record (MpmGrid.h:14-34, half of it dead padding) becomes
+//    separate channel arrays m / v[3] / idx.
+//  * solver vectors (dv, residual, x, b ...) are DOF-indexed "TVStack" arrays n_nodes x 3.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace hot {
+
+// ---- SPGrid geometry for GridState<double,3> (128 B record): data_bits 7, block 2x4x4 -------------
+// Lib/SPGrid/Core/SPGrid_Mask.h:31-52 evaluated for log2_struct=7, dim=3, log2_page=12.
+struct Geo {
+    static constexpr int data_bits = 7;
+    static constexpr int block_bits = 5;
+    static constexpr int xb = 1, yb = 2, zb = 2;
+    static constexpr int BX = 1 << xb, BY = 1 << yb, BZ = 1 << zb;
+    static constexpr int E = 1 << block_bits; // nodes per page
+    static constexpr int index_bits = 32 - block_bits; // MpmSimulationBase.cpp:1071
+    static constexpr uint64_t xmask = 0x9249249249249800ull;
+    static constexpr uint64_t ymask = 0x4924924924924600ull;
+    static constexpr uint64_t zmask = 0x2492492492492180ull;
+    // touched node tile of the particles of one page: (B+2) per axis
+    static constexpr int TX = BX + 2, TY = BY + 2, TZ = BZ + 2;
+    static constexpr int TILE = TX * TY * TZ;
+};
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // grow-only; contents are NOT preserved
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        release();
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void swap(DevBuf& o)
+    {
+        T* tp = p; p = o.p; o.p = tp;
+        size_t tc = cap; cap = o.cap; o.cap = tc;
+    }
+};
+
+// particle attribute set, component-major SoA (attribute a, component c at a[c*stride + s])
+struct ParticleSoA {
+    DevBuf<double> X, V, M, C, F, Fn, vol, mu, lam, gradV;
+    DevBuf<int> orig_id;
+    size_t stride = 0;
+    cudaError_t reserve(size_t n);
+    void swap(ParticleSoA& o);
+};
+
+struct Sim {
+    int device = 0;
+    cudaStream_t stream = 0;
+    std::string err;
+    long long launches = 0;
+
+    double dx = 1, apic_rpic_ratio = 1, cfl = 0.6;
+    double dt = 0, gravity[3] = {0, 0, 0};
+
+    // ---- particles
+    long N = 0;
+    ParticleSoA P, Palt; // current (sorted after a5) and the double buffer used by the reorder
+    bool sorted = false;
+
+    // ---- a5 outputs
+    DevBuf<uint64_t> keys, keys_alt; // particle_sorter (sorted keys live in `keys` after the sort)
+    DevBuf<int> perm, perm_alt;
+    DevBuf<int> group_first; // n_groups + 1 entries (last = N)
+    DevBuf<uint64_t> group_block; // block_offset (key >> 32)
+    DevBuf<int> group_slot; // page slot of each group's page
+    long n_groups = 0;
+    // page table
+    long n_pages = 0;
+    DevBuf<uint32_t> page_id; // page ids (offset >> 12) in first-Set order
+    DevBuf<uint32_t> pid_sorted; // the same ids ascending ...
+    DevBuf<int> slot_sorted; // ... and the slot of each
+    DevBuf<int> nbr8; // n_pages x 8: slot of page + (i,j,k) block, -1 if absent
+    // scratch
+    DevBuf<unsigned char> cub_tmp;
+    DevBuf<uint32_t> cand_key, cand_key_alt;
+    DevBuf<int> cand_val, cand_val_alt, head_flag, scratch_i;
+    DevBuf<int> dcount; // small device counters
+    int* hcount = nullptr; // pinned mirror
+
+    // ---- grid channels, n_pages*E entries
+    DevBuf<double> g_m, g_v; // g_v: 3 channels, channel-major
+    DevBuf<int> g_idx; // DOF id or -1
+    size_t g_stride = 0;
+    int num_nodes = 0;
+    DevBuf<int> dof_slot; // inverse of g_idx
+    bool p2g_done = false;
+
+    // ---- DOF vectors
+    DevBuf<double> dv, vn, mass_matrix;
+
+    DevBuf<int> flags; // g2p CFL flags
+};
+
+int fail(Sim* s, const std::string& msg);
+int cuda_fail(Sim* s, cudaError_t e, const char* what);
+
+#define HOT_CUDA(call)                                                 \
+    do {                                                               \
+        cudaError_t e__ = (call);                                      \
+        if (e__ != cudaSuccess) return cuda_fail(s, e__, #call);       \
+    } while (0)
+
+#define HOT_LAUNCHED(s)                                                \
+    do {                                                               \
+        (s)->launches++;                                               \
+        cudaError_t e__ = cudaGetLastError();                          \
+        if (e__ != cudaSuccess) return cuda_fail(s, e__, "kernel launch"); \
+    } while (0)
+
+// sort.cu
+int sort_and_activate(Sim* s);
+int number_nodes(Sim* s); // a7, after the P2G scatter
+// transfer.cu
+int p2g(Sim* s);
+int g2p(Sim* s, double dt, int* flags);
+
+// ---- device helpers ----------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// software pdep (the reference's non-HASWELL Bit_Spread, SPGrid_Utilities.h:77-343)
+__host__ __device__ inline uint64_t bit_spread(uint32_t v, uint64_t mask)
+{
+    uint64_t r = 0;
+    while (mask) {
+        uint64_t low = mask & (~mask + 1);
+        if (v & 1u) r |= low;
+        v >>= 1;
+        mask ^= low;
+    }
+    return r;
+}
+__host__ __device__ inline uint32_t bit_pack(uint64_t v, uint64_t mask)
+{
+    uint32_t r = 0;
+    int o = 0;
+    while (mask) {
+        uint64_t low = mask & (~mask + 1);
+        if (v & low) r |= 1u << o;
+        ++o;
+        mask ^= low;
+    }
+    return r;
+}
+// SPGrid_Mask.h:150-166
+__host__ __device__ inline uint64_t linear_offset(int i, int j, int k)
+{
+    return bit_spread((uint32_t)i, Geo::xmask) | bit_spread((uint32_t)j, Geo::ymask) | bit_spread((uint32_t)k, Geo::zmask);
+}
+// SPGrid_Mask.h:237-245
+__host__ __device__ inline uint64_t packed_add(uint64_t a, uint64_t b)
+{
+    const uint64_t w = ~(Geo::xmask | Geo::ymask | Geo::zmask);
+    uint64_t rx = ((a | ~Geo::xmask) + (b & Geo::xmask)) & Geo::xmask;
+    uint64_t ry = ((a | ~Geo::ymask) + (b & Geo::ymask)) & Geo::ymask;
+    uint64_t rz = ((a | ~Geo::zmask) + (b & Geo::zmask)) & Geo::zmask;
+    uint64_t rw = ((a | ~w) + (b & w)) & w;
+    return rx | ry | rz | rw;
+}
+// MathTools.h:15-25 + BSplines.h:16-20.  The product X*one_over_dx and the -0.5 are evaluated unfused
+// (IEEE round-to-nearest each) so that particle->cell indices are bit-exact against the CPU evaluation.
+__device__ inline int base_node_of(double X, double one_over_dx, double* x_index_space)
+{
+    double x = __dmul_rn(X, one_over_dx);
+    double y = __dadd_rn(x, -0.5);
+    int i = (int)y;
+    *x_index_space = x;
+    return i - (i > y);
+}
+#endif
+
+} // namespace hot

@@ -1,0 +1,377 @@
+// a5 + a7 on the device: particle keys, u64 radix sort, page groups, page activation in the reference's
+// first-Set order, neighbour-page table, DOF numbering.
+//
+// Reference: MpmSimulationBase::sortParticlesAndPolluteGrid (Lib/MPM/MpmSimulationBase.cpp:1066-1137),
+// SPGrid_Page_Map::Set_Page / Get_Blocks (Lib/SPGrid/Core/SPGrid_Page_Map.h:61-96),
+// MpmGrid::getNumNodes (Lib/MPM/MpmGrid.h:148-161).
+//
+// The reference's serial loops (group detection, Set_Page in particle order, getNumNodes scan) are
+// re-expressed as data-parallel primitives that reproduce the serial ORDER exactly:
+//   page list  = first occurrence order of the sequence  [P_g, P_g+n(0,0,0) .. P_g+n(1,1,1)]_g
+//              = stable sort by page id -> run heads (min position) -> sort heads by position;
+//   DOF ids    = exclusive scan of (m != 0) over (page list order x in-page element order).
+// Radix sort / scan / select come from CUB (CUDA toolkit headers); everything else is ours.
+#include "sim.h"
+#include <cub/cub.cuh>
+
+namespace hot {
+
+int fail(Sim* s, const std::string& msg)
+{
+    s->err = msg;
+    return -1;
+}
+int cuda_fail(Sim* s, cudaError_t e, const char* what)
+{
+    s->err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return -2;
+}
+
+cudaError_t ParticleSoA::reserve(size_t n)
+{
+    size_t st = (n + 31) & ~(size_t)31; // 256-byte aligned component rows
+    cudaError_t e;
+    if ((e = X.reserve(3 * st)) != cudaSuccess) return e;
+    if ((e = V.reserve(3 * st)) != cudaSuccess) return e;
+    if ((e = M.reserve(st)) != cudaSuccess) return e;
+    if ((e = C.reserve(9 * st)) != cudaSuccess) return e;
+    if ((e = F.reserve(9 * st)) != cudaSuccess) return e;
+    if ((e = vol.reserve(st)) != cudaSuccess) return e;
+    if ((e = mu.reserve(st)) != cudaSuccess) return e;
+    if ((e = lam.reserve(st)) != cudaSuccess) return e;
+    if ((e = orig_id.reserve(st)) != cudaSuccess) return e;
+    stride = st;
+    return cudaSuccess;
+}
+void ParticleSoA::swap(ParticleSoA& o)
+{
+    X.swap(o.X); V.swap(o.V); M.swap(o.M); C.swap(o.C); F.swap(o.F);
+    vol.swap(o.vol); mu.swap(o.mu); lam.swap(o.lam); orig_id.swap(o.orig_id);
+    size_t t = stride; stride = o.stride; o.stride = t;
+}
+
+namespace {
+
+constexpr int TPB = 256;
+inline int nblk(long n) { return (int)((n + TPB - 1) / TPB); }
+
+// MpmSimulationBase.cpp:1080-1085
+__global__ void k_make_keys(long n, const double* __restrict__ X, size_t stride, const int* __restrict__ orig_id,
+    double one_over_dx, uint64_t* __restrict__ keys, int* __restrict__ vals, int* __restrict__ bad)
+{
+    long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int b[3];
+    bool oob = false;
+    for (int d = 0; d < 3; ++d) {
+        double X_d = X[d * stride + s], xi;
+        b[d] = base_node_of(X_d, one_over_dx, &xi);
+        if (!(xi == xi) || !(fabs(xi) < 1e9) || b[d] < 0 || b[d] + 2 >= 4096) oob = true;
+    }
+    if (oob) {
+        atomicOr(bad, 1);
+        b[0] = b[1] = b[2] = 0;
+    }
+    uint64_t off = linear_offset(b[0], b[1], b[2]);
+    keys[s] = ((off >> Geo::data_bits) << Geo::index_bits) + (uint64_t)orig_id[s];
+    vals[s] = (int)s;
+}
+
+// permute the persistent particle attributes into sorted order
+__global__ void k_reorder(long n, const int* __restrict__ perm, size_t ss, size_t ds,
+    const double* __restrict__ sX, const double* __restrict__ sV, const double* __restrict__ sM, const double* __restrict__ sC,
+    const double* __restrict__ sF, const double* __restrict__ svol, const double* __restrict__ smu, const double* __restrict__ slam,
+    const int* __restrict__ sid,
+    double* __restrict__ dX, double* __restrict__ dV, double* __restrict__ dM, double* __restrict__ dC, double* __restrict__ dF,
+    double* __restrict__ dvol, double* __restrict__ dmu, double* __restrict__ dlam, int* __restrict__ did)
+{
+    long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    long p = perm[s];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        dX[c * ds + s] = sX[c * ss + p];
+        dV[c * ds + s] = sV[c * ss + p];
+    }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        dC[c * ds + s] = sC[c * ss + p];
+        dF[c * ds + s] = sF[c * ss + p];
+    }
+    dM[s] = sM[p];
+    dvol[s] = svol[p];
+    dmu[s] = smu[p];
+    dlam[s] = slam[p];
+    did[s] = sid[p];
+}
+
+__global__ void k_group_flags(long n, const uint64_t* __restrict__ keys, int* __restrict__ flag)
+{
+    long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    flag[s] = (s == 0) || ((keys[s] >> 32) != (keys[s - 1] >> 32));
+}
+
+// per group: block_offset and the 8 page candidates of MpmSimulationBase.cpp:1104-1124.
+// Position t = 8*g + (i*4 + j*2 + k) reproduces the serial Set_Page order (Set_Page(P) itself == q 0).
+__global__ void k_group_pages(long n_groups, long n, const uint64_t* __restrict__ keys, int* __restrict__ group_first,
+    uint64_t* __restrict__ group_block, uint32_t* __restrict__ cand_key, int* __restrict__ cand_val)
+{
+    long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_groups) return;
+    if (g == n_groups) {
+        group_first[g] = (int)n;
+        return;
+    }
+    uint64_t key = keys[group_first[g]];
+    group_block[g] = key >> 32;
+    uint64_t off = (key >> 32) << 12;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        uint64_t nb = linear_offset(Geo::BX * (q >> 2), Geo::BY * ((q >> 1) & 1), Geo::BZ * (q & 1));
+        cand_key[g * 8 + q] = (uint32_t)(packed_add(off, nb) >> 12);
+        cand_val[g * 8 + q] = (int)(g * 8 + q);
+    }
+}
+
+__global__ void k_head_flags(long n, const uint32_t* __restrict__ k, int* __restrict__ flag)
+{
+    long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    flag[s] = (s == 0) || (k[s] != k[s - 1]);
+}
+
+__global__ void k_iota(long n, int* __restrict__ v)
+{
+    long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) v[s] = (int)s;
+}
+
+// order[slot] = index j into the ascending page id list
+__global__ void k_finish_pages(long n_pages, const int* __restrict__ order, const uint32_t* __restrict__ pid_sorted,
+    uint32_t* __restrict__ page_id, int* __restrict__ slot_sorted)
+{
+    long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_pages) return;
+    int j = order[slot];
+    page_id[slot] = pid_sorted[j];
+    slot_sorted[j] = (int)slot;
+}
+
+__device__ inline int find_slot(uint32_t pid, long n_pages, const uint32_t* __restrict__ pid_sorted, const int* __restrict__ slot_sorted)
+{
+    long lo = 0, hi = n_pages;
+    while (lo < hi) {
+        long mid = (lo + hi) >> 1;
+        if (pid_sorted[mid] < pid) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < n_pages && pid_sorted[lo] == pid) ? slot_sorted[lo] : -1;
+}
+
+__global__ void k_neighbours(long n_pages, const uint32_t* __restrict__ page_id, const uint32_t* __restrict__ pid_sorted,
+    const int* __restrict__ slot_sorted, int* __restrict__ nbr8)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pages * 8) return;
+    long slot = t >> 3;
+    int q = (int)(t & 7);
+    uint64_t off = (uint64_t)page_id[slot] << 12;
+    uint64_t nb = linear_offset(Geo::BX * (q >> 2), Geo::BY * ((q >> 1) & 1), Geo::BZ * (q & 1));
+    uint64_t sum = packed_add(off, nb);
+    // a neighbour that wrapped around the 4096^3 box is not a neighbour
+    bool wrapped = (q & 4 && bit_pack(off, Geo::xmask) + Geo::BX >= 4096u) || (q & 2 && bit_pack(off, Geo::ymask) + Geo::BY >= 4096u)
+        || (q & 1 && bit_pack(off, Geo::zmask) + Geo::BZ >= 4096u);
+    nbr8[t] = wrapped ? -1 : find_slot((uint32_t)(sum >> 12), n_pages, pid_sorted, slot_sorted);
+}
+
+__global__ void k_group_slots(long n_groups, const uint64_t* __restrict__ group_block, long n_pages,
+    const uint32_t* __restrict__ pid_sorted, const int* __restrict__ slot_sorted, int* __restrict__ group_slot)
+{
+    long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    group_slot[g] = find_slot((uint32_t)group_block[g], n_pages, pid_sorted, slot_sorted);
+}
+
+__global__ void k_mass_flags(long n, const double* __restrict__ m, int* __restrict__ flag)
+{
+    long a = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < n) flag[a] = m[a] != 0.0;
+}
+
+// MpmGrid.h:148-161 (idx), MpmSimulationBase.cpp:523-531 (v /= m), :817-826 (mass_matrix)
+__global__ void k_number_and_normalise(long n, size_t gs, const int* __restrict__ scan, double* __restrict__ m, double* __restrict__ v,
+    int* __restrict__ idx, int* __restrict__ dof_slot, double* __restrict__ mass_matrix, double* __restrict__ vn)
+{
+    long a = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    double mm = m[a];
+    if (mm != 0.0) {
+        int id = scan[a];
+        idx[a] = id;
+        dof_slot[id] = (int)a;
+        mass_matrix[id] = mm;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double q = v[d * gs + a] / mm;
+            v[d * gs + a] = q;
+            vn[3 * (size_t)id + d] = q;
+        }
+    }
+    else {
+        idx[a] = -1;
+    }
+}
+
+template <class F>
+int with_tmp(Sim* s, F f)
+{
+    size_t bytes = 0;
+    cudaError_t e = f((void*)nullptr, bytes);
+    if (e != cudaSuccess) return cuda_fail(s, e, "cub size query");
+    e = s->cub_tmp.reserve(bytes + 16);
+    if (e != cudaSuccess) return cuda_fail(s, e, "cub temp alloc");
+    e = f((void*)s->cub_tmp.p, bytes);
+    if (e != cudaSuccess) return cuda_fail(s, e, "cub run");
+    s->launches += 1; // CUB launches several kernels per call; counted once (conservative)
+    return 0;
+}
+
+} // namespace
+
+int sort_and_activate(Sim* s)
+{
+    const long n = s->N;
+    cudaStream_t st = s->stream;
+    if (n <= 0) return fail(s, "no particles");
+    if (n >= (1l << Geo::index_bits)) return fail(s, "particle count must be < 2^index_bits (MpmSimulationBase.cpp:1072)");
+    HOT_CUDA(s->keys.reserve(n));
+    HOT_CUDA(s->keys_alt.reserve(n));
+    HOT_CUDA(s->perm.reserve(n));
+    HOT_CUDA(s->perm_alt.reserve(n));
+    HOT_CUDA(s->head_flag.reserve(n > 64 ? n : 64));
+    HOT_CUDA(s->group_first.reserve(n + 1));
+    HOT_CUDA(s->dcount.reserve(8));
+    HOT_CUDA(s->Palt.reserve(n));
+    if (!s->hcount) HOT_CUDA(cudaMallocHost((void**)&s->hcount, 8 * sizeof(int)));
+
+    HOT_CUDA(cudaMemsetAsync(s->dcount.p, 0, 8 * sizeof(int), st));
+    const double one_over_dx = 1.0 / s->dx;
+    k_make_keys<<<nblk(n), TPB, 0, st>>>(n, s->P.X.p, s->P.stride, s->P.orig_id.p, one_over_dx, s->keys_alt.p, s->perm_alt.p, s->dcount.p);
+    HOT_LAUNCHED(s);
+    int rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceRadixSort::SortPairs(t, b, s->keys_alt.p, s->keys.p, s->perm_alt.p, s->perm.p, (int)n, 0, 64, st);
+    });
+    if (rc) return rc;
+    k_reorder<<<nblk(n), TPB, 0, st>>>(n, s->perm.p, s->P.stride, s->Palt.stride, s->P.X.p, s->P.V.p, s->P.M.p, s->P.C.p, s->P.F.p,
+        s->P.vol.p, s->P.mu.p, s->P.lam.p, s->P.orig_id.p, s->Palt.X.p, s->Palt.V.p, s->Palt.M.p, s->Palt.C.p, s->Palt.F.p,
+        s->Palt.vol.p, s->Palt.mu.p, s->Palt.lam.p, s->Palt.orig_id.p);
+    HOT_LAUNCHED(s);
+    s->P.swap(s->Palt);
+
+    // page groups: maximal runs of equal key>>32 (MpmSimulationBase.cpp:1089-1097)
+    k_group_flags<<<nblk(n), TPB, 0, st>>>(n, s->keys.p, s->head_flag.p);
+    HOT_LAUNCHED(s);
+    rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<int>(0), s->head_flag.p, s->group_first.p, s->dcount.p + 1, (int)n, st);
+    });
+    if (rc) return rc;
+    HOT_CUDA(cudaMemcpyAsync(s->hcount, s->dcount.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    HOT_CUDA(cudaStreamSynchronize(st));
+    if (s->hcount[0]) return fail(s, "particle outside the 4096^3 SPGrid box or non-finite position (MpmGrid.h:109,127)");
+    const long G = s->hcount[1];
+    s->n_groups = G;
+
+    // page activation
+    HOT_CUDA(s->group_block.reserve(G));
+    HOT_CUDA(s->group_slot.reserve(G));
+    HOT_CUDA(s->cand_key.reserve(8 * G));
+    HOT_CUDA(s->cand_key_alt.reserve(8 * G));
+    HOT_CUDA(s->cand_val.reserve(8 * G));
+    HOT_CUDA(s->cand_val_alt.reserve(8 * G));
+    HOT_CUDA(s->scratch_i.reserve(8 * G));
+    HOT_CUDA(s->head_flag.reserve(8 * G));
+    k_group_pages<<<nblk(G + 1), TPB, 0, st>>>(G, n, s->keys.p, s->group_first.p, s->group_block.p, s->cand_key.p, s->cand_val.p);
+    HOT_LAUNCHED(s);
+    rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceRadixSort::SortPairs(t, b, s->cand_key.p, s->cand_key_alt.p, s->cand_val.p, s->cand_val_alt.p, (int)(8 * G), 0, 32, st);
+    });
+    if (rc) return rc;
+    k_head_flags<<<nblk(8 * G), TPB, 0, st>>>(8 * G, s->cand_key_alt.p, s->head_flag.p);
+    HOT_LAUNCHED(s);
+    // run heads: ascending page ids -> cand_key, their first position -> cand_val
+    rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceSelect::Flagged(t, b, s->cand_key_alt.p, s->head_flag.p, s->cand_key.p, s->dcount.p + 2, (int)(8 * G), st);
+    });
+    if (rc) return rc;
+    rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceSelect::Flagged(t, b, s->cand_val_alt.p, s->head_flag.p, s->cand_val.p, s->dcount.p + 2, (int)(8 * G), st);
+    });
+    if (rc) return rc;
+    HOT_CUDA(cudaMemcpyAsync(s->hcount + 2, s->dcount.p + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HOT_CUDA(cudaStreamSynchronize(st));
+    const long NP = s->hcount[2];
+    s->n_pages = NP;
+    HOT_CUDA(s->page_id.reserve(NP));
+    HOT_CUDA(s->pid_sorted.reserve(NP));
+    HOT_CUDA(s->slot_sorted.reserve(NP));
+    HOT_CUDA(s->nbr8.reserve(8 * NP));
+    HOT_CUDA(cudaMemcpyAsync(s->pid_sorted.p, s->cand_key.p, NP * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    // sort the heads by first position -> first-Set order
+    k_iota<<<nblk(NP), TPB, 0, st>>>(NP, s->scratch_i.p);
+    HOT_LAUNCHED(s);
+    rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceRadixSort::SortPairs(t, b, (const uint32_t*)s->cand_val.p, s->cand_key_alt.p, s->scratch_i.p, s->cand_val_alt.p, (int)NP, 0, 32, st);
+    });
+    if (rc) return rc;
+    k_finish_pages<<<nblk(NP), TPB, 0, st>>>(NP, s->cand_val_alt.p, s->pid_sorted.p, s->page_id.p, s->slot_sorted.p);
+    HOT_LAUNCHED(s);
+    k_neighbours<<<nblk(NP * 8), TPB, 0, st>>>(NP, s->page_id.p, s->pid_sorted.p, s->slot_sorted.p, s->nbr8.p);
+    HOT_LAUNCHED(s);
+    k_group_slots<<<nblk(G), TPB, 0, st>>>(G, s->group_block.p, NP, s->pid_sorted.p, s->slot_sorted.p, s->group_slot.p);
+    HOT_LAUNCHED(s);
+
+    // zero the pages, idx = -1 (MpmSimulationBase.cpp:1128-1136)
+    const size_t gn = (size_t)NP * Geo::E;
+    HOT_CUDA(s->g_m.reserve(gn));
+    HOT_CUDA(s->g_v.reserve(3 * gn));
+    HOT_CUDA(s->g_idx.reserve(gn));
+    HOT_CUDA(s->dof_slot.reserve(gn));
+    s->g_stride = gn;
+    HOT_CUDA(cudaMemsetAsync(s->g_m.p, 0, gn * sizeof(double), st));
+    HOT_CUDA(cudaMemsetAsync(s->g_v.p, 0, 3 * gn * sizeof(double), st));
+    HOT_CUDA(cudaMemsetAsync(s->g_idx.p, 0xff, gn * sizeof(int), st));
+    s->num_nodes = 0;
+    s->sorted = true;
+    s->p2g_done = false;
+    return 0;
+}
+
+int number_nodes(Sim* s)
+{
+    cudaStream_t st = s->stream;
+    const size_t gn = s->g_stride;
+    HOT_CUDA(s->head_flag.reserve(gn));
+    HOT_CUDA(s->scratch_i.reserve(gn));
+    HOT_CUDA(s->mass_matrix.reserve(gn));
+    HOT_CUDA(s->vn.reserve(3 * gn));
+    HOT_CUDA(s->dv.reserve(3 * gn));
+    k_mass_flags<<<nblk(gn), TPB, 0, st>>>(gn, s->g_m.p, s->head_flag.p);
+    HOT_LAUNCHED(s);
+    int rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceScan::ExclusiveSum(t, b, s->head_flag.p, s->scratch_i.p, (int)gn, st);
+    });
+    if (rc) return rc;
+    k_number_and_normalise<<<nblk(gn), TPB, 0, st>>>(gn, gn, s->scratch_i.p, s->g_m.p, s->g_v.p, s->g_idx.p, s->dof_slot.p,
+        s->mass_matrix.p, s->vn.p);
+    HOT_LAUNCHED(s);
+    // n_nodes = scan[last] + flag[last]
+    HOT_CUDA(cudaMemcpyAsync(s->hcount + 4, s->scratch_i.p + (gn - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    HOT_CUDA(cudaMemcpyAsync(s->hcount + 5, s->head_flag.p + (gn - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    HOT_CUDA(cudaStreamSynchronize(st));
+    s->num_nodes = s->hcount[4] + s->hcount[5];
+    HOT_CUDA(cudaMemsetAsync(s->dv.p, 0, 3 * (size_t)s->num_nodes * sizeof(double), st));
+    return 0;
+}
+
+} // namespace hot

@@ -1,0 +1,175 @@
+"""Host-side mirror of the reference's MpmSimulationBase operator surface for the hot path.
+
+Method names follow Lib/MPM/MpmSimulationBase.h:138-220 (sortParticlesAndPolluteGrid, particlesToGrid,
+gridToParticles ...) so that the parity tests read like calls into the reference.  All compute happens in
+libhot_b200.so on the GPU; numpy arrays are only the caller-owned host buffers of the C ABI.
+"""
+import ctypes as C
+import numpy as np
+
+from ._lib import load_library
+
+
+class HotError(RuntimeError):
+    """Raised where the reference throws std::runtime_error from ZIRAN_ASSERT (Lib/Ziran/CS/Util/Debug.h:19-42)."""
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class MpmSimulationB200:
+    ELEMENTS_PER_BLOCK = 32  # GridState<double,3>: 2x4x4 nodes per 4 KB page
+
+    def __init__(self, dx, apic_rpic_ratio=1.0, cfl=0.6, device=-1, stream=None):
+        self._lib = load_library()
+        self._h = self._lib.hot_create(float(dx), float(apic_rpic_ratio), float(cfl), int(device))
+        if not self._h:
+            raise HotError("hot_create failed: no usable CUDA device (hot_b200 has no CPU fallback)")
+        self.dx = float(dx)
+        if stream is not None:
+            self.set_stream(stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.hot_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HotError(self._lib.hot_last_error(self._h).decode())
+
+    # ---- plumbing
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._lib.hot_set_stream(self._h, C.c_void_p(int(cuda_stream_ptr))))
+
+    def synchronize(self):
+        self._check(self._lib.hot_synchronize(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.hot_launch_count(self._h))
+
+    # ---- SPGrid addressing
+    def linear_offset(self, ijk):
+        ijk = np.ascontiguousarray(ijk, dtype=np.int32).reshape(-1, 3)
+        out = np.empty(len(ijk), dtype=np.uint64)
+        self._check(self._lib.hot_linear_offset(self._h, len(ijk), ijk.ctypes.data_as(C.POINTER(C.c_int)),
+                                                out.ctypes.data_as(C.POINTER(C.c_ulonglong))))
+        return out
+
+    def linear_to_coord(self, off):
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        out = np.empty((len(off), 3), dtype=np.int32)
+        self._check(self._lib.hot_linear_to_coord(self._h, len(off), off.ctypes.data_as(C.POINTER(C.c_ulonglong)),
+                                                  out.ctypes.data_as(C.POINTER(C.c_int))))
+        return out
+
+    def packed_add(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = np.ascontiguousarray(b, dtype=np.uint64)
+        out = np.empty(len(a), dtype=np.uint64)
+        p = C.POINTER(C.c_ulonglong)
+        self._check(self._lib.hot_packed_add(self._h, len(a), a.ctypes.data_as(p), b.ctypes.data_as(p), out.ctypes.data_as(p)))
+        return out
+
+    # ---- particles
+    def set_particles(self, X, V, mass, C_, F, vol, mu, lam):
+        n = len(mass)
+        arrs = [_f64(X, (n, 3)), _f64(V, (n, 3)), _f64(mass, (n,)), _f64(C_, (n, 9)), _f64(F, (n, 9)), _f64(vol, (n,)),
+                _f64(mu, (n,)), _f64(lam, (n,))]
+        self._check(self._lib.hot_set_particles(self._h, n, *[_ptr(a) for a in arrs]))
+        self.N = n
+
+    def set_particles_ptr(self, n, ptrs):
+        """Raw-pointer variant for pinned host buffers (bench.py e2e leg)."""
+        self._check(self._lib.hot_set_particles(self._h, n, *[C.c_void_p(int(p)) for p in ptrs]))
+        self.N = n
+
+    def get_particles_ptr(self, ptrs):
+        self._check(self._lib.hot_get_particles(self._h, *[None if p is None else C.c_void_p(int(p)) for p in ptrs]))
+
+    def get_particles(self, gradV=True):
+        n = self.N
+        X = np.empty((n, 3)); V = np.empty((n, 3)); Cm = np.empty((n, 9)); F = np.empty((n, 9))
+        G = np.empty((n, 9)) if gradV else None
+        self._check(self._lib.hot_get_particles(self._h, _ptr(X), _ptr(V), _ptr(Cm), _ptr(F), _ptr(G)))
+        return dict(X=X, V=V, C=Cm, F=F, gradV=G)
+
+    # ---- a5
+    def sortParticlesAndPolluteGrid(self):
+        self._check(self._lib.hot_sort_and_activate(self._h))
+
+    @property
+    def num_groups(self):
+        return int(self._lib.hot_num_groups(self._h))
+
+    @property
+    def num_pages(self):
+        return int(self._lib.hot_num_pages(self._h))
+
+    def get_sort(self):
+        n = self.N
+        sorter = np.empty(n, dtype=np.uint64); order = np.empty(n, dtype=np.int32); base = np.empty(n, dtype=np.uint64)
+        self._check(self._lib.hot_get_sort(self._h, _ptr(sorter), _ptr(order), _ptr(base)))
+        return sorter, order, base
+
+    def get_groups(self):
+        g = self.num_groups
+        first = np.empty(g, dtype=np.int32); last = np.empty(g, dtype=np.int32); blk = np.empty(g, dtype=np.uint64)
+        self._check(self._lib.hot_get_groups(self._h, _ptr(first), _ptr(last), _ptr(blk)))
+        return first, last, blk
+
+    def get_pages(self):
+        out = np.empty(self.num_pages, dtype=np.uint64)
+        self._check(self._lib.hot_get_pages(self._h, _ptr(out)))
+        return out
+
+    # ---- a6 / a7
+    def particlesToGrid(self):
+        n = C.c_int(0)
+        self._check(self._lib.hot_p2g(self._h, C.byref(n)))
+        return n.value
+
+    @property
+    def num_nodes(self):
+        return int(self._lib.hot_num_nodes(self._h))
+
+    def get_grid(self):
+        gn = self.num_pages * self.ELEMENTS_PER_BLOCK
+        idx = np.empty(gn, dtype=np.int64); m = np.empty(gn); v = np.empty((gn, 3))
+        self._check(self._lib.hot_get_grid(self._h, _ptr(idx), _ptr(m), _ptr(v)))
+        return idx, m, v
+
+    def get_id2coord(self):
+        out = np.empty((self.num_nodes, 3), dtype=np.int32)
+        self._check(self._lib.hot_get_id2coord(self._h, _ptr(out)))
+        return out
+
+    def buildMassMatrix(self):
+        out = np.empty(self.num_nodes)
+        self._check(self._lib.hot_get_mass_matrix(self._h, _ptr(out)))
+        return out
+
+    # ---- a23
+    def set_dv(self, dv):
+        dv = _f64(dv, (self.num_nodes, 3))
+        self._check(self._lib.hot_set_dv(self._h, _ptr(dv)))
+
+    def gridToParticles(self, dt, want_flags=True):
+        flags = (C.c_int * 2)(0, 0)
+        self._check(self._lib.hot_g2p(self._h, float(dt), flags if want_flags else None))
+        return (flags[0], flags[1])

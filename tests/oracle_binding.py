@@ -1,0 +1,154 @@
+"""ctypes binding of oracle/libhot_oracle.so — TEST INFRASTRUCTURE (the checker), never the product path."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_lib = C.CDLL(os.path.join(ROOT, "oracle", "libhot_oracle.so"))
+_lib.orc_create.restype = C.c_void_p
+_lib.orc_create.argtypes = [C.c_double, C.c_double, C.c_double]
+_lib.orc_last_error.restype = C.c_char_p
+for _n in ["orc_num_particles", "orc_num_groups", "orc_num_pages", "orc_activate"]:
+    getattr(_lib, _n).restype = C.c_long
+lib = _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _vp(h):
+    return C.c_void_p(h)
+
+
+def mask_info(fp32=False):
+    out = (C.c_int * 6)()
+    masks = (C.c_ulonglong * 3)()
+    _lib.orc_mask_info(int(fp32), out, masks)
+    return list(out), [int(m) for m in masks]
+
+
+def linear_offset(ijk, fp32=False):
+    ijk = np.ascontiguousarray(ijk, dtype=np.int32).reshape(-1, 3)
+    out = np.empty(len(ijk), dtype=np.uint64)
+    _lib.orc_linear_offset(int(fp32), C.c_long(len(ijk)), _p(ijk), _p(out))
+    return out
+
+
+def linear_to_coord(off, fp32=False):
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    out = np.empty((len(off), 3), dtype=np.int32)
+    _lib.orc_linear_to_coord(int(fp32), C.c_long(len(off)), _p(off), _p(out))
+    return out
+
+
+def packed_add(a, b, fp32=False):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    out = np.empty(len(a), dtype=np.uint64)
+    _lib.orc_packed_add(int(fp32), C.c_long(len(a)), _p(a), _p(b), _p(out))
+    return out
+
+
+def activate(group_offsets, fp32=False):
+    g = np.ascontiguousarray(group_offsets, dtype=np.uint64)
+    out = np.empty(9 * len(g) + 8, dtype=np.uint64)
+    n = _lib.orc_activate(int(fp32), C.c_long(len(g)), _p(g), _p(out), C.c_long(len(out)))
+    return out[:n].copy()
+
+
+class OracleSim:
+    """Same method names as hot_b200.MpmSimulationB200 so one harness drives both."""
+    ELEMENTS_PER_BLOCK = 32
+
+    def __init__(self, dx, apic_rpic_ratio=1.0, cfl=0.6):
+        self._h = _lib.orc_create(float(dx), float(apic_rpic_ratio), float(cfl))
+        self.dx = dx
+
+    def close(self):
+        if self._h:
+            _lib.orc_destroy(_vp(self._h))
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(_lib.orc_last_error(_vp(self._h)).decode())
+
+    def set_particles(self, X, V, mass, C_, F, vol, mu, lam):
+        n = len(mass)
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        arrs = [f(X), f(V), f(mass), f(C_), f(F), f(vol), f(mu), f(lam)]
+        self._check(_lib.orc_set_particles(_vp(self._h), C.c_long(n), *[_p(a) for a in arrs]))
+        self.N = n
+
+    def get_particles(self, gradV=True):
+        n = self.N
+        X = np.empty((n, 3)); V = np.empty((n, 3)); Cm = np.empty((n, 9)); F = np.empty((n, 9)); G = np.empty((n, 9))
+        self._check(_lib.orc_get_particles(_vp(self._h), _p(X), _p(V), _p(Cm), _p(F), _p(G)))
+        return dict(X=X, V=V, C=Cm, F=F, gradV=G)
+
+    def sortParticlesAndPolluteGrid(self):
+        self._check(_lib.orc_sort_and_activate(_vp(self._h)))
+
+    @property
+    def num_groups(self):
+        return int(_lib.orc_num_groups(_vp(self._h)))
+
+    @property
+    def num_pages(self):
+        return int(_lib.orc_num_pages(_vp(self._h)))
+
+    @property
+    def num_nodes(self):
+        return int(_lib.orc_num_nodes(_vp(self._h)))
+
+    def get_sort(self):
+        n = self.N
+        sorter = np.empty(n, dtype=np.uint64); order = np.empty(n, dtype=np.int32); base = np.empty(n, dtype=np.uint64)
+        self._check(_lib.orc_get_sort(_vp(self._h), _p(sorter), _p(order), _p(base)))
+        return sorter, order, base
+
+    def get_groups(self):
+        g = self.num_groups
+        first = np.empty(g, dtype=np.int32); last = np.empty(g, dtype=np.int32); blk = np.empty(g, dtype=np.uint64)
+        self._check(_lib.orc_get_groups(_vp(self._h), _p(first), _p(last), _p(blk)))
+        return first, last, blk
+
+    def get_pages(self):
+        out = np.empty(self.num_pages, dtype=np.uint64)
+        self._check(_lib.orc_get_pages(_vp(self._h), _p(out)))
+        return out
+
+    def particlesToGrid(self):
+        n = C.c_int(0)
+        self._check(_lib.orc_p2g(_vp(self._h), C.byref(n)))
+        return n.value
+
+    def get_grid(self):
+        gn = self.num_pages * self.ELEMENTS_PER_BLOCK
+        idx = np.empty(gn, dtype=np.int64); m = np.empty(gn); v = np.empty((gn, 3))
+        self._check(_lib.orc_get_grid(_vp(self._h), _p(idx), _p(m), _p(v)))
+        return idx, m, v
+
+    def get_id2coord(self):
+        out = np.empty((self.num_nodes, 3), dtype=np.int32)
+        self._check(_lib.orc_get_id2coord(_vp(self._h), _p(out)))
+        return out
+
+    def buildMassMatrix(self):
+        out = np.empty(self.num_nodes)
+        self._check(_lib.orc_get_mass_matrix(_vp(self._h), _p(out)))
+        return out
+
+    def set_dv(self, dv):
+        dv = np.ascontiguousarray(dv, dtype=np.float64)
+        self._check(_lib.orc_set_dv(_vp(self._h), _p(dv)))
+
+    def gridToParticles(self, dt, want_flags=True):
+        flags = (C.c_int * 2)(0, 0)
+        self._check(_lib.orc_g2p(_vp(self._h), C.c_double(dt), flags))
+        return (flags[0], flags[1])
