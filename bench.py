@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json metric: Mparticles/s for P2G+G2P).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c4]
+
+A step = one pass of the transfer hot path over the workload: hot_p2g (APIC scatter + DOF numbering + mass
+normalisation, a6+a7) followed by hot_g2p (gather + X/V/C/gradV write + F update, a23), particle state resident
+in HBM, exactly the `Mparticles/s = N_p / (t_P2G + t_G2P)` definition of BASELINE.md (the particle sort a5 is
+timed separately and reported as `sort_ms`).  G2P runs with dt = 0 inside the timed loop so that the particle
+order stays valid between steps (same reads, writes and arithmetic as any other dt); the e2e leg runs the whole
+public-API sequence with host buffers and a real dt:  set_particles (H2D) -> sort -> P2G -> G2P -> get_particles (D2H).
+
+L2 is flushed (256 MiB memset) before every timed step; every step is timed with CUDA events on the stream the
+kernels are launched on; multi-rank results take the max over ranks.
+`--impl reference` times the CPU path (the OpenMP oracle that restates the reference's TBB schedule; the
+reference itself cannot be built in this image) on the host cores with the same metric.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mparticles/s P2G+G2P"
+UNIT = "Mparticles/s"
+
+
+def make_workload(name, rank=0):
+    from hot_b200 import scenes
+    sc = {"c1": scenes.config_c1, "c2": scenes.config_c2, "c4": scenes.config_c4}[name](seed=rank)
+    desc = {"c1": "C1 box drop 18^3 cells ppc 8 (46 656 particles)",
+            "c2": "C2 twisting-bar block 22x165x22 cells ppc 12 (958 320 particles, 256^3-class SPGrid)",
+            "c4": "C4 column 100x400x25 cells ppc 8 (8.0 M particles, 512^3-class SPGrid)"}[name]
+    return sc, desc
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+        self.active = False
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            while not self.stop_flag:
+                if self.active:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
+                time.sleep(0.005)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def result(self):
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline(sc, reps, warmup=1):
+    """The CPU path (oracle, OpenMP over all host cores) on the same workload: P2G + G2P(dt=0) per step."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as orc
+    o = orc.OracleSim(sc["dx"])
+    o.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
+    t0 = time.perf_counter()
+    o.sortParticlesAndPolluteGrid()
+    t_sort = time.perf_counter() - t0
+    times = []
+    for it in range(warmup + reps):
+        t0 = time.perf_counter()
+        o.particlesToGrid()
+        o.gridToParticles(0.0)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    n = o.N
+    cores = int(orc.lib.orc_num_threads())
+    o.close()
+    return n, times, cores, t_sort
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sc, desc = make_workload(args.workload)
+    n, times, cores, t_sort = cpu_baseline(sc, args.steps, args.warmup)
+    ms = 1e3 * float(np.mean(times))
+    val = n / (ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"whole workload, {args.steps} steps of P2G+G2P (OpenMP restatement of the reference's 8-colour TBB schedule; sort {1e3 * t_sort:.1f} ms untimed)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import hot_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    # weak scaling: every rank owns an independent object of the named shape (the path shards by objects/pages
+    # with no data-path collective; ghost exchange between page partitions of ONE object is a later row of 8e)
+    sc, desc = make_workload(args.workload, rank)
+    n = len(sc["mass"])
+    stream = torch.cuda.current_stream()
+    sim = hot_b200.MpmSimulationB200(sc["dx"], device=local, stream=stream.cuda_stream)
+    sim.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
+    sim.sortParticlesAndPolluteGrid()
+    n_nodes = sim.particlesToGrid()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-resident leg -------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        flush.zero_()
+        sim.particlesToGrid(); sim.gridToParticles(0.0, want_flags=False)
+    sampler = ClockSampler(local); sampler.start()
+    sim.timing(2)
+    l0 = sim.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    sampler.active = True
+    wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()
+        a.record(stream)
+        sim.particlesToGrid(); sim.gridToParticles(0.0, want_flags=False)
+        b.record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    sampler.active = False
+    launches = sim.launch_count - l0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(np.sum(step_ms))
+    kt = sim.get_timings()
+    sim.timing(0)
+
+    # ---- end-to-end leg: host buffers through the public API ------------------------------------------
+    host_in = [torch.from_numpy(np.ascontiguousarray(sc[k])).pin_memory() for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam")]
+    host_out = [torch.empty((n, c), dtype=torch.float64).pin_memory() for c in (3, 3, 9, 9)]
+    h2d = sum(t.numel() * 8 for t in host_in)
+    d2h = sum(t.numel() * 8 for t in host_out)
+    dt = 1e-4
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        sim.set_particles_ptr(n, [t.data_ptr() for t in host_in])
+        sim.sortParticlesAndPolluteGrid()
+        sim.particlesToGrid()
+        sim.gridToParticles(dt, want_flags=False)
+        sim.get_particles_ptr([t.data_ptr() for t in host_out] + [None])
+
+    e2e_step()
+    barrier()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    eb.record(stream)
+    barrier()
+    e2e_ms = ea.elapsed_time(eb) / e2e_steps
+    # sort alone (reported, not part of the metric)
+    sim.set_particles_ptr(n, [t.data_ptr() for t in host_in])
+    sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sa.record(stream); sim.sortParticlesAndPolluteGrid(); sb.record(stream)
+    torch.cuda.synchronize()
+    sort_ms = sa.elapsed_time(sb)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(n)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms, e2e_ms = [float(x) for x in t.tolist()]
+    n_total = float(cnt.item())
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = n_total / (ms_per_step * 1e-3) / 1e6
+        peak, peak_src = peaks()
+        # roofline of the dominant kernel; algorithmic bytes per SURVEY.md 8d (fp64)
+        alg = {"p2g": 128 * n + 32 * n_nodes, "g2p": 288 * n + 24 * n_nodes}
+        per = {k: (kt[k][0] / kt[k][1]) for k in ("p2g", "g2p", "number_nodes") if k in kt}
+        dom = max(("p2g", "g2p"), key=lambda k: per.get(k, 0.0))
+        ach = alg[dom] / (per[dom] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src,
+                "per_kernel": {k: {"ms": per[k], "alg_GBps": (alg[k] / (per[k] * 1e-3) / 1e9 if k in alg else None),
+                                   "frac": (alg[k] / (per[k] * 1e-3) / 1e9 / peak if k in alg else None)} for k in per},
+                "combined_p2g_g2p": {"alg_bytes": alg["p2g"] + alg["g2p"], "frac": (alg["p2g"] + alg["g2p"]) / (ms_per_step * 1e-3) / 1e9 / peak}}
+        if args.cpu_reps > 0:
+            cn, ctimes, cores, _ = cpu_baseline(sc, args.cpu_reps)
+            cms = float(np.mean(ctimes))
+            cpu = {"value": cn / cms / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"whole workload ({cn} particles), {args.cpu_reps} timed P2G+G2P steps of the OpenMP oracle after 1 warm-up"}
+        else:
+            cpu = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": desc, "particles_per_gpu": n, "grid_nodes": n_nodes, "pages": sim.num_pages,
+                       "l2": "flushed before every timed step (256 MiB memset)",
+                       "parallelism": f"{world} independent objects (one per GPU), no data-path collective"},
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "includes": "H2D from pinned host, sort, P2G, G2P(dt), D2H of X,V,C,F"},
+            "gpu_launches": launches, "clocks": sampler.result(), "sort_ms": sort_ms, "wall_s_timed_loop": wall,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
+    ap.add_argument("--cpu-reps", type=int, default=5)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,9 @@ def load_library(path=LIB_PATH):
         "hot_set_stream": (C.c_int, [vp, vp]),
         "hot_synchronize": (C.c_int, [vp]),
         "hot_launch_count": (C.c_longlong, [vp]),
+        "hot_timing": (C.c_int, [vp, C.c_int]),
+        "hot_get_timings": (C.c_int, [vp, C.c_int, _c_double_p, _c_i64_p]),
+        "hot_timing_name": (C.c_char_p, [C.c_int]),
         "hot_linear_offset": (C.c_int, [vp, C.c_long, _c_int_p, _c_u64_p]),
         "hot_linear_to_coord": (C.c_int, [vp, C.c_long, _c_u64_p, _c_int_p]),
         "hot_packed_add": (C.c_int, [vp, C.c_long, _c_u64_p, _c_u64_p, _c_u64_p]),

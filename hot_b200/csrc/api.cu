@@ -154,6 +154,31 @@ int hot_synchronize(hot_sim* s)
 }
 long long hot_launch_count(hot_sim* s) { return s->launches; }
 
+int hot_timing(hot_sim* s, int enable)
+{
+    s->timers.collect();
+    s->timers.on = enable != 0;
+    if (enable == 2) // reset
+        for (int c = 0; c < KC_COUNT; ++c) s->timers.ms[c] = 0, s->timers.count[c] = 0;
+    return 0;
+}
+int hot_get_timings(hot_sim* s, int n, double* ms_total, long long* counts)
+{
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
+    s->timers.collect();
+    for (int c = 0; c < n && c < KC_COUNT; ++c) {
+        if (ms_total) ms_total[c] = s->timers.ms[c];
+        if (counts) counts[c] = s->timers.count[c];
+    }
+    return KC_COUNT;
+}
+const char* hot_timing_name(int c)
+{
+    static const char* names[KC_COUNT] = {"sort", "p2g", "number_nodes", "g2p", "gather", "stress", "force", "hessian_apply", "assemble",
+        "spmv", "gs_smooth", "transfer", "blas1"};
+    return (c >= 0 && c < KC_COUNT) ? names[c] : "";
+}
+
 static int mask_op(hot_sim* s, int op, long n, const int* ijk_in, const unsigned long long* a, const unsigned long long* b,
     unsigned long long* out, int* ijk_out)
 {

@@ -73,7 +73,39 @@ struct ParticleSoA {
     void swap(ParticleSoA& o);
 };
 
+// kernel classes of hot_get_timings (same order as HOT_K_* in include/hot_b200.h)
+enum KernelClass { KC_SORT = 0, KC_P2G, KC_NUMBER, KC_G2P, KC_GATHER, KC_STRESS, KC_FORCE, KC_HESSIAN, KC_ASSEMBLE, KC_SPMV, KC_GS,
+    KC_TRANSFER, KC_BLAS1, KC_COUNT };
+
+struct Sim;
+// CUDA-event timing of one kernel class on the handle's stream (enabled by hot_timing)
+struct KTimers {
+    bool on = false;
+    struct Pending { int c; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> pool;
+    double ms[KC_COUNT] = {0};
+    long long count[KC_COUNT] = {0};
+    cudaEvent_t get()
+    {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void collect()
+    {
+        for (auto& p : pending) {
+            cudaEventSynchronize(p.b);
+            float t = 0; cudaEventElapsedTime(&t, p.a, p.b);
+            ms[p.c] += t; count[p.c]++;
+            pool.push_back(p.a); pool.push_back(p.b);
+        }
+        pending.clear();
+    }
+    ~KTimers() { collect(); for (auto e : pool) cudaEventDestroy(e); }
+};
+
 struct Sim {
+    KTimers timers;
     int device = 0;
     cudaStream_t stream = 0;
     std::string err;
@@ -93,6 +125,7 @@ struct Sim {
     DevBuf<int> group_first; // n_groups + 1 entries (last = N)
     DevBuf<uint64_t> group_block; // block_offset (key >> 32)
     DevBuf<int> group_slot; // page slot of each group's page
+    DevBuf<int> cell_start; // n_groups x (E+1): first sorted particle of every cell of the group's page
     long n_groups = 0;
     // page table
     long n_pages = 0;
@@ -136,6 +169,18 @@ int cuda_fail(Sim* s, cudaError_t e, const char* what);
         cudaError_t e__ = cudaGetLastError();                          \
         if (e__ != cudaSuccess) return cuda_fail(s, e__, "kernel launch"); \
     } while (0)
+
+struct KTime { // RAII: times everything launched on s->stream in its scope under class c
+    Sim* s; cudaEvent_t a = nullptr; int c;
+    KTime(Sim* s_, int c_) : s(s_), c(c_)
+    {
+        if (s->timers.on) { a = s->timers.get(); cudaEventRecord(a, s->stream); }
+    }
+    ~KTime()
+    {
+        if (a) { cudaEvent_t b = s->timers.get(); cudaEventRecord(b, s->stream); s->timers.pending.push_back({c, a, b}); }
+    }
+};
 
 // sort.cu
 int sort_and_activate(Sim* s);

@@ -193,6 +193,24 @@ __global__ void k_group_slots(long n_groups, const uint64_t* __restrict__ group_
     group_slot[g] = find_slot((uint32_t)group_block[g], n_pages, pid_sorted, slot_sorted);
 }
 
+// first sorted particle of every in-page cell of a group (lower bound on key >> index_bits)
+__global__ void k_cell_start(long n_groups, const int* __restrict__ group_first, const uint64_t* __restrict__ group_block,
+    const uint64_t* __restrict__ keys, int* __restrict__ cell_start)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups * (Geo::E + 1)) return;
+    long g = t / (Geo::E + 1);
+    int c = (int)(t - g * (Geo::E + 1));
+    int lo = group_first[g], hi = group_first[g + 1];
+    uint64_t want = (group_block[g] << Geo::block_bits) + (uint64_t)c; // page id . cell
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if ((keys[mid] >> Geo::index_bits) < want) lo = mid + 1;
+        else hi = mid;
+    }
+    cell_start[t] = lo;
+}
+
 __global__ void k_mass_flags(long n, const double* __restrict__ m, int* __restrict__ flag)
 {
     long a = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,6 +263,7 @@ int sort_and_activate(Sim* s)
     cudaStream_t st = s->stream;
     if (n <= 0) return fail(s, "no particles");
     if (n >= (1l << Geo::index_bits)) return fail(s, "particle count must be < 2^index_bits (MpmSimulationBase.cpp:1072)");
+    KTime timer(s, KC_SORT);
     HOT_CUDA(s->keys.reserve(n));
     HOT_CUDA(s->keys_alt.reserve(n));
     HOT_CUDA(s->perm.reserve(n));
@@ -329,6 +348,9 @@ int sort_and_activate(Sim* s)
     k_neighbours<<<nblk(NP * 8), TPB, 0, st>>>(NP, s->page_id.p, s->pid_sorted.p, s->slot_sorted.p, s->nbr8.p);
     HOT_LAUNCHED(s);
     k_group_slots<<<nblk(G), TPB, 0, st>>>(G, s->group_block.p, NP, s->pid_sorted.p, s->slot_sorted.p, s->group_slot.p);
+    HOT_LAUNCHED(s);
+    HOT_CUDA(s->cell_start.reserve((size_t)G * (Geo::E + 1)));
+    k_cell_start<<<nblk(G * (Geo::E + 1)), TPB, 0, st>>>(G, s->group_first.p, s->group_block.p, s->keys.p, s->cell_start.p);
     HOT_LAUNCHED(s);
 
     // zero the pages, idx = -1 (MpmSimulationBase.cpp:1128-1136)

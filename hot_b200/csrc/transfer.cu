@@ -19,180 +19,84 @@
 //      the lanes of a warp hit distinct nodes (a warp holds < 16 consecutive cells, i.e. distinct (cy,cz)),
 //      so plain read-modify-write + __syncwarp suffices;
 //   4. the warp tiles are summed and flushed with one fp64 RED per touched node and channel.
-#include "sim.h"
+#include "scatter.cuh"
 
 namespace hot {
 namespace {
 
 constexpr int E = Geo::E;
 constexpr int TILE = Geo::TILE;
-constexpr int P2G_THREADS = 3 * E; // one thread per (cell, x-plane)
-constexpr int P2G_WARPS = P2G_THREADS / 32;
-constexpr int CHUNK = 128; // particles staged per pass
-constexpr int REC = 28; // doubles per staged record
-static_assert(P2G_THREADS % 32 == 0, "whole warps");
 
-// quadratic B-spline weights of one axis exactly in the reference's operation order (BSplines.h:55-81)
-__device__ __forceinline__ void bspline_axis(double d0, double* w, double* dw)
-{
-    double z = 1.5 - d0;
-    w[0] = 0.5 * (z * z);
-    double d1 = d0 - 1.0;
-    w[1] = 0.75 - d1 * d1;
-    double d2 = 1.0 - d1;
-    double zz = 1.5 - d2;
-    w[2] = 0.5 * (zz * zz);
-    if (dw) {
-        dw[0] = -z;
-        dw[1] = -2.0 * d1;
-        dw[2] = zz;
-    }
-}
-
-// tile node -> grid array index (page neighbour q, in-page element e)
-__device__ __forceinline__ long tile_to_grid(int n, const int* __restrict__ nbr)
-{
-    int tz = n % Geo::TZ, ty = (n / Geo::TZ) % Geo::TY, tx = n / (Geo::TZ * Geo::TY);
-    int q = ((tx >= Geo::BX) << 2) | ((ty >= Geo::BY) << 1) | (tz >= Geo::BZ);
-    int e = (((tx & (Geo::BX - 1)) << Geo::yb | (ty & (Geo::BY - 1))) << Geo::zb) | (tz & (Geo::BZ - 1));
-    int slot = nbr[q];
-    return slot < 0 ? -1 : (long)slot * E + e;
-}
-
-__global__ void __launch_bounds__(P2G_THREADS) k_p2g(const int* __restrict__ group_first, const int* __restrict__ group_slot,
-    const int* __restrict__ nbr8, size_t ps, const double* __restrict__ X, const double* __restrict__ V, const double* __restrict__ M,
-    const double* __restrict__ C, double dx, double one_over_dx, size_t gs, double* __restrict__ g_m, double* __restrict__ g_v)
-{
-    __shared__ __align__(16) double rec[CHUNK * REC];
-    __shared__ double wtile[P2G_WARPS][4 * TILE];
-    __shared__ int s_cell[CHUNK];
-    __shared__ int cstart[E + 1];
-    __shared__ int s_nbr[8];
-
-    const int g = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int first = group_first[g], end = group_first[g + 1];
-    if (tid < 8) s_nbr[tid] = nbr8[(size_t)group_slot[g] * 8 + tid];
-    for (int a = tid; a < P2G_WARPS * 4 * TILE; a += P2G_THREADS) (&wtile[0][0])[a] = 0.0;
-
-    const int c = tid / 3, pl = tid - 3 * c; // cell (in-page element index) and x-plane of this thread
-    double acc[9][4];
-#pragma unroll
-    for (int a = 0; a < 9; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.0;
-
-    for (int cb = first; cb < end; cb += CHUNK) {
-        const int cn = min(CHUNK, end - cb);
-        __syncthreads(); // previous chunk fully consumed
-        // ---- stage: node-independent part of the transfer, one thread per particle
-        for (int p = tid; p < cn; p += P2G_THREADS) {
-            const size_t s = (size_t)cb + p;
-            double w[3][3], d0n[3];
-            int cell = 0;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                double Xd = X[d * ps + s], xi;
-                int b = base_node_of(Xd, one_over_dx, &xi);
-                bspline_axis(xi - (double)b, w[d], nullptr);
-                d0n[d] = (double)b * dx - Xd; // x_node(base) - x_p
-                int bits = d == 0 ? Geo::xb : (d == 1 ? Geo::yb : Geo::zb);
-                cell = (cell << bits) | (b & ((1 << bits) - 1));
-            }
-            s_cell[p] = cell;
-            const double m = M[s];
-            double mv[3], Cm[9];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) mv[d] = m * V[d * ps + s];
-#pragma unroll
-            for (int q = 0; q < 9; ++q) Cm[q] = m * C[q * ps + s];
-            double* r = rec + (size_t)p * REC;
-            r[0] = w[1][0]; r[1] = w[1][1]; r[2] = w[1][2];
-            r[3] = w[2][0]; r[4] = w[2][1]; r[5] = w[2][2];
-            r[6] = Cm[3]; r[7] = Cm[4]; r[8] = Cm[5]; // column 1 of m*C
-            r[9] = Cm[6]; r[10] = Cm[7]; r[11] = Cm[8]; // column 2
-            r[12] = d0n[1]; r[13] = d0n[2];
-            r[14] = m; r[15] = 0.0;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                double dxi = (double)i * dx + d0n[0];
-                r[16 + 4 * i] = w[0][i];
-                r[17 + 4 * i] = mv[0] + Cm[0] * dxi;
-                r[18 + 4 * i] = mv[1] + Cm[1] * dxi;
-                r[19 + 4 * i] = mv[2] + Cm[2] * dxi;
-            }
-        }
-        __syncthreads();
-        // ---- cell boundaries inside the chunk (particles of a group are ordered by cell)
-        for (int p = tid; p < cn; p += P2G_THREADS) {
-            int e = s_cell[p], ep = p > 0 ? s_cell[p - 1] : -1;
-            for (int q = ep + 1; q <= e; ++q) cstart[q] = p;
-            if (p == cn - 1)
-                for (int q = e + 1; q <= E; ++q) cstart[q] = cn;
-        }
-        __syncthreads();
-        // ---- accumulate: thread (c, pl) over the particles of cell c
-        const int pb = cstart[c], pe = cstart[c + 1];
-        for (int p = pb; p < pe; ++p) {
-            const double2* r2 = reinterpret_cast<const double2*>(rec + (size_t)p * REC);
-            double2 a0 = r2[0], a1 = r2[1], a2 = r2[2], a3 = r2[3], a4 = r2[4], a5 = r2[5], a6 = r2[6], a7 = r2[7];
-            double2 b0 = r2[8 + 2 * pl], b1 = r2[9 + 2 * pl];
-            const double wy[3] = {a0.x, a0.y, a1.x}, wz[3] = {a1.y, a2.x, a2.y};
-            const double c1[3] = {a3.x, a3.y, a4.x}, c2[3] = {a4.y, a5.x, a5.y};
-            const double dy0 = a6.x, dz0 = a6.y, m = a7.x;
-            const double wi = b0.x, ai[3] = {b0.y, b1.x, b1.y};
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const double dyj = (double)j * dx + dy0;
-                const double wij = wi * wy[j];
-                const double bj[3] = {ai[0] + c1[0] * dyj, ai[1] + c1[1] * dyj, ai[2] + c1[2] * dyj};
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const double dzk = (double)k * dx + dz0;
-                    const double w = wij * wz[k];
-                    acc[j * 3 + k][0] += w * m;
-                    acc[j * 3 + k][1] += w * (bj[0] + c2[0] * dzk);
-                    acc[j * 3 + k][2] += w * (bj[1] + c2[1] * dzk);
-                    acc[j * 3 + k][3] += w * (bj[2] + c2[2] * dzk);
-                }
-            }
-        }
-    }
-    // ---- per-warp tile accumulation, conflict-free per (j,k) step
+// a6: g.m += w m_p ; g.v += w (m_p C_p (x_i - x_p) + m_p v_p)   (MpmSimulationBase.cpp:636-652)
+struct P2GPolicy {
+    static constexpr int NCH = 4, REC = 28, GATHER = 0;
+    struct Args {
+        size_t ps;
+        const double *X, *V, *M, *C;
+        double dx, one_over_dx;
+        size_t gs;
+        double *g_m, *g_v;
+    };
+    __device__ static void gather_node(const Args&, long, double (&)[3]) {}
+    __device__ static void stage(const Args& a, size_t s, double* r, const double*)
     {
-        const int cz = c & (Geo::BZ - 1), cy = (c >> Geo::zb) & (Geo::BY - 1), cx = c >> (Geo::zb + Geo::yb);
-        double* wt = wtile[tid >> 5];
-        __syncthreads(); // tiles zeroed
+        SplineEval sp;
+        sp.eval(a.X, a.ps, s, a.dx, a.one_over_dx, false);
+        const double m = a.M[s];
+        double mv[3], Cm[9];
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
+        for (int d = 0; d < 3; ++d) mv[d] = m * a.V[d * a.ps + s];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) Cm[q] = m * a.C[q * a.ps + s];
+        r[0] = sp.w[1][0]; r[1] = sp.w[1][1]; r[2] = sp.w[1][2];
+        r[3] = sp.w[2][0]; r[4] = sp.w[2][1]; r[5] = sp.w[2][2];
+        r[6] = Cm[3]; r[7] = Cm[4]; r[8] = Cm[5]; // column 1 of m*C
+        r[9] = Cm[6]; r[10] = Cm[7]; r[11] = Cm[8]; // column 2
+        r[12] = sp.d0n[1]; r[13] = sp.d0n[2];
+        r[14] = m; r[15] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double dxi = (double)i * a.dx + sp.d0n[0];
+            r[16 + 4 * i] = sp.w[0][i];
+            r[17 + 4 * i] = mv[0] + Cm[0] * dxi;
+            r[18 + 4 * i] = mv[1] + Cm[1] * dxi;
+            r[19 + 4 * i] = mv[2] + Cm[2] * dxi;
+        }
+    }
+    __device__ __forceinline__ static void accumulate(const Args& a, const double* rec, int pl, double (&acc)[9][4])
+    {
+        const double2* r2 = reinterpret_cast<const double2*>(rec);
+        double2 a0 = r2[0], a1 = r2[1], a2 = r2[2], a3 = r2[3], a4 = r2[4], a5 = r2[5], a6 = r2[6], a7 = r2[7];
+        double2 b0 = r2[8 + 2 * pl], b1 = r2[9 + 2 * pl];
+        const double wy[3] = {a0.x, a0.y, a1.x}, wz[3] = {a1.y, a2.x, a2.y};
+        const double c1[3] = {a3.x, a3.y, a4.x}, c2[3] = {a4.y, a5.x, a5.y};
+        const double dy0 = a6.x, dz0 = a6.y, m = a7.x;
+        const double wi = b0.x, ai[3] = {b0.y, b1.x, b1.y};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double dyj = (double)j * a.dx + dy0;
+            const double wij = wi * wy[j];
+            const double bj[3] = {ai[0] + c1[0] * dyj, ai[1] + c1[1] * dyj, ai[2] + c1[2] * dyj};
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const int n = ((cx + pl) * Geo::TY + (cy + j)) * Geo::TZ + (cz + k);
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) wt[ch * TILE + n] += acc[j * 3 + k][ch];
-                __syncwarp();
-            }
-    }
-    __syncthreads();
-    // ---- flush: one RED per touched node and channel
-    for (int n = tid; n < TILE; n += P2G_THREADS) {
-        double v[4];
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-            double sum = 0.0;
-#pragma unroll
-            for (int w = 0; w < P2G_WARPS; ++w) sum += wtile[w][ch * TILE + n];
-            v[ch] = sum;
-        }
-        if (v[0] != 0.0) {
-            long a = tile_to_grid(n, s_nbr);
-            if (a >= 0) {
-                atomicAdd(g_m + a, v[0]);
-                atomicAdd(g_v + a, v[1]);
-                atomicAdd(g_v + gs + a, v[2]);
-                atomicAdd(g_v + 2 * gs + a, v[3]);
+                const double dzk = (double)k * a.dx + dz0;
+                const double w = wij * wz[k];
+                acc[j * 3 + k][0] += w * m;
+                acc[j * 3 + k][1] += w * (bj[0] + c2[0] * dzk);
+                acc[j * 3 + k][2] += w * (bj[1] + c2[1] * dzk);
+                acc[j * 3 + k][3] += w * (bj[2] + c2[2] * dzk);
             }
         }
     }
-}
+    __device__ static void flush(const Args& a, long n, const double (&v)[4])
+    {
+        if (v[0] == 0.0) return;
+        atomicAdd(a.g_m + n, v[0]);
+        atomicAdd(a.g_v + n, v[1]);
+        atomicAdd(a.g_v + a.gs + n, v[2]);
+        atomicAdd(a.g_v + 2 * a.gs + n, v[3]);
+    }
+};
 
 constexpr int G2P_THREADS = 128;
 
@@ -306,10 +210,17 @@ int p2g(Sim* s)
     // the pages are re-zeroed so the call is repeatable (the reference zeroes them in the sort, :1128-1136)
     HOT_CUDA(cudaMemsetAsync(s->g_m.p, 0, gn * sizeof(double), st));
     HOT_CUDA(cudaMemsetAsync(s->g_v.p, 0, 3 * gn * sizeof(double), st));
-    k_p2g<<<(unsigned)s->n_groups, P2G_THREADS, 0, st>>>(s->group_first.p, s->group_slot.p, s->nbr8.p, s->P.stride, s->P.X.p, s->P.V.p,
-        s->P.M.p, s->P.C.p, s->dx, 1.0 / s->dx, gn, s->g_m.p, s->g_v.p);
-    HOT_LAUNCHED(s);
-    int rc = number_nodes(s);
+    {
+        KTime t(s, KC_P2G);
+        P2GPolicy::Args a{s->P.stride, s->P.X.p, s->P.V.p, s->P.M.p, s->P.C.p, s->dx, 1.0 / s->dx, gn, s->g_m.p, s->g_v.p};
+        k_plane_scatter<P2GPolicy><<<(unsigned)s->n_groups, SC_THREADS, 0, st>>>(a, s->cell_start.p, s->group_slot.p, s->nbr8.p);
+        HOT_LAUNCHED(s);
+    }
+    int rc;
+    {
+        KTime t(s, KC_NUMBER);
+        rc = number_nodes(s);
+    }
     if (rc) return rc;
     s->p2g_done = true;
     return 0;
@@ -322,10 +233,13 @@ int g2p(Sim* s, double dt, int* flags)
     HOT_CUDA(s->flags.reserve(2));
     HOT_CUDA(s->P.gradV.reserve(9 * s->P.stride));
     HOT_CUDA(cudaMemsetAsync(s->flags.p, 0, 2 * sizeof(int), st));
-    k_g2p<<<(unsigned)s->n_groups, G2P_THREADS, 0, st>>>(s->group_first.p, s->group_slot.p, s->nbr8.p, s->P.stride, s->P.X.p, s->P.V.p,
-        s->P.C.p, s->P.F.p, s->P.gradV.p, s->dx, 1.0 / s->dx, dt, s->apic_rpic_ratio, s->cfl, s->g_stride, s->g_v.p, s->g_idx.p,
-        s->dv.p, s->flags.p);
-    HOT_LAUNCHED(s);
+    {
+        KTime t(s, KC_G2P);
+        k_g2p<<<(unsigned)s->n_groups, G2P_THREADS, 0, st>>>(s->group_first.p, s->group_slot.p, s->nbr8.p, s->P.stride, s->P.X.p,
+            s->P.V.p, s->P.C.p, s->P.F.p, s->P.gradV.p, s->dx, 1.0 / s->dx, dt, s->apic_rpic_ratio, s->cfl, s->g_stride, s->g_v.p,
+            s->g_idx.p, s->dv.p, s->flags.p);
+        HOT_LAUNCHED(s);
+    }
     if (flags) {
         HOT_CUDA(cudaMemcpyAsync(s->hcount + 6, s->flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         HOT_CUDA(cudaStreamSynchronize(st));

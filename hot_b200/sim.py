@@ -63,6 +63,15 @@ class MpmSimulationB200:
     def launch_count(self):
         return int(self._lib.hot_launch_count(self._h))
 
+    def timing(self, enable=1):
+        self._check(self._lib.hot_timing(self._h, int(enable)))
+
+    def get_timings(self):
+        """{kernel class: (total ms, launches)} measured with CUDA events on the handle's stream"""
+        ms = (C.c_double * 64)(); cnt = (C.c_longlong * 64)()
+        k = self._lib.hot_get_timings(self._h, 64, ms, cnt)
+        return {self._lib.hot_timing_name(i).decode(): (ms[i], int(cnt[i])) for i in range(k) if cnt[i]}
+
     # ---- SPGrid addressing
     def linear_offset(self, ijk):
         ijk = np.ascontiguousarray(ijk, dtype=np.int32).reshape(-1, 3)

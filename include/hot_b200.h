@@ -37,6 +37,13 @@ int hot_synchronize(hot_sim* h);
 /* number of CUDA kernels this handle has launched so far (bench.py's gpu_launches) */
 long long hot_launch_count(hot_sim* h);
 
+/* Per-kernel-class CUDA-event timing on the handle's stream (replaces ZIRAN_TIMER / ScopedTimer,
+ * Lib/Ziran/CS/Util/Timer.h:34-58, and the per-level V-cycle table, MultigridPreconditioner.h:417-419).
+ * enable: 0 off, 1 on, 2 on + reset.  hot_get_timings synchronises, fills up to n classes, returns the class count. */
+int hot_timing(hot_sim* h, int enable);
+int hot_get_timings(hot_sim* h, int n, double* ms_total, long long* counts);
+const char* hot_timing_name(int kernel_class);
+
 /* ---- SPGrid addressing (Lib/SPGrid/Core/SPGrid_Mask.h) -- device evaluation, host buffers ---------- */
 /* Linear_Offset :150-166 */
 int hot_linear_offset(hot_sim* h, long n, const int* ijk, unsigned long long* out);

@@ -56,6 +56,8 @@ struct Sim {
 
     int num_nodes = 0;
     std::vector<double> dv, vn, mass_matrix;
+    void* force_state = nullptr; // oracle_force.inl
+    void* matrix_state = nullptr; // oracle_matrix.inl
 
     GridState* node_at(uint64_t offset)
     {
@@ -371,6 +373,12 @@ int orc_p2g(void* h, int* n_nodes)
     }
     s->dv.assign(3 * (size_t)total, 0.0);
     s->vn.assign(3 * (size_t)total, 0.0);
+    s->mass_matrix.assign(total, 0.0); // buildMassMatrix, MpmSimulationBase.cpp:817-826
+    for (auto& g : s->grid)
+        if (g.idx >= 0) {
+            s->mass_matrix[g.idx] = g.m;
+            for (int d = 0; d < 3; ++d) s->vn[3 * g.idx + d] = g.v[d];
+        }
     if (n_nodes) *n_nodes = total;
     return 0;
 }
@@ -495,3 +503,5 @@ int orc_g2p(void* h, double dt, int* flags)
 }
 
 } // extern "C"
+
+#include "oracle_force.inl"

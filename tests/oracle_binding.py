@@ -152,3 +152,84 @@ class OracleSim:
         flags = (C.c_int * 2)(0, 0)
         self._check(_lib.orc_g2p(_vp(self._h), C.c_double(dt), flags))
         return (flags[0], flags[1])
+
+
+# ---- force model (oracle_force.inl) ------------------------------------------------------------------------
+def constitutive(F, mu, lam, project=True, dF=None):
+    """single-particle CorotatedIsotropic evaluation: psi, P, dPdF (9x9, index i+3j), dP(dF), U, sigma, V"""
+    F = np.ascontiguousarray(np.asarray(F, dtype=np.float64).reshape(3, 3).T)  # -> column-major buffer
+    psi = C.c_double(0)
+    P = np.empty(9); H = np.empty(81); dP = np.empty(9); U = np.empty(9); sg = np.empty(3); V = np.empty(9)
+    dFb = None if dF is None else np.ascontiguousarray(np.asarray(dF, dtype=np.float64).reshape(3, 3).T)
+    _lib.orc_constitutive(_p(F), C.c_double(mu), C.c_double(lam), int(project), C.byref(psi), _p(P), _p(H), _p(dFb),
+                          _p(dP) if dF is not None else None, _p(U), _p(sg), _p(V))
+    cm = lambda a: a.reshape(3, 3).T.copy()
+    return dict(psi=psi.value, P=cm(P), dPdF=H.reshape(9, 9).T.copy(), dP=cm(dP) if dF is not None else None, U=cm(U), sigma=sg, V=cm(V))
+
+
+def _add_force_methods(cls):
+    def set_dt_gravity(self, dt, g):
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        self._check(_lib.orc_set_dt_gravity(_vp(self._h), C.c_double(dt), _p(g)))
+        self.dt = dt
+
+    def set_project(self, project):
+        self._check(_lib.orc_set_project(_vp(self._h), int(project)))
+
+    def set_bc(self, node_id, P=None, R=None, Rinv=None, slip=None, dv_bc=None, mode=0):
+        node_id = np.ascontiguousarray(node_id, dtype=np.int32)
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        P, R, Rinv, dv_bc = f(P), f(R), f(Rinv), f(dv_bc)
+        slip = None if slip is None else np.ascontiguousarray(slip, dtype=np.int32)
+        self._check(_lib.orc_set_bc(_vp(self._h), int(mode), len(node_id), _p(node_id), _p(P), _p(R), _p(Rinv), _p(slip), _p(dv_bc)))
+
+    def get_dv(self):
+        out = np.empty((self.num_nodes, 3))
+        self._check(_lib.orc_get_dv(_vp(self._h), _p(out)))
+        return out
+
+    def backupStrain(self):
+        self._check(_lib.orc_backup_strain(_vp(self._h)))
+
+    def restoreStrain(self):
+        self._check(_lib.orc_restore_strain(_vp(self._h)))
+
+    def updateState(self, dv=None):
+        e = C.c_double(0)
+        dvb = None if dv is None else np.ascontiguousarray(dv, dtype=np.float64)
+        self._check(_lib.orc_update_state(_vp(self._h), _p(dvb), C.byref(e)))
+        return e.value
+
+    def get_stress(self):
+        S = np.empty((self.N, 9)); F = np.empty((self.N, 9))
+        self._check(_lib.orc_get_stress(_vp(self._h), _p(S), _p(F)))
+        return S, F
+
+    def computeResidual(self):
+        r = np.empty((self.num_nodes, 3))
+        self._check(_lib.orc_compute_residual(_vp(self._h), _p(r)))
+        return r
+
+    def project(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64).copy()
+        self._check(_lib.orc_project(_vp(self._h), _p(v)))
+        return v
+
+    def multiply(self, x):
+        """matrix-free Hessian apply (ImplicitSolverObjective::multiply with --matfree)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        b = np.empty_like(x)
+        self._check(_lib.orc_hessian_apply_mf(_vp(self._h), _p(x), _p(b)))
+        return b
+
+    def evaluatePerNodeCNTolerance(self, eps, dt):
+        tol = np.empty(self.num_nodes)
+        self._check(_lib.orc_eval_cn_tolerance(_vp(self._h), C.c_double(eps), C.c_double(dt), _p(tol)))
+        return tol
+
+    for k, v in list(locals().items()):
+        if callable(v) and k != "cls":
+            setattr(cls, k, v)
+
+
+_add_force_methods(OracleSim)
