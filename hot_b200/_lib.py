@@ -67,6 +67,18 @@ def load_library(path=LIB_PATH):
         "hot_get_mass_matrix": (C.c_int, [vp, vp]),
         "hot_set_dv": (C.c_int, [vp, vp]),
         "hot_g2p": (C.c_int, [vp, C.c_double, _c_int_p]),
+        "hot_set_dt_gravity": (C.c_int, [vp, C.c_double, vp]),
+        "hot_set_project": (C.c_int, [vp, C.c_int]),
+        "hot_set_bc": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
+        "hot_get_dv": (C.c_int, [vp, vp]),
+        "hot_backup_strain": (C.c_int, [vp]),
+        "hot_restore_strain": (C.c_int, [vp]),
+        "hot_update_state": (C.c_int, [vp, vp, _c_double_p]),
+        "hot_get_stress": (C.c_int, [vp, vp, vp]),
+        "hot_compute_residual": (C.c_int, [vp, vp]),
+        "hot_project": (C.c_int, [vp, vp]),
+        "hot_hessian_apply_mf": (C.c_int, [vp, vp, vp]),
+        "hot_eval_cn_tolerance": (C.c_int, [vp, C.c_double, C.c_double, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -137,6 +137,7 @@ void hot_destroy(hot_sim* s)
 {
     if (!s) return;
     if (s->hcount) cudaFreeHost(s->hcount);
+    if (s->h_red) cudaFreeHost(s->h_red);
     delete s;
 }
 
@@ -357,5 +358,109 @@ int hot_set_dv(hot_sim* s, const double* dv)
 }
 
 int hot_g2p(hot_sim* s, double dt, int* flags) { return g2p(s, dt, flags); }
+
+// ---- force model (force.cu): host-buffer wrappers around the device-resident operators ---------------------------
+static int upload_dof(hot_sim* s, DevBuf<double>& buf, const double* host, size_t per_node = 3)
+{
+    const size_t n = per_node * (size_t)s->num_nodes;
+    HOT_CUDA(buf.reserve(n > 0 ? n : 1));
+    if (host && n) HOT_CUDA(cudaMemcpyAsync(buf.p, host, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    return 0;
+}
+
+int hot_set_dt_gravity(hot_sim* s, double dt, const double* g)
+{
+    if (!(dt >= 0)) return fail(s, "hot_set_dt_gravity: dt must be non-negative");
+    s->dt = dt;
+    for (int d = 0; d < 3; ++d) s->gravity[d] = g ? g[d] : 0.0;
+    s->state_valid = s->hessian_valid = false;
+    return 0;
+}
+int hot_set_project(hot_sim* s, int project)
+{
+    s->project_pd = project != 0;
+    s->hessian_valid = false;
+    return 0;
+}
+int hot_set_bc(hot_sim* s, int mode, int n_bc, const int* node_id, const double* P, const double* R, const double* Rinv, const int* slip,
+    const double* dv_bc)
+{
+    return set_bc(s, mode, n_bc, node_id, P, R, Rinv, slip, dv_bc);
+}
+int hot_get_dv(hot_sim* s, double* dv)
+{
+    if (!s->p2g_done) return fail(s, "hot_get_dv: call hot_p2g first");
+    return d2h(s, dv, s->dv.p, 3 * (size_t)s->num_nodes);
+}
+int hot_backup_strain(hot_sim* s) { return backup_strain(s); }
+int hot_restore_strain(hot_sim* s) { return restore_strain(s); }
+
+int hot_update_state(hot_sim* s, const double* dv, double* energy)
+{
+    if (!s->p2g_done) return fail(s, "hot_update_state: call hot_p2g first");
+    if (dv) HOT_CUDA(cudaMemcpyAsync(s->dv.p, dv, 3 * (size_t)s->num_nodes * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    return update_state(s, energy != nullptr, energy);
+}
+
+int hot_get_stress(hot_sim* s, double* vPFnT, double* F)
+{
+    if (!s->state_valid) return fail(s, "hot_get_stress: call hot_update_state first");
+    const long n = s->N;
+    HOT_CUDA(s->stage.reserve(28 * (size_t)n));
+    struct Item { double* h; const double* soa; };
+    Item items[] = {{vPFnT, s->f_stress.p}, {F, s->P.F.p}};
+    size_t off = 0;
+    for (const Item& it : items) {
+        if (!it.h) continue;
+        double* d = s->stage.p + off;
+        k_soa_to_aos<<<nblk(n * 9), TPB, 0, s->stream>>>(n, 9, it.soa, s->P.stride, s->P.orig_id.p, d);
+        HOT_LAUNCHED(s);
+        HOT_CUDA(cudaMemcpyAsync(it.h, d, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        off += (size_t)n * 9;
+    }
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int hot_compute_residual(hot_sim* s, double* r)
+{
+    int rc = upload_dof(s, s->work[1], nullptr);
+    if (rc) return rc;
+    rc = compute_residual(s, s->work[1].p);
+    if (rc) return rc;
+    return d2h(s, r, s->work[1].p, 3 * (size_t)s->num_nodes);
+}
+
+int hot_project(hot_sim* s, double* v)
+{
+    if (!s->p2g_done) return fail(s, "hot_project: call hot_p2g first");
+    int rc = upload_dof(s, s->work[1], v);
+    if (rc) return rc;
+    rc = bc_project(s, s->work[1].p);
+    if (rc) return rc;
+    return d2h(s, v, s->work[1].p, 3 * (size_t)s->num_nodes);
+}
+
+int hot_hessian_apply_mf(hot_sim* s, const double* x, double* b)
+{
+    if (!s->state_valid) return fail(s, "hot_hessian_apply_mf: call hot_update_state first");
+    int rc = upload_dof(s, s->work[1], x);
+    if (rc) return rc;
+    rc = upload_dof(s, s->work[2], nullptr);
+    if (rc) return rc;
+    rc = hessian_apply_mf(s, s->work[1].p, s->work[2].p);
+    if (rc) return rc;
+    return d2h(s, b, s->work[2].p, 3 * (size_t)s->num_nodes);
+}
+
+int hot_eval_cn_tolerance(hot_sim* s, double eps, double dt, double* tol)
+{
+    if (!s->p2g_done) return fail(s, "hot_eval_cn_tolerance: call hot_p2g first");
+    HOT_CUDA(s->cn_tol.reserve(s->num_nodes > 0 ? s->num_nodes : 1));
+    int rc = eval_cn_tolerance(s, eps, dt, s->cn_tol.p);
+    if (rc) return rc;
+    if (tol) return d2h(s, tol, s->cn_tol.p, (size_t)s->num_nodes);
+    return 0;
+}
 
 } // extern "C"

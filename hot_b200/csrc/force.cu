@@ -1,0 +1,619 @@
+// Elastic force model of the hot path on the device: a9 (grid -> particle gradient gather), a10 (F-based force helper),
+// a11 (fixed-corotated model), a12 (force rasterisation), a13 (matrix-free Hessian apply), a14 (residual / energy /
+// BC projection), a18-prep (per-node CN tolerance).
+//
+// Reference: MpmForceBase::{evalInterpolantAndGradient, rasterizeForceToTVStack, addScaledForceDifferential,
+// updatePositionBasedState} (Lib/MPM/Force/MpmForceBase.cpp:100-153,213-328), FBasedMpmForceHelper
+// (Lib/MPM/Force/FBasedMpmForceHelper.cpp:25-160, .h:123-157), CorotatedIsotropic
+// (Lib/Ziran/Physics/ConstitutiveModel/CorotatedIsotropic.h:110-230), SvdBasedIsotropicHelper.h:223-282,
+// ImplicitSolverObjective::{computeResidual, updateState, totalEnergy, multiply, evaluatePerNodeCNTolerance}
+// (Projects/multigrid/ImplicitSolver.h:128-155,237-275,667-696,741-763), MassLumpedInertia (Inertia.cpp:16-53).
+//
+// Re-design for the GPU
+//  * updateState = ONE kernel: CTA per page group stages the (vn+dv) node tile in shared memory, each thread gathers its
+//    particle's grad v, evolves F, runs the SVD and writes F, vol*P*Fn^T, U, sigma, V and the energy density (the
+//    reference runs three colour-serialised / particle-parallel passes with 72-byte round trips between them).
+//  * The matrix-free Hessian apply does not redo U^T(.)V / U(.)V^T per particle and per Krylov iteration like
+//    firstPiolaDifferential: once per linearisation each particle's Hessian is contracted with Fn on both sides into the
+//    symmetric 9x9 map  H~ : grad x_p -> vol * dP(grad x_p Fn) Fn^T  (45 doubles), so an apply is
+//    gather(27) -> 81 FMA -> scatter(27) and the same H~ feeds the matrix assembly (a15).
+//  * scatters use the shared k_plane_scatter skeleton (scatter.cuh): no colour passes, no atomics in the particle loop.
+#include "scatter.cuh"
+#include "dense3.cuh"
+#include "reduce.cuh"
+
+namespace hot {
+namespace {
+
+constexpr int TILE = Geo::TILE;
+constexpr int TPB = 256;
+inline int nblk(long n) { return (int)((n + TPB - 1) / TPB); }
+
+// grad f_p = sum_i f_i grad w_ip^T over the 27 stencil nodes, field staged as tile[3][TILE]; weight gradients in the
+// reference's association (MpmGrid.h:272-291)
+__device__ __forceinline__ void gather_gradient(const double* __restrict__ tile, const SplineEval& sp, double one_over_dx, double (&G)[9])
+{
+    const int tb = tile_base(sp.base[0], sp.base[1], sp.base[2]);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) G[q] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double wi = sp.w[0][i], dwidxi = one_over_dx * sp.dw[0][i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double wij = wi * sp.w[1][j], dwijdxi = dwidxi * sp.w[1][j], dwijdxj = wi * one_over_dx * sp.dw[1][j];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int n = tb + (i * Geo::TY + j) * Geo::TZ + k;
+                const double wk = sp.w[2][k];
+                const double gw[3] = {dwijdxi * wk, dwijdxj * wk, wij * one_over_dx * sp.dw[2][k]};
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double nv = tile[r * TILE + n];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) G[r + 3 * c] += nv * gw[c];
+                }
+            }
+        }
+    }
+}
+
+// packed upper triangle of a symmetric 9x9: entry (i <= j) at j(j+1)/2 + i
+__device__ __forceinline__ constexpr int tri(int i, int j) { return i <= j ? j * (j + 1) / 2 + i : i * (i + 1) / 2 + j; }
+
+// ---- a9 + a10 + a11: ImplicitSolverObjective::updateState -------------------------------------------------------
+constexpr int US_THREADS = 128;
+
+__global__ void __launch_bounds__(US_THREADS) k_update_state(const int* __restrict__ group_first, const int* __restrict__ group_slot,
+    const int* __restrict__ nbr8, size_t ps, const double* __restrict__ X, const double* __restrict__ Fn, double* __restrict__ F,
+    const double* __restrict__ vol, const double* __restrict__ mu, const double* __restrict__ lam, double* __restrict__ stress,
+    double* __restrict__ Uo, double* __restrict__ Vo, double* __restrict__ sigo, double* __restrict__ gradV, double dx, double one_over_dx,
+    double dt, size_t gs, const double* __restrict__ g_v, const int* __restrict__ g_idx, const double* __restrict__ dv,
+    double* __restrict__ group_psi)
+{
+    __shared__ double tile[3 * TILE];
+    __shared__ int s_nbr[8];
+    __shared__ double s_res[1];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const int first = group_first[g], end = group_first[g + 1];
+    if (tid < 8) s_nbr[tid] = nbr8[(size_t)group_slot[g] * 8 + tid];
+    __syncthreads();
+    // moveNodes + the field of computeVAndGradV: v_i = vn_i + dv_i  (MpmSimulationBase.cpp:735-747)
+    for (int n = tid; n < TILE; n += US_THREADS) {
+        long a = tile_to_grid(n, s_nbr);
+        double nv[3] = {0, 0, 0};
+        if (a >= 0) {
+            int id = g_idx[a];
+            if (id >= 0)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) nv[d] = g_v[d * gs + a] + dv[3 * (size_t)id + d];
+        }
+        tile[n] = nv[0]; tile[TILE + n] = nv[1]; tile[2 * TILE + n] = nv[2];
+    }
+    __syncthreads();
+    double e[1] = {0.0};
+    for (int s = first + tid; s < end; s += US_THREADS) {
+        SplineEval sp;
+        sp.eval(X, ps, s, dx, one_over_dx, true);
+        double G[9], A[9], Fo[9], Fnew[9];
+        gather_gradient(tile, sp, one_over_dx, G);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            gradV[q * ps + s] = G[q];
+            A[q] = dt * G[q];
+            Fo[q] = Fn[q * ps + s];
+        }
+        A[0] += 1.0; A[4] += 1.0; A[8] += 1.0;
+        mm(A, Fo, Fnew); // evolveStrain: F = (I + dt gradV) Fn, FBasedMpmForceHelper.cpp:100-114
+        double U[9], V[9], sig[3], R[9], cof[9], P[9], T[9];
+        svd3(Fnew, U, sig, V);
+        mm_bt(U, V, R);
+        cofactor3(Fnew, cof);
+        const double J = sig[0] * sig[1] * sig[2], m_ = mu[s], l_ = lam[s], vo = vol[s];
+        double n2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            const double d = Fnew[q] - R[q];
+            n2 += d * d;
+            P[q] = 2.0 * m_ * d + l_ * (J - 1.0) * cof[q]; // firstPiola, CorotatedIsotropic.h:157-160
+        }
+        e[0] += vo * (m_ * n2 + 0.5 * l_ * (J - 1.0) * (J - 1.0)); // psi, :151-155
+        mm_bt(P, Fo, T); // updateImplicitState: vol P Fn^T, FBasedMpmForceHelper.cpp:72-97
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            F[q * ps + s] = Fnew[q];
+            stress[q * ps + s] = vo * T[q];
+            Uo[q * ps + s] = U[q];
+            Vo[q * ps + s] = V[q];
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) sigo[d * ps + s] = sig[d];
+    }
+    block_sum<1>(e, s_res);
+    if (tid == 0) group_psi[g] = s_res[0];
+}
+
+// inertia + gravity terms of totalEnergy (ImplicitSolver.h:254-275, Inertia.cpp:16-30): [sum m |dv|^2, sum m g.dv]
+struct EnergyNodesF {
+    const double *dv, *mass;
+    double g0, g1, g2;
+    __device__ void operator()(long i, double (&acc)[2]) const
+    {
+        const double a = dv[3 * i], b = dv[3 * i + 1], c = dv[3 * i + 2], m = mass[i];
+        acc[0] += (a * a + b * b + c * c) * m;
+        acc[1] += (g0 * a + g1 * b + g2 * c) * m;
+    }
+};
+struct SumF {
+    const double* a;
+    __device__ void operator()(long i, double (&acc)[1]) const { acc[0] += a[i]; }
+};
+
+// ---- contracted particle Hessian H~ (see file header) ---------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_build_hessian(long n, size_t ps, const double* __restrict__ Fn, const double* __restrict__ vol,
+    const double* __restrict__ mu, const double* __restrict__ lam, const double* __restrict__ Ui, const double* __restrict__ Vi,
+    const double* __restrict__ sigi, int project, double* __restrict__ H)
+{
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    double U[9], V[9], F0[9], sig[3];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        U[q] = Ui[q * ps + s];
+        V[q] = Vi[q * ps + s];
+        F0[q] = Fn[q * ps + s];
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) sig[d] = sigi[d * ps + s];
+    HessBlocks hb;
+    corotated_blocks(sig, mu[s], lam[s], project != 0, hb);
+    const double vo = vol[s];
+    // FV = Fn V (3x3): D for the basis gradient e_a e_d^T is  (U^T e_a) (row d of Fn V)
+    double FV[9];
+    mm(F0, V, FV);
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int col = a + 3 * d; // column-major index of grad x entry (a, d)
+            double D[9], K[9], t[9], dP[9], T[9];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) D[r + 3 * c] = U[a + 3 * r] * FV[d + 3 * c];
+            blocks_contract(hb, D, K);
+            mm(U, K, t);
+            mm_bt(t, V, dP);
+            mm_bt(dP, F0, T);
+#pragma unroll
+            for (int row = 0; row < 9; ++row)
+                if (row <= col) H[(size_t)tri(row, col) * ps + s] = vo * T[row];
+        }
+}
+
+// ---- scatters -------------------------------------------------------------------------------------------------------
+// Common record of the two vector scatters (a12 force, a13 Hessian apply): node value = T grad w with a per-particle 3x3 T.
+//   [0..2] wy  [3..5] wz  [6..8] dwy/dx  [9..11] dwz/dx   then per x-plane i: T(:,0)*dwx_i/dx, T(:,1)*wx_i, T(:,2)*wx_i
+struct TGradScatter {
+    static constexpr int NCH = 3, REC = 40;
+    __device__ __forceinline__ static void fill(const SplineEval& sp, double one_over_dx, const double* T, double* r)
+    {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            r[j] = sp.w[1][j];
+            r[3 + j] = sp.w[2][j];
+            r[6 + j] = one_over_dx * sp.dw[1][j];
+            r[9 + j] = one_over_dx * sp.dw[2][j];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double wx = sp.w[0][i], dwx = one_over_dx * sp.dw[0][i];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                r[12 + 9 * i + q] = T[q] * dwx;
+                r[12 + 9 * i + 3 + q] = T[3 + q] * wx;
+                r[12 + 9 * i + 6 + q] = T[6 + q] * wx;
+            }
+        }
+        r[39] = 0.0;
+    }
+    __device__ __forceinline__ static void accumulate(const double* rec, int pl, double (&acc)[9][3])
+    {
+        const double2* r2 = reinterpret_cast<const double2*>(rec);
+        const double2 a0 = r2[0], a1 = r2[1], a2 = r2[2], a3 = r2[3], a4 = r2[4], a5 = r2[5];
+        const double wy[3] = {a0.x, a0.y, a1.x}, wz[3] = {a1.y, a2.x, a2.y};
+        const double gy[3] = {a3.x, a3.y, a4.x}, gz[3] = {a4.y, a5.x, a5.y};
+        const double* p = rec + 12 + 9 * pl;
+        const double ax[3] = {p[0], p[1], p[2]}, ay[3] = {p[3], p[4], p[5]}, az[3] = {p[6], p[7], p[8]};
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double c0 = wy[j] * wz[k], c1 = gy[j] * wz[k], c2 = wy[j] * gz[k];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) acc[j * 3 + k][r] += ax[r] * c0 + ay[r] * c1 + az[r] * c2;
+            }
+    }
+};
+
+// a12: rasterizeForceToTVStack: f_i -= scale * (vol P Fn^T) grad w   (MpmForceBase.cpp:100-153)
+struct ForcePolicy {
+    static constexpr int NCH = 3, REC = TGradScatter::REC, GATHER = 0;
+    struct Args {
+        size_t ps;
+        const double *X, *stress;
+        double dx, one_over_dx, scale;
+        const int* g_idx;
+        double* out; // DOF vector
+    };
+    __device__ static void gather_node(const Args&, long, double (&)[3]) {}
+    __device__ static void stage(const Args& a, size_t s, double* r, const double*)
+    {
+        SplineEval sp;
+        sp.eval(a.X, a.ps, s, a.dx, a.one_over_dx, true);
+        double T[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) T[q] = -a.scale * a.stress[q * a.ps + s];
+        TGradScatter::fill(sp, a.one_over_dx, T, r);
+    }
+    __device__ __forceinline__ static void accumulate(const Args&, const double* rec, int pl, double (&acc)[9][3])
+    {
+        TGradScatter::accumulate(rec, pl, acc);
+    }
+    __device__ static void flush(const Args& a, long n, const double (&v)[3])
+    {
+        const int id = a.g_idx[n];
+        if (id < 0) return;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) atomicAdd(a.out + 3 * (size_t)id + d, v[d]);
+    }
+};
+
+// a13: b += dt^2 * sum_p [H~_p : grad x_p] grad w   (MpmForceBase.cpp:261-306 with scale = -dt^2)
+struct HessianPolicy {
+    static constexpr int NCH = 3, REC = TGradScatter::REC, GATHER = 1;
+    struct Args {
+        size_t ps;
+        const double *X, *H;
+        double dx, one_over_dx, dt2;
+        const int* g_idx;
+        const double* x; // DOF vector in
+        double* out; // DOF vector out
+    };
+    __device__ static void gather_node(const Args& a, long n, double (&v)[3])
+    {
+        const int id = a.g_idx[n];
+        if (id < 0) return;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v[d] = a.x[3 * (size_t)id + d];
+    }
+    __device__ static void stage(const Args& a, size_t s, double* r, const double* gtile)
+    {
+        SplineEval sp;
+        sp.eval(a.X, a.ps, s, a.dx, a.one_over_dx, true);
+        double G[9], T[9];
+        gather_gradient(gtile, sp, a.one_over_dx, G);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) T[q] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+#pragma unroll
+            for (int i = 0; i <= j; ++i) {
+                const double h = a.H[(size_t)tri(i, j) * a.ps + s];
+                T[i] += h * G[j];
+                if (i != j) T[j] += h * G[i];
+            }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) T[q] *= a.dt2;
+        TGradScatter::fill(sp, a.one_over_dx, T, r);
+    }
+    __device__ __forceinline__ static void accumulate(const Args&, const double* rec, int pl, double (&acc)[9][3])
+    {
+        TGradScatter::accumulate(rec, pl, acc);
+    }
+    __device__ static void flush(const Args& a, long n, const double (&v)[3])
+    {
+        const int id = a.g_idx[n];
+        if (id < 0) return;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) atomicAdd(a.out + 3 * (size_t)id + d, v[d]);
+    }
+};
+
+// a18: nodeCNTol_i += w_ip m_p ||dPdF(F = I)||_F   (ImplicitSolver.h:667-696, FBasedMpmForceHelper.h:123-157)
+struct CNTolPolicy {
+    static constexpr int NCH = 1, REC = 10, GATHER = 0;
+    struct Args {
+        size_t ps;
+        const double *X, *M, *mu, *lam;
+        double dx, one_over_dx;
+        int project;
+        const int* g_idx;
+        double* out; // per node
+    };
+    __device__ static void gather_node(const Args&, long, double (&)[3]) {}
+    __device__ static void stage(const Args& a, size_t s, double* r, const double*)
+    {
+        SplineEval sp;
+        sp.eval(a.X, a.ps, s, a.dx, a.one_over_dx, false);
+        // dPdF = Q blockdiag(A, B01, B12, B20) Q^T with Q orthogonal, so ||dPdF||_F^2 = sum of the block norms^2
+        const double one[3] = {1.0, 1.0, 1.0};
+        HessBlocks hb;
+        corotated_blocks(one, a.mu[s], a.lam[s], a.project != 0, hb);
+        double n2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) n2 += hb.A[q] * hb.A[q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) n2 += hb.B01[q] * hb.B01[q] + hb.B12[q] * hb.B12[q] + hb.B20[q] * hb.B20[q];
+        const double val = a.M[s] * sqrt(n2);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            r[j] = sp.w[1][j];
+            r[3 + j] = sp.w[2][j];
+            r[6 + j] = val * sp.w[0][j];
+        }
+        r[9] = 0.0;
+    }
+    __device__ __forceinline__ static void accumulate(const Args&, const double* rec, int pl, double (&acc)[9][1])
+    {
+        const double v = rec[6 + pl];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc[j * 3 + k][0] += v * (rec[j] * rec[3 + k]);
+    }
+    __device__ static void flush(const Args& a, long n, const double (&v)[1])
+    {
+        const int id = a.g_idx[n];
+        if (id >= 0) atomicAdd(a.out + id, v[0]);
+    }
+};
+
+// r = dt m g - m dv   (the gravity and inertia terms of computeResidual, ImplicitSolver.h:133-145, Inertia.cpp:33-41)
+__global__ void k_residual_init(int n, const double* __restrict__ mass, const double* __restrict__ dv, double dtg0, double dtg1, double dtg2,
+    double* __restrict__ r)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * n) return;
+    const int i = t / 3, d = t - 3 * i;
+    const double m = mass[i];
+    r[t] = (d == 0 ? dtg0 : (d == 1 ? dtg1 : dtg2)) * m - m * dv[t];
+}
+// b = M x   (MassLumpedInertia::addScaledForceDifferential with scale -dt^2, Inertia.cpp:45-53)
+__global__ void k_mass_mul(int n, const double* __restrict__ mass, const double* __restrict__ x, double* __restrict__ b)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 3 * n) b[t] = mass[t / 3] * x[t];
+}
+// objective.project (MultigridSimulation.h:104-125)
+__global__ void k_bc_project(int n_bc, int mode, const int* __restrict__ node, const int* __restrict__ slip, const double* __restrict__ P,
+    double* __restrict__ v)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_bc) return;
+    double* x = v + 3 * (size_t)node[b];
+    if (mode == 1) {
+        x[0] = 0.0;
+        if (!slip[b]) x[1] = x[2] = 0.0;
+    }
+    else {
+        const double* Pm = P + 9 * (size_t)b;
+        const double x0 = x[0], x1 = x[1], x2 = x[2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) x[r] = Pm[r] * x0 + Pm[r + 3] * x1 + Pm[r + 6] * x2;
+    }
+}
+// transformResidual / recoverSolution (ImplicitSolver.h:106-125)
+__global__ void k_bc_rotate(int n_bc, const int* __restrict__ node, const int* __restrict__ slip, const double* __restrict__ R,
+    double* __restrict__ v)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_bc || !slip[b]) return;
+    double* x = v + 3 * (size_t)node[b];
+    const double* Rm = R + 9 * (size_t)b;
+    const double x0 = x[0], x1 = x[1], x2 = x[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) x[r] = Rm[r] * x0 + Rm[r + 3] * x1 + Rm[r + 6] * x2;
+}
+// Newton initial guess (MpmSimulationBase.cpp:1177-1180): dv = g dt on free nodes ...
+__global__ void k_fill3(int n, double a, double b, double c, double* __restrict__ v)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * n) return;
+    const int d = t % 3;
+    v[t] = d == 0 ? a : (d == 1 ? b : c);
+}
+// ... and the collider velocity difference on BC nodes
+__global__ void k_set_bc_dv(int n_bc, const int* __restrict__ node, const double* __restrict__ dv_bc, double* __restrict__ dv)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_bc) return;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) dv[3 * (size_t)node[b] + d] = dv_bc ? dv_bc[3 * b + d] : 0.0;
+}
+__global__ void k_cn_finish(int n, const double* __restrict__ mass, double factor, double* __restrict__ tol)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tol[i] *= factor / mass[i];
+}
+
+} // namespace
+
+// FBasedMpmForceHelper::backupStrain / restoreStrain, FBasedMpmForceHelper.cpp:25-44
+int backup_strain(Sim* s)
+{
+    if (!s->sorted) return fail(s, "backupStrain: call hot_sort_and_activate first");
+    HOT_CUDA(s->P.Fn.reserve(9 * s->P.stride));
+    HOT_CUDA(cudaMemcpyAsync(s->P.Fn.p, s->P.F.p, 9 * s->P.stride * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    s->strain_backed_up = true;
+    s->state_valid = s->hessian_valid = false;
+    return 0;
+}
+int restore_strain(Sim* s)
+{
+    if (!s->strain_backed_up) return fail(s, "restoreStrain: no backup (call hot_backup_strain first)");
+    HOT_CUDA(cudaMemcpyAsync(s->P.F.p, s->P.Fn.p, 9 * s->P.stride * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    return 0;
+}
+
+// host arrays in; also sets the Newton initial guess (buildInitialDvAndVnForNewton, MpmSimulationBase.cpp:1139-1184)
+int set_bc(Sim* s, int mode, int n_bc, const int* node_id, const double* P, const double* R, const double* Rinv, const int* slip,
+    const double* dv_bc)
+{
+    if (!s->p2g_done) return fail(s, "hot_set_bc: call hot_p2g first");
+    if (n_bc < 0 || (n_bc > 0 && !node_id)) return fail(s, "hot_set_bc: bad BC table");
+    for (int b = 0; b < n_bc; ++b)
+        if (node_id[b] < 0 || node_id[b] >= s->num_nodes) return fail(s, "hot_set_bc: node id out of range");
+    cudaStream_t st = s->stream;
+    const size_t nb = n_bc > 0 ? n_bc : 1;
+    HOT_CUDA(s->bc_node.reserve(nb));
+    HOT_CUDA(s->bc_slip.reserve(nb));
+    HOT_CUDA(s->bc_P.reserve(9 * nb));
+    HOT_CUDA(s->bc_R.reserve(9 * nb));
+    HOT_CUDA(s->bc_Rinv.reserve(9 * nb));
+    HOT_CUDA(s->work[0].reserve(3 * nb));
+    s->bc_mode = mode;
+    s->n_bc = n_bc;
+    HOT_CUDA(cudaMemsetAsync(s->bc_slip.p, 0, nb * sizeof(int), st));
+    HOT_CUDA(cudaMemsetAsync(s->bc_P.p, 0, 9 * nb * sizeof(double), st));
+    HOT_CUDA(cudaMemsetAsync(s->bc_R.p, 0, 9 * nb * sizeof(double), st));
+    HOT_CUDA(cudaMemsetAsync(s->bc_Rinv.p, 0, 9 * nb * sizeof(double), st));
+    if (n_bc > 0) {
+        HOT_CUDA(cudaMemcpyAsync(s->bc_node.p, node_id, n_bc * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (slip) HOT_CUDA(cudaMemcpyAsync(s->bc_slip.p, slip, n_bc * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (P) HOT_CUDA(cudaMemcpyAsync(s->bc_P.p, P, 9 * (size_t)n_bc * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (R) HOT_CUDA(cudaMemcpyAsync(s->bc_R.p, R, 9 * (size_t)n_bc * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (Rinv) HOT_CUDA(cudaMemcpyAsync(s->bc_Rinv.p, Rinv, 9 * (size_t)n_bc * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (dv_bc) HOT_CUDA(cudaMemcpyAsync(s->work[0].p, dv_bc, 3 * (size_t)n_bc * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    const int nn = s->num_nodes;
+    k_fill3<<<nblk(3 * (long)nn), TPB, 0, st>>>(nn, s->gravity[0] * s->dt, s->gravity[1] * s->dt, s->gravity[2] * s->dt, s->dv.p);
+    HOT_LAUNCHED(s);
+    if (n_bc > 0) {
+        k_set_bc_dv<<<nblk(n_bc), TPB, 0, st>>>(n_bc, s->bc_node.p, dv_bc ? s->work[0].p : nullptr, s->dv.p);
+        HOT_LAUNCHED(s);
+    }
+    HOT_CUDA(cudaStreamSynchronize(st)); // the host arrays may be released by the caller
+    s->state_valid = s->hessian_valid = false;
+    return 0;
+}
+
+int bc_project(Sim* s, double* v)
+{
+    if (s->n_bc <= 0) return 0;
+    k_bc_project<<<nblk(s->n_bc), TPB, 0, s->stream>>>(s->n_bc, s->bc_mode, s->bc_node.p, s->bc_slip.p, s->bc_P.p, v);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+int bc_rotate(Sim* s, double* v, bool inverse)
+{
+    if (s->n_bc <= 0 || s->bc_mode != 1) return 0;
+    k_bc_rotate<<<nblk(s->n_bc), TPB, 0, s->stream>>>(s->n_bc, s->bc_node.p, s->bc_slip.p, inverse ? s->bc_Rinv.p : s->bc_R.p, v);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+
+// ImplicitSolverObjective::updateState (ImplicitSolver.h:237-252) on the device-resident dv
+int update_state(Sim* s, bool want_energy, double* energy)
+{
+    if (!s->p2g_done) return fail(s, "updateState: call hot_p2g first");
+    if (!s->strain_backed_up) return fail(s, "updateState: call hot_backup_strain first (startBackwardEuler, MultigridSimulation.h:167-186)");
+    cudaStream_t st = s->stream;
+    const size_t ps = s->P.stride;
+    HOT_CUDA(s->f_stress.reserve(9 * ps));
+    HOT_CUDA(s->f_U.reserve(9 * ps));
+    HOT_CUDA(s->f_V.reserve(9 * ps));
+    HOT_CUDA(s->f_sig.reserve(3 * ps));
+    HOT_CUDA(s->P.gradV.reserve(9 * ps));
+    HOT_CUDA(s->group_psi.reserve(s->n_groups));
+    {
+        KTime t(s, KC_STRESS);
+        k_update_state<<<(unsigned)s->n_groups, US_THREADS, 0, st>>>(s->group_first.p, s->group_slot.p, s->nbr8.p, ps, s->P.X.p, s->P.Fn.p,
+            s->P.F.p, s->P.vol.p, s->P.mu.p, s->P.lam.p, s->f_stress.p, s->f_U.p, s->f_V.p, s->f_sig.p, s->P.gradV.p, s->dx, 1.0 / s->dx,
+            s->dt, s->g_stride, s->g_v.p, s->g_idx.p, s->dv.p, s->group_psi.p);
+        HOT_LAUNCHED(s);
+    }
+    s->state_valid = true;
+    s->hessian_valid = false;
+    if (want_energy) {
+        KTime t(s, KC_BLAS1);
+        HOT_CUDA(s->red_out.reserve(64));
+        int rc = reduce_to<1>(s, s->n_groups, SumF{s->group_psi.p}, s->red_out.p + 8, nullptr);
+        if (rc) return rc;
+        double h[2];
+        rc = reduce_to<2>(s, s->num_nodes, EnergyNodesF{s->dv.p, s->mass_matrix.p, s->gravity[0], s->gravity[1], s->gravity[2]},
+            s->red_out.p + 9, nullptr);
+        if (rc) return rc;
+        HOT_CUDA(cudaMemcpyAsync(s->h_red, s->red_out.p + 8, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        HOT_CUDA(cudaStreamSynchronize(st));
+        h[0] = s->h_red[1]; h[1] = s->h_red[2];
+        if (energy) *energy = s->h_red[0] + h[0] / 2 - s->dt * h[1];
+    }
+    return 0;
+}
+
+// ImplicitSolverObjective::computeResidual, ImplicitSolver.h:128-155
+int compute_residual(Sim* s, double* r)
+{
+    if (!s->state_valid) return fail(s, "computeResidual: call hot_update_state first");
+    cudaStream_t st = s->stream;
+    const int nn = s->num_nodes;
+    KTime t(s, KC_FORCE);
+    k_residual_init<<<nblk(3 * (long)nn), TPB, 0, st>>>(nn, s->mass_matrix.p, s->dv.p, s->dt * s->gravity[0], s->dt * s->gravity[1],
+        s->dt * s->gravity[2], r);
+    HOT_LAUNCHED(s);
+    ForcePolicy::Args a{s->P.stride, s->P.X.p, s->f_stress.p, s->dx, 1.0 / s->dx, s->dt, s->g_idx.p, r};
+    k_plane_scatter<ForcePolicy><<<(unsigned)s->n_groups, SC_THREADS, 0, st>>>(a, s->cell_start.p, s->group_slot.p, s->nbr8.p);
+    HOT_LAUNCHED(s);
+    int rc = bc_rotate(s, r, false);
+    if (rc) return rc;
+    return bc_project(s, r);
+}
+
+int ensure_hessian(Sim* s)
+{
+    if (!s->state_valid) return fail(s, "Hessian: call hot_update_state first");
+    if (s->hessian_valid) return 0;
+    const size_t ps = s->P.stride;
+    HOT_CUDA(s->f_H.reserve(45 * ps));
+    KTime t(s, KC_STRESS);
+    k_build_hessian<<<(unsigned)((s->N + 127) / 128), 128, 0, s->stream>>>(s->N, ps, s->P.Fn.p, s->P.vol.p, s->P.mu.p, s->P.lam.p, s->f_U.p,
+        s->f_V.p, s->f_sig.p, s->project_pd ? 1 : 0, s->f_H.p);
+    HOT_LAUNCHED(s);
+    s->hessian_valid = true;
+    return 0;
+}
+
+// ImplicitSolverObjective::multiply with matrix_free, ImplicitSolver.h:741-763
+int hessian_apply_mf(Sim* s, const double* x, double* b)
+{
+    int rc = ensure_hessian(s);
+    if (rc) return rc;
+    cudaStream_t st = s->stream;
+    const int nn = s->num_nodes;
+    KTime t(s, KC_HESSIAN);
+    k_mass_mul<<<nblk(3 * (long)nn), TPB, 0, st>>>(nn, s->mass_matrix.p, x, b);
+    HOT_LAUNCHED(s);
+    HessianPolicy::Args a{s->P.stride, s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, s->dt * s->dt, s->g_idx.p, x, b};
+    k_plane_scatter<HessianPolicy><<<(unsigned)s->n_groups, SC_THREADS, 0, st>>>(a, s->cell_start.p, s->group_slot.p, s->nbr8.p);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+
+// ImplicitSolverObjective::evaluatePerNodeCNTolerance, ImplicitSolver.h:667-696
+int eval_cn_tolerance(Sim* s, double eps, double dt, double* tol)
+{
+    if (!s->p2g_done) return fail(s, "evaluatePerNodeCNTolerance: call hot_p2g first");
+    cudaStream_t st = s->stream;
+    const int nn = s->num_nodes;
+    KTime t(s, KC_FORCE);
+    HOT_CUDA(cudaMemsetAsync(tol, 0, (size_t)nn * sizeof(double), st));
+    CNTolPolicy::Args a{s->P.stride, s->P.X.p, s->P.M.p, s->P.mu.p, s->P.lam.p, s->dx, 1.0 / s->dx, s->project_pd ? 1 : 0, s->g_idx.p, tol};
+    k_plane_scatter<CNTolPolicy><<<(unsigned)s->n_groups, SC_THREADS, 0, st>>>(a, s->cell_start.p, s->group_slot.p, s->nbr8.p);
+    HOT_LAUNCHED(s);
+    k_cn_finish<<<nblk(nn), TPB, 0, st>>>(nn, s->mass_matrix.p, eps * 24 * s->dx * s->dx * dt, tol);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+
+} // namespace hot

@@ -152,6 +152,22 @@ struct Sim {
     DevBuf<double> dv, vn, mass_matrix;
 
     DevBuf<int> flags; // g2p CFL flags
+
+    // ---- force model state (force.cu); particle arrays are in sorted order and live for one time step
+    bool project_pd = true; // CorotatedIsotropic::project (CorotatedIsotropic.h:60)
+    bool strain_backed_up = false, state_valid = false, hessian_valid = false;
+    DevBuf<double> f_stress; // vol P Fn^T, 9 rows
+    DevBuf<double> f_U, f_V, f_sig; // SVD of the trial F
+    DevBuf<double> f_H; // 45 rows: packed upper triangle of the contracted particle Hessian (see force.cu)
+    DevBuf<double> group_psi; // per-group sum of vol*psi
+    DevBuf<double> red_partial, red_out; // deterministic two-stage reductions
+    double* h_red = nullptr; // pinned mirror of red_out
+    // BC table (a8 output): CollisionNode{node_id,P,R,Rinv,shouldRotate}, CollisionObject.h:16-45
+    int bc_mode = 0, n_bc = 0;
+    DevBuf<int> bc_node, bc_slip;
+    DevBuf<double> bc_P, bc_R, bc_Rinv;
+    DevBuf<double> cn_tol; // per-node CN tolerance (a18)
+    DevBuf<double> work[8]; // DOF-sized scratch vectors of the host-buffer entry points
 };
 
 int fail(Sim* s, const std::string& msg);
@@ -188,6 +204,18 @@ int number_nodes(Sim* s); // a7, after the P2G scatter
 // transfer.cu
 int p2g(Sim* s);
 int g2p(Sim* s, double dt, int* flags);
+// force.cu -- all pointers are DEVICE pointers to DOF vectors (n_nodes x 3)
+int backup_strain(Sim* s);
+int restore_strain(Sim* s);
+int set_bc(Sim* s, int mode, int n_bc, const int* node_id, const double* P, const double* R, const double* Rinv, const int* slip,
+    const double* dv_bc);
+int update_state(Sim* s, bool want_energy, double* energy);
+int compute_residual(Sim* s, double* r);
+int bc_project(Sim* s, double* v);
+int bc_rotate(Sim* s, double* v, bool inverse);
+int ensure_hessian(Sim* s);
+int hessian_apply_mf(Sim* s, const double* x, double* b);
+int eval_cn_tolerance(Sim* s, double eps, double dt, double* tol);
 
 // ---- device helpers ----------------------------------------------------------------------------------
 #ifdef __CUDACC__

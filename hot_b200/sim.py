@@ -182,3 +182,64 @@ class MpmSimulationB200:
         flags = (C.c_int * 2)(0, 0)
         self._check(self._lib.hot_g2p(self._h, float(dt), flags if want_flags else None))
         return (flags[0], flags[1])
+
+    # ---- force model / objective (ImplicitSolverObjective surface, Projects/multigrid/ImplicitSolver.h)
+    def set_dt_gravity(self, dt, g):
+        g = _f64(g, (3,))
+        self._check(self._lib.hot_set_dt_gravity(self._h, float(dt), _ptr(g)))
+        self.dt = float(dt)
+
+    def set_project(self, project):
+        self._check(self._lib.hot_set_project(self._h, int(project)))
+
+    def set_bc(self, node_id, P=None, R=None, Rinv=None, slip=None, dv_bc=None, mode=0):
+        node_id = np.ascontiguousarray(node_id, dtype=np.int32)
+        f = lambda a: None if a is None else _f64(a)
+        P, R, Rinv, dv_bc = f(P), f(R), f(Rinv), f(dv_bc)
+        slip = None if slip is None else np.ascontiguousarray(slip, dtype=np.int32)
+        self._check(self._lib.hot_set_bc(self._h, int(mode), len(node_id), _ptr(node_id), _ptr(P), _ptr(R), _ptr(Rinv),
+                                         _ptr(slip), _ptr(dv_bc)))
+
+    def get_dv(self):
+        out = np.empty((self.num_nodes, 3))
+        self._check(self._lib.hot_get_dv(self._h, _ptr(out)))
+        return out
+
+    def backupStrain(self):
+        self._check(self._lib.hot_backup_strain(self._h))
+
+    def restoreStrain(self):
+        self._check(self._lib.hot_restore_strain(self._h))
+
+    def updateState(self, dv=None, want_energy=True):
+        e = C.c_double(0)
+        dvb = None if dv is None else _f64(dv, (self.num_nodes, 3))
+        self._check(self._lib.hot_update_state(self._h, _ptr(dvb), C.byref(e) if want_energy else None))
+        return e.value
+
+    def get_stress(self):
+        S = np.empty((self.N, 9)); F = np.empty((self.N, 9))
+        self._check(self._lib.hot_get_stress(self._h, _ptr(S), _ptr(F)))
+        return S, F
+
+    def computeResidual(self):
+        r = np.empty((self.num_nodes, 3))
+        self._check(self._lib.hot_compute_residual(self._h, _ptr(r)))
+        return r
+
+    def project(self, v):
+        v = _f64(v, (self.num_nodes, 3)).copy()
+        self._check(self._lib.hot_project(self._h, _ptr(v)))
+        return v
+
+    def multiply(self, x):
+        """matrix-free Hessian apply (ImplicitSolverObjective::multiply with --matfree)"""
+        x = _f64(x, (self.num_nodes, 3))
+        b = np.empty_like(x)
+        self._check(self._lib.hot_hessian_apply_mf(self._h, _ptr(x), _ptr(b)))
+        return b
+
+    def evaluatePerNodeCNTolerance(self, eps, dt):
+        tol = np.empty(self.num_nodes)
+        self._check(self._lib.hot_eval_cn_tolerance(self._h, float(eps), float(dt), _ptr(tol)))
+        return tol

@@ -90,6 +90,37 @@ int hot_get_mass_matrix(hot_sim* h, double* mass);
 int hot_set_dv(hot_sim* h, const double* dv);
 int hot_g2p(hot_sim* h, double dt, int* flags /* [0] faster than dx, [1] faster than cfl*dx/2 */);
 
+/* ---- force model: the operator surface ImplicitSolverObjective drives (Projects/multigrid/ImplicitSolver.h) ------- */
+/* simulation.dt / simulation.gravity (MpmSimulationBase.h:69-131) */
+int hot_set_dt_gravity(hot_sim* h, double dt, const double* gravity3);
+/* CorotatedIsotropic::project, the PSD clamp of the SVD-space Hessian blocks (CorotatedIsotropic.h:60,139-143) */
+int hot_set_project(hot_sim* h, int project);
+/* a8 output of buildInitialDvAndVnForNewton (Lib/MPM/MpmSimulationBase.cpp:1139-1184), evaluated by the host from its
+ * collision objects: the CollisionNode table {node_id, P, R, Rinv, shouldRotate} (CollisionObject.h:16-45; 3x3
+ * column-major, any of P/R/Rinv/slip may be NULL) and the collider velocity difference dv_bc (NULL = 0).
+ * mode 0: project(v) = P v on every BC node (MultigridSimulation.h:104-125 default); mode 1: HOTSettings::boundaryType
+ * == 1 && systemBCProject: rotate slip nodes with R, zero component 0 (slip) or the whole node (sticky).
+ * Also sets the Newton initial guess dv = gravity*dt on free nodes and dv_bc on BC nodes (:1177-1180). */
+int hot_set_bc(hot_sim* h, int mode, int n_bc, const int* node_id, const double* P, const double* R, const double* Rinv,
+    const int* slip, const double* dv_bc);
+int hot_get_dv(hot_sim* h, double* dv);
+/* FBasedMpmForceHelper::backupStrain / restoreStrain (Lib/MPM/Force/FBasedMpmForceHelper.cpp:25-44) */
+int hot_backup_strain(hot_sim* h);
+int hot_restore_strain(hot_sim* h);
+/* ImplicitSolverObjective::updateState (ImplicitSolver.h:237-252): moveNodes(dv) (dv NULL = keep the device dv),
+ * MpmForceBase::updatePositionBasedState (MpmForceBase.cpp:308-328); energy (nullable) = totalEnergy (:254-275) */
+int hot_update_state(hot_sim* h, const double* dv, double* energy);
+/* scratch_stress = vol P Fn^T and the trial F, original particle order (FBasedMpmForceHelper.cpp:72-97) */
+int hot_get_stress(hot_sim* h, double* vPFnT, double* F);
+/* ImplicitSolverObjective::computeResidual (ImplicitSolver.h:128-155) */
+int hot_compute_residual(hot_sim* h, double* residual);
+/* objective.project (MultigridSimulation.h:104-125), in place */
+int hot_project(hot_sim* h, double* v);
+/* ImplicitSolverObjective::multiply with --matfree (ImplicitSolver.h:741-763): b = M x + dt^2 K x */
+int hot_hessian_apply_mf(hot_sim* h, const double* x, double* b);
+/* ImplicitSolverObjective::evaluatePerNodeCNTolerance (ImplicitSolver.h:667-696); tol may be NULL (kept on device) */
+int hot_eval_cn_tolerance(hot_sim* h, double eps, double dt, double* tol);
+
 #ifdef __cplusplus
 }
 #endif

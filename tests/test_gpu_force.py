@@ -1,0 +1,150 @@
+"""Parity of the CUDA force model (a9-a14, a18 tolerance) against the CPU oracle through the C ABI, plus the
+reference's own correctness notions run on the GPU path: the finite-difference test of Lib/Ziran/Sim/DiffTest.h:19-138,
+symmetry / PD of the operator (SquareMatrix.h:84-194) and BC dofs zero (ImplicitSolver.h:284-296).
+
+Tolerances (fp64): per-particle quantities 1e-11 relative to the field magnitude (the device SVD is the same Jacobi
+iteration as the oracle's, but nvcc contracts FMAs differently from gcc); scattered DOF vectors 1e-11 of the field
+magnitude (different summation order); energies 1e-12 relative.
+"""
+import numpy as np
+import pytest
+
+from hot_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, tol=1e-11):
+    np.testing.assert_allclose(a, b, rtol=0, atol=tol * max(np.abs(b).max(), 1e-300))
+
+
+CASES = {
+    "small": lambda: scenes.block((4, 5, 4), 0.04, ppc=6, seed=4, E=1e4),
+    "ragged": lambda: scenes.block((7, 5, 9), 0.02, ppc=5, seed=6),
+    "dense_cells": lambda: scenes.block((4, 4, 4), 0.04, ppc=40, seed=8),
+    "c1_box": lambda: scenes.config_c1(),
+}
+
+
+def _pair(hot, oracle, sc, project=True, gravity=(0, -9.8, 0), dt=2e-3):
+    g = hot.MpmSimulationB200(sc["dx"])
+    o = oracle.OracleSim(sc["dx"])
+    for s in (g, o):
+        s.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
+        s.set_dt_gravity(dt, gravity)
+        s.set_project(project)
+        s.sortParticlesAndPolluteGrid()
+        s.particlesToGrid()
+        s.backupStrain()
+    return g, o
+
+
+def _floor_bc(o):
+    coord = o.get_id2coord()
+    bc = np.nonzero(coord[:, 1] <= coord[:, 1].min() + 1)[0].astype(np.int32)
+    return bc
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("project", [True, False])
+def test_update_state_residual_multiply_parity(hot, oracle, case, project):
+    sc = CASES[case]()
+    g, o = _pair(hot, oracle, sc, project=project)
+    n = o.num_nodes
+    assert g.num_nodes == n
+    bc = _floor_bc(o)
+    rng = np.random.default_rng(11)
+    dv_bc = 0.01 * (rng.random((len(bc), 3)) - 0.5)
+    for s in (g, o):
+        s.set_bc(bc, P=np.zeros((len(bc), 9)), dv_bc=dv_bc)
+    _close(g.get_dv(), o.get_dv(), 1e-15)
+    dv = o.get_dv() + 0.2 * (rng.random((n, 3)) - 0.5)
+    eg, eo = g.updateState(dv), o.updateState(dv)
+    assert abs(eg - eo) <= 1e-12 * abs(eo)
+    Sg, Fg = g.get_stress(); So, Fo = o.get_stress()
+    _close(Fg, Fo, 1e-13)
+    _close(Sg, So)
+    rg, ro = g.computeResidual(), o.computeResidual()
+    _close(rg, ro)
+    assert np.abs(rg[bc]).max() == 0.0
+    x = rng.random((n, 3)) - 0.5
+    _close(g.multiply(x), o.multiply(x))
+    _close(g.project(x), o.project(x), 1e-15)
+
+
+def test_slip_bc_mode_parity(hot, oracle):
+    sc = CASES["small"]()
+    g, o = _pair(hot, oracle, sc)
+    n = o.num_nodes
+    bc = _floor_bc(o)
+    rng = np.random.default_rng(3)
+    # slip on a tilted plane for half of the nodes: R rotates the normal onto x (MpmSimulationBase.h:278)
+    nrm = np.array([0.2, 1.0, -0.1]); nrm /= np.linalg.norm(nrm)
+    v = np.cross(nrm, [1.0, 0, 0]); s_, c_ = np.linalg.norm(v), nrm[0]
+    vx = np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+    R = np.eye(3) + vx + vx @ vx * ((1 - c_) / s_ ** 2)
+    assert np.allclose(R @ nrm, [1, 0, 0])
+    Rs = np.tile(R.T.reshape(1, 9), (len(bc), 1)); Ris = np.tile(R.reshape(1, 9), (len(bc), 1))  # column-major R, R^-1 = R^T
+    slip = (np.arange(len(bc)) % 2).astype(np.int32)
+    for s in (g, o):
+        s.set_bc(bc, R=Rs, Rinv=Ris, slip=slip, mode=1)
+    dv = o.get_dv() + 0.1 * (rng.random((n, 3)) - 0.5)
+    g.updateState(dv); o.updateState(dv)
+    rg, ro = g.computeResidual(), o.computeResidual()
+    _close(rg, ro)
+    assert np.abs(rg[bc][slip == 0]).max() == 0 and np.abs(rg[bc][slip == 1][:, 0]).max() == 0
+
+
+def test_cn_tolerance_parity(hot, oracle):
+    sc = CASES["ragged"]()
+    sc["mu"] = sc["mu"] * (1 + np.arange(len(sc["mu"])) % 3)   # non-uniform material
+    g, o = _pair(hot, oracle, sc)
+    _close(g.evaluatePerNodeCNTolerance(1e-7, 2e-3), o.evaluatePerNodeCNTolerance(1e-7, 2e-3), 1e-12)
+
+
+def test_diff_test_on_gpu(hot, oracle):
+    """DiffTest.h on the CUDA path: residual = -dE/d(dv), multiply = -d(residual)/d(dv) (unprojected Hessian)."""
+    sc = CASES["small"]()
+    g, o = _pair(hot, oracle, sc, project=False)
+    n = g.num_nodes
+    rng = np.random.default_rng(123)
+    g.set_bc(np.zeros(0, dtype=np.int32))
+    dv0 = g.get_dv() + 0.3 * (rng.random((n, 3)) - 0.5)
+    d = rng.random((n, 3)) - 0.5
+    errs_e, errs_h = [], []
+    for h in (1e-3, 5e-4):
+        ep = g.updateState(dv0 + h * d); rp = g.computeResidual()
+        em = g.updateState(dv0 - h * d); rm = g.computeResidual()
+        g.updateState(dv0); r0 = g.computeResidual(); Ad = g.multiply(d)
+        errs_e.append(abs((ep - em) / (2 * h) + (r0 * d).sum()) / abs((r0 * d).sum()))
+        errs_h.append(np.abs((rp - rm) / (2 * h) + Ad).max() / np.abs(Ad).max())
+    assert errs_e[0] < 1e-5 and errs_h[0] < 1e-4
+    assert errs_e[1] < errs_e[0] * 0.5 or errs_e[1] < 1e-8
+    assert errs_h[1] < errs_h[0] * 0.5 or errs_h[1] < 1e-8
+
+
+def test_operator_symmetric_pd_on_gpu(hot, oracle):
+    sc = CASES["ragged"]()
+    g, o = _pair(hot, oracle, sc, project=True)
+    n = g.num_nodes
+    rng = np.random.default_rng(5)
+    g.set_bc(np.zeros(0, dtype=np.int32))
+    g.updateState(g.get_dv() + 0.5 * (rng.random((n, 3)) - 0.5))
+    x, y = rng.random((n, 3)) - 0.5, rng.random((n, 3)) - 0.5
+    Ax, Ay = g.multiply(x), g.multiply(y)
+    assert abs((y * Ax).sum() - (x * Ay).sum()) < 1e-10 * abs((y * Ax).sum())
+    assert (x * Ax).sum() > 0
+
+
+def test_call_order_errors(hot):
+    sc = CASES["small"]()
+    g = hot.MpmSimulationB200(sc["dx"])
+    g.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
+    g.sortParticlesAndPolluteGrid(); g.particlesToGrid()
+    with pytest.raises(hot.HotError):
+        g.updateState()          # no backupStrain yet
+    g.backupStrain()
+    with pytest.raises(hot.HotError):
+        g.computeResidual()      # no updateState yet
+    with pytest.raises(hot.HotError):
+        g.set_bc(np.array([g.num_nodes], dtype=np.int32))
