@@ -505,3 +505,4 @@ int orc_g2p(void* h, double dt, int* flags)
 } // extern "C"
 
 #include "oracle_force.inl"
+#include "oracle_matrix.inl"

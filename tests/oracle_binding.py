@@ -233,3 +233,98 @@ def _add_force_methods(cls):
 
 
 _add_force_methods(OracleSim)
+
+
+# ---- assembled matrix / multigrid (oracle_matrix.inl) --------------------------------------------------------
+def _add_matrix_methods(cls):
+    _ip = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    def buildMatrix(self, bcproject=True):
+        self._check(_lib.orc_build_matrix(_vp(self._h), int(bcproject)))
+
+    def buildDiagonal(self, Ainv=1):
+        out = np.empty((self.num_nodes, 9))
+        self._check(_lib.orc_build_diagonal(_vp(self._h), int(Ainv), _p(out)))
+        return out
+
+    def get_matrix(self):
+        n = self.num_nodes
+        col = np.empty((n, 125), dtype=np.int32); val = np.empty((n, 125, 9))
+        self._check(_lib.orc_get_matrix(_vp(self._h), _ip(col), _p(val)))
+        return col, val
+
+    def buildMultigrid(self, levels=3, smoother=5, coarseSolver=2, Ainv=1, times=1, levelscale=0, topomega=0.1):
+        self._check(_lib.orc_build_mg(_vp(self._h), levels, smoother, coarseSolver, Ainv, times, levelscale, C.c_double(topomega)))
+
+    def level_dofs(self):
+        L = _lib.orc_mg_levels(_vp(self._h))
+        out = (C.c_int * L)()
+        self._check(_lib.orc_get_level_dofs(_vp(self._h), out))
+        return list(out)
+
+    def level_coords(self, level):
+        out = np.empty((self.level_dofs()[level], 3), dtype=np.int32)
+        self._check(_lib.orc_get_level_coords(_vp(self._h), level, _ip(out)))
+        return out
+
+    def level_matrix(self, level, kind=0):
+        cs = C.c_int(0)
+        self._check(_lib.orc_get_level_matrix(_vp(self._h), level, kind, C.byref(cs), None, None))
+        d = self.level_dofs()
+        rows = d[level + 1] if kind == 2 else d[level]
+        col = np.empty((rows, cs.value), dtype=np.int32); val = np.empty((rows, cs.value, 9))
+        self._check(_lib.orc_get_level_matrix(_vp(self._h), level, kind, C.byref(cs), _ip(col), _p(val)))
+        return col, val
+
+    def level_diagonal(self, level):
+        n = self.level_dofs()[level]
+        D = np.empty((n, 9)); Di = np.empty((n, 9))
+        self._check(_lib.orc_get_level_diagonal(_vp(self._h), level, _p(D), _p(Di)))
+        return D, Di
+
+    def color_order(self, level):
+        out = np.empty((self.level_dofs()[level], 3), dtype=np.int32)
+        self._check(_lib.orc_get_color_order(_vp(self._h), level, _ip(out)))
+        return out
+
+    def spmv(self, level, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        b = np.empty_like(x)
+        self._check(_lib.orc_spmv(_vp(self._h), level, _p(x), _p(b)))
+        return b
+
+    def restrict(self, level, fine):
+        fine = np.ascontiguousarray(fine, dtype=np.float64)
+        out = np.empty((self.level_dofs()[level + 1], 3))
+        self._check(_lib.orc_restrict(_vp(self._h), level, _p(fine), _p(out)))
+        return out
+
+    def prolong(self, level, coarse):
+        coarse = np.ascontiguousarray(coarse, dtype=np.float64)
+        out = np.empty((self.level_dofs()[level], 3))
+        self._check(_lib.orc_prolong(_vp(self._h), level, _p(coarse), _p(out)))
+        return out
+
+    def smooth(self, level, kind, u, r, iterations, tolerance=0.0, initial_residual=None):
+        u = np.ascontiguousarray(u, dtype=np.float64).copy(); r = np.ascontiguousarray(r, dtype=np.float64).copy()
+        ir = None if initial_residual is None else np.ascontiguousarray(initial_residual, dtype=np.float64)
+        self._check(_lib.orc_smooth(_vp(self._h), level, kind, _p(u), _p(r), iterations, C.c_double(tolerance), _p(ir)))
+        return u, r
+
+    def vcycle(self, r):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        out = np.empty_like(r)
+        self._check(_lib.orc_vcycle(_vp(self._h), _p(r), _p(out)))
+        return out
+
+    def vcycle_timing(self):
+        t = np.zeros((10, 4)); it = C.c_int(0)
+        self._check(_lib.orc_vcycle_timing(_vp(self._h), _p(t), C.byref(it)))
+        return t, it.value
+
+    for k, v in list(locals().items()):
+        if callable(v) and not k.startswith("_") and k != "cls":
+            setattr(cls, k, v)
+
+
+_add_matrix_methods(OracleSim)
