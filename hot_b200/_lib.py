@@ -79,6 +79,23 @@ def load_library(path=LIB_PATH):
         "hot_project": (C.c_int, [vp, vp]),
         "hot_hessian_apply_mf": (C.c_int, [vp, vp, vp]),
         "hot_eval_cn_tolerance": (C.c_int, [vp, C.c_double, C.c_double, vp]),
+        "hot_build_matrix": (C.c_int, [vp, C.c_int]),
+        "hot_get_matrix": (C.c_int, [vp, vp, vp]),
+        "hot_build_diagonal": (C.c_int, [vp, C.c_int, vp]),
+        "hot_build_mg": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+        "hot_mg_levels": (C.c_int, [vp]),
+        "hot_get_level_dofs": (C.c_int, [vp, _c_int_p]),
+        "hot_get_level_coords": (C.c_int, [vp, C.c_int, vp]),
+        "hot_get_level_matrix": (C.c_int, [vp, C.c_int, C.c_int, _c_int_p, vp, vp]),
+        "hot_get_level_diagonal": (C.c_int, [vp, C.c_int, vp, vp]),
+        "hot_get_gs_schedule": (C.c_int, [vp, C.c_int, _c_int_p, _c_int_p, vp, vp]),
+        "hot_spmv": (C.c_int, [vp, C.c_int, vp, vp]),
+        "hot_restrict": (C.c_int, [vp, C.c_int, vp, vp]),
+        "hot_prolong": (C.c_int, [vp, C.c_int, vp, vp]),
+        "hot_smooth": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_double, vp]),
+        "hot_vcycle": (C.c_int, [vp, vp, vp]),
+        "hot_vcycle_timing": (C.c_int, [vp, vp, _c_int_p]),
+        "hot_vcycle_bench": (C.c_int, [vp, C.c_int, _c_double_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -1,14 +1,7 @@
 // extern "C" entry points of include/hot_b200.h: argument checking, host<->device marshalling, dispatch.
-#include "../../include/hot_b200.h"
-#include "sim.h"
+#include "api_internal.h"
 
 using namespace hot;
-
-struct hot_sim : public hot::Sim {
-    DevBuf<double> stage; // AoS staging for host<->device particle marshalling
-    DevBuf<unsigned long long> stage_u;
-    DevBuf<int> stage_i;
-};
 
 namespace {
 
@@ -85,16 +78,6 @@ __global__ void k_export_grid(long n, size_t gs, const int* __restrict__ idx, co
     v_aos[3 * a] = v[a];
     v_aos[3 * a + 1] = v[gs + a];
     v_aos[3 * a + 2] = v[2 * gs + a];
-}
-__global__ void k_id2coord(int n_nodes, const int* __restrict__ dof_slot, const uint32_t* __restrict__ page_id, int* __restrict__ coord)
-{
-    int id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= n_nodes) return;
-    int a = dof_slot[id];
-    uint64_t off = ((uint64_t)page_id[a / Geo::E] << 12) | ((uint64_t)(a % Geo::E) << Geo::data_bits);
-    coord[3 * id] = (int)bit_pack(off, Geo::xmask);
-    coord[3 * id + 1] = (int)bit_pack(off, Geo::ymask);
-    coord[3 * id + 2] = (int)bit_pack(off, Geo::zmask);
 }
 
 template <class T>
@@ -339,8 +322,8 @@ int hot_get_id2coord(hot_sim* s, int* coord)
     const int n = s->num_nodes;
     if (n == 0) return 0;
     HOT_CUDA(s->stage_i.reserve(3 * (size_t)n));
-    k_id2coord<<<nblk(n), TPB, 0, s->stream>>>(n, s->dof_slot.p, s->page_id.p, s->stage_i.p);
-    HOT_LAUNCHED(s);
+    int rc = fill_id2coord(s, s->stage_i.p);
+    if (rc) return rc;
     return d2h(s, coord, s->stage_i.p, 3 * (size_t)n);
 }
 

@@ -1,0 +1,902 @@
+// a16-a20: Galerkin multigrid on the device - hierarchy build, block-row SpMV, restriction / prolongation,
+// 8-colour block Gauss-Seidel, Jacobi / optimal-Jacobi / PCG smoothers, V-cycle.
+//
+// Reference: MultigridBuilder::build (Projects/multigrid/MultigridPreconditioner.h:553-703), linear_weight_template
+// (:445-466), SquareMatrix::{multiply, buildDiagonal, buildCoarseMatrix, buildTransposeMatrix, comp}
+// (SquareMatrix.h:39-46,301-324,477-487,526-607), MultigridOperator::{jacobi_smooth, optimal_jacobi_smooth, cg_smooth,
+// gs_smooth, operator()} (MultigridPreconditioner.h:160-226,266-318,362-421), setup_logic / setup_parameters (:480-551).
+//
+// Re-design for the GPU
+//  * rows are coordinate-addressed on every level (slot = 5^3 stencil offset), so the Galerkin triple product needs no
+//    hash maps: thread (coarse row I, slot) sums  w_a w_b A_f[2I+a][slot(2(I-J)+a-b)]  over the <= 27 x 27 children pairs;
+//  * the serial first-touch numbering of coarse nodes and the (colour, first-seen block, first-seen node) sweep order are
+//    reproduced with stable radix sorts + run heads (same trick as the page list in sort.cu), so coarse DOF ids and the
+//    Gauss-Seidel sequence are identical to the reference's;
+//  * SpMV / GS are warp-per-row over the padded row layout documented in sim.h (coalesced 256-byte requests).
+#include "sim.h"
+#include "reduce.cuh"
+#include <cub/cub.cuh>
+
+namespace hot {
+namespace {
+
+constexpr int TPB = 256;
+inline int nblk(long n) { return (int)((n + TPB - 1) / TPB); }
+constexpr int W = MGLevel::W;
+constexpr uint64_t NOKEY = ~0ull;
+
+template <class F>
+int with_tmp(Sim* s, F f)
+{
+    size_t bytes = 0;
+    cudaError_t e = f((void*)nullptr, bytes);
+    if (e != cudaSuccess) return cuda_fail(s, e, "cub size query");
+    e = s->cub_tmp.reserve(bytes + 16);
+    if (e != cudaSuccess) return cuda_fail(s, e, "cub temp alloc");
+    e = f((void*)s->cub_tmp.p, bytes);
+    if (e != cudaSuccess) return cuda_fail(s, e, "cub run");
+    s->launches += 1;
+    return 0;
+}
+
+__host__ __device__ inline uint64_t coord_key(int x, int y, int z) { return ((uint64_t)x << 24) | ((uint64_t)y << 12) | (uint64_t)z; }
+
+__device__ inline int find_node(const uint64_t* __restrict__ keys, const int* __restrict__ ids, int n, uint64_t key)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < n && keys[lo] == key) ? ids[lo] : -1;
+}
+
+__global__ void k_coord_keys(int n, const int* __restrict__ coord, uint64_t* __restrict__ key, int* __restrict__ id)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    key[i] = coord_key(coord[3 * i], coord[3 * i + 1], coord[3 * i + 2]);
+    id[i] = i;
+}
+
+// candidates of the coarse node set, MultigridPreconditioner.h:630-668: position i*8 + q reproduces the serial visiting
+// order (fine ids ascending, new_x outer / new_z inner); zero-weight candidates get NOKEY
+__global__ void k_coarse_candidates(int n, const int* __restrict__ coord, uint64_t* __restrict__ key, int* __restrict__ pos)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 8) return;
+    const int i = t >> 3, q = t & 7;
+    const int x = coord[3 * i], y = coord[3 * i + 1], z = coord[3 * i + 2];
+    const int qx = q >> 2, qy = (q >> 1) & 1, qz = q & 1;
+    const bool nonzero = (qx == 0 || (x & 1)) && (qy == 0 || (y & 1)) && (qz == 0 || (z & 1));
+    key[t] = nonzero ? coord_key(x / 2 + qx, y / 2 + qy, z / 2 + qz) : NOKEY;
+    pos[t] = t;
+}
+__global__ void k_head_flags64(long n, const uint64_t* __restrict__ k, int* __restrict__ flag)
+{
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    flag[s] = (k[s] != NOKEY) && ((s == 0) || (k[s] != k[s - 1]));
+}
+__global__ void k_iota(long n, int* __restrict__ v)
+{
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) v[s] = (int)s;
+}
+// order[c] = index into the ascending key list of the c-th coarse node (first-touch order)
+__global__ void k_coarse_finish(int nc, const int* __restrict__ order, const uint64_t* __restrict__ key_asc, int* __restrict__ coord,
+    int* __restrict__ id_sorted)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    const int j = order[c];
+    const uint64_t k = key_asc[j];
+    coord[3 * c] = (int)(k >> 24);
+    coord[3 * c + 1] = (int)((k >> 12) & 0xfff);
+    coord[3 * c + 2] = (int)(k & 0xfff);
+    id_sorted[j] = c;
+}
+
+// P rows: 8 slots (x/2 + {0,1})^3, trilinear weights w * I3; zero-weight slots alias slot 0's column (:640-647)
+__global__ void k_build_P(int n, const int* __restrict__ coord, const uint64_t* __restrict__ ckeys, const int* __restrict__ cids, int nc,
+    int* __restrict__ pcol, double* __restrict__ pw)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = coord[3 * i], y = coord[3 * i + 1], z = coord[3 * i + 2];
+    int c0 = 0;
+    for (int q = 0; q < 8; ++q) {
+        const int qx = q >> 2, qy = (q >> 1) & 1, qz = q & 1;
+        const bool nonzero = (qx == 0 || (x & 1)) && (qy == 0 || (y & 1)) && (qz == 0 || (z & 1));
+        int c = c0;
+        double w = 0.0;
+        if (nonzero) {
+            c = find_node(ckeys, cids, nc, coord_key(x / 2 + qx, y / 2 + qy, z / 2 + qz));
+            w = ((x & 1) ? 0.5 : 1.0) * ((y & 1) ? 0.5 : 1.0) * ((z & 1) ? 0.5 : 1.0);
+        }
+        if (q == 0) c0 = c;
+        pcol[(size_t)i * 8 + q] = c;
+        pw[(size_t)i * 8 + q] = w;
+    }
+}
+// R = P^T rows: children 2I + a, a in {-1,0,1}^3, weight prod (a == 0 ? 1 : 1/2); 27 entries padded to 32
+__global__ void k_build_R(int nc, const int* __restrict__ ccoord, const uint64_t* __restrict__ fkeys, const int* __restrict__ fids, int nf,
+    int* __restrict__ rcol, double* __restrict__ rw)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nc * 32) return;
+    const int I = t >> 5, k = t & 31;
+    int c = 0;
+    double w = 0.0;
+    if (k < 27) {
+        const int ax = k / 9 - 1, ay = (k / 3) % 3 - 1, az = k % 3 - 1;
+        const int x = 2 * ccoord[3 * I] + ax, y = 2 * ccoord[3 * I + 1] + ay, z = 2 * ccoord[3 * I + 2] + az;
+        if (x >= 0 && y >= 0 && z >= 0) {
+            const int f = find_node(fkeys, fids, nf, coord_key(x, y, z));
+            if (f >= 0) {
+                c = f;
+                w = (ax ? 0.5 : 1.0) * (ay ? 0.5 : 1.0) * (az ? 0.5 : 1.0);
+            }
+        }
+    }
+    rcol[t] = c;
+    rw[t] = w;
+}
+
+// Galerkin product A_c = R (A_f P), one CTA (128 threads = padded slots) per coarse row
+__global__ void __launch_bounds__(W) k_galerkin(int nc, const int* __restrict__ ccoord, const uint64_t* __restrict__ ckeys,
+    const int* __restrict__ cids, const int* __restrict__ rcol, const double* __restrict__ rw, const double* __restrict__ fval,
+    int* __restrict__ ccol, double* __restrict__ cval)
+{
+    const int I = blockIdx.x, s = threadIdx.x;
+    __shared__ int s_child[27];
+    __shared__ double s_w[27];
+    if (s < 27) {
+        s_child[s] = rcol[(size_t)I * 32 + s];
+        s_w[s] = rw[(size_t)I * 32 + s];
+    }
+    __syncthreads();
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int J = I;
+    if (s < 125) {
+        const int Dx = s / 25 - 2, Dy = (s / 5) % 5 - 2, Dz = s % 5 - 2; // coord_I - coord_J
+        const int jx = ccoord[3 * I] - Dx, jy = ccoord[3 * I + 1] - Dy, jz = ccoord[3 * I + 2] - Dz;
+        int found = -1;
+        if (jx >= 0 && jy >= 0 && jz >= 0) found = find_node(ckeys, cids, nc, coord_key(jx, jy, jz));
+        if (found >= 0) {
+            J = found;
+            for (int k = 0; k < 27; ++k) {
+                const double wa = s_w[k];
+                if (wa == 0.0) continue;
+                const int ax = k / 9 - 1, ay = (k / 3) % 3 - 1, az = k % 3 - 1;
+                const double* row = fval + (size_t)s_child[k] * 9 * W;
+                for (int bx = -1; bx <= 1; ++bx) {
+                    const int ex = 2 * Dx + ax - bx;
+                    if (ex < -2 || ex > 2) continue;
+                    for (int by = -1; by <= 1; ++by) {
+                        const int ey = 2 * Dy + ay - by;
+                        if (ey < -2 || ey > 2) continue;
+                        for (int bz = -1; bz <= 1; ++bz) {
+                            const int ez = 2 * Dz + az - bz;
+                            if (ez < -2 || ez > 2) continue;
+                            const double w = wa * (bx ? 0.5 : 1.0) * (by ? 0.5 : 1.0) * (bz ? 0.5 : 1.0);
+                            const int fs = (ex + 2) * 25 + (ey + 2) * 5 + (ez + 2);
+#pragma unroll
+                            for (int q = 0; q < 9; ++q) acc[q] += w * row[q * W + fs];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    ccol[(size_t)I * W + s] = J;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) cval[((size_t)I * 9 + q) * W + s] = acc[q];
+}
+
+__device__ __forceinline__ void inv3(const double* A, double* B)
+{
+    const double c0 = A[4] * A[8] - A[7] * A[5], c1 = A[7] * A[2] - A[1] * A[8], c2 = A[1] * A[5] - A[4] * A[2];
+    const double det = A[0] * c0 + A[3] * c1 + A[6] * c2;
+    B[0] = c0 / det; B[1] = c1 / det; B[2] = c2 / det;
+    B[3] = (A[6] * A[5] - A[3] * A[8]) / det; B[4] = (A[0] * A[8] - A[6] * A[2]) / det; B[5] = (A[3] * A[2] - A[0] * A[5]) / det;
+    B[6] = (A[3] * A[7] - A[6] * A[4]) / det; B[7] = (A[6] * A[1] - A[0] * A[7]) / det; B[8] = (A[0] * A[4] - A[3] * A[1]) / det;
+}
+// SquareMatrix::buildDiagonal: D_i = the self block (slot 62), its inverse by -Ainv
+__global__ void k_level_diagonal(int n, int Ainv, const double* __restrict__ val, double* __restrict__ diag, double* __restrict__ dinv)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a[9], b[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) a[q] = val[((size_t)i * 9 + q) * W + 62];
+    if (Ainv == 0) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) b[q] = (q == 0 || q == 4 || q == 8) ? 1.0 / a[q] : 0.0;
+    }
+    else inv3(a, b);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        diag[9 * (size_t)i + q] = a[q];
+        dinv[9 * (size_t)i + q] = b[q];
+    }
+}
+
+// ---- Gauss-Seidel schedule ---------------------------------------------------------------------------------------------
+__global__ void k_block_keys(int n, const int* __restrict__ coord, uint32_t* __restrict__ key, int* __restrict__ id)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    key[i] = ((uint32_t)(coord[3 * i] >> 2) << 20) | ((uint32_t)(coord[3 * i + 1] >> 2) << 10) | (uint32_t)(coord[3 * i + 2] >> 2);
+    id[i] = i;
+}
+__global__ void k_head_flags32(int n, const uint32_t* __restrict__ k, int* __restrict__ flag)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) flag[s] = (s == 0) || (k[s] != k[s - 1]);
+}
+// key2 = colour << 32 | first (smallest) node id of the 4^3 block: sorting by it gives (colour, first-seen block) order
+__global__ void k_sweep_keys(int n, const uint32_t* __restrict__ bkey_sorted, const int* __restrict__ id_sorted, const int* __restrict__ seg_incl,
+    const int* __restrict__ head_pos, uint64_t* __restrict__ key2)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t b = bkey_sorted[p];
+    const uint32_t color = (((b >> 20) & 1) << 2) | (((b >> 10) & 1) << 1) | (b & 1);
+    const int first_id = id_sorted[head_pos[seg_incl[p] - 1]];
+    key2[p] = ((uint64_t)color << 32) | (uint32_t)first_id;
+}
+__global__ void k_head_flags_key2(int n, const uint64_t* __restrict__ k, int* __restrict__ flag, int* __restrict__ color_count)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const bool head = (s == 0) || (k[s] != k[s - 1]);
+    flag[s] = head;
+    if (head) atomicAdd(color_count + (int)(k[s] >> 32), 1);
+}
+__global__ void k_rank(int n, const int* __restrict__ seq, int* __restrict__ rank)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) rank[seq[p]] = p;
+}
+
+// ---- operators ---------------------------------------------------------------------------------------------------------
+// SquareMatrix::multiply: one warp per block row.  mode 0: b = A x; mode 1: b -= A x
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_spmv(int n, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
+    double* __restrict__ b)
+{
+    const int row = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const int* c = col + (size_t)row * W;
+    const double* v = val + (size_t)row * 9 * W;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int t = 0; t < W / 32; ++t) {
+        const int s = lane + 32 * t;
+        const int j = c[s];
+        const double x0 = x[3 * (size_t)j], x1 = x[3 * (size_t)j + 1], x2 = x[3 * (size_t)j + 2];
+        a0 += v[s] * x0 + v[3 * W + s] * x1 + v[6 * W + s] * x2;
+        a1 += v[W + s] * x0 + v[4 * W + s] * x1 + v[7 * W + s] * x2;
+        a2 += v[2 * W + s] * x0 + v[5 * W + s] * x1 + v[8 * W + s] * x2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o);
+        a1 += __shfl_down_sync(0xffffffffu, a1, o);
+        a2 += __shfl_down_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+        double* o = b + 3 * (size_t)row;
+        if (MODE == 0) { o[0] = a0; o[1] = a1; o[2] = a2; }
+        else { o[0] -= a0; o[1] -= a1; o[2] -= a2; }
+    }
+}
+
+// restriction: coarse_I = sum_k rw[I,k] fine[rcol[I,k]], one warp per coarse node
+__global__ void __launch_bounds__(TPB) k_restrict(int nc, const int* __restrict__ rcol, const double* __restrict__ rw,
+    const double* __restrict__ fine, double* __restrict__ coarse)
+{
+    const int I = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (I >= nc) return;
+    const int j = rcol[(size_t)I * 32 + lane];
+    const double w = rw[(size_t)I * 32 + lane];
+    double a0 = w * fine[3 * (size_t)j], a1 = w * fine[3 * (size_t)j + 1], a2 = w * fine[3 * (size_t)j + 2];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o);
+        a1 += __shfl_down_sync(0xffffffffu, a1, o);
+        a2 += __shfl_down_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+        coarse[3 * (size_t)I] = a0; coarse[3 * (size_t)I + 1] = a1; coarse[3 * (size_t)I + 2] = a2;
+    }
+}
+// prolongation: fine_i = sum_q pw[i,q] coarse[pcol[i,q]]
+__global__ void k_prolong(int nf, const int* __restrict__ pcol, const double* __restrict__ pw, const double* __restrict__ coarse,
+    double* __restrict__ fine)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int j = pcol[(size_t)i * 8 + q];
+        const double w = pw[(size_t)i * 8 + q];
+        a0 += w * coarse[3 * (size_t)j]; a1 += w * coarse[3 * (size_t)j + 1]; a2 += w * coarse[3 * (size_t)j + 2];
+    }
+    fine[3 * (size_t)i] = a0; fine[3 * (size_t)i + 1] = a1; fine[3 * (size_t)i + 2] = a2;
+}
+
+// one colour phase of gs_smooth (MultigridPreconditioner.h:276-310): one warp per 4^3 block, nodes of the block in
+// sequence, lanes over the 125 slots.  FWD: out_i = Dinv_i (rhs_i - sum_{rank j < rank i} A_ij out_j); BWD: rank j > rank i.
+template <bool FWD>
+__global__ void __launch_bounds__(128) k_gs_phase(int b0, int b1, const int* __restrict__ block_start, const int* __restrict__ seq,
+    const int* __restrict__ rank, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ dinv,
+    const double* __restrict__ rhs, double* out)
+{
+    const int b = b0 + (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (b >= b1) return;
+    const int ps = block_start[b], pe = block_start[b + 1];
+    for (int it = 0; it < pe - ps; ++it) {
+        const int p = FWD ? ps + it : pe - 1 - it;
+        const int i = seq[p];
+        const int* c = col + (size_t)i * W;
+        const double* v = val + (size_t)i * 9 * W;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int t = 0; t < W / 32; ++t) {
+            const int s = lane + 32 * t;
+            const int j = c[s];
+            const int rj = rank[j];
+            if (FWD ? rj < p : rj > p) {
+                const double x0 = out[3 * (size_t)j], x1 = out[3 * (size_t)j + 1], x2 = out[3 * (size_t)j + 2];
+                a0 += v[s] * x0 + v[3 * W + s] * x1 + v[6 * W + s] * x2;
+                a1 += v[W + s] * x0 + v[4 * W + s] * x1 + v[7 * W + s] * x2;
+                a2 += v[2 * W + s] * x0 + v[5 * W + s] * x1 + v[8 * W + s] * x2;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_down_sync(0xffffffffu, a0, o);
+            a1 += __shfl_down_sync(0xffffffffu, a1, o);
+            a2 += __shfl_down_sync(0xffffffffu, a2, o);
+        }
+        if (lane == 0) {
+            const double r0 = rhs[3 * (size_t)i] - a0, r1 = rhs[3 * (size_t)i + 1] - a1, r2 = rhs[3 * (size_t)i + 2] - a2;
+            const double* d = dinv + 9 * (size_t)i;
+            out[3 * (size_t)i] = d[0] * r0 + d[3] * r1 + d[6] * r2;
+            out[3 * (size_t)i + 1] = d[1] * r0 + d[4] * r1 + d[7] * r2;
+            out[3 * (size_t)i + 2] = d[2] * r0 + d[5] * r1 + d[8] * r2;
+        }
+        __syncwarp(); // orders lane 0's stores before the next node's loads of `out`
+    }
+}
+
+__global__ void k_block_diag_inplace(int n, const double* __restrict__ D, double* __restrict__ x)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* d = D + 9 * (size_t)i;
+    const double x0 = x[3 * (size_t)i], x1 = x[3 * (size_t)i + 1], x2 = x[3 * (size_t)i + 2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) x[3 * (size_t)i + r] = d[r] * x0 + d[r + 3] * x1 + d[r + 6] * x2;
+}
+__global__ void k_block_diag(int n, const double* __restrict__ D, const double* __restrict__ x, double* __restrict__ y, double scale)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* d = D + 9 * (size_t)i;
+    const double x0 = x[3 * (size_t)i], x1 = x[3 * (size_t)i + 1], x2 = x[3 * (size_t)i + 2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) y[3 * (size_t)i + r] = scale * (d[r] * x0 + d[r + 3] * x1 + d[r + 6] * x2);
+}
+
+// ---- BLAS-1 (K16) --------------------------------------------------------------------------------------------------------
+__global__ void k_axpy(long n, double a, const double* __restrict__ x, double* __restrict__ y)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += a * x[i];
+}
+__global__ void k_axpy_dev(long n, const double* __restrict__ num, const double* __restrict__ den, double sign, const double* __restrict__ x,
+    double* __restrict__ y)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += sign * (num[0] / den[0]) * x[i];
+}
+__global__ void k_xpay_dev(long n, const double* __restrict__ x, const double* __restrict__ num, const double* __restrict__ den,
+    double* __restrict__ y)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = x[i] + (num[0] / den[0]) * y[i];
+}
+__global__ void k_scale(long n, double a, double* __restrict__ y)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] *= a;
+}
+
+int reserve_level_vectors(Sim* s, MGLevel& L)
+{
+    const size_t m = 3 * (size_t)L.n;
+    HOT_CUDA(L.residual.reserve(m));
+    HOT_CUDA(L.initial_residual.reserve(m));
+    HOT_CUDA(L.sol.reserve(m));
+    HOT_CUDA(L.du.reserve(m));
+    HOT_CUDA(L.dAu.reserve(m));
+    HOT_CUDA(L.tmp.reserve(m));
+    return 0;
+}
+
+// (colour, first-seen block, node id) sweep order of markColors, MultigridPreconditioner.h:582-605
+int build_gs_schedule(Sim* s, MGLevel& L)
+{
+    cudaStream_t st = s->stream;
+    const int n = L.n;
+    HOT_CUDA(s->cand_key.reserve(n));
+    HOT_CUDA(s->cand_key_alt.reserve(n));
+    HOT_CUDA(s->cand_val.reserve(n));
+    HOT_CUDA(s->cand_val_alt.reserve(n));
+    HOT_CUDA(s->head_flag.reserve(n));
+    HOT_CUDA(s->scratch_i.reserve(2 * (size_t)n + 2));
+    HOT_CUDA(s->keys_alt.reserve(2 * (size_t)n));
+    HOT_CUDA(s->dcount.reserve(16));
+    HOT_CUDA(L.gs_seq.reserve(n));
+    HOT_CUDA(L.gs_rank.reserve(n));
+    HOT_CUDA(L.gs_block_start.reserve((size_t)n + 1));
+    if (!s->hcount) HOT_CUDA(cudaMallocHost((void**)&s->hcount, 32 * sizeof(int)));
+    k_block_keys<<<nblk(n), TPB, 0, st>>>(n, L.coord.p, s->cand_key.p, s->cand_val.p);
+    HOT_LAUNCHED(s);
+    int rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceRadixSort::SortPairs(t, b, s->cand_key.p, s->cand_key_alt.p, s->cand_val.p, s->cand_val_alt.p, n, 0, 30, st);
+    });
+    if (rc) return rc;
+    // segments of equal block key: inclusive scan of the head flags, head positions
+    k_head_flags32<<<nblk(n), TPB, 0, st>>>(n, s->cand_key_alt.p, s->head_flag.p);
+    HOT_LAUNCHED(s);
+    int* seg_incl = s->scratch_i.p;
+    int* head_pos = s->scratch_i.p + n;
+    rc = with_tmp(s, [&](void* t, size_t& b) { return cub::DeviceScan::InclusiveSum(t, b, s->head_flag.p, seg_incl, n, st); });
+    if (rc) return rc;
+    rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<int>(0), s->head_flag.p, head_pos, s->dcount.p, n, st);
+    });
+    if (rc) return rc;
+    uint64_t* key2 = s->keys_alt.p;
+    uint64_t* key2_sorted = s->keys_alt.p + n;
+    k_sweep_keys<<<nblk(n), TPB, 0, st>>>(n, s->cand_key_alt.p, s->cand_val_alt.p, seg_incl, head_pos, key2);
+    HOT_LAUNCHED(s);
+    rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceRadixSort::SortPairs(t, b, key2, key2_sorted, s->cand_val_alt.p, L.gs_seq.p, n, 0, 35, st);
+    });
+    if (rc) return rc;
+    HOT_CUDA(cudaMemsetAsync(s->dcount.p, 0, 16 * sizeof(int), st));
+    k_head_flags_key2<<<nblk(n), TPB, 0, st>>>(n, key2_sorted, s->head_flag.p, s->dcount.p + 1);
+    HOT_LAUNCHED(s);
+    rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceSelect::Flagged(t, b, cub::CountingInputIterator<int>(0), s->head_flag.p, L.gs_block_start.p, s->dcount.p, n, st);
+    });
+    if (rc) return rc;
+    k_rank<<<nblk(n), TPB, 0, st>>>(n, L.gs_seq.p, L.gs_rank.p);
+    HOT_LAUNCHED(s);
+    HOT_CUDA(cudaMemcpyAsync(s->hcount, s->dcount.p, 9 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    HOT_CUDA(cudaStreamSynchronize(st));
+    L.n_blocks = s->hcount[0];
+    HOT_CUDA(cudaMemcpyAsync(L.gs_block_start.p + L.n_blocks, &n, sizeof(int), cudaMemcpyHostToDevice, st));
+    HOT_CUDA(cudaStreamSynchronize(st)); // &n is a stack variable
+    L.color_first_block[0] = 0;
+    for (int c = 0; c < 8; ++c) L.color_first_block[c + 1] = L.color_first_block[c] + s->hcount[1 + c];
+    return 0;
+}
+
+int coarsen(Sim* s, MGLevel& F, MGLevel& C)
+{
+    cudaStream_t st = s->stream;
+    const int nf = F.n;
+    const long nc8 = (long)nf * 8;
+    DevBuf<uint64_t> ckey, ckey_sorted;
+    DevBuf<int> cpos, cpos_sorted, heads_pos, order;
+    DevBuf<uint64_t> heads_key;
+    HOT_CUDA(ckey.reserve(nc8));
+    HOT_CUDA(ckey_sorted.reserve(nc8));
+    HOT_CUDA(cpos.reserve(nc8));
+    HOT_CUDA(cpos_sorted.reserve(nc8));
+    HOT_CUDA(heads_pos.reserve(nc8));
+    HOT_CUDA(heads_key.reserve(nc8));
+    HOT_CUDA(order.reserve(2 * nc8));
+    HOT_CUDA(s->head_flag.reserve(nc8));
+    HOT_CUDA(s->dcount.reserve(16));
+    if (!s->hcount) HOT_CUDA(cudaMallocHost((void**)&s->hcount, 32 * sizeof(int)));
+    k_coarse_candidates<<<nblk(nc8), TPB, 0, st>>>(nf, F.coord.p, ckey.p, cpos.p);
+    HOT_LAUNCHED(s);
+    int rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceRadixSort::SortPairs(t, b, ckey.p, ckey_sorted.p, cpos.p, cpos_sorted.p, (int)nc8, 0, 64, st);
+    });
+    if (rc) return rc;
+    k_head_flags64<<<nblk(nc8), TPB, 0, st>>>(nc8, ckey_sorted.p, s->head_flag.p);
+    HOT_LAUNCHED(s);
+    rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceSelect::Flagged(t, b, ckey_sorted.p, s->head_flag.p, heads_key.p, s->dcount.p, (int)nc8, st);
+    });
+    if (rc) return rc;
+    rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceSelect::Flagged(t, b, cpos_sorted.p, s->head_flag.p, heads_pos.p, s->dcount.p, (int)nc8, st);
+    });
+    if (rc) return rc;
+    HOT_CUDA(cudaMemcpyAsync(s->hcount, s->dcount.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HOT_CUDA(cudaStreamSynchronize(st));
+    const int nc = s->hcount[0];
+    if (nc <= 0) return fail(s, "multigrid: empty coarse level");
+    C.n = nc;
+    // first-touch order = heads sorted by their first candidate position
+    int* iota = order.p;
+    int* ord = order.p + nc8;
+    k_iota<<<nblk(nc), TPB, 0, st>>>(nc, iota);
+    HOT_LAUNCHED(s);
+    rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceRadixSort::SortPairs(t, b, (const uint32_t*)heads_pos.p, (uint32_t*)cpos.p, iota, ord, nc, 0, 32, st);
+    });
+    if (rc) return rc;
+    HOT_CUDA(C.coord.reserve(3 * (size_t)nc));
+    HOT_CUDA(C.key_sorted.reserve(nc));
+    HOT_CUDA(C.id_sorted.reserve(nc));
+    HOT_CUDA(cudaMemcpyAsync(C.key_sorted.p, heads_key.p, (size_t)nc * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    k_coarse_finish<<<nblk(nc), TPB, 0, st>>>(nc, ord, heads_key.p, C.coord.p, C.id_sorted.p);
+    HOT_LAUNCHED(s);
+    // transfer operators
+    HOT_CUDA(F.pcol.reserve((size_t)nf * 8));
+    HOT_CUDA(F.pw.reserve((size_t)nf * 8));
+    HOT_CUDA(F.rcol.reserve((size_t)nc * 32));
+    HOT_CUDA(F.rw.reserve((size_t)nc * 32));
+    k_build_P<<<nblk(nf), TPB, 0, st>>>(nf, F.coord.p, C.key_sorted.p, C.id_sorted.p, nc, F.pcol.p, F.pw.p);
+    HOT_LAUNCHED(s);
+    k_build_R<<<nblk((long)nc * 32), TPB, 0, st>>>(nc, C.coord.p, F.key_sorted.p, F.id_sorted.p, nf, F.rcol.p, F.rw.p);
+    HOT_LAUNCHED(s);
+    // Galerkin product
+    HOT_CUDA(C.col.reserve((size_t)nc * W));
+    HOT_CUDA(C.val.reserve((size_t)nc * 9 * W));
+    k_galerkin<<<nc, W, 0, st>>>(nc, C.coord.p, C.key_sorted.p, C.id_sorted.p, F.rcol.p, F.rw.p, F.val.p, C.col.p, C.val.p);
+    HOT_LAUNCHED(s);
+    HOT_CUDA(cudaStreamSynchronize(st)); // the local scratch buffers are freed on return
+    return 0;
+}
+
+int finish_level(Sim* s, MGLevel& L, int Ainv, bool colors)
+{
+    HOT_CUDA(L.diag.reserve(9 * (size_t)L.n));
+    HOT_CUDA(L.dinv.reserve(9 * (size_t)L.n));
+    k_level_diagonal<<<nblk(L.n), TPB, 0, s->stream>>>(L.n, Ainv, L.val.p, L.diag.p, L.dinv.p);
+    HOT_LAUNCHED(s);
+    int rc = reserve_level_vectors(s, L);
+    if (rc) return rc;
+    if (colors) return build_gs_schedule(s, L);
+    return 0;
+}
+
+inline int regular_iters(const Sim* s, int level) { return s->mg_times + level * s->mg_levelscale; }
+inline int top_iters(const Sim* s, int level)
+{ // setup_parameters, MultigridPreconditioner.h:524-551 (topDownMGS = false)
+    if (s->mg_levels == 1) return regular_iters(s, level);
+    if (!(s->mg_coarse == 2 || s->mg_coarse == 6)) return regular_iters(s, level) * 3;
+    return 10000;
+}
+
+int level_project(Sim* s, int level, double* v)
+{ // A.project: only level 0 of a system that was not BC-projected carries the projection (:695-699)
+    if (level == 0 && !s->matrix_bcproject) return bc_project(s, v);
+    return 0;
+}
+
+int mg_scale(Sim* s, MGLevel& L, const double* r, double* mr, double scale = 1.0)
+{ // scaler_func: D^-1 r with the -Ainv flavour baked into dinv
+    k_block_diag<<<nblk(L.n), TPB, 0, s->stream>>>(L.n, L.dinv.p, r, mr, scale);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+
+#define RC(x)                  \
+    do {                       \
+        int rc__ = (x);        \
+        if (rc__) return rc__; \
+    } while (0)
+
+int smooth_jacobi(Sim* s, int level, double* u, double* r, int iterations)
+{
+    MGLevel& L = *s->levels[level];
+    const long m = 3L * L.n;
+    for (; iterations--;) {
+        RC(mg_scale(s, L, r, L.du.p, s->mg_topomega));
+        RC(vec_axpy(s, m, 1.0, L.du.p, u));
+        RC(level_spmv(s, level, L.du.p, L.dAu.p));
+        RC(level_project(s, level, L.dAu.p));
+        RC(vec_axpy(s, m, -1.0, L.dAu.p, r));
+    }
+    return 0;
+}
+int smooth_optimal_jacobi(Sim* s, int level, double* u, double* r, int iterations, double tolerance)
+{
+    MGLevel& L = *s->levels[level];
+    const long m = 3L * L.n;
+    double* sc = s->red_out.p; // device scalars
+    for (; iterations--;) {
+        double rr;
+        RC(vec_dot(s, m, r, r, sc, &rr));
+        if (sqrt(rr) < tolerance) break;
+        RC(mg_scale(s, L, r, L.du.p));
+        RC(level_spmv(s, level, L.du.p, L.dAu.p));
+        RC(level_project(s, level, L.dAu.p));
+        RC(vec_dot(s, m, L.du.p, r, sc + 1, nullptr));
+        RC(vec_dot(s, m, L.du.p, L.dAu.p, sc + 2, nullptr));
+        RC(vec_axpy_dev(s, m, sc + 1, sc + 2, 1.0, L.du.p, u));
+        RC(vec_axpy_dev(s, m, sc + 1, sc + 2, -1.0, L.dAu.p, r));
+    }
+    return 0;
+}
+// cg_smooth, MultigridPreconditioner.h:190-226: Jacobi-PCG until z.r < 0.25 z0.r0 of the restricted INITIAL residual
+int smooth_cg(Sim* s, int level, double* u, double* r, int iterations)
+{
+    MGLevel& L = *s->levels[level];
+    const long m = 3L * L.n;
+    double* sc = s->red_out.p;
+    double* z = L.tmp.p;
+    double zTrk0, zTrk;
+    RC(mg_scale(s, L, L.initial_residual.p, z));
+    RC(vec_dot(s, m, z, L.initial_residual.p, sc, &zTrk0));
+    RC(mg_scale(s, L, r, z));
+    RC(vec_copy(s, m, z, L.du.p));
+    RC(vec_dot(s, m, z, r, sc + 1, &zTrk)); // sc[1] = z.r (current)
+    const double tolerance = zTrk0 * 0.25;
+    int cnt = 0;
+    for (; iterations--;) {
+        if (zTrk < tolerance) break;
+        RC(level_spmv(s, level, L.du.p, L.dAu.p));
+        RC(level_project(s, level, L.dAu.p));
+        RC(vec_dot(s, m, L.dAu.p, L.du.p, sc + 2, nullptr));
+        RC(vec_axpy_dev(s, m, sc + 1, sc + 2, 1.0, L.du.p, u));
+        RC(vec_axpy_dev(s, m, sc + 1, sc + 2, -1.0, L.dAu.p, r));
+        RC(mg_scale(s, L, r, z));
+        HOT_CUDA(cudaMemcpyAsync(sc + 3, sc + 1, sizeof(double), cudaMemcpyDeviceToDevice, s->stream)); // zTrkPre
+        RC(vec_dot(s, m, z, r, sc + 1, &zTrk));
+        RC(vec_xpay_dev(s, m, z, sc + 1, sc + 3, L.du.p)); // du = z + beta du
+        ++cnt;
+    }
+    s->last_cg_iters = cnt;
+    return 0;
+}
+// gs_smooth, MultigridPreconditioner.h:266-318
+int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
+{
+    MGLevel& L = *s->levels[level];
+    if (L.n_blocks <= 0) return fail(s, "gs_smooth: the hierarchy was built without the colour schedule (smoother / coarseSolver 5)");
+    cudaStream_t st = s->stream;
+    const long m = 3L * L.n;
+    double* hdu = L.tmp.p;
+    iterations = (iterations + 1) >> 1;
+    for (; iterations--;) {
+        RC(vec_zero(s, m, hdu));
+        for (int c = 0; c < 8; ++c) {
+            const int b0 = L.color_first_block[c], b1 = L.color_first_block[c + 1];
+            if (b1 == b0) continue;
+            k_gs_phase<true><<<(b1 - b0 + 3) / 4, 128, 0, st>>>(b0, b1, L.gs_block_start.p, L.gs_seq.p, L.gs_rank.p, L.col.p, L.val.p, L.dinv.p, r, hdu);
+            HOT_LAUNCHED(s);
+        }
+        k_block_diag_inplace<<<nblk(L.n), TPB, 0, st>>>(L.n, L.diag.p, hdu);
+        HOT_LAUNCHED(s);
+        RC(vec_zero(s, m, L.du.p));
+        for (int c = 7; c >= 0; --c) {
+            const int b0 = L.color_first_block[c], b1 = L.color_first_block[c + 1];
+            if (b1 == b0) continue;
+            k_gs_phase<false><<<(b1 - b0 + 3) / 4, 128, 0, st>>>(b0, b1, L.gs_block_start.p, L.gs_seq.p, L.gs_rank.p, L.col.p, L.val.p, L.dinv.p, hdu,
+                L.du.p);
+            HOT_LAUNCHED(s);
+        }
+        RC(vec_axpy(s, m, 1.0, L.du.p, u));
+        RC(level_spmv(s, level, L.du.p, L.dAu.p));
+        RC(level_project(s, level, L.dAu.p));
+        RC(vec_axpy(s, m, -1.0, L.dAu.p, r));
+    }
+    return 0;
+}
+
+} // namespace
+
+// ---- vector ops -----------------------------------------------------------------------------------------------------------
+int vec_axpy(Sim* s, long n, double a, const double* x, double* y)
+{
+    if (n <= 0) return 0;
+    k_axpy<<<nblk(n), TPB, 0, s->stream>>>(n, a, x, y);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+int vec_axpy_dev(Sim* s, long n, const double* num, const double* den, double sign, const double* x, double* y)
+{
+    if (n <= 0) return 0;
+    k_axpy_dev<<<nblk(n), TPB, 0, s->stream>>>(n, num, den, sign, x, y);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+int vec_xpay_dev(Sim* s, long n, const double* x, const double* num, const double* den, double* y)
+{
+    if (n <= 0) return 0;
+    k_xpay_dev<<<nblk(n), TPB, 0, s->stream>>>(n, x, num, den, y);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+int vec_copy(Sim* s, long n, const double* x, double* y)
+{
+    HOT_CUDA(cudaMemcpyAsync(y, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    return 0;
+}
+int vec_zero(Sim* s, long n, double* y)
+{
+    HOT_CUDA(cudaMemsetAsync(y, 0, (size_t)n * sizeof(double), s->stream));
+    return 0;
+}
+int vec_scale(Sim* s, long n, double a, double* y)
+{
+    if (n <= 0) return 0;
+    k_scale<<<nblk(n), TPB, 0, s->stream>>>(n, a, y);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+int vec_dot(Sim* s, long n, const double* a, const double* b, double* dev_out, double* host_out)
+{
+    return reduce_to<1>(s, n, DotF{a, b}, dev_out, host_out);
+}
+
+// ---- hierarchy --------------------------------------------------------------------------------------------------------------
+int build_coord_map(Sim* s, MGLevel& L)
+{
+    const int n = L.n;
+    HOT_CUDA(L.key_sorted.reserve(n));
+    HOT_CUDA(L.id_sorted.reserve(n));
+    HOT_CUDA(s->keys_alt.reserve(n));
+    HOT_CUDA(s->cand_val.reserve(n));
+    k_coord_keys<<<nblk(n), TPB, 0, s->stream>>>(n, L.coord.p, s->keys_alt.p, s->cand_val.p);
+    HOT_LAUNCHED(s);
+    return with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceRadixSort::SortPairs(t, b, s->keys_alt.p, L.key_sorted.p, s->cand_val.p, L.id_sorted.p, n, 0, 36, s->stream);
+    });
+}
+
+// MultigridBuilder::build
+int build_mg(Sim* s, int levels, int smoother, int coarse_solver, int Ainv, int times, int levelscale, double topomega)
+{
+    if (!s->matrix_built) return fail(s, "buildMultigrid: call hot_build_matrix first");
+    if (levels < 1 || levels > 10) return fail(s, "Level depth exceeds 10! Too Deep!");
+    if (!s->matrix_bcproject && levels > 1) return fail(s, "multigrid needs the BC-projected system (ImplicitSolver.h:339)");
+    for (int k : {smoother, coarse_solver})
+        if (!(k == 0 || k == 1 || k == 2 || k == 5)) return fail(s, "No proper smoother is selected! (supported: 0 Jacobi, 1 optimal Jacobi, 2 PCG, 5 GS)");
+    if (!(Ainv == 0 || Ainv == 1)) return fail(s, "The Dinv function picked doesn't exist.");
+    KTime t(s, KC_TRANSFER);
+    s->mg_levels = levels; s->mg_smoother = smoother; s->mg_coarse = coarse_solver; s->mg_Ainv = Ainv; s->mg_times = times;
+    s->mg_levelscale = levelscale; s->mg_topomega = topomega;
+    while ((int)s->levels.size() < levels) s->levels.push_back(new MGLevel);
+    HOT_CUDA(s->red_out.reserve(64));
+    const bool colors = smoother == 5 || coarse_solver == 5;
+    RC(build_coord_map(s, *s->levels[0]));
+    RC(finish_level(s, *s->levels[0], Ainv, colors));
+    for (int l = 0; l + 1 < levels; ++l) {
+        RC(coarsen(s, *s->levels[l], *s->levels[l + 1]));
+        RC(finish_level(s, *s->levels[l + 1], Ainv, colors));
+    }
+    for (int l = 0; l < levels; ++l)
+        if (!colors) s->levels[l]->n_blocks = 0;
+    s->mg_built = true;
+    return 0;
+}
+
+int level_spmv(Sim* s, int level, const double* x, double* b)
+{
+    MGLevel& L = *s->levels[level];
+    KTime t(s, KC_SPMV);
+    k_spmv<0><<<nblk(32L * L.n), TPB, 0, s->stream>>>(L.n, L.col.p, L.val.p, x, b);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+static int level_spmv_sub(Sim* s, int level, const double* x, double* b)
+{
+    MGLevel& L = *s->levels[level];
+    KTime t(s, KC_SPMV);
+    k_spmv<1><<<nblk(32L * L.n), TPB, 0, s->stream>>>(L.n, L.col.p, L.val.p, x, b);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+int level_restrict(Sim* s, int level, const double* fine, double* coarse)
+{
+    MGLevel& F = *s->levels[level];
+    const int nc = s->levels[level + 1]->n;
+    KTime t(s, KC_TRANSFER);
+    k_restrict<<<nblk(32L * nc), TPB, 0, s->stream>>>(nc, F.rcol.p, F.rw.p, fine, coarse);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+int level_prolong(Sim* s, int level, const double* coarse, double* fine)
+{
+    MGLevel& F = *s->levels[level];
+    KTime t(s, KC_TRANSFER);
+    k_prolong<<<nblk(F.n), TPB, 0, s->stream>>>(F.n, F.pcol.p, F.pw.p, coarse, fine);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+
+// smoothFunc(u, r, du, dAu, A, iterations, tolerance) with the integer codes of -smoother / -coarseSolver
+int level_smooth(Sim* s, int level, int kind, double* u, double* r, int iterations, double tolerance)
+{
+    KTime t(s, KC_GS);
+    switch (kind) {
+    case 0: return smooth_jacobi(s, level, u, r, iterations);
+    case 1: return smooth_optimal_jacobi(s, level, u, r, iterations, tolerance);
+    case 2: return smooth_cg(s, level, u, r, iterations);
+    case 5: return smooth_gs(s, level, u, r, iterations);
+    default: return fail(s, "No proper smoother is selected! (supported: 0 Jacobi, 1 optimal Jacobi, 2 PCG, 5 GS)");
+    }
+}
+
+// MultigridOperator::operator(), MultigridPreconditioner.h:362-421.  `out` must not alias `in`.
+int vcycle(Sim* s, const double* in, double* out, bool timed)
+{
+    if (!s->mg_built) return fail(s, "vcycle: call hot_build_mg first");
+    cudaStream_t st = s->stream;
+    const int Lc = s->mg_levels;
+    std::vector<MGLevel*>& lv = s->levels;
+    struct Seg { int level, what; cudaEvent_t a, b; };
+    std::vector<Seg> segs;
+    auto begin = [&](int level, int what) {
+        if (!timed) return;
+        Seg g{level, what, s->timers.get(), s->timers.get()};
+        cudaEventRecord(g.a, st);
+        segs.push_back(g);
+    };
+    auto end = [&]() {
+        if (timed) cudaEventRecord(segs.back().b, st);
+    };
+    RC(vec_copy(s, 3L * lv[0]->n, in, lv[0]->residual.p)); // correctResidualProjection adds dRhs == 0
+    RC(vec_zero(s, 3L * lv[0]->n, out));
+    if (Lc > 1) RC(level_restrict(s, 0, lv[0]->residual.p, lv[1]->initial_residual.p));
+    else RC(vec_copy(s, 3L * lv[0]->n, lv[0]->residual.p, lv[0]->initial_residual.p));
+    for (int l = 1; l < Lc - 1; ++l) RC(level_restrict(s, l, lv[l]->initial_residual.p, lv[l + 1]->initial_residual.p));
+    int level;
+    for (level = 0; level < Lc - 1; ++level) {
+        double* sol = level == 0 ? out : lv[level]->sol.p;
+        begin(level, 0);
+        RC(level_smooth(s, level, s->mg_smoother, sol, lv[level]->residual.p, regular_iters(s, level), 0.0));
+        end();
+        begin(level, 1);
+        RC(level_restrict(s, level, lv[level]->residual.p, lv[level + 1]->residual.p));
+        end();
+        RC(vec_zero(s, 3L * lv[level + 1]->n, lv[level + 1]->sol.p));
+    }
+    begin(level, 0);
+    RC(level_smooth(s, level, s->mg_coarse, level == 0 ? out : lv[level]->sol.p, lv[level]->residual.p, top_iters(s, level), 0.0));
+    end();
+    for (--level; level >= 0; --level) {
+        double* sol = level == 0 ? out : lv[level]->sol.p;
+        begin(level, 2);
+        RC(level_prolong(s, level, lv[level + 1]->sol.p, lv[level]->du.p));
+        end();
+        begin(level, 3);
+        RC(vec_axpy(s, 3L * lv[level]->n, 1.0, lv[level]->du.p, sol));
+        RC(level_spmv_sub(s, level, lv[level]->du.p, lv[level]->residual.p)); // residual -= A du (dAu fused away)
+        end();
+        begin(level, 0);
+        RC(level_smooth(s, level, s->mg_smoother, sol, lv[level]->residual.p, regular_iters(s, level), 0.0));
+        end();
+    }
+    if (timed) {
+        for (int i = 0; i < 10; ++i)
+            for (int j = 0; j < 4; ++j) s->vc_ms[i][j] = 0.0;
+        HOT_CUDA(cudaStreamSynchronize(st));
+        for (Seg& g : segs) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, g.a, g.b);
+            if (g.level < 10) s->vc_ms[g.level][g.what] += ms;
+            s->timers.pool.push_back(g.a);
+            s->timers.pool.push_back(g.b);
+        }
+    }
+    return 0;
+}
+
+} // namespace hot

@@ -77,6 +77,33 @@ struct ParticleSoA {
 enum KernelClass { KC_SORT = 0, KC_P2G, KC_NUMBER, KC_G2P, KC_GATHER, KC_STRESS, KC_FORCE, KC_HESSIAN, KC_ASSEMBLE, KC_SPMV, KC_GS,
     KC_TRANSFER, KC_BLAS1, KC_COUNT };
 
+// One multigrid level (level 0 = the assembled system of a15).  Block rows of the reference's fixed-width
+// SquareMatrix (entryCol/entryVal, SquareMatrix.h:27-35) are re-laid for warp-per-row kernels:
+//   slot s = (dx+2)*25 + (dy+2)*5 + (dz+2) addresses the neighbour at coord_i - (dx,dy,dz) on EVERY level
+//   (ImplicitSolver.h:465-468; the Galerkin product keeps the 5^3 stencil, so coarse rows need no hash maps);
+//   col[i*128 + s]            neighbour DOF id (i itself where the neighbour does not exist; 125..127 padding)
+//   val[(i*9 + q)*128 + s]    entry q (column-major 3x3) of block s: a lane reads 32 consecutive slots of one q,
+//                             so a warp streams its 9 KB row with fully coalesced 256-byte requests.
+struct MGLevel {
+    static constexpr int W = 128; // padded row width (125 slots)
+    int n = 0;
+    DevBuf<int> coord; // 3n
+    DevBuf<uint64_t> key_sorted; // coordinate keys ascending ...
+    DevBuf<int> id_sorted; // ... and the node id of each
+    DevBuf<int> col;
+    DevBuf<double> val;
+    DevBuf<double> diag, dinv; // 9n each: D_i (column-major) and its inverse (block or entry-wise, -Ainv)
+    // 8-colour 4^3-block Gauss-Seidel schedule (MultigridPreconditioner.h:582-605)
+    DevBuf<int> gs_seq, gs_rank, gs_block_start; // node ids in sweep order; rank of a node; block b = gs_seq[start[b]..start[b+1])
+    int n_blocks = 0;
+    int color_first_block[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // transfer to the next coarser level: P rows (8 parents per fine node), R = P^T rows (<= 27 children, padded to 32)
+    DevBuf<int> pcol, rcol;
+    DevBuf<double> pw, rw;
+    // V-cycle work vectors (MultigridOperator::residuals/initialResiduals/sols/dus/dAus/tmps)
+    DevBuf<double> residual, initial_residual, sol, du, dAu, tmp;
+};
+
 struct Sim;
 // CUDA-event timing of one kernel class on the handle's stream (enabled by hot_timing)
 struct KTimers {
@@ -168,6 +195,18 @@ struct Sim {
     DevBuf<double> bc_P, bc_R, bc_Rinv;
     DevBuf<double> cn_tol; // per-node CN tolerance (a18)
     DevBuf<double> work[8]; // DOF-sized scratch vectors of the host-buffer entry points
+
+    // ---- assembled system + multigrid hierarchy (matrix.cu, multigrid.cu)
+    std::vector<MGLevel*> levels; // levels[0] = assembled matrix
+    bool matrix_built = false, mg_built = false, matrix_bcproject = true;
+    DevBuf<int> bc_of; // node -> BC table row or -1
+    DevBuf<double> diag_mf; // 9n: inverse diagonal blocks of the matrix-free operator (buildDiagonal)
+    // HOTSettings (Projects/multigrid/Configurations.h:18-42)
+    int mg_smoother = 5, mg_coarse = 2, mg_Ainv = 1, mg_levels = 3, mg_times = 1, mg_levelscale = 0;
+    double mg_topomega = 0.1;
+    double vc_ms[10][4]; // per-level [smooth, restrict, prolongate, merge] of the last timed V-cycle
+    int last_cg_iters = 0;
+    ~Sim();
 };
 
 int fail(Sim* s, const std::string& msg);
@@ -216,6 +255,27 @@ int bc_rotate(Sim* s, double* v, bool inverse);
 int ensure_hessian(Sim* s);
 int hessian_apply_mf(Sim* s, const double* x, double* b);
 int eval_cn_tolerance(Sim* s, double eps, double dt, double* tol);
+// matrix.cu
+int fill_id2coord(Sim* s, int* coord_dev);
+int build_matrix(Sim* s, bool bcproject);
+int build_diagonal_mf(Sim* s, int Ainv);
+int apply_block_diag(Sim* s, int n, const double* D9, const double* x, double* y);
+// multigrid.cu
+int build_mg(Sim* s, int levels, int smoother, int coarse_solver, int Ainv, int times, int levelscale, double topomega);
+int level_spmv(Sim* s, int level, const double* x, double* b);
+int level_restrict(Sim* s, int level, const double* fine, double* coarse);
+int level_prolong(Sim* s, int level, const double* coarse, double* fine);
+int level_smooth(Sim* s, int level, int kind, double* u, double* r, int iterations, double tolerance);
+int vcycle(Sim* s, const double* in, double* out, bool timed);
+int build_coord_map(Sim* s, MGLevel& L);
+// vector ops (multigrid.cu)
+int vec_axpy(Sim* s, long n, double a, const double* x, double* y); // y += a x
+int vec_axpy_dev(Sim* s, long n, const double* num, const double* den, double sign, const double* x, double* y); // y += sign*(num/den) x
+int vec_xpay_dev(Sim* s, long n, const double* x, const double* num, const double* den, double* y); // y = x + (num/den) y
+int vec_copy(Sim* s, long n, const double* x, double* y);
+int vec_zero(Sim* s, long n, double* y);
+int vec_scale(Sim* s, long n, double a, double* y);
+int vec_dot(Sim* s, long n, const double* a, const double* b, double* dev_out, double* host_out);
 
 // ---- device helpers ----------------------------------------------------------------------------------
 #ifdef __CUDACC__

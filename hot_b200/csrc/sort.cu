@@ -272,7 +272,7 @@ int sort_and_activate(Sim* s)
     HOT_CUDA(s->group_first.reserve(n + 1));
     HOT_CUDA(s->dcount.reserve(8));
     HOT_CUDA(s->Palt.reserve(n));
-    if (!s->hcount) HOT_CUDA(cudaMallocHost((void**)&s->hcount, 8 * sizeof(int)));
+    if (!s->hcount) HOT_CUDA(cudaMallocHost((void**)&s->hcount, 32 * sizeof(int)));
 
     HOT_CUDA(cudaMemsetAsync(s->dcount.p, 0, 8 * sizeof(int), st));
     const double one_over_dx = 1.0 / s->dx;

@@ -243,3 +243,109 @@ class MpmSimulationB200:
         tol = np.empty(self.num_nodes)
         self._check(self._lib.hot_eval_cn_tolerance(self._h, float(eps), float(dt), _ptr(tol)))
         return tol
+
+    # ---- assembled system / Galerkin multigrid (ImplicitSolver.h:470-603, MultigridPreconditioner.h)
+    def buildMatrix(self, bcproject=True):
+        self._check(self._lib.hot_build_matrix(self._h, int(bcproject)))
+
+    def get_matrix(self):
+        n = self.num_nodes
+        col = np.empty((n, 125), dtype=np.int32); val = np.empty((n, 125, 9))
+        self._check(self._lib.hot_get_matrix(self._h, _ptr(col), _ptr(val)))
+        return col, val
+
+    def buildDiagonal(self, Ainv=1):
+        out = np.empty((self.num_nodes, 9))
+        self._check(self._lib.hot_build_diagonal(self._h, int(Ainv), _ptr(out)))
+        return out
+
+    def buildMultigrid(self, levels=3, smoother=5, coarseSolver=2, Ainv=1, times=1, levelscale=0, topomega=0.1):
+        self._check(self._lib.hot_build_mg(self._h, levels, smoother, coarseSolver, Ainv, times, levelscale, float(topomega)))
+
+    def level_dofs(self):
+        L = self._lib.hot_mg_levels(self._h)
+        out = (C.c_int * max(L, 1))()
+        self._check(self._lib.hot_get_level_dofs(self._h, out))
+        return list(out)[:L]
+
+    def level_coords(self, level):
+        out = np.empty((self.level_dofs()[level], 3), dtype=np.int32)
+        self._check(self._lib.hot_get_level_coords(self._h, level, _ptr(out)))
+        return out
+
+    def level_matrix(self, level, kind=0):
+        """kind 0: (col, val[n,125,9]); kind 1 / 2: (col, scalar weights) of P_l / R_l"""
+        cs = C.c_int(0)
+        self._check(self._lib.hot_get_level_matrix(self._h, level, kind, C.byref(cs), None, None))
+        d = self.level_dofs()
+        rows = d[level + 1] if kind == 2 else d[level]
+        col = np.empty((rows, cs.value), dtype=np.int32)
+        val = np.empty((rows, cs.value, 9)) if kind == 0 else np.empty((rows, cs.value))
+        self._check(self._lib.hot_get_level_matrix(self._h, level, kind, C.byref(cs), _ptr(col), _ptr(val)))
+        return col, val
+
+    def level_diagonal(self, level):
+        n = self.level_dofs()[level]
+        D = np.empty((n, 9)); Di = np.empty((n, 9))
+        self._check(self._lib.hot_get_level_diagonal(self._h, level, _ptr(D), _ptr(Di)))
+        return D, Di
+
+    def gs_schedule(self, level):
+        nb = C.c_int(0); cfb = (C.c_int * 9)()
+        self._check(self._lib.hot_get_gs_schedule(self._h, level, C.byref(nb), cfb, None, None))
+        seq = np.empty(self.level_dofs()[level], dtype=np.int32); start = np.empty(nb.value + 1, dtype=np.int32)
+        self._check(self._lib.hot_get_gs_schedule(self._h, level, C.byref(nb), cfb, _ptr(seq), _ptr(start)))
+        return seq, start, list(cfb)
+
+    def color_order(self, level):
+        """(colour, block id within the colour, 1-based position in the block) per node = SquareMatrix::colorOrder"""
+        seq, start, cfb = self.gs_schedule(level)
+        out = np.empty((len(seq), 3), dtype=np.int32)
+        for c in range(8):
+            for b in range(cfb[c], cfb[c + 1]):
+                nodes = seq[start[b]:start[b + 1]]
+                out[nodes, 0] = c; out[nodes, 1] = b - cfb[c]; out[nodes, 2] = np.arange(1, len(nodes) + 1)
+        return out
+
+    def _dofvec(self, level, a):
+        return _f64(a, (self.level_dofs()[level] if self._lib.hot_mg_levels(self._h) else self.num_nodes, 3))
+
+    def spmv(self, level, x):
+        x = self._dofvec(level, x)
+        b = np.empty_like(x)
+        self._check(self._lib.hot_spmv(self._h, level, _ptr(x), _ptr(b)))
+        return b
+
+    def restrict(self, level, fine):
+        fine = self._dofvec(level, fine)
+        out = np.empty((self.level_dofs()[level + 1], 3))
+        self._check(self._lib.hot_restrict(self._h, level, _ptr(fine), _ptr(out)))
+        return out
+
+    def prolong(self, level, coarse):
+        coarse = self._dofvec(level + 1, coarse)
+        out = np.empty((self.level_dofs()[level], 3))
+        self._check(self._lib.hot_prolong(self._h, level, _ptr(coarse), _ptr(out)))
+        return out
+
+    def smooth(self, level, kind, u, r, iterations, tolerance=0.0, initial_residual=None):
+        u = self._dofvec(level, u).copy(); r = self._dofvec(level, r).copy()
+        ir = None if initial_residual is None else self._dofvec(level, initial_residual)
+        self._check(self._lib.hot_smooth(self._h, level, kind, _ptr(u), _ptr(r), iterations, float(tolerance), _ptr(ir)))
+        return u, r
+
+    def vcycle(self, r):
+        r = self._dofvec(0, r)
+        out = np.empty_like(r)
+        self._check(self._lib.hot_vcycle(self._h, _ptr(r), _ptr(out)))
+        return out
+
+    def vcycle_timing(self):
+        t = np.zeros((10, 4)); it = C.c_int(0)
+        self._check(self._lib.hot_vcycle_timing(self._h, _ptr(t), C.byref(it)))
+        return t, it.value
+
+    def vcycle_bench(self, reps):
+        ms = C.c_double(0)
+        self._check(self._lib.hot_vcycle_bench(self._h, int(reps), C.byref(ms)))
+        return ms.value / reps

@@ -121,6 +121,101 @@ int hot_hessian_apply_mf(hot_sim* h, const double* x, double* b);
 /* ImplicitSolverObjective::evaluatePerNodeCNTolerance (ImplicitSolver.h:667-696); tol may be NULL (kept on device) */
 int hot_eval_cn_tolerance(hot_sim* h, double eps, double dt, double* tol);
 
+/* ---- a15: assembled system (Projects/multigrid/ImplicitSolver.h:470-603) ------------------------------------------ */
+/* buildMatrix<bcproject>: block rows of 125 slots, slot (dx+2)*25+(dy+2)*5+(dz+2) = neighbour at coord_i - d
+ * (linearOffset :465-468), M + dt^2 K at the current trial state, BC-projected when bcproject (--bcproject). */
+int hot_build_matrix(hot_sim* h, int bcproject);
+/* entryCol (n x 125) / entryVal (n x 125 x 9, blocks column-major).  Structurally empty slots carry the row's own index
+ * with a zero block (the reference pads them with column 0 / 1 and a zero block, :568-571: same operator). */
+int hot_get_matrix(hot_sim* h, int* entryCol, double* entryVal);
+/* buildDiagonal (:605-665): inverse diagonal blocks (Ainv 1) / entries (Ainv 0) of the matrix-free operator */
+int hot_build_diagonal(hot_sim* h, int Ainv, double* diag_inv /* 9 per node, nullable */);
+
+/* ---- a16-a20: Galerkin multigrid (Projects/multigrid/MultigridPreconditioner.h) ------------------------------------ */
+/* MultigridBuilder::build :553-703 with HOTSettings {levelCnt, smoother, coarseSolver, Ainv, times, levelscale, topomega}
+ * (= -mg_level -smoother -coarseSolver -Ainv -mg_times -mg_scale -mg_jomega; integer codes 0 Jacobi, 1 optimal Jacobi,
+ * 2 PCG, 5 GS as in setup_logic :480-522; 6 Chebyshev / 7 IC are not provided) */
+int hot_build_mg(hot_sim* h, int levels, int smoother, int coarse_solver, int Ainv, int times, int levelscale, double topomega);
+int hot_mg_levels(hot_sim* h);
+int hot_get_level_dofs(hot_sim* h, int* dofs);
+int hot_get_level_coords(hot_sim* h, int level, int* coord3);
+/* kind 0: system matrix A_l (colsize 125, val 9 per entry); kind 1: prolongation P_l (colsize 8) and kind 2: restriction
+ * R_l = P_l^T (colsize 32, 27 used) with ONE scalar weight per entry (the reference stores w * I3).  col / val nullable. */
+int hot_get_level_matrix(hot_sim* h, int level, int kind, int* colsize, int* col, double* val);
+/* SquareMatrix::diagonalVal and its inverse (diagonalBlock / diagonalEntry by Ainv), SquareMatrix.h:301-324 */
+int hot_get_level_diagonal(hot_sim* h, int level, double* diagonalVal, double* diagonalInv);
+/* markColors :582-605 as a sweep schedule: nodes in (colour, first-seen block, first-seen node) order, block b =
+ * seq[block_start[b] .. block_start[b+1]), colour c = blocks [color_first_block[c], color_first_block[c+1]) */
+int hot_get_gs_schedule(hot_sim* h, int level, int* n_blocks, int* color_first_block9, int* seq, int* block_start);
+/* SquareMatrix::multiply (SquareMatrix.h:477-487) / SparseMatrix::multiply (SparseMatrixFast.h:60-73) */
+int hot_spmv(hot_sim* h, int level, const double* x, double* b);
+/* SparseMPMMatrix::transposeMultiply / multiply (MPMMultigridMatrix.h:63-70) between level and level+1 */
+int hot_restrict(hot_sim* h, int level, const double* fine, double* coarse);
+int hot_prolong(hot_sim* h, int level, const double* coarse, double* fine);
+/* smoothFunc(u, r, du, dAu, A, iterations, tolerance) (:68-73); kind = the -smoother code; u, r updated in place;
+ * initial_residual (nullable) = initialResiduals[level], the reference of the PCG stopping test (:197-209) */
+int hot_smooth(hot_sim* h, int level, int kind, double* u, double* r, int iterations, double tolerance, const double* initial_residual);
+/* MultigridOperator::operator() :362-421 */
+int hot_vcycle(hot_sim* h, const double* in, double* out);
+/* per-level [smooth, restrict, prolongate, merge] milliseconds of the last hot_vcycle (the table of :417-419), 10 x 4 */
+int hot_vcycle_timing(hot_sim* h, double* ms40, int* coarse_cg_iters);
+/* `reps` device-resident V-cycles on the right-hand side of the last hot_vcycle; total milliseconds (CUDA events) */
+int hot_vcycle_bench(hot_sim* h, int reps, double* ms_total);
+
+/* ---- a21, a22, a24: solvers and the time step ----------------------------------------------------------------------- */
+/* HOTSettings (Projects/multigrid/Configurations.h:18-42) + the solver limits MultigridSimulation / the objective hard-code
+ * (MultigridSimulation.h:97-99: newton(objective, 1, 3), lbfgs(objective, 1, 10000); ImplicitSolver.h:78: cg(10000)).
+ * Field names follow the command-line flags of Projects/multigrid/main.cpp:40-84. */
+typedef struct hot_solver_options {
+    int lsolver;        /* -lsolver: 2 = Newton + inexact PCG (PN-PCG / PN-MGPCG), 3 = L-BFGS around the V-cycle (HOT) */
+    int matfree;        /* --matfree: matrix-free apply + block-Jacobi (lsolver 2 only, README:13-15) */
+    int project;        /* --project: PSD-project the particle Hessians */
+    int bcproject;      /* --bcproject: BC-project the assembled system */
+    int linesearch;     /* --linesearch */
+    int usecn;          /* --usecn: characteristic-norm stopping test */
+    int adaptive_h;     /* --adaptiveH: rebuild the Hessian approximation every 16 L-BFGS iterations */
+    int mg_level;       /* -mg_level */
+    int mg_times;       /* -mg_times */
+    int mg_scale;       /* -mg_scale */
+    int smoother;       /* -smoother */
+    int coarse_solver;  /* -coarseSolver */
+    int Ainv;           /* -Ainv */
+    int max_newton_iterations; /* 3 */
+    int max_lbfgs_iterations;  /* 10000 */
+    int max_cg_iterations;     /* 10000 */
+    double cneps;       /* -cneps */
+    double topomega;    /* -mg_jomega */
+} hot_solver_options;
+/* fills the defaults of the HOT configuration (tog.sh:38): -lsolver 3 -Ainv 1 --project --linesearch --bcproject
+ * -mg_level 3 -mg_times 1 -coarseSolver 2 -smoother 5 --usecn -cneps 1e-7 */
+void hot_default_options(hot_solver_options* o);
+
+#define HOT_LOG_CAP 256
+/* telemetry of one backward-Euler solve: what the reference prints through ZIRAN_INFO (ImplicitSolver.h:186-207,
+ * InexactConjugateGradient.h:73-80, LBFGS.h:337-349) */
+typedef struct hot_solve_log {
+    int iterations;              /* nonlinear iterations taken (Newton steps / L-BFGS iterations) */
+    int converged;               /* shouldExitByCN returned true */
+    int n_log;                   /* entries filled below (min(iterations + 1, HOT_LOG_CAP)) */
+    int matrix_builds;           /* buildMatrix + hierarchy rebuilds */
+    int total_linear_iterations; /* PCG iterations (lsolver 2) or V-cycles (lsolver 3) */
+    int total_linesearch_probes; /* updateState calls made by lineSearch */
+    double tolerance;            /* newton.tolerance = lbfgs.tolerance = cg.tolerance (MultigridSimulation.h:199-211) */
+    double residual_norm[HOT_LOG_CAP]; /* ||r||_2 at the top of each nonlinear iteration */
+    double scaled_norm[HOT_LOG_CAP];   /* sqrt(sum |r_i|^2 / tol_i^2 / n) with --usecn, else = residual_norm */
+    double energy[HOT_LOG_CAP];        /* Ek (only with --linesearch) */
+    int linear_iterations[HOT_LOG_CAP];/* PCG iterations of that Newton step */
+} hot_solve_log;
+
+/* InexactConjugateGradient::solve (Lib/Ziran/Math/Linear/InexactConjugateGradient.h:49-103) on A = assembled matrix
+ * (matfree 0) or the matrix-free operator (matfree 1); preconditioner 0: none, 1: block/entry Jacobi of that operator,
+ * 2: multigrid V-cycle.  x is in/out (must satisfy the BCs), returns the iteration count through *iters. */
+int hot_pcg(hot_sim* h, const double* b, double* x, double tolerance, int max_iterations, int matfree, int preconditioner, int* iters);
+/* MultigridSimulation::backwardEulerStep (Projects/multigrid/MultigridSimulation.h:188-233) minus
+ * buildInitialDvAndVnForNewton, which the caller does through hot_set_bc: backupStrain, tolerances, Newton / L-BFGS solve
+ * on the device-resident dv, restoreStrain.  The result stays in the device dv (hot_get_dv) for hot_g2p. */
+int hot_backward_euler_step(hot_sim* h, const hot_solver_options* opt, hot_solve_log* log);
+
 #ifdef __cplusplus
 }
 #endif
