@@ -14,6 +14,30 @@ class LibraryMissing(RuntimeError):
 
 _lib = None
 
+HOT_LOG_CAP = 256
+
+
+class SolverOptions(C.Structure):
+    """hot_solver_options of include/hot_b200.h (field names = the reference's command-line flags)"""
+    _fields_ = [(n, C.c_int) for n in ("lsolver", "matfree", "project", "bcproject", "linesearch", "usecn", "adaptive_h", "mg_level",
+                                       "mg_times", "mg_scale", "smoother", "coarse_solver", "Ainv", "max_newton_iterations",
+                                       "max_lbfgs_iterations", "max_cg_iterations")] + [("cneps", C.c_double), ("topomega", C.c_double)]
+
+
+class SolveLog(C.Structure):
+    """hot_solve_log of include/hot_b200.h"""
+    _fields_ = [(n, C.c_int) for n in ("iterations", "converged", "n_log", "matrix_builds", "total_linear_iterations",
+                                       "total_linesearch_probes")] + [
+        ("tolerance", C.c_double), ("residual_norm", C.c_double * HOT_LOG_CAP), ("scaled_norm", C.c_double * HOT_LOG_CAP),
+        ("energy", C.c_double * HOT_LOG_CAP), ("linear_iterations", C.c_int * HOT_LOG_CAP)]
+
+    def as_dict(self):
+        n = self.n_log
+        return dict(iterations=self.iterations, converged=bool(self.converged), matrix_builds=self.matrix_builds,
+                    total_linear_iterations=self.total_linear_iterations, total_linesearch_probes=self.total_linesearch_probes,
+                    tolerance=self.tolerance, residual_norm=list(self.residual_norm[:n]), scaled_norm=list(self.scaled_norm[:n]),
+                    energy=list(self.energy[:n]), linear_iterations=list(self.linear_iterations[:n]))
+
 _c_double_p = C.POINTER(C.c_double)
 _c_int_p = C.POINTER(C.c_int)
 _c_u64_p = C.POINTER(C.c_ulonglong)
@@ -96,6 +120,10 @@ def load_library(path=LIB_PATH):
         "hot_vcycle": (C.c_int, [vp, vp, vp]),
         "hot_vcycle_timing": (C.c_int, [vp, vp, _c_int_p]),
         "hot_vcycle_bench": (C.c_int, [vp, C.c_int, _c_double_p]),
+        "hot_default_options": (None, [C.POINTER(SolverOptions)]),
+        "hot_pcg": (C.c_int, [vp, vp, vp, C.c_double, C.c_int, C.c_int, C.c_int, _c_int_p]),
+        "hot_get_dv0": (C.c_int, [vp, vp]),
+        "hot_backward_euler_step": (C.c_int, [vp, C.POINTER(SolverOptions), C.POINTER(SolveLog)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

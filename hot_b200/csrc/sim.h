@@ -204,6 +204,8 @@ struct Sim {
     // HOTSettings (Projects/multigrid/Configurations.h:18-42)
     int mg_smoother = 5, mg_coarse = 2, mg_Ainv = 1, mg_levels = 3, mg_times = 1, mg_levelscale = 0;
     double mg_topomega = 0.1;
+    DevBuf<double> sv[32]; // solver work vectors (solver.cu)
+    bool dv0_valid = false;
     double vc_ms[10][4]; // per-level [smooth, restrict, prolongate, merge] of the last timed V-cycle
     int last_cg_iters = 0;
     ~Sim();

@@ -7,7 +7,7 @@ libhot_b200.so on the GPU; numpy arrays are only the caller-owned host buffers o
 import ctypes as C
 import numpy as np
 
-from ._lib import load_library
+from ._lib import load_library, SolverOptions, SolveLog
 
 
 class HotError(RuntimeError):
@@ -349,3 +349,32 @@ class MpmSimulationB200:
         ms = C.c_double(0)
         self._check(self._lib.hot_vcycle_bench(self._h, int(reps), C.byref(ms)))
         return ms.value / reps
+
+    # ---- solvers (InexactConjugateGradient.h, LBFGS.h, ExtendedNewtonsMethod.h, MultigridSimulation.h:188-233)
+    def default_options(self, **kw):
+        o = SolverOptions()
+        self._lib.hot_default_options(C.byref(o))
+        for k, v in kw.items():
+            if not hasattr(o, k):
+                raise AttributeError(k)
+            setattr(o, k, v)
+        return o
+
+    def pcg(self, b, x0=None, tolerance=1.0, max_iterations=10000, matfree=False, preconditioner=1):
+        b = _f64(b, (self.num_nodes, 3))
+        x = np.zeros_like(b) if x0 is None else _f64(x0, (self.num_nodes, 3)).copy()
+        it = C.c_int(0)
+        self._check(self._lib.hot_pcg(self._h, _ptr(b), _ptr(x), float(tolerance), int(max_iterations), int(matfree),
+                                      int(preconditioner), C.byref(it)))
+        return x, it.value
+
+    def backwardEulerStep(self, options=None, **kw):
+        o = options if options is not None else self.default_options(**kw)
+        log = SolveLog()
+        self._check(self._lib.hot_backward_euler_step(self._h, C.byref(o), C.byref(log)))
+        return log.as_dict()
+
+    def get_dv0(self):
+        out = np.empty((self.num_nodes, 3))
+        self._check(self._lib.hot_get_dv0(self._h, _ptr(out)))
+        return out

@@ -215,6 +215,11 @@ int hot_pcg(hot_sim* h, const double* b, double* x, double tolerance, int max_it
  * buildInitialDvAndVnForNewton, which the caller does through hot_set_bc: backupStrain, tolerances, Newton / L-BFGS solve
  * on the device-resident dv, restoreStrain.  The result stays in the device dv (hot_get_dv) for hot_g2p. */
 int hot_backward_euler_step(hot_sim* h, const hot_solver_options* opt, hot_solve_log* log);
+/* ImplicitSolverObjective::dv0 (ImplicitSolver.h:58): the last iterate the line search accepted.  With --linesearch the
+ * reference exits with dv = dv0 + one more copy of the last step (x aliases simulation.dv, LBFGS.h:412-413 /
+ * ExtendedNewtonsMethod.h:62 run after lineSearch already moved the nodes) and hot_backward_euler_step reproduces that;
+ * without --linesearch dv0 == dv. */
+int hot_get_dv0(hot_sim* h, double* dv0);
 
 #ifdef __cplusplus
 }

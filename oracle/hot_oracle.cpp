@@ -506,3 +506,4 @@ int orc_g2p(void* h, double dt, int* flags)
 
 #include "oracle_force.inl"
 #include "oracle_matrix.inl"
+#include "oracle_solver.inl"

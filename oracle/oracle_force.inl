@@ -424,7 +424,7 @@ int orc_update_state(void* h, const double* dv, double* energy)
     ForceState& f = force_of(s);
     if (f.Fn.size() != s->F.size()) return fail(s, "orc_update_state: call orc_backup_strain first (startBackwardEuler)");
     const long n = s->N;
-    if (dv) s->dv.assign(dv, dv + 3 * (size_t)s->num_nodes); // moveNodes
+    if (dv && dv != s->dv.data()) s->dv.assign(dv, dv + 3 * (size_t)s->num_nodes); // moveNodes (no-op when dv aliases, :738-739)
     std::vector<double> field(3 * (size_t)s->num_nodes);
     for (size_t q = 0; q < field.size(); ++q) field[q] = s->vn[q] + s->dv[q];
     eval_interpolant_and_gradient(s, field.data(), f.vp, f.gradV);

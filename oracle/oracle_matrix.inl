@@ -186,6 +186,7 @@ struct MatrixState {
     bool mg_built = false;
     double last_timing[10][4];
     int last_cg_iters = 0;
+    std::vector<double> dv0; // accepted iterate of the last backward-Euler solve
 };
 
 MatrixState& matrix_of(Sim* s)

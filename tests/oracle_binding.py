@@ -328,3 +328,43 @@ def _add_matrix_methods(cls):
 
 
 _add_matrix_methods(OracleSim)
+
+
+# ---- solvers (oracle_solver.inl) -----------------------------------------------------------------------------
+def _add_solver_methods(cls):
+    from hot_b200._lib import SolverOptions, SolveLog   # plain ctypes mirrors of the public C structs
+
+    def default_options(self, **kw):
+        o = SolverOptions()
+        _lib.orc_default_options(C.byref(o))
+        for k, v in kw.items():
+            if not hasattr(o, k):
+                raise AttributeError(k)
+            setattr(o, k, v)
+        return o
+
+    def pcg(self, b, x0=None, tolerance=1.0, max_iterations=10000, matfree=False, preconditioner=1):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros_like(b) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+        it = C.c_int(0)
+        self._check(_lib.orc_pcg(_vp(self._h), _p(b), _p(x), C.c_double(tolerance), int(max_iterations), int(matfree),
+                                 int(preconditioner), C.byref(it)))
+        return x, it.value
+
+    def backwardEulerStep(self, options=None, **kw):
+        o = options if options is not None else self.default_options(**kw)
+        log = SolveLog()
+        self._check(_lib.orc_backward_euler_step(_vp(self._h), C.byref(o), C.byref(log)))
+        return log.as_dict()
+
+    def get_dv0(self):
+        out = np.empty((self.num_nodes, 3))
+        self._check(_lib.orc_get_dv0(_vp(self._h), _p(out)))
+        return out
+
+    for k, v in list(locals().items()):
+        if callable(v) and not k.startswith("_") and k not in ("cls", "SolverOptions", "SolveLog"):
+            setattr(cls, k, v)
+
+
+_add_solver_methods(OracleSim)
