@@ -132,6 +132,64 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+SOLVER_DT = 1.0 / 480  # a tenth of the scene's frame_dt = 1/48 (MultigridInit3D.h:571-664) so the perturbed synthetic state stays uninverted
+
+
+def end_cap_bc(coord, cells=8):
+    """sticky end caps of the bar like the two capped cylinders of test 777001 (MultigridInit3D.h:571-664)"""
+    y = coord[:, 1]
+    return np.nonzero((y <= y.min() + cells) | (y >= y.max() - cells))[0].astype(np.int32)
+
+
+def solver_leg(sim, sc, args):
+    """V-cycle ms (BASELINE.json metric, second half) + the other solver-side kernels on the same resident state."""
+    n = len(sc["mass"])
+    sim.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
+    sim.set_dt_gravity(SOLVER_DT, (0.0, 0.0, 0.0))
+    sim.sortParticlesAndPolluteGrid()
+    nn = sim.particlesToGrid()
+    bc = end_cap_bc(sim.get_id2coord())
+    sim.set_bc(bc, P=np.zeros((len(bc), 9)), dv_bc=np.zeros((len(bc), 3)))
+    sim.backupStrain()
+    sim.updateState()
+    reps = max(3, min(args.steps, 20))
+    out = {"dt": SOLVER_DT, "bc_nodes": int(len(bc)), "grid_nodes": nn}
+    peak, _ = peaks()
+    ms = sim.op_bench("hessian_apply", reps)
+    hb = 416 * n + 56 * nn
+    out["hessian_apply_mf"] = {"ms": ms, "alg_bytes": hb, "alg_GBps": hb / ms / 1e6, "frac": hb / ms / 1e6 / peak}
+    ms = sim.op_bench("update_state", reps)
+    out["update_state"] = {"ms": ms}
+    ms = sim.op_bench("residual", reps)
+    rb = 96 * n + 56 * nn
+    out["residual"] = {"ms": ms, "alg_bytes": rb, "alg_GBps": rb / ms / 1e6, "frac": rb / ms / 1e6 / peak}
+    sim.buildMatrix(True)
+    out["build_matrix_ms"] = sim.op_bench("build_matrix", 2)
+    sim.buildMultigrid(levels=3, smoother=5, coarseSolver=2, Ainv=1, times=1)
+    out["build_mg_ms"] = sim.op_bench("build_mg", 2)
+    dofs = sim.level_dofs()
+    nnzb = [sim.level_nnz_blocks(l) for l in range(3)]
+    spmv_bytes = [76 * nnzb[l] + 48 * dofs[l] for l in range(3)]
+    out["levels"] = {"dofs": dofs, "nnz_blocks": nnzb}
+    out["spmv"] = []
+    out["gs_smooth"] = []
+    for l in range(3):
+        ms = sim.op_bench("spmv", reps, level=l)
+        out["spmv"].append({"level": l, "ms": ms, "alg_bytes": spmv_bytes[l], "alg_GBps": spmv_bytes[l] / ms / 1e6, "frac": spmv_bytes[l] / ms / 1e6 / peak})
+        ms = sim.op_bench("smooth", reps, level=l)
+        gb = 3 * spmv_bytes[l] + 5 * 24 * dofs[l]
+        out["gs_smooth"].append({"level": l, "ms": ms, "alg_bytes": gb, "alg_GBps": gb / ms / 1e6, "frac": gb / ms / 1e6 / peak})
+    r = sim.computeResidual()
+    sim.vcycle(r)
+    table, cg_it = sim.vcycle_timing()
+    vms = sim.vcycle_bench(reps)
+    vb = 7 * (spmv_bytes[0] + spmv_bytes[1]) + cg_it * spmv_bytes[2] + 30 * 24 * dofs[0]
+    out["vcycle"] = {"ms": vms, "levels": 3, "smoother": "GS(5)", "coarse": "PCG(2)", "times": 1, "coarse_cg_iters": cg_it,
+                     "alg_bytes": vb, "alg_GBps": vb / vms / 1e6, "frac": vb / vms / 1e6 / peak,
+                     "per_level_ms[smooth,restrict,prolongate,merge]": [[round(float(x), 4) for x in row] for row in table[:3]]}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -219,6 +277,8 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    solver = solver_leg(sim, sc, args) if not args.no_solver else None
+
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(n)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -259,6 +319,7 @@ def run_ours(args):
             "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "includes": "H2D from pinned host, sort, P2G, G2P(dt), D2H of X,V,C,F"},
             "gpu_launches": launches, "clocks": sampler.result(), "sort_ms": sort_ms, "wall_s_timed_loop": wall,
+            "solver_kernels": solver,
         }
         print(json.dumps(line))
     if world > 1:
@@ -273,6 +334,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
     ap.add_argument("--cpu-reps", type=int, default=5)
+    ap.add_argument("--no-solver", action="store_true", help="skip the solver-side kernel timings (V-cycle ms, Hessian apply ...)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -109,6 +109,7 @@ def load_library(path=LIB_PATH):
         "hot_build_mg": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
         "hot_mg_levels": (C.c_int, [vp]),
         "hot_get_level_dofs": (C.c_int, [vp, _c_int_p]),
+        "hot_level_nnz_blocks": (C.c_int, [vp, C.c_int, _c_i64_p]),
         "hot_get_level_coords": (C.c_int, [vp, C.c_int, vp]),
         "hot_get_level_matrix": (C.c_int, [vp, C.c_int, C.c_int, _c_int_p, vp, vp]),
         "hot_get_level_diagonal": (C.c_int, [vp, C.c_int, vp, vp]),
@@ -120,6 +121,7 @@ def load_library(path=LIB_PATH):
         "hot_vcycle": (C.c_int, [vp, vp, vp]),
         "hot_vcycle_timing": (C.c_int, [vp, vp, _c_int_p]),
         "hot_vcycle_bench": (C.c_int, [vp, C.c_int, _c_double_p]),
+        "hot_op_bench": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, _c_double_p]),
         "hot_default_options": (None, [C.POINTER(SolverOptions)]),
         "hot_pcg": (C.c_int, [vp, vp, vp, C.c_double, C.c_int, C.c_int, C.c_int, _c_int_p]),
         "hot_get_dv0": (C.c_int, [vp, vp]),

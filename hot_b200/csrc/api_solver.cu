@@ -1,6 +1,8 @@
 // extern "C" entry points of the assembled-matrix / multigrid / solver part of include/hot_b200.h: host-buffer
 // marshalling around the device-resident operators of matrix.cu, multigrid.cu and solver.cu.
 #include "api_internal.h"
+#include <algorithm>
+#include "reduce.cuh"
 
 using namespace hot;
 
@@ -37,6 +39,11 @@ __global__ void k_export_rows(int n, const int* __restrict__ col, const double* 
 #pragma unroll
         for (int q = 0; q < 9; ++q) eval[9 * (size_t)t + q] = val[((size_t)i * 9 + q) * W + s];
 }
+
+struct NnzF { // entries whose column is not the row itself (empty slots alias the row, the diagonal is counted apart)
+    const int* col;
+    __device__ void operator()(long t, double (&acc)[1]) const { acc[0] += col[t] != (int)(t / W) ? 1.0 : 0.0; }
+};
 
 int check_level(hot_sim* s, int level, const char* who, bool need_coarser = false)
 {
@@ -83,6 +90,17 @@ int hot_get_level_dofs(hot_sim* s, int* dofs)
 {
     if (!s->mg_built) return fail(s, "hot_get_level_dofs: call hot_build_mg first");
     for (int l = 0; l < s->mg_levels; ++l) dofs[l] = s->levels[l]->n;
+    return 0;
+}
+// structurally non-zero 3x3 blocks of A_level (the nnzb of the SpMV roofline): stored neighbours + the diagonal
+int hot_level_nnz_blocks(hot_sim* s, int level, long long* nnzb)
+{
+    if (!s->matrix_built || level < 0 || level >= (int)s->levels.size() || (level > 0 && !s->mg_built)) return fail(s, "hot_level_nnz_blocks: bad level");
+    MGLevel& L = *s->levels[level];
+    double h = 0;
+    int rc = reduce_to<1>(s, (long)L.n * W, NnzF{L.col.p}, nullptr, &h);
+    if (rc) return rc;
+    *nnzb = (long long)(h + 0.5) + L.n;
     return 0;
 }
 int hot_get_level_coords(hot_sim* s, int level, int* coord)
@@ -232,6 +250,47 @@ int hot_vcycle_bench(hot_sim* s, int reps, double* ms_total)
     cudaEventRecord(a, s->stream);
     for (int i = 0; i < reps; ++i) {
         int rc = vcycle(s, s->work[1].p, s->work[2].p, false);
+        if (rc) return rc;
+    }
+    cudaEventRecord(b, s->stream);
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    if (ms_total) *ms_total = ms;
+    s->timers.pool.push_back(a);
+    s->timers.pool.push_back(b);
+    return 0;
+}
+
+// `reps` device-resident applications of one operator of the path, timed with CUDA events on the handle's stream:
+// op 0 matrix-free Hessian apply (a13), 1 block SpMV on `level` (a16), 2 updateState without energy (a9-a11),
+// 3 computeResidual (a12), 4 one smoother call of the configured -smoother on `level` (a18), 5 hot_build_matrix (a15),
+// 6 hot_build_mg with the current settings (a17)
+int hot_op_bench(hot_sim* s, int op, int level, int reps, double* ms_total)
+{
+    if (!s->state_valid) return fail(s, "hot_op_bench: call hot_update_state first");
+    if ((op == 1 || op == 4) && (level < 0 || level >= (int)s->levels.size() || !s->matrix_built || (op == 4 && !s->mg_built)))
+        return fail(s, "hot_op_bench: matrix / hierarchy not built or bad level");
+    if (op == 6 && !s->matrix_built) return fail(s, "hot_op_bench: matrix not built");
+    const size_t m = 3 * (size_t)((op == 1 || op == 4) ? s->levels[level]->n : s->num_nodes);
+    HOT_CUDA(s->work[3].reserve(m));
+    HOT_CUDA(s->work[4].reserve(m));
+    HOT_CUDA(cudaMemsetAsync(s->work[4].p, 0, m * sizeof(double), s->stream));
+    if (op != 4) HOT_CUDA(cudaMemcpyAsync(s->work[3].p, s->dv.p, std::min(m, 3 * (size_t)s->num_nodes) * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    cudaEvent_t a = s->timers.get(), b = s->timers.get();
+    cudaEventRecord(a, s->stream);
+    for (int i = 0; i < reps; ++i) {
+        int rc = 0;
+        switch (op) {
+        case 0: rc = hessian_apply_mf(s, s->work[3].p, s->work[4].p); break;
+        case 1: rc = level_spmv(s, level, s->work[3].p, s->work[4].p); break;
+        case 2: rc = update_state(s, false, nullptr); break;
+        case 3: rc = compute_residual(s, s->work[4].p); break;
+        case 4: rc = level_smooth(s, level, s->mg_smoother, s->work[4].p, s->work[3].p, s->mg_times, 0.0); break;
+        case 5: rc = build_matrix(s, s->matrix_bcproject); break;
+        case 6: rc = build_mg(s, s->mg_levels, s->mg_smoother, s->mg_coarse, s->mg_Ainv, s->mg_times, s->mg_levelscale, s->mg_topomega); break;
+        default: rc = fail(s, "hot_op_bench: unknown op");
+        }
         if (rc) return rc;
     }
     cudaEventRecord(b, s->stream);

@@ -260,6 +260,12 @@ __global__ void k_rank(int n, const int* __restrict__ seq, int* __restrict__ ran
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n) rank[seq[p]] = p;
 }
+// sweep rank of every stored neighbour, in the row layout of col: saves the dependent rank[col] gather in the sweeps
+__global__ void k_colrank(long n_entries, const int* __restrict__ col, const int* __restrict__ rank, int* __restrict__ colrank)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_entries) colrank[t] = rank[col[t]];
+}
 
 // ---- operators ---------------------------------------------------------------------------------------------------------
 // SquareMatrix::multiply: one warp per block row.  mode 0: b = A x; mode 1: b -= A x
@@ -374,6 +380,177 @@ __global__ void __launch_bounds__(128) k_gs_phase(int b0, int b1, const int* __r
     }
 }
 
+
+// One colour phase of gs_smooth, two-phase form (the version the V-cycle uses).  One CTA per 4^3 block:
+//   phase A (all warps, bandwidth-bound): every row of the block streams its 125 slots once.  Couplings to nodes that the
+//     sweep has already finalised OUTSIDE the block (earlier colours) are multiplied with their values and folded into the
+//     right-hand side; couplings to nodes of the SAME block that precede the row are parked in shared memory as a dense
+//     lower-triangular array of 3x3 blocks (<= 64*63/2 blocks = 145 KB);
+//   phase B (one warp, latency-bound but on-chip): right-looking block forward substitution over the <= 64 nodes, each lane
+//     owning two rows, the pivot value broadcast by shuffle.
+// Same-colour blocks are >= 5 nodes apart, beyond the stencil radius 2, so this equals the reference's node-serial sweep
+// (MultigridPreconditioner.h:276-310) up to the order of additions.  FWD: out_i = Dinv_i (rhs_i - sum_{rank j < rank i} A_ij out_j),
+// optionally out_scaled_i = D_i out_i (the "hdu = D hdu" pass of :292-293 fused); BWD: rank j > rank i.
+constexpr int GS_THREADS = 512;
+constexpr int GS_MAXN = 64;
+constexpr size_t GS_SMEM = (size_t)(GS_MAXN * (GS_MAXN - 1) / 2) * 9 * sizeof(double) + 2 * GS_MAXN * 3 * sizeof(double);
+
+template <bool FWD>
+__global__ void __launch_bounds__(GS_THREADS) k_gs_block(int b0, const int* __restrict__ block_start, const int* __restrict__ seq,
+    const int* __restrict__ colrank, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ dinv,
+    const double* __restrict__ diag, const double* __restrict__ rhs, double* out, double* __restrict__ out_scaled)
+{
+    extern __shared__ double gs_smem[];
+    double* Lt = gs_smem;                                   // [il (il - 1) / 2 + kl][9]
+    double* s_rhs = gs_smem + (GS_MAXN * (GS_MAXN - 1) / 2) * 9; // [GS_MAXN][3]
+    double* s_x = s_rhs + GS_MAXN * 3;
+    const int b = b0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ps = block_start[b], pe = block_start[b + 1], nb = pe - ps;
+    for (int e = tid; e < nb * (nb - 1) / 2 * 9; e += GS_THREADS) Lt[e] = 0.0;
+    __syncthreads();
+    // local index in sweep order: FWD il = p - ps, BWD il = pe - 1 - p
+    for (int il = warp; il < nb; il += GS_THREADS / 32) {
+        const int p = FWD ? ps + il : pe - 1 - il;
+        const int i = seq[p];
+        const int* c = col + (size_t)i * W;
+        const int* cr = colrank + (size_t)i * W;
+        const double* v = val + (size_t)i * 9 * W;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        int jj[W / 32], rr[W / 32];
+#pragma unroll
+        for (int t = 0; t < W / 32; ++t) {
+            jj[t] = c[lane + 32 * t];
+            rr[t] = cr[lane + 32 * t];
+        }
+#pragma unroll
+        for (int t = 0; t < W / 32; ++t) {
+            const int sl = lane + 32 * t;
+            const int j = jj[t];
+            const int rj = rr[t];
+            const bool ext = FWD ? rj < ps : rj >= pe;
+            const bool inb = FWD ? (rj >= ps && rj < p) : (rj < pe && rj > p);
+            if (ext || inb) {
+                const double v0 = v[sl], v1 = v[W + sl], v2 = v[2 * W + sl], v3 = v[3 * W + sl], v4 = v[4 * W + sl], v5 = v[5 * W + sl],
+                             v6 = v[6 * W + sl], v7 = v[7 * W + sl], v8 = v[8 * W + sl];
+                if (ext) {
+                    const double x0 = out[3 * (size_t)j], x1 = out[3 * (size_t)j + 1], x2 = out[3 * (size_t)j + 2];
+                    a0 += v0 * x0 + v3 * x1 + v6 * x2;
+                    a1 += v1 * x0 + v4 * x1 + v7 * x2;
+                    a2 += v2 * x0 + v5 * x1 + v8 * x2;
+                }
+                else {
+                    const int kl = FWD ? rj - ps : pe - 1 - rj;
+                    double* d = Lt + (size_t)(il * (il - 1) / 2 + kl) * 9;
+                    d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3; d[4] = v4; d[5] = v5; d[6] = v6; d[7] = v7; d[8] = v8;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_down_sync(0xffffffffu, a0, o);
+            a1 += __shfl_down_sync(0xffffffffu, a1, o);
+            a2 += __shfl_down_sync(0xffffffffu, a2, o);
+        }
+        if (lane == 0) {
+            s_rhs[3 * il] = rhs[3 * (size_t)i] - a0;
+            s_rhs[3 * il + 1] = rhs[3 * (size_t)i + 1] - a1;
+            s_rhs[3 * il + 2] = rhs[3 * (size_t)i + 2] - a2;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double r[2][3], D[2][9];
+        int node[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int il = lane + 32 * h;
+            node[h] = -1;
+            if (il < nb) {
+                node[h] = seq[FWD ? ps + il : pe - 1 - il];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) r[h][d] = s_rhs[3 * il + d];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) D[h][q] = dinv[9 * (size_t)node[h] + q];
+            }
+        }
+        for (int k = 0; k < nb; ++k) {
+            const int owner = k & 31, h = k >> 5;
+            double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+            if (lane == owner) {
+                double Dk[9], rk[3];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) Dk[q] = h ? D[1][q] : D[0][q]; // selects, not indexing: keeps D / r in registers
+#pragma unroll
+                for (int d = 0; d < 3; ++d) rk[d] = h ? r[1][d] : r[0][d];
+                x0 = Dk[0] * rk[0] + Dk[3] * rk[1] + Dk[6] * rk[2];
+                x1 = Dk[1] * rk[0] + Dk[4] * rk[1] + Dk[7] * rk[2];
+                x2 = Dk[2] * rk[0] + Dk[5] * rk[1] + Dk[8] * rk[2];
+                s_x[3 * k] = x0; s_x[3 * k + 1] = x1; s_x[3 * k + 2] = x2;
+            }
+            x0 = __shfl_sync(0xffffffffu, x0, owner);
+            x1 = __shfl_sync(0xffffffffu, x1, owner);
+            x2 = __shfl_sync(0xffffffffu, x2, owner);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int il = lane + 32 * hh;
+                if (il > k && il < nb) {
+                    const double* l = Lt + (size_t)(il * (il - 1) / 2 + k) * 9;
+                    r[hh][0] -= l[0] * x0 + l[3] * x1 + l[6] * x2;
+                    r[hh][1] -= l[1] * x0 + l[4] * x1 + l[7] * x2;
+                    r[hh][2] -= l[2] * x0 + l[5] * x1 + l[8] * x2;
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int il = lane + 32 * h;
+            if (il < nb) {
+                const int i = node[h];
+                const double x0 = s_x[3 * il], x1 = s_x[3 * il + 1], x2 = s_x[3 * il + 2];
+                out[3 * (size_t)i] = x0; out[3 * (size_t)i + 1] = x1; out[3 * (size_t)i + 2] = x2;
+                if (FWD && out_scaled) {
+                    const double* d = diag + 9 * (size_t)i;
+                    out_scaled[3 * (size_t)i] = d[0] * x0 + d[3] * x1 + d[6] * x2;
+                    out_scaled[3 * (size_t)i + 1] = d[1] * x0 + d[4] * x1 + d[7] * x2;
+                    out_scaled[3 * (size_t)i + 2] = d[2] * x0 + d[5] * x1 + d[8] * x2;
+                }
+            }
+        }
+    }
+}
+
+// u += du and r -= A du in one pass over A (the tail of gs_smooth, :311-314); one warp per row
+__global__ void __launch_bounds__(TPB) k_spmv_update(int n, const int* __restrict__ col, const double* __restrict__ val,
+    const double* __restrict__ du, double* __restrict__ u, double* __restrict__ r)
+{
+    const int row = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const int* c = col + (size_t)row * W;
+    const double* v = val + (size_t)row * 9 * W;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int t = 0; t < W / 32; ++t) {
+        const int s = lane + 32 * t;
+        const int j = c[s];
+        const double x0 = du[3 * (size_t)j], x1 = du[3 * (size_t)j + 1], x2 = du[3 * (size_t)j + 2];
+        a0 += v[s] * x0 + v[3 * W + s] * x1 + v[6 * W + s] * x2;
+        a1 += v[W + s] * x0 + v[4 * W + s] * x1 + v[7 * W + s] * x2;
+        a2 += v[2 * W + s] * x0 + v[5 * W + s] * x1 + v[8 * W + s] * x2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o);
+        a1 += __shfl_down_sync(0xffffffffu, a1, o);
+        a2 += __shfl_down_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+        const size_t o = 3 * (size_t)row;
+        r[o] -= a0; r[o + 1] -= a1; r[o + 2] -= a2;
+        u[o] += du[o]; u[o + 1] += du[o + 1]; u[o + 2] += du[o + 2];
+    }
+}
+
 __global__ void k_block_diag_inplace(int n, const double* __restrict__ D, double* __restrict__ x)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -479,6 +656,9 @@ int build_gs_schedule(Sim* s, MGLevel& L)
     });
     if (rc) return rc;
     k_rank<<<nblk(n), TPB, 0, st>>>(n, L.gs_seq.p, L.gs_rank.p);
+    HOT_LAUNCHED(s);
+    HOT_CUDA(L.gs_colrank.reserve((size_t)n * W));
+    k_colrank<<<nblk((long)n * W), TPB, 0, st>>>((long)n * W, L.col.p, L.gs_rank.p, L.gs_colrank.p);
     HOT_LAUNCHED(s);
     HOT_CUDA(cudaMemcpyAsync(s->hcount, s->dcount.p, 9 * sizeof(int), cudaMemcpyDeviceToHost, st));
     HOT_CUDA(cudaStreamSynchronize(st));
@@ -670,31 +850,41 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
     MGLevel& L = *s->levels[level];
     if (L.n_blocks <= 0) return fail(s, "gs_smooth: the hierarchy was built without the colour schedule (smoother / coarseSolver 5)");
     cudaStream_t st = s->stream;
-    const long m = 3L * L.n;
-    double* hdu = L.tmp.p;
+    double* hdu = L.tmp.p;   // unscaled forward solution (what the forward sweep itself reads)
+    double* dhdu = L.dAu.p;  // D hdu, the right-hand side of the backward sweep
+    static bool attr_set = false;
+    if (!attr_set) {
+        HOT_CUDA(cudaFuncSetAttribute(k_gs_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
+        HOT_CUDA(cudaFuncSetAttribute(k_gs_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
+        attr_set = true;
+    }
+    const bool project = level == 0 && !s->matrix_bcproject;
     iterations = (iterations + 1) >> 1;
     for (; iterations--;) {
-        RC(vec_zero(s, m, hdu));
         for (int c = 0; c < 8; ++c) {
             const int b0 = L.color_first_block[c], b1 = L.color_first_block[c + 1];
             if (b1 == b0) continue;
-            k_gs_phase<true><<<(b1 - b0 + 3) / 4, 128, 0, st>>>(b0, b1, L.gs_block_start.p, L.gs_seq.p, L.gs_rank.p, L.col.p, L.val.p, L.dinv.p, r, hdu);
+            k_gs_block<true><<<b1 - b0, GS_THREADS, GS_SMEM, st>>>(b0, L.gs_block_start.p, L.gs_seq.p, L.gs_colrank.p, L.col.p, L.val.p, L.dinv.p,
+                L.diag.p, r, hdu, dhdu);
             HOT_LAUNCHED(s);
         }
-        k_block_diag_inplace<<<nblk(L.n), TPB, 0, st>>>(L.n, L.diag.p, hdu);
-        HOT_LAUNCHED(s);
-        RC(vec_zero(s, m, L.du.p));
         for (int c = 7; c >= 0; --c) {
             const int b0 = L.color_first_block[c], b1 = L.color_first_block[c + 1];
             if (b1 == b0) continue;
-            k_gs_phase<false><<<(b1 - b0 + 3) / 4, 128, 0, st>>>(b0, b1, L.gs_block_start.p, L.gs_seq.p, L.gs_rank.p, L.col.p, L.val.p, L.dinv.p, hdu,
-                L.du.p);
+            k_gs_block<false><<<b1 - b0, GS_THREADS, GS_SMEM, st>>>(b0, L.gs_block_start.p, L.gs_seq.p, L.gs_colrank.p, L.col.p, L.val.p, L.dinv.p,
+                L.diag.p, dhdu, L.du.p, nullptr);
             HOT_LAUNCHED(s);
         }
-        RC(vec_axpy(s, m, 1.0, L.du.p, u));
-        RC(level_spmv(s, level, L.du.p, L.dAu.p));
-        RC(level_project(s, level, L.dAu.p));
-        RC(vec_axpy(s, m, -1.0, L.dAu.p, r));
+        if (!project) {
+            k_spmv_update<<<nblk(32L * L.n), TPB, 0, st>>>(L.n, L.col.p, L.val.p, L.du.p, u, r);
+            HOT_LAUNCHED(s);
+        }
+        else {
+            RC(vec_axpy(s, 3L * L.n, 1.0, L.du.p, u));
+            RC(level_spmv(s, level, L.du.p, L.dAu.p));
+            RC(level_project(s, level, L.dAu.p));
+            RC(vec_axpy(s, 3L * L.n, -1.0, L.dAu.p, r));
+        }
     }
     return 0;
 }

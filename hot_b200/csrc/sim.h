@@ -94,6 +94,7 @@ struct MGLevel {
     DevBuf<double> val;
     DevBuf<double> diag, dinv; // 9n each: D_i (column-major) and its inverse (block or entry-wise, -Ainv)
     // 8-colour 4^3-block Gauss-Seidel schedule (MultigridPreconditioner.h:582-605)
+    DevBuf<int> gs_colrank; // rank of col[i*128+s], same layout as col
     DevBuf<int> gs_seq, gs_rank, gs_block_start; // node ids in sweep order; rank of a node; block b = gs_seq[start[b]..start[b+1])
     int n_blocks = 0;
     int color_first_block[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};

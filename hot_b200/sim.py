@@ -378,3 +378,16 @@ class MpmSimulationB200:
         out = np.empty((self.num_nodes, 3))
         self._check(self._lib.hot_get_dv0(self._h, _ptr(out)))
         return out
+
+    OPS = {"hessian_apply": 0, "spmv": 1, "update_state": 2, "residual": 3, "smooth": 4, "build_matrix": 5, "build_mg": 6}
+
+    def op_bench(self, op, reps=10, level=0):
+        """milliseconds per application of one device-resident operator (CUDA events)"""
+        ms = C.c_double(0)
+        self._check(self._lib.hot_op_bench(self._h, self.OPS[op], int(level), int(reps), C.byref(ms)))
+        return ms.value / reps
+
+    def level_nnz_blocks(self, level):
+        n = C.c_longlong(0)
+        self._check(self._lib.hot_level_nnz_blocks(self._h, int(level), C.byref(n)))
+        return n.value

@@ -139,6 +139,8 @@ int hot_build_mg(hot_sim* h, int levels, int smoother, int coarse_solver, int Ai
 int hot_mg_levels(hot_sim* h);
 int hot_get_level_dofs(hot_sim* h, int* dofs);
 int hot_get_level_coords(hot_sim* h, int level, int* coord3);
+/* number of structurally non-zero 3x3 blocks of A_level (the reference stores 125 per row regardless) */
+int hot_level_nnz_blocks(hot_sim* h, int level, long long* nnzb);
 /* kind 0: system matrix A_l (colsize 125, val 9 per entry); kind 1: prolongation P_l (colsize 8) and kind 2: restriction
  * R_l = P_l^T (colsize 32, 27 used) with ONE scalar weight per entry (the reference stores w * I3).  col / val nullable. */
 int hot_get_level_matrix(hot_sim* h, int level, int kind, int* colsize, int* col, double* val);
@@ -161,6 +163,10 @@ int hot_vcycle(hot_sim* h, const double* in, double* out);
 int hot_vcycle_timing(hot_sim* h, double* ms40, int* coarse_cg_iters);
 /* `reps` device-resident V-cycles on the right-hand side of the last hot_vcycle; total milliseconds (CUDA events) */
 int hot_vcycle_bench(hot_sim* h, int reps, double* ms_total);
+/* `reps` device-resident applications of one operator (measurement hook of bench.py): op 0 matrix-free Hessian apply,
+ * 1 block SpMV on `level`, 2 updateState, 3 computeResidual, 4 one -smoother call on `level`, 5 hot_build_matrix,
+ * 6 hot_build_mg; total milliseconds (CUDA events on the handle's stream) */
+int hot_op_bench(hot_sim* h, int op, int level, int reps, double* ms_total);
 
 /* ---- a21, a22, a24: solvers and the time step ----------------------------------------------------------------------- */
 /* HOTSettings (Projects/multigrid/Configurations.h:18-42) + the solver limits MultigridSimulation / the objective hard-code
