@@ -102,6 +102,8 @@ def load_library(path=LIB_PATH):
         "hot_compute_residual": (C.c_int, [vp, vp]),
         "hot_project": (C.c_int, [vp, vp]),
         "hot_hessian_apply_mf": (C.c_int, [vp, vp, vp]),
+        "hot_add_scaled_forces": (C.c_int, [vp, C.c_double, vp]),
+        "hot_add_scaled_force_differentials": (C.c_int, [vp, C.c_double, vp, vp]),
         "hot_eval_cn_tolerance": (C.c_int, [vp, C.c_double, C.c_double, vp]),
         "hot_build_matrix": (C.c_int, [vp, C.c_int]),
         "hot_get_matrix": (C.c_int, [vp, vp, vp]),

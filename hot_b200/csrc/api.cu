@@ -436,6 +436,26 @@ int hot_hessian_apply_mf(hot_sim* s, const double* x, double* b)
     return d2h(s, b, s->work[2].p, 3 * (size_t)s->num_nodes);
 }
 
+int hot_add_scaled_forces(hot_sim* s, double scale, double* f)
+{
+    if (!s->state_valid) return fail(s, "hot_add_scaled_forces: call hot_update_state first");
+    int rc = upload_dof(s, s->work[1], f);
+    if (rc) return rc;
+    rc = add_scaled_forces(s, scale, s->work[1].p);
+    if (rc) return rc;
+    return d2h(s, f, s->work[1].p, 3 * (size_t)s->num_nodes);
+}
+int hot_add_scaled_force_differentials(hot_sim* s, double scale, const double* x, double* f)
+{
+    if (!s->state_valid) return fail(s, "hot_add_scaled_force_differentials: call hot_update_state first");
+    int rc = upload_dof(s, s->work[1], x);
+    if (!rc) rc = upload_dof(s, s->work[2], f);
+    if (rc) return rc;
+    rc = add_scaled_force_differentials(s, scale, s->work[1].p, s->work[2].p);
+    if (rc) return rc;
+    return d2h(s, f, s->work[2].p, 3 * (size_t)s->num_nodes);
+}
+
 int hot_eval_cn_tolerance(hot_sim* s, double eps, double dt, double* tol)
 {
     if (!s->p2g_done) return fail(s, "hot_eval_cn_tolerance: call hot_p2g first");

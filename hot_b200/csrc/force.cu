@@ -570,6 +570,17 @@ int compute_residual(Sim* s, double* r)
     return bc_project(s, r);
 }
 
+// MpmSimulationBase::addScaledForces (MpmSimulationBase.cpp:829-833 -> MpmForceBase::rasterizeForceToTVStack): f -= scale (vol P Fn^T) grad w
+int add_scaled_forces(Sim* s, double scale, double* f)
+{
+    if (!s->state_valid) return fail(s, "addScaledForces: call hot_update_state first");
+    KTime t(s, KC_FORCE);
+    ForcePolicy::Args a{s->P.stride, s->P.X.p, s->f_stress.p, s->dx, 1.0 / s->dx, scale, s->g_idx.p, f};
+    k_plane_scatter<ForcePolicy><<<(unsigned)s->n_groups, SC_THREADS, 0, s->stream>>>(a, s->cell_start.p, s->group_slot.p, s->nbr8.p);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+
 int ensure_hessian(Sim* s)
 {
     if (!s->state_valid) return fail(s, "Hessian: call hot_update_state first");
@@ -596,6 +607,19 @@ int hessian_apply_mf(Sim* s, const double* x, double* b)
     HOT_LAUNCHED(s);
     HessianPolicy::Args a{s->P.stride, s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, s->dt * s->dt, s->g_idx.p, x, b};
     k_plane_scatter<HessianPolicy><<<(unsigned)s->n_groups, SC_THREADS, 0, st>>>(a, s->cell_start.p, s->group_slot.p, s->nbr8.p);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+
+// MpmSimulationBase::addScaledForceDifferentials (-> MpmForceBase::addScaledForceDifferential, MpmForceBase.cpp:261-306):
+// f += scale * df(x), df = -K x  (the objective calls it with scale = -dt^2)
+int add_scaled_force_differentials(Sim* s, double scale, const double* x, double* f)
+{
+    int rc = ensure_hessian(s);
+    if (rc) return rc;
+    KTime t(s, KC_HESSIAN);
+    HessianPolicy::Args a{s->P.stride, s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, -scale, s->g_idx.p, x, f};
+    k_plane_scatter<HessianPolicy><<<(unsigned)s->n_groups, SC_THREADS, 0, s->stream>>>(a, s->cell_start.p, s->group_slot.p, s->nbr8.p);
     HOT_LAUNCHED(s);
     return 0;
 }

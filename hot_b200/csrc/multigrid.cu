@@ -381,139 +381,130 @@ __global__ void __launch_bounds__(128) k_gs_phase(int b0, int b1, const int* __r
 }
 
 
-// One colour phase of gs_smooth, two-phase form (the version the V-cycle uses).  One CTA per 4^3 block:
-//   phase A (all warps, bandwidth-bound): every row of the block streams its 125 slots once.  Couplings to nodes that the
-//     sweep has already finalised OUTSIDE the block (earlier colours) are multiplied with their values and folded into the
-//     right-hand side; couplings to nodes of the SAME block that precede the row are parked in shared memory as a dense
-//     lower-triangular array of 3x3 blocks (<= 64*63/2 blocks = 145 KB);
-//   phase B (one warp, latency-bound but on-chip): right-looking block forward substitution over the <= 64 nodes, each lane
-//     owning two rows, the pivot value broadcast by shuffle.
+// One colour phase of gs_smooth, two-phase form (the version the V-cycle uses).  One CTA per 4^3 block, the block's
+// <= 64 nodes processed as two halves of <= 32 in sweep order; per half
+//   phase A (all warps, bandwidth-bound): every row streams its 125 slots once.  Couplings to nodes that are already final
+//     (earlier colours from HBM, the first half of this block from shared memory) are multiplied with their values and folded
+//     into the right-hand side; couplings to earlier rows of the SAME half are parked in shared memory as a dense strictly
+//     lower-triangular array of 3x3 blocks, stored per pivot column and per matrix entry so that phase B reads are
+//     conflict-free (32*31/2 blocks = 36 KB, so several CTAs share an SM and overlap each other's phases);
+//   phase B (one warp, on-chip): right-looking block forward substitution, one row per lane, pivot broadcast by shuffle.
 // Same-colour blocks are >= 5 nodes apart, beyond the stencil radius 2, so this equals the reference's node-serial sweep
 // (MultigridPreconditioner.h:276-310) up to the order of additions.  FWD: out_i = Dinv_i (rhs_i - sum_{rank j < rank i} A_ij out_j),
 // optionally out_scaled_i = D_i out_i (the "hdu = D hdu" pass of :292-293 fused); BWD: rank j > rank i.
-constexpr int GS_THREADS = 512;
-constexpr int GS_MAXN = 64;
-constexpr size_t GS_SMEM = (size_t)(GS_MAXN * (GS_MAXN - 1) / 2) * 9 * sizeof(double) + 2 * GS_MAXN * 3 * sizeof(double);
+constexpr int GS_THREADS = 256;
+constexpr int GS_HALF = 32;
+constexpr int GS_PAIRS = GS_HALF * (GS_HALF - 1) / 2; // 496
+__device__ __forceinline__ int gs_pair(int il, int kl) { return kl * (GS_HALF - 1) - kl * (kl - 1) / 2 + (il - kl - 1); } // il > kl
 
 template <bool FWD>
-__global__ void __launch_bounds__(GS_THREADS) k_gs_block(int b0, const int* __restrict__ block_start, const int* __restrict__ seq,
+__global__ void __launch_bounds__(GS_THREADS, 3) k_gs_block(int b0, const int* __restrict__ block_start, const int* __restrict__ seq,
     const int* __restrict__ colrank, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ dinv,
     const double* __restrict__ diag, const double* __restrict__ rhs, double* out, double* __restrict__ out_scaled)
 {
-    extern __shared__ double gs_smem[];
-    double* Lt = gs_smem;                                   // [il (il - 1) / 2 + kl][9]
-    double* s_rhs = gs_smem + (GS_MAXN * (GS_MAXN - 1) / 2) * 9; // [GS_MAXN][3]
-    double* s_x = s_rhs + GS_MAXN * 3;
+    __shared__ double Lt[9][GS_PAIRS]; // entry q of the coupling (il, kl) at Lt[q][gs_pair(il, kl)]
+    __shared__ double s_rhs[GS_HALF][3];
+    __shared__ double s_x[2 * GS_HALF][3];
     const int b = b0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ps = block_start[b], pe = block_start[b + 1], nb = pe - ps;
-    for (int e = tid; e < nb * (nb - 1) / 2 * 9; e += GS_THREADS) Lt[e] = 0.0;
-    __syncthreads();
-    // local index in sweep order: FWD il = p - ps, BWD il = pe - 1 - p
-    for (int il = warp; il < nb; il += GS_THREADS / 32) {
-        const int p = FWD ? ps + il : pe - 1 - il;
-        const int i = seq[p];
-        const int* c = col + (size_t)i * W;
-        const int* cr = colrank + (size_t)i * W;
-        const double* v = val + (size_t)i * 9 * W;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        int jj[W / 32], rr[W / 32];
+    for (int h0 = 0; h0 < nb; h0 += GS_HALF) {
+        const int hn = min(GS_HALF, nb - h0);
+        __syncthreads(); // previous half fully consumed (Lt, s_rhs) and its s_x visible
+        for (int e = tid; e < 9 * GS_PAIRS; e += GS_THREADS) (&Lt[0][0])[e] = 0.0;
+        __syncthreads();
+        // sweep-local index of a node: FWD rank - ps, BWD pe - 1 - rank
+        for (int il = warp; il < hn; il += GS_THREADS / 32) {
+            const int gl = h0 + il; // index in the block
+            const int p = FWD ? ps + gl : pe - 1 - gl;
+            const int i = seq[p];
+            const int* c = col + (size_t)i * W;
+            const int* cr = colrank + (size_t)i * W;
+            const double* v = val + (size_t)i * 9 * W;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            int jj[W / 32], rr[W / 32];
 #pragma unroll
-        for (int t = 0; t < W / 32; ++t) {
-            jj[t] = c[lane + 32 * t];
-            rr[t] = cr[lane + 32 * t];
-        }
-#pragma unroll
-        for (int t = 0; t < W / 32; ++t) {
-            const int sl = lane + 32 * t;
-            const int j = jj[t];
-            const int rj = rr[t];
-            const bool ext = FWD ? rj < ps : rj >= pe;
-            const bool inb = FWD ? (rj >= ps && rj < p) : (rj < pe && rj > p);
-            if (ext || inb) {
-                const double v0 = v[sl], v1 = v[W + sl], v2 = v[2 * W + sl], v3 = v[3 * W + sl], v4 = v[4 * W + sl], v5 = v[5 * W + sl],
-                             v6 = v[6 * W + sl], v7 = v[7 * W + sl], v8 = v[8 * W + sl];
-                if (ext) {
-                    const double x0 = out[3 * (size_t)j], x1 = out[3 * (size_t)j + 1], x2 = out[3 * (size_t)j + 2];
-                    a0 += v0 * x0 + v3 * x1 + v6 * x2;
-                    a1 += v1 * x0 + v4 * x1 + v7 * x2;
-                    a2 += v2 * x0 + v5 * x1 + v8 * x2;
-                }
-                else {
-                    const int kl = FWD ? rj - ps : pe - 1 - rj;
-                    double* d = Lt + (size_t)(il * (il - 1) / 2 + kl) * 9;
-                    d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3; d[4] = v4; d[5] = v5; d[6] = v6; d[7] = v7; d[8] = v8;
-                }
+            for (int t = 0; t < W / 32; ++t) {
+                jj[t] = c[lane + 32 * t];
+                rr[t] = cr[lane + 32 * t];
             }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a0 += __shfl_down_sync(0xffffffffu, a0, o);
-            a1 += __shfl_down_sync(0xffffffffu, a1, o);
-            a2 += __shfl_down_sync(0xffffffffu, a2, o);
-        }
-        if (lane == 0) {
-            s_rhs[3 * il] = rhs[3 * (size_t)i] - a0;
-            s_rhs[3 * il + 1] = rhs[3 * (size_t)i + 1] - a1;
-            s_rhs[3 * il + 2] = rhs[3 * (size_t)i + 2] - a2;
-        }
-    }
-    __syncthreads();
-    if (warp == 0) {
-        double r[2][3], D[2][9];
-        int node[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int il = lane + 32 * h;
-            node[h] = -1;
-            if (il < nb) {
-                node[h] = seq[FWD ? ps + il : pe - 1 - il];
-#pragma unroll
-                for (int d = 0; d < 3; ++d) r[h][d] = s_rhs[3 * il + d];
-#pragma unroll
-                for (int q = 0; q < 9; ++q) D[h][q] = dinv[9 * (size_t)node[h] + q];
-            }
-        }
-        for (int k = 0; k < nb; ++k) {
-            const int owner = k & 31, h = k >> 5;
-            double x0 = 0.0, x1 = 0.0, x2 = 0.0;
-            if (lane == owner) {
-                double Dk[9], rk[3];
-#pragma unroll
-                for (int q = 0; q < 9; ++q) Dk[q] = h ? D[1][q] : D[0][q]; // selects, not indexing: keeps D / r in registers
-#pragma unroll
-                for (int d = 0; d < 3; ++d) rk[d] = h ? r[1][d] : r[0][d];
-                x0 = Dk[0] * rk[0] + Dk[3] * rk[1] + Dk[6] * rk[2];
-                x1 = Dk[1] * rk[0] + Dk[4] * rk[1] + Dk[7] * rk[2];
-                x2 = Dk[2] * rk[0] + Dk[5] * rk[1] + Dk[8] * rk[2];
-                s_x[3 * k] = x0; s_x[3 * k + 1] = x1; s_x[3 * k + 2] = x2;
-            }
-            x0 = __shfl_sync(0xffffffffu, x0, owner);
-            x1 = __shfl_sync(0xffffffffu, x1, owner);
-            x2 = __shfl_sync(0xffffffffu, x2, owner);
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int il = lane + 32 * hh;
-                if (il > k && il < nb) {
-                    const double* l = Lt + (size_t)(il * (il - 1) / 2 + k) * 9;
-                    r[hh][0] -= l[0] * x0 + l[3] * x1 + l[6] * x2;
-                    r[hh][1] -= l[1] * x0 + l[4] * x1 + l[7] * x2;
-                    r[hh][2] -= l[2] * x0 + l[5] * x1 + l[8] * x2;
+            for (int t = 0; t < W / 32; ++t) {
+                const int sl = lane + 32 * t;
+                const int j = jj[t];
+                const int kl = FWD ? rr[t] - ps : pe - 1 - rr[t]; // < 0: final before this block; [0, gl): earlier in this block
+                if (kl < gl) {
+                    const double v0 = v[sl], v1 = v[W + sl], v2 = v[2 * W + sl], v3 = v[3 * W + sl], v4 = v[4 * W + sl], v5 = v[5 * W + sl],
+                                 v6 = v[6 * W + sl], v7 = v[7 * W + sl], v8 = v[8 * W + sl];
+                    if (kl < h0) {
+                        double x0, x1, x2;
+                        if (kl < 0) {
+                            x0 = out[3 * (size_t)j]; x1 = out[3 * (size_t)j + 1]; x2 = out[3 * (size_t)j + 2];
+                        }
+                        else {
+                            x0 = s_x[kl][0]; x1 = s_x[kl][1]; x2 = s_x[kl][2];
+                        }
+                        a0 += v0 * x0 + v3 * x1 + v6 * x2;
+                        a1 += v1 * x0 + v4 * x1 + v7 * x2;
+                        a2 += v2 * x0 + v5 * x1 + v8 * x2;
+                    }
+                    else {
+                        const int e = gs_pair(il, kl - h0);
+                        Lt[0][e] = v0; Lt[1][e] = v1; Lt[2][e] = v2; Lt[3][e] = v3; Lt[4][e] = v4; Lt[5][e] = v5; Lt[6][e] = v6; Lt[7][e] = v7;
+                        Lt[8][e] = v8;
+                    }
                 }
             }
-        }
-        __syncwarp();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int il = lane + 32 * h;
-            if (il < nb) {
-                const int i = node[h];
-                const double x0 = s_x[3 * il], x1 = s_x[3 * il + 1], x2 = s_x[3 * il + 2];
-                out[3 * (size_t)i] = x0; out[3 * (size_t)i + 1] = x1; out[3 * (size_t)i + 2] = x2;
+            for (int o = 16; o > 0; o >>= 1) {
+                a0 += __shfl_down_sync(0xffffffffu, a0, o);
+                a1 += __shfl_down_sync(0xffffffffu, a1, o);
+                a2 += __shfl_down_sync(0xffffffffu, a2, o);
+            }
+            if (lane == 0) {
+                s_rhs[il][0] = rhs[3 * (size_t)i] - a0;
+                s_rhs[il][1] = rhs[3 * (size_t)i + 1] - a1;
+                s_rhs[il][2] = rhs[3 * (size_t)i + 2] - a2;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0, D[9];
+            int node = -1;
+            if (lane < hn) {
+                node = seq[FWD ? ps + h0 + lane : pe - 1 - (h0 + lane)];
+                r0 = s_rhs[lane][0]; r1 = s_rhs[lane][1]; r2 = s_rhs[lane][2];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) D[q] = dinv[9 * (size_t)node + q];
+            }
+            else {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) D[q] = 0.0;
+            }
+            double mx0 = 0.0, mx1 = 0.0, mx2 = 0.0; // this lane's solution
+            for (int k = 0; k < hn; ++k) {
+                // every lane evaluates Dinv r of its own row; the pivot lane's value is the one that counts
+                const double y0 = D[0] * r0 + D[3] * r1 + D[6] * r2;
+                const double y1 = D[1] * r0 + D[4] * r1 + D[7] * r2;
+                const double y2 = D[2] * r0 + D[5] * r1 + D[8] * r2;
+                const double x0 = __shfl_sync(0xffffffffu, y0, k);
+                const double x1 = __shfl_sync(0xffffffffu, y1, k);
+                const double x2 = __shfl_sync(0xffffffffu, y2, k);
+                if (lane == k) { mx0 = y0; mx1 = y1; mx2 = y2; }
+                if (lane > k && lane < hn) {
+                    const int e = gs_pair(lane, k);
+                    r0 -= Lt[0][e] * x0 + Lt[3][e] * x1 + Lt[6][e] * x2;
+                    r1 -= Lt[1][e] * x0 + Lt[4][e] * x1 + Lt[7][e] * x2;
+                    r2 -= Lt[2][e] * x0 + Lt[5][e] * x1 + Lt[8][e] * x2;
+                }
+            }
+            if (lane < hn) {
+                s_x[h0 + lane][0] = mx0; s_x[h0 + lane][1] = mx1; s_x[h0 + lane][2] = mx2;
+                out[3 * (size_t)node] = mx0; out[3 * (size_t)node + 1] = mx1; out[3 * (size_t)node + 2] = mx2;
                 if (FWD && out_scaled) {
-                    const double* d = diag + 9 * (size_t)i;
-                    out_scaled[3 * (size_t)i] = d[0] * x0 + d[3] * x1 + d[6] * x2;
-                    out_scaled[3 * (size_t)i + 1] = d[1] * x0 + d[4] * x1 + d[7] * x2;
-                    out_scaled[3 * (size_t)i + 2] = d[2] * x0 + d[5] * x1 + d[8] * x2;
+                    const double* d = diag + 9 * (size_t)node;
+                    out_scaled[3 * (size_t)node] = d[0] * mx0 + d[3] * mx1 + d[6] * mx2;
+                    out_scaled[3 * (size_t)node + 1] = d[1] * mx0 + d[4] * mx1 + d[7] * mx2;
+                    out_scaled[3 * (size_t)node + 2] = d[2] * mx0 + d[5] * mx1 + d[8] * mx2;
                 }
             }
         }
@@ -852,26 +843,20 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
     cudaStream_t st = s->stream;
     double* hdu = L.tmp.p;   // unscaled forward solution (what the forward sweep itself reads)
     double* dhdu = L.dAu.p;  // D hdu, the right-hand side of the backward sweep
-    static bool attr_set = false;
-    if (!attr_set) {
-        HOT_CUDA(cudaFuncSetAttribute(k_gs_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
-        HOT_CUDA(cudaFuncSetAttribute(k_gs_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
-        attr_set = true;
-    }
     const bool project = level == 0 && !s->matrix_bcproject;
     iterations = (iterations + 1) >> 1;
     for (; iterations--;) {
         for (int c = 0; c < 8; ++c) {
             const int b0 = L.color_first_block[c], b1 = L.color_first_block[c + 1];
             if (b1 == b0) continue;
-            k_gs_block<true><<<b1 - b0, GS_THREADS, GS_SMEM, st>>>(b0, L.gs_block_start.p, L.gs_seq.p, L.gs_colrank.p, L.col.p, L.val.p, L.dinv.p,
+            k_gs_block<true><<<b1 - b0, GS_THREADS, 0, st>>>(b0, L.gs_block_start.p, L.gs_seq.p, L.gs_colrank.p, L.col.p, L.val.p, L.dinv.p,
                 L.diag.p, r, hdu, dhdu);
             HOT_LAUNCHED(s);
         }
         for (int c = 7; c >= 0; --c) {
             const int b0 = L.color_first_block[c], b1 = L.color_first_block[c + 1];
             if (b1 == b0) continue;
-            k_gs_block<false><<<b1 - b0, GS_THREADS, GS_SMEM, st>>>(b0, L.gs_block_start.p, L.gs_seq.p, L.gs_colrank.p, L.col.p, L.val.p, L.dinv.p,
+            k_gs_block<false><<<b1 - b0, GS_THREADS, 0, st>>>(b0, L.gs_block_start.p, L.gs_seq.p, L.gs_colrank.p, L.col.p, L.val.p, L.dinv.p,
                 L.diag.p, dhdu, L.du.p, nullptr);
             HOT_LAUNCHED(s);
         }

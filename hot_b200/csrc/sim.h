@@ -256,6 +256,8 @@ int compute_residual(Sim* s, double* r);
 int bc_project(Sim* s, double* v);
 int bc_rotate(Sim* s, double* v, bool inverse);
 int ensure_hessian(Sim* s);
+int add_scaled_forces(Sim* s, double scale, double* f);
+int add_scaled_force_differentials(Sim* s, double scale, const double* x, double* f);
 int hessian_apply_mf(Sim* s, const double* x, double* b);
 int eval_cn_tolerance(Sim* s, double eps, double dt, double* tol);
 // matrix.cu

@@ -391,3 +391,13 @@ class MpmSimulationB200:
         n = C.c_longlong(0)
         self._check(self._lib.hot_level_nnz_blocks(self._h, int(level), C.byref(n)))
         return n.value
+
+    def addScaledForces(self, scale, f):
+        f = _f64(f, (self.num_nodes, 3)).copy()
+        self._check(self._lib.hot_add_scaled_forces(self._h, float(scale), _ptr(f)))
+        return f
+
+    def addScaledForceDifferentials(self, scale, x, f):
+        x = _f64(x, (self.num_nodes, 3)); f = _f64(f, (self.num_nodes, 3)).copy()
+        self._check(self._lib.hot_add_scaled_force_differentials(self._h, float(scale), _ptr(x), _ptr(f)))
+        return f

@@ -118,6 +118,10 @@ int hot_compute_residual(hot_sim* h, double* residual);
 int hot_project(hot_sim* h, double* v);
 /* ImplicitSolverObjective::multiply with --matfree (ImplicitSolver.h:741-763): b = M x + dt^2 K x */
 int hot_hessian_apply_mf(hot_sim* h, const double* x, double* b);
+/* MpmSimulationBase::addScaledForces(scale, f) (Lib/MPM/MpmSimulationBase.cpp:829-833): f += scale * (elastic nodal force) */
+int hot_add_scaled_forces(hot_sim* h, double scale, double* f);
+/* MpmSimulationBase::addScaledForceDifferentials(scale, x, f) (:835-840): f += scale * df(x), df = -K x */
+int hot_add_scaled_force_differentials(hot_sim* h, double scale, const double* x, double* f);
 /* ImplicitSolverObjective::evaluatePerNodeCNTolerance (ImplicitSolver.h:667-696); tol may be NULL (kept on device) */
 int hot_eval_cn_tolerance(hot_sim* h, double eps, double dt, double* tol);
 

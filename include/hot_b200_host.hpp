@@ -1,0 +1,448 @@
+// hot_b200 host side (C++17, header-only): the reference's operator surface for the hot path, re-expressed over the
+// C ABI of hot_b200.h.  The reference is in-process C++ (Eigen + TBB), so a drop-in keeps ITS names and call order:
+//
+//   MpmSimulationBase<T,dim> virtuals  (Lib/MPM/MpmSimulationBase.h:138-220)        -> hot_b200::MpmSimulationB200
+//   ImplicitSolverObjective concept    (Projects/multigrid/ImplicitSolver.h:41-47,128-333,741-763) -> ::ImplicitSolverObjectiveB200
+//   smoothFunc pointers / -smoother codes (MultigridPreconditioner.h:68-73,496-521)  -> hot_b200::{jacobi,optimal_jacobi,cg,gs}_smooth
+//   HOTSettings statics + FLAGS        (Configurations.h:18-42, main.cpp:40-84)      -> hot_b200::HOTSettings, parseFlags
+//   AnalyticCollisionObject / CollisionNode (CollisionObject.h:16-45, .cpp:108-149,384-452) -> host-evaluated a8
+//
+// TVStack here is a std::vector<double> of n x (x,y,z) - the memory layout of Eigen::Matrix<T,3,Dynamic>; 3x3 matrices are
+// column-major 9-arrays like Eigen.  With Eigen available, `Eigen::Map<TVStack>(v.data(), 3, n)` views these buffers with
+// no copy (INTEGRATION.md shows the Ziran-side glue).  Errors surface as std::runtime_error like ZIRAN_ASSERT
+// (Lib/Ziran/CS/Util/Debug.h:19-42).  There is no CPU fallback: construction fails without a usable GPU.
+#pragma once
+#include "hot_b200.h"
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace hot_b200 {
+
+using TVStack = std::vector<double>;
+using TV = std::array<double, 3>;
+using TM = std::array<double, 9>; // column-major
+
+struct HotError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// Projects/multigrid/Configurations.h:18-42 - same names, same defaults
+namespace HOTSettings {
+inline double cneps = 1e-5;
+inline bool useAdaptiveHessian = false, useCN = false, matrixFree = false, project = false, systemBCProject = false, linesearch = false;
+inline int boundaryType = 0, lsolver = 0, Ainv = 0, smoother = 0, coarseSolver = 0, levelCnt = 1, times = 1, levelscale = 0, debugMode = 0;
+inline double omega = 1, topomega = 0.1;
+} // namespace HOTSettings
+
+// the flag subset of Projects/multigrid/main.cpp:40-84 that drives the hot path; unknown flags throw like
+// FLAGS::ParseFlags (Lib/Ziran/CS/Util/CommandLineFlags.h:185-206)
+inline void parseFlags(int argc, const char* const* argv)
+{
+    using namespace HOTSettings;
+    auto need = [&](int& i) -> const char* {
+        if (i + 1 >= argc) throw HotError(std::string("Missing value for flag ") + argv[i]);
+        return argv[++i];
+    };
+    for (int i = 1; i < argc; ++i) {
+        const std::string f = argv[i];
+        if (f == "--usecn") useCN = true;
+        else if (f == "--adaptiveH") useAdaptiveHessian = true;
+        else if (f == "--matfree") matrixFree = true;
+        else if (f == "--project") project = true;
+        else if (f == "--bcproject") systemBCProject = true;
+        else if (f == "--linesearch") linesearch = true;
+        else if (f == "--3d" || f == "--double") {}
+        else if (f == "-cneps") cneps = std::stod(need(i));
+        else if (f == "-bc") boundaryType = std::stoi(need(i));
+        else if (f == "-lsolver") lsolver = std::stoi(need(i));
+        else if (f == "-Ainv") Ainv = std::stoi(need(i));
+        else if (f == "-smoother") smoother = std::stoi(need(i));
+        else if (f == "-coarseSolver") coarseSolver = std::stoi(need(i));
+        else if (f == "-mg_level") levelCnt = std::stoi(need(i));
+        else if (f == "-mg_times") times = std::stoi(need(i));
+        else if (f == "-mg_scale") levelscale = std::stoi(need(i));
+        else if (f == "-mg_omega") omega = std::stod(need(i));
+        else if (f == "-mg_jomega") topomega = std::stod(need(i));
+        else if (f == "-test" || f == "-o" || f == "-t" || f == "-cmd0" || f == "-cmd1" || f == "-dbg") need(i);
+        else throw HotError("Unknown flag: " + f);
+    }
+}
+
+inline hot_solver_options optionsFromSettings()
+{
+    hot_solver_options o;
+    hot_default_options(&o);
+    o.lsolver = HOTSettings::lsolver; o.matfree = HOTSettings::matrixFree; o.project = HOTSettings::project;
+    o.bcproject = HOTSettings::systemBCProject; o.linesearch = HOTSettings::linesearch; o.usecn = HOTSettings::useCN;
+    o.adaptive_h = HOTSettings::useAdaptiveHessian; o.mg_level = HOTSettings::levelCnt; o.mg_times = HOTSettings::times;
+    o.mg_scale = HOTSettings::levelscale; o.smoother = HOTSettings::smoother; o.coarse_solver = HOTSettings::coarseSolver;
+    o.Ainv = HOTSettings::Ainv; o.cneps = HOTSettings::cneps; o.topomega = HOTSettings::topomega;
+    return o;
+}
+
+// ---- small 3x3 helpers -------------------------------------------------------------------------------------------------
+inline TV sub(const TV& a, const TV& b) { return {a[0] - b[0], a[1] - b[1], a[2] - b[2]}; }
+inline double dot(const TV& a, const TV& b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+inline double norm(const TV& a) { return std::sqrt(dot(a, a)); }
+inline TM identity() { return {1, 0, 0, 0, 1, 0, 0, 0, 1}; }
+
+// ---- a8: collision objects, evaluated on the host (O(N_nodes) analytic tests per step) ------------------------------------
+enum COLLISION_OBJECT_TYPE { STICKY = 1, SLIP = 2, SEPARATE = 3, GHOST = 4 }; // CollisionObject.h:51-56
+
+// AnalyticLevelSet (Lib/Ziran/Math/Geometry/AnalyticLevelSet.h): signed distance + outward normal
+struct AnalyticLevelSet {
+    virtual ~AnalyticLevelSet() = default;
+    virtual bool query(const TV& X, double& phi, TV& n) const = 0; // true when inside (phi <= 0)
+};
+struct HalfSpace : AnalyticLevelSet { // AnalyticLevelSet.cpp:259-304
+    TV origin, outward_normal;
+    HalfSpace(const TV& o, const TV& n_in) : origin(o)
+    {
+        const double l = norm(n_in);
+        outward_normal = {n_in[0] / l, n_in[1] / l, n_in[2] / l};
+    }
+    bool query(const TV& X, double& phi, TV& n) const override
+    {
+        phi = dot(outward_normal, sub(X, origin));
+        n = outward_normal;
+        return phi <= 0;
+    }
+};
+struct Sphere : AnalyticLevelSet { // AnalyticLevelSet.h Sphere: phi = |X - c| - r
+    TV center;
+    double radius;
+    Sphere(const TV& c, double r) : center(c), radius(r) {}
+    bool query(const TV& X, double& phi, TV& n) const override
+    {
+        const TV d = sub(X, center);
+        const double l = norm(d);
+        phi = l - radius;
+        n = l > 0 ? TV{d[0] / l, d[1] / l, d[2] / l} : TV{0, 1, 0};
+        return phi <= 0;
+    }
+};
+
+// AnalyticCollisionObject restricted to translating objects (R = I, s = 1, omega = 0): CollisionObject.cpp:384-452
+struct AnalyticCollisionObject {
+    std::shared_ptr<AnalyticLevelSet> ls;
+    COLLISION_OBJECT_TYPE type;
+    double friction = 0;
+    TV b{0, 0, 0}, dbdt{0, 0, 0};
+    std::function<void(double, AnalyticCollisionObject&)> updateState; // collision_objects[k]->updateState(t + dt), MultigridSimulation.h:292-295
+    AnalyticCollisionObject(std::shared_ptr<AnalyticLevelSet> l, COLLISION_OBJECT_TYPE t) : ls(std::move(l)), type(t) {}
+
+    bool detectAndResolveCollision(const TV& x, TV& v, TV& n) const
+    {
+        if (type == GHOST) return false;
+        n = {NAN, NAN, NAN};
+        double phi;
+        TV N;
+        if (!ls->query(sub(x, b), phi, N)) return false;
+        for (int d = 0; d < 3; ++d) v[d] -= dbdt[d];
+        if (type == STICKY) v = {0, 0, 0};
+        else {
+            n = N;
+            const double dn = dot(v, n);
+            if (type == SLIP || dn < 0) {
+                for (int d = 0; d < 3; ++d) v[d] -= n[d] * dn;
+                if (friction != 0 && dn < 0) {
+                    const double l = norm(v);
+                    if (-dn * friction < l)
+                        for (int d = 0; d < 3; ++d) v[d] += v[d] / l * dn * friction;
+                    else v = {0, 0, 0};
+                }
+            }
+        }
+        for (int d = 0; d < 3; ++d) v[d] += dbdt[d];
+        return true;
+    }
+};
+
+// multiObjectCollision, CollisionObject.cpp:108-149
+inline bool multiObjectCollision(const std::vector<AnalyticCollisionObject>& objects, const TV& xi, TV& vi, TM& normal_basis, TV& wn)
+{
+    bool any = false;
+    int slip_count = 0;
+    normal_basis.fill(0.0);
+    for (const auto& o : objects) {
+        if (o.type == GHOST) continue;
+        TV n;
+        const bool collide = o.detectAndResolveCollision(xi, vi, n);
+        any = any || collide;
+        if (!collide) continue;
+        if (o.type == STICKY) {
+            wn = {0, 0, 0};
+            normal_basis = identity();
+            break;
+        }
+        for (int c = 0; c < slip_count; ++c) { // Gram-Schmidt the normals
+            const TV old{normal_basis[3 * c], normal_basis[3 * c + 1], normal_basis[3 * c + 2]};
+            const double d = dot(old, n);
+            for (int k = 0; k < 3; ++k) n[k] -= d * old[k];
+        }
+        wn = n;
+        const double l = norm(n);
+        if (l) {
+            for (int k = 0; k < 3; ++k) normal_basis[3 * slip_count + k] = n[k] / l;
+            if (++slip_count == 3) break;
+        }
+    }
+    return any;
+}
+
+// RotationExtractor<T,3>::rotate (MpmSimulationBase.h:270-281): Quaternion::setFromTwoVectors(a, e_x) as a matrix
+inline TM rotateToX(const TV& a_in)
+{
+    const double l = norm(a_in);
+    const TV a{a_in[0] / l, a_in[1] / l, a_in[2] / l};
+    const double c = a[0]; // a . e_x
+    if (c < -1 + 1e-12) return {-1, 0, 0, 0, -1, 0, 0, 0, 1}; // antiparallel: rotate by pi about z
+    const TV v{0, a[2], -a[1]}; // a x e_x
+    const double k = 1 / (1 + c);
+    // R = I + [v]x + [v]x^2 / (1 + c)
+    return {1 + k * (-v[1] * v[1] - v[2] * v[2]), v[2] + k * v[0] * v[1], -v[1] + k * v[0] * v[2],
+        -v[2] + k * v[0] * v[1], 1 + k * (-v[0] * v[0] - v[2] * v[2]), v[0] + k * v[1] * v[2],
+        v[1] + k * v[0] * v[2], -v[0] + k * v[1] * v[2], 1 + k * (-v[0] * v[0] - v[1] * v[1])};
+}
+
+struct CollisionNode { // CollisionObject.h:16-45
+    int node_id;
+    TM P, R, Rinv;
+    bool shouldRotate;
+};
+
+// ---- MpmSimulationBase surface -----------------------------------------------------------------------------------------------
+class MpmSimulationB200 {
+public:
+    // public data members the solvers of the reference read directly (MpmSimulationBase.h:69-131)
+    double dx, dt = 0, cfl = 0.6, apic_rpic_ratio = 1;
+    TV gravity{0, 0, 0};
+    int num_nodes = 0;
+    std::vector<double> mass_matrix;
+    TVStack dv, vn;
+    std::vector<AnalyticCollisionObject> collision_objects;
+    std::vector<CollisionNode> collision_nodes;
+    double time = 0;
+    hot_solve_log last_log;
+
+    MpmSimulationB200(double dx_, double apic_rpic_ratio_ = 1.0, double cfl_ = 0.6, int device = -1)
+        : dx(dx_), cfl(cfl_), apic_rpic_ratio(apic_rpic_ratio_)
+    {
+        h = hot_create(dx, apic_rpic_ratio, cfl, device);
+        if (!h) throw HotError("hot_create failed: no usable CUDA device (hot_b200 has no CPU fallback)");
+        std::memset(&last_log, 0, sizeof last_log);
+    }
+    ~MpmSimulationB200() { hot_destroy(h); }
+    MpmSimulationB200(const MpmSimulationB200&) = delete;
+    MpmSimulationB200& operator=(const MpmSimulationB200&) = delete;
+    hot_sim* handle() { return h; }
+
+    // particles.X / V / mass, APIC C, F, element measure, CorotatedIsotropic mu / lambda (original order, AoS)
+    void setParticles(long n, const double* X, const double* V, const double* mass, const double* C, const double* F, const double* vol,
+        const double* mu, const double* lambda)
+    {
+        check(hot_set_particles(h, n, X, V, mass, C, F, vol, mu, lambda));
+        N = n;
+    }
+    void getParticles(double* X, double* V, double* C, double* F) { check(hot_get_particles(h, X, V, C, F, nullptr)); }
+    long particleCount() const { return N; }
+
+    void sortParticlesAndPolluteGrid() { check(hot_sort_and_activate(h)); } // MpmSimulationBase.cpp:1066-1137
+    void particlesToGrid() { check(hot_p2g(h, &num_nodes)); } // :461-533
+    void buildMassMatrix() // :817-826
+    {
+        mass_matrix.resize(num_nodes);
+        if (num_nodes) check(hot_get_mass_matrix(h, mass_matrix.data()));
+    }
+    // :1139-1184 - collider tests on the host, the BC table crosses the boundary once per step
+    void buildInitialDvAndVnForNewton()
+    {
+        std::vector<int> coord(3 * (size_t)num_nodes);
+        std::vector<long long> idx((size_t)hot_num_pages(h) * 32);
+        std::vector<double> gv(3 * idx.size());
+        if (num_nodes) check(hot_get_id2coord(h, coord.data()));
+        check(hot_get_grid(h, idx.data(), nullptr, gv.data()));
+        vn.assign(3 * (size_t)num_nodes, 0.0);
+        for (size_t a = 0; a < idx.size(); ++a)
+            if (idx[a] >= 0)
+                for (int d = 0; d < 3; ++d) vn[3 * idx[a] + d] = gv[3 * a + d];
+        collision_nodes.clear();
+        std::vector<int> node_id, slip;
+        std::vector<double> P, R, Rinv, dv_bc;
+        for (int i = 0; i < num_nodes; ++i) {
+            const TV xi{coord[3 * i] * dx, coord[3 * i + 1] * dx, coord[3 * i + 2] * dx};
+            const TV old_v{vn[3 * i], vn[3 * i + 1], vn[3 * i + 2]};
+            TV vi = old_v, wn{0, 0, 0};
+            TM nb;
+            if (!multiObjectCollision(collision_objects, xi, vi, nb, wn)) continue;
+            const bool isSlip = wn[0] != 0 || wn[1] != 0 || wn[2] != 0;
+            CollisionNode Z;
+            Z.node_id = i;
+            Z.shouldRotate = isSlip;
+            Z.R = isSlip ? rotateToX(wn) : identity();
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) Z.Rinv[r + 3 * c] = Z.R[c + 3 * r]; // rotation: inverse = transpose
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    double kk = 0;
+                    for (int k = 0; k < 3; ++k) kk += nb[r + 3 * k] * nb[c + 3 * k];
+                    Z.P[r + 3 * c] = (r == c ? 1.0 : 0.0) - kk;
+                }
+            collision_nodes.push_back(Z);
+            node_id.push_back(i);
+            slip.push_back(isSlip);
+            P.insert(P.end(), Z.P.begin(), Z.P.end());
+            R.insert(R.end(), Z.R.begin(), Z.R.end());
+            Rinv.insert(Rinv.end(), Z.Rinv.begin(), Z.Rinv.end());
+            for (int d = 0; d < 3; ++d) dv_bc.push_back(vi[d] - old_v[d]);
+        }
+        const int mode = (HOTSettings::systemBCProject && HOTSettings::boundaryType == 1) ? 1 : 0; // MultigridSimulation.h:104-125
+        check(hot_set_dt_gravity(h, dt, gravity.data()));
+        check(hot_set_bc(h, mode, (int)node_id.size(), node_id.data(), P.data(), R.data(), Rinv.data(), slip.data(), dv_bc.data()));
+        dv.resize(3 * (size_t)num_nodes);
+        if (num_nodes) check(hot_get_dv(h, dv.data()));
+    }
+    void moveNodes(const TVStack& dv_in) // :735-747 (folded into updateState on the device)
+    {
+        dv = dv_in;
+        check(hot_set_dv(h, dv.data()));
+    }
+    void addScaledForces(double scale, TVStack& f) { check(hot_add_scaled_forces(h, scale, f.data())); } // :829-833
+    void addScaledForceDifferentials(double scale, const TVStack& x, TVStack& f) // :835-840
+    {
+        check(hot_add_scaled_force_differentials(h, scale, x.data(), f.data()));
+    }
+    void constructNewVelocityFromNewtonResult() {} // :891-901 - fused into the node-tile staging of hot_g2p
+    void gridToParticles(double dt_) // :903-1042 (+ evolveStrain)
+    {
+        int flags[2] = {0, 0};
+        check(hot_g2p(h, dt_, flags));
+        faster_than_dx = flags[0] != 0;
+        faster_than_half_dx = flags[1] != 0;
+    }
+    bool faster_than_dx = false, faster_than_half_dx = false;
+
+    // MultigridSimulation::startBackwardEuler (MultigridSimulation.h:167-186)
+    void startBackwardEuler()
+    {
+        buildMassMatrix();
+        buildInitialDvAndVnForNewton();
+        check(hot_backup_strain(h));
+    }
+    // MultigridSimulation::backwardEulerStep (:188-233): tolerances, Newton / L-BFGS by HOTSettings::lsolver, restoreStrain
+    void backwardEulerStep()
+    {
+        buildMassMatrix();
+        buildInitialDvAndVnForNewton();
+        const hot_solver_options o = optionsFromSettings();
+        check(hot_backward_euler_step(h, &o, &last_log));
+        if (num_nodes) check(hot_get_dv(h, dv.data()));
+    }
+    // MultigridSimulation::advanceOneTimeStep (:235-297): reinitialize -> P2G -> BE solve -> collider update -> G2P
+    void advanceOneTimeStep(double dt_)
+    {
+        dt = dt_;
+        sortParticlesAndPolluteGrid();
+        particlesToGrid();
+        backwardEulerStep();
+        for (auto& o : collision_objects)
+            if (o.updateState) o.updateState(time + dt, o);
+        gridToParticles(dt);
+        time += dt;
+    }
+
+    void check(int rc) const
+    {
+        if (rc != 0) throw HotError(hot_last_error(h));
+    }
+
+private:
+    hot_sim* h = nullptr;
+    long N = 0;
+};
+
+// ---- Krylov / Newton objective concept ---------------------------------------------------------------------------------------
+class ImplicitSolverObjectiveB200 {
+public:
+    using Scalar = double;
+    using NewtonVector = TVStack;
+    MpmSimulationB200& simulation;
+    bool matrix_free = false;
+    std::function<void(TVStack&)> project;
+    std::function<void(const TVStack&, TVStack&)> precondition;
+    double Ek = 0;
+
+    explicit ImplicitSolverObjectiveB200(MpmSimulationB200& sim) : simulation(sim)
+    {
+        project = [this](TVStack& v) { simulation.check(hot_project(simulation.handle(), v.data())); };
+        precondition = [this](const TVStack& in, TVStack& out) { // rebuildPreconditioner installs the V-cycle here (SparseMatrixFast.h:46-58)
+            out.resize(in.size());
+            simulation.check(hot_vcycle(simulation.handle(), in.data(), out.data()));
+        };
+    }
+    void updateState(const TVStack& dv, bool = false) // ImplicitSolver.h:237-252
+    {
+        simulation.check(hot_update_state(simulation.handle(), dv.data(), HOTSettings::linesearch ? &Ek : nullptr));
+    }
+    void computeResidual(TVStack& r, bool = false) // :128-155
+    {
+        r.resize(3 * (size_t)simulation.num_nodes);
+        simulation.check(hot_compute_residual(simulation.handle(), r.data()));
+    }
+    double computeNorm(const TVStack& r) const { return std::sqrt(innerProduct(r, r)); } // :158-171
+    double innerProduct(const TVStack& a, const TVStack& b) const // :213-234
+    {
+        double s = 0;
+        for (size_t i = 0; i < a.size(); ++i) s += a[i] * b[i];
+        return s;
+    }
+    void multiply(const TVStack& x, TVStack& b) const // :741-763
+    {
+        b.resize(x.size());
+        if (matrix_free) simulation.check(hot_hessian_apply_mf(simulation.handle(), x.data(), b.data()));
+        else simulation.check(hot_spmv(simulation.handle(), 0, x.data(), b.data()));
+    }
+    void buildMatrix(bool projectSystem) { simulation.check(hot_build_matrix(simulation.handle(), projectSystem)); } // :470-603
+    void HinvApproxInit() // :335-353
+    {
+        buildMatrix(true);
+        simulation.check(hot_build_mg(simulation.handle(), HOTSettings::levelCnt, HOTSettings::smoother, HOTSettings::coarseSolver,
+            HOTSettings::Ainv, HOTSettings::times, HOTSettings::levelscale, HOTSettings::topomega));
+    }
+};
+
+// ---- -smoother / -coarseSolver function-pointer surface (MultigridPreconditioner.h:68-73) -----------------------------------
+struct MPMSpMatB200 { // stands for MPMSpMat& A: one level of the device hierarchy
+    MpmSimulationB200* sim;
+    int level;
+};
+using SmoothFunc = void (*)(TVStack& u, TVStack& r, TVStack& du, TVStack& dAu, MPMSpMatB200& A, int iterations, double tolerance);
+namespace detail {
+inline void smooth(int kind, TVStack& u, TVStack& r, MPMSpMatB200& A, int iterations, double tolerance)
+{
+    A.sim->check(hot_smooth(A.sim->handle(), A.level, kind, u.data(), r.data(), iterations, tolerance, nullptr));
+}
+} // namespace detail
+inline void jacobi_smooth(TVStack& u, TVStack& r, TVStack&, TVStack&, MPMSpMatB200& A, int it, double tol) { detail::smooth(0, u, r, A, it, tol); }
+inline void optimal_jacobi_smooth(TVStack& u, TVStack& r, TVStack&, TVStack&, MPMSpMatB200& A, int it, double tol) { detail::smooth(1, u, r, A, it, tol); }
+inline void cg_smooth(TVStack& u, TVStack& r, TVStack&, TVStack&, MPMSpMatB200& A, int it, double tol) { detail::smooth(2, u, r, A, it, tol); }
+inline void gs_smooth(TVStack& u, TVStack& r, TVStack&, TVStack&, MPMSpMatB200& A, int it, double tol) { detail::smooth(5, u, r, A, it, tol); }
+// selectSmoother, MultigridPreconditioner.h:496-521
+inline SmoothFunc selectSmoother(int opt)
+{
+    switch (opt) {
+    case 0: return jacobi_smooth;
+    case 1: return optimal_jacobi_smooth;
+    case 2: return cg_smooth;
+    case 5: return gs_smooth;
+    default: throw HotError("No proper smoother is selected!");
+    }
+}
+
+} // namespace hot_b200

@@ -1,0 +1,112 @@
+"""The C++ host mirror (include/hot_b200_host.hpp: MpmSimulationB200::advanceOneTimeStep, host-evaluated collision
+objects = a8, HOTSettings / flag parsing, -smoother function pointers) against the CPU oracle stepping the same scene
+with the same reference flags.  The oracle side evaluates a8 in numpy (HalfSpace STICKY / SLIP,
+CollisionObject.cpp:108-149,384-452; MpmSimulationBase.cpp:1139-1184)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from hot_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def host_step(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("cpp") / "host_step")
+    lib = os.path.join(ROOT, "hot_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "host_step.cpp"), "-o", exe, "-L", lib, "-lhot_b200",
+                           f"-Wl,-rpath,{lib}", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    return exe
+
+
+def _rotate_to_x(a):
+    a = a / np.linalg.norm(a)
+    v = np.cross(a, [1.0, 0, 0]); c = a[0]
+    vx = np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+    return np.eye(3) + vx + vx @ vx / (1 + c)
+
+
+def _oracle_step(o, dt, ground, gtype, opts):
+    """MultigridSimulation::advanceOneTimeStep with the oracle: sort, P2G, a8 in numpy, BE solve, G2P"""
+    o.set_dt_gravity(dt, (0, -9.8, 0))
+    o.sortParticlesAndPolluteGrid(); o.particlesToGrid()
+    coord = o.get_id2coord(); idx, _, v = o.get_grid()
+    n = o.num_nodes
+    vn = np.zeros((n, 3)); vn[idx[idx >= 0]] = v[idx >= 0]
+    inside = coord[:, 1] * o.dx - ground <= 0
+    bc = np.nonzero(inside)[0].astype(np.int32)
+    nrm = np.array([0.0, 1.0, 0.0])
+    if gtype == 1:       # STICKY: v = 0, P = 0
+        vi = np.zeros((len(bc), 3)); P = np.zeros((len(bc), 9)); R = np.tile(np.eye(3).reshape(1, 9), (len(bc), 1)); slip = np.zeros(len(bc), np.int32)
+    else:                # SLIP: remove the normal component, P = I - n n^T, R rotates n onto x
+        vi = vn[bc] - np.outer(vn[bc] @ nrm, nrm)
+        P = np.tile((np.eye(3) - np.outer(nrm, nrm)).T.reshape(1, 9), (len(bc), 1))
+        R = np.tile(_rotate_to_x(nrm).T.reshape(1, 9), (len(bc), 1)); slip = np.ones(len(bc), np.int32)
+    Rinv = R.reshape(-1, 3, 3).transpose(0, 2, 1).reshape(-1, 9)
+    mode = 1 if (opts.get("bcproject") and opts.get("bc_type") == 1) else 0
+    o.set_bc(bc, P=P, R=R, Rinv=Rinv, slip=slip, dv_bc=vi - vn[bc], mode=mode)
+    kw = {k: v for k, v in opts.items() if k != "bc_type"}
+    log = o.backwardEulerStep(**kw)
+    o.gridToParticles(dt)
+    return log, n, len(bc)
+
+
+CASES = {
+    "hot_sticky": (1, ["-lsolver", "3", "-Ainv", "1", "--project", "--linesearch", "--bcproject", "-mg_level", "3", "-mg_times", "1",
+                       "-coarseSolver", "2", "-smoother", "5", "--usecn", "-cneps", "1e-7"],
+                   dict(lsolver=3, Ainv=1, project=1, linesearch=1, bcproject=1, mg_level=3, mg_times=1, coarse_solver=2, smoother=5, usecn=1, cneps=1e-7)),
+    "pnmf_sticky": (1, ["-lsolver", "2", "-Ainv", "1", "--project", "--linesearch", "--matfree", "--usecn", "-cneps", "1e-7"],
+                    dict(lsolver=2, Ainv=1, project=1, linesearch=1, matfree=1, bcproject=0, mg_level=1, mg_times=1, smoother=0, coarse_solver=0,
+                         usecn=1, cneps=1e-7)),
+    "hot_slip": (2, ["-lsolver", "3", "-Ainv", "1", "--project", "--linesearch", "--bcproject", "-bc", "1", "-mg_level", "3", "-mg_times", "1",
+                     "-coarseSolver", "2", "-smoother", "5", "--usecn", "-cneps", "1e-7"],
+                 dict(lsolver=3, Ainv=1, project=1, linesearch=1, bcproject=1, bc_type=1, mg_level=3, mg_times=1, coarse_solver=2, smoother=5,
+                      usecn=1, cneps=1e-7)),
+}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_cpp_host_time_steps_match_oracle(host_step, oracle, tmp_path, case):
+    gtype, flags, opts = CASES[case]
+    sc = scenes.block((6, 6, 6), 1.0 / 32, ppc=6, origin_cells=(8, 8, 8), rho=1000.0, E=2.5e4, nu=0.4, seed=3)
+    sc["V"][:, 1] -= 0.5                                             # falling onto the ground
+    ground = 9.0 / 32                                                # one cell into the box: the lowest node layers collide
+    n = len(sc["mass"]); steps, dt = 2, 2e-3
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<qd", n, sc["dx"]))
+        for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam"):
+            f.write(np.ascontiguousarray(sc[k], dtype=np.float64).tobytes())
+    out = subprocess.run([host_step, fin, fout, str(steps), repr(dt), repr(ground), str(gtype)] + flags, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    raw = np.fromfile(fout, dtype=np.float64, offset=8)
+    X = raw[:3 * n].reshape(n, 3); V = raw[3 * n:6 * n].reshape(n, 3); F = raw[15 * n:24 * n].reshape(n, 9)
+    rec = raw[24 * n:].reshape(steps, 5)
+
+    o = oracle.OracleSim(sc["dx"])
+    o.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
+    for s in range(steps):
+        log, nn, nbc = _oracle_step(o, dt, ground, gtype, opts)
+        assert bool(rec[s, 1]) == log["converged"]      # Newton may stop at its 3-iteration cap like the reference
+        assert int(rec[s, 0]) == log["iterations"] and int(rec[s, 2]) == nn and int(rec[s, 3]) == nbc and nbc > 0
+        assert abs(rec[s, 4] - log["residual_norm"][-1]) <= 1e-5 * log["residual_norm"][0]
+    po = o.get_particles()
+    for a, b in ((X, po["X"]), (V, po["V"]), (F, po["F"])):
+        assert np.abs(a - b).max() < 1e-6 * np.abs(b).max()
+
+
+def test_cpp_host_rejects_unknown_flag(host_step, tmp_path):
+    fin = str(tmp_path / "in.bin")
+    sc = scenes.block((3, 3, 3), 1.0 / 32, ppc=2, seed=1)
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<qd", len(sc["mass"]), sc["dx"]))
+        for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam"):
+            f.write(np.ascontiguousarray(sc[k], dtype=np.float64).tobytes())
+    out = subprocess.run([host_step, fin, str(tmp_path / "o.bin"), "1", "1e-3", "0.2", "1", "--l2norm"], capture_output=True, text=True)
+    assert out.returncode == 1 and "Unknown flag" in out.stderr      # like the reference
