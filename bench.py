@@ -112,6 +112,40 @@ def cpu_baseline(sc, reps, warmup=1):
     return n, times, cores, t_sort
 
 
+def cpu_vcycle_baseline(full_nodes, reps=3):
+    """V-cycle ms of the CPU path (oracle = OpenMP restatement of the reference's block-ELL / coloured-GS code) on a BOUNDED
+    sample of the C2 workload: a 22x40x22-cell slab of the same bar (same dx, ppc, material, end-cap BCs), scaled to the
+    full node count for the headline comparison."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as orc
+    from hot_b200 import scenes
+    sc = scenes.block((22, 40, 22), 0.12 / 22, ppc=12, origin_cells=(16, 16, 16), rho=2000.0, E=1e5, nu=0.3, seed=0)
+    o = orc.OracleSim(sc["dx"])
+    o.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
+    o.set_dt_gravity(SOLVER_DT, (0.0, 0.0, 0.0))
+    o.sortParticlesAndPolluteGrid(); nn = o.particlesToGrid()
+    bc = end_cap_bc(o.get_id2coord())
+    o.set_bc(bc, P=np.zeros((len(bc), 9)), dv_bc=np.zeros((len(bc), 3)))
+    o.backupStrain(); o.updateState()
+    t0 = time.perf_counter(); o.buildMatrix(True); t_asm = time.perf_counter() - t0
+    t0 = time.perf_counter(); o.buildMultigrid(levels=3, smoother=5, coarseSolver=2, Ainv=1, times=1); t_mg = time.perf_counter() - t0
+    r = o.computeResidual()
+    o.vcycle(r)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); o.vcycle(r); ts.append(time.perf_counter() - t0)
+    x = np.ones((nn, 3))
+    t0 = time.perf_counter(); o.multiply(x); t_mf = time.perf_counter() - t0
+    ms = 1e3 * float(np.mean(ts))
+    cores = int(orc.lib.orc_num_threads())
+    n_p = o.N
+    o.close()
+    return {"vcycle_ms_sample": ms, "vcycle_ms_scaled_to_full": ms * full_nodes / nn, "cores": cores, "kind": "port",
+            "sample": f"22x40x22-cell slab of the C2 bar: {n_p} particles, {nn} nodes (full workload {full_nodes} nodes); {reps} V-cycles after 1 warm-up",
+            "build_matrix_ms_sample": 1e3 * t_asm, "build_mg_ms_sample": 1e3 * t_mg, "hessian_apply_mf_ms_sample": 1e3 * t_mf,
+            "sample_particles": n_p, "sample_nodes": nn}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -306,6 +340,8 @@ def run_ours(args):
             cms = float(np.mean(ctimes))
             cpu = {"value": cn / cms / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"whole workload ({cn} particles), {args.cpu_reps} timed P2G+G2P steps of the OpenMP oracle after 1 warm-up"}
+            if solver is not None:
+                cpu["vcycle"] = cpu_vcycle_baseline(n_nodes)
         else:
             cpu = None
         line = {
