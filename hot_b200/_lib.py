@@ -13,6 +13,7 @@ class LibraryMissing(RuntimeError):
 
 
 _lib = None
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_long)
 
 HOT_LOG_CAP = 256
 
@@ -91,6 +92,9 @@ def load_library(path=LIB_PATH):
         "hot_get_mass_matrix": (C.c_int, [vp, vp]),
         "hot_set_dv": (C.c_int, [vp, vp]),
         "hot_g2p": (C.c_int, [vp, C.c_double, _c_int_p]),
+        "hot_set_partition": (C.c_int, [vp, C.c_int, C.c_int, ALLREDUCE_FN, vp]),
+        "hot_set_exchange_buffer": (C.c_int, [vp, vp, C.c_long]),
+        "hot_get_partition": (C.c_int, [vp, C.POINTER(C.c_long)]),
         "hot_set_dt_gravity": (C.c_int, [vp, C.c_double, vp]),
         "hot_set_project": (C.c_int, [vp, C.c_int]),
         "hot_set_bc": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),

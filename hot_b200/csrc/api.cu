@@ -342,6 +342,33 @@ int hot_set_dv(hot_sim* s, const double* dv)
 
 int hot_g2p(hot_sim* s, double dt, int* flags) { return g2p(s, dt, flags); }
 
+// ---- row (e): one object over several GPUs (dist.cu) ---------------------------------------------------------------
+int hot_set_partition(hot_sim* s, int rank, int world, hot_allreduce_fn fn, void* user)
+{
+    if (world < 1 || world > 32 || rank < 0 || rank >= world) return fail(s, "hot_set_partition: need 0 <= rank < world <= 32");
+    if (world > 1 && !fn) return fail(s, "hot_set_partition: an all-reduce callback is required for world > 1");
+    s->rank = rank;
+    s->world = world;
+    s->allreduce = fn;
+    s->allreduce_user = user;
+    s->sorted = false; // the partition is computed by the next hot_sort_and_activate
+    s->p2g_done = false;
+    return 0;
+}
+int hot_set_exchange_buffer(hot_sim* s, void* device_ptr, long capacity_doubles)
+{
+    s->xbuf = (double*)device_ptr;
+    s->xbuf_cap = device_ptr ? capacity_doubles : 0;
+    return 0;
+}
+int hot_get_partition(hot_sim* s, long* out8)
+{
+    if (!s->sorted) return fail(s, "hot_get_partition: call hot_sort_and_activate first");
+    out8[0] = s->g0; out8[1] = s->g1; out8[2] = s->p0; out8[3] = s->p1;
+    out8[4] = s->dof0; out8[5] = s->dof1; out8[6] = s->n_iface; out8[7] = s->world;
+    return 0;
+}
+
 // ---- force model (force.cu): host-buffer wrappers around the device-resident operators ---------------------------
 static int upload_dof(hot_sim* s, DevBuf<double>& buf, const double* host, size_t per_node = 3)
 {

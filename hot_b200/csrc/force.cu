@@ -431,6 +431,11 @@ __global__ void k_set_bc_dv(int n_bc, const int* __restrict__ node, const double
 #pragma unroll
     for (int d = 0; d < 3; ++d) dv[3 * (size_t)node[b] + d] = dv_bc ? dv_bc[3 * b + d] : 0.0;
 }
+__global__ void k_add(long n, const double* __restrict__ x, double* __restrict__ y)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
 __global__ void k_cn_finish(int n, const double* __restrict__ mass, double factor, double* __restrict__ tol)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -528,7 +533,8 @@ int update_state(Sim* s, bool want_energy, double* energy)
     HOT_CUDA(s->group_psi.reserve(s->n_groups));
     {
         KTime t(s, KC_STRESS);
-        k_update_state<<<(unsigned)s->n_groups, US_THREADS, 0, st>>>(s->group_first.p, s->group_slot.p, s->nbr8.p, ps, s->P.X.p, s->P.Fn.p,
+        if (s->g1 > s->g0)
+        k_update_state<<<(unsigned)(s->g1 - s->g0), US_THREADS, 0, st>>>(s->group_first.p + s->g0, s->group_slot.p + s->g0, s->nbr8.p, ps, s->P.X.p, s->P.Fn.p,
             s->P.F.p, s->P.vol.p, s->P.mu.p, s->P.lam.p, s->f_stress.p, s->f_U.p, s->f_V.p, s->f_sig.p, s->P.gradV.p, s->dx, 1.0 / s->dx,
             s->dt, s->g_stride, s->g_v.p, s->g_idx.p, s->dv.p, s->group_psi.p);
         HOT_LAUNCHED(s);
@@ -538,16 +544,48 @@ int update_state(Sim* s, bool want_energy, double* energy)
     if (want_energy) {
         KTime t(s, KC_BLAS1);
         HOT_CUDA(s->red_out.reserve(64));
-        int rc = reduce_to<1>(s, s->n_groups, SumF{s->group_psi.p}, s->red_out.p + 8, nullptr);
+        // own particles' strain energy + own nodes' inertia / gravity terms, summed over the ranks
+        int rc = reduce_to<1>(s, s->g1 - s->g0, SumF{s->group_psi.p}, s->red_out.p + 8, nullptr);
         if (rc) return rc;
-        double h[2];
-        rc = reduce_to<2>(s, s->num_nodes, EnergyNodesF{s->dv.p, s->mass_matrix.p, s->gravity[0], s->gravity[1], s->gravity[2]},
+        const int d0 = s->world > 1 ? s->dof0 : 0, d1 = s->world > 1 ? s->dof1 : s->num_nodes;
+        rc = reduce_to<2>(s, d1 - d0, EnergyNodesF{s->dv.p + 3 * (size_t)d0, s->mass_matrix.p + d0, s->gravity[0], s->gravity[1], s->gravity[2]},
             s->red_out.p + 9, nullptr);
         if (rc) return rc;
         HOT_CUDA(cudaMemcpyAsync(s->h_red, s->red_out.p + 8, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
         HOT_CUDA(cudaStreamSynchronize(st));
-        h[0] = s->h_red[1]; h[1] = s->h_red[2];
-        if (energy) *energy = s->h_red[0] + h[0] / 2 - s->dt * h[1];
+        double h[3] = {s->h_red[0], s->h_red[1], s->h_red[2]};
+        rc = dist_allreduce_host(s, h, 3, 0);
+        if (rc) return rc;
+        if (energy) *energy = h[0] + h[1] / 2 - s->dt * h[2];
+    }
+    return 0;
+}
+
+// One particle->grid scatter of this rank's page groups into a DOF array.  Single GPU: straight into `out` (which already
+// holds the node-local terms).  Partitioned: into a zeroed scratch array, summed over the ranks on the interface nodes, then
+// added to `out` - so node-local terms are counted once.
+template <class Policy>
+int scatter_to_dofs(Sim* s, typename Policy::Args a, double* Policy::Args::*target, double* out, int comps)
+{
+    cudaStream_t st = s->stream;
+    const size_t m = (size_t)comps * s->num_nodes;
+    double* dst = out;
+    if (s->world > 1) {
+        HOT_CUDA(s->scat_tmp.reserve(m > 0 ? m : 1));
+        HOT_CUDA(cudaMemsetAsync(s->scat_tmp.p, 0, m * sizeof(double), st));
+        dst = s->scat_tmp.p;
+    }
+    a.*target = dst;
+    if (s->g1 > s->g0) {
+        k_plane_scatter<Policy><<<(unsigned)(s->g1 - s->g0), SC_THREADS, 0, st>>>(a, s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0,
+            s->nbr8.p);
+        HOT_LAUNCHED(s);
+    }
+    if (s->world > 1) {
+        int rc = dist_exchange_iface(s, dst, comps);
+        if (rc) return rc;
+        k_add<<<nblk((long)m), TPB, 0, st>>>((long)m, dst, out);
+        HOT_LAUNCHED(s);
     }
     return 0;
 }
@@ -563,9 +601,9 @@ int compute_residual(Sim* s, double* r)
         s->dt * s->gravity[2], r);
     HOT_LAUNCHED(s);
     ForcePolicy::Args a{s->P.stride, s->P.X.p, s->f_stress.p, s->dx, 1.0 / s->dx, s->dt, s->g_idx.p, r};
-    k_plane_scatter<ForcePolicy><<<(unsigned)s->n_groups, SC_THREADS, 0, st>>>(a, s->cell_start.p, s->group_slot.p, s->nbr8.p);
-    HOT_LAUNCHED(s);
-    int rc = bc_rotate(s, r, false);
+    int rc = scatter_to_dofs<ForcePolicy>(s, a, &ForcePolicy::Args::out, r, 3);
+    if (rc) return rc;
+    rc = bc_rotate(s, r, false);
     if (rc) return rc;
     return bc_project(s, r);
 }
@@ -576,9 +614,7 @@ int add_scaled_forces(Sim* s, double scale, double* f)
     if (!s->state_valid) return fail(s, "addScaledForces: call hot_update_state first");
     KTime t(s, KC_FORCE);
     ForcePolicy::Args a{s->P.stride, s->P.X.p, s->f_stress.p, s->dx, 1.0 / s->dx, scale, s->g_idx.p, f};
-    k_plane_scatter<ForcePolicy><<<(unsigned)s->n_groups, SC_THREADS, 0, s->stream>>>(a, s->cell_start.p, s->group_slot.p, s->nbr8.p);
-    HOT_LAUNCHED(s);
-    return 0;
+    return scatter_to_dofs<ForcePolicy>(s, a, &ForcePolicy::Args::out, f, 3);
 }
 
 int ensure_hessian(Sim* s)
@@ -588,9 +624,12 @@ int ensure_hessian(Sim* s)
     const size_t ps = s->P.stride;
     HOT_CUDA(s->f_H.reserve(45 * ps));
     KTime t(s, KC_STRESS);
-    k_build_hessian<<<(unsigned)((s->N + 127) / 128), 128, 0, s->stream>>>(s->N, ps, s->P.Fn.p, s->P.vol.p, s->P.mu.p, s->P.lam.p, s->f_U.p,
-        s->f_V.p, s->f_sig.p, s->project_pd ? 1 : 0, s->f_H.p);
-    HOT_LAUNCHED(s);
+    const long np = s->p1 - s->p0, o = s->p0; // own particles: every row pointer shifted by p0
+    if (np > 0) {
+        k_build_hessian<<<(unsigned)((np + 127) / 128), 128, 0, s->stream>>>(np, ps, s->P.Fn.p + o, s->P.vol.p + o, s->P.mu.p + o, s->P.lam.p + o,
+            s->f_U.p + o, s->f_V.p + o, s->f_sig.p + o, s->project_pd ? 1 : 0, s->f_H.p + o);
+        HOT_LAUNCHED(s);
+    }
     s->hessian_valid = true;
     return 0;
 }
@@ -606,9 +645,7 @@ int hessian_apply_mf(Sim* s, const double* x, double* b)
     k_mass_mul<<<nblk(3 * (long)nn), TPB, 0, st>>>(nn, s->mass_matrix.p, x, b);
     HOT_LAUNCHED(s);
     HessianPolicy::Args a{s->P.stride, s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, s->dt * s->dt, s->g_idx.p, x, b};
-    k_plane_scatter<HessianPolicy><<<(unsigned)s->n_groups, SC_THREADS, 0, st>>>(a, s->cell_start.p, s->group_slot.p, s->nbr8.p);
-    HOT_LAUNCHED(s);
-    return 0;
+    return scatter_to_dofs<HessianPolicy>(s, a, &HessianPolicy::Args::out, b, 3);
 }
 
 // MpmSimulationBase::addScaledForceDifferentials (-> MpmForceBase::addScaledForceDifferential, MpmForceBase.cpp:261-306):
@@ -619,9 +656,7 @@ int add_scaled_force_differentials(Sim* s, double scale, const double* x, double
     if (rc) return rc;
     KTime t(s, KC_HESSIAN);
     HessianPolicy::Args a{s->P.stride, s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, -scale, s->g_idx.p, x, f};
-    k_plane_scatter<HessianPolicy><<<(unsigned)s->n_groups, SC_THREADS, 0, s->stream>>>(a, s->cell_start.p, s->group_slot.p, s->nbr8.p);
-    HOT_LAUNCHED(s);
-    return 0;
+    return scatter_to_dofs<HessianPolicy>(s, a, &HessianPolicy::Args::out, f, 3);
 }
 
 // ImplicitSolverObjective::evaluatePerNodeCNTolerance, ImplicitSolver.h:667-696
@@ -633,8 +668,8 @@ int eval_cn_tolerance(Sim* s, double eps, double dt, double* tol)
     KTime t(s, KC_FORCE);
     HOT_CUDA(cudaMemsetAsync(tol, 0, (size_t)nn * sizeof(double), st));
     CNTolPolicy::Args a{s->P.stride, s->P.X.p, s->P.M.p, s->P.mu.p, s->P.lam.p, s->dx, 1.0 / s->dx, s->project_pd ? 1 : 0, s->g_idx.p, tol};
-    k_plane_scatter<CNTolPolicy><<<(unsigned)s->n_groups, SC_THREADS, 0, st>>>(a, s->cell_start.p, s->group_slot.p, s->nbr8.p);
-    HOT_LAUNCHED(s);
+    int rc = scatter_to_dofs<CNTolPolicy>(s, a, &CNTolPolicy::Args::out, tol, 1);
+    if (rc) return rc;
     k_cn_finish<<<nblk(nn), TPB, 0, st>>>(nn, s->mass_matrix.p, eps * 24 * s->dx * s->dx * dt, tol);
     HOT_LAUNCHED(s);
     return 0;

@@ -250,6 +250,11 @@ __global__ void k_diag_mf(long n, size_t ps, const double* __restrict__ X, const
             atomicAdd(D + 9 * (size_t)id + rr + 3 * ss, dt2 * v);
         }
 }
+__global__ void k_add9(long n, const double* __restrict__ x, double* __restrict__ y)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
 __global__ void k_diag_mf_init(int n, const double* __restrict__ mass, double* __restrict__ D)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -294,6 +299,7 @@ int fill_id2coord(Sim* s, int* coord_dev)
 
 int build_matrix(Sim* s, bool bcproject)
 {
+    if (s->world > 1) return fail(s, "buildMatrix: the assembled-matrix / multigrid path is single-GPU in this version; partitioned runs use --matfree (lsolver 2)");
     int rc = ensure_hessian(s);
     if (rc) return rc;
     cudaStream_t st = s->stream;
@@ -339,8 +345,24 @@ int build_diagonal_mf(Sim* s, int Ainv)
     KTime t(s, KC_ASSEMBLE);
     k_diag_mf_init<<<nblk(9 * (long)nn), TPB, 0, st>>>(nn, s->mass_matrix.p, s->diag_mf.p);
     HOT_LAUNCHED(s);
-    k_diag_mf<<<nblk(s->N * 27), TPB, 0, st>>>(s->N, s->P.stride, s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, s->dt * s->dt, s->g_idx.p, s->pid_sorted.p, s->slot_sorted.p, s->n_pages, s->diag_mf.p);
-    HOT_LAUNCHED(s);
+    double* dst = s->diag_mf.p;
+    if (s->world > 1) { // own particles into a zeroed scratch, summed on the interface nodes, added to the mass term
+        HOT_CUDA(s->scat_tmp.reserve(9 * (size_t)nn));
+        HOT_CUDA(cudaMemsetAsync(s->scat_tmp.p, 0, 9 * (size_t)nn * sizeof(double), st));
+        dst = s->scat_tmp.p;
+    }
+    const long np = s->p1 - s->p0;
+    if (np > 0) {
+        k_diag_mf<<<nblk(np * 27), TPB, 0, st>>>(np, s->P.stride, s->P.X.p + s->p0, s->f_H.p + s->p0, s->dx, 1.0 / s->dx, s->dt * s->dt, s->g_idx.p,
+            s->pid_sorted.p, s->slot_sorted.p, s->n_pages, dst);
+        HOT_LAUNCHED(s);
+    }
+    if (s->world > 1) {
+        rc = dist_exchange_iface(s, dst, 9);
+        if (rc) return rc;
+        k_add9<<<nblk(9 * (long)nn), TPB, 0, st>>>(9 * (long)nn, dst, s->diag_mf.p);
+        HOT_LAUNCHED(s);
+    }
     k_diag_invert<<<nblk(nn), TPB, 0, st>>>(nn, Ainv, s->diag_mf.p);
     HOT_LAUNCHED(s);
     return 0;

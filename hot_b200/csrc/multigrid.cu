@@ -915,9 +915,20 @@ int vec_scale(Sim* s, long n, double a, double* y)
     HOT_LAUNCHED(s);
     return 0;
 }
+// dot over the DOF vectors of level 0 (n = 3 num_nodes): own nodes + all-reduce when the object is partitioned
 int vec_dot(Sim* s, long n, const double* a, const double* b, double* dev_out, double* host_out)
 {
-    return reduce_to<1>(s, n, DotF{a, b}, dev_out, host_out);
+    if (s->world <= 1 || n != 3L * s->num_nodes) return reduce_to<1>(s, n, DotF{a, b}, dev_out, host_out);
+    HOT_CUDA(s->red_out.reserve(64));
+    if (!dev_out) dev_out = s->red_out.p;
+    const size_t o = 3 * (size_t)s->dof0;
+    int rc = reduce_to<1>(s, 3L * (s->dof1 - s->dof0), DotF{a + o, b + o}, dev_out, nullptr);
+    if (!rc) rc = dist_allreduce_buffer(s, dev_out, 1, 0);
+    if (rc || !host_out) return rc;
+    HOT_CUDA(cudaMemcpyAsync(s->h_red, dev_out, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
+    *host_out = s->h_red[0];
+    return 0;
 }
 
 // ---- hierarchy --------------------------------------------------------------------------------------------------------------

@@ -105,6 +105,7 @@ struct MGLevel {
     DevBuf<double> residual, initial_residual, sol, du, dAu, tmp;
 };
 
+
 struct Sim;
 // CUDA-event timing of one kernel class on the handle's stream (enabled by hot_timing)
 struct KTimers {
@@ -205,6 +206,21 @@ struct Sim {
     // HOTSettings (Projects/multigrid/Configurations.h:18-42)
     int mg_smoother = 5, mg_coarse = 2, mg_Ainv = 1, mg_levels = 3, mg_times = 1, mg_levelscale = 0;
     double mg_topomega = 0.1;
+    // ---- multi-GPU partition of ONE object (dist.cu): the sort / page table / DOF numbering are replicated on every rank
+    // (identical to the single-GPU result), particle work is split by contiguous page-group ranges, nodes are owned by
+    // the rank whose groups touch their page first (= contiguous DOF ranges), and scatter results are summed over the ranks
+    // on the interface nodes only (pages touched by >= 2 ranks) through the caller-provided all-reduce.
+    int rank = 0, world = 1;
+    int (*allreduce)(void* user, int op, long count) = nullptr; // (user, op 0 sum / 1 max / 2 reserve, count of doubles in the exchange buffer)
+    void* allreduce_user = nullptr;
+    double* xbuf = nullptr; // caller-owned device exchange buffer
+    long xbuf_cap = 0;
+    long g0 = 0, g1 = 0, p0 = 0, p1 = 0; // own page groups [g0, g1) and sorted particles [p0, p1)
+    int dof0 = 0, dof1 = 0; // own DOF ids
+    int n_iface = 0;
+    DevBuf<int> iface_dof, group_rank;
+    DevBuf<unsigned> page_mask;
+    DevBuf<double> scat_tmp;
     DevBuf<double> sv[32]; // solver work vectors (solver.cu)
     bool dv0_valid = false;
     double vc_ms[10][4]; // per-level [smooth, restrict, prolongate, merge] of the last timed V-cycle
@@ -260,6 +276,12 @@ int add_scaled_forces(Sim* s, double scale, double* f);
 int add_scaled_force_differentials(Sim* s, double scale, const double* x, double* f);
 int hessian_apply_mf(Sim* s, const double* x, double* b);
 int eval_cn_tolerance(Sim* s, double eps, double dt, double* tol);
+// dist.cu
+int dist_after_sort(Sim* s); // group / particle ranges of this rank
+int dist_after_numbering(Sim* s); // page ownership, DOF ranges, interface node list
+int dist_allreduce_buffer(Sim* s, double* dev, long count, int op); // whole device array, in place
+int dist_exchange_iface(Sim* s, double* v, int comps); // sum over ranks on the interface nodes of a DOF array with `comps` per node
+int dist_allreduce_host(Sim* s, double* host, int count, int op); // a few scalars
 // matrix.cu
 int fill_id2coord(Sim* s, int* coord_dev);
 int build_matrix(Sim* s, bool bcproject);

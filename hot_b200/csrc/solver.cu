@@ -92,7 +92,9 @@ int residual_norms(Objective& O, const double* r, double* l2, double* scaled)
 {
     Sim* s = O.s;
     double h[2];
-    RC(reduce_to<2>(s, s->num_nodes, CNNormF{r, O.opt.usecn ? s->cn_tol.p : nullptr}, s->red_out.p + 16, h));
+    const int d0 = s->world > 1 ? s->dof0 : 0, d1 = s->world > 1 ? s->dof1 : s->num_nodes;
+    RC(reduce_to<2>(s, d1 - d0, CNNormF{r + 3 * (size_t)d0, O.opt.usecn ? s->cn_tol.p + d0 : nullptr}, s->red_out.p + 16, h));
+    RC(dist_allreduce_host(s, h, 2, 0));
     *l2 = sqrt(h[1]);
     *scaled = h[0];
     return 0;
@@ -410,6 +412,8 @@ int hot_backward_euler_step(hot_sim* s, const hot_solver_options* opt, hot_solve
     if (!s->p2g_done) return fail(s, "backwardEulerStep: call hot_p2g (and hot_set_bc) first");
     if (opt->lsolver != 2 && opt->lsolver != 3) return fail(s, "lsolver must be 2 (Newton + PCG) or 3 (L-BFGS)");
     if (opt->lsolver == 3 && opt->matfree) return fail(s, "LBFGS only works with project & with-matrix (Projects/multigrid/README:13-15)");
+    if (s->world > 1 && !(opt->lsolver == 2 && opt->matfree))
+        return fail(s, "partitioned runs support the matrix-free PN-PCG solver (-lsolver 2 --matfree); the multigrid path is single-GPU in this version");
     Objective O;
     O.s = s;
     O.opt = *opt;
@@ -430,12 +434,17 @@ int hot_backward_euler_step(hot_sim* s, const hot_solver_options* opt, hot_solve
         if (rc) return rc;
         unsigned long long* mx = (unsigned long long*)(s->red_out.p + 32);
         HOT_CUDA(cudaMemsetAsync(mx, 0, sizeof(*mx), s->stream));
-        k_max_dpdf_norm<<<nblk(s->N), TPB, 0, s->stream>>>(s->N, s->P.mu.p, s->P.lam.p, s->project_pd ? 1 : 0, mx);
-        HOT_LAUNCHED(s);
+        if (s->p1 > s->p0) {
+            k_max_dpdf_norm<<<nblk(s->p1 - s->p0), TPB, 0, s->stream>>>(s->p1 - s->p0, s->P.mu.p + s->p0, s->P.lam.p + s->p0, s->project_pd ? 1 : 0, mx);
+            HOT_LAUNCHED(s);
+        }
         if (!s->h_red) HOT_CUDA(cudaMallocHost((void**)&s->h_red, 64 * sizeof(double)));
         HOT_CUDA(cudaMemcpyAsync(s->h_red, mx, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
         HOT_CUDA(cudaStreamSynchronize(s->stream));
-        tol = opt->cneps * s->dt * 24 * std::sqrt((double)s->num_nodes) * s->dx * s->dx * s->h_red[0];
+        double nmax = s->h_red[0];
+        rc = dist_allreduce_host(s, &nmax, 1, 1);
+        if (rc) return rc;
+        tol = opt->cneps * s->dt * 24 * std::sqrt((double)s->num_nodes) * s->dx * s->dx * nmax;
     }
     if (log) log->tolerance = tol;
     const double cg_tol = opt->usecn ? tol : 1.0; // cg.setTolerance(1) in the objective ctor, maxcntol with --usecn

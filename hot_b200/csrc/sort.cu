@@ -366,7 +366,7 @@ int sort_and_activate(Sim* s)
     s->num_nodes = 0;
     s->sorted = true;
     s->p2g_done = false;
-    return 0;
+    return dist_after_sort(s);
 }
 
 int number_nodes(Sim* s)

@@ -213,14 +213,25 @@ int p2g(Sim* s)
     {
         KTime t(s, KC_P2G);
         P2GPolicy::Args a{s->P.stride, s->P.X.p, s->P.V.p, s->P.M.p, s->P.C.p, s->dx, 1.0 / s->dx, gn, s->g_m.p, s->g_v.p};
-        k_plane_scatter<P2GPolicy><<<(unsigned)s->n_groups, SC_THREADS, 0, st>>>(a, s->cell_start.p, s->group_slot.p, s->nbr8.p);
-        HOT_LAUNCHED(s);
+        if (s->g1 > s->g0) {
+            k_plane_scatter<P2GPolicy><<<(unsigned)(s->g1 - s->g0), SC_THREADS, 0, st>>>(a, s->cell_start.p + s->g0 * (Geo::E + 1),
+                s->group_slot.p + s->g0, s->nbr8.p);
+            HOT_LAUNCHED(s);
+        }
     }
     int rc;
+    if (s->world > 1) { // once per step: the replicated DOF numbering needs the complete mass field on every rank
+        KTime t(s, KC_TRANSFER);
+        rc = dist_allreduce_buffer(s, s->g_m.p, (long)gn, 0);
+        if (!rc) rc = dist_allreduce_buffer(s, s->g_v.p, 3 * (long)gn, 0);
+        if (rc) return rc;
+    }
     {
         KTime t(s, KC_NUMBER);
         rc = number_nodes(s);
     }
+    if (rc) return rc;
+    rc = dist_after_numbering(s);
     if (rc) return rc;
     s->p2g_done = true;
     return 0;
@@ -235,7 +246,8 @@ int g2p(Sim* s, double dt, int* flags)
     HOT_CUDA(cudaMemsetAsync(s->flags.p, 0, 2 * sizeof(int), st));
     {
         KTime t(s, KC_G2P);
-        k_g2p<<<(unsigned)s->n_groups, G2P_THREADS, 0, st>>>(s->group_first.p, s->group_slot.p, s->nbr8.p, s->P.stride, s->P.X.p,
+        if (s->g1 > s->g0)
+        k_g2p<<<(unsigned)(s->g1 - s->g0), G2P_THREADS, 0, st>>>(s->group_first.p + s->g0, s->group_slot.p + s->g0, s->nbr8.p, s->P.stride, s->P.X.p,
             s->P.V.p, s->P.C.p, s->P.F.p, s->P.gradV.p, s->dx, 1.0 / s->dx, dt, s->apic_rpic_ratio, s->cfl, s->g_stride, s->g_v.p,
             s->g_idx.p, s->dv.p, s->flags.p);
         HOT_LAUNCHED(s);

@@ -7,7 +7,7 @@ libhot_b200.so on the GPU; numpy arrays are only the caller-owned host buffers o
 import ctypes as C
 import numpy as np
 
-from ._lib import load_library, SolverOptions, SolveLog
+from ._lib import load_library, SolverOptions, SolveLog, ALLREDUCE_FN
 
 
 class HotError(RuntimeError):
@@ -401,3 +401,30 @@ class MpmSimulationB200:
         x = _f64(x, (self.num_nodes, 3)); f = _f64(f, (self.num_nodes, 3)).copy()
         self._check(self._lib.hot_add_scaled_force_differentials(self._h, float(scale), _ptr(x), _ptr(f)))
         return f
+
+    # ---- one object over several GPUs (include/hot_b200.h "row (e)")
+    def set_partition(self, rank, world, allreduce=None, alloc=None):
+        """allreduce(buffer, op, count): sum (op 0) / max (op 1) of buffer[:count] over the ranks, in place, on the handle's stream.
+        alloc(n_doubles) -> (object keeping the memory alive, device pointer).  See hot_b200.dist.torch_partition."""
+        self._xkeep = None
+
+        def cb(user, op, count):
+            try:
+                if op == 2:
+                    self._xkeep, ptr = alloc(int(count) + int(count) // 4 + 1024)
+                    self._xcap = int(count) + int(count) // 4 + 1024
+                    self._lib.hot_set_exchange_buffer(self._h, C.c_void_p(int(ptr)), self._xcap)
+                else:
+                    allreduce(self._xkeep, int(op), int(count))
+                return 0
+            except Exception as e:  # pragma: no cover - surfaces as HotError through the return code
+                import traceback; traceback.print_exc()
+                return 1
+
+        self._cb = ALLREDUCE_FN(cb) if world > 1 else ALLREDUCE_FN(0)
+        self._check(self._lib.hot_set_partition(self._h, int(rank), int(world), self._cb, None))
+
+    def get_partition(self):
+        out = (C.c_long * 8)()
+        self._check(self._lib.hot_get_partition(self._h, out))
+        return dict(zip(("group0", "group1", "particle0", "particle1", "dof0", "dof1", "n_interface", "world"), [int(v) for v in out]))

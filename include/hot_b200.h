@@ -90,6 +90,22 @@ int hot_get_mass_matrix(hot_sim* h, double* mass);
 int hot_set_dv(hot_sim* h, const double* dv);
 int hot_g2p(hot_sim* h, double dt, int* flags /* [0] faster than dx, [1] faster than cfl*dx/2 */);
 
+/* ---- one object over the GPUs of a box (no counterpart in the reference, which is single-process: SURVEY 2a / 8e) ------
+ * Every rank holds all particle positions and runs the same sort / page activation / DOF numbering (bit-identical on
+ * every rank and to the single-GPU result).  Page groups are cut into `world` contiguous ranges balanced by particle count;
+ * a rank runs the particle kernels on its range only, owns the nodes whose pages its groups touch first, and scatter results
+ * are summed over the ranks on the interface nodes only (pages touched by >= 2 ranks) through the caller's all-reduce:
+ * op 0 = sum, 1 = max over `count` doubles at the start of the exchange buffer, enqueued on the handle's stream (e.g.
+ * ncclAllReduce, or torch.distributed.all_reduce on a tensor aliasing the buffer); op 2 = "make the exchange buffer at
+ * least `count` doubles" (the callback answers with hot_set_exchange_buffer).  Returns non-zero on failure.
+ * Supported partitioned path: sort, P2G, G2P, updateState, residual, matrix-free Hessian apply, block-Jacobi diagonal, CN
+ * tolerance and the matrix-free PN-PCG solve (-lsolver 2 --matfree); the assembled-matrix / multigrid path is single-GPU. */
+typedef int (*hot_allreduce_fn)(void* user, int op, long count);
+int hot_set_partition(hot_sim* h, int rank, int world, hot_allreduce_fn fn, void* user);
+int hot_set_exchange_buffer(hot_sim* h, void* device_ptr, long capacity_doubles);
+/* {group0, group1, particle0, particle1 (sorted index ranges), dof0, dof1 (owned DOF ids), interface nodes, world} */
+int hot_get_partition(hot_sim* h, long* out8);
+
 /* ---- force model: the operator surface ImplicitSolverObjective drives (Projects/multigrid/ImplicitSolver.h) ------- */
 /* simulation.dt / simulation.gravity (MpmSimulationBase.h:69-131) */
 int hot_set_dt_gravity(hot_sim* h, double dt, const double* gravity3);
