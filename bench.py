@@ -31,8 +31,17 @@ METRIC = "Mparticles/s P2G+G2P"
 UNIT = "Mparticles/s"
 
 
-def make_workload(name, rank=0):
+def make_workload(name, rank=0, world=1):
+    """N = 1: the named configuration.  N > 1 (weak scaling): ONE object N times as long (the bar / column extended along y),
+    partitioned over the N GPUs by page ranges with ghost exchange - every rank builds the same object (seed 0)."""
     from hot_b200 import scenes
+    if world > 1:
+        cells, dx, ppc, kw = {"c1": ((18, 18, 18), 1.0 / 64, 8, dict(rho=1000.0, E=2.5e4, nu=0.4)),
+                              "c2": ((22, 165, 22), 0.12 / 22, 12, dict(rho=2000.0, E=1e5, nu=0.3)),
+                              "c4": ((100, 400, 25), 1.0 / 512, 8, dict(rho=1600.0, E=1e6, nu=0.3))}[name]
+        cells = (cells[0], cells[1] * world, cells[2])
+        sc = scenes.block(cells, dx, ppc=ppc, origin_cells=(16, 16, 16), seed=0, **kw)
+        return sc, f"{name.upper()} object extended {world}x along y: {cells[0]}x{cells[1]}x{cells[2]} cells ppc {ppc} ({len(sc['mass'])} particles), ONE object partitioned over {world} GPUs"
     sc = {"c1": scenes.config_c1, "c2": scenes.config_c2, "c4": scenes.config_c4}[name](seed=rank)
     desc = {"c1": "C1 box drop 18^3 cells ppc 8 (46 656 particles)",
             "c2": "C2 twisting-bar block 22x165x22 cells ppc 12 (958 320 particles, 256^3-class SPGrid)",
@@ -224,6 +233,25 @@ def solver_leg(sim, sc, args):
     return out
 
 
+def dist_solver_leg(sim, sc, args):
+    """partitioned solver-side kernels (matrix-free path): Hessian apply / updateState / residual with interface-only exchange"""
+    n = len(sc["mass"])
+    sim.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
+    sim.set_dt_gravity(SOLVER_DT, (0.0, 0.0, 0.0))
+    sim.sortParticlesAndPolluteGrid()
+    nn = sim.particlesToGrid()
+    bc = end_cap_bc(sim.get_id2coord())
+    sim.set_bc(bc, P=np.zeros((len(bc), 9)), dv_bc=np.zeros((len(bc), 3)))
+    sim.backupStrain()
+    sim.updateState()
+    reps = max(3, min(args.steps, 20))
+    part = sim.get_partition()
+    out = {"dt": SOLVER_DT, "grid_nodes": nn, "interface_nodes": part["n_interface"], "own_particles": part["particle1"] - part["particle0"]}
+    for op in ("hessian_apply", "update_state", "residual"):
+        out[op] = {"ms": sim.op_bench(op, reps)}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -237,12 +265,15 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    # weak scaling: every rank owns an independent object of the named shape (the path shards by objects/pages
-    # with no data-path collective; ghost exchange between page partitions of ONE object is a later row of 8e)
-    sc, desc = make_workload(args.workload, rank)
+    # weak scaling on ONE object: N GPUs carry an object N times as long, cut into contiguous page-group ranges; the data-path
+    # exchange is the per-step all-reduce of the grid mass / momentum (P2G) through NCCL; G2P gathers need none
+    sc, desc = make_workload(args.workload, rank, world)
     n = len(sc["mass"])
     stream = torch.cuda.current_stream()
     sim = hot_b200.MpmSimulationB200(sc["dx"], device=local, stream=stream.cuda_stream)
+    if world > 1:
+        from hot_b200.dist import torch_partition
+        torch_partition(sim, dev)
     sim.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
     sim.sortParticlesAndPolluteGrid()
     n_nodes = sim.particlesToGrid()
@@ -311,22 +342,27 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    solver = solver_leg(sim, sc, args) if not args.no_solver else None
+    if args.no_solver:
+        solver = None
+    elif world == 1:
+        solver = solver_leg(sim, sc, args)
+    else:
+        solver = dist_solver_leg(sim, sc, args)
+    part = sim.get_partition() if world > 1 else None
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([float(n)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     total_ms, e2e_ms = [float(x) for x in t.tolist()]
-    n_total = float(cnt.item())
+    n_total = float(n)                         # one object: every rank holds the same particle count n = whole job
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = n_total / (ms_per_step * 1e-3) / 1e6
         peak, peak_src = peaks()
         # roofline of the dominant kernel; algorithmic bytes per SURVEY.md 8d (fp64)
-        alg = {"p2g": 128 * n + 32 * n_nodes, "g2p": 288 * n + 24 * n_nodes}
+        n_own = n // world                       # particle kernels run on this rank's share; the grid terms are whole-object
+        alg = {"p2g": 128 * n_own + 32 * n_nodes, "g2p": 288 * n_own + 24 * n_nodes}
         per = {k: (kt[k][0] / kt[k][1]) for k in ("p2g", "g2p", "number_nodes") if k in kt}
         dom = max(("p2g", "g2p"), key=lambda k: per.get(k, 0.0))
         ach = alg[dom] / (per[dom] * 1e-3) / 1e9
@@ -335,7 +371,7 @@ def run_ours(args):
                 "per_kernel": {k: {"ms": per[k], "alg_GBps": (alg[k] / (per[k] * 1e-3) / 1e9 if k in alg else None),
                                    "frac": (alg[k] / (per[k] * 1e-3) / 1e9 / peak if k in alg else None)} for k in per},
                 "combined_p2g_g2p": {"alg_bytes": alg["p2g"] + alg["g2p"], "frac": (alg["p2g"] + alg["g2p"]) / (ms_per_step * 1e-3) / 1e9 / peak}}
-        if args.cpu_reps > 0:
+        if args.cpu_reps > 0 and world == 1:
             cn, ctimes, cores, _ = cpu_baseline(sc, args.cpu_reps)
             cms = float(np.mean(ctimes))
             cpu = {"value": cn / cms / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
@@ -348,9 +384,11 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": desc, "particles_per_gpu": n, "grid_nodes": n_nodes, "pages": sim.num_pages,
+            "config": {"workload": desc, "particles_per_gpu": n // world, "grid_nodes": n_nodes, "pages": sim.num_pages,
                        "l2": "flushed before every timed step (256 MiB memset)",
-                       "parallelism": f"{world} independent objects (one per GPU), no data-path collective"},
+                       "parallelism": ("single GPU" if world == 1 else
+                                       f"one object over {world} GPUs: contiguous page-group ranges, replicated sort / DOF numbering, NCCL all-reduce of grid mass+momentum per P2G "
+                                       f"(interface nodes per rank pair boundary: {part['n_interface']})")},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "includes": "H2D from pinned host, sort, P2G, G2P(dt), D2H of X,V,C,F"},

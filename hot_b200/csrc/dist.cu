@@ -78,6 +78,7 @@ int dist_after_sort(Sim* s)
 {
     s->g0 = 0; s->g1 = s->n_groups; s->p0 = 0; s->p1 = s->N;
     s->dof0 = 0; s->dof1 = 0; s->n_iface = 0;
+    s->iface_valid = false;
     if (s->world <= 1) return 0;
     // balanced contiguous split of the page groups by particle count (host: n_groups + 1 ints)
     std::vector<int> first((size_t)s->n_groups + 1);
@@ -108,6 +109,7 @@ int dist_after_numbering(Sim* s)
         s->dof0 = 0; s->dof1 = s->num_nodes;
         return 0;
     }
+    if (s->iface_valid) return 0; // same sort -> same pages, same numbering
     cudaStream_t st = s->stream;
     const long gn = (long)s->g_stride;
     const int nn = s->num_nodes;
@@ -134,6 +136,7 @@ int dist_after_numbering(Sim* s)
     s->n_iface = s->hcount[16];
     s->dof0 = s->hcount[18] >= 0 ? s->hcount[17] : 0;
     s->dof1 = s->hcount[18] >= 0 ? s->hcount[18] + 1 : 0;
+    s->iface_valid = true;
     return 0;
 }
 

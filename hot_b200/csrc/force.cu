@@ -191,45 +191,82 @@ __global__ void __launch_bounds__(128) k_build_hessian(long n, size_t ps, const 
         }
 }
 
+// a13, first half: T_p = dt^2 * H~_p : grad x_p for every particle of a page group (CTA per group like k_update_state: the
+// group's x node tile is staged once, one thread per particle).  The scatter half reuses the force rasterisation kernel.
+__global__ void __launch_bounds__(US_THREADS) k_hessian_gather(const int* __restrict__ group_first, const int* __restrict__ group_slot,
+    const int* __restrict__ nbr8, size_t ps, const double* __restrict__ X, const double* __restrict__ H, double dx, double one_over_dx,
+    double scale, const int* __restrict__ g_idx, const double* __restrict__ x, double* __restrict__ Tout)
+{
+    __shared__ double tile[3 * TILE];
+    __shared__ int s_nbr[8];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const int first = group_first[g], end = group_first[g + 1];
+    if (tid < 8) s_nbr[tid] = nbr8[(size_t)group_slot[g] * 8 + tid];
+    __syncthreads();
+    for (int n = tid; n < TILE; n += US_THREADS) {
+        long a = tile_to_grid(n, s_nbr);
+        double nv[3] = {0, 0, 0};
+        if (a >= 0) {
+            int id = g_idx[a];
+            if (id >= 0)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) nv[d] = x[3 * (size_t)id + d];
+        }
+        tile[n] = nv[0]; tile[TILE + n] = nv[1]; tile[2 * TILE + n] = nv[2];
+    }
+    __syncthreads();
+    for (int s = first + tid; s < end; s += US_THREADS) {
+        SplineEval sp;
+        sp.eval(X, ps, s, dx, one_over_dx, true);
+        double G[9], T[9];
+        gather_gradient(tile, sp, one_over_dx, G);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) T[q] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+#pragma unroll
+            for (int i = 0; i <= j; ++i) {
+                const double h = H[(size_t)tri(i, j) * ps + s];
+                T[i] += h * G[j];
+                if (i != j) T[j] += h * G[i];
+            }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) Tout[q * ps + s] = scale * T[q];
+    }
+}
+
 // ---- scatters -------------------------------------------------------------------------------------------------------
 // Common record of the two vector scatters (a12 force, a13 Hessian apply): node value = T grad w with a per-particle 3x3 T.
-//   [0..2] wy  [3..5] wz  [6..8] dwy/dx  [9..11] dwz/dx   then per x-plane i: T(:,0)*dwx_i/dx, T(:,1)*wx_i, T(:,2)*wx_i
+//   record: X(3)  T(9, column-major)
 struct TGradScatter {
-    static constexpr int NCH = 3, REC = 40;
-    __device__ __forceinline__ static void fill(const SplineEval& sp, double one_over_dx, const double* T, double* r)
+    static constexpr int NCH = 3, RAW = 12;
+    __device__ __forceinline__ static void fill(const double* X, size_t ps, size_t s, const double* T, double* r)
     {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            r[j] = sp.w[1][j];
-            r[3 + j] = sp.w[2][j];
-            r[6 + j] = one_over_dx * sp.dw[1][j];
-            r[9 + j] = one_over_dx * sp.dw[2][j];
-        }
+        for (int d = 0; d < 3; ++d) r[d * SC_PAD] = X[d * ps + s];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const double wx = sp.w[0][i], dwx = one_over_dx * sp.dw[0][i];
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                r[12 + 9 * i + q] = T[q] * dwx;
-                r[12 + 9 * i + 3 + q] = T[3 + q] * wx;
-                r[12 + 9 * i + 6 + q] = T[6 + q] * wx;
-            }
-        }
-        r[39] = 0.0;
+        for (int q = 0; q < 9; ++q) r[(3 + q) * SC_PAD] = T[q];
     }
-    __device__ __forceinline__ static void accumulate(const double* rec, int pl, double (&acc)[9][3])
+    __device__ __forceinline__ static void accumulate(const double* rec, double dx, double one_over_dx, int pl, double (&acc)[9][3])
     {
-        const double2* r2 = reinterpret_cast<const double2*>(rec);
-        const double2 a0 = r2[0], a1 = r2[1], a2 = r2[2], a3 = r2[3], a4 = r2[4], a5 = r2[5];
-        const double wy[3] = {a0.x, a0.y, a1.x}, wz[3] = {a1.y, a2.x, a2.y};
-        const double gy[3] = {a3.x, a3.y, a4.x}, gz[3] = {a4.y, a5.x, a5.y};
-        const double* p = rec + 12 + 9 * pl;
-        const double ax[3] = {p[0], p[1], p[2]}, ay[3] = {p[3], p[4], p[5]}, az[3] = {p[6], p[7], p[8]};
+        SplineEval sp;
+        sp.eval_rec(rec, dx, one_over_dx, true);
+        const double wx = pl == 0 ? sp.w[0][0] : (pl == 1 ? sp.w[0][1] : sp.w[0][2]);
+        const double dwx = one_over_dx * (pl == 0 ? sp.dw[0][0] : (pl == 1 ? sp.dw[0][1] : sp.dw[0][2]));
+        double ax[3], ay[3], az[3], gy[3], gz[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            ax[r] = rec[(3 + r) * SC_PAD] * dwx;
+            ay[r] = rec[(6 + r) * SC_PAD] * wx;
+            az[r] = rec[(9 + r) * SC_PAD] * wx;
+            gy[r] = one_over_dx * sp.dw[1][r];
+            gz[r] = one_over_dx * sp.dw[2][r];
+        }
 #pragma unroll
         for (int j = 0; j < 3; ++j)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const double c0 = wy[j] * wz[k], c1 = gy[j] * wz[k], c2 = wy[j] * gz[k];
+                const double c0 = sp.w[1][j] * sp.w[2][k], c1 = gy[j] * sp.w[2][k], c2 = sp.w[1][j] * gz[k];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) acc[j * 3 + k][r] += ax[r] * c0 + ay[r] * c1 + az[r] * c2;
             }
@@ -238,7 +275,7 @@ struct TGradScatter {
 
 // a12: rasterizeForceToTVStack: f_i -= scale * (vol P Fn^T) grad w   (MpmForceBase.cpp:100-153)
 struct ForcePolicy {
-    static constexpr int NCH = 3, REC = TGradScatter::REC, GATHER = 0;
+    static constexpr int NCH = 3, RAW = TGradScatter::RAW, GATHER = 0;
     struct Args {
         size_t ps;
         const double *X, *stress;
@@ -249,67 +286,14 @@ struct ForcePolicy {
     __device__ static void gather_node(const Args&, long, double (&)[3]) {}
     __device__ static void stage(const Args& a, size_t s, double* r, const double*)
     {
-        SplineEval sp;
-        sp.eval(a.X, a.ps, s, a.dx, a.one_over_dx, true);
         double T[9];
 #pragma unroll
         for (int q = 0; q < 9; ++q) T[q] = -a.scale * a.stress[q * a.ps + s];
-        TGradScatter::fill(sp, a.one_over_dx, T, r);
+        TGradScatter::fill(a.X, a.ps, s, T, r);
     }
-    __device__ __forceinline__ static void accumulate(const Args&, const double* rec, int pl, double (&acc)[9][3])
+    __device__ __forceinline__ static void accumulate(const Args& a, const double* rec, int pl, double (&acc)[9][3])
     {
-        TGradScatter::accumulate(rec, pl, acc);
-    }
-    __device__ static void flush(const Args& a, long n, const double (&v)[3])
-    {
-        const int id = a.g_idx[n];
-        if (id < 0) return;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) atomicAdd(a.out + 3 * (size_t)id + d, v[d]);
-    }
-};
-
-// a13: b += dt^2 * sum_p [H~_p : grad x_p] grad w   (MpmForceBase.cpp:261-306 with scale = -dt^2)
-struct HessianPolicy {
-    static constexpr int NCH = 3, REC = TGradScatter::REC, GATHER = 1;
-    struct Args {
-        size_t ps;
-        const double *X, *H;
-        double dx, one_over_dx, dt2;
-        const int* g_idx;
-        const double* x; // DOF vector in
-        double* out; // DOF vector out
-    };
-    __device__ static void gather_node(const Args& a, long n, double (&v)[3])
-    {
-        const int id = a.g_idx[n];
-        if (id < 0) return;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) v[d] = a.x[3 * (size_t)id + d];
-    }
-    __device__ static void stage(const Args& a, size_t s, double* r, const double* gtile)
-    {
-        SplineEval sp;
-        sp.eval(a.X, a.ps, s, a.dx, a.one_over_dx, true);
-        double G[9], T[9];
-        gather_gradient(gtile, sp, a.one_over_dx, G);
-#pragma unroll
-        for (int q = 0; q < 9; ++q) T[q] = 0.0;
-#pragma unroll
-        for (int j = 0; j < 9; ++j)
-#pragma unroll
-            for (int i = 0; i <= j; ++i) {
-                const double h = a.H[(size_t)tri(i, j) * a.ps + s];
-                T[i] += h * G[j];
-                if (i != j) T[j] += h * G[i];
-            }
-#pragma unroll
-        for (int q = 0; q < 9; ++q) T[q] *= a.dt2;
-        TGradScatter::fill(sp, a.one_over_dx, T, r);
-    }
-    __device__ __forceinline__ static void accumulate(const Args&, const double* rec, int pl, double (&acc)[9][3])
-    {
-        TGradScatter::accumulate(rec, pl, acc);
+        TGradScatter::accumulate(rec, a.dx, a.one_over_dx, pl, acc);
     }
     __device__ static void flush(const Args& a, long n, const double (&v)[3])
     {
@@ -322,7 +306,8 @@ struct HessianPolicy {
 
 // a18: nodeCNTol_i += w_ip m_p ||dPdF(F = I)||_F   (ImplicitSolver.h:667-696, FBasedMpmForceHelper.h:123-157)
 struct CNTolPolicy {
-    static constexpr int NCH = 1, REC = 10, GATHER = 0;
+    // record: X(3)  m_p ||dPdF(I)||_F
+    static constexpr int NCH = 1, RAW = 4, GATHER = 0;
     struct Args {
         size_t ps;
         const double *X, *M, *mu, *lam;
@@ -334,8 +319,6 @@ struct CNTolPolicy {
     __device__ static void gather_node(const Args&, long, double (&)[3]) {}
     __device__ static void stage(const Args& a, size_t s, double* r, const double*)
     {
-        SplineEval sp;
-        sp.eval(a.X, a.ps, s, a.dx, a.one_over_dx, false);
         // dPdF = Q blockdiag(A, B01, B12, B20) Q^T with Q orthogonal, so ||dPdF||_F^2 = sum of the block norms^2
         const double one[3] = {1.0, 1.0, 1.0};
         HessBlocks hb;
@@ -345,22 +328,19 @@ struct CNTolPolicy {
         for (int q = 0; q < 9; ++q) n2 += hb.A[q] * hb.A[q];
 #pragma unroll
         for (int q = 0; q < 4; ++q) n2 += hb.B01[q] * hb.B01[q] + hb.B12[q] * hb.B12[q] + hb.B20[q] * hb.B20[q];
-        const double val = a.M[s] * sqrt(n2);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            r[j] = sp.w[1][j];
-            r[3 + j] = sp.w[2][j];
-            r[6 + j] = val * sp.w[0][j];
-        }
-        r[9] = 0.0;
+        for (int d = 0; d < 3; ++d) r[d * SC_PAD] = a.X[d * a.ps + s];
+        r[3 * SC_PAD] = a.M[s] * sqrt(n2);
     }
-    __device__ __forceinline__ static void accumulate(const Args&, const double* rec, int pl, double (&acc)[9][1])
+    __device__ __forceinline__ static void accumulate(const Args& a, const double* rec, int pl, double (&acc)[9][1])
     {
-        const double v = rec[6 + pl];
+        SplineEval sp;
+        sp.eval_rec(rec, a.dx, a.one_over_dx, false);
+        const double v = rec[3 * SC_PAD] * (pl == 0 ? sp.w[0][0] : (pl == 1 ? sp.w[0][1] : sp.w[0][2]));
 #pragma unroll
         for (int j = 0; j < 3; ++j)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) acc[j * 3 + k][0] += v * (rec[j] * rec[3 + k]);
+            for (int k = 0; k < 3; ++k) acc[j * 3 + k][0] += v * (sp.w[1][j] * sp.w[2][k]);
     }
     __device__ static void flush(const Args& a, long n, const double (&v)[1])
     {
@@ -634,6 +614,22 @@ int ensure_hessian(Sim* s)
     return 0;
 }
 
+// out += scale * sum_p [H~_p : grad x_p] grad w: per-particle gather kernel, then the force scatter on the 9 doubles it leaves
+// behind (two lean kernels beat one fused gather->scatter CTA: the fused form serialises a 45-load stage in front of the
+// register-heavy accumulate loop and halves the occupancy of both)
+static int hessian_scatter(Sim* s, double scale, const double* x, double* out)
+{
+    const size_t ps = s->P.stride;
+    HOT_CUDA(s->f_T.reserve(9 * ps));
+    if (s->g1 > s->g0) {
+        k_hessian_gather<<<(unsigned)(s->g1 - s->g0), US_THREADS, 0, s->stream>>>(s->group_first.p + s->g0, s->group_slot.p + s->g0, s->nbr8.p, ps,
+            s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, scale, s->g_idx.p, x, s->f_T.p);
+        HOT_LAUNCHED(s);
+    }
+    ForcePolicy::Args a{ps, s->P.X.p, s->f_T.p, s->dx, 1.0 / s->dx, -1.0, s->g_idx.p, out};
+    return scatter_to_dofs<ForcePolicy>(s, a, &ForcePolicy::Args::out, out, 3);
+}
+
 // ImplicitSolverObjective::multiply with matrix_free, ImplicitSolver.h:741-763
 int hessian_apply_mf(Sim* s, const double* x, double* b)
 {
@@ -644,8 +640,7 @@ int hessian_apply_mf(Sim* s, const double* x, double* b)
     KTime t(s, KC_HESSIAN);
     k_mass_mul<<<nblk(3 * (long)nn), TPB, 0, st>>>(nn, s->mass_matrix.p, x, b);
     HOT_LAUNCHED(s);
-    HessianPolicy::Args a{s->P.stride, s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, s->dt * s->dt, s->g_idx.p, x, b};
-    return scatter_to_dofs<HessianPolicy>(s, a, &HessianPolicy::Args::out, b, 3);
+    return hessian_scatter(s, s->dt * s->dt, x, b);
 }
 
 // MpmSimulationBase::addScaledForceDifferentials (-> MpmForceBase::addScaledForceDifferential, MpmForceBase.cpp:261-306):
@@ -655,8 +650,7 @@ int add_scaled_force_differentials(Sim* s, double scale, const double* x, double
     int rc = ensure_hessian(s);
     if (rc) return rc;
     KTime t(s, KC_HESSIAN);
-    HessianPolicy::Args a{s->P.stride, s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, -scale, s->g_idx.p, x, f};
-    return scatter_to_dofs<HessianPolicy>(s, a, &HessianPolicy::Args::out, f, 3);
+    return hessian_scatter(s, -scale, x, f);
 }
 
 // ImplicitSolverObjective::evaluatePerNodeCNTolerance, ImplicitSolver.h:667-696

@@ -16,8 +16,11 @@
 #include "sim.h"
 #include "reduce.cuh"
 #include <cub/cub.cuh>
+#include <cooperative_groups.h>
+#include <algorithm>
 
 namespace hot {
+namespace cg = cooperative_groups;
 namespace {
 
 constexpr int TPB = 256;
@@ -397,23 +400,29 @@ constexpr int GS_HALF = 32;
 constexpr int GS_PAIRS = GS_HALF * (GS_HALF - 1) / 2; // 496
 __device__ __forceinline__ int gs_pair(int il, int kl) { return kl * (GS_HALF - 1) - kl * (kl - 1) / 2 + (il - kl - 1); } // il > kl
 
-template <bool FWD>
-__global__ void __launch_bounds__(GS_THREADS, 3) k_gs_block(int b0, const int* __restrict__ block_start, const int* __restrict__ seq,
+struct GSShared {
+    double Lt[9][GS_PAIRS]; // entry q of the coupling (il, kl) at Lt[q][gs_pair(il, kl)]
+    double s_rhs[GS_HALF][3];
+    double s_x[2 * GS_HALF][3];
+};
+
+template <bool FWD, int THREADS>
+__device__ __forceinline__ void gs_block_body(GSShared& sh, int b, const int* __restrict__ block_start, const int* __restrict__ seq,
     const int* __restrict__ colrank, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ dinv,
-    const double* __restrict__ diag, const double* __restrict__ rhs, double* out, double* __restrict__ out_scaled)
+    const double* __restrict__ diag, const double* rhs, double* out, double* out_scaled)
 {
-    __shared__ double Lt[9][GS_PAIRS]; // entry q of the coupling (il, kl) at Lt[q][gs_pair(il, kl)]
-    __shared__ double s_rhs[GS_HALF][3];
-    __shared__ double s_x[2 * GS_HALF][3];
-    const int b = b0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double (&Lt)[9][GS_PAIRS] = sh.Lt;
+    double (&s_rhs)[GS_HALF][3] = sh.s_rhs;
+    double (&s_x)[2 * GS_HALF][3] = sh.s_x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ps = block_start[b], pe = block_start[b + 1], nb = pe - ps;
     for (int h0 = 0; h0 < nb; h0 += GS_HALF) {
         const int hn = min(GS_HALF, nb - h0);
         __syncthreads(); // previous half fully consumed (Lt, s_rhs) and its s_x visible
-        for (int e = tid; e < 9 * GS_PAIRS; e += GS_THREADS) (&Lt[0][0])[e] = 0.0;
+        for (int e = tid; e < 9 * GS_PAIRS; e += THREADS) (&Lt[0][0])[e] = 0.0;
         __syncthreads();
         // sweep-local index of a node: FWD rank - ps, BWD pe - 1 - rank
-        for (int il = warp; il < hn; il += GS_THREADS / 32) {
+        for (int il = warp; il < hn; il += THREADS / 32) {
             const int gl = h0 + il; // index in the block
             const int p = FWD ? ps + gl : pe - 1 - gl;
             const int i = seq[p];
@@ -507,6 +516,73 @@ __global__ void __launch_bounds__(GS_THREADS, 3) k_gs_block(int b0, const int* _
                     out_scaled[3 * (size_t)node + 2] = d[2] * mx0 + d[5] * mx1 + d[8] * mx2;
                 }
             }
+        }
+    }
+}
+
+
+struct GSArgs {
+    int n;
+    int cfb[9];
+    const int *block_start, *seq, *colrank, *col;
+    const double *val, *dinv, *diag;
+    double *r, *hdu, *dhdu, *du, *u;
+    int fuse_update; // u += du, r -= A du in the same launch (no BC projection needed on this level)
+};
+
+// One colour phase as its own launch (fallback when a cooperative launch is not possible)
+template <bool FWD>
+__global__ void __launch_bounds__(GS_THREADS, 3) k_gs_block(int b0, GSArgs a)
+{
+    __shared__ GSShared sh;
+    if (FWD) gs_block_body<true, GS_THREADS>(sh, b0 + blockIdx.x, a.block_start, a.seq, a.colrank, a.col, a.val, a.dinv, a.diag, a.r, a.hdu, a.dhdu);
+    else gs_block_body<false, GS_THREADS>(sh, b0 + blockIdx.x, a.block_start, a.seq, a.colrank, a.col, a.val, a.dinv, a.diag, a.dhdu, a.du, nullptr);
+}
+
+// The whole symmetric sweep of gs_smooth in ONE cooperative launch: 8 forward colour phases, 8 backward ones, then
+// u += du, r -= A du, separated by grid barriers instead of 17 dependent launches (on the coarse levels a phase is a
+// handful of blocks, so launch gaps and ramp-up dominated the smoother).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_gs_sweep(GSArgs a)
+{
+    __shared__ GSShared sh;
+    cg::grid_group grid = cg::this_grid();
+    for (int c = 0; c < 8; ++c) {
+        for (int b = a.cfb[c] + blockIdx.x; b < a.cfb[c + 1]; b += gridDim.x)
+            gs_block_body<true, THREADS>(sh, b, a.block_start, a.seq, a.colrank, a.col, a.val, a.dinv, a.diag, a.r, a.hdu, a.dhdu);
+        grid.sync();
+    }
+    for (int c = 7; c >= 0; --c) {
+        for (int b = a.cfb[c] + blockIdx.x; b < a.cfb[c + 1]; b += gridDim.x)
+            gs_block_body<false, THREADS>(sh, b, a.block_start, a.seq, a.colrank, a.col, a.val, a.dinv, a.diag, a.dhdu, a.du, nullptr);
+        grid.sync();
+    }
+    if (!a.fuse_update) return;
+    const int lane = threadIdx.x & 31;
+    const long nwarps = (long)gridDim.x * (THREADS / 32);
+    for (long row = (long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); row < a.n; row += nwarps) {
+        const int* c = a.col + (size_t)row * W;
+        const double* v = a.val + (size_t)row * 9 * W;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int t = 0; t < W / 32; ++t) {
+            const int s = lane + 32 * t;
+            const int j = c[s];
+            const double x0 = a.du[3 * (size_t)j], x1 = a.du[3 * (size_t)j + 1], x2 = a.du[3 * (size_t)j + 2];
+            a0 += v[s] * x0 + v[3 * W + s] * x1 + v[6 * W + s] * x2;
+            a1 += v[W + s] * x0 + v[4 * W + s] * x1 + v[7 * W + s] * x2;
+            a2 += v[2 * W + s] * x0 + v[5 * W + s] * x1 + v[8 * W + s] * x2;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_down_sync(0xffffffffu, a0, o);
+            a1 += __shfl_down_sync(0xffffffffu, a1, o);
+            a2 += __shfl_down_sync(0xffffffffu, a2, o);
+        }
+        if (lane == 0) {
+            const size_t o = 3 * (size_t)row;
+            a.r[o] -= a0; a.r[o + 1] -= a1; a.r[o + 2] -= a2;
+            a.u[o] += a.du[o]; a.u[o + 1] += a.du[o + 1]; a.u[o + 2] += a.du[o + 2];
         }
     }
 }
@@ -835,36 +911,75 @@ int smooth_cg(Sim* s, int level, double* u, double* r, int iterations)
     s->last_cg_iters = cnt;
     return 0;
 }
+template <int THREADS>
+int launch_gs_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
+{
+    static int per_sm = -1, n_sm = 0;
+    if (per_sm < 0) {
+        int dev = 0, coop = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gs_sweep<THREADS>, THREADS, 0) != cudaSuccess || !coop) per_sm = 0;
+    }
+    *launched = false;
+    if (per_sm <= 0) return 0;
+    int grid = std::min(max_blocks_per_color, per_sm * n_sm);
+    if (a.fuse_update) grid = std::max(grid, std::min(per_sm * n_sm, (a.n + THREADS / 32 - 1) / (THREADS / 32)));
+    if (grid < 1) grid = 1;
+    void* params[] = {&a};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_gs_sweep<THREADS>, dim3(grid), dim3(THREADS), params, 0, s->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError(); // clear; fall back to per-phase launches
+        per_sm = 0;
+        return 0;
+    }
+    s->launches++;
+    *launched = true;
+    return 0;
+}
+
 // gs_smooth, MultigridPreconditioner.h:266-318
 int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
 {
     MGLevel& L = *s->levels[level];
     if (L.n_blocks <= 0) return fail(s, "gs_smooth: the hierarchy was built without the colour schedule (smoother / coarseSolver 5)");
     cudaStream_t st = s->stream;
-    double* hdu = L.tmp.p;   // unscaled forward solution (what the forward sweep itself reads)
-    double* dhdu = L.dAu.p;  // D hdu, the right-hand side of the backward sweep
     const bool project = level == 0 && !s->matrix_bcproject;
+    GSArgs a;
+    a.n = L.n;
+    int max_blocks = 0;
+    for (int c = 0; c < 9; ++c) a.cfb[c] = L.color_first_block[c];
+    for (int c = 0; c < 8; ++c) max_blocks = std::max(max_blocks, a.cfb[c + 1] - a.cfb[c]);
+    a.block_start = L.gs_block_start.p; a.seq = L.gs_seq.p; a.colrank = L.gs_colrank.p; a.col = L.col.p;
+    a.val = L.val.p; a.dinv = L.dinv.p; a.diag = L.diag.p;
+    a.r = r; a.hdu = L.tmp.p; a.dhdu = L.dAu.p; a.du = L.du.p; a.u = u; // hdu: unscaled forward solution; dhdu = D hdu
+    a.fuse_update = project ? 0 : 1;
     iterations = (iterations + 1) >> 1;
     for (; iterations--;) {
-        for (int c = 0; c < 8; ++c) {
-            const int b0 = L.color_first_block[c], b1 = L.color_first_block[c + 1];
-            if (b1 == b0) continue;
-            k_gs_block<true><<<b1 - b0, GS_THREADS, 0, st>>>(b0, L.gs_block_start.p, L.gs_seq.p, L.gs_colrank.p, L.col.p, L.val.p, L.dinv.p,
-                L.diag.p, r, hdu, dhdu);
-            HOT_LAUNCHED(s);
+        bool launched = false;
+        // few blocks per colour: a big CTA per block (16 warps stream the rows) on one SM each; many: 3 CTAs of 8 warps per SM
+        if (max_blocks <= 2 * 148) RC(launch_gs_sweep<512>(s, a, max_blocks, &launched));
+        else RC(launch_gs_sweep<GS_THREADS>(s, a, max_blocks, &launched));
+        if (!launched) {
+            for (int c = 0; c < 8; ++c) {
+                const int b0 = a.cfb[c], b1 = a.cfb[c + 1];
+                if (b1 == b0) continue;
+                k_gs_block<true><<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
+                HOT_LAUNCHED(s);
+            }
+            for (int c = 7; c >= 0; --c) {
+                const int b0 = a.cfb[c], b1 = a.cfb[c + 1];
+                if (b1 == b0) continue;
+                k_gs_block<false><<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
+                HOT_LAUNCHED(s);
+            }
+            if (!project) {
+                k_spmv_update<<<nblk(32L * L.n), TPB, 0, st>>>(L.n, L.col.p, L.val.p, L.du.p, u, r);
+                HOT_LAUNCHED(s);
+            }
         }
-        for (int c = 7; c >= 0; --c) {
-            const int b0 = L.color_first_block[c], b1 = L.color_first_block[c + 1];
-            if (b1 == b0) continue;
-            k_gs_block<false><<<b1 - b0, GS_THREADS, 0, st>>>(b0, L.gs_block_start.p, L.gs_seq.p, L.gs_colrank.p, L.col.p, L.val.p, L.dinv.p,
-                L.diag.p, dhdu, L.du.p, nullptr);
-            HOT_LAUNCHED(s);
-        }
-        if (!project) {
-            k_spmv_update<<<nblk(32L * L.n), TPB, 0, st>>>(L.n, L.col.p, L.val.p, L.du.p, u, r);
-            HOT_LAUNCHED(s);
-        }
-        else {
+        if (project) {
             RC(vec_axpy(s, 3L * L.n, 1.0, L.du.p, u));
             RC(level_spmv(s, level, L.du.p, L.dAu.p));
             RC(level_project(s, level, L.dAu.p));

@@ -1,16 +1,20 @@
-// Shared skeleton of the three particle->grid scatters of the hot path (a6 P2G, a12 force rasterisation,
-// a13 matrix-free Hessian apply): one CTA per page group, thread = (cell of the page, x-plane of the 3x3x3 stencil).
+// Shared skeleton of the particle->grid scatters of the hot path (a6 P2G, a12 force rasterisation, a13 matrix-free
+// Hessian apply, a18 CN tolerance): one CTA per page group, thread = (cell of the page, x-plane of the 3x3x3 stencil).
 //
 // The reference serialises these scatters into 8 colour passes (MpmSimulationBase.h:251-264) and does a
 // read-modify-write of a 128-byte GridState per (particle, node).  Here (see transfer.cu for the roofline argument):
-//   stage      one thread per particle turns the particle's SoA attributes (coalesced loads of one contiguous run)
-//              into a shared-memory record holding everything that does not depend on the stencil node;
-//   accumulate thread (c, pl) walks the particles of cell c (adjacent thanks to the sort key) and keeps the
-//              9 nodes x NCH channels of x-plane pl in registers - no atomics, no shared-memory traffic but the
-//              record reads;
-//   combine    per-warp (B+2)^3 tiles in shared memory, 9 (j,k) steps; inside a step the lanes of a warp hit
-//              distinct nodes (a warp holds < 16 consecutive cells => distinct (cy,cz); the 3 planes of a cell are
-//              distinct x), so plain RMW + __syncwarp is race free;
+//   stage      the particle's SoA attributes (coalesced loads of one contiguous run) are reduced to a small RAW record
+//              (position + the policy's per-particle payload, e.g. m, m v, m C for P2G or the 3x3 matrix T for the vector
+//              scatters) in shared memory, field-major and index-swizzled so that the strided reads below are conflict-free;
+//              up to SC_CHUNK = 3 x CTA-size particles per pass, so a typical page group (~8-12 particles per cell) is ONE
+//              pass and every (cell, plane) thread has work;
+//   accumulate thread (c, pl) walks the particles of cell c (adjacent thanks to the sort key), re-derives the B-spline
+//              weights from the position (cheaper than staging them: 12 extra doubles per particle would halve the chunk)
+//              and keeps the 9 nodes x NCH channels of x-plane pl in registers - no atomics, no shared-memory traffic but
+//              the record reads;
+//   combine    per-warp (B+2)^3 tiles in shared memory, 9 (j,k) steps; inside a step the lanes of a warp hit distinct nodes
+//              (a warp holds < 16 consecutive cells => distinct (cy,cz); the 3 planes of a cell are distinct x), so plain
+//              RMW + __syncwarp is race free;
 //   flush      warp tiles are summed and written with one fp64 RED per touched node and channel.
 #pragma once
 #include "sim.h"
@@ -19,8 +23,11 @@ namespace hot {
 
 constexpr int SC_THREADS = 3 * Geo::E; // 96 for the 2x4x4 fp64 page
 constexpr int SC_WARPS = SC_THREADS / 32;
-constexpr int SC_CHUNK = SC_THREADS; // particles staged per pass: one per thread
+constexpr int SC_CHUNK = 3 * SC_THREADS; // particles staged per pass
+constexpr int SC_PAD = SC_CHUNK + SC_CHUNK / 8 + 2; // swizzled row length
 static_assert(SC_THREADS % 32 == 0, "whole warps");
+// neighbouring cells read records ~ppc apart: p + p/8 spreads them over the banks for the usual 4..16 particles per cell
+__device__ __forceinline__ int sc_swz(int p) { return p + (p >> 3); }
 
 // quadratic B-spline weights of one axis in the reference's operation order (BSplines.h:55-81)
 __device__ __forceinline__ void bspline_axis(double d0, double* w, double* dw)
@@ -56,9 +63,10 @@ __device__ __forceinline__ int tile_base(int bx, int by, int bz)
 }
 
 // Policy interface:
-//   static constexpr int NCH, REC (doubles per record, even), GATHER (0/1: stage needs a gathered DOF field tile)
+//   static constexpr int NCH, RAW (doubles per staged particle; fields 0..2 are the position), GATHER (0/1: stage needs a
+//                                  gathered DOF field tile)
 //   struct Args { ... }                              kernel arguments (trivially copyable)
-//   __device__ static void stage(const Args&, size_t s, double* rec, const double* gtile)
+//   __device__ static void stage(const Args&, size_t s, double* rec /* field f at rec[f * SC_PAD] */, const double* gtile)
 //   __device__ static void accumulate(const Args&, const double* rec, int pl, double (&acc)[9][NCH])
 //   __device__ static void flush(const Args&, long a, const double (&v)[NCH])     a = grid array index
 //   __device__ static void gather_node(const Args&, long a, double (&v)[3])       (GATHER only)
@@ -66,8 +74,8 @@ template <class Policy>
 __global__ void __launch_bounds__(SC_THREADS, 5) k_plane_scatter(typename Policy::Args args, const int* __restrict__ cell_start,
     const int* __restrict__ group_slot, const int* __restrict__ nbr8)
 {
-    constexpr int NCH = Policy::NCH, REC = Policy::REC, TILE = Geo::TILE, E = Geo::E;
-    constexpr int REC_DOUBLES = SC_CHUNK * REC, TILE_DOUBLES = SC_WARPS * NCH * TILE;
+    constexpr int NCH = Policy::NCH, RAW = Policy::RAW, TILE = Geo::TILE, E = Geo::E;
+    constexpr int REC_DOUBLES = RAW * SC_PAD, TILE_DOUBLES = SC_WARPS * NCH * TILE;
     // the warp tiles alias the record buffer: records are dead once the last chunk has been accumulated
     __shared__ __align__(16) double smem[REC_DOUBLES > TILE_DOUBLES ? REC_DOUBLES : TILE_DOUBLES];
     __shared__ double gtile[Policy::GATHER ? 3 * TILE : 1];
@@ -98,10 +106,10 @@ __global__ void __launch_bounds__(SC_THREADS, 5) k_plane_scatter(typename Policy
     for (int cb = first; cb < end; cb += SC_CHUNK) {
         const int cn = min(SC_CHUNK, end - cb);
         __syncthreads(); // previous chunk consumed (and gtile ready on the first pass)
-        if (tid < cn) Policy::stage(args, (size_t)cb + tid, smem + (size_t)tid * REC, gtile);
+        for (int k = tid; k < cn; k += SC_THREADS) Policy::stage(args, (size_t)cb + k, smem + sc_swz(k), gtile);
         __syncthreads();
         const int pb = max(my_b, cb) - cb, pe = min(my_e, cb + cn) - cb;
-        for (int p = pb; p < pe; ++p) Policy::accumulate(args, smem + (size_t)p * REC, pl, acc);
+        for (int p = pb; p < pe; ++p) Policy::accumulate(args, smem + sc_swz(p), pl, acc);
     }
     __syncthreads(); // records dead -> reuse as warp tiles
     for (int a = tid; a < TILE_DOUBLES; a += SC_THREADS) smem[a] = 0.0;
@@ -140,11 +148,21 @@ __global__ void __launch_bounds__(SC_THREADS, 5) k_plane_scatter(typename Policy
     }
 }
 
-// fills the weight part shared by all policies: record layout
-//   [0..2] wy  [3..5] wz  [6..8] dwy/dx  [9..11] dwz/dx  then policy data; returns the in-page cell via base
+// B-spline evaluation of one particle
 struct SplineEval {
     double w[3][3], dw[3][3], d0n[3]; // weights, weight derivatives (not yet / dx), x_node(base) - x_p
     int base[3];
+    // from a staged record (fields 0..2 = position)
+    __device__ __forceinline__ void eval_rec(const double* __restrict__ rec, double dx, double one_over_dx, bool want_dw)
+    {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double Xd = rec[d * SC_PAD], xi;
+            base[d] = base_node_of(Xd, one_over_dx, &xi);
+            bspline_axis(xi - (double)base[d], w[d], want_dw ? dw[d] : nullptr);
+            d0n[d] = (double)base[d] * dx - Xd;
+        }
+    }
     __device__ __forceinline__ void eval(const double* __restrict__ X, size_t ps, size_t s, double dx, double one_over_dx, bool want_dw)
     {
 #pragma unroll

@@ -187,6 +187,7 @@ struct Sim {
     bool strain_backed_up = false, state_valid = false, hessian_valid = false;
     DevBuf<double> f_stress; // vol P Fn^T, 9 rows
     DevBuf<double> f_U, f_V, f_sig; // SVD of the trial F
+    DevBuf<double> f_T; // 9 rows: per-particle result of the Hessian gather (a13)
     DevBuf<double> f_H; // 45 rows: packed upper triangle of the contracted particle Hessian (see force.cu)
     DevBuf<double> group_psi; // per-group sum of vol*psi
     DevBuf<double> red_partial, red_out; // deterministic two-stage reductions
@@ -218,6 +219,7 @@ struct Sim {
     long g0 = 0, g1 = 0, p0 = 0, p1 = 0; // own page groups [g0, g1) and sorted particles [p0, p1)
     int dof0 = 0, dof1 = 0; // own DOF ids
     int n_iface = 0;
+    bool iface_valid = false; // interface list built for the current sort
     DevBuf<int> iface_dof, group_rank;
     DevBuf<unsigned> page_mask;
     DevBuf<double> scat_tmp;

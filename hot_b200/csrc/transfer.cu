@@ -29,7 +29,8 @@ constexpr int TILE = Geo::TILE;
 
 // a6: g.m += w m_p ; g.v += w (m_p C_p (x_i - x_p) + m_p v_p)   (MpmSimulationBase.cpp:636-652)
 struct P2GPolicy {
-    static constexpr int NCH = 4, REC = 28, GATHER = 0;
+    // record: X(3) m  m*v(3)  m*C(9, column-major)
+    static constexpr int NCH = 4, RAW = 16, GATHER = 0;
     struct Args {
         size_t ps;
         const double *X, *V, *M, *C;
@@ -40,47 +41,39 @@ struct P2GPolicy {
     __device__ static void gather_node(const Args&, long, double (&)[3]) {}
     __device__ static void stage(const Args& a, size_t s, double* r, const double*)
     {
-        SplineEval sp;
-        sp.eval(a.X, a.ps, s, a.dx, a.one_over_dx, false);
         const double m = a.M[s];
-        double mv[3], Cm[9];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) mv[d] = m * a.V[d * a.ps + s];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) Cm[q] = m * a.C[q * a.ps + s];
-        r[0] = sp.w[1][0]; r[1] = sp.w[1][1]; r[2] = sp.w[1][2];
-        r[3] = sp.w[2][0]; r[4] = sp.w[2][1]; r[5] = sp.w[2][2];
-        r[6] = Cm[3]; r[7] = Cm[4]; r[8] = Cm[5]; // column 1 of m*C
-        r[9] = Cm[6]; r[10] = Cm[7]; r[11] = Cm[8]; // column 2
-        r[12] = sp.d0n[1]; r[13] = sp.d0n[2];
-        r[14] = m; r[15] = 0.0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            double dxi = (double)i * a.dx + sp.d0n[0];
-            r[16 + 4 * i] = sp.w[0][i];
-            r[17 + 4 * i] = mv[0] + Cm[0] * dxi;
-            r[18 + 4 * i] = mv[1] + Cm[1] * dxi;
-            r[19 + 4 * i] = mv[2] + Cm[2] * dxi;
+        for (int d = 0; d < 3; ++d) {
+            r[d * SC_PAD] = a.X[d * a.ps + s];
+            r[(4 + d) * SC_PAD] = m * a.V[d * a.ps + s];
         }
+        r[3 * SC_PAD] = m;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) r[(7 + q) * SC_PAD] = m * a.C[q * a.ps + s];
     }
     __device__ __forceinline__ static void accumulate(const Args& a, const double* rec, int pl, double (&acc)[9][4])
     {
-        const double2* r2 = reinterpret_cast<const double2*>(rec);
-        double2 a0 = r2[0], a1 = r2[1], a2 = r2[2], a3 = r2[3], a4 = r2[4], a5 = r2[5], a6 = r2[6], a7 = r2[7];
-        double2 b0 = r2[8 + 2 * pl], b1 = r2[9 + 2 * pl];
-        const double wy[3] = {a0.x, a0.y, a1.x}, wz[3] = {a1.y, a2.x, a2.y};
-        const double c1[3] = {a3.x, a3.y, a4.x}, c2[3] = {a4.y, a5.x, a5.y};
-        const double dy0 = a6.x, dz0 = a6.y, m = a7.x;
-        const double wi = b0.x, ai[3] = {b0.y, b1.x, b1.y};
+        SplineEval sp;
+        sp.eval_rec(rec, a.dx, a.one_over_dx, false);
+        const double m = rec[3 * SC_PAD];
+        const double wi = pl == 0 ? sp.w[0][0] : (pl == 1 ? sp.w[0][1] : sp.w[0][2]);
+        const double dxi = (double)pl * a.dx + sp.d0n[0];
+        double ai[3], c1[3], c2[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            ai[r] = rec[(4 + r) * SC_PAD] + rec[(7 + r) * SC_PAD] * dxi; // m v + m C(:,0) (x_i - x_p)_x
+            c1[r] = rec[(10 + r) * SC_PAD];
+            c2[r] = rec[(13 + r) * SC_PAD];
+        }
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            const double dyj = (double)j * a.dx + dy0;
-            const double wij = wi * wy[j];
+            const double dyj = (double)j * a.dx + sp.d0n[1];
+            const double wij = wi * sp.w[1][j];
             const double bj[3] = {ai[0] + c1[0] * dyj, ai[1] + c1[1] * dyj, ai[2] + c1[2] * dyj};
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const double dzk = (double)k * a.dx + dz0;
-                const double w = wij * wz[k];
+                const double dzk = (double)k * a.dx + sp.d0n[2];
+                const double w = wij * sp.w[2][k];
                 acc[j * 3 + k][0] += w * m;
                 acc[j * 3 + k][1] += w * (bj[0] + c2[0] * dzk);
                 acc[j * 3 + k][2] += w * (bj[1] + c2[1] * dzk);
@@ -100,7 +93,7 @@ struct P2GPolicy {
 
 constexpr int G2P_THREADS = 128;
 
-__global__ void __launch_bounds__(G2P_THREADS) k_g2p(const int* __restrict__ group_first, const int* __restrict__ group_slot,
+__global__ void __launch_bounds__(G2P_THREADS, 4) k_g2p(const int* __restrict__ group_first, const int* __restrict__ group_slot,
     const int* __restrict__ nbr8, size_t ps, double* __restrict__ X, double* __restrict__ V, double* __restrict__ C,
     double* __restrict__ F, double* __restrict__ gradV, double dx, double one_over_dx, double dt, double apic_rpic_ratio, double cfl,
     size_t gs, const double* __restrict__ g_v, const int* __restrict__ g_idx, const double* __restrict__ dv, int* __restrict__ flags)
@@ -128,45 +121,58 @@ __global__ void __launch_bounds__(G2P_THREADS) k_g2p(const int* __restrict__ gro
     const double ca = (apic_rpic_ratio + 1.0) * 0.5, cb = (apic_rpic_ratio - 1.0) * 0.5;
     int fast = 0, half_fast = 0;
     for (int s = first + tid; s < end; s += G2P_THREADS) {
-        double Xp[3], w[3][3], dw[3][3], d0n[3];
+        double Xp[3], w[3][3], gw[3][3], xm[3][3]; // weights, weight derivatives / dx, x_node - x_p per axis and stencil index
         int tb[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             Xp[d] = X[d * ps + s];
-            double xi;
+            double xi, dw[3];
             int b = base_node_of(Xp[d], one_over_dx, &xi);
-            bspline_axis(xi - (double)b, w[d], dw[d]);
-            d0n[d] = (double)b * dx - Xp[d];
+            bspline_axis(xi - (double)b, w[d], dw);
+            const double d0n = (double)b * dx - Xp[d];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                gw[d][i] = one_over_dx * dw[i];
+                xm[d][i] = (double)i * dx + d0n;
+            }
             int bits = d == 0 ? Geo::xb : (d == 1 ? Geo::yb : Geo::zb);
             tb[d] = b & ((1 << bits) - 1);
         }
+        // The 27-node sums  v_p = sum w v,  B = sum w v (x_i - x_p)^T,  grad v = sum v grad w^T  (MpmSimulationBase.cpp:942-1006)
+        // are evaluated as a tensor-product contraction z -> y -> x: 441 FMA instead of 27 x 32 (fp64 issue is the bound of this
+        // kernel), same terms in a different association.
         double vp[3] = {0, 0, 0}, B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const double wz0 = w[2][0] * xm[2][0], wz1 = w[2][1] * xm[2][1], wz2 = w[2][2] * xm[2][2];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const double wi = w[0][i], dwidxi = one_over_dx * dw[0][i], xi0 = (double)i * dx + d0n[0];
+            double Av[3] = {0, 0, 0}, Agy[3] = {0, 0, 0}, Agz[3] = {0, 0, 0}, Aby[3] = {0, 0, 0}, Abz[3] = {0, 0, 0};
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                const double wij = wi * w[1][j], dwijdxi = dwidxi * w[1][j], dwijdxj = wi * one_over_dx * dw[1][j];
-                const double xj1 = (double)j * dx + d0n[1];
+                const int n0 = ((tb[0] + i) * Geo::TY + (tb[1] + j)) * Geo::TZ + tb[2];
+                const double wj = w[1][j], gj = gw[1][j], wyj = wj * xm[1][j];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int n = ((tb[0] + i) * Geo::TY + (tb[1] + j)) * Geo::TZ + (tb[2] + k);
-                    const double wk = w[2][k];
-                    const double wijk = wij * wk;
-                    const double gw[3] = {dwijdxi * wk, dwijdxj * wk, wij * one_over_dx * dw[2][k]};
-                    const double xm[3] = {xi0, xj1, (double)k * dx + d0n[2]};
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        const double nv = tile[r][n];
-                        const double wv = wijk * nv;
-                        vp[r] += wv;
-#pragma unroll
-                        for (int cc = 0; cc < 3; ++cc) {
-                            B[r + 3 * cc] += wv * xm[cc];
-                            G[r + 3 * cc] += nv * gw[cc];
-                        }
-                    }
+                for (int r = 0; r < 3; ++r) {
+                    const double v0 = tile[r][n0], v1 = tile[r][n0 + 1], v2 = tile[r][n0 + 2];
+                    const double a = w[2][0] * v0 + w[2][1] * v1 + w[2][2] * v2;                       // sum_k w_k v
+                    const double g = gw[2][0] * v0 + gw[2][1] * v1 + gw[2][2] * v2;                    // sum_k dw_k/dx v
+                    const double c = wz0 * v0 + wz1 * v1 + wz2 * v2;                                   // sum_k w_k z_k v
+                    Av[r] += wj * a;
+                    Agy[r] += gj * a;
+                    Agz[r] += wj * g;
+                    Aby[r] += wyj * a;
+                    Abz[r] += wj * c;
                 }
+            }
+            const double wi = w[0][i], gi = gw[0][i], wxi = wi * xm[0][i];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                vp[r] += wi * Av[r];
+                G[r] += gi * Av[r];
+                G[r + 3] += wi * Agy[r];
+                G[r + 6] += wi * Agz[r];
+                B[r] += wxi * Av[r];
+                B[r + 3] += wi * Aby[r];
+                B[r + 6] += wi * Abz[r];
             }
         }
         double inc = 0;
