@@ -18,6 +18,7 @@
 #include <cub/cub.cuh>
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <cstdlib>
 
 namespace hot {
 namespace cg = cooperative_groups;
@@ -400,6 +401,12 @@ constexpr int GS_HALF = 32;
 constexpr int GS_PAIRS = GS_HALF * (GS_HALF - 1) / 2; // 496
 __device__ __forceinline__ int gs_pair(int il, int kl) { return kl * (GS_HALF - 1) - kl * (kl - 1) / 2 + (il - kl - 1); } // il > kl
 
+__device__ long long* g_gs_dbg = nullptr; // debug: clock64 stamps of one block (HOT_GS_DEBUG)
+#define GS_STAMP(k)                                                                  \
+    do {                                                                             \
+        if (g_gs_dbg && b == g_gs_dbg[31] && threadIdx.x == 0) g_gs_dbg[k] = clock64(); \
+    } while (0)
+
 struct GSShared {
     double Lt[9][GS_PAIRS]; // entry q of the coupling (il, kl) at Lt[q][gs_pair(il, kl)]
     double s_rhs[GS_HALF][3];
@@ -416,96 +423,121 @@ __device__ __forceinline__ void gs_block_body(GSShared& sh, int b, const int* __
     double (&s_x)[2 * GS_HALF][3] = sh.s_x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ps = block_start[b], pe = block_start[b + 1], nb = pe - ps;
+    GS_STAMP(0);
     for (int h0 = 0; h0 < nb; h0 += GS_HALF) {
         const int hn = min(GS_HALF, nb - h0);
         __syncthreads(); // previous half fully consumed (Lt, s_rhs) and its s_x visible
+        GS_STAMP(h0 ? 5 : 1);
         for (int e = tid; e < 9 * GS_PAIRS; e += THREADS) (&Lt[0][0])[e] = 0.0;
         __syncthreads();
-        // sweep-local index of a node: FWD rank - ps, BWD pe - 1 - rank
-        for (int il = warp; il < hn; il += THREADS / 32) {
-            const int gl = h0 + il; // index in the block
-            const int p = FWD ? ps + gl : pe - 1 - gl;
-            const int i = seq[p];
-            const int* c = col + (size_t)i * W;
-            const int* cr = colrank + (size_t)i * W;
-            const double* v = val + (size_t)i * 9 * W;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-            int jj[W / 32], rr[W / 32];
+        GS_STAMP(h0 ? 6 : 2);
+        // sweep-local index of a node: FWD rank - ps, BWD pe - 1 - rank.
+        // Rows are taken two at a time per warp so that the index loads of both rows, then the value loads of both rows, are
+        // in flight together (fp64 dependent-issue latency on this part is ~45 cycles and a cold row costs two DRAM round
+        // trips: memory-level parallelism per warp is what bounds this phase on the coarse levels).
+        constexpr int NW = THREADS / 32;
+        for (int il0 = warp; il0 < hn; il0 += 2 * NW) {
+            int il_[2], i_[2], gl_[2], jj[2][W / 32], rr[2][W / 32];
+            bool on[2];
 #pragma unroll
-            for (int t = 0; t < W / 32; ++t) {
-                jj[t] = c[lane + 32 * t];
-                rr[t] = cr[lane + 32 * t];
+            for (int u = 0; u < 2; ++u) {
+                il_[u] = il0 + u * NW;
+                on[u] = il_[u] < hn;
+                gl_[u] = h0 + il_[u];
+                const int p = FWD ? ps + gl_[u] : pe - 1 - gl_[u];
+                i_[u] = on[u] ? seq[p] : 0;
             }
 #pragma unroll
-            for (int t = 0; t < W / 32; ++t) {
-                const int sl = lane + 32 * t;
-                const int j = jj[t];
-                const int kl = FWD ? rr[t] - ps : pe - 1 - rr[t]; // < 0: final before this block; [0, gl): earlier in this block
-                if (kl < gl) {
-                    const double v0 = v[sl], v1 = v[W + sl], v2 = v[2 * W + sl], v3 = v[3 * W + sl], v4 = v[4 * W + sl], v5 = v[5 * W + sl],
-                                 v6 = v[6 * W + sl], v7 = v[7 * W + sl], v8 = v[8 * W + sl];
-                    if (kl < h0) {
-                        double x0, x1, x2;
-                        if (kl < 0) {
-                            x0 = out[3 * (size_t)j]; x1 = out[3 * (size_t)j + 1]; x2 = out[3 * (size_t)j + 2];
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int t = 0; t < W / 32; ++t) {
+                    jj[u][t] = on[u] ? col[(size_t)i_[u] * W + lane + 32 * t] : 0;
+                    rr[u][t] = on[u] ? colrank[(size_t)i_[u] * W + lane + 32 * t] : 0;
+                }
+            double Dm[2][9];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int q = 0; q < 9; ++q) Dm[u][q] = on[u] ? dinv[9 * (size_t)i_[u] + q] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!on[u]) continue; // warp-uniform
+                const int il = il_[u], gl = gl_[u], i = i_[u];
+                const double* v = val + (size_t)i * 9 * W;
+                double acc[W / 32][3];
+#pragma unroll
+                for (int t = 0; t < W / 32; ++t) {
+                    acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
+                    const int sl = lane + 32 * t;
+                    const int j = jj[u][t];
+                    const int kl = FWD ? rr[u][t] - ps : pe - 1 - rr[u][t]; // < 0: final before this block; [0, gl): earlier in this block
+                    if (kl < gl) {
+                        const double v0 = v[sl], v1 = v[W + sl], v2 = v[2 * W + sl], v3 = v[3 * W + sl], v4 = v[4 * W + sl], v5 = v[5 * W + sl],
+                                     v6 = v[6 * W + sl], v7 = v[7 * W + sl], v8 = v[8 * W + sl];
+                        if (kl < h0) {
+                            double x0, x1, x2;
+                            if (kl < 0) {
+                                x0 = out[3 * (size_t)j]; x1 = out[3 * (size_t)j + 1]; x2 = out[3 * (size_t)j + 2];
+                            }
+                            else {
+                                x0 = s_x[kl][0]; x1 = s_x[kl][1]; x2 = s_x[kl][2];
+                            }
+                            acc[t][0] = v0 * x0 + v3 * x1 + v6 * x2;
+                            acc[t][1] = v1 * x0 + v4 * x1 + v7 * x2;
+                            acc[t][2] = v2 * x0 + v5 * x1 + v8 * x2;
                         }
-                        else {
-                            x0 = s_x[kl][0]; x1 = s_x[kl][1]; x2 = s_x[kl][2];
+                        else { // same half, earlier row: park Dinv_i * A_ik for the on-chip substitution
+                            const int e = gs_pair(il, kl - h0);
+                            const double* D = Dm[u];
+                            Lt[0][e] = D[0] * v0 + D[3] * v1 + D[6] * v2; Lt[1][e] = D[1] * v0 + D[4] * v1 + D[7] * v2;
+                            Lt[2][e] = D[2] * v0 + D[5] * v1 + D[8] * v2; Lt[3][e] = D[0] * v3 + D[3] * v4 + D[6] * v5;
+                            Lt[4][e] = D[1] * v3 + D[4] * v4 + D[7] * v5; Lt[5][e] = D[2] * v3 + D[5] * v4 + D[8] * v5;
+                            Lt[6][e] = D[0] * v6 + D[3] * v7 + D[6] * v8; Lt[7][e] = D[1] * v6 + D[4] * v7 + D[7] * v8;
+                            Lt[8][e] = D[2] * v6 + D[5] * v7 + D[8] * v8;
                         }
-                        a0 += v0 * x0 + v3 * x1 + v6 * x2;
-                        a1 += v1 * x0 + v4 * x1 + v7 * x2;
-                        a2 += v2 * x0 + v5 * x1 + v8 * x2;
-                    }
-                    else {
-                        const int e = gs_pair(il, kl - h0);
-                        Lt[0][e] = v0; Lt[1][e] = v1; Lt[2][e] = v2; Lt[3][e] = v3; Lt[4][e] = v4; Lt[5][e] = v5; Lt[6][e] = v6; Lt[7][e] = v7;
-                        Lt[8][e] = v8;
                     }
                 }
-            }
+                double a0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+                double a1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+                double a2 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                a0 += __shfl_down_sync(0xffffffffu, a0, o);
-                a1 += __shfl_down_sync(0xffffffffu, a1, o);
-                a2 += __shfl_down_sync(0xffffffffu, a2, o);
-            }
-            if (lane == 0) {
-                s_rhs[il][0] = rhs[3 * (size_t)i] - a0;
-                s_rhs[il][1] = rhs[3 * (size_t)i + 1] - a1;
-                s_rhs[il][2] = rhs[3 * (size_t)i + 2] - a2;
+                for (int o = 16; o > 0; o >>= 1) {
+                    a0 += __shfl_down_sync(0xffffffffu, a0, o);
+                    a1 += __shfl_down_sync(0xffffffffu, a1, o);
+                    a2 += __shfl_down_sync(0xffffffffu, a2, o);
+                }
+                if (lane == 0) { // r~ = Dinv (rhs - external couplings)
+                    const double* D = Dm[u];
+                    const double r0 = rhs[3 * (size_t)i] - a0, r1 = rhs[3 * (size_t)i + 1] - a1, r2 = rhs[3 * (size_t)i + 2] - a2;
+                    s_rhs[il][0] = D[0] * r0 + D[3] * r1 + D[6] * r2;
+                    s_rhs[il][1] = D[1] * r0 + D[4] * r1 + D[7] * r2;
+                    s_rhs[il][2] = D[2] * r0 + D[5] * r1 + D[8] * r2;
+                }
             }
         }
         __syncthreads();
+        GS_STAMP(h0 ? 7 : 3);
         if (warp == 0) {
-            double r0 = 0.0, r1 = 0.0, r2 = 0.0, D[9];
+            // x_k = r~_k ; r~_i -= (Dinv_i A_ik) x_k for the later rows i: the pivot needs no multiply, the update is one
+            // 3-deep FMA chain per component
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
             int node = -1;
             if (lane < hn) {
                 node = seq[FWD ? ps + h0 + lane : pe - 1 - (h0 + lane)];
                 r0 = s_rhs[lane][0]; r1 = s_rhs[lane][1]; r2 = s_rhs[lane][2];
-#pragma unroll
-                for (int q = 0; q < 9; ++q) D[q] = dinv[9 * (size_t)node + q];
             }
-            else {
-#pragma unroll
-                for (int q = 0; q < 9; ++q) D[q] = 0.0;
-            }
-            double mx0 = 0.0, mx1 = 0.0, mx2 = 0.0; // this lane's solution
             for (int k = 0; k < hn; ++k) {
-                // every lane evaluates Dinv r of its own row; the pivot lane's value is the one that counts
-                const double y0 = D[0] * r0 + D[3] * r1 + D[6] * r2;
-                const double y1 = D[1] * r0 + D[4] * r1 + D[7] * r2;
-                const double y2 = D[2] * r0 + D[5] * r1 + D[8] * r2;
-                const double x0 = __shfl_sync(0xffffffffu, y0, k);
-                const double x1 = __shfl_sync(0xffffffffu, y1, k);
-                const double x2 = __shfl_sync(0xffffffffu, y2, k);
-                if (lane == k) { mx0 = y0; mx1 = y1; mx2 = y2; }
+                const double x0 = __shfl_sync(0xffffffffu, r0, k);
+                const double x1 = __shfl_sync(0xffffffffu, r1, k);
+                const double x2 = __shfl_sync(0xffffffffu, r2, k);
                 if (lane > k && lane < hn) {
                     const int e = gs_pair(lane, k);
-                    r0 -= Lt[0][e] * x0 + Lt[3][e] * x1 + Lt[6][e] * x2;
-                    r1 -= Lt[1][e] * x0 + Lt[4][e] * x1 + Lt[7][e] * x2;
-                    r2 -= Lt[2][e] * x0 + Lt[5][e] * x1 + Lt[8][e] * x2;
+                    r0 = fma(-Lt[6][e], x2, fma(-Lt[3][e], x1, fma(-Lt[0][e], x0, r0)));
+                    r1 = fma(-Lt[7][e], x2, fma(-Lt[4][e], x1, fma(-Lt[1][e], x0, r1)));
+                    r2 = fma(-Lt[8][e], x2, fma(-Lt[5][e], x1, fma(-Lt[2][e], x0, r2)));
                 }
             }
+            const double mx0 = r0, mx1 = r1, mx2 = r2;
             if (lane < hn) {
                 s_x[h0 + lane][0] = mx0; s_x[h0 + lane][1] = mx1; s_x[h0 + lane][2] = mx2;
                 out[3 * (size_t)node] = mx0; out[3 * (size_t)node + 1] = mx1; out[3 * (size_t)node + 2] = mx2;
@@ -516,6 +548,7 @@ __device__ __forceinline__ void gs_block_body(GSShared& sh, int b, const int* __
                     out_scaled[3 * (size_t)node + 2] = d[2] * mx0 + d[5] * mx1 + d[8] * mx2;
                 }
             }
+            GS_STAMP(h0 ? 8 : 4);
         }
     }
 }
@@ -956,11 +989,25 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
     a.r = r; a.hdu = L.tmp.p; a.dhdu = L.dAu.p; a.du = L.du.p; a.u = u; // hdu: unscaled forward solution; dhdu = D hdu
     a.fuse_update = project ? 0 : 1;
     iterations = (iterations + 1) >> 1;
+    static long long* dbg_dev = nullptr;
+    const char* dbg_env = getenv("HOT_GS_DEBUG");
+    if (dbg_env && !dbg_dev) {
+        cudaMalloc((void**)&dbg_dev, 32 * sizeof(long long));
+        cudaMemcpyToSymbol(g_gs_dbg, &dbg_dev, sizeof(dbg_dev));
+    }
+    if (dbg_dev) {
+        long long init[32] = {0};
+        init[31] = a.cfb[0] + atoi(dbg_env); // watched block: the n-th of colour 0
+        cudaMemcpy(dbg_dev, init, sizeof init, cudaMemcpyHostToDevice);
+    }
     for (; iterations--;) {
         bool launched = false;
         // few blocks per colour: a big CTA per block (16 warps stream the rows) on one SM each; many: 3 CTAs of 8 warps per SM
+        // (many blocks per colour: the per-phase launches below keep 3 CTAs per SM busy, which measures faster than the
+        //  cooperative form whose register budget allows only 2)
+        static const bool force_coop = getenv("HOT_GS_COOP") != nullptr;
         if (max_blocks <= 2 * 148) RC(launch_gs_sweep<512>(s, a, max_blocks, &launched));
-        else RC(launch_gs_sweep<GS_THREADS>(s, a, max_blocks, &launched));
+        else if (force_coop) RC(launch_gs_sweep<GS_THREADS>(s, a, max_blocks, &launched));
         if (!launched) {
             for (int c = 0; c < 8; ++c) {
                 const int b0 = a.cfb[c], b1 = a.cfb[c + 1];
@@ -985,6 +1032,13 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
             RC(level_project(s, level, L.dAu.p));
             RC(vec_axpy(s, 3L * L.n, -1.0, L.dAu.p, r));
         }
+    }
+    if (dbg_dev) {
+        long long h[32];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, dbg_dev, sizeof h, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[gs dbg] level %d n %d blocks/colour<=%d: half0 wait %lld zero %lld phaseA %lld phaseB %lld | half1 wait %lld zero %lld phaseA %lld phaseB %lld cycles\n",
+            level, L.n, max_blocks, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[8] - h[7]);
     }
     return 0;
 }
