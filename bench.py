@@ -387,7 +387,7 @@ def run_ours(args):
             "config": {"workload": desc, "particles_per_gpu": n // world, "grid_nodes": n_nodes, "pages": sim.num_pages,
                        "l2": "flushed before every timed step (256 MiB memset)",
                        "parallelism": ("single GPU" if world == 1 else
-                                       f"one object over {world} GPUs: contiguous page-group ranges, replicated sort / DOF numbering, NCCL all-reduce of grid mass+momentum per P2G "
+                                       f"one object over {world} GPUs: contiguous page-group ranges, replicated sort / DOF numbering, NCCL all-reduce of the interface pages (mass+momentum) + one mask per page per P2G "
                                        f"(interface nodes per rank pair boundary: {part['n_interface']})")},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

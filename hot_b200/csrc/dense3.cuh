@@ -195,6 +195,15 @@ __device__ __forceinline__ double clamp_small_magnitude(double x, double eps)
     return x;
 }
 
+// PSD projection of [[a, b], [b, a]]
+__device__ __forceinline__ void pd2_equal_diagonal(double* B)
+{
+    const double l1 = fmax(B[0] + B[1], 0.0), l2 = fmax(B[0] - B[1], 0.0);
+    const double d = 0.5 * (l1 + l2), o = 0.5 * (l1 - l2);
+    B[0] = B[3] = d;
+    B[1] = B[2] = o;
+}
+
 // SVD-space Hessian blocks of the fixed-corotated model, CorotatedIsotropic.h:116-144 +
 // SvdBasedIsotropicHelper.h:223-247.  A: 3x3 symmetric (column-major 9), B01/B12/B20: 2x2 symmetric (4 each).
 struct HessBlocks {
@@ -222,10 +231,19 @@ __device__ inline void corotated_blocks(const double* sig, double mu, double lam
     h.B12[0] = h.B12[3] = (m12 + p12) * 0.5; h.B12[1] = h.B12[2] = (m12 - p12) * 0.5;
     h.B20[0] = h.B20[3] = (m02 + p02) * 0.5; h.B20[1] = h.B20[2] = (m02 - p02) * 0.5;
     if (project) {
-        make_pd<3>(h.A);
-        make_pd<2>(h.B01);
-        make_pd<2>(h.B12);
-        make_pd<2>(h.B20);
+        // makePD (EigenDecomposition.h:126-135).  The 2x2 blocks have equal diagonal entries [[a, b], [b, a]]: eigenvalues
+        // a + b, a - b on the fixed eigenvectors (1, +-1)/sqrt(2), so the clamp is closed-form (no iteration, no sqrt / divide).
+        // The 3x3 block is positive definite for all but strongly compressed / inverted states: a Sylvester test skips the
+        // Jacobi iteration then (fp64 divide / sqrt sequences cost ~1k dependent cycles each on this part).
+        pd2_equal_diagonal(h.B01);
+        pd2_equal_diagonal(h.B12);
+        pd2_equal_diagonal(h.B20);
+        const double m2 = h.A[0] * h.A[4] - h.A[1] * h.A[1];
+        const double m3 = h.A[0] * (h.A[4] * h.A[8] - h.A[5] * h.A[5]) - h.A[1] * (h.A[1] * h.A[8] - h.A[5] * h.A[2])
+            + h.A[2] * (h.A[1] * h.A[5] - h.A[4] * h.A[2]);
+        const double scale = fabs(h.A[0]) + fabs(h.A[4]) + fabs(h.A[8]);
+        const bool pd = h.A[0] > 1e-12 * scale && m2 > 1e-12 * scale * scale && m3 > 1e-12 * scale * scale * scale;
+        if (!pd) make_pd<3>(h.A);
     }
 }
 // dPdFOfSigmaContract(Projected), SvdBasedIsotropicHelper.h:256-282: K = dPdF_Sigma : D (both in SVD space)

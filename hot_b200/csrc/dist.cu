@@ -48,6 +48,47 @@ __global__ void k_node_owner(long gn, const int* __restrict__ g_idx, const unsig
         atomicMax(range + 1, id);
     }
 }
+// grid channels of the interface pages <-> exchange buffer: [page k][channel 0..3][element e]
+__global__ void k_pack_pages(int n_ip, const int* __restrict__ ipage, size_t gs, const double* __restrict__ g_m, const double* __restrict__ g_v,
+    double* __restrict__ buf)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)n_ip * 4 * Geo::E) return;
+    const int e = (int)(t % Geo::E), ch = (int)((t / Geo::E) % 4), k = (int)(t / (4 * Geo::E));
+    const size_t a = (size_t)ipage[k] * Geo::E + e;
+    buf[t] = ch == 0 ? g_m[a] : g_v[(size_t)(ch - 1) * gs + a];
+}
+__global__ void k_unpack_pages(int n_ip, const int* __restrict__ ipage, size_t gs, const double* __restrict__ buf, double* __restrict__ g_m,
+    double* __restrict__ g_v)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)n_ip * 4 * Geo::E) return;
+    const int e = (int)(t % Geo::E), ch = (int)((t / Geo::E) % 4), k = (int)(t / (4 * Geo::E));
+    const size_t a = (size_t)ipage[k] * Geo::E + e;
+    if (ch == 0) g_m[a] = buf[t];
+    else g_v[(size_t)(ch - 1) * gs + a] = buf[t];
+}
+// per page: bit e set when node e carries mass (as a double: exact for 32 bits; the MAX over ranks is the complete mask
+// because every rank that touches a page holds its complete mass after the interface exchange, the others hold 0)
+__global__ void k_page_nonzero(long n_pages, const double* __restrict__ g_m, const unsigned* __restrict__ mask, int rank, double* __restrict__ out)
+{
+    const long pg = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pg >= n_pages) return;
+    unsigned bits = 0;
+    if (mask[pg] & (1u << rank))
+        for (int e = 0; e < Geo::E; ++e) bits |= (g_m[(size_t)pg * Geo::E + e] != 0.0 ? 1u : 0u) << e;
+    out[pg] = (double)bits;
+}
+__global__ void k_flags_from_bits(long gn, const double* __restrict__ bits, int* __restrict__ flag)
+{
+    const long a = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < gn) flag[a] = (((unsigned)bits[a / Geo::E]) >> (a % Geo::E)) & 1u;
+}
+__global__ void k_ipage_flags(long n_pages, const unsigned* __restrict__ mask, int* __restrict__ flag)
+{
+    const long pg = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pg < n_pages) flag[pg] = __popc(mask[pg]) >= 2;
+}
 __global__ void k_pack(int n, int comps, const int* __restrict__ dof, const double* __restrict__ v, double* __restrict__ buf)
 {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,6 +141,52 @@ int dist_after_sort(Sim* s)
     HOT_CUDA(cudaStreamSynchronize(s->stream));
     s->g0 = cut[s->rank]; s->g1 = cut[s->rank + 1];
     s->p0 = first[s->g0]; s->p1 = first[s->g1];
+    // which ranks touch which page, and the interface pages (touched by >= 2 ranks)
+    cudaStream_t st = s->stream;
+    HOT_CUDA(s->page_mask.reserve(s->n_pages));
+    HOT_CUDA(s->iface_page.reserve(s->n_pages));
+    HOT_CUDA(s->head_flag.reserve(s->n_pages));
+    HOT_CUDA(s->dcount.reserve(16));
+    HOT_CUDA(cudaMemsetAsync(s->page_mask.p, 0, s->n_pages * sizeof(unsigned), st));
+    k_page_touch<<<nblk(s->n_groups * 8), TPB, 0, st>>>(s->n_groups, s->group_slot.p, s->group_rank.p, s->nbr8.p, s->page_mask.p);
+    HOT_LAUNCHED(s);
+    k_ipage_flags<<<nblk(s->n_pages), TPB, 0, st>>>(s->n_pages, s->page_mask.p, s->head_flag.p);
+    HOT_LAUNCHED(s);
+    size_t bytes = 0;
+    cub::DeviceSelect::Flagged(nullptr, bytes, cub::CountingInputIterator<int>(0), s->head_flag.p, s->iface_page.p, s->dcount.p, (int)s->n_pages, st);
+    HOT_CUDA(s->cub_tmp.reserve(bytes + 16));
+    HOT_CUDA(cub::DeviceSelect::Flagged(s->cub_tmp.p, bytes, cub::CountingInputIterator<int>(0), s->head_flag.p, s->iface_page.p, s->dcount.p,
+        (int)s->n_pages, st));
+    s->launches++;
+    HOT_CUDA(cudaMemcpyAsync(s->hcount + 20, s->dcount.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HOT_CUDA(cudaStreamSynchronize(st));
+    s->n_iface_pages = s->hcount[20];
+    return 0;
+}
+
+// P2G of a partitioned object: sum the partial mass / momentum of the interface pages, then agree on which nodes carry mass
+// (one 32-bit mask per page) so that every rank computes the same DOF numbering as a single GPU would
+int dist_p2g_exchange(Sim* s, int* node_flags /* n_pages * E, out */)
+{
+    cudaStream_t st = s->stream;
+    const long cnt = (long)s->n_iface_pages * 4 * Geo::E;
+    KTime t(s, KC_TRANSFER);
+    if (cnt > 0) {
+        int rc = reserve_xbuf(s, cnt);
+        if (rc) return rc;
+        k_pack_pages<<<nblk(cnt), TPB, 0, st>>>(s->n_iface_pages, s->iface_page.p, s->g_stride, s->g_m.p, s->g_v.p, s->xbuf);
+        HOT_LAUNCHED(s);
+        if (s->allreduce(s->allreduce_user, 0, cnt) != 0) return fail(s, "all-reduce callback failed");
+        k_unpack_pages<<<nblk(cnt), TPB, 0, st>>>(s->n_iface_pages, s->iface_page.p, s->g_stride, s->xbuf, s->g_m.p, s->g_v.p);
+        HOT_LAUNCHED(s);
+    }
+    int rc = reserve_xbuf(s, s->n_pages);
+    if (rc) return rc;
+    k_page_nonzero<<<nblk(s->n_pages), TPB, 0, st>>>(s->n_pages, s->g_m.p, s->page_mask.p, s->rank, s->xbuf);
+    HOT_LAUNCHED(s);
+    if (s->allreduce(s->allreduce_user, 1, s->n_pages) != 0) return fail(s, "all-reduce callback failed");
+    k_flags_from_bits<<<nblk((long)s->g_stride), TPB, 0, st>>>((long)s->g_stride, s->xbuf, node_flags);
+    HOT_LAUNCHED(s);
     return 0;
 }
 
@@ -113,16 +200,12 @@ int dist_after_numbering(Sim* s)
     cudaStream_t st = s->stream;
     const long gn = (long)s->g_stride;
     const int nn = s->num_nodes;
-    HOT_CUDA(s->page_mask.reserve(s->n_pages));
     HOT_CUDA(s->head_flag.reserve(nn > 0 ? nn : 1));
     HOT_CUDA(s->iface_dof.reserve(nn > 0 ? nn : 1));
     HOT_CUDA(s->dcount.reserve(16));
-    HOT_CUDA(cudaMemsetAsync(s->page_mask.p, 0, s->n_pages * sizeof(unsigned), st));
     HOT_CUDA(cudaMemsetAsync(s->head_flag.p, 0, (size_t)nn * sizeof(int), st));
     const int init[2] = {0x7fffffff, -1};
     HOT_CUDA(cudaMemcpyAsync(s->dcount.p + 8, init, sizeof init, cudaMemcpyHostToDevice, st));
-    k_page_touch<<<nblk(s->n_groups * 8), TPB, 0, st>>>(s->n_groups, s->group_slot.p, s->group_rank.p, s->nbr8.p, s->page_mask.p);
-    HOT_LAUNCHED(s);
     k_node_owner<<<nblk(gn), TPB, 0, st>>>(gn, s->g_idx.p, s->page_mask.p, s->rank, s->head_flag.p, s->dcount.p + 8);
     HOT_LAUNCHED(s);
     size_t bytes = 0;

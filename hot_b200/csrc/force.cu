@@ -419,7 +419,7 @@ __global__ void k_add(long n, const double* __restrict__ x, double* __restrict__
 __global__ void k_cn_finish(int n, const double* __restrict__ mass, double factor, double* __restrict__ tol)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) tol[i] *= factor / mass[i];
+    if (i < n) tol[i] = mass[i] != 0.0 ? tol[i] * (factor / mass[i]) : 1.0; // (mass 0: a node only other ranks touch)
 }
 
 } // namespace

@@ -273,6 +273,10 @@ __global__ void k_diag_invert(int n, int Ainv, double* __restrict__ D)
 #pragma unroll
         for (int q = 0; q < 9; ++q) b[q] = (q == 0 || q == 4 || q == 8) ? 1.0 / a[q] : 0.0;
     }
+    else if (a[0] == 0.0 && a[4] == 0.0 && a[8] == 0.0) { // a node only other ranks touch (partitioned run): keep it finite
+#pragma unroll
+        for (int q = 0; q < 9; ++q) b[q] = (q == 0 || q == 4 || q == 8) ? 1.0 : 0.0;
+    }
     else inv3(a, b);
 #pragma unroll
     for (int q = 0; q < 9; ++q) D[9 * (size_t)i + q] = b[q];

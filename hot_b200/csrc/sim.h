@@ -220,7 +220,8 @@ struct Sim {
     int dof0 = 0, dof1 = 0; // own DOF ids
     int n_iface = 0;
     bool iface_valid = false; // interface list built for the current sort
-    DevBuf<int> iface_dof, group_rank;
+    DevBuf<int> iface_dof, group_rank, iface_page;
+    int n_iface_pages = 0;
     DevBuf<unsigned> page_mask;
     DevBuf<double> scat_tmp;
     DevBuf<double> sv[32]; // solver work vectors (solver.cu)
@@ -260,7 +261,7 @@ struct KTime { // RAII: times everything launched on s->stream in its scope unde
 
 // sort.cu
 int sort_and_activate(Sim* s);
-int number_nodes(Sim* s); // a7, after the P2G scatter
+int number_nodes(Sim* s, bool flags_ready = false); // a7, after the P2G scatter (flags_ready: head_flag already holds the non-zero node flags)
 // transfer.cu
 int p2g(Sim* s);
 int g2p(Sim* s, double dt, int* flags);
@@ -280,6 +281,7 @@ int hessian_apply_mf(Sim* s, const double* x, double* b);
 int eval_cn_tolerance(Sim* s, double eps, double dt, double* tol);
 // dist.cu
 int dist_after_sort(Sim* s); // group / particle ranges of this rank
+int dist_p2g_exchange(Sim* s, int* node_flags); // interface-page sum of (m, mv) + global non-zero node flags
 int dist_after_numbering(Sim* s); // page ownership, DOF ranges, interface node list
 int dist_allreduce_buffer(Sim* s, double* dev, long count, int op); // whole device array, in place
 int dist_exchange_iface(Sim* s, double* v, int comps); // sum over ranks on the interface nodes of a DOF array with `comps` per node

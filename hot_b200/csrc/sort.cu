@@ -218,20 +218,21 @@ __global__ void k_mass_flags(long n, const double* __restrict__ m, int* __restri
 }
 
 // MpmGrid.h:148-161 (idx), MpmSimulationBase.cpp:523-531 (v /= m), :817-826 (mass_matrix)
-__global__ void k_number_and_normalise(long n, size_t gs, const int* __restrict__ scan, double* __restrict__ m, double* __restrict__ v,
-    int* __restrict__ idx, int* __restrict__ dof_slot, double* __restrict__ mass_matrix, double* __restrict__ vn)
+// (flag = node carries mass; in a partitioned run a rank numbers nodes whose mass only other ranks hold: m == 0 there)
+__global__ void k_number_and_normalise(long n, size_t gs, const int* __restrict__ scan, const int* __restrict__ flag, double* __restrict__ m,
+    double* __restrict__ v, int* __restrict__ idx, int* __restrict__ dof_slot, double* __restrict__ mass_matrix, double* __restrict__ vn)
 {
     long a = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     double mm = m[a];
-    if (mm != 0.0) {
+    if (flag[a]) {
         int id = scan[a];
         idx[a] = id;
         dof_slot[id] = (int)a;
         mass_matrix[id] = mm;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            double q = v[d * gs + a] / mm;
+            double q = mm != 0.0 ? v[d * gs + a] / mm : 0.0;
             v[d * gs + a] = q;
             vn[3 * (size_t)id + d] = q;
         }
@@ -369,7 +370,7 @@ int sort_and_activate(Sim* s)
     return dist_after_sort(s);
 }
 
-int number_nodes(Sim* s)
+int number_nodes(Sim* s, bool flags_ready)
 {
     cudaStream_t st = s->stream;
     const size_t gn = s->g_stride;
@@ -378,13 +379,15 @@ int number_nodes(Sim* s)
     HOT_CUDA(s->mass_matrix.reserve(gn));
     HOT_CUDA(s->vn.reserve(3 * gn));
     HOT_CUDA(s->dv.reserve(3 * gn));
-    k_mass_flags<<<nblk(gn), TPB, 0, st>>>(gn, s->g_m.p, s->head_flag.p);
-    HOT_LAUNCHED(s);
+    if (!flags_ready) {
+        k_mass_flags<<<nblk(gn), TPB, 0, st>>>(gn, s->g_m.p, s->head_flag.p);
+        HOT_LAUNCHED(s);
+    }
     int rc = with_tmp(s, [&](void* t, size_t& b) {
         return cub::DeviceScan::ExclusiveSum(t, b, s->head_flag.p, s->scratch_i.p, (int)gn, st);
     });
     if (rc) return rc;
-    k_number_and_normalise<<<nblk(gn), TPB, 0, st>>>(gn, gn, s->scratch_i.p, s->g_m.p, s->g_v.p, s->g_idx.p, s->dof_slot.p,
+    k_number_and_normalise<<<nblk(gn), TPB, 0, st>>>(gn, gn, s->scratch_i.p, s->head_flag.p, s->g_m.p, s->g_v.p, s->g_idx.p, s->dof_slot.p,
         s->mass_matrix.p, s->vn.p);
     HOT_LAUNCHED(s);
     // n_nodes = scan[last] + flag[last]

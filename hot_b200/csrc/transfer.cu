@@ -226,15 +226,14 @@ int p2g(Sim* s)
         }
     }
     int rc;
-    if (s->world > 1) { // once per step: the replicated DOF numbering needs the complete mass field on every rank
-        KTime t(s, KC_TRANSFER);
-        rc = dist_allreduce_buffer(s, s->g_m.p, (long)gn, 0);
-        if (!rc) rc = dist_allreduce_buffer(s, s->g_v.p, 3 * (long)gn, 0);
+    if (s->world > 1) { // ghost-layer exchange: interface pages only (+ one mask per page so that the numbering is global)
+        HOT_CUDA(s->head_flag.reserve(gn));
+        rc = dist_p2g_exchange(s, s->head_flag.p);
         if (rc) return rc;
     }
     {
         KTime t(s, KC_NUMBER);
-        rc = number_nodes(s);
+        rc = number_nodes(s, s->world > 1);
     }
     if (rc) return rc;
     rc = dist_after_numbering(s);
