@@ -253,6 +253,7 @@ def dist_solver_leg(sim, sc, args):
 
 
 def run_ours(args):
+    os.environ["NCCL_DEBUG"] = "WARN"          # the JSON line must be the only thing rank 0 writes to stdout
     import torch
     import torch.distributed as dist
     import hot_b200
