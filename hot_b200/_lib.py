@@ -92,6 +92,10 @@ def load_library(path=LIB_PATH):
         "hot_get_mass_matrix": (C.c_int, [vp, vp]),
         "hot_set_dv": (C.c_int, [vp, vp]),
         "hot_g2p": (C.c_int, [vp, C.c_double, _c_int_p]),
+        "hot_set_plasticity": (C.c_int, [vp, C.c_int, vp]),
+        "hot_apply_plasticity": (C.c_int, [vp]),
+        "hot_get_plastic_state": (C.c_int, [vp, vp, vp, vp]),
+        "hot_set_plastic_state": (C.c_int, [vp, vp]),
         "hot_set_partition": (C.c_int, [vp, C.c_int, C.c_int, ALLREDUCE_FN, vp]),
         "hot_set_exchange_buffer": (C.c_int, [vp, vp, C.c_long]),
         "hot_get_partition": (C.c_int, [vp, C.POINTER(C.c_long)]),

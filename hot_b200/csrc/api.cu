@@ -29,6 +29,11 @@ __global__ void k_soa_to_aos(long n, int comps, const double* __restrict__ soa, 
     int c = (int)(t - s * comps);
     aos[(size_t)orig_id[s] * comps + c] = soa[c * stride + s];
 }
+__global__ void k_fill1(long n, double a, double* v)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) v[t] = a;
+}
 __global__ void k_iota_i(long n, int* v)
 {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -211,6 +216,8 @@ int hot_set_particles(hot_sim* s, long n, const double* X, const double* V, cons
     }
     k_iota_i<<<nblk(n), TPB, 0, st>>>(n, s->P.orig_id.p);
     HOT_LAUNCHED(s);
+    k_fill1<<<nblk(n), TPB, 0, st>>>(n, 1.0, s->P.Jp.p); // SnowPlasticity::Jp starts at 1
+    HOT_LAUNCHED(s);
     s->sorted = false;
     s->p2g_done = false;
     return 0;
@@ -341,6 +348,50 @@ int hot_set_dv(hot_sim* s, const double* dv)
 }
 
 int hot_g2p(hot_sim* s, double dt, int* flags) { return g2p(s, dt, flags); }
+
+// ---- plasticity (rank 2 of SURVEY 8f): return mapping applied by hot_g2p after evolveStrain -------------------------------
+int hot_set_plasticity(hot_sim* s, int model, const double* params)
+{
+    if (model < 0 || model > 2) return fail(s, "hot_set_plasticity: model must be 0 (none), 1 (VonMisesFixedCorotated) or 2 (SnowPlasticity)");
+    if (model && !params) return fail(s, "hot_set_plasticity: null parameters");
+    if (model == 1 && !(params[0] >= 0)) return fail(s, "yield_stress must be non-negative (PlasticityApplier.cpp:99)");
+    s->plastic_model = model;
+    for (int k = 0; k < 5; ++k) s->plastic_param[k] = (model == 2 || (model == 1 && k == 0)) ? params[k] : 0.0;
+    return 0;
+}
+int hot_apply_plasticity(hot_sim* s)
+{
+    if (s->N <= 0) return fail(s, "hot_apply_plasticity: no particles");
+    if (!s->sorted) { s->p0 = 0; s->p1 = s->N; }
+    return apply_plasticity(s);
+}
+// per-particle plastic state in original order: SnowPlasticity::Jp and the (hardened) mu / lambda; any pointer may be NULL
+int hot_get_plastic_state(hot_sim* s, double* Jp, double* mu, double* lambda)
+{
+    const long n = s->N;
+    if (n <= 0) return fail(s, "hot_get_plastic_state: no particles");
+    HOT_CUDA(s->stage.reserve(28 * (size_t)n));
+    struct Item { double* h; const double* soa; };
+    Item items[] = {{Jp, s->P.Jp.p}, {mu, s->P.mu.p}, {lambda, s->P.lam.p}};
+    size_t off = 0;
+    for (const Item& it : items) {
+        if (!it.h) continue;
+        double* d = s->stage.p + off;
+        k_soa_to_aos<<<nblk(n), TPB, 0, s->stream>>>(n, 1, it.soa, s->P.stride, s->P.orig_id.p, d);
+        HOT_LAUNCHED(s);
+        HOT_CUDA(cudaMemcpyAsync(it.h, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        off += (size_t)n;
+    }
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+int hot_set_plastic_state(hot_sim* s, const double* Jp)
+{
+    if (s->N <= 0 || s->sorted) return fail(s, "hot_set_plastic_state: call right after hot_set_particles (original particle order)");
+    HOT_CUDA(cudaMemcpyAsync(s->P.Jp.p, Jp, (size_t)s->N * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
 
 // ---- row (e): one object over several GPUs (dist.cu) ---------------------------------------------------------------
 int hot_set_partition(hot_sim* s, int rank, int world, hot_allreduce_fn fn, void* user)

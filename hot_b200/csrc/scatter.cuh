@@ -70,8 +70,8 @@ __device__ __forceinline__ int tile_base(int bx, int by, int bz)
 //   __device__ static void accumulate(const Args&, const double* rec, int pl, double (&acc)[9][NCH])
 //   __device__ static void flush(const Args&, long a, const double (&v)[NCH])     a = grid array index
 //   __device__ static void gather_node(const Args&, long a, double (&v)[3])       (GATHER only)
-template <class Policy>
-__global__ void __launch_bounds__(SC_THREADS, 5) k_plane_scatter(typename Policy::Args args, const int* __restrict__ cell_start,
+template <class Policy, int MINB = 5, int UNROLL = 1>
+__global__ void __launch_bounds__(SC_THREADS, MINB) k_plane_scatter(typename Policy::Args args, const int* __restrict__ cell_start,
     const int* __restrict__ group_slot, const int* __restrict__ nbr8)
 {
     constexpr int NCH = Policy::NCH, RAW = Policy::RAW, TILE = Geo::TILE, E = Geo::E;
@@ -109,7 +109,14 @@ __global__ void __launch_bounds__(SC_THREADS, 5) k_plane_scatter(typename Policy
         for (int k = tid; k < cn; k += SC_THREADS) Policy::stage(args, (size_t)cb + k, smem + sc_swz(k), gtile);
         __syncthreads();
         const int pb = max(my_b, cb) - cb, pe = min(my_e, cb + cn) - cb;
-        for (int p = pb; p < pe; ++p) Policy::accumulate(args, smem + sc_swz(p), pl, acc);
+        int p = pb;
+        if (UNROLL == 2) { // two particles per trip: their weight evaluations are independent instruction streams (ILP)
+            for (; p + 1 < pe; p += 2) {
+                Policy::accumulate(args, smem + sc_swz(p), pl, acc);
+                Policy::accumulate(args, smem + sc_swz(p + 1), pl, acc);
+            }
+        }
+        for (; p < pe; ++p) Policy::accumulate(args, smem + sc_swz(p), pl, acc);
     }
     __syncthreads(); // records dead -> reuse as warp tiles
     for (int a = tid; a < TILE_DOUBLES; a += SC_THREADS) smem[a] = 0.0;

@@ -67,6 +67,7 @@ struct DevBuf {
 // particle attribute set, component-major SoA (attribute a, component c at a[c*stride + s])
 struct ParticleSoA {
     DevBuf<double> X, V, M, C, F, Fn, vol, mu, lam, gradV;
+    DevBuf<double> Jp; // SnowPlasticity::Jp (PlasticityApplier.h:57-80), 1 per particle
     DevBuf<int> orig_id;
     size_t stride = 0;
     cudaError_t reserve(size_t n);
@@ -181,6 +182,9 @@ struct Sim {
     DevBuf<double> dv, vn, mass_matrix;
 
     DevBuf<int> flags; // g2p CFL flags
+    // plasticity applied after G2P + evolveStrain (MpmSimulationBase.cpp:1039-1064): 0 none, 1 VonMisesFixedCorotated, 2 SnowPlasticity
+    int plastic_model = 0;
+    double plastic_param[5] = {0, 0, 0, 0, 0};
 
     // ---- force model state (force.cu); particle arrays are in sorted order and live for one time step
     bool project_pd = true; // CorotatedIsotropic::project (CorotatedIsotropic.h:60)
@@ -265,6 +269,7 @@ int number_nodes(Sim* s, bool flags_ready = false); // a7, after the P2G scatter
 // transfer.cu
 int p2g(Sim* s);
 int g2p(Sim* s, double dt, int* flags);
+int apply_plasticity(Sim* s);
 // force.cu -- all pointers are DEVICE pointers to DOF vectors (n_nodes x 3)
 int backup_strain(Sim* s);
 int restore_strain(Sim* s);

@@ -39,6 +39,7 @@ cudaError_t ParticleSoA::reserve(size_t n)
     if ((e = vol.reserve(st)) != cudaSuccess) return e;
     if ((e = mu.reserve(st)) != cudaSuccess) return e;
     if ((e = lam.reserve(st)) != cudaSuccess) return e;
+    if ((e = Jp.reserve(st)) != cudaSuccess) return e;
     if ((e = orig_id.reserve(st)) != cudaSuccess) return e;
     stride = st;
     return cudaSuccess;
@@ -46,7 +47,7 @@ cudaError_t ParticleSoA::reserve(size_t n)
 void ParticleSoA::swap(ParticleSoA& o)
 {
     X.swap(o.X); V.swap(o.V); M.swap(o.M); C.swap(o.C); F.swap(o.F);
-    vol.swap(o.vol); mu.swap(o.mu); lam.swap(o.lam); orig_id.swap(o.orig_id);
+    vol.swap(o.vol); mu.swap(o.mu); lam.swap(o.lam); orig_id.swap(o.orig_id); Jp.swap(o.Jp);
     size_t t = stride; stride = o.stride; o.stride = t;
 }
 
@@ -81,9 +82,9 @@ __global__ void k_make_keys(long n, const double* __restrict__ X, size_t stride,
 __global__ void k_reorder(long n, const int* __restrict__ perm, size_t ss, size_t ds,
     const double* __restrict__ sX, const double* __restrict__ sV, const double* __restrict__ sM, const double* __restrict__ sC,
     const double* __restrict__ sF, const double* __restrict__ svol, const double* __restrict__ smu, const double* __restrict__ slam,
-    const int* __restrict__ sid,
+    const int* __restrict__ sid, const double* __restrict__ sJp,
     double* __restrict__ dX, double* __restrict__ dV, double* __restrict__ dM, double* __restrict__ dC, double* __restrict__ dF,
-    double* __restrict__ dvol, double* __restrict__ dmu, double* __restrict__ dlam, int* __restrict__ did)
+    double* __restrict__ dvol, double* __restrict__ dmu, double* __restrict__ dlam, int* __restrict__ did, double* __restrict__ dJp)
 {
     long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -103,6 +104,7 @@ __global__ void k_reorder(long n, const int* __restrict__ perm, size_t ss, size_
     dmu[s] = smu[p];
     dlam[s] = slam[p];
     did[s] = sid[p];
+    dJp[s] = sJp[p];
 }
 
 __global__ void k_group_flags(long n, const uint64_t* __restrict__ keys, int* __restrict__ flag)
@@ -284,8 +286,8 @@ int sort_and_activate(Sim* s)
     });
     if (rc) return rc;
     k_reorder<<<nblk(n), TPB, 0, st>>>(n, s->perm.p, s->P.stride, s->Palt.stride, s->P.X.p, s->P.V.p, s->P.M.p, s->P.C.p, s->P.F.p,
-        s->P.vol.p, s->P.mu.p, s->P.lam.p, s->P.orig_id.p, s->Palt.X.p, s->Palt.V.p, s->Palt.M.p, s->Palt.C.p, s->Palt.F.p,
-        s->Palt.vol.p, s->Palt.mu.p, s->Palt.lam.p, s->Palt.orig_id.p);
+        s->P.vol.p, s->P.mu.p, s->P.lam.p, s->P.orig_id.p, s->P.Jp.p, s->Palt.X.p, s->Palt.V.p, s->Palt.M.p, s->Palt.C.p, s->Palt.F.p,
+        s->Palt.vol.p, s->Palt.mu.p, s->Palt.lam.p, s->Palt.orig_id.p, s->Palt.Jp.p);
     HOT_LAUNCHED(s);
     s->P.swap(s->Palt);
 

@@ -20,6 +20,8 @@
 //      so plain read-modify-write + __syncwarp suffices;
 //   4. the warp tiles are summed and flushed with one fp64 RED per touched node and channel.
 #include "scatter.cuh"
+#include "dense3.cuh"
+#include <cstdlib>
 
 namespace hot {
 namespace {
@@ -206,7 +208,82 @@ __global__ void __launch_bounds__(G2P_THREADS, 4) k_g2p(const int* __restrict__ 
     if (half_fast) atomicOr(flags + 1, 1);
 }
 
+// PlasticityApplier<...>::applyPlasticity -> projectStrain on every particle's F (Lib/Ziran/Physics/PlasticityApplier.h:40-55):
+// model 1 VonMisesFixedCorotated::projectStrain (PlasticityApplier.cpp:94-131), model 2 SnowPlasticity::projectStrain (:16-50)
+__global__ void k_plasticity(long n, size_t ps, int model, double p0, double p1, double p2, double p3, double p4, double* __restrict__ F,
+    double* __restrict__ mu, double* __restrict__ lam, double* __restrict__ Jp)
+{
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    double Fm[9], U[9], V[9], sig[3];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) Fm[q] = F[q * ps + s];
+    svd3(Fm, U, sig, V);
+    double sn[3];
+    if (model == 1) {
+        const double m_ = mu[s], l_ = lam[s], yield_stress = p0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) sig[d] = fmax(1e-4, sig[d]);
+        const double J = sig[0] * sig[1] * sig[2];
+        double tau[3], tr = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            tau[d] = 2.0 * m_ * (sig[d] - 1.0) * sig[d] + l_ * (J - 1.0) * J;
+            tr += tau[d];
+        }
+        double sdev[3], n2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            sdev[d] = tau[d] - tr / 3.0;
+            n2 += sdev[d] * sdev[d];
+        }
+        const double s_norm = sqrt(n2), scaled_tauy = sqrt(2.0 / 3.0) * yield_stress; // sqrt(2 / (6 - dim))
+        if (s_norm - scaled_tauy <= 0.0) return;
+        const double alpha = scaled_tauy / s_norm;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double tau_new = alpha * sdev[d] + tr / 3.0;
+            const double b2m4ac = m_ * m_ - 2.0 * m_ * (l_ * (J - 1.0) * J - tau_new);
+            sn[d] = (m_ + sqrt(b2m4ac)) / (2.0 * m_);
+        }
+    }
+    else {
+        const double psi = p0, theta_c = p1, theta_s = p2, min_Jp = p3, max_Jp = p4;
+        double Fe_det = 1.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            sn[d] = fmax(fmin(sig[d], 1.0 + theta_s), 1.0 - theta_c);
+            Fe_det *= sn[d];
+        }
+        const double Jold = Jp[s];
+        double Jnew = Jold * det3(Fm) / Fe_det;
+        if (!(Jnew <= max_Jp)) Jnew = max_Jp;
+        if (!(Jnew >= min_Jp)) Jnew = min_Jp;
+        const double h = exp(psi * (Jold - Jnew));
+        mu[s] *= h;
+        lam[s] *= h;
+        Jp[s] = Jnew;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) F[(r + 3 * c) * ps + s] = U[r] * sn[0] * V[c] + U[r + 3] * sn[1] * V[c + 3] + U[r + 6] * sn[2] * V[c + 6];
+}
+
 } // namespace
+
+int apply_plasticity(Sim* s)
+{
+    if (s->plastic_model == 0) return 0;
+    const long np = s->p1 > s->p0 ? s->p1 - s->p0 : 0, o = s->p0;
+    if (np <= 0) return 0;
+    KTime t(s, KC_STRESS);
+    const double* q = s->plastic_param;
+    k_plasticity<<<(unsigned)((np + 127) / 128), 128, 0, s->stream>>>(np, s->P.stride, s->plastic_model, q[0], q[1], q[2], q[3], q[4], s->P.F.p + o,
+        s->P.mu.p + o, s->P.lam.p + o, s->P.Jp.p + o);
+    HOT_LAUNCHED(s);
+    return 0;
+}
 
 int p2g(Sim* s)
 {
@@ -220,8 +297,14 @@ int p2g(Sim* s)
         KTime t(s, KC_P2G);
         P2GPolicy::Args a{s->P.stride, s->P.X.p, s->P.V.p, s->P.M.p, s->P.C.p, s->dx, 1.0 / s->dx, gn, s->g_m.p, s->g_v.p};
         if (s->g1 > s->g0) {
-            k_plane_scatter<P2GPolicy><<<(unsigned)(s->g1 - s->g0), SC_THREADS, 0, st>>>(a, s->cell_start.p + s->g0 * (Geo::E + 1),
-                s->group_slot.p + s->g0, s->nbr8.p);
+            static const int variant = getenv("HOT_P2G_VARIANT") ? atoi(getenv("HOT_P2G_VARIANT")) : 0;
+            const unsigned grid = (unsigned)(s->g1 - s->g0);
+            const int* cs = s->cell_start.p + s->g0 * (Geo::E + 1);
+            const int* gsl = s->group_slot.p + s->g0;
+            if (variant == 1) k_plane_scatter<P2GPolicy, 4, 2><<<grid, SC_THREADS, 0, st>>>(a, cs, gsl, s->nbr8.p);
+            else if (variant == 2) k_plane_scatter<P2GPolicy, 4, 1><<<grid, SC_THREADS, 0, st>>>(a, cs, gsl, s->nbr8.p);
+            else if (variant == 3) k_plane_scatter<P2GPolicy, 3, 2><<<grid, SC_THREADS, 0, st>>>(a, cs, gsl, s->nbr8.p);
+            else k_plane_scatter<P2GPolicy><<<grid, SC_THREADS, 0, st>>>(a, cs, gsl, s->nbr8.p);
             HOT_LAUNCHED(s);
         }
     }
@@ -256,6 +339,10 @@ int g2p(Sim* s, double dt, int* flags)
             s->P.V.p, s->P.C.p, s->P.F.p, s->P.gradV.p, s->dx, 1.0 / s->dx, dt, s->apic_rpic_ratio, s->cfl, s->g_stride, s->g_v.p,
             s->g_idx.p, s->dv.p, s->flags.p);
         HOT_LAUNCHED(s);
+    }
+    if (dt != 0.0) { // evolveStrain is followed by applyPlasticity (MpmSimulationBase.cpp:1039-1041)
+        int rc = apply_plasticity(s);
+        if (rc) return rc;
     }
     if (flags) {
         HOT_CUDA(cudaMemcpyAsync(s->hcount + 6, s->flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -428,3 +428,18 @@ class MpmSimulationB200:
         out = (C.c_long * 8)()
         self._check(self._lib.hot_get_partition(self._h, out))
         return dict(zip(("group0", "group1", "particle0", "particle1", "dof0", "dof1", "n_interface", "world"), [int(v) for v in out]))
+
+    # ---- plasticity (PlasticityApplier.cpp): applied by gridToParticles after evolveStrain
+    def set_plasticity(self, model, params=()):
+        m = {"none": 0, "von_mises": 1, "snow": 2}.get(model, model)
+        p = _f64(list(params) + [0.0] * (5 - len(params)), (5,))
+        self._check(self._lib.hot_set_plasticity(self._h, int(m), _ptr(p)))
+
+    def applyPlasticity(self):
+        self._check(self._lib.hot_apply_plasticity(self._h))
+
+    def get_plastic_state(self):
+        n = self.N
+        Jp = np.empty(n); mu = np.empty(n); lam = np.empty(n)
+        self._check(self._lib.hot_get_plastic_state(self._h, _ptr(Jp), _ptr(mu), _ptr(lam)))
+        return Jp, mu, lam

@@ -90,6 +90,15 @@ int hot_get_mass_matrix(hot_sim* h, double* mass);
 int hot_set_dv(hot_sim* h, const double* dv);
 int hot_g2p(hot_sim* h, double dt, int* flags /* [0] faster than dx, [1] faster than cfl*dx/2 */);
 
+/* ---- plasticity: MpmSimulationBase::applyPlasticity (Lib/MPM/MpmSimulationBase.cpp:1044-1064), run by hot_g2p right after
+ * evolveStrain like :1039-1041.  model 0 none; 1 VonMisesFixedCorotated::projectStrain (Lib/Ziran/Physics/PlasticityApplier.cpp:94-131),
+ * params = {yield_stress}; 2 SnowPlasticity::projectStrain (:16-50), params = {psi, theta_c, theta_s, min_Jp, max_Jp}
+ * (defaults 10, 2e-2, 7.5e-3, 0.6, 20: PlasticityApplier.h:61), hardening mu / lambda and Jp kept per particle on the device. */
+int hot_set_plasticity(hot_sim* h, int model, const double* params);
+int hot_apply_plasticity(hot_sim* h);
+int hot_get_plastic_state(hot_sim* h, double* Jp, double* mu, double* lambda);
+int hot_set_plastic_state(hot_sim* h, const double* Jp);
+
 /* ---- one object over the GPUs of a box (no counterpart in the reference, which is single-process: SURVEY 2a / 8e) ------
  * Every rank holds all particle positions and runs the same sort / page activation / DOF numbering (bit-identical on
  * every rank and to the single-GPU result).  Page groups are cut into `world` contiguous ranges balanced by particle count;

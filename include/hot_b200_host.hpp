@@ -327,6 +327,14 @@ public:
         faster_than_half_dx = flags[1] != 0;
     }
     bool faster_than_dx = false, faster_than_half_dx = false;
+    // PlasticityApplier (Lib/Ziran/Physics/PlasticityApplier.h): the return mapping hot_g2p runs after evolveStrain (:1039-1064)
+    void addVonMisesFixedCorotated(double yield_stress) { check(hot_set_plasticity(h, 1, &yield_stress)); }
+    void addSnowPlasticity(double psi = 10, double theta_c = 2e-2, double theta_s = 7.5e-3, double min_Jp = 0.6, double max_Jp = 20)
+    {
+        const double q[5] = {psi, theta_c, theta_s, min_Jp, max_Jp};
+        check(hot_set_plasticity(h, 2, q));
+    }
+    void applyPlasticity() { check(hot_apply_plasticity(h)); }
 
     // MultigridSimulation::startBackwardEuler (MultigridSimulation.h:167-186)
     void startBackwardEuler()

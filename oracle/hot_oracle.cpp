@@ -39,7 +39,9 @@ struct Sim {
 
     // particles, original order (AoS like Eigen StdVector<TV>/<TM>)
     int64_t N = 0;
-    std::vector<double> X, V, mass, C, F, vol, mu, lambda, gradV;
+    std::vector<double> X, V, mass, C, F, vol, mu, lambda, gradV, Jp;
+    int plastic_model = 0;
+    double plastic_param[5] = {0, 0, 0, 0, 0};
 
     // a5 outputs (MpmSimulationBase.h:98-112)
     std::vector<uint64_t> sorter;
@@ -204,6 +206,7 @@ int orc_set_particles(void* h, long n, const double* X, const double* V, const d
     s->mu.assign(mu, mu + n);
     s->lambda.assign(lambda, lambda + n);
     s->gradV.assign(9 * n, 0.0);
+    s->Jp.assign(n, 1.0);
     return 0;
 }
 int orc_get_particles(void* h, double* X, double* V, double* C, double* F, double* gradV)
@@ -444,6 +447,7 @@ static void construct_new_velocity(Sim* s)
     }
 }
 
+int orc_apply_plasticity(void* h);
 // a23: gridToParticlesHelper<true,false,false> (MpmSimulationBase.cpp:930-1006) preceded by
 // constructNewVelocityFromNewtonResult (:891-901) and followed by evolveStrain
 // (FBasedMpmForceHelper.cpp:100-114).  flags[0] = faster than a grid cell, flags[1] = faster than half.
@@ -499,6 +503,7 @@ int orc_g2p(void* h, double dt, int* flags)
         flags[0] = fast;
         flags[1] = half_fast;
     }
+    if (dt != 0.0) orc_apply_plasticity(h); // MpmSimulationBase.cpp:1039-1041
     return 0;
 }
 

@@ -535,6 +535,78 @@ int orc_eval_cn_tolerance(void* h, double eps, double dt, double* tol)
     return 0;
 }
 
+// MpmSimulationBase::applyPlasticity (MpmSimulationBase.cpp:1044-1064): VonMisesFixedCorotated::projectStrain
+// (PlasticityApplier.cpp:94-131) or SnowPlasticity::projectStrain (:16-50) on every particle's F
+int orc_set_plasticity(void* h, int model, const double* params)
+{
+    Sim* s = (Sim*)h;
+    s->plastic_model = model;
+    for (int k = 0; k < 5; ++k) s->plastic_param[k] = (model && params) ? params[k] : 0.0;
+    return 0;
+}
+int orc_apply_plasticity(void* h)
+{
+    Sim* s = (Sim*)h;
+    if (s->plastic_model == 0) return 0;
+    const double* q = s->plastic_param;
+#pragma omp parallel for
+    for (long i = 0; i < s->N; ++i) {
+        double* F = &s->F[9 * i];
+        double U[9], V[9], sig[3], sn[3];
+        svd3(F, U, sig, V);
+        if (s->plastic_model == 1) {
+            const double mu = s->mu[i], lambda = s->lambda[i];
+            for (int d = 0; d < 3; ++d) sig[d] = std::max(1e-4, sig[d]);
+            const double J = sig[0] * sig[1] * sig[2];
+            double tau[3], tr = 0;
+            for (int d = 0; d < 3; ++d) {
+                tau[d] = 2 * mu * (sig[d] - 1) * sig[d] + lambda * (J - 1) * J;
+                tr += tau[d];
+            }
+            double sd[3], n2 = 0;
+            for (int d = 0; d < 3; ++d) {
+                sd[d] = tau[d] - tr / 3;
+                n2 += sd[d] * sd[d];
+            }
+            const double s_norm = std::sqrt(n2), scaled_tauy = std::sqrt(2.0 / 3.0) * q[0];
+            if (s_norm - scaled_tauy <= 0) continue;
+            const double alpha = scaled_tauy / s_norm;
+            for (int d = 0; d < 3; ++d) {
+                const double tau_new = alpha * sd[d] + tr / 3;
+                const double b2m4ac = mu * mu - 2 * mu * (lambda * (J - 1) * J - tau_new);
+                sn[d] = (mu + std::sqrt(b2m4ac)) / (2 * mu);
+            }
+        }
+        else {
+            double Fe_det = 1;
+            for (int d = 0; d < 3; ++d) {
+                sn[d] = std::max(std::min(sig[d], 1 + q[2]), 1 - q[1]);
+                Fe_det *= sn[d];
+            }
+            double Jnew = s->Jp[i] * det3(F) / Fe_det;
+            if (!(Jnew <= q[4])) Jnew = q[4];
+            if (!(Jnew >= q[3])) Jnew = q[3];
+            const double hd = std::exp(q[0] * (s->Jp[i] - Jnew));
+            s->mu[i] *= hd;
+            s->lambda[i] *= hd;
+            s->Jp[i] = Jnew;
+        }
+        double Fe[9];
+        for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r) Fe[r + 3 * c] = U[r] * sn[0] * V[c] + U[r + 3] * sn[1] * V[c + 3] + U[r + 6] * sn[2] * V[c + 6];
+        std::copy(Fe, Fe + 9, F);
+    }
+    return 0;
+}
+int orc_get_plastic_state(void* h, double* Jp, double* mu, double* lambda)
+{
+    Sim* s = (Sim*)h;
+    if (Jp) std::copy(s->Jp.begin(), s->Jp.end(), Jp);
+    if (mu) std::copy(s->mu.begin(), s->mu.end(), mu);
+    if (lambda) std::copy(s->lambda.begin(), s->lambda.end(), lambda);
+    return 0;
+}
+
 // single-particle constitutive evaluation for unit tests against numpy
 int orc_constitutive(const double* F, double mu, double lambda, int project, double* psi, double* P, double* dPdF81,
     const double* dF, double* dP, double* U, double* sigma, double* V)

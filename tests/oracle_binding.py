@@ -222,6 +222,19 @@ def _add_force_methods(cls):
         self._check(_lib.orc_hessian_apply_mf(_vp(self._h), _p(x), _p(b)))
         return b
 
+    def set_plasticity(self, model, params=()):
+        m = {"none": 0, "von_mises": 1, "snow": 2}.get(model, model)
+        p = np.ascontiguousarray(list(params) + [0.0] * (5 - len(params)), dtype=np.float64)
+        self._check(_lib.orc_set_plasticity(_vp(self._h), int(m), _p(p)))
+
+    def applyPlasticity(self):
+        self._check(_lib.orc_apply_plasticity(_vp(self._h)))
+
+    def get_plastic_state(self):
+        Jp = np.empty(self.N); mu = np.empty(self.N); lam = np.empty(self.N)
+        self._check(_lib.orc_get_plastic_state(_vp(self._h), _p(Jp), _p(mu), _p(lam)))
+        return Jp, mu, lam
+
     def evaluatePerNodeCNTolerance(self, eps, dt):
         tol = np.empty(self.num_nodes)
         self._check(_lib.orc_eval_cn_tolerance(_vp(self._h), C.c_double(eps), C.c_double(dt), _p(tol)))
