@@ -21,6 +21,7 @@
 #include "scatter.cuh"
 #include "dense3.cuh"
 #include "reduce.cuh"
+#include <cstdlib>
 
 namespace hot {
 namespace {
@@ -63,36 +64,53 @@ __device__ __forceinline__ constexpr int tri(int i, int j) { return i <= j ? j *
 
 // ---- a9 + a10 + a11: ImplicitSolverObjective::updateState -------------------------------------------------------
 constexpr int US_THREADS = 128;
+static_assert(TILE <= 2 * US_THREADS && TILE >= US_THREADS, "tile staged in two rounds");
 
-__global__ void __launch_bounds__(US_THREADS) k_update_state(const int* __restrict__ group_first, const int* __restrict__ group_slot,
-    const int* __restrict__ nbr8, size_t ps, const double* __restrict__ X, const double* __restrict__ Fn, double* __restrict__ F,
-    const double* __restrict__ vol, const double* __restrict__ mu, const double* __restrict__ lam, double* __restrict__ stress,
-    double* __restrict__ Uo, double* __restrict__ Vo, double* __restrict__ sigo, double* __restrict__ gradV, double dx, double one_over_dx,
-    double dt, size_t gs, const double* __restrict__ g_v, const int* __restrict__ g_idx, const double* __restrict__ dv,
-    double* __restrict__ group_psi)
+__global__ void __launch_bounds__(US_THREADS) k_update_state(const int* __restrict__ group_first, const int* __restrict__ tile_dof, size_t ps,
+    const double* __restrict__ X, const double* __restrict__ Fn, double* __restrict__ F, const double* __restrict__ vol,
+    const double* __restrict__ mu, const double* __restrict__ lam, double* __restrict__ stress, double* __restrict__ Uo, double* __restrict__ Vo,
+    double* __restrict__ sigo, double* __restrict__ gradV, double dx, double one_over_dx, double dt, const double* __restrict__ vn,
+    const double* __restrict__ dv, double* __restrict__ group_psi, int pf_dist)
 {
     __shared__ double tile[3 * TILE];
-    __shared__ int s_nbr[8];
     __shared__ double s_res[1];
     const int g = blockIdx.x, tid = threadIdx.x;
+    const int id0 = tile_dof[(size_t)g * TILE + tid];
+    const int id1 = tid + US_THREADS < TILE ? tile_dof[(size_t)g * TILE + tid + US_THREADS] : -1;
     const int first = group_first[g], end = group_first[g + 1];
-    if (tid < 8) s_nbr[tid] = nbr8[(size_t)group_slot[g] * 8 + tid];
-    __syncthreads();
+    int pf_first = 0, pf_end = 0;
+    if (pf_dist > 0 && g + pf_dist < (int)gridDim.x) {
+        pf_first = group_first[g + pf_dist];
+        pf_end = group_first[g + pf_dist + 1];
+    }
+    // the first particle's rows are requested before the tile gather
+    if (first + tid < end) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) prefetch_l2(X + d * ps + first + tid);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) prefetch_l2(Fn + q * ps + first + tid);
+    }
     // moveNodes + the field of computeVAndGradV: v_i = vn_i + dv_i  (MpmSimulationBase.cpp:735-747)
-    for (int n = tid; n < TILE; n += US_THREADS) {
-        long a = tile_to_grid(n, s_nbr);
-        double nv[3] = {0, 0, 0};
-        if (a >= 0) {
-            int id = g_idx[a];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int n = tid + u * US_THREADS, id = u ? id1 : id0;
+        if (n < TILE) {
+            double nv[3] = {0, 0, 0};
             if (id >= 0)
 #pragma unroll
-                for (int d = 0; d < 3; ++d) nv[d] = g_v[d * gs + a] + dv[3 * (size_t)id + d];
+                for (int d = 0; d < 3; ++d) nv[d] = vn[3 * (size_t)id + d] + dv[3 * (size_t)id + d];
+            tile[n] = nv[0]; tile[TILE + n] = nv[1]; tile[2 * TILE + n] = nv[2];
         }
-        tile[n] = nv[0]; tile[TILE + n] = nv[1]; tile[2 * TILE + n] = nv[2];
     }
     __syncthreads();
     double e[1] = {0.0};
     for (int s = first + tid; s < end; s += US_THREADS) {
+        if (s + US_THREADS < end) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) prefetch_l2(X + d * ps + s + US_THREADS);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) prefetch_l2(Fn + q * ps + s + US_THREADS);
+        }
         SplineEval sp;
         sp.eval(X, ps, s, dx, one_over_dx, true);
         double G[9], A[9], Fo[9], Fnew[9];
@@ -129,6 +147,8 @@ __global__ void __launch_bounds__(US_THREADS) k_update_state(const int* __restri
 #pragma unroll
         for (int d = 0; d < 3; ++d) sigo[d * ps + s] = sig[d];
     }
+    prefetch_rows_l2(X, ps, 3, pf_first, pf_end, tid, US_THREADS);
+    prefetch_rows_l2(Fn, ps, 9, pf_first, pf_end, tid, US_THREADS);
     block_sum<1>(e, s_res);
     if (tid == 0) group_psi[g] = s_res[0];
 }
@@ -193,26 +213,36 @@ __global__ void __launch_bounds__(128) k_build_hessian(long n, size_t ps, const 
 
 // a13, first half: T_p = dt^2 * H~_p : grad x_p for every particle of a page group (CTA per group like k_update_state: the
 // group's x node tile is staged once, one thread per particle).  The scatter half reuses the force rasterisation kernel.
-__global__ void __launch_bounds__(US_THREADS) k_hessian_gather(const int* __restrict__ group_first, const int* __restrict__ group_slot,
-    const int* __restrict__ nbr8, size_t ps, const double* __restrict__ X, const double* __restrict__ H, double dx, double one_over_dx,
-    double scale, const int* __restrict__ g_idx, const double* __restrict__ x, double* __restrict__ Tout)
+__global__ void __launch_bounds__(US_THREADS, 6) k_hessian_gather(const int* __restrict__ group_first, const int* __restrict__ tile_dof, size_t ps,
+    const double* __restrict__ X, const double* __restrict__ H, double dx, double one_over_dx, double scale, const double* __restrict__ x,
+    double* __restrict__ Tout, int pf_dist)
 {
     __shared__ double tile[3 * TILE];
-    __shared__ int s_nbr[8];
     const int g = blockIdx.x, tid = threadIdx.x;
+    const int id0 = tile_dof[(size_t)g * TILE + tid];
+    const int id1 = tid + US_THREADS < TILE ? tile_dof[(size_t)g * TILE + tid + US_THREADS] : -1;
     const int first = group_first[g], end = group_first[g + 1];
-    if (tid < 8) s_nbr[tid] = nbr8[(size_t)group_slot[g] * 8 + tid];
-    __syncthreads();
-    for (int n = tid; n < TILE; n += US_THREADS) {
-        long a = tile_to_grid(n, s_nbr);
-        double nv[3] = {0, 0, 0};
-        if (a >= 0) {
-            int id = g_idx[a];
+    int pf_first = 0, pf_end = 0;
+    if (pf_dist > 0 && g + pf_dist < (int)gridDim.x) {
+        pf_first = group_first[g + pf_dist];
+        pf_end = group_first[g + pf_dist + 1];
+    }
+    // (an L2 prefetch of the particle's 45 H~ rows ahead of the staging was measured: it RAISED the DRAM reads from 381 MB
+    //  to 539 MB per launch - prefetched lines were evicted before use - so only the position rows are requested early)
+    if (first + tid < end) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) prefetch_l2(X + d * ps + first + tid);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int n = tid + u * US_THREADS, id = u ? id1 : id0;
+        if (n < TILE) {
+            double nv[3] = {0, 0, 0};
             if (id >= 0)
 #pragma unroll
                 for (int d = 0; d < 3; ++d) nv[d] = x[3 * (size_t)id + d];
+            tile[n] = nv[0]; tile[TILE + n] = nv[1]; tile[2 * TILE + n] = nv[2];
         }
-        tile[n] = nv[0]; tile[TILE + n] = nv[1]; tile[2 * TILE + n] = nv[2];
     }
     __syncthreads();
     for (int s = first + tid; s < end; s += US_THREADS) {
@@ -233,6 +263,9 @@ __global__ void __launch_bounds__(US_THREADS) k_hessian_gather(const int* __rest
 #pragma unroll
         for (int q = 0; q < 9; ++q) Tout[q * ps + s] = scale * T[q];
     }
+    // long distance (the group that takes over this CTA's slot): 48 rows = ~100 KB per group, 6 CTAs per SM x distance in L2
+    prefetch_rows_l2(X, ps, 3, pf_first, pf_end, tid, US_THREADS);
+    prefetch_rows_l2(H, ps, 45, pf_first, pf_end, tid, US_THREADS);
 }
 
 // ---- scatters -------------------------------------------------------------------------------------------------------
@@ -246,6 +279,35 @@ struct TGradScatter {
         for (int d = 0; d < 3; ++d) r[d * SC_PAD] = X[d * ps + s];
 #pragma unroll
         for (int q = 0; q < 9; ++q) r[(3 + q) * SC_PAD] = T[q];
+    }
+    // column form (k_column_scatter).  Prepared record: w[3][3], dw[3][3] / dx, T(9)
+    static constexpr int REC = 27;
+    __device__ __forceinline__ static void prep(const double* X, size_t ps, size_t s, double dx, double one_over_dx, const double (&T)[9], double* __restrict__ r)
+    {
+        double Xp[3], d0n[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) Xp[d] = X[d * ps + s];
+        prep_weights<true>(Xp, dx, one_over_dx, r, d0n);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) r[(18 + q) * CS_PAD] = T[q];
+    }
+    // node (i, j, k): T grad w,  grad w = (gx_i wy_j wz_k, wx_i gy_j wz_k, wx_i wy_j gz_k)
+    __device__ __forceinline__ static void accumulate_col(const double* __restrict__ rec, int i, int j, double (&acc)[3][3])
+    {
+        const double wx = rec[i * CS_PAD], wy = rec[(3 + j) * CS_PAD], gx = rec[(9 + i) * CS_PAD], gy = rec[(12 + j) * CS_PAD];
+        const double c0 = gx * wy, c1 = wx * gy, c2 = wx * wy;
+        double ab[3], cc[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            ab[r] = fma(rec[(21 + r) * CS_PAD], c1, rec[(18 + r) * CS_PAD] * c0);
+            cc[r] = rec[(24 + r) * CS_PAD] * c2;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double wz = rec[(6 + k) * CS_PAD], gz = rec[(15 + k) * CS_PAD];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) acc[k][r] = fma(cc[r], gz, fma(ab[r], wz, acc[k][r]));
+        }
     }
     __device__ __forceinline__ static void accumulate(const double* rec, double dx, double one_over_dx, int pl, double (&acc)[9][3])
     {
@@ -302,6 +364,25 @@ struct ForcePolicy {
 #pragma unroll
         for (int d = 0; d < 3; ++d) atomicAdd(a.out + 3 * (size_t)id + d, v[d]);
     }
+    static constexpr int REC = TGradScatter::REC;
+    __device__ __forceinline__ static void prep(const Args& a, size_t s, double* __restrict__ r)
+    {
+        double T[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) T[q] = -a.scale * a.stress[q * a.ps + s];
+        TGradScatter::prep(a.X, a.ps, s, a.dx, a.one_over_dx, T, r);
+    }
+    __device__ __forceinline__ static void accumulate_col(const double* __restrict__ rec, int i, int j, double, double, double (&acc)[3][3])
+    {
+        TGradScatter::accumulate_col(rec, i, j, acc);
+    }
+    static constexpr bool DOF = true;
+    __device__ __forceinline__ static void prefetch(const Args& a, int first, int end, int tid, int nt)
+    {
+        prefetch_rows_l2(a.X, a.ps, 3, first, end, tid, nt);
+        prefetch_rows_l2(a.stress, a.ps, 9, first, end, tid, nt);
+    }
+    __device__ __forceinline__ static void flush1(const Args& a, long id, int ch, double v) { atomicAdd(a.out + 3 * (size_t)id + ch, v); }
 };
 
 // a18: nodeCNTol_i += w_ip m_p ||dPdF(F = I)||_F   (ImplicitSolver.h:667-696, FBasedMpmForceHelper.h:123-157)
@@ -347,6 +428,33 @@ struct CNTolPolicy {
         const int id = a.g_idx[n];
         if (id >= 0) atomicAdd(a.out + id, v[0]);
     }
+    // column form: w[3][3], m_p ||dPdF(I)||_F
+    static constexpr int REC = 10;
+    __device__ __forceinline__ static void prep(const Args& a, size_t s, double* __restrict__ r)
+    {
+        const double one[3] = {1.0, 1.0, 1.0};
+        HessBlocks hb;
+        corotated_blocks(one, a.mu[s], a.lam[s], a.project != 0, hb);
+        double n2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) n2 += hb.A[q] * hb.A[q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) n2 += hb.B01[q] * hb.B01[q] + hb.B12[q] * hb.B12[q] + hb.B20[q] * hb.B20[q];
+        double Xp[3], d0n[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) Xp[d] = a.X[d * a.ps + s];
+        prep_weights<false>(Xp, a.dx, a.one_over_dx, r, d0n);
+        r[9 * CS_PAD] = a.M[s] * sqrt(n2);
+    }
+    __device__ __forceinline__ static void accumulate_col(const double* __restrict__ rec, int i, int j, double, double, double (&acc)[3][1])
+    {
+        const double v = rec[9 * CS_PAD] * (rec[i * CS_PAD] * rec[(3 + j) * CS_PAD]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[k][0] = fma(v, rec[(6 + k) * CS_PAD], acc[k][0]);
+    }
+    static constexpr bool DOF = true;
+    __device__ __forceinline__ static void prefetch(const Args&, int, int, int, int) {} // once per step: not worth it
+    __device__ __forceinline__ static void flush1(const Args& a, long id, int, double v) { atomicAdd(a.out + id, v); }
 };
 
 // r = dt m g - m dv   (the gravity and inertia terms of computeResidual, ImplicitSolver.h:133-145, Inertia.cpp:33-41)
@@ -514,9 +622,9 @@ int update_state(Sim* s, bool want_energy, double* energy)
     {
         KTime t(s, KC_STRESS);
         if (s->g1 > s->g0)
-        k_update_state<<<(unsigned)(s->g1 - s->g0), US_THREADS, 0, st>>>(s->group_first.p + s->g0, s->group_slot.p + s->g0, s->nbr8.p, ps, s->P.X.p, s->P.Fn.p,
-            s->P.F.p, s->P.vol.p, s->P.mu.p, s->P.lam.p, s->f_stress.p, s->f_U.p, s->f_V.p, s->f_sig.p, s->P.gradV.p, s->dx, 1.0 / s->dx,
-            s->dt, s->g_stride, s->g_v.p, s->g_idx.p, s->dv.p, s->group_psi.p);
+        k_update_state<<<(unsigned)(s->g1 - s->g0), US_THREADS, 0, st>>>(s->group_first.p + s->g0, s->tile_dof.p + (size_t)s->g0 * TILE, ps, s->P.X.p,
+            s->P.Fn.p, s->P.F.p, s->P.vol.p, s->P.mu.p, s->P.lam.p, s->f_stress.p, s->f_U.p, s->f_V.p, s->f_sig.p, s->P.gradV.p, s->dx, 1.0 / s->dx,
+            s->dt, s->vn.p, s->dv.p, s->group_psi.p, pf_distance(s, 4));
         HOT_LAUNCHED(s);
     }
     s->state_valid = true;
@@ -557,9 +665,16 @@ int scatter_to_dofs(Sim* s, typename Policy::Args a, double* Policy::Args::*targ
     }
     a.*target = dst;
     if (s->g1 > s->g0) {
-        k_plane_scatter<Policy><<<(unsigned)(s->g1 - s->g0), SC_THREADS, 0, st>>>(a, s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0,
-            s->nbr8.p);
-        HOT_LAUNCHED(s);
+        static const bool plane = getenv("HOT_SCATTER_PLANE") != nullptr; // A/B switch: the previous (cell, x-plane) skeleton
+        if (plane) {
+            k_plane_scatter<Policy><<<(unsigned)(s->g1 - s->g0), SC_THREADS, 0, st>>>(a, s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0,
+                s->nbr8.p);
+            HOT_LAUNCHED(s);
+        }
+        else {
+            int rc = launch_column_scatter<Policy>(s, a);
+            if (rc) return rc;
+        }
     }
     if (s->world > 1) {
         int rc = dist_exchange_iface(s, dst, comps);
@@ -622,8 +737,8 @@ static int hessian_scatter(Sim* s, double scale, const double* x, double* out)
     const size_t ps = s->P.stride;
     HOT_CUDA(s->f_T.reserve(9 * ps));
     if (s->g1 > s->g0) {
-        k_hessian_gather<<<(unsigned)(s->g1 - s->g0), US_THREADS, 0, s->stream>>>(s->group_first.p + s->g0, s->group_slot.p + s->g0, s->nbr8.p, ps,
-            s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, scale, s->g_idx.p, x, s->f_T.p);
+        k_hessian_gather<<<(unsigned)(s->g1 - s->g0), US_THREADS, 0, s->stream>>>(s->group_first.p + s->g0, s->tile_dof.p + (size_t)s->g0 * TILE, ps,
+            s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, scale, x, s->f_T.p, pf_distance(s, 3));
         HOT_LAUNCHED(s);
     }
     ForcePolicy::Args a{ps, s->P.X.p, s->f_T.p, s->dx, 1.0 / s->dx, -1.0, s->g_idx.p, out};

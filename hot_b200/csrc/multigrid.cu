@@ -775,9 +775,9 @@ int coarsen(Sim* s, MGLevel& F, MGLevel& C)
     cudaStream_t st = s->stream;
     const int nf = F.n;
     const long nc8 = (long)nf * 8;
-    DevBuf<uint64_t> ckey, ckey_sorted;
-    DevBuf<int> cpos, cpos_sorted, heads_pos, order;
-    DevBuf<uint64_t> heads_key;
+    // persistent scratch (a cudaMalloc / cudaFree pair per buffer and level used to dominate the hierarchy build)
+    DevBuf<uint64_t>&ckey = s->mg_ckey, &ckey_sorted = s->mg_ckey_sorted, &heads_key = s->mg_heads_key;
+    DevBuf<int>&cpos = s->mg_cpos, &cpos_sorted = s->mg_cpos_sorted, &heads_pos = s->mg_heads_pos, &order = s->mg_order;
     HOT_CUDA(ckey.reserve(nc8));
     HOT_CUDA(ckey_sorted.reserve(nc8));
     HOT_CUDA(cpos.reserve(nc8));
@@ -838,7 +838,6 @@ int coarsen(Sim* s, MGLevel& F, MGLevel& C)
     HOT_CUDA(C.val.reserve((size_t)nc * 9 * W));
     k_galerkin<<<nc, W, 0, st>>>(nc, C.coord.p, C.key_sorted.p, C.id_sorted.p, F.rcol.p, F.rw.p, F.val.p, C.col.p, C.val.p);
     HOT_LAUNCHED(s);
-    HOT_CUDA(cudaStreamSynchronize(st)); // the local scratch buffers are freed on return
     return 0;
 }
 

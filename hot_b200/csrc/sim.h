@@ -176,11 +176,15 @@ struct Sim {
     size_t g_stride = 0;
     int num_nodes = 0;
     DevBuf<int> dof_slot; // inverse of g_idx
+    DevBuf<int> tile_dof; // n_groups x Geo::TILE: DOF id of every node of a page group's (B+2)^3 tile (sort.cu: k_tile_dof)
     bool p2g_done = false;
 
     // ---- DOF vectors
     DevBuf<double> dv, vn, mass_matrix;
 
+    int pf_dist = -1; // L2 prefetch distance of the per-group kernels in CTAs (-1: default = one wave of resident CTAs; 0: off; HOT_PF_DIST)
+    DevBuf<short> cs_table; // combine table of the column scatter (scatter.cuh)
+    bool cs_table_ready = false;
     DevBuf<int> flags; // g2p CFL flags
     // plasticity applied after G2P + evolveStrain (MpmSimulationBase.cpp:1039-1064): 0 none, 1 VonMisesFixedCorotated, 2 SnowPlasticity
     int plastic_model = 0;
@@ -206,6 +210,8 @@ struct Sim {
     // ---- assembled system + multigrid hierarchy (matrix.cu, multigrid.cu)
     std::vector<MGLevel*> levels; // levels[0] = assembled matrix
     bool matrix_built = false, mg_built = false, matrix_bcproject = true;
+    DevBuf<uint64_t> mg_ckey, mg_ckey_sorted, mg_heads_key; // coarsening scratch (multigrid.cu: coarsen)
+    DevBuf<int> mg_cpos, mg_cpos_sorted, mg_heads_pos, mg_order;
     DevBuf<int> bc_of; // node -> BC table row or -1
     DevBuf<double> diag_mf; // 9n: inverse diagonal blocks of the matrix-free operator (buildDiagonal)
     // HOTSettings (Projects/multigrid/Configurations.h:18-42)
@@ -353,6 +359,20 @@ __host__ __device__ inline uint64_t packed_add(uint64_t a, uint64_t b)
     uint64_t rz = ((a | ~Geo::zmask) + (b & Geo::zmask)) & Geo::zmask;
     uint64_t rw = ((a | ~w) + (b & w)) & w;
     return rx | ry | rz | rw;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// L2 prefetch of the sorted-particle run [first, end) of `nrows` consecutive SoA rows (row stride ps), one 128-byte line per
+// thread and trip.  Used at long distance: a CTA requests the rows of the CTA that will occupy its slot next, so that the
+// DRAM round trip of a work item's compulsory loads is paid while an earlier work item computes.
+__device__ __forceinline__ void prefetch_rows_l2(const double* base, size_t ps, int nrows, int first, int end, int tid, int nthreads)
+{
+    if (end <= first) return;
+    const int nl = ((end - first) * 8 + 127) / 128 + 1; // + 1: the run is not line-aligned
+    for (int t = tid; t < nrows * nl; t += nthreads) {
+        const int r = t / nl, l = t - r * nl;
+        const char* p = (const char*)(base + (size_t)r * ps + first) + (size_t)l * 128;
+        if (p < (const char*)(base + (size_t)r * ps + end)) prefetch_l2(p);
+    }
 }
 // MathTools.h:15-25 + BSplines.h:16-20.  The product X*one_over_dx and the -0.5 are evaluated unfused
 // (IEEE round-to-nearest each) so that particle->cell indices are bit-exact against the CPU evaluation.

@@ -213,28 +213,90 @@ __global__ void k_cell_start(long n_groups, const int* __restrict__ group_first,
     cell_start[t] = lo;
 }
 
-__global__ void k_mass_flags(long n, const double* __restrict__ m, int* __restrict__ flag)
+// node carries mass (flag) -> one 32-bit mask per page (a page is one warp: Geo::E == 32 nodes); the last CTA to finish turns
+// the per-page counts into exclusive offsets in page-list order and leaves the node count in *total
+constexpr int NM_WARPS = 8;
+constexpr int NM_ITEMS = 8;
+static_assert(Geo::E == 32, "one warp per page");
+__global__ void __launch_bounds__(32 * NM_WARPS) k_page_masks(int n_pages, const double* __restrict__ m, const int* __restrict__ flag,
+    unsigned* __restrict__ mask, int* __restrict__ base, int* __restrict__ done, int* __restrict__ total, volatile int* total_host)
 {
-    long a = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a < n) flag[a] = m[a] != 0.0;
+    const int page = blockIdx.x * NM_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (page < n_pages) {
+        const size_t a = (size_t)page * Geo::E + lane;
+        const unsigned b = __ballot_sync(0xffffffffu, flag ? flag[a] != 0 : m[a] != 0.0);
+        if (lane == 0) {
+            mask[page] = b;
+            base[page] = __popc(b);
+        }
+    }
+    __shared__ int s_last;
+    __shared__ int s_part[32 * NM_WARPS];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // exclusive scan of base[0..n_pages) by this CTA: super-tiles of T x NM_ITEMS counts, all loads of a super-tile in flight
+    // together (coalesced), one warp-shuffle block scan per row of T
+    constexpr int T = 32 * NM_WARPS;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    __shared__ int s_carry;
+    if (tid == 0) s_carry = 0;
+    for (int t0 = 0; t0 < n_pages; t0 += T * NM_ITEMS) {
+        int c[NM_ITEMS];
+#pragma unroll
+        for (int it = 0; it < NM_ITEMS; ++it) {
+            const int p = t0 + it * T + tid;
+            c[it] = p < n_pages ? ((volatile int*)base)[p] : 0;
+        }
+#pragma unroll
+        for (int it = 0; it < NM_ITEMS; ++it) {
+            int incl = c[it];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            __syncthreads(); // s_part / s_carry of the previous row consumed
+            if (lane == 31) s_part[warp] = incl;
+            __syncthreads();
+            int off = s_carry;
+            for (int w = 0; w < warp; ++w) off += s_part[w];
+            const int p = t0 + it * T + tid;
+            if (p < n_pages) base[p] = off + incl - c[it];
+            __syncthreads();
+            if (tid == T - 1) s_carry = off + incl;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        *total = s_carry;
+        *total_host = s_carry; // mapped pinned word the host spins on (no D2H copy, no stream synchronize on the step path)
+        __threadfence_system();
+    }
 }
 
 // MpmGrid.h:148-161 (idx), MpmSimulationBase.cpp:523-531 (v /= m), :817-826 (mass_matrix)
-// (flag = node carries mass; in a partitioned run a rank numbers nodes whose mass only other ranks hold: m == 0 there)
-__global__ void k_number_and_normalise(long n, size_t gs, const int* __restrict__ scan, const int* __restrict__ flag, double* __restrict__ m,
-    double* __restrict__ v, int* __restrict__ idx, int* __restrict__ dof_slot, double* __restrict__ mass_matrix, double* __restrict__ vn)
+// (mask bit = node carries mass; in a partitioned run a rank numbers nodes whose mass only other ranks hold: m == 0 there)
+__global__ void __launch_bounds__(32 * NM_WARPS) k_number_and_normalise(int n_pages, size_t gs, const unsigned* __restrict__ mask,
+    const int* __restrict__ base, double* __restrict__ m, double* __restrict__ v, int* __restrict__ idx, int* __restrict__ dof_slot,
+    double* __restrict__ mass_matrix, double* __restrict__ vn)
 {
-    long a = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n) return;
-    double mm = m[a];
-    if (flag[a]) {
-        int id = scan[a];
+    const int page = blockIdx.x * NM_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (page >= n_pages) return;
+    const size_t a = (size_t)page * Geo::E + lane;
+    const unsigned b = mask[page];
+    if (b >> lane & 1u) {
+        const int id = base[page] + __popc(b & ((1u << lane) - 1u));
+        const double mm = m[a];
         idx[a] = id;
         dof_slot[id] = (int)a;
         mass_matrix[id] = mm;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            double q = mm != 0.0 ? v[d * gs + a] / mm : 0.0;
+            const double q = mm != 0.0 ? v[d * gs + a] / mm : 0.0;
             v[d * gs + a] = q;
             vn[3 * (size_t)id + d] = q;
         }
@@ -242,6 +304,24 @@ __global__ void k_number_and_normalise(long n, size_t gs, const int* __restrict_
     else {
         idx[a] = -1;
     }
+}
+
+// tile_dof[g][n]: DOF id of node n of the (B+2)^3 tile of page group g, -1 where the node carries no mass / its page is absent.
+// Built once per step; the per-group gather kernels (G2P, updateState, Hessian gather) and the scatter flushes read it with one
+// coalesced load instead of the dependent chain group_slot -> nbr8 -> g_idx.
+__global__ void __launch_bounds__(160) k_tile_dof(const int* __restrict__ group_slot, const int* __restrict__ nbr8, const int* __restrict__ g_idx,
+    int* __restrict__ tile_dof)
+{
+    __shared__ int s_nbr[8];
+    const int g = blockIdx.x, n = threadIdx.x;
+    if (n < 8) s_nbr[n] = nbr8[(size_t)group_slot[g] * 8 + n];
+    __syncthreads();
+    if (n >= Geo::TILE) return;
+    const int tz = n % Geo::TZ, ty = (n / Geo::TZ) % Geo::TY, tx = n / (Geo::TZ * Geo::TY);
+    const int q = ((tx >= Geo::BX) << 2) | ((ty >= Geo::BY) << 1) | (tz >= Geo::BZ);
+    const int e = (((tx & (Geo::BX - 1)) << Geo::yb | (ty & (Geo::BY - 1))) << Geo::zb) | (tz & (Geo::BZ - 1));
+    const int slot = s_nbr[q];
+    tile_dof[(size_t)g * Geo::TILE + n] = slot < 0 ? -1 : g_idx[(size_t)slot * Geo::E + e];
 }
 
 template <class F>
@@ -273,7 +353,7 @@ int sort_and_activate(Sim* s)
     HOT_CUDA(s->perm_alt.reserve(n));
     HOT_CUDA(s->head_flag.reserve(n > 64 ? n : 64));
     HOT_CUDA(s->group_first.reserve(n + 1));
-    HOT_CUDA(s->dcount.reserve(8));
+    HOT_CUDA(s->dcount.reserve(16));
     HOT_CUDA(s->Palt.reserve(n));
     if (!s->hcount) HOT_CUDA(cudaMallocHost((void**)&s->hcount, 32 * sizeof(int)));
 
@@ -376,27 +456,41 @@ int number_nodes(Sim* s, bool flags_ready)
 {
     cudaStream_t st = s->stream;
     const size_t gn = s->g_stride;
+    const int NP = (int)s->n_pages;
     HOT_CUDA(s->head_flag.reserve(gn));
-    HOT_CUDA(s->scratch_i.reserve(gn));
+    HOT_CUDA(s->scratch_i.reserve(2 * (size_t)NP + 2));
     HOT_CUDA(s->mass_matrix.reserve(gn));
     HOT_CUDA(s->vn.reserve(3 * gn));
     HOT_CUDA(s->dv.reserve(3 * gn));
-    if (!flags_ready) {
-        k_mass_flags<<<nblk(gn), TPB, 0, st>>>(gn, s->g_m.p, s->head_flag.p);
-        HOT_LAUNCHED(s);
-    }
-    int rc = with_tmp(s, [&](void* t, size_t& b) {
-        return cub::DeviceScan::ExclusiveSum(t, b, s->head_flag.p, s->scratch_i.p, (int)gn, st);
-    });
-    if (rc) return rc;
-    k_number_and_normalise<<<nblk(gn), TPB, 0, st>>>(gn, gn, s->scratch_i.p, s->head_flag.p, s->g_m.p, s->g_v.p, s->g_idx.p, s->dof_slot.p,
+    // two launches: per-page node masks with the exclusive scan over the pages done by the last CTA to finish, then numbering
+    // + normalisation (the serial running count of MpmGrid.h:148-161 over pages in list order x in-page element order)
+    unsigned* mask = (unsigned*)s->scratch_i.p;
+    int* base = s->scratch_i.p + NP;
+    HOT_CUDA(cudaMemsetAsync(s->dcount.p + 12, 0, sizeof(int), st));
+    volatile int* hn = s->hcount + 4; // pinned + mapped (UVA): written by the last CTA of k_page_masks
+    *hn = -1;
+    k_page_masks<<<(NP + NM_WARPS - 1) / NM_WARPS, 32 * NM_WARPS, 0, st>>>(NP, s->g_m.p, flags_ready ? s->head_flag.p : nullptr, mask, base,
+        s->dcount.p + 12, s->dcount.p + 13, hn);
+    HOT_LAUNCHED(s);
+    k_number_and_normalise<<<(NP + NM_WARPS - 1) / NM_WARPS, 32 * NM_WARPS, 0, st>>>(NP, gn, mask, base, s->g_m.p, s->g_v.p, s->g_idx.p, s->dof_slot.p,
         s->mass_matrix.p, s->vn.p);
     HOT_LAUNCHED(s);
-    // n_nodes = scan[last] + flag[last]
-    HOT_CUDA(cudaMemcpyAsync(s->hcount + 4, s->scratch_i.p + (gn - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-    HOT_CUDA(cudaMemcpyAsync(s->hcount + 5, s->head_flag.p + (gn - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-    HOT_CUDA(cudaStreamSynchronize(st));
-    s->num_nodes = s->hcount[4] + s->hcount[5];
+    HOT_CUDA(s->tile_dof.reserve((size_t)s->n_groups * Geo::TILE));
+    if (s->n_groups > 0) {
+        k_tile_dof<<<(unsigned)s->n_groups, 160, 0, st>>>(s->group_slot.p, s->nbr8.p, s->g_idx.p, s->tile_dof.p);
+        HOT_LAUNCHED(s);
+    }
+    // the node count arrives while k_number_and_normalise is still running: the host goes on enqueueing without a stream sync
+    for (long spin = 0; *hn < 0; ++spin) {
+        if ((spin & 0xfff) == 0xfff) {
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q != cudaErrorNotReady) {
+                if (q != cudaSuccess) return cuda_fail(s, q, "number_nodes");
+                if (*hn < 0) return fail(s, "number_nodes: the node count never arrived");
+            }
+        }
+    }
+    s->num_nodes = *hn;
     HOT_CUDA(cudaMemsetAsync(s->dv.p, 0, 3 * (size_t)s->num_nodes * sizeof(double), st));
     return 0;
 }

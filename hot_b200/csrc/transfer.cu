@@ -91,32 +91,108 @@ struct P2GPolicy {
         atomicAdd(a.g_v + a.gs + n, v[2]);
         atomicAdd(a.g_v + 2 * a.gs + n, v[3]);
     }
+
+    // ---- column form (scatter.cuh, k_column_scatter).  Prepared record: w[3][3], m, A(3) = m v + m C (x_node0 - x_p),
+    // Gx(3), Gy(3), Gz(3) = dx * m C(:, d): the node value of stencil node (i, j, k) is A + i Gx + j Gy + k Gz.
+    static constexpr int REC = 22;
+    static constexpr bool DOF = false;
+    __device__ __forceinline__ static void prefetch(const Args& a, int first, int end, int tid, int nt)
+    {
+        prefetch_rows_l2(a.X, a.ps, 3, first, end, tid, nt);
+        prefetch_rows_l2(a.V, a.ps, 3, first, end, tid, nt);
+        prefetch_rows_l2(a.M, a.ps, 1, first, end, tid, nt);
+        prefetch_rows_l2(a.C, a.ps, 9, first, end, tid, nt);
+    }
+    __device__ __forceinline__ static void prep(const Args& a, size_t s, double* __restrict__ r)
+    {
+        const double m = a.M[s];
+        double Xp[3], v[3], Cm[9], d0n[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            Xp[d] = a.X[d * a.ps + s];
+            v[d] = a.V[d * a.ps + s];
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) Cm[q] = m * a.C[q * a.ps + s];
+        prep_weights<false>(Xp, a.dx, a.one_over_dx, r, d0n);
+        r[9 * CS_PAD] = m;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            r[(10 + c) * CS_PAD] = m * v[c] + (Cm[c] * d0n[0] + Cm[c + 3] * d0n[1] + Cm[c + 6] * d0n[2]);
+            r[(13 + c) * CS_PAD] = a.dx * Cm[c];
+            r[(16 + c) * CS_PAD] = a.dx * Cm[c + 3];
+            r[(19 + c) * CS_PAD] = a.dx * Cm[c + 6];
+        }
+    }
+    __device__ __forceinline__ static void accumulate_col(const double* __restrict__ rec, int i, int j, double di, double dj, double (&acc)[3][4])
+    {
+        const double wij = rec[i * CS_PAD] * rec[(3 + j) * CS_PAD];
+        const double m = rec[9 * CS_PAD];
+        double b[3], gz[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            b[c] = fma(dj, rec[(16 + c) * CS_PAD], fma(di, rec[(13 + c) * CS_PAD], rec[(10 + c) * CS_PAD]));
+            gz[c] = rec[(19 + c) * CS_PAD];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double w = wij * rec[(6 + k) * CS_PAD];
+            acc[k][0] = fma(w, m, acc[k][0]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double val = k == 0 ? b[c] : (k == 1 ? b[c] + gz[c] : fma(2.0, gz[c], b[c]));
+                acc[k][1 + c] = fma(w, val, acc[k][1 + c]);
+            }
+        }
+    }
+    __device__ __forceinline__ static void flush1(const Args& a, long n, int ch, double v)
+    {
+        atomicAdd(ch == 0 ? a.g_m + n : a.g_v + (size_t)(ch - 1) * a.gs + n, v);
+    }
 };
 
 constexpr int G2P_THREADS = 128;
+static_assert(TILE <= 2 * G2P_THREADS && TILE >= G2P_THREADS, "tile staged in two rounds");
 
-__global__ void __launch_bounds__(G2P_THREADS, 4) k_g2p(const int* __restrict__ group_first, const int* __restrict__ group_slot,
-    const int* __restrict__ nbr8, size_t ps, double* __restrict__ X, double* __restrict__ V, double* __restrict__ C,
-    double* __restrict__ F, double* __restrict__ gradV, double dx, double one_over_dx, double dt, double apic_rpic_ratio, double cfl,
-    size_t gs, const double* __restrict__ g_v, const int* __restrict__ g_idx, const double* __restrict__ dv, int* __restrict__ flags)
+__global__ void __launch_bounds__(G2P_THREADS, 4) k_g2p(const int* __restrict__ group_first, const int* __restrict__ tile_dof, size_t ps,
+    double* __restrict__ X, double* __restrict__ V, double* __restrict__ C, double* __restrict__ F, double* __restrict__ gradV, double dx,
+    double one_over_dx, double dt, double apic_rpic_ratio, double cfl, const double* __restrict__ vn, const double* __restrict__ dv,
+    int* __restrict__ flags, int pf_dist)
 {
     __shared__ double tile[3][TILE];
-    __shared__ int s_nbr[8];
     const int g = blockIdx.x, tid = threadIdx.x;
+    // dependent DRAM round trips of a CTA: {group_first, tile_dof} -> {vn + dv gather, X} -> F (L2-prefetched); the tile's DOF ids
+    // come from the per-step table instead of the chain group_slot -> nbr8 -> g_idx
+    const int id0 = tile_dof[(size_t)g * TILE + tid];
+    const int id1 = tid + G2P_THREADS < TILE ? tile_dof[(size_t)g * TILE + tid + G2P_THREADS] : -1;
     const int first = group_first[g], end = group_first[g + 1];
-    if (tid < 8) s_nbr[tid] = nbr8[(size_t)group_slot[g] * 8 + tid];
-    __syncthreads();
-    // new_v = v + dv on the touched tile (constructNewVelocityFromNewtonResult fused into the staging)
-    for (int n = tid; n < TILE; n += G2P_THREADS) {
-        long a = tile_to_grid(n, s_nbr);
-        double nv[3] = {0, 0, 0};
-        if (a >= 0) {
-            int id = g_idx[a];
-            if (id >= 0)
+    // the group that takes over this CTA's slot: its rows are requested from L2 at the end (bounds requested now)
+    int pf_first = 0, pf_end = 0;
+    if (pf_dist > 0 && g + pf_dist < (int)gridDim.x) {
+        pf_first = group_first[g + pf_dist];
+        pf_end = group_first[g + pf_dist + 1];
+    }
+    double X0[3] = {0.0, 0.0, 0.0};
+    if (first + tid < end) {
 #pragma unroll
-                for (int d = 0; d < 3; ++d) nv[d] = g_v[d * gs + a] + dv[3 * (size_t)id + d];
+        for (int d = 0; d < 3; ++d) X0[d] = X[d * ps + first + tid];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) prefetch_l2(F + q * ps + first + tid);
+    }
+    // new_v = v + dv on the touched tile (constructNewVelocityFromNewtonResult fused into the staging; vn = the normalised v)
+    {
+        double nv[3] = {0, 0, 0};
+        if (id0 >= 0)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) nv[d] = vn[3 * (size_t)id0 + d] + dv[3 * (size_t)id0 + d];
+        tile[0][tid] = nv[0]; tile[1][tid] = nv[1]; tile[2][tid] = nv[2];
+        if (tid + G2P_THREADS < TILE) {
+            double nw[3] = {0, 0, 0};
+            if (id1 >= 0)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) nw[d] = vn[3 * (size_t)id1 + d] + dv[3 * (size_t)id1 + d];
+            tile[0][tid + G2P_THREADS] = nw[0]; tile[1][tid + G2P_THREADS] = nw[1]; tile[2][tid + G2P_THREADS] = nw[2];
         }
-        tile[0][n] = nv[0]; tile[1][n] = nv[1]; tile[2][n] = nv[2];
     }
     __syncthreads();
     const double D_inverse = 4.0 / (dx * dx); // MpmSimulationBase.cpp:114-118
@@ -125,9 +201,17 @@ __global__ void __launch_bounds__(G2P_THREADS, 4) k_g2p(const int* __restrict__ 
     for (int s = first + tid; s < end; s += G2P_THREADS) {
         double Xp[3], w[3][3], gw[3][3], xm[3][3]; // weights, weight derivatives / dx, x_node - x_p per axis and stencil index
         int tb[3];
+        // software pipeline: the next particle's position load and F prefetch are in flight during this particle's contraction
+        double Xn[3] = {0.0, 0.0, 0.0};
+        if (s + G2P_THREADS < end) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) Xn[d] = X[d * ps + s + G2P_THREADS];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) prefetch_l2(F + q * ps + s + G2P_THREADS);
+        }
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            Xp[d] = X[d * ps + s];
+            Xp[d] = X0[d];
             double xi, dw[3];
             int b = base_node_of(Xp[d], one_over_dx, &xi);
             bspline_axis(xi - (double)b, w[d], dw);
@@ -203,7 +287,12 @@ __global__ void __launch_bounds__(G2P_THREADS, 4) k_g2p(const int* __restrict__ 
                 C[(r + 3 * cc) * ps + s] = ca * B[r + 3 * cc] + cb * B[cc + 3 * r];
                 F[(r + 3 * cc) * ps + s] = A[r] * Fo[3 * cc] + A[r + 3] * Fo[3 * cc + 1] + A[r + 6] * Fo[3 * cc + 2];
             }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) X0[d] = Xn[d];
     }
+    prefetch_rows_l2(X, ps, 3, pf_first, pf_end, tid, G2P_THREADS);
+    prefetch_rows_l2(F, ps, 9, pf_first, pf_end, tid, G2P_THREADS);
+    if (pf_end > pf_first && tid < 5) prefetch_l2(tile_dof + (size_t)(g + pf_dist) * TILE + tid * 32);
     if (fast) atomicOr(flags, 1);
     if (half_fast) atomicOr(flags + 1, 1);
 }
@@ -297,15 +386,18 @@ int p2g(Sim* s)
         KTime t(s, KC_P2G);
         P2GPolicy::Args a{s->P.stride, s->P.X.p, s->P.V.p, s->P.M.p, s->P.C.p, s->dx, 1.0 / s->dx, gn, s->g_m.p, s->g_v.p};
         if (s->g1 > s->g0) {
-            static const int variant = getenv("HOT_P2G_VARIANT") ? atoi(getenv("HOT_P2G_VARIANT")) : 0;
+            static const int variant = getenv("HOT_SCATTER_PLANE") ? 1 : 0; // A/B switch: the previous (cell, x-plane) skeleton
             const unsigned grid = (unsigned)(s->g1 - s->g0);
             const int* cs = s->cell_start.p + s->g0 * (Geo::E + 1);
             const int* gsl = s->group_slot.p + s->g0;
-            if (variant == 1) k_plane_scatter<P2GPolicy, 4, 2><<<grid, SC_THREADS, 0, st>>>(a, cs, gsl, s->nbr8.p);
-            else if (variant == 2) k_plane_scatter<P2GPolicy, 4, 1><<<grid, SC_THREADS, 0, st>>>(a, cs, gsl, s->nbr8.p);
-            else if (variant == 3) k_plane_scatter<P2GPolicy, 3, 2><<<grid, SC_THREADS, 0, st>>>(a, cs, gsl, s->nbr8.p);
-            else k_plane_scatter<P2GPolicy><<<grid, SC_THREADS, 0, st>>>(a, cs, gsl, s->nbr8.p);
-            HOT_LAUNCHED(s);
+            if (variant == 1) {
+                k_plane_scatter<P2GPolicy><<<grid, SC_THREADS, 0, st>>>(a, cs, gsl, s->nbr8.p);
+                HOT_LAUNCHED(s);
+            }
+            else {
+                int rc = launch_column_scatter<P2GPolicy>(s, a);
+                if (rc) return rc;
+            }
         }
     }
     int rc;
@@ -335,9 +427,9 @@ int g2p(Sim* s, double dt, int* flags)
     {
         KTime t(s, KC_G2P);
         if (s->g1 > s->g0)
-        k_g2p<<<(unsigned)(s->g1 - s->g0), G2P_THREADS, 0, st>>>(s->group_first.p + s->g0, s->group_slot.p + s->g0, s->nbr8.p, s->P.stride, s->P.X.p,
-            s->P.V.p, s->P.C.p, s->P.F.p, s->P.gradV.p, s->dx, 1.0 / s->dx, dt, s->apic_rpic_ratio, s->cfl, s->g_stride, s->g_v.p,
-            s->g_idx.p, s->dv.p, s->flags.p);
+        k_g2p<<<(unsigned)(s->g1 - s->g0), G2P_THREADS, 0, st>>>(s->group_first.p + s->g0, s->tile_dof.p + (size_t)s->g0 * TILE, s->P.stride, s->P.X.p,
+            s->P.V.p, s->P.C.p, s->P.F.p, s->P.gradV.p, s->dx, 1.0 / s->dx, dt, s->apic_rpic_ratio, s->cfl, s->vn.p, s->dv.p, s->flags.p,
+            pf_distance(s, 4));
         HOT_LAUNCHED(s);
     }
     if (dt != 0.0) { // evolveStrain is followed by applyPlasticity (MpmSimulationBase.cpp:1039-1041)

@@ -56,4 +56,4 @@ def test_apply_plasticity_standalone_and_errors(hot, oracle):
         g.set_plasticity("von_mises", [-1.0])
     for s in (g, o):
         s.set_plasticity("von_mises", [100.0]); s.applyPlasticity()   # before any sort: original order
-    np.testing.assert_allclose(g.get_particles()["F"], o.get_particles()["F"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(g.get_particles(gradV=False)["F"], o.get_particles()["F"], rtol=0, atol=1e-11)   # no G2P yet: gradV undefined
