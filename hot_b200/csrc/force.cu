@@ -17,7 +17,8 @@
 //    firstPiolaDifferential: once per linearisation each particle's Hessian is contracted with Fn on both sides into the
 //    symmetric 9x9 map  H~ : grad x_p -> vol * dP(grad x_p Fn) Fn^T  (45 doubles), so an apply is
 //    gather(27) -> 81 FMA -> scatter(27) and the same H~ feeds the matrix assembly (a15).
-//  * scatters use the shared k_plane_scatter skeleton (scatter.cuh): no colour passes, no atomics in the particle loop.
+//  * scatters use the shared prep / accumulate / gather-combine skeletons of scatter.cuh: no colour passes, no atomics in
+//    the particle loop.
 #include "scatter.cuh"
 #include "dense3.cuh"
 #include "reduce.cuh"
@@ -213,23 +214,43 @@ __global__ void __launch_bounds__(128) k_build_hessian(long n, size_t ps, const 
 
 // a13, first half: T_p = dt^2 * H~_p : grad x_p for every particle of a page group (CTA per group like k_update_state: the
 // group's x node tile is staged once, one thread per particle).  The scatter half reuses the force rasterisation kernel.
-__global__ void __launch_bounds__(US_THREADS, 6) k_hessian_gather(const int* __restrict__ group_first, const int* __restrict__ tile_dof, size_t ps,
-    const double* __restrict__ X, const double* __restrict__ H, double dx, double one_over_dx, double scale, const double* __restrict__ x,
-    double* __restrict__ Tout, int pf_dist)
+// TMA = true: the X and H~ rows of the group (48 runs, 360 + 24 bytes per particle: the HBM stream of the whole matrix-free
+// apply) are staged in shared memory by bulk copies issued by one thread, HG_CAP particles per chunk.
+constexpr int HG_CAP = US_THREADS;
+constexpr size_t HG_SMEM = (size_t)48 * (HG_CAP + 2) * sizeof(double);
+template <bool TMA>
+__global__ void __launch_bounds__(US_THREADS, TMA ? 4 : 6) k_hessian_gather(const int* __restrict__ group_first, const int* __restrict__ tile_dof,
+    size_t ps, const double* __restrict__ X, const double* __restrict__ H, double dx, double one_over_dx, double scale,
+    const double* __restrict__ x, double* __restrict__ Tout, int pf_dist)
 {
     __shared__ double tile[3 * TILE];
+    __shared__ __align__(8) unsigned long long s_bar;
+    extern __shared__ __align__(16) double hg_rows[]; // [48][HG_CAP + 2]
     const int g = blockIdx.x, tid = threadIdx.x;
+    if (TMA && tid == 0) mbar_init(&s_bar, 1);
     const int id0 = tile_dof[(size_t)g * TILE + tid];
     const int id1 = tid + US_THREADS < TILE ? tile_dof[(size_t)g * TILE + tid + US_THREADS] : -1;
     const int first = group_first[g], end = group_first[g + 1];
     int pf_first = 0, pf_end = 0;
-    if (pf_dist > 0 && g + pf_dist < (int)gridDim.x) {
+    if (!TMA && pf_dist > 0 && g + pf_dist < (int)gridDim.x) {
         pf_first = group_first[g + pf_dist];
         pf_end = group_first[g + pf_dist + 1];
     }
-    // (an L2 prefetch of the particle's 45 H~ rows ahead of the staging was measured: it RAISED the DRAM reads from 381 MB
-    //  to 539 MB per launch - prefetched lines were evicted before use - so only the position rows are requested early)
-    if (first + tid < end) {
+    auto issue_chunk = [&](int c0) {
+        const int cn = min(HG_CAP, end - c0), start = c0 & ~1, cnt = (c0 + cn - start + 1) & ~1;
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar, 48u * cnt * 8u);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) bulk_load(hg_rows + d * (HG_CAP + 2), X + d * ps + start, cnt * 8u, &s_bar);
+        for (int q = 0; q < 45; ++q) bulk_load(hg_rows + (3 + q) * (HG_CAP + 2), H + q * ps + start, cnt * 8u, &s_bar);
+    };
+    if (TMA) {
+        __syncthreads(); // barrier initialised
+        if (tid == 0 && first < end) issue_chunk(first);
+    }
+    else if (first + tid < end) {
+        // (an L2 prefetch of the particle's 45 H~ rows ahead of the staging was measured: it RAISED the DRAM reads from 381 MB
+        //  to 539 MB per launch - prefetched lines were evicted before use - so only the position rows are requested early)
 #pragma unroll
         for (int d = 0; d < 3; ++d) prefetch_l2(X + d * ps + first + tid);
     }
@@ -245,23 +266,39 @@ __global__ void __launch_bounds__(US_THREADS, 6) k_hessian_gather(const int* __r
         }
     }
     __syncthreads();
-    for (int s = first + tid; s < end; s += US_THREADS) {
-        SplineEval sp;
-        sp.eval(X, ps, s, dx, one_over_dx, true);
-        double G[9], T[9];
-        gather_gradient(tile, sp, one_over_dx, G);
-#pragma unroll
-        for (int q = 0; q < 9; ++q) T[q] = 0.0;
-#pragma unroll
-        for (int j = 0; j < 9; ++j)
-#pragma unroll
-            for (int i = 0; i <= j; ++i) {
-                const double h = H[(size_t)tri(i, j) * ps + s];
-                T[i] += h * G[j];
-                if (i != j) T[j] += h * G[i];
+    unsigned phase = 0;
+    for (int c0 = first; c0 < end; c0 += TMA ? HG_CAP : end - first) {
+        const int c1 = TMA ? min(c0 + HG_CAP, end) : end, start = c0 & ~1;
+        if (TMA) {
+            if (c0 != first) {
+                __syncthreads(); // every thread is done with the previous chunk's rows
+                if (tid == 0) issue_chunk(c0);
             }
+            mbar_wait(&s_bar, phase);
+            phase ^= 1;
+        }
+        for (int s = c0 + tid; s < c1; s += US_THREADS) {
+            SplineEval sp;
+            if (TMA) {
+                const double Xp[3] = {hg_rows[s - start], hg_rows[(HG_CAP + 2) + s - start], hg_rows[2 * (HG_CAP + 2) + s - start]};
+                sp.eval3(Xp, dx, one_over_dx, true);
+            }
+            else sp.eval(X, ps, s, dx, one_over_dx, true);
+            double G[9], T[9];
+            gather_gradient(tile, sp, one_over_dx, G);
 #pragma unroll
-        for (int q = 0; q < 9; ++q) Tout[q * ps + s] = scale * T[q];
+            for (int q = 0; q < 9; ++q) T[q] = 0.0;
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+#pragma unroll
+                for (int i = 0; i <= j; ++i) {
+                    const double h = TMA ? hg_rows[(3 + tri(i, j)) * (HG_CAP + 2) + s - start] : H[(size_t)tri(i, j) * ps + s];
+                    T[i] += h * G[j];
+                    if (i != j) T[j] += h * G[i];
+                }
+#pragma unroll
+            for (int q = 0; q < 9; ++q) Tout[q * ps + s] = scale * T[q];
+        }
     }
     // long distance (the group that takes over this CTA's slot): 48 rows = ~100 KB per group, 6 CTAs per SM x distance in L2
     prefetch_rows_l2(X, ps, 3, pf_first, pf_end, tid, US_THREADS);
@@ -272,72 +309,78 @@ __global__ void __launch_bounds__(US_THREADS, 6) k_hessian_gather(const int* __r
 // Common record of the two vector scatters (a12 force, a13 Hessian apply): node value = T grad w with a per-particle 3x3 T.
 //   record: X(3)  T(9, column-major)
 struct TGradScatter {
-    static constexpr int NCH = 3, RAW = 12;
-    __device__ __forceinline__ static void fill(const double* X, size_t ps, size_t s, const double* T, double* r)
-    {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) r[d * SC_PAD] = X[d * ps + s];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) r[(3 + q) * SC_PAD] = T[q];
-    }
-    // column form (k_column_scatter).  Prepared record: w[3][3], dw[3][3] / dx, T(9)
-    static constexpr int REC = 27;
+    static constexpr int NCH = 3;
+    // column form (k_column_scatter).  Prepared record (30 doubles, 16-byte words):
+    //   [0..5] (wx_t, gx_t) t = 0..2 | [6..11] (wy_t, gy_t) | [12..14] wz [15..17] gz | [18..26] T (column-major) | pad;  g = dw / dx
+    static constexpr int REC = 30;
     __device__ __forceinline__ static void prep(const double* X, size_t ps, size_t s, double dx, double one_over_dx, const double (&T)[9], double* __restrict__ r)
     {
-        double Xp[3], d0n[3];
+        double Xp[3], d0n[3], w[3][3], g[3][3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) Xp[d] = X[d * ps + s];
-        prep_weights<true>(Xp, dx, one_over_dx, r, d0n);
+        prep_weights<true>(Xp, dx, one_over_dx, w, g, d0n);
 #pragma unroll
-        for (int q = 0; q < 9; ++q) r[(18 + q) * CS_PAD] = T[q];
+        for (int t = 0; t < 3; ++t) {
+            sts2(r + 2 * t, w[0][t], g[0][t]);
+            sts2(r + 6 + 2 * t, w[1][t], g[1][t]);
+        }
+        sts2(r + 12, w[2][0], w[2][1]); sts2(r + 14, w[2][2], g[2][0]); sts2(r + 16, g[2][1], g[2][2]);
+        sts2(r + 18, T[0], T[1]); sts2(r + 20, T[2], T[3]); sts2(r + 22, T[4], T[5]); sts2(r + 24, T[6], T[7]); sts2(r + 26, T[8], 0.0);
     }
     // node (i, j, k): T grad w,  grad w = (gx_i wy_j wz_k, wx_i gy_j wz_k, wx_i wy_j gz_k)
     __device__ __forceinline__ static void accumulate_col(const double* __restrict__ rec, int i, int j, double (&acc)[3][3])
     {
-        const double wx = rec[i * CS_PAD], wy = rec[(3 + j) * CS_PAD], gx = rec[(9 + i) * CS_PAD], gy = rec[(12 + j) * CS_PAD];
+        double wx, gx, wy, gy, wz[3], gz[3], T[10];
+        lds2(rec + 2 * i, wx, gx); lds2(rec + 6 + 2 * j, wy, gy);
+        lds2(rec + 12, wz[0], wz[1]); lds2(rec + 14, wz[2], gz[0]); lds2(rec + 16, gz[1], gz[2]);
+        lds2(rec + 18, T[0], T[1]); lds2(rec + 20, T[2], T[3]); lds2(rec + 22, T[4], T[5]); lds2(rec + 24, T[6], T[7]); lds2(rec + 26, T[8], T[9]);
         const double c0 = gx * wy, c1 = wx * gy, c2 = wx * wy;
         double ab[3], cc[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            ab[r] = fma(rec[(21 + r) * CS_PAD], c1, rec[(18 + r) * CS_PAD] * c0);
-            cc[r] = rec[(24 + r) * CS_PAD] * c2;
+            ab[r] = fma(T[3 + r], c1, T[r] * c0);
+            cc[r] = T[6 + r] * c2;
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const double wz = rec[(6 + k) * CS_PAD], gz = rec[(15 + k) * CS_PAD];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) acc[k][r] = fma(cc[r], gz, fma(ab[r], wz, acc[k][r]));
+            for (int r = 0; r < 3; ++r) acc[k][r] = fma(cc[r], gz[k], fma(ab[r], wz[k], acc[k][r]));
         }
     }
-    __device__ __forceinline__ static void accumulate(const double* rec, double dx, double one_over_dx, int pl, double (&acc)[9][3])
+    // plane form: the 9 nodes (j, k) of x-plane i
+    __device__ __forceinline__ static void accumulate_plane(const double* __restrict__ rec, int i, double (&acc)[9][3])
     {
-        SplineEval sp;
-        sp.eval_rec(rec, dx, one_over_dx, true);
-        const double wx = pl == 0 ? sp.w[0][0] : (pl == 1 ? sp.w[0][1] : sp.w[0][2]);
-        const double dwx = one_over_dx * (pl == 0 ? sp.dw[0][0] : (pl == 1 ? sp.dw[0][1] : sp.dw[0][2]));
-        double ax[3], ay[3], az[3], gy[3], gz[3];
+        double wx, gx, wy[3], gy[3], wz[3], gz[3], T[10];
+        lds2(rec + 2 * i, wx, gx);
+        lds2(rec + 6, wy[0], gy[0]); lds2(rec + 8, wy[1], gy[1]); lds2(rec + 10, wy[2], gy[2]);
+        lds2(rec + 12, wz[0], wz[1]); lds2(rec + 14, wz[2], gz[0]); lds2(rec + 16, gz[1], gz[2]);
+        lds2(rec + 18, T[0], T[1]); lds2(rec + 20, T[2], T[3]); lds2(rec + 22, T[4], T[5]); lds2(rec + 24, T[6], T[7]); lds2(rec + 26, T[8], T[9]);
+        double tx[3], ty[3], tz[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            ax[r] = rec[(3 + r) * SC_PAD] * dwx;
-            ay[r] = rec[(6 + r) * SC_PAD] * wx;
-            az[r] = rec[(9 + r) * SC_PAD] * wx;
-            gy[r] = one_over_dx * sp.dw[1][r];
-            gz[r] = one_over_dx * sp.dw[2][r];
+            tx[r] = T[r] * gx; // column 0 x d/dx part
+            ty[r] = T[3 + r] * wx;
+            tz[r] = T[6 + r] * wx;
         }
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
+        for (int j = 0; j < 3; ++j) {
+            double ab[3], cc[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const double c0 = sp.w[1][j] * sp.w[2][k], c1 = gy[j] * sp.w[2][k], c2 = sp.w[1][j] * gz[k];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) acc[j * 3 + k][r] += ax[r] * c0 + ay[r] * c1 + az[r] * c2;
+            for (int r = 0; r < 3; ++r) {
+                ab[r] = fma(ty[r], gy[j], tx[r] * wy[j]);
+                cc[r] = tz[r] * wy[j];
             }
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) acc[j * 3 + k][r] = fma(cc[r], gz[k], fma(ab[r], wz[k], acc[j * 3 + k][r]));
+        }
     }
 };
 
 // a12: rasterizeForceToTVStack: f_i -= scale * (vol P Fn^T) grad w   (MpmForceBase.cpp:100-153)
 struct ForcePolicy {
-    static constexpr int NCH = 3, RAW = TGradScatter::RAW, GATHER = 0;
+    static constexpr int NCH = 3;
     struct Args {
         size_t ps;
         const double *X, *stress;
@@ -345,26 +388,8 @@ struct ForcePolicy {
         const int* g_idx;
         double* out; // DOF vector
     };
-    __device__ static void gather_node(const Args&, long, double (&)[3]) {}
-    __device__ static void stage(const Args& a, size_t s, double* r, const double*)
-    {
-        double T[9];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) T[q] = -a.scale * a.stress[q * a.ps + s];
-        TGradScatter::fill(a.X, a.ps, s, T, r);
-    }
-    __device__ __forceinline__ static void accumulate(const Args& a, const double* rec, int pl, double (&acc)[9][3])
-    {
-        TGradScatter::accumulate(rec, a.dx, a.one_over_dx, pl, acc);
-    }
-    __device__ static void flush(const Args& a, long n, const double (&v)[3])
-    {
-        const int id = a.g_idx[n];
-        if (id < 0) return;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) atomicAdd(a.out + 3 * (size_t)id + d, v[d]);
-    }
-    static constexpr int REC = TGradScatter::REC;
+    static constexpr int REC = TGradScatter::REC, MINB = 4; // 45 KB of records per CTA
+    static constexpr bool PLANE = false; // measured: column 0.107 ms, plane 0.137 ms (its 92 KB of records leave 2 CTAs per SM)
     __device__ __forceinline__ static void prep(const Args& a, size_t s, double* __restrict__ r)
     {
         double T[9];
@@ -375,6 +400,10 @@ struct ForcePolicy {
     __device__ __forceinline__ static void accumulate_col(const double* __restrict__ rec, int i, int j, double, double, double (&acc)[3][3])
     {
         TGradScatter::accumulate_col(rec, i, j, acc);
+    }
+    __device__ __forceinline__ static void accumulate_plane(const double* __restrict__ rec, int i, double, double (&acc)[9][3])
+    {
+        TGradScatter::accumulate_plane(rec, i, acc);
     }
     static constexpr bool DOF = true;
     __device__ __forceinline__ static void prefetch(const Args& a, int first, int end, int tid, int nt)
@@ -387,8 +416,7 @@ struct ForcePolicy {
 
 // a18: nodeCNTol_i += w_ip m_p ||dPdF(F = I)||_F   (ImplicitSolver.h:667-696, FBasedMpmForceHelper.h:123-157)
 struct CNTolPolicy {
-    // record: X(3)  m_p ||dPdF(I)||_F
-    static constexpr int NCH = 1, RAW = 4, GATHER = 0;
+    static constexpr int NCH = 1;
     struct Args {
         size_t ps;
         const double *X, *M, *mu, *lam;
@@ -397,39 +425,10 @@ struct CNTolPolicy {
         const int* g_idx;
         double* out; // per node
     };
-    __device__ static void gather_node(const Args&, long, double (&)[3]) {}
-    __device__ static void stage(const Args& a, size_t s, double* r, const double*)
-    {
-        // dPdF = Q blockdiag(A, B01, B12, B20) Q^T with Q orthogonal, so ||dPdF||_F^2 = sum of the block norms^2
-        const double one[3] = {1.0, 1.0, 1.0};
-        HessBlocks hb;
-        corotated_blocks(one, a.mu[s], a.lam[s], a.project != 0, hb);
-        double n2 = 0.0;
-#pragma unroll
-        for (int q = 0; q < 9; ++q) n2 += hb.A[q] * hb.A[q];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) n2 += hb.B01[q] * hb.B01[q] + hb.B12[q] * hb.B12[q] + hb.B20[q] * hb.B20[q];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) r[d * SC_PAD] = a.X[d * a.ps + s];
-        r[3 * SC_PAD] = a.M[s] * sqrt(n2);
-    }
-    __device__ __forceinline__ static void accumulate(const Args& a, const double* rec, int pl, double (&acc)[9][1])
-    {
-        SplineEval sp;
-        sp.eval_rec(rec, a.dx, a.one_over_dx, false);
-        const double v = rec[3 * SC_PAD] * (pl == 0 ? sp.w[0][0] : (pl == 1 ? sp.w[0][1] : sp.w[0][2]));
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) acc[j * 3 + k][0] += v * (sp.w[1][j] * sp.w[2][k]);
-    }
-    __device__ static void flush(const Args& a, long n, const double (&v)[1])
-    {
-        const int id = a.g_idx[n];
-        if (id >= 0) atomicAdd(a.out + id, v[0]);
-    }
-    // column form: w[3][3], m_p ||dPdF(I)||_F
-    static constexpr int REC = 10;
+    // dPdF = Q blockdiag(A, B01, B12, B20) Q^T with Q orthogonal, so ||dPdF||_F^2 = sum of the block norms^2
+    // column form: [0..8] w[3][3], [9] m_p ||dPdF(I)||_F
+    static constexpr int REC = 10, MINB = 4;
+    static constexpr bool PLANE = false;
     __device__ __forceinline__ static void prep(const Args& a, size_t s, double* __restrict__ r)
     {
         const double one[3] = {1.0, 1.0, 1.0};
@@ -440,17 +439,27 @@ struct CNTolPolicy {
         for (int q = 0; q < 9; ++q) n2 += hb.A[q] * hb.A[q];
 #pragma unroll
         for (int q = 0; q < 4; ++q) n2 += hb.B01[q] * hb.B01[q] + hb.B12[q] * hb.B12[q] + hb.B20[q] * hb.B20[q];
-        double Xp[3], d0n[3];
+        double Xp[3], d0n[3], w[3][3], g[3][3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) Xp[d] = a.X[d * a.ps + s];
-        prep_weights<false>(Xp, a.dx, a.one_over_dx, r, d0n);
-        r[9 * CS_PAD] = a.M[s] * sqrt(n2);
+        prep_weights<false>(Xp, a.dx, a.one_over_dx, w, g, d0n);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) r[q] = w[q / 3][q % 3];
+        r[9] = a.M[s] * sqrt(n2);
     }
     __device__ __forceinline__ static void accumulate_col(const double* __restrict__ rec, int i, int j, double, double, double (&acc)[3][1])
     {
-        const double v = rec[9 * CS_PAD] * (rec[i * CS_PAD] * rec[(3 + j) * CS_PAD]);
+        const double v = rec[9] * (rec[i] * rec[3 + j]);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) acc[k][0] = fma(v, rec[(6 + k) * CS_PAD], acc[k][0]);
+        for (int k = 0; k < 3; ++k) acc[k][0] = fma(v, rec[6 + k], acc[k][0]);
+    }
+    __device__ __forceinline__ static void accumulate_plane(const double* __restrict__ rec, int i, double, double (&acc)[9][1])
+    {
+        const double v = rec[9] * rec[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc[j * 3 + k][0] = fma(v, rec[3 + j] * rec[6 + k], acc[j * 3 + k][0]);
     }
     static constexpr bool DOF = true;
     __device__ __forceinline__ static void prefetch(const Args&, int, int, int, int) {} // once per step: not worth it
@@ -665,16 +674,8 @@ int scatter_to_dofs(Sim* s, typename Policy::Args a, double* Policy::Args::*targ
     }
     a.*target = dst;
     if (s->g1 > s->g0) {
-        static const bool plane = getenv("HOT_SCATTER_PLANE") != nullptr; // A/B switch: the previous (cell, x-plane) skeleton
-        if (plane) {
-            k_plane_scatter<Policy><<<(unsigned)(s->g1 - s->g0), SC_THREADS, 0, st>>>(a, s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0,
-                s->nbr8.p);
-            HOT_LAUNCHED(s);
-        }
-        else {
-            int rc = launch_column_scatter<Policy>(s, a);
-            if (rc) return rc;
-        }
+        int rc = launch_scatter<Policy>(s, a);
+        if (rc) return rc;
     }
     if (s->world > 1) {
         int rc = dist_exchange_iface(s, dst, comps);
@@ -737,8 +738,16 @@ static int hessian_scatter(Sim* s, double scale, const double* x, double* out)
     const size_t ps = s->P.stride;
     HOT_CUDA(s->f_T.reserve(9 * ps));
     if (s->g1 > s->g0) {
-        k_hessian_gather<<<(unsigned)(s->g1 - s->g0), US_THREADS, 0, s->stream>>>(s->group_first.p + s->g0, s->tile_dof.p + (size_t)s->g0 * TILE, ps,
-            s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, scale, x, s->f_T.p, pf_distance(s, 3));
+        static const bool tma = !(getenv("HOT_HG_TMA") && atoi(getenv("HOT_HG_TMA")) == 0); // A/B switch, default on
+        if (tma) {
+            static const cudaError_t attr = cudaFuncSetAttribute(k_hessian_gather<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HG_SMEM);
+            HOT_CUDA(attr);
+            k_hessian_gather<true><<<(unsigned)(s->g1 - s->g0), US_THREADS, HG_SMEM, s->stream>>>(s->group_first.p + s->g0,
+                s->tile_dof.p + (size_t)s->g0 * TILE, ps, s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, scale, x, s->f_T.p, 0);
+        }
+        else
+            k_hessian_gather<false><<<(unsigned)(s->g1 - s->g0), US_THREADS, 0, s->stream>>>(s->group_first.p + s->g0,
+                s->tile_dof.p + (size_t)s->g0 * TILE, ps, s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, scale, x, s->f_T.p, pf_distance(s, 3));
         HOT_LAUNCHED(s);
     }
     ForcePolicy::Args a{ps, s->P.X.p, s->f_T.p, s->dx, 1.0 / s->dx, -1.0, s->g_idx.p, out};

@@ -1,34 +1,24 @@
-// Shared skeleton of the particle->grid scatters of the hot path (a6 P2G, a12 force rasterisation, a13 matrix-free
-// Hessian apply, a18 CN tolerance): one CTA per page group, thread = (cell of the page, x-plane of the 3x3x3 stencil).
+// Particle->grid scatters of the hot path (a6 P2G, a12 force rasterisation, a13 matrix-free Hessian apply, a18 CN tolerance):
+// one CTA per (half) page group, no colour passes, no atomics in the particle loop.
 //
-// The reference serialises these scatters into 8 colour passes (MpmSimulationBase.h:251-264) and does a
-// read-modify-write of a 128-byte GridState per (particle, node).  Here (see transfer.cu for the roofline argument):
-//   stage      the particle's SoA attributes (coalesced loads of one contiguous run) are reduced to a small RAW record
-//              (position + the policy's per-particle payload, e.g. m, m v, m C for P2G or the 3x3 matrix T for the vector
-//              scatters) in shared memory, field-major and index-swizzled so that the strided reads below are conflict-free;
-//              up to SC_CHUNK = 3 x CTA-size particles per pass, so a typical page group (~8-12 particles per cell) is ONE
-//              pass and every (cell, plane) thread has work;
-//   accumulate thread (c, pl) walks the particles of cell c (adjacent thanks to the sort key), re-derives the B-spline
-//              weights from the position (cheaper than staging them: 12 extra doubles per particle would halve the chunk)
-//              and keeps the 9 nodes x NCH channels of x-plane pl in registers - no atomics, no shared-memory traffic but
-//              the record reads;
-//   combine    per-warp (B+2)^3 tiles in shared memory, 9 (j,k) steps; inside a step the lanes of a warp hit distinct nodes
-//              (a warp holds < 16 consecutive cells => distinct (cy,cz); the 3 planes of a cell are distinct x), so plain
-//              RMW + __syncwarp is race free;
-//   flush      warp tiles are summed and written with one fp64 RED per touched node and channel.
+// The reference serialises these scatters into 8 colour passes (MpmSimulationBase.h:251-264) and does a read-modify-write of
+// a 128-byte GridState per (particle, node).  Here the particles of a page group (one contiguous, coalesced run of every
+// sorted SoA row) go through three phases:
+//   prep       thread per particle: everything that does not depend on the stencil node (B-spline weights of the three axes
+//              in the reference's operation order, the policy's payload) is computed once and parked in shared memory as a
+//              particle-major record;
+//   accumulate thread per (cell, part of the 3x3x3 stencil) walks the particles of ITS cell - adjacent thanks to the sort key -
+//              and keeps its nodes x channels in registers;
+//   combine    every thread parks its sums, then thread (tile node) adds the contributions of its node in a fixed order read
+//              from a small index table and issues one fp64 RED per channel.
+// Two thread mappings share this structure: the COLUMN form (9 threads per cell, 3 nodes each; half-page CTAs) and the PLANE
+// form (3 threads per cell, 9 nodes each; cells handed to lanes by decreasing particle count).  Which one a policy uses is
+// a measured choice (Policy::PLANE), see DESIGN.md.
 #pragma once
 #include "sim.h"
 #include <cstdlib>
 
 namespace hot {
-
-constexpr int SC_THREADS = 3 * Geo::E; // 96 for the 2x4x4 fp64 page
-constexpr int SC_WARPS = SC_THREADS / 32;
-constexpr int SC_CHUNK = 3 * SC_THREADS; // particles staged per pass
-constexpr int SC_PAD = SC_CHUNK + SC_CHUNK / 8 + 2; // swizzled row length
-static_assert(SC_THREADS % 32 == 0, "whole warps");
-// neighbouring cells read records ~ppc apart: p + p/8 spreads them over the banks for the usual 4..16 particles per cell
-__device__ __forceinline__ int sc_swz(int p) { return p + (p >> 3); }
 
 // quadratic B-spline weights of one axis in the reference's operation order (BSplines.h:55-81)
 __device__ __forceinline__ void bspline_axis(double d0, double* w, double* dw)
@@ -63,100 +53,7 @@ __device__ __forceinline__ int tile_base(int bx, int by, int bz)
     return (((bx & (Geo::BX - 1)) * Geo::TY) + (by & (Geo::BY - 1))) * Geo::TZ + (bz & (Geo::BZ - 1));
 }
 
-// Policy interface:
-//   static constexpr int NCH, RAW (doubles per staged particle; fields 0..2 are the position), GATHER (0/1: stage needs a
-//                                  gathered DOF field tile)
-//   struct Args { ... }                              kernel arguments (trivially copyable)
-//   __device__ static void stage(const Args&, size_t s, double* rec /* field f at rec[f * SC_PAD] */, const double* gtile)
-//   __device__ static void accumulate(const Args&, const double* rec, int pl, double (&acc)[9][NCH])
-//   __device__ static void flush(const Args&, long a, const double (&v)[NCH])     a = grid array index
-//   __device__ static void gather_node(const Args&, long a, double (&v)[3])       (GATHER only)
-template <class Policy, int MINB = 5, int UNROLL = 1>
-__global__ void __launch_bounds__(SC_THREADS, MINB) k_plane_scatter(typename Policy::Args args, const int* __restrict__ cell_start,
-    const int* __restrict__ group_slot, const int* __restrict__ nbr8)
-{
-    constexpr int NCH = Policy::NCH, RAW = Policy::RAW, TILE = Geo::TILE, E = Geo::E;
-    constexpr int REC_DOUBLES = RAW * SC_PAD, TILE_DOUBLES = SC_WARPS * NCH * TILE;
-    // the warp tiles alias the record buffer: records are dead once the last chunk has been accumulated
-    __shared__ __align__(16) double smem[REC_DOUBLES > TILE_DOUBLES ? REC_DOUBLES : TILE_DOUBLES];
-    __shared__ double gtile[Policy::GATHER ? 3 * TILE : 1];
-    __shared__ int s_cs[E + 1];
-    __shared__ int s_nbr[8];
-
-    const int g = blockIdx.x, tid = threadIdx.x;
-    if (tid <= E) s_cs[tid] = cell_start[(size_t)g * (E + 1) + tid];
-    if (tid < 8) s_nbr[tid] = nbr8[(size_t)group_slot[g] * 8 + tid];
-    __syncthreads();
-    if (Policy::GATHER) {
-        for (int n = tid; n < TILE; n += SC_THREADS) {
-            double v[3] = {0.0, 0.0, 0.0};
-            long a = tile_to_grid(n, s_nbr);
-            if (a >= 0) Policy::gather_node(args, a, v);
-            gtile[n] = v[0]; gtile[TILE + n] = v[1]; gtile[2 * TILE + n] = v[2];
-        }
-    }
-    const int first = s_cs[0], end = s_cs[E];
-    const int c = tid / 3, pl = tid - 3 * c;
-    const int my_b = s_cs[c], my_e = s_cs[c + 1];
-    double acc[9][NCH];
-#pragma unroll
-    for (int a = 0; a < 9; ++a)
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) acc[a][ch] = 0.0;
-
-    for (int cb = first; cb < end; cb += SC_CHUNK) {
-        const int cn = min(SC_CHUNK, end - cb);
-        __syncthreads(); // previous chunk consumed (and gtile ready on the first pass)
-        for (int k = tid; k < cn; k += SC_THREADS) Policy::stage(args, (size_t)cb + k, smem + sc_swz(k), gtile);
-        __syncthreads();
-        const int pb = max(my_b, cb) - cb, pe = min(my_e, cb + cn) - cb;
-        int p = pb;
-        if (UNROLL == 2) { // two particles per trip: their weight evaluations are independent instruction streams (ILP)
-            for (; p + 1 < pe; p += 2) {
-                Policy::accumulate(args, smem + sc_swz(p), pl, acc);
-                Policy::accumulate(args, smem + sc_swz(p + 1), pl, acc);
-            }
-        }
-        for (; p < pe; ++p) Policy::accumulate(args, smem + sc_swz(p), pl, acc);
-    }
-    __syncthreads(); // records dead -> reuse as warp tiles
-    for (int a = tid; a < TILE_DOUBLES; a += SC_THREADS) smem[a] = 0.0;
-    __syncthreads();
-    {
-        const int cz = c & (Geo::BZ - 1), cy = (c >> Geo::zb) & (Geo::BY - 1), cx = c >> (Geo::zb + Geo::yb);
-        double* wt = smem + (size_t)(tid >> 5) * NCH * TILE;
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int n = ((cx + pl) * Geo::TY + (cy + j)) * Geo::TZ + (cz + k);
-                if (my_e > my_b) {
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch) wt[ch * TILE + n] += acc[j * 3 + k][ch];
-                }
-                __syncwarp();
-            }
-    }
-    __syncthreads();
-    for (int n = tid; n < TILE; n += SC_THREADS) {
-        double v[NCH];
-        bool any = false;
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-            double sum = 0.0;
-#pragma unroll
-            for (int w = 0; w < SC_WARPS; ++w) sum += smem[(size_t)w * NCH * TILE + ch * TILE + n];
-            v[ch] = sum;
-            any |= sum != 0.0;
-        }
-        if (any) {
-            long a = tile_to_grid(n, s_nbr);
-            if (a >= 0) Policy::flush(args, a, v);
-        }
-    }
-}
-
-// ---- column scatter (the version the hot path uses) -----------------------------------------------------------------
+// ---- column scatter -----------------------------------------------------------------
 // One CTA per HALF page group (SPLIT = 2: the 16 cells of one x-layer of the 2x4x4 page), thread = (cell, (i, j) column of
 // the 3x3x3 stencil): 9 threads per cell, each keeping the 3 nodes x NCH channels of its z-column in registers.
 // Compared with the plane skeleton above (ncu: 16.4 of 32 lanes active in its accumulate loop, 29 % of the stalls on the CTA
@@ -184,14 +81,24 @@ struct ColGeo {
 static_assert(Geo::BX == 2, "SPLIT = 2 halves the page along x");
 constexpr int CS_SPLIT = 2;
 constexpr int CS_CHUNK = 192; // particles per prep pass
-constexpr int CS_PAD = CS_CHUNK + 1; // odd row length: field f of particle p sits in bank 2 (f + p) mod 32
 constexpr int CS_THREADS = ColGeo<CS_SPLIT>::THREADS;
+// Prepared records are PARTICLE-major, Policy::REC doubles each (REC even, REC / 2 odd: 16-byte aligned records whose
+// starts walk over all 8 groups of 4 banks), so that the (cell, column) threads fetch them as 128-bit words: the accumulate
+// loop is bound by shared-memory wavefronts (ncu: 1.7 wavefronts per LDS.64 even with 9 lanes reading the same word), and
+// an LDS.128 moves twice the data per wavefront.
 template <class Policy>
 constexpr size_t cs_smem_bytes()
 {
-    constexpr size_t rec = (size_t)Policy::REC * CS_PAD, con = (size_t)3 * Policy::NCH * CS_THREADS;
+    static_assert(Policy::REC % 2 == 0 && (Policy::REC / 2) % 2 == 1, "record stride: odd multiple of 16 bytes");
+    constexpr size_t rec = (size_t)Policy::REC * CS_CHUNK, con = (size_t)3 * Policy::NCH * CS_THREADS;
     return (rec > con ? rec : con) * sizeof(double);
 }
+__device__ __forceinline__ void lds2(const double* p, double& a, double& b)
+{
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    a = v.x; b = v.y;
+}
+__device__ __forceinline__ void sts2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 // host side of the combine table: start[NT + 1] then src[NSRC]; src = k * THREADS + cell_local * 9 + i * 3 + j
 inline void cs_build_table(short* tab)
 {
@@ -218,18 +125,22 @@ inline void cs_build_table(short* tab)
 constexpr int CS_TABLE_LEN = ColGeo<CS_SPLIT>::NT + 1 + ColGeo<CS_SPLIT>::NSRC;
 
 // Policy interface (column form):
-//   static constexpr int NCH, REC (doubles per prepared particle)
+//   static constexpr int NCH, REC (doubles per prepared particle), MINB (CTAs per SM the shared-memory footprint allows)
 //   struct Args
-//   __device__ static void prep(const Args&, size_t s, double* rec /* field f at rec[f * CS_PAD] */)
+//   __device__ static void prep(const Args&, size_t s, double* rec /* this particle's record */)
 //   __device__ static void accumulate_col(const double* rec, int i, int j, double di, double dj, double (&acc)[3][NCH])
 //   __device__ static void prefetch(const Args&, int first, int end, int tid, int nthreads)   L2 prefetch of the particle rows
 //   static constexpr bool DOF                                                   target is a DOF vector (a = DOF id) or grid channels
 //   __device__ static void flush1(const Args&, long a, int ch, double v)        a = DOF id / grid array index
-template <class Policy, int MINB = 5>
+// DBG: clock64 stamps of every CTA's phases are averaged into dbg[0..7] (HOT_CS_DEBUG; profiling aid, never the bench path)
+template <class Policy, int MINB = Policy::MINB, bool DBG = false>
 __global__ void __launch_bounds__(CS_THREADS, MINB) k_column_scatter(typename Policy::Args args, const int* __restrict__ cell_start,
     const int* __restrict__ group_slot, const int* __restrict__ nbr8, const short* __restrict__ table, const int* __restrict__ tile_dof,
-    int pf_dist)
+    int pf_dist, unsigned long long* dbg = nullptr)
 {
+    long long t_[8];
+#define CS_STAMP(k) do { if (DBG) t_[k] = clock64(); } while (0)
+    CS_STAMP(0);
     using G = ColGeo<CS_SPLIT>;
     constexpr int NCH = Policy::NCH, E = Geo::E, THREADS = G::THREADS;
     extern __shared__ __align__(16) double cs_smem[];
@@ -261,14 +172,19 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_column_scatter(typename Po
     for (int cb = first; cb < end; cb += CS_CHUNK) {
         const int cn = min(CS_CHUNK, end - cb);
         if (cb != first) __syncthreads(); // previous pass consumed
-        for (int k = tid; k < cn; k += THREADS) Policy::prep(args, (size_t)cb + k, cs_smem + k);
+        if (cb == first) CS_STAMP(1);
+        for (int k = tid; k < cn; k += THREADS) Policy::prep(args, (size_t)cb + k, cs_smem + (size_t)k * Policy::REC);
+        if (cb == first) CS_STAMP(2);
         __syncthreads(); // records (and, on the first pass, s_cs / s_nbr) visible
+        if (cb == first) CS_STAMP(3);
         const int my_b = s_cs[c], my_e = s_cs[c + 1];
         const int pb = max(my_b, cb) - cb, pe = min(my_e, cb + cn) - cb;
-        for (int p = pb; p < pe; ++p) Policy::accumulate_col(cs_smem + p, i, j, di, dj, acc);
+        for (int p = pb; p < pe; ++p) Policy::accumulate_col(cs_smem + (size_t)p * Policy::REC, i, j, di, dj, acc);
     }
+    CS_STAMP(4);
     Policy::prefetch(args, pf_first, pf_end, tid, THREADS);
     __syncthreads(); // records dead -> reuse as the contribution array [ch][k][tid]
+    CS_STAMP(5);
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
@@ -294,6 +210,12 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_column_scatter(typename Po
                 if (sum[ch] != 0.0) Policy::flush1(args, a, ch, sum[ch]);
         }
     }
+    if (DBG && (tid & 31) == 0 && end - first <= CS_CHUNK) { // per warp: start->loads issued, prep, barrier wait, accumulate, ..., total
+        CS_STAMP(7);
+        for (int k = 1; k < 8; ++k) atomicAdd(dbg + k, (unsigned long long)(t_[k] - t_[k - 1]));
+        atomicAdd(dbg, 1ull);
+    }
+#undef CS_STAMP
 }
 
 // prefetch distance in CTAs: HOT_PF_DIST if set, else one wave of resident CTAs (148 SMs x ctas_per_sm)
@@ -321,28 +243,201 @@ int launch_column_scatter(Sim* s, const typename Policy::Args& a)
     static const cudaError_t attr = cudaFuncSetAttribute(k_column_scatter<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
         (int)cs_smem_bytes<Policy>());
     HOT_CUDA(attr);
+    static int dbg_runs = getenv("HOT_CS_DEBUG") ? atoi(getenv("HOT_CS_DEBUG")) : 0;
+    if (dbg_runs > 0) {
+        --dbg_runs;
+        static const cudaError_t attr2 = cudaFuncSetAttribute(k_column_scatter<Policy, Policy::MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int)cs_smem_bytes<Policy>());
+        HOT_CUDA(attr2);
+        unsigned long long* d = nullptr;
+        unsigned long long h[8] = {0};
+        HOT_CUDA(cudaMalloc((void**)&d, sizeof h));
+        HOT_CUDA(cudaMemcpy(d, h, sizeof h, cudaMemcpyHostToDevice));
+        k_column_scatter<Policy, Policy::MINB, true><<<(unsigned)(CS_SPLIT * (s->g1 - s->g0)), CS_THREADS, cs_smem_bytes<Policy>(), s->stream>>>(a,
+            s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0, s->nbr8.p, s->cs_table.p,
+            Policy::DOF ? s->tile_dof.p + (size_t)s->g0 * Geo::TILE : nullptr, pf_distance(s, Policy::MINB), d);
+        HOT_CUDA(cudaStreamSynchronize(s->stream));
+        HOT_CUDA(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        const double n = h[0] ? (double)h[0] : 1.0;
+        fprintf(stderr, "[cs dbg] NCH %d: %llu warps; mean cycles: bounds+issue %.0f | prep %.0f | barrier %.0f | accumulate %.0f | prefetch+barrier %.0f | park+barrier %.0f | combine+flush %.0f\n",
+            Policy::NCH, h[0], h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[7] / n);
+        s->launches++;
+        return 0;
+    }
     k_column_scatter<Policy><<<(unsigned)(CS_SPLIT * (s->g1 - s->g0)), CS_THREADS, cs_smem_bytes<Policy>(), s->stream>>>(a,
         s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0, s->nbr8.p, s->cs_table.p,
-        Policy::DOF ? s->tile_dof.p + (size_t)s->g0 * Geo::TILE : nullptr, pf_distance(s, 5));
+        Policy::DOF ? s->tile_dof.p + (size_t)s->g0 * Geo::TILE : nullptr, pf_distance(s, Policy::MINB));
     HOT_LAUNCHED(s);
     return 0;
 }
 
-// B-spline weights of the three axes of one particle into a prepared record: fields 0..8 = w[axis][t]; with GRAD also
-// fields 9..17 = dw[axis][t] / dx.  Returns x_node(base) - x_p per axis.
+// ---- plane scatter, second form ---------------------------------------------------------------------------------------
+// The column skeleton above turned out to be bound by shared-memory wavefronts: its 9 threads per cell each fetch the same
+// ~16 per-particle doubles (ncu: 19 wavefronts per particle, 66 us of the 113 us kernel, LDS.128 did not help).  Going back
+// to thread = (cell, x-plane) - 3 threads per cell, 9 nodes x NCH accumulators each - cuts that traffic 3x per particle while
+// keeping what the column form established: per-particle prep pass (weights once per particle), particle-major records,
+// table-driven gather combine.  The plane form's own weakness - a warp holds 10.7 cells whose particle counts differ, 16 of
+// 32 lanes active in the first plane kernel - is removed by handing the cells to the lanes in order of DECREASING particle
+// count, which the gather combine permits (any thread may own any cell).
+constexpr int PS_THREADS = 3 * Geo::E; // 96
+constexpr int PS_CAP = 384; // particles per prep pass: a full page at 12 particles per cell
+constexpr int PS_NSRC = 27 * Geo::E;
+constexpr int PS_TABLE_LEN = Geo::TILE + 1 + PS_NSRC;
+// combine table: start[TILE + 1] then src[864]; src = (j * 3 + k) * PS_THREADS + cell * 3 + i
+inline void ps_build_table(short* tab)
+{
+    short* start = tab;
+    short* src = tab + Geo::TILE + 1;
+    int fill[Geo::TILE + 1] = {0};
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int c = 0; c < Geo::E; ++c) {
+            const int cz = c & (Geo::BZ - 1), cy = (c >> Geo::zb) & (Geo::BY - 1), cx = c >> (Geo::zb + Geo::yb);
+            for (int i = 0; i < 3; ++i)
+                for (int jk = 0; jk < 9; ++jk) {
+                    const int n = ((cx + i) * Geo::TY + (cy + jk / 3)) * Geo::TZ + (cz + jk % 3);
+                    if (pass == 0) fill[n + 1]++;
+                    else src[fill[n]++] = (short)(jk * PS_THREADS + c * 3 + i);
+                }
+        }
+        if (pass == 0) {
+            for (int n = 0; n < Geo::TILE; ++n) fill[n + 1] += fill[n];
+            for (int n = 0; n <= Geo::TILE; ++n) start[n] = (short)fill[n];
+        }
+    }
+}
+template <class Policy>
+constexpr size_t ps_smem_bytes()
+{
+    constexpr size_t rec = (size_t)Policy::REC * PS_CAP, con = (size_t)9 * Policy::NCH * PS_THREADS;
+    return (rec > con ? rec : con) * sizeof(double);
+}
+// Policy interface (plane form): NCH, REC, DOF, prep, prefetch, flush1 as for the column form and
+//   __device__ static void accumulate_plane(const double* rec, int i, double di, double (&acc)[9][NCH])
+template <class Policy>
+__global__ void __launch_bounds__(PS_THREADS, 3) k_plane2_scatter(typename Policy::Args args, const int* __restrict__ cell_start,
+    const int* __restrict__ group_slot, const int* __restrict__ nbr8, const short* __restrict__ table, const int* __restrict__ tile_dof,
+    int pf_dist)
+{
+    constexpr int NCH = Policy::NCH, E = Geo::E, THREADS = PS_THREADS;
+    extern __shared__ __align__(16) double cs_smem[];
+    __shared__ int s_cs[E + 1];
+    __shared__ int s_order[E];
+    __shared__ int s_nbr[8];
+
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const int* csg = cell_start + (size_t)g * (E + 1);
+    const int first = csg[0], end = csg[E]; // every thread: the prep loads below start without waiting for a CTA barrier
+    int pf_first = 0, pf_end = 0;
+    if (pf_dist > 0 && g + pf_dist < (int)gridDim.x) {
+        pf_first = cell_start[(size_t)(g + pf_dist) * (E + 1)];
+        pf_end = cell_start[(size_t)(g + pf_dist) * (E + 1) + E];
+    }
+    if (tid <= E) s_cs[tid] = csg[tid];
+    if (tid < 8) s_nbr[tid] = nbr8[(size_t)group_slot[g] * 8 + tid];
+    double acc[9][NCH];
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) acc[a][ch] = 0.0;
+    int c = 0;
+    const int i = tid % 3;
+    const double di = (double)i;
+    for (int cb = first; cb < end; cb += PS_CAP) {
+        const int cn = min(PS_CAP, end - cb);
+        if (cb != first) __syncthreads(); // previous pass consumed
+        for (int k = tid; k < cn; k += THREADS) Policy::prep(args, (size_t)cb + k, cs_smem + (size_t)k * Policy::REC);
+        __syncthreads(); // records (and, on the first pass, s_cs / s_nbr) visible
+        if (cb == first) {
+            // cells to lanes in order of decreasing particle count: the lanes of a warp then run loops of similar length
+            if (tid < E) {
+                const int cnt = s_cs[tid + 1] - s_cs[tid];
+                int rank = 0;
+                for (int o = 0; o < E; ++o) {
+                    const int co = s_cs[o + 1] - s_cs[o];
+                    rank += (co > cnt) || (co == cnt && o < tid);
+                }
+                s_order[rank] = tid;
+            }
+            __syncthreads();
+            c = s_order[tid / 3];
+        }
+        const int my_b = s_cs[c], my_e = s_cs[c + 1];
+        const int pb = max(my_b, cb) - cb, pe = min(my_e, cb + cn) - cb;
+        for (int p = pb; p < pe; ++p) Policy::accumulate_plane(cs_smem + (size_t)p * Policy::REC, i, di, acc);
+    }
+    Policy::prefetch(args, pf_first, pf_end, tid, THREADS);
+    __syncthreads(); // records dead -> reuse as the contribution array [ch][jk][cell * 3 + i]
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) cs_smem[(ch * 9 + a) * THREADS + c * 3 + i] = acc[a][ch];
+    __syncthreads();
+    for (int n = tid; n < Geo::TILE; n += THREADS) {
+        const int e0 = table[n], e1 = table[n + 1];
+        double sum[NCH];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) sum[ch] = 0.0;
+        for (int e = e0; e < e1; ++e) {
+            const int src = table[Geo::TILE + 1 + e];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) sum[ch] += cs_smem[ch * 9 * THREADS + src];
+        }
+        const long a = Policy::DOF ? (long)tile_dof[(size_t)g * Geo::TILE + n] : tile_to_grid(n, s_nbr);
+        if (a >= 0) {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch)
+                if (sum[ch] != 0.0) Policy::flush1(args, a, ch, sum[ch]);
+        }
+    }
+}
+template <class Policy>
+int launch_plane2_scatter(Sim* s, const typename Policy::Args& a)
+{
+    if (s->g1 <= s->g0) return 0;
+    if (!s->ps_table_ready) {
+        short tab[PS_TABLE_LEN];
+        ps_build_table(tab);
+        HOT_CUDA(s->ps_table.reserve(PS_TABLE_LEN));
+        HOT_CUDA(cudaMemcpyAsync(s->ps_table.p, tab, sizeof tab, cudaMemcpyHostToDevice, s->stream));
+        HOT_CUDA(cudaStreamSynchronize(s->stream)); // tab is a stack array
+        s->ps_table_ready = true;
+    }
+    static const cudaError_t attr = cudaFuncSetAttribute(k_plane2_scatter<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        (int)ps_smem_bytes<Policy>());
+    HOT_CUDA(attr);
+    k_plane2_scatter<Policy><<<(unsigned)(s->g1 - s->g0), PS_THREADS, ps_smem_bytes<Policy>(), s->stream>>>(a,
+        s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0, s->nbr8.p, s->ps_table.p,
+        Policy::DOF ? s->tile_dof.p + (size_t)s->g0 * Geo::TILE : nullptr, pf_distance(s, 3));
+    HOT_LAUNCHED(s);
+    return 0;
+}
+// which skeleton a scatter uses: the policy's measured default, or HOT_SCATTER = plane | column for A/B runs
+template <class Policy>
+int launch_scatter(Sim* s, const typename Policy::Args& a)
+{
+    static const int forced = [] {
+        const char* e = getenv("HOT_SCATTER");
+        return !e ? 0 : (e[0] == 'c' ? 1 : 2);
+    }();
+    const bool plane = forced ? forced == 2 : Policy::PLANE;
+    return plane ? launch_plane2_scatter<Policy>(s, a) : launch_column_scatter<Policy>(s, a);
+}
+
+// B-spline weights (and, with GRAD, weight derivatives / dx) of the three axes of one particle in the reference's operation
+// order; d0n = x_node(base) - x_p per axis
 template <bool GRAD>
-__device__ __forceinline__ void prep_weights(const double (&Xp)[3], double dx, double one_over_dx, double* __restrict__ rec, double (&d0n)[3])
+__device__ __forceinline__ void prep_weights(const double (&Xp)[3], double dx, double one_over_dx, double (&w)[3][3], double (&g)[3][3], double (&d0n)[3])
 {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        double xi, w[3], dw[3];
+        double xi, dw[3];
         const int b = base_node_of(Xp[d], one_over_dx, &xi);
-        bspline_axis(xi - (double)b, w, GRAD ? dw : nullptr);
+        bspline_axis(xi - (double)b, w[d], GRAD ? dw : nullptr);
         d0n[d] = (double)b * dx - Xp[d];
+        if (GRAD) {
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            rec[(3 * d + t) * CS_PAD] = w[t];
-            if (GRAD) rec[(9 + 3 * d + t) * CS_PAD] = one_over_dx * dw[t];
+            for (int t = 0; t < 3; ++t) g[d][t] = one_over_dx * dw[t];
         }
     }
 }
@@ -351,15 +446,14 @@ __device__ __forceinline__ void prep_weights(const double (&Xp)[3], double dx, d
 struct SplineEval {
     double w[3][3], dw[3][3], d0n[3]; // weights, weight derivatives (not yet / dx), x_node(base) - x_p
     int base[3];
-    // from a staged record (fields 0..2 = position)
-    __device__ __forceinline__ void eval_rec(const double* __restrict__ rec, double dx, double one_over_dx, bool want_dw)
+    __device__ __forceinline__ void eval3(const double (&Xp)[3], double dx, double one_over_dx, bool want_dw)
     {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            double Xd = rec[d * SC_PAD], xi;
-            base[d] = base_node_of(Xd, one_over_dx, &xi);
+            double xi;
+            base[d] = base_node_of(Xp[d], one_over_dx, &xi);
             bspline_axis(xi - (double)base[d], w[d], want_dw ? dw[d] : nullptr);
-            d0n[d] = (double)base[d] * dx - Xd;
+            d0n[d] = (double)base[d] * dx - Xp[d];
         }
     }
     __device__ __forceinline__ void eval(const double* __restrict__ X, size_t ps, size_t s, double dx, double one_over_dx, bool want_dw)

@@ -183,8 +183,8 @@ struct Sim {
     DevBuf<double> dv, vn, mass_matrix;
 
     int pf_dist = -1; // L2 prefetch distance of the per-group kernels in CTAs (-1: default = one wave of resident CTAs; 0: off; HOT_PF_DIST)
-    DevBuf<short> cs_table; // combine table of the column scatter (scatter.cuh)
-    bool cs_table_ready = false;
+    DevBuf<short> cs_table, ps_table; // combine tables of the column / plane scatter (scatter.cuh)
+    bool cs_table_ready = false, ps_table_ready = false;
     DevBuf<int> flags; // g2p CFL flags
     // plasticity applied after G2P + evolveStrain (MpmSimulationBase.cpp:1039-1064): 0 none, 1 VonMisesFixedCorotated, 2 SnowPlasticity
     int plastic_model = 0;
@@ -359,6 +359,36 @@ __host__ __device__ inline uint64_t packed_add(uint64_t a, uint64_t b)
     uint64_t rz = ((a | ~Geo::zmask) + (b & Geo::zmask)) & Geo::zmask;
     uint64_t rw = ((a | ~w) + (b & w)) & w;
     return rx | ry | rz | rw;
+}
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: contiguous runs of the sorted particle rows are
+// staged into shared memory by ONE thread without occupying registers or scoreboard slots; source, destination and size are
+// multiples of 16 bytes.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_addr(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_addr(b)), "r"(parity)
+                     : "memory");
+    } while (!ok);
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // L2 prefetch of the sorted-particle run [first, end) of `nrows` consecutive SoA rows (row stride ps), one 128-byte line per

@@ -6,19 +6,11 @@
 // constructNewVelocityFromNewtonResult (:891-901), FBasedMpmForceHelper::evolveStrain
 // (Lib/MPM/Force/FBasedMpmForceHelper.cpp:100-114).
 //
-// P2G design (why it is not the reference's 8-colour scatter): fp64 P2G sits on the B200 ridge
-// (128 B and >= ~300 DFMA-class ops per particle; 18.5 T DFMA/s vs 6.5 TB/s), so the kernel minimises
-// fp64 issue slots and has no atomics in the particle loop:
-//   1. the group's particles (one contiguous, coalesced run of every SoA row) are staged in shared memory as
-//      per-particle records holding everything that is independent of the stencil node (weights, m*v,
-//      m*C columns, x_node0 - x_p);
-//   2. thread (cell c of the page, x-plane i of the 3x3x3 stencil) walks the particles of ITS cell - they
-//      are adjacent because the sort key contains the in-page cell bits - and accumulates the 9 nodes x 4
-//      channels of its plane in registers (36 accumulators);
-//   3. the per-cell sums go to a per-warp (B+2)^3 node tile in shared memory in 9 (j,k) steps; inside one step
-//      the lanes of a warp hit distinct nodes (a warp holds < 16 consecutive cells, i.e. distinct (cy,cz)),
-//      so plain read-modify-write + __syncwarp suffices;
-//   4. the warp tiles are summed and flushed with one fp64 RED per touched node and channel.
+// P2G design (why it is not the reference's 8-colour scatter): fp64 P2G sits near the B200 ridge (128 B and ~300 DFMA-class
+// ops per particle; ~17 T DFMA/s vs 6.5 TB/s), so the kernel minimises fp64 issue slots and shared-memory wavefronts and has
+// no atomics in the particle loop - see scatter.cuh for the prep / accumulate / gather-combine structure it shares with the
+// force and Hessian scatters.  G2P is the matching gather: CTA per page group, the group's (v + dv) node tile staged in
+// shared memory through the per-step tile -> DOF table, one thread per particle, tensor-product contraction, F update fused.
 #include "scatter.cuh"
 #include "dense3.cuh"
 #include <cstdlib>
@@ -31,8 +23,7 @@ constexpr int TILE = Geo::TILE;
 
 // a6: g.m += w m_p ; g.v += w (m_p C_p (x_i - x_p) + m_p v_p)   (MpmSimulationBase.cpp:636-652)
 struct P2GPolicy {
-    // record: X(3) m  m*v(3)  m*C(9, column-major)
-    static constexpr int NCH = 4, RAW = 16, GATHER = 0;
+    static constexpr int NCH = 4;
     struct Args {
         size_t ps;
         const double *X, *V, *M, *C;
@@ -40,61 +31,11 @@ struct P2GPolicy {
         size_t gs;
         double *g_m, *g_v;
     };
-    __device__ static void gather_node(const Args&, long, double (&)[3]) {}
-    __device__ static void stage(const Args& a, size_t s, double* r, const double*)
-    {
-        const double m = a.M[s];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            r[d * SC_PAD] = a.X[d * a.ps + s];
-            r[(4 + d) * SC_PAD] = m * a.V[d * a.ps + s];
-        }
-        r[3 * SC_PAD] = m;
-#pragma unroll
-        for (int q = 0; q < 9; ++q) r[(7 + q) * SC_PAD] = m * a.C[q * a.ps + s];
-    }
-    __device__ __forceinline__ static void accumulate(const Args& a, const double* rec, int pl, double (&acc)[9][4])
-    {
-        SplineEval sp;
-        sp.eval_rec(rec, a.dx, a.one_over_dx, false);
-        const double m = rec[3 * SC_PAD];
-        const double wi = pl == 0 ? sp.w[0][0] : (pl == 1 ? sp.w[0][1] : sp.w[0][2]);
-        const double dxi = (double)pl * a.dx + sp.d0n[0];
-        double ai[3], c1[3], c2[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            ai[r] = rec[(4 + r) * SC_PAD] + rec[(7 + r) * SC_PAD] * dxi; // m v + m C(:,0) (x_i - x_p)_x
-            c1[r] = rec[(10 + r) * SC_PAD];
-            c2[r] = rec[(13 + r) * SC_PAD];
-        }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const double dyj = (double)j * a.dx + sp.d0n[1];
-            const double wij = wi * sp.w[1][j];
-            const double bj[3] = {ai[0] + c1[0] * dyj, ai[1] + c1[1] * dyj, ai[2] + c1[2] * dyj};
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const double dzk = (double)k * a.dx + sp.d0n[2];
-                const double w = wij * sp.w[2][k];
-                acc[j * 3 + k][0] += w * m;
-                acc[j * 3 + k][1] += w * (bj[0] + c2[0] * dzk);
-                acc[j * 3 + k][2] += w * (bj[1] + c2[1] * dzk);
-                acc[j * 3 + k][3] += w * (bj[2] + c2[2] * dzk);
-            }
-        }
-    }
-    __device__ static void flush(const Args& a, long n, const double (&v)[4])
-    {
-        if (v[0] == 0.0) return;
-        atomicAdd(a.g_m + n, v[0]);
-        atomicAdd(a.g_v + n, v[1]);
-        atomicAdd(a.g_v + a.gs + n, v[2]);
-        atomicAdd(a.g_v + 2 * a.gs + n, v[3]);
-    }
-
-    // ---- column form (scatter.cuh, k_column_scatter).  Prepared record: w[3][3], m, A(3) = m v + m C (x_node0 - x_p),
-    // Gx(3), Gy(3), Gz(3) = dx * m C(:, d): the node value of stencil node (i, j, k) is A + i Gx + j Gy + k Gz.
-    static constexpr int REC = 22;
+    // Prepared record (22 doubles, 16-byte words):
+    //   [0..2] wx  [3..5] wy | [6..8] wz [9] m | [10..12] A = m v + m C (x_node0 - x_p) | [13..15] Gx [16..18] Gy [19..21] Gz,
+    //   G* = dx * m C(:, d): the node value of stencil node (i, j, k) is A + i Gx + j Gy + k Gz.
+    static constexpr int REC = 22, MINB = 5; // column form: 33 KB of records per CTA, plane form 66 KB
+    static constexpr bool PLANE = true; // measured: plane 0.104 ms, column 0.109 ms (C2)
     static constexpr bool DOF = false;
     __device__ __forceinline__ static void prefetch(const Args& a, int first, int end, int tid, int nt)
     {
@@ -106,7 +47,7 @@ struct P2GPolicy {
     __device__ __forceinline__ static void prep(const Args& a, size_t s, double* __restrict__ r)
     {
         const double m = a.M[s];
-        double Xp[3], v[3], Cm[9], d0n[3];
+        double Xp[3], v[3], Cm[9], d0n[3], w[3][3], g[3][3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             Xp[d] = a.X[d * a.ps + s];
@@ -114,34 +55,65 @@ struct P2GPolicy {
         }
 #pragma unroll
         for (int q = 0; q < 9; ++q) Cm[q] = m * a.C[q * a.ps + s];
-        prep_weights<false>(Xp, a.dx, a.one_over_dx, r, d0n);
-        r[9 * CS_PAD] = m;
+        prep_weights<false>(Xp, a.dx, a.one_over_dx, w, g, d0n);
+        double A[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            r[(10 + c) * CS_PAD] = m * v[c] + (Cm[c] * d0n[0] + Cm[c + 3] * d0n[1] + Cm[c + 6] * d0n[2]);
-            r[(13 + c) * CS_PAD] = a.dx * Cm[c];
-            r[(16 + c) * CS_PAD] = a.dx * Cm[c + 3];
-            r[(19 + c) * CS_PAD] = a.dx * Cm[c + 6];
-        }
+        for (int c = 0; c < 3; ++c) A[c] = m * v[c] + (Cm[c] * d0n[0] + Cm[c + 3] * d0n[1] + Cm[c + 6] * d0n[2]);
+        sts2(r + 0, w[0][0], w[0][1]); sts2(r + 2, w[0][2], w[1][0]); sts2(r + 4, w[1][1], w[1][2]);
+        sts2(r + 6, w[2][0], w[2][1]); sts2(r + 8, w[2][2], m);
+        sts2(r + 10, A[0], A[1]); sts2(r + 12, A[2], a.dx * Cm[0]); sts2(r + 14, a.dx * Cm[1], a.dx * Cm[2]);
+        sts2(r + 16, a.dx * Cm[3], a.dx * Cm[4]); sts2(r + 18, a.dx * Cm[5], a.dx * Cm[6]); sts2(r + 20, a.dx * Cm[7], a.dx * Cm[8]);
     }
     __device__ __forceinline__ static void accumulate_col(const double* __restrict__ rec, int i, int j, double di, double dj, double (&acc)[3][4])
     {
-        const double wij = rec[i * CS_PAD] * rec[(3 + j) * CS_PAD];
-        const double m = rec[9 * CS_PAD];
-        double b[3], gz[3];
+        const double wij = rec[i] * rec[3 + j];
+        double wz[3], m, A[3], gx[3], gy[3], gz[3];
+        lds2(rec + 6, wz[0], wz[1]); lds2(rec + 8, wz[2], m);
+        lds2(rec + 10, A[0], A[1]); lds2(rec + 12, A[2], gx[0]); lds2(rec + 14, gx[1], gx[2]);
+        lds2(rec + 16, gy[0], gy[1]); lds2(rec + 18, gy[2], gz[0]); lds2(rec + 20, gz[1], gz[2]);
+        double b[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            b[c] = fma(dj, rec[(16 + c) * CS_PAD], fma(di, rec[(13 + c) * CS_PAD], rec[(10 + c) * CS_PAD]));
-            gz[c] = rec[(19 + c) * CS_PAD];
-        }
+        for (int c = 0; c < 3; ++c) b[c] = fma(dj, gy[c], fma(di, gx[c], A[c]));
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const double w = wij * rec[(6 + k) * CS_PAD];
+            const double w = wij * wz[k];
             acc[k][0] = fma(w, m, acc[k][0]);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const double val = k == 0 ? b[c] : (k == 1 ? b[c] + gz[c] : fma(2.0, gz[c], b[c]));
                 acc[k][1 + c] = fma(w, val, acc[k][1 + c]);
+            }
+        }
+    }
+    // plane form: the 9 nodes (j, k) of x-plane i
+    __device__ __forceinline__ static void accumulate_plane(const double* __restrict__ rec, int i, double di, double (&acc)[9][4])
+    {
+        double wy[3], wz[3], m, A[3], gx[3], gy[3], gz[3];
+        const double wx = rec[i];
+        wy[0] = rec[3];
+        lds2(rec + 4, wy[1], wy[2]);
+        lds2(rec + 6, wz[0], wz[1]); lds2(rec + 8, wz[2], m);
+        lds2(rec + 10, A[0], A[1]); lds2(rec + 12, A[2], gx[0]); lds2(rec + 14, gx[1], gx[2]);
+        lds2(rec + 16, gy[0], gy[1]); lds2(rec + 18, gy[2], gz[0]); lds2(rec + 20, gz[1], gz[2]);
+        double b[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) b[c] = fma(di, gx[c], A[c]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double wij = wx * wy[j];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double w = wij * wz[k];
+                acc[j * 3 + k][0] = fma(w, m, acc[j * 3 + k][0]);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double val = k == 0 ? b[c] : (k == 1 ? b[c] + gz[c] : fma(2.0, gz[c], b[c]));
+                    acc[j * 3 + k][1 + c] = fma(w, val, acc[j * 3 + k][1 + c]);
+                }
+            }
+            if (j < 2) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) b[c] += gy[c];
             }
         }
     }
@@ -154,13 +126,20 @@ struct P2GPolicy {
 constexpr int G2P_THREADS = 128;
 static_assert(TILE <= 2 * G2P_THREADS && TILE >= G2P_THREADS, "tile staged in two rounds");
 
+// TMA = true: the group's X and F rows (12 runs of <= G2P_CAP particles) are staged in shared memory by bulk copies that one
+// thread issues before the tile gather, so the particle loop has no global loads and no scoreboard waits of its own.
+constexpr int G2P_CAP = 256;
+template <bool TMA>
 __global__ void __launch_bounds__(G2P_THREADS, 4) k_g2p(const int* __restrict__ group_first, const int* __restrict__ tile_dof, size_t ps,
     double* __restrict__ X, double* __restrict__ V, double* __restrict__ C, double* __restrict__ F, double* __restrict__ gradV, double dx,
     double one_over_dx, double dt, double apic_rpic_ratio, double cfl, const double* __restrict__ vn, const double* __restrict__ dv,
     int* __restrict__ flags, int pf_dist)
 {
     __shared__ double tile[3][TILE];
+    __shared__ __align__(16) double s_rows[TMA ? 12 : 1][TMA ? G2P_CAP + 2 : 2];
+    __shared__ __align__(8) unsigned long long s_bar;
     const int g = blockIdx.x, tid = threadIdx.x;
+    if (TMA && tid == 0) mbar_init(&s_bar, 1);
     // dependent DRAM round trips of a CTA: {group_first, tile_dof} -> {vn + dv gather, X} -> F (L2-prefetched); the tile's DOF ids
     // come from the per-step table instead of the chain group_slot -> nbr8 -> g_idx
     const int id0 = tile_dof[(size_t)g * TILE + tid];
@@ -173,11 +152,25 @@ __global__ void __launch_bounds__(G2P_THREADS, 4) k_g2p(const int* __restrict__ 
         pf_end = group_first[g + pf_dist + 1];
     }
     double X0[3] = {0.0, 0.0, 0.0};
-    if (first + tid < end) {
+    if (!TMA && first + tid < end) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) X0[d] = X[d * ps + first + tid];
 #pragma unroll
         for (int q = 0; q < 9; ++q) prefetch_l2(F + q * ps + first + tid);
+    }
+    // chunk [c0, c0 + cn) of the group: the bulk copies start at the even index below c0 and move an even count (16-byte rule)
+    auto issue_chunk = [&](int c0) {
+        const int cn = min(G2P_CAP, end - c0), start = c0 & ~1, cnt = (c0 + cn - start + 1) & ~1;
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar, 12u * cnt * 8u);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) bulk_load(s_rows[d], X + d * ps + start, cnt * 8u, &s_bar);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) bulk_load(s_rows[3 + q], F + q * ps + start, cnt * 8u, &s_bar);
+    };
+    if (TMA) {
+        __syncthreads(); // barrier initialised
+        if (tid == 0 && first < end) issue_chunk(first);
     }
     // new_v = v + dv on the touched tile (constructNewVelocityFromNewtonResult fused into the staging; vn = the normalised v)
     {
@@ -198,12 +191,27 @@ __global__ void __launch_bounds__(G2P_THREADS, 4) k_g2p(const int* __restrict__ 
     const double D_inverse = 4.0 / (dx * dx); // MpmSimulationBase.cpp:114-118
     const double ca = (apic_rpic_ratio + 1.0) * 0.5, cb = (apic_rpic_ratio - 1.0) * 0.5;
     int fast = 0, half_fast = 0;
-    for (int s = first + tid; s < end; s += G2P_THREADS) {
+    unsigned phase = 0;
+    for (int c0 = first; c0 < end; c0 += TMA ? G2P_CAP : end - first) {
+    const int c1 = TMA ? min(c0 + G2P_CAP, end) : end, start = c0 & ~1;
+    if (TMA) {
+        if (c0 != first) {
+            __syncthreads(); // every thread is done with the previous chunk's rows
+            if (tid == 0) issue_chunk(c0);
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1;
+    }
+    for (int s = c0 + tid; s < c1; s += G2P_THREADS) {
         double Xp[3], w[3][3], gw[3][3], xm[3][3]; // weights, weight derivatives / dx, x_node - x_p per axis and stencil index
         int tb[3];
+        if (TMA) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) X0[d] = s_rows[d][s - start];
+        }
         // software pipeline: the next particle's position load and F prefetch are in flight during this particle's contraction
         double Xn[3] = {0.0, 0.0, 0.0};
-        if (s + G2P_THREADS < end) {
+        if (!TMA && s + G2P_THREADS < end) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) Xn[d] = X[d * ps + s + G2P_THREADS];
 #pragma unroll
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 4) k_g2p(const int* __restrict__ 
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
             B[q] *= D_inverse;
-            Fo[q] = F[q * ps + s];
+            Fo[q] = TMA ? s_rows[3 + q][s - start] : F[q * ps + s];
             A[q] = dt * G[q];
             gradV[q * ps + s] = G[q];
         }
@@ -289,6 +297,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 4) k_g2p(const int* __restrict__ 
             }
 #pragma unroll
         for (int d = 0; d < 3; ++d) X0[d] = Xn[d];
+    }
     }
     prefetch_rows_l2(X, ps, 3, pf_first, pf_end, tid, G2P_THREADS);
     prefetch_rows_l2(F, ps, 9, pf_first, pf_end, tid, G2P_THREADS);
@@ -386,18 +395,8 @@ int p2g(Sim* s)
         KTime t(s, KC_P2G);
         P2GPolicy::Args a{s->P.stride, s->P.X.p, s->P.V.p, s->P.M.p, s->P.C.p, s->dx, 1.0 / s->dx, gn, s->g_m.p, s->g_v.p};
         if (s->g1 > s->g0) {
-            static const int variant = getenv("HOT_SCATTER_PLANE") ? 1 : 0; // A/B switch: the previous (cell, x-plane) skeleton
-            const unsigned grid = (unsigned)(s->g1 - s->g0);
-            const int* cs = s->cell_start.p + s->g0 * (Geo::E + 1);
-            const int* gsl = s->group_slot.p + s->g0;
-            if (variant == 1) {
-                k_plane_scatter<P2GPolicy><<<grid, SC_THREADS, 0, st>>>(a, cs, gsl, s->nbr8.p);
-                HOT_LAUNCHED(s);
-            }
-            else {
-                int rc = launch_column_scatter<P2GPolicy>(s, a);
-                if (rc) return rc;
-            }
+            int rc = launch_scatter<P2GPolicy>(s, a);
+            if (rc) return rc;
         }
     }
     int rc;
@@ -426,8 +425,9 @@ int g2p(Sim* s, double dt, int* flags)
     HOT_CUDA(cudaMemsetAsync(s->flags.p, 0, 2 * sizeof(int), st));
     {
         KTime t(s, KC_G2P);
+        static const bool tma = !(getenv("HOT_G2P_TMA") && atoi(getenv("HOT_G2P_TMA")) == 0); // A/B switch, default on
         if (s->g1 > s->g0)
-        k_g2p<<<(unsigned)(s->g1 - s->g0), G2P_THREADS, 0, st>>>(s->group_first.p + s->g0, s->tile_dof.p + (size_t)s->g0 * TILE, s->P.stride, s->P.X.p,
+        (tma ? k_g2p<true> : k_g2p<false>)<<<(unsigned)(s->g1 - s->g0), G2P_THREADS, 0, st>>>(s->group_first.p + s->g0, s->tile_dof.p + (size_t)s->g0 * TILE, s->P.stride, s->P.X.p,
             s->P.V.p, s->P.C.p, s->P.F.p, s->P.gradV.p, s->dx, 1.0 / s->dx, dt, s->apic_rpic_ratio, s->cfl, s->vn.p, s->dv.p, s->flags.p,
             pf_distance(s, 4));
         HOT_LAUNCHED(s);
