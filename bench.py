@@ -56,6 +56,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r1_traffic.json,
+    written by profiles/ncu_traffic.py from the .ncu-rep of the same workload); None if the capture is absent."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel, {}).get("dram_bytes")
+
+
 class ClockSampler(threading.Thread):
     """samples SM clock / throttle reasons through NVML while the timed region runs"""
 
@@ -90,7 +99,7 @@ class ClockSampler(threading.Thread):
                     for bit, nm in names.items():
                         if r & bit:
                             self.reasons.add(nm)
-                time.sleep(0.005)
+                time.sleep(0.0005)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 
@@ -327,12 +336,15 @@ def run_ours(args):
 
     e2e_step()
     barrier()
+    n_kernel_leg_samples = len(sampler.samples)
+    sampler.active = True                      # the e2e leg is a timed region as well
     ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ea.record(stream)
     for _ in range(e2e_steps):
         e2e_step()
     eb.record(stream)
     barrier()
+    sampler.active = False
     e2e_ms = ea.elapsed_time(eb) / e2e_steps
     # sort alone (reported, not part of the metric)
     sim.set_particles_ptr(n, [t.data_ptr() for t in host_in])
@@ -367,8 +379,10 @@ def run_ours(args):
         per = {k: (kt[k][0] / kt[k][1]) for k in ("p2g", "g2p", "number_nodes") if k in kt}
         dom = max(("p2g", "g2p"), key=lambda k: per.get(k, 0.0))
         ach = alg[dom] / (per[dom] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": f"k_{dom}", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "peak_source": peak_src,
+        kernel_name = {"p2g": "k_plane2_scatter<P2GPolicy>", "g2p": "k_g2p<true>"}[dom]
+        roof = {"bound": "hbm", "kernel": kernel_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": ncu_traffic(dom), "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json)",
+                "alg_bytes_per_launch": alg[dom], "peak_source": peak_src,
                 "per_kernel": {k: {"ms": per[k], "alg_GBps": (alg[k] / (per[k] * 1e-3) / 1e9 if k in alg else None),
                                    "frac": (alg[k] / (per[k] * 1e-3) / 1e9 / peak if k in alg else None)} for k in per},
                 "combined_p2g_g2p": {"alg_bytes": alg["p2g"] + alg["g2p"], "frac": (alg["p2g"] + alg["g2p"]) / (ms_per_step * 1e-3) / 1e9 / peak}}
@@ -393,7 +407,8 @@ def run_ours(args):
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "includes": "H2D from pinned host, sort, P2G, G2P(dt), D2H of X,V,C,F"},
-            "gpu_launches": launches, "clocks": sampler.result(), "sort_ms": sort_ms, "wall_s_timed_loop": wall,
+            "gpu_launches": launches, "clocks": dict(sampler.result(), samples_kernel_leg=n_kernel_leg_samples), "sort_ms": sort_ms, "wall_s_timed_loop": wall,
+            "vcycle_ms": (solver or {}).get("vcycle", {}).get("ms"), "hessian_apply_mf_ms": (solver or {}).get("hessian_apply_mf", {}).get("ms"),
             "solver_kernels": solver,
         }
         print(json.dumps(line))

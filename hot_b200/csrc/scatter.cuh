@@ -10,7 +10,7 @@
 //   accumulate thread per (cell, part of the 3x3x3 stencil) walks the particles of ITS cell - adjacent thanks to the sort key -
 //              and keeps its nodes x channels in registers;
 //   combine    every thread parks its sums, then thread (tile node) adds the contributions of its node in a fixed order read
-//              from a small index table and issues one fp64 RED per channel.
+//              (a closed-form walk, no index table) and issues one fp64 RED per channel.
 // Two thread mappings share this structure: the COLUMN form (9 threads per cell, 3 nodes each; half-page CTAs) and the PLANE
 // form (3 threads per cell, 9 nodes each; cells handed to lanes by decreasing particle count).  Which one a policy uses is
 // a measured choice (Policy::PLANE), see DESIGN.md.
@@ -66,7 +66,7 @@ __device__ __forceinline__ int tile_base(int bx, int by, int bz)
 //     CHUNK = 192 particles (a second pass serialises a DRAM round trip behind a quarter-full accumulate loop), 34-42 KB of
 //     shared memory, 5 CTAs per SM at different phases;
 //   * combine is a gather: every thread parks its 3 x NCH sums, then thread (node) adds the contributions of its node in a
-//     fixed order read from a tiny index table (csr_start / csr_src: which (cell, column, k) feed which tile node) - no
+//     fixed order (closed-form walk over the (cell, column, k) triples that feed the node) - no
 //     shared-memory atomics, no warp tiles, deterministic inside the CTA - and issues one RED per channel.
 // HBM traffic is the algorithmic minimum: every particle attribute is read once (coalesced runs of the sorted SoA rows),
 // every touched node receives one RED per channel and half page.
@@ -99,31 +99,6 @@ __device__ __forceinline__ void lds2(const double* p, double& a, double& b)
     a = v.x; b = v.y;
 }
 __device__ __forceinline__ void sts2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
-// host side of the combine table: start[NT + 1] then src[NSRC]; src = k * THREADS + cell_local * 9 + i * 3 + j
-inline void cs_build_table(short* tab)
-{
-    using G = ColGeo<CS_SPLIT>;
-    short* start = tab;
-    short* src = tab + G::NT + 1;
-    int fill[G::NT + 1] = {0};
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int c = 0; c < G::CELLS; ++c) {
-            const int cz = c & (Geo::BZ - 1), cy = (c >> Geo::zb) & (Geo::BY - 1), cx = c >> (Geo::zb + Geo::yb);
-            for (int ij = 0; ij < 9; ++ij)
-                for (int k = 0; k < 3; ++k) {
-                    const int n = ((cx + ij / 3) * Geo::TY + (cy + ij % 3)) * Geo::TZ + (cz + k);
-                    if (pass == 0) fill[n + 1]++;
-                    else src[fill[n]++] = (short)(k * G::THREADS + c * 9 + ij);
-                }
-        }
-        if (pass == 0) {
-            for (int n = 0; n < G::NT; ++n) fill[n + 1] += fill[n];
-            for (int n = 0; n <= G::NT; ++n) start[n] = (short)fill[n];
-        }
-    }
-}
-constexpr int CS_TABLE_LEN = ColGeo<CS_SPLIT>::NT + 1 + ColGeo<CS_SPLIT>::NSRC;
-
 // Policy interface (column form):
 //   static constexpr int NCH, REC (doubles per prepared particle), MINB (CTAs per SM the shared-memory footprint allows)
 //   struct Args
@@ -135,7 +110,7 @@ constexpr int CS_TABLE_LEN = ColGeo<CS_SPLIT>::NT + 1 + ColGeo<CS_SPLIT>::NSRC;
 // DBG: clock64 stamps of every CTA's phases are averaged into dbg[0..7] (HOT_CS_DEBUG; profiling aid, never the bench path)
 template <class Policy, int MINB = Policy::MINB, bool DBG = false>
 __global__ void __launch_bounds__(CS_THREADS, MINB) k_column_scatter(typename Policy::Args args, const int* __restrict__ cell_start,
-    const int* __restrict__ group_slot, const int* __restrict__ nbr8, const short* __restrict__ table, const int* __restrict__ tile_dof,
+    const int* __restrict__ group_slot, const int* __restrict__ nbr8, const int* __restrict__ tile_dof,
     int pf_dist, unsigned long long* dbg = nullptr)
 {
     long long t_[8];
@@ -190,15 +165,20 @@ __global__ void __launch_bounds__(CS_THREADS, MINB) k_column_scatter(typename Po
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) cs_smem[(ch * 3 + k) * THREADS + tid] = acc[k][ch];
     __syncthreads();
+    // gather combine: tile node (txl, ty, tz) of the half page receives column (i = txl, j) / node k of cell (0, ty - j, tz - k);
+    // the source index moves by a constant per loop step, so the walk needs no index table and no dependent loads
     if (tid < G::NT) {
-        const int e0 = table[tid], e1 = table[tid + 1];
+        const int tz = tid % Geo::TZ, ty = (tid / Geo::TZ) % Geo::TY, txl = tid / (Geo::TZ * Geo::TY);
+        const int j0 = max(0, ty - (Geo::BY - 1)), j1 = min(2, ty), k0 = max(0, tz - (Geo::BZ - 1)), k1 = min(2, tz);
         double sum[NCH];
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) sum[ch] = 0.0;
-        for (int e = e0; e < e1; ++e) {
-            const int src = table[G::NT + 1 + e];
+        for (int j = j0; j <= j1; ++j) {
+            int src = k0 * THREADS + ((((ty - j) << Geo::zb) | (tz - k0)) * 9) + txl * 3 + j;
+            for (int k = k0; k <= k1; ++k, src += THREADS - 9) {
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) sum[ch] += cs_smem[ch * 3 * THREADS + src];
+                for (int ch = 0; ch < NCH; ++ch) sum[ch] += cs_smem[ch * 3 * THREADS + src];
+            }
         }
         // node tid of the half tile = node (h + txl, ty, tz) of the page tile; DOF-vector targets take the node's DOF id from the
         // per-step table, grid-channel targets (P2G runs before the numbering) the grid slot
@@ -232,14 +212,6 @@ template <class Policy>
 int launch_column_scatter(Sim* s, const typename Policy::Args& a)
 {
     if (s->g1 <= s->g0) return 0;
-    if (!s->cs_table_ready) {
-        short tab[CS_TABLE_LEN];
-        cs_build_table(tab);
-        HOT_CUDA(s->cs_table.reserve(CS_TABLE_LEN));
-        HOT_CUDA(cudaMemcpyAsync(s->cs_table.p, tab, sizeof tab, cudaMemcpyHostToDevice, s->stream));
-        HOT_CUDA(cudaStreamSynchronize(s->stream)); // tab is a stack array
-        s->cs_table_ready = true;
-    }
     static const cudaError_t attr = cudaFuncSetAttribute(k_column_scatter<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
         (int)cs_smem_bytes<Policy>());
     HOT_CUDA(attr);
@@ -254,7 +226,7 @@ int launch_column_scatter(Sim* s, const typename Policy::Args& a)
         HOT_CUDA(cudaMalloc((void**)&d, sizeof h));
         HOT_CUDA(cudaMemcpy(d, h, sizeof h, cudaMemcpyHostToDevice));
         k_column_scatter<Policy, Policy::MINB, true><<<(unsigned)(CS_SPLIT * (s->g1 - s->g0)), CS_THREADS, cs_smem_bytes<Policy>(), s->stream>>>(a,
-            s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0, s->nbr8.p, s->cs_table.p,
+            s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0, s->nbr8.p,
             Policy::DOF ? s->tile_dof.p + (size_t)s->g0 * Geo::TILE : nullptr, pf_distance(s, Policy::MINB), d);
         HOT_CUDA(cudaStreamSynchronize(s->stream));
         HOT_CUDA(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
@@ -266,7 +238,7 @@ int launch_column_scatter(Sim* s, const typename Policy::Args& a)
         return 0;
     }
     k_column_scatter<Policy><<<(unsigned)(CS_SPLIT * (s->g1 - s->g0)), CS_THREADS, cs_smem_bytes<Policy>(), s->stream>>>(a,
-        s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0, s->nbr8.p, s->cs_table.p,
+        s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0, s->nbr8.p,
         Policy::DOF ? s->tile_dof.p + (size_t)s->g0 * Geo::TILE : nullptr, pf_distance(s, Policy::MINB));
     HOT_LAUNCHED(s);
     return 0;
@@ -277,35 +249,11 @@ int launch_column_scatter(Sim* s, const typename Policy::Args& a)
 // ~16 per-particle doubles (ncu: 19 wavefronts per particle, 66 us of the 113 us kernel, LDS.128 did not help).  Going back
 // to thread = (cell, x-plane) - 3 threads per cell, 9 nodes x NCH accumulators each - cuts that traffic 3x per particle while
 // keeping what the column form established: per-particle prep pass (weights once per particle), particle-major records,
-// table-driven gather combine.  The plane form's own weakness - a warp holds 10.7 cells whose particle counts differ, 16 of
+// gather combine.  The plane form's own weakness - a warp holds 10.7 cells whose particle counts differ, 16 of
 // 32 lanes active in the first plane kernel - is removed by handing the cells to the lanes in order of DECREASING particle
 // count, which the gather combine permits (any thread may own any cell).
 constexpr int PS_THREADS = 3 * Geo::E; // 96
 constexpr int PS_CAP = 384; // particles per prep pass: a full page at 12 particles per cell
-constexpr int PS_NSRC = 27 * Geo::E;
-constexpr int PS_TABLE_LEN = Geo::TILE + 1 + PS_NSRC;
-// combine table: start[TILE + 1] then src[864]; src = (j * 3 + k) * PS_THREADS + cell * 3 + i
-inline void ps_build_table(short* tab)
-{
-    short* start = tab;
-    short* src = tab + Geo::TILE + 1;
-    int fill[Geo::TILE + 1] = {0};
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int c = 0; c < Geo::E; ++c) {
-            const int cz = c & (Geo::BZ - 1), cy = (c >> Geo::zb) & (Geo::BY - 1), cx = c >> (Geo::zb + Geo::yb);
-            for (int i = 0; i < 3; ++i)
-                for (int jk = 0; jk < 9; ++jk) {
-                    const int n = ((cx + i) * Geo::TY + (cy + jk / 3)) * Geo::TZ + (cz + jk % 3);
-                    if (pass == 0) fill[n + 1]++;
-                    else src[fill[n]++] = (short)(jk * PS_THREADS + c * 3 + i);
-                }
-        }
-        if (pass == 0) {
-            for (int n = 0; n < Geo::TILE; ++n) fill[n + 1] += fill[n];
-            for (int n = 0; n <= Geo::TILE; ++n) start[n] = (short)fill[n];
-        }
-    }
-}
 template <class Policy>
 constexpr size_t ps_smem_bytes()
 {
@@ -316,7 +264,7 @@ constexpr size_t ps_smem_bytes()
 //   __device__ static void accumulate_plane(const double* rec, int i, double di, double (&acc)[9][NCH])
 template <class Policy>
 __global__ void __launch_bounds__(PS_THREADS, 3) k_plane2_scatter(typename Policy::Args args, const int* __restrict__ cell_start,
-    const int* __restrict__ group_slot, const int* __restrict__ nbr8, const short* __restrict__ table, const int* __restrict__ tile_dof,
+    const int* __restrict__ group_slot, const int* __restrict__ nbr8, const int* __restrict__ tile_dof,
     int pf_dist)
 {
     constexpr int NCH = Policy::NCH, E = Geo::E, THREADS = PS_THREADS;
@@ -373,21 +321,33 @@ __global__ void __launch_bounds__(PS_THREADS, 3) k_plane2_scatter(typename Polic
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) cs_smem[(ch * 9 + a) * THREADS + c * 3 + i] = acc[a][ch];
     __syncthreads();
-    for (int n = tid; n < Geo::TILE; n += THREADS) {
-        const int e0 = table[n], e1 = table[n + 1];
-        double sum[NCH];
+    // gather combine: tile node (tx, ty, tz) receives node (j, k) of plane i of cell (tx - i, ty - j, tz - k); the source index
+    // moves by a constant per loop step (no index table, no dependent loads).  Work item = (node, half of the channels):
+    // 2 x 144 items over 96 threads.
+    constexpr int CH2 = (NCH + 1) / 2;
+    for (int it = tid; it < 2 * Geo::TILE; it += THREADS) {
+        const int n = it % Geo::TILE, c0 = (it / Geo::TILE) * CH2;
+        if (c0 >= NCH) break;
+        const int tz = n % Geo::TZ, ty = (n / Geo::TZ) % Geo::TY, tx = n / (Geo::TZ * Geo::TY);
+        const int i0 = max(0, tx - (Geo::BX - 1)), i1 = min(2, tx), j0 = max(0, ty - (Geo::BY - 1)), j1 = min(2, ty),
+                  k0 = max(0, tz - (Geo::BZ - 1)), k1 = min(2, tz);
+        double sum[CH2];
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) sum[ch] = 0.0;
-        for (int e = e0; e < e1; ++e) {
-            const int src = table[Geo::TILE + 1 + e];
+        for (int ch = 0; ch < CH2; ++ch) sum[ch] = 0.0;
+        for (int pi = i0; pi <= i1; ++pi)
+            for (int j = j0; j <= j1; ++j) {
+                int src = (j * 3 + k0) * THREADS + (((((tx - pi) << Geo::yb) | (ty - j)) << Geo::zb) | (tz - k0)) * 3 + pi;
+                for (int k = k0; k <= k1; ++k, src += THREADS - 3) {
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) sum[ch] += cs_smem[ch * 9 * THREADS + src];
-        }
+                    for (int ch = 0; ch < CH2; ++ch)
+                        if (c0 + ch < NCH) sum[ch] += cs_smem[(c0 + ch) * 9 * THREADS + src];
+                }
+            }
         const long a = Policy::DOF ? (long)tile_dof[(size_t)g * Geo::TILE + n] : tile_to_grid(n, s_nbr);
         if (a >= 0) {
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch)
-                if (sum[ch] != 0.0) Policy::flush1(args, a, ch, sum[ch]);
+            for (int ch = 0; ch < CH2; ++ch)
+                if (c0 + ch < NCH && sum[ch] != 0.0) Policy::flush1(args, a, c0 + ch, sum[ch]);
         }
     }
 }
@@ -395,19 +355,11 @@ template <class Policy>
 int launch_plane2_scatter(Sim* s, const typename Policy::Args& a)
 {
     if (s->g1 <= s->g0) return 0;
-    if (!s->ps_table_ready) {
-        short tab[PS_TABLE_LEN];
-        ps_build_table(tab);
-        HOT_CUDA(s->ps_table.reserve(PS_TABLE_LEN));
-        HOT_CUDA(cudaMemcpyAsync(s->ps_table.p, tab, sizeof tab, cudaMemcpyHostToDevice, s->stream));
-        HOT_CUDA(cudaStreamSynchronize(s->stream)); // tab is a stack array
-        s->ps_table_ready = true;
-    }
     static const cudaError_t attr = cudaFuncSetAttribute(k_plane2_scatter<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
         (int)ps_smem_bytes<Policy>());
     HOT_CUDA(attr);
     k_plane2_scatter<Policy><<<(unsigned)(s->g1 - s->g0), PS_THREADS, ps_smem_bytes<Policy>(), s->stream>>>(a,
-        s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0, s->nbr8.p, s->ps_table.p,
+        s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0, s->nbr8.p,
         Policy::DOF ? s->tile_dof.p + (size_t)s->g0 * Geo::TILE : nullptr, pf_distance(s, 3));
     HOT_LAUNCHED(s);
     return 0;

@@ -183,8 +183,6 @@ struct Sim {
     DevBuf<double> dv, vn, mass_matrix;
 
     int pf_dist = -1; // L2 prefetch distance of the per-group kernels in CTAs (-1: default = one wave of resident CTAs; 0: off; HOT_PF_DIST)
-    DevBuf<short> cs_table, ps_table; // combine tables of the column / plane scatter (scatter.cuh)
-    bool cs_table_ready = false, ps_table_ready = false;
     DevBuf<int> flags; // g2p CFL flags
     // plasticity applied after G2P + evolveStrain (MpmSimulationBase.cpp:1039-1064): 0 none, 1 VonMisesFixedCorotated, 2 SnowPlasticity
     int plastic_model = 0;
