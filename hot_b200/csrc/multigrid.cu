@@ -271,6 +271,77 @@ __global__ void k_colrank(long n_entries, const int* __restrict__ col, const int
     if (t < n_entries) colrank[t] = rank[col[t]];
 }
 
+// ---- Gauss-Seidel row stream --------------------------------------------------------------------------------------------
+// A sweep only uses the couplings of a row to nodes that come EARLIER (forward) or LATER (backward) in the sweep order - about
+// half of the 125 slots each - but which slots those are depends on the rank of the neighbours, so the fixed-slot row has to be
+// read whole (all of its sectors are touched).  The stream stores, per sweep position p and direction, only the entries that
+// direction uses, compacted into chunks of 32 (code[32] + 9 x value[32], the coalesced layout of the fixed rows):
+//   code >= 0   the neighbour is final when the row's block is swept (other block): its DOF id
+//   code <  0   the neighbour belongs to the row's own 4^3 block: -(sweep-local index in that direction) - 1
+// Padding entries carry code = GS_PAD (skipped) and zero blocks.  ~2.3 chunks per row and direction instead of 4.
+constexpr int GS_PAD = -2147483647 - 1;
+__global__ void k_gs_pblock(int n_blocks, const int* __restrict__ block_start, int* __restrict__ pblock)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    for (int p = block_start[b]; p < block_start[b + 1]; ++p) pblock[p] = b;
+}
+// pass 0 (fill == false): chunk counts per position; pass 1: the entries.  One warp per sweep position.
+template <bool FILL>
+__global__ void __launch_bounds__(TPB) k_gs_stream(int n, const int* __restrict__ seq, const int* __restrict__ rank, const int* __restrict__ pblock,
+    const int* __restrict__ block_start, const int* __restrict__ col, const double* __restrict__ val, int* __restrict__ cntF,
+    int* __restrict__ cntB, const int* __restrict__ offF, const int* __restrict__ offB, int* __restrict__ codeF, double* __restrict__ svalF,
+    int* __restrict__ codeB, double* __restrict__ svalB)
+{
+    const int p = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (p >= n) return;
+    const int i = seq[p], b = pblock[p], ps = block_start[b], pe = block_start[b + 1];
+    int nF = 0, nB = 0;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int t = 0; t < W / 32; ++t) {
+        const int sl = lane + 32 * t;
+        const int j = col[(size_t)i * W + sl];
+        const int rj = (sl < 125 && j != i) ? rank[j] : p; // self / absent / padding slots: in neither set
+        const bool f = rj < p, bk = rj > p;
+        const unsigned mf = __ballot_sync(0xffffffffu, f), mb = __ballot_sync(0xffffffffu, bk);
+        if (FILL) {
+            if (f || bk) {
+                const int e = f ? nF + __popc(mf & lt) : nB + __popc(mb & lt);
+                const size_t c = (size_t)(f ? offF[p] : offB[p]) + (e >> 5);
+                const int l = e & 31;
+                const bool inblock = rj >= ps && rj < pe;
+                const int code = !inblock ? j : -((f ? rj - ps : pe - 1 - rj) + 1);
+                (f ? codeF : codeB)[c * 32 + l] = code;
+                double* dst = (f ? svalF : svalB) + c * 9 * 32 + l;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) dst[q * 32] = val[((size_t)i * 9 + q) * W + sl];
+            }
+        }
+        nF += __popc(mf);
+        nB += __popc(mb);
+    }
+    if (!FILL) {
+        if (lane == 0) {
+            cntF[p] = (nF + 31) >> 5;
+            cntB[p] = (nB + 31) >> 5;
+        }
+        return;
+    }
+    // pad the last chunk of either direction
+    for (int d = 0; d < 2; ++d) {
+        const int cnt = d ? nB : nF, e = cnt + lane;
+        if ((cnt & 31) != 0 && (e >> 5) == (cnt >> 5)) {
+            const size_t c = (size_t)(d ? offB[p] : offF[p]) + (e >> 5);
+            const int l = e & 31;
+            (d ? codeB : codeF)[c * 32 + l] = GS_PAD;
+            double* dst = (d ? svalB : svalF) + c * 9 * 32 + l;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) dst[q * 32] = 0.0;
+        }
+    }
+}
+
 // ---- operators ---------------------------------------------------------------------------------------------------------
 // SquareMatrix::multiply: one warp per block row.  mode 0: b = A x; mode 1: b -= A x
 template <int MODE>
@@ -413,11 +484,14 @@ struct GSShared {
     double s_x[2 * GS_HALF][3];
 };
 
-template <bool FWD, int THREADS>
+template <bool FWD, int THREADS, bool STREAM>
 __device__ __forceinline__ void gs_block_body(GSShared& sh, int b, const int* __restrict__ block_start, const int* __restrict__ seq,
     const int* __restrict__ colrank, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ dinv,
-    const double* __restrict__ diag, const double* rhs, double* out, double* out_scaled)
+    const double* __restrict__ diag, const double* rhs, double* out, double* out_scaled, const int* __restrict__ soff,
+    const int* __restrict__ scode, const double* __restrict__ sval)
 {
+    // STREAM: the rows come from the per-direction stream (k_gs_stream: only the entries this sweep direction uses,
+    // chunks of 32), otherwise from the fixed 125-slot rows with the rank test per slot
     double (&Lt)[9][GS_PAIRS] = sh.Lt;
     double (&s_rhs)[GS_HALF][3] = sh.s_rhs;
     double (&s_x)[2 * GS_HALF][3] = sh.s_x;
@@ -437,7 +511,7 @@ __device__ __forceinline__ void gs_block_body(GSShared& sh, int b, const int* __
         // trips: memory-level parallelism per warp is what bounds this phase on the coarse levels).
         constexpr int NW = THREADS / 32;
         for (int il0 = warp; il0 < hn; il0 += 2 * NW) {
-            int il_[2], i_[2], gl_[2], jj[2][W / 32], rr[2][W / 32];
+            int il_[2], i_[2], gl_[2], jj[2][W / 32], rr[2][W / 32], c0_[2], nc_[2];
             bool on[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -446,13 +520,22 @@ __device__ __forceinline__ void gs_block_body(GSShared& sh, int b, const int* __
                 gl_[u] = h0 + il_[u];
                 const int p = FWD ? ps + gl_[u] : pe - 1 - gl_[u];
                 i_[u] = on[u] ? seq[p] : 0;
+                c0_[u] = (STREAM && on[u]) ? soff[p] : 0;
+                nc_[u] = (STREAM && on[u]) ? soff[p + 1] - c0_[u] : 0;
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u)
 #pragma unroll
                 for (int t = 0; t < W / 32; ++t) {
-                    jj[u][t] = on[u] ? col[(size_t)i_[u] * W + lane + 32 * t] : 0;
-                    rr[u][t] = on[u] ? colrank[(size_t)i_[u] * W + lane + 32 * t] : 0;
+                    if (STREAM) {
+                        // jj = code of the entry (>= 0: DOF id of a final neighbour, < 0: -(sweep-local index) - 1); rr unused
+                        jj[u][t] = t < nc_[u] ? scode[((size_t)c0_[u] + t) * 32 + lane] : 0;
+                        rr[u][t] = 0;
+                    }
+                    else {
+                        jj[u][t] = on[u] ? col[(size_t)i_[u] * W + lane + 32 * t] : 0;
+                        rr[u][t] = on[u] ? colrank[(size_t)i_[u] * W + lane + 32 * t] : 0;
+                    }
                 }
             double Dm[2][9];
 #pragma unroll
@@ -470,10 +553,14 @@ __device__ __forceinline__ void gs_block_body(GSShared& sh, int b, const int* __
                     acc[t][0] = acc[t][1] = acc[t][2] = 0.0;
                     const int sl = lane + 32 * t;
                     const int j = jj[u][t];
-                    const int kl = FWD ? rr[u][t] - ps : pe - 1 - rr[u][t]; // < 0: final before this block; [0, gl): earlier in this block
-                    if (kl < gl) {
-                        const double v0 = v[sl], v1 = v[W + sl], v2 = v[2 * W + sl], v3 = v[3 * W + sl], v4 = v[4 * W + sl], v5 = v[5 * W + sl],
-                                     v6 = v[6 * W + sl], v7 = v[7 * W + sl], v8 = v[8 * W + sl];
+                    // kl < 0: final before this block; [0, gl): earlier in this block
+                    const int kl = STREAM ? (j >= 0 ? -1 : -j - 1) : (FWD ? rr[u][t] - ps : pe - 1 - rr[u][t]);
+                    if (STREAM ? (t < nc_[u] && j != GS_PAD) : kl < gl) {
+                        // entry q of this lane's block: stream chunk (c0 + t), lane-major per entry, or slot sl of the fixed row
+                        const double* vp = STREAM ? sval + ((size_t)c0_[u] + t) * 9 * 32 + lane : v + sl;
+                        const int vs = STREAM ? 32 : W;
+                        const double v0 = vp[0], v1 = vp[vs], v2 = vp[2 * vs], v3 = vp[3 * vs], v4 = vp[4 * vs], v5 = vp[5 * vs],
+                                     v6 = vp[6 * vs], v7 = vp[7 * vs], v8 = vp[8 * vs];
                         if (kl < h0) {
                             double x0, x1, x2;
                             if (kl < 0) {
@@ -561,33 +648,39 @@ struct GSArgs {
     const double *val, *dinv, *diag;
     double *r, *hdu, *dhdu, *du, *u;
     int fuse_update; // u += du, r -= A du in the same launch (no BC projection needed on this level)
+    const int *soff[2], *scode[2]; // per-direction row stream (null: fixed rows); [0] forward, [1] backward
+    const double* sval[2];
 };
 
 // One colour phase as its own launch (fallback when a cooperative launch is not possible)
-template <bool FWD>
+template <bool FWD, bool STREAM>
 __global__ void __launch_bounds__(GS_THREADS, 3) k_gs_block(int b0, GSArgs a)
 {
     __shared__ GSShared sh;
-    if (FWD) gs_block_body<true, GS_THREADS>(sh, b0 + blockIdx.x, a.block_start, a.seq, a.colrank, a.col, a.val, a.dinv, a.diag, a.r, a.hdu, a.dhdu);
-    else gs_block_body<false, GS_THREADS>(sh, b0 + blockIdx.x, a.block_start, a.seq, a.colrank, a.col, a.val, a.dinv, a.diag, a.dhdu, a.du, nullptr);
+    if (FWD)
+        gs_block_body<true, GS_THREADS, STREAM>(sh, b0 + blockIdx.x, a.block_start, a.seq, a.colrank, a.col, a.val, a.dinv, a.diag, a.r, a.hdu, a.dhdu,
+            a.soff[0], a.scode[0], a.sval[0]);
+    else
+        gs_block_body<false, GS_THREADS, STREAM>(sh, b0 + blockIdx.x, a.block_start, a.seq, a.colrank, a.col, a.val, a.dinv, a.diag, a.dhdu, a.du, nullptr,
+            a.soff[1], a.scode[1], a.sval[1]);
 }
 
 // The whole symmetric sweep of gs_smooth in ONE cooperative launch: 8 forward colour phases, 8 backward ones, then
 // u += du, r -= A du, separated by grid barriers instead of 17 dependent launches (on the coarse levels a phase is a
 // handful of blocks, so launch gaps and ramp-up dominated the smoother).
-template <int THREADS>
+template <int THREADS, bool STREAM>
 __global__ void __launch_bounds__(THREADS) k_gs_sweep(GSArgs a)
 {
     __shared__ GSShared sh;
     cg::grid_group grid = cg::this_grid();
     for (int c = 0; c < 8; ++c) {
         for (int b = a.cfb[c] + blockIdx.x; b < a.cfb[c + 1]; b += gridDim.x)
-            gs_block_body<true, THREADS>(sh, b, a.block_start, a.seq, a.colrank, a.col, a.val, a.dinv, a.diag, a.r, a.hdu, a.dhdu);
+            gs_block_body<true, THREADS, STREAM>(sh, b, a.block_start, a.seq, a.colrank, a.col, a.val, a.dinv, a.diag, a.r, a.hdu, a.dhdu, a.soff[0], a.scode[0], a.sval[0]);
         grid.sync();
     }
     for (int c = 7; c >= 0; --c) {
         for (int b = a.cfb[c] + blockIdx.x; b < a.cfb[c + 1]; b += gridDim.x)
-            gs_block_body<false, THREADS>(sh, b, a.block_start, a.seq, a.colrank, a.col, a.val, a.dinv, a.diag, a.dhdu, a.du, nullptr);
+            gs_block_body<false, THREADS, STREAM>(sh, b, a.block_start, a.seq, a.colrank, a.col, a.val, a.dinv, a.diag, a.dhdu, a.du, nullptr, a.soff[1], a.scode[1], a.sval[1]);
         grid.sync();
     }
     if (!a.fuse_update) return;
@@ -716,7 +809,7 @@ int build_gs_schedule(Sim* s, MGLevel& L)
     HOT_CUDA(s->cand_val.reserve(n));
     HOT_CUDA(s->cand_val_alt.reserve(n));
     HOT_CUDA(s->head_flag.reserve(n));
-    HOT_CUDA(s->scratch_i.reserve(2 * (size_t)n + 2));
+    HOT_CUDA(s->scratch_i.reserve(2 * (size_t)n + 4));
     HOT_CUDA(s->keys_alt.reserve(2 * (size_t)n));
     HOT_CUDA(s->dcount.reserve(16));
     HOT_CUDA(L.gs_seq.reserve(n));
@@ -767,6 +860,33 @@ int build_gs_schedule(Sim* s, MGLevel& L)
     HOT_CUDA(cudaStreamSynchronize(st)); // &n is a stack variable
     L.color_first_block[0] = 0;
     for (int c = 0; c < 8; ++c) L.color_first_block[c + 1] = L.color_first_block[c] + s->hcount[1 + c];
+    // the per-direction row stream of the sweeps
+    HOT_CUDA(L.gs_pblock.reserve(n));
+    HOT_CUDA(L.gs_off[0].reserve((size_t)n + 1));
+    HOT_CUDA(L.gs_off[1].reserve((size_t)n + 1));
+    int* cntF = s->scratch_i.p;
+    int* cntB = s->scratch_i.p + n + 1;
+    k_gs_pblock<<<nblk(L.n_blocks), TPB, 0, st>>>(L.n_blocks, L.gs_block_start.p, L.gs_pblock.p);
+    HOT_LAUNCHED(s);
+    HOT_CUDA(cudaMemsetAsync(s->scratch_i.p, 0, (2 * (size_t)n + 2) * sizeof(int), st));
+    k_gs_stream<false><<<nblk(32L * n), TPB, 0, st>>>(n, L.gs_seq.p, L.gs_rank.p, L.gs_pblock.p, L.gs_block_start.p, L.col.p, L.val.p, cntF, cntB,
+        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    HOT_LAUNCHED(s);
+    for (int d = 0; d < 2; ++d) {
+        int* cnt = d ? cntB : cntF;
+        rc = with_tmp(s, [&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt, L.gs_off[d].p, n + 1, st); });
+        if (rc) return rc;
+        HOT_CUDA(cudaMemcpyAsync(s->hcount + 10 + d, L.gs_off[d].p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    HOT_CUDA(cudaStreamSynchronize(st));
+    for (int d = 0; d < 2; ++d) {
+        L.gs_chunks[d] = s->hcount[10 + d];
+        HOT_CUDA(L.gs_code[d].reserve((size_t)L.gs_chunks[d] * 32 + 32));
+        HOT_CUDA(L.gs_sval[d].reserve((size_t)L.gs_chunks[d] * 9 * 32 + 32));
+    }
+    k_gs_stream<true><<<nblk(32L * n), TPB, 0, st>>>(n, L.gs_seq.p, L.gs_rank.p, L.gs_pblock.p, L.gs_block_start.p, L.col.p, L.val.p, nullptr, nullptr,
+        L.gs_off[0].p, L.gs_off[1].p, L.gs_code[0].p, L.gs_sval[0].p, L.gs_code[1].p, L.gs_sval[1].p);
+    HOT_LAUNCHED(s);
     return 0;
 }
 
@@ -943,7 +1063,7 @@ int smooth_cg(Sim* s, int level, double* u, double* r, int iterations)
     s->last_cg_iters = cnt;
     return 0;
 }
-template <int THREADS>
+template <int THREADS, bool STREAM>
 int launch_gs_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
 {
     static int per_sm = -1, n_sm = 0;
@@ -952,7 +1072,7 @@ int launch_gs_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gs_sweep<THREADS>, THREADS, 0) != cudaSuccess || !coop) per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gs_sweep<THREADS, STREAM>, THREADS, 0) != cudaSuccess || !coop) per_sm = 0;
     }
     *launched = false;
     if (per_sm <= 0) return 0;
@@ -960,7 +1080,7 @@ int launch_gs_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
     if (a.fuse_update) grid = std::max(grid, std::min(per_sm * n_sm, (a.n + THREADS / 32 - 1) / (THREADS / 32)));
     if (grid < 1) grid = 1;
     void* params[] = {&a};
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_gs_sweep<THREADS>, dim3(grid), dim3(THREADS), params, 0, s->stream);
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_gs_sweep<THREADS, STREAM>, dim3(grid), dim3(THREADS), params, 0, s->stream);
     if (e != cudaSuccess) {
         cudaGetLastError(); // clear; fall back to per-phase launches
         per_sm = 0;
@@ -987,6 +1107,12 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
     a.val = L.val.p; a.dinv = L.dinv.p; a.diag = L.diag.p;
     a.r = r; a.hdu = L.tmp.p; a.dhdu = L.dAu.p; a.du = L.du.p; a.u = u; // hdu: unscaled forward solution; dhdu = D hdu
     a.fuse_update = project ? 0 : 1;
+    static const bool use_stream = !(getenv("HOT_GS_STREAM") && atoi(getenv("HOT_GS_STREAM")) == 0); // A/B switch, default on
+    for (int d = 0; d < 2; ++d) {
+        a.soff[d] = use_stream ? L.gs_off[d].p : nullptr;
+        a.scode[d] = use_stream ? L.gs_code[d].p : nullptr;
+        a.sval[d] = use_stream ? L.gs_sval[d].p : nullptr;
+    }
     iterations = (iterations + 1) >> 1;
     static long long* dbg_dev = nullptr;
     const char* dbg_env = getenv("HOT_GS_DEBUG");
@@ -1005,19 +1131,20 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         // (many blocks per colour: the per-phase launches below keep 3 CTAs per SM busy, which measures faster than the
         //  cooperative form whose register budget allows only 2)
         static const bool force_coop = getenv("HOT_GS_COOP") != nullptr;
-        if (max_blocks <= 2 * 148) RC(launch_gs_sweep<512>(s, a, max_blocks, &launched));
-        else if (force_coop) RC(launch_gs_sweep<GS_THREADS>(s, a, max_blocks, &launched));
+        if (max_blocks <= 2 * 148) RC((use_stream ? launch_gs_sweep<512, true>(s, a, max_blocks, &launched) : launch_gs_sweep<512, false>(s, a, max_blocks, &launched)));
+        else if (force_coop)
+            RC((use_stream ? launch_gs_sweep<GS_THREADS, true>(s, a, max_blocks, &launched) : launch_gs_sweep<GS_THREADS, false>(s, a, max_blocks, &launched)));
         if (!launched) {
             for (int c = 0; c < 8; ++c) {
                 const int b0 = a.cfb[c], b1 = a.cfb[c + 1];
                 if (b1 == b0) continue;
-                k_gs_block<true><<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
+                (use_stream ? k_gs_block<true, true> : k_gs_block<true, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
                 HOT_LAUNCHED(s);
             }
             for (int c = 7; c >= 0; --c) {
                 const int b0 = a.cfb[c], b1 = a.cfb[c + 1];
                 if (b1 == b0) continue;
-                k_gs_block<false><<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
+                (use_stream ? k_gs_block<false, true> : k_gs_block<false, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
                 HOT_LAUNCHED(s);
             }
             if (!project) {

@@ -96,6 +96,10 @@ struct MGLevel {
     DevBuf<double> diag, dinv; // 9n each: D_i (column-major) and its inverse (block or entry-wise, -Ainv)
     // 8-colour 4^3-block Gauss-Seidel schedule (MultigridPreconditioner.h:582-605)
     DevBuf<int> gs_colrank; // rank of col[i*128+s], same layout as col
+    // per-direction row stream of the sweeps (multigrid.cu: k_gs_stream): chunk offsets per sweep position, codes, values
+    DevBuf<int> gs_pblock, gs_off[2], gs_code[2];
+    DevBuf<double> gs_sval[2];
+    int gs_chunks[2] = {0, 0};
     DevBuf<int> gs_seq, gs_rank, gs_block_start; // node ids in sweep order; rank of a node; block b = gs_seq[start[b]..start[b+1])
     int n_blocks = 0;
     int color_first_block[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
