@@ -613,16 +613,28 @@ __device__ __forceinline__ void gs_block_body(GSShared& sh, int b, const int* __
                 node = seq[FWD ? ps + h0 + lane : pe - 1 - (h0 + lane)];
                 r0 = s_rhs[lane][0]; r1 = s_rhs[lane][1]; r2 = s_rhs[lane][2];
             }
+            // the coupling blocks of pivot k + 1 are fetched from shared memory while pivot k's update runs (they do not depend
+            // on x), so a step's critical path is shuffle -> 3-deep FMA chain only
+            double l[9], ln[9];
+            const bool row = lane < hn;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) l[q] = (row && lane > 0) ? Lt[q][gs_pair(lane, 0)] : 0.0;
+            int en = lane - 1; // gs_pair(lane, k + 1) kept incrementally: gs_pair(l, k + 1) - gs_pair(l, k) = GS_HALF - 2 - k
             for (int k = 0; k < hn; ++k) {
+                const bool nxt = row && lane > k + 1 && k + 1 < hn;
+                en += GS_HALF - 2 - k;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) ln[q] = nxt ? Lt[q][en] : 0.0; // (en is only in range where nxt holds)
                 const double x0 = __shfl_sync(0xffffffffu, r0, k);
                 const double x1 = __shfl_sync(0xffffffffu, r1, k);
                 const double x2 = __shfl_sync(0xffffffffu, r2, k);
-                if (lane > k && lane < hn) {
-                    const int e = gs_pair(lane, k);
-                    r0 = fma(-Lt[6][e], x2, fma(-Lt[3][e], x1, fma(-Lt[0][e], x0, r0)));
-                    r1 = fma(-Lt[7][e], x2, fma(-Lt[4][e], x1, fma(-Lt[1][e], x0, r1)));
-                    r2 = fma(-Lt[8][e], x2, fma(-Lt[5][e], x1, fma(-Lt[2][e], x0, r2)));
+                if (lane > k) { // (l = 0 on lanes >= hn)
+                    r0 = fma(-l[6], x2, fma(-l[3], x1, fma(-l[0], x0, r0)));
+                    r1 = fma(-l[7], x2, fma(-l[4], x1, fma(-l[1], x0, r1)));
+                    r2 = fma(-l[8], x2, fma(-l[5], x1, fma(-l[2], x0, r2)));
                 }
+#pragma unroll
+                for (int q = 0; q < 9; ++q) l[q] = ln[q];
             }
             const double mx0 = r0, mx1 = r1, mx2 = r2;
             if (lane < hn) {
@@ -650,7 +662,49 @@ struct GSArgs {
     int fuse_update; // u += du, r -= A du in the same launch (no BC projection needed on this level)
     const int *soff[2], *scode[2]; // per-direction row stream (null: fixed rows); [0] forward, [1] backward
     const double* sval[2];
+    const int* pblock; // block of every sweep position
+    int stream_update; // the tail uses r_new = L (hdu - du) from the forward stream
 };
+
+// Tail of gs_smooth (u += du, r -= A du, MultigridPreconditioner.h:311-314) from the forward stream.  With (D + L) hdu = r and
+// (D + U) du = D hdu (the two sweeps, L / U = couplings to earlier / later nodes of the sweep order):
+//   r - A du = (D + L) hdu - L du - (D + U) du = L (hdu - du),
+// so the new residual needs only the LOWER couplings - exactly the forward stream, about half of the bytes of the full rows.
+// Holds when Dinv is the inverse of the diagonal block (-Ainv 1) and no BC projection sits between A du and r.
+__device__ __forceinline__ void gs_stream_update_row(const GSArgs& a, int p, int lane)
+{
+    const int i = a.seq[p], ps = a.block_start[a.pblock[p]];
+    const int c0 = a.soff[0][p], c1 = a.soff[0][p + 1];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int c = c0; c < c1; ++c) {
+        const int code = a.scode[0][(size_t)c * 32 + lane];
+        if (code != GS_PAD) {
+            const int j = code >= 0 ? code : a.seq[ps - code - 1];
+            const double x0 = a.hdu[3 * (size_t)j] - a.du[3 * (size_t)j], x1 = a.hdu[3 * (size_t)j + 1] - a.du[3 * (size_t)j + 1],
+                         x2 = a.hdu[3 * (size_t)j + 2] - a.du[3 * (size_t)j + 2];
+            const double* v = a.sval[0] + (size_t)c * 9 * 32 + lane;
+            a0 += v[0] * x0 + v[3 * 32] * x1 + v[6 * 32] * x2;
+            a1 += v[32] * x0 + v[4 * 32] * x1 + v[7 * 32] * x2;
+            a2 += v[2 * 32] * x0 + v[5 * 32] * x1 + v[8 * 32] * x2;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o);
+        a1 += __shfl_down_sync(0xffffffffu, a1, o);
+        a2 += __shfl_down_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+        const size_t o = 3 * (size_t)i;
+        a.r[o] = a0; a.r[o + 1] = a1; a.r[o + 2] = a2;
+        a.u[o] += a.du[o]; a.u[o + 1] += a.du[o + 1]; a.u[o + 2] += a.du[o + 2];
+    }
+}
+__global__ void __launch_bounds__(TPB) k_gs_stream_update(GSArgs a)
+{
+    const int p = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (p < a.n) gs_stream_update_row(a, p, threadIdx.x & 31);
+}
 
 // One colour phase as its own launch (fallback when a cooperative launch is not possible)
 template <bool FWD, bool STREAM>
@@ -686,6 +740,10 @@ __global__ void __launch_bounds__(THREADS) k_gs_sweep(GSArgs a)
     if (!a.fuse_update) return;
     const int lane = threadIdx.x & 31;
     const long nwarps = (long)gridDim.x * (THREADS / 32);
+    if (STREAM && a.stream_update) {
+        for (long p = (long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); p < a.n; p += nwarps) gs_stream_update_row(a, (int)p, lane);
+        return;
+    }
     for (long row = (long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); row < a.n; row += nwarps) {
         const int* c = a.col + (size_t)row * W;
         const double* v = a.val + (size_t)row * 9 * W;
@@ -1113,6 +1171,9 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         a.scode[d] = use_stream ? L.gs_code[d].p : nullptr;
         a.sval[d] = use_stream ? L.gs_sval[d].p : nullptr;
     }
+    a.pblock = L.gs_pblock.p;
+    static const bool no_ident = getenv("HOT_GS_STREAM_UPDATE") && atoi(getenv("HOT_GS_STREAM_UPDATE")) == 0; // A/B switch
+    a.stream_update = (use_stream && !project && s->mg_Ainv == 1 && !no_ident) ? 1 : 0;
     iterations = (iterations + 1) >> 1;
     static long long* dbg_dev = nullptr;
     const char* dbg_env = getenv("HOT_GS_DEBUG");
@@ -1148,7 +1209,8 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
                 HOT_LAUNCHED(s);
             }
             if (!project) {
-                k_spmv_update<<<nblk(32L * L.n), TPB, 0, st>>>(L.n, L.col.p, L.val.p, L.du.p, u, r);
+                if (a.stream_update) k_gs_stream_update<<<nblk(32L * L.n), TPB, 0, st>>>(a);
+                else k_spmv_update<<<nblk(32L * L.n), TPB, 0, st>>>(L.n, L.col.p, L.val.p, L.du.p, u, r);
                 HOT_LAUNCHED(s);
             }
         }
