@@ -7,14 +7,12 @@ hdr, units = rows[0], rows[1]
 def col(name):
     return hdr.index(name) if name in hdr else None
 want = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "MB rd"), ("dram__bytes_write.sum", "MB wr"),
-        ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram%"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"), ("launch__registers_per_thread", "regs"),
         ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64%"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
         ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem conflicts"),
-        ("lts__t_sector_hit_rate.pct", "L2hit%"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
-        ("smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "stall_lsb"),
-        ("smsp__average_warp_latency_issue_stalled_barrier.ratio", "stall_bar")]
+        ("lts__t_sector_hit_rate.pct", "L2hit%"), ("launch__grid_size", "grid"), ("launch__block_size", "block")]
 def conv(v, u, name):
     try:
         x = float(v.replace(",", ""))
