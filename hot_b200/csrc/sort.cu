@@ -222,23 +222,32 @@ __global__ void __launch_bounds__(32 * NM_WARPS) k_page_masks(int n_pages, const
     unsigned* __restrict__ mask, int* __restrict__ base, int* __restrict__ done, int* __restrict__ total, volatile int* total_host)
 {
     const int page = blockIdx.x * NM_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    __shared__ int s_cnt[NM_WARPS];
     if (page < n_pages) {
         const size_t a = (size_t)page * Geo::E + lane;
         const unsigned b = __ballot_sync(0xffffffffu, flag ? flag[a] != 0 : m[a] != 0.0);
         if (lane == 0) {
             mask[page] = b;
-            base[page] = __popc(b);
+            s_cnt[threadIdx.x >> 5] = __popc(b);
         }
     }
+    else if (lane == 0) s_cnt[threadIdx.x >> 5] = 0;
     __shared__ int s_last;
     __shared__ int s_part[32 * NM_WARPS];
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < NM_WARPS; ++w) t += s_cnt[w];
+        base[blockIdx.x] = t; // node count of this CTA's NM_WARPS pages; turned into an exclusive offset by the last CTA
+        __threadfence();
+        s_last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+    }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // exclusive scan of base[0..n_pages) by this CTA: super-tiles of T x NM_ITEMS counts, all loads of a super-tile in flight
+    n_pages = gridDim.x; // from here on: exclusive scan over the per-CTA counts (8x fewer than pages)
+    // exclusive scan of base[0..n) by this CTA: super-tiles of T x NM_ITEMS counts, all loads of a super-tile in flight
     // together (coalesced), one warp-shuffle block scan per row of T
     constexpr int T = 32 * NM_WARPS;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -284,12 +293,19 @@ __global__ void __launch_bounds__(32 * NM_WARPS) k_number_and_normalise(int n_pa
     const int* __restrict__ base, double* __restrict__ m, double* __restrict__ v, int* __restrict__ idx, int* __restrict__ dof_slot,
     double* __restrict__ mass_matrix, double* __restrict__ vn)
 {
-    const int page = blockIdx.x * NM_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, page = blockIdx.x * NM_WARPS + warp, lane = threadIdx.x & 31;
     if (page >= n_pages) return;
     const size_t a = (size_t)page * Geo::E + lane;
-    const unsigned b = mask[page];
+    // offset of this page = exclusive offset of the CTA (k_page_masks) + the node counts of the CTA's earlier pages
+    const int pw = blockIdx.x * NM_WARPS + lane;
+    const unsigned mw = (lane < NM_WARPS && pw < n_pages) ? mask[pw] : 0u;
+    int before = lane < warp ? __popc(mw) : 0;
+#pragma unroll
+    for (int o = NM_WARPS / 2; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    before = __shfl_sync(0xffffffffu, before, 0); // lanes 0..NM_WARPS-1 hold the sum
+    const unsigned b = __shfl_sync(0xffffffffu, mw, warp);
     if (b >> lane & 1u) {
-        const int id = base[page] + __popc(b & ((1u << lane) - 1u));
+        const int id = base[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u));
         const double mm = m[a];
         idx[a] = id;
         dof_slot[id] = (int)a;
