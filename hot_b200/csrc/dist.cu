@@ -70,19 +70,24 @@ __global__ void k_unpack_pages(int n_ip, const int* __restrict__ ipage, size_t g
 }
 // per page: bit e set when node e carries mass (as a double: exact for 32 bits; the MAX over ranks is the complete mask
 // because every rank that touches a page holds its complete mass after the interface exchange, the others hold 0)
+// node masks of the pages that exactly ONE rank touches, contributed by that rank (the others add 0: a SUM all-reduce carries
+// them next to the interface pages' mass / momentum); pages touched by >= 2 ranks get their mask from the summed mass instead
 __global__ void k_page_nonzero(long n_pages, const double* __restrict__ g_m, const unsigned* __restrict__ mask, int rank, double* __restrict__ out)
 {
     const long pg = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (pg >= n_pages) return;
     unsigned bits = 0;
-    if (mask[pg] & (1u << rank))
+    if (mask[pg] == (1u << rank))
         for (int e = 0; e < Geo::E; ++e) bits |= (g_m[(size_t)pg * Geo::E + e] != 0.0 ? 1u : 0u) << e;
     out[pg] = (double)bits;
 }
-__global__ void k_flags_from_bits(long gn, const double* __restrict__ bits, int* __restrict__ flag)
+__global__ void k_flags_from_bits(long gn, const double* __restrict__ bits, const unsigned* __restrict__ mask, const double* __restrict__ g_m,
+    int* __restrict__ flag)
 {
     const long a = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a < gn) flag[a] = (((unsigned)bits[a / Geo::E]) >> (a % Geo::E)) & 1u;
+    if (a >= gn) return;
+    const long pg = a / Geo::E;
+    flag[a] = __popc(mask[pg]) >= 2 ? (g_m[a] != 0.0) : ((((unsigned)bits[pg]) >> (a % Geo::E)) & 1u);
 }
 __global__ void k_ipage_flags(long n_pages, const unsigned* __restrict__ mask, int* __restrict__ flag)
 {
@@ -171,21 +176,21 @@ int dist_p2g_exchange(Sim* s, int* node_flags /* n_pages * E, out */)
     cudaStream_t st = s->stream;
     const long cnt = (long)s->n_iface_pages * 4 * Geo::E;
     KTime t(s, KC_TRANSFER);
+    // ONE sum all-reduce: [interface pages: m, mv] [one node mask per page from the page's only toucher]
+    int rc = reserve_xbuf(s, cnt + s->n_pages);
+    if (rc) return rc;
     if (cnt > 0) {
-        int rc = reserve_xbuf(s, cnt);
-        if (rc) return rc;
         k_pack_pages<<<nblk(cnt), TPB, 0, st>>>(s->n_iface_pages, s->iface_page.p, s->g_stride, s->g_m.p, s->g_v.p, s->xbuf);
         HOT_LAUNCHED(s);
-        if (s->allreduce(s->allreduce_user, 0, cnt) != 0) return fail(s, "all-reduce callback failed");
+    }
+    k_page_nonzero<<<nblk(s->n_pages), TPB, 0, st>>>(s->n_pages, s->g_m.p, s->page_mask.p, s->rank, s->xbuf + cnt);
+    HOT_LAUNCHED(s);
+    if (s->allreduce(s->allreduce_user, 0, cnt + s->n_pages) != 0) return fail(s, "all-reduce callback failed");
+    if (cnt > 0) {
         k_unpack_pages<<<nblk(cnt), TPB, 0, st>>>(s->n_iface_pages, s->iface_page.p, s->g_stride, s->xbuf, s->g_m.p, s->g_v.p);
         HOT_LAUNCHED(s);
     }
-    int rc = reserve_xbuf(s, s->n_pages);
-    if (rc) return rc;
-    k_page_nonzero<<<nblk(s->n_pages), TPB, 0, st>>>(s->n_pages, s->g_m.p, s->page_mask.p, s->rank, s->xbuf);
-    HOT_LAUNCHED(s);
-    if (s->allreduce(s->allreduce_user, 1, s->n_pages) != 0) return fail(s, "all-reduce callback failed");
-    k_flags_from_bits<<<nblk((long)s->g_stride), TPB, 0, st>>>((long)s->g_stride, s->xbuf, node_flags);
+    k_flags_from_bits<<<nblk((long)s->g_stride), TPB, 0, st>>>((long)s->g_stride, s->xbuf + cnt, s->page_mask.p, s->g_m.p, node_flags);
     HOT_LAUNCHED(s);
     return 0;
 }
