@@ -168,7 +168,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sc, desc = make_workload(args.workload)
+    # torchrun pins OMP_NUM_THREADS to 1 per process: the CPU arm gets all the host cores back (set before libgomp loads)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    # same object as the GPU arm at this N (N > 1: the bar / column extended N times along y)
+    sc, desc = make_workload(args.workload, 0, max(1, args.gpus))
     n, times, cores, t_sort = cpu_baseline(sc, args.steps, args.warmup)
     ms = 1e3 * float(np.mean(times))
     val = n / (ms * 1e-3) / 1e6
