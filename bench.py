@@ -265,7 +265,12 @@ def dist_solver_leg(sim, sc, args):
 
 
 def run_ours(args):
-    os.environ["NCCL_DEBUG"] = "WARN"          # the JSON line must be the only thing rank 0 writes to stdout
+    # the JSON line must be the only thing rank 0 writes to stdout: NCCL's banner / debug output (stdout by default, also at
+    # NCCL_DEBUG=WARN) goes to stderr, and stdout itself is pointed at stderr until the line is printed
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import hot_b200
@@ -414,7 +419,10 @@ def run_ours(args):
             "vcycle_ms": (solver or {}).get("vcycle", {}).get("ms"), "hessian_apply_mf_ms": (solver or {}).get("hessian_apply_mf", {}).get("ms"),
             "solver_kernels": solver,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
