@@ -410,52 +410,6 @@ __global__ void k_prolong(int nf, const int* __restrict__ pcol, const double* __
     fine[3 * (size_t)i] = a0; fine[3 * (size_t)i + 1] = a1; fine[3 * (size_t)i + 2] = a2;
 }
 
-// one colour phase of gs_smooth (MultigridPreconditioner.h:276-310): one warp per 4^3 block, nodes of the block in
-// sequence, lanes over the 125 slots.  FWD: out_i = Dinv_i (rhs_i - sum_{rank j < rank i} A_ij out_j); BWD: rank j > rank i.
-template <bool FWD>
-__global__ void __launch_bounds__(128) k_gs_phase(int b0, int b1, const int* __restrict__ block_start, const int* __restrict__ seq,
-    const int* __restrict__ rank, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ dinv,
-    const double* __restrict__ rhs, double* out)
-{
-    const int b = b0 + (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (b >= b1) return;
-    const int ps = block_start[b], pe = block_start[b + 1];
-    for (int it = 0; it < pe - ps; ++it) {
-        const int p = FWD ? ps + it : pe - 1 - it;
-        const int i = seq[p];
-        const int* c = col + (size_t)i * W;
-        const double* v = val + (size_t)i * 9 * W;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-#pragma unroll
-        for (int t = 0; t < W / 32; ++t) {
-            const int s = lane + 32 * t;
-            const int j = c[s];
-            const int rj = rank[j];
-            if (FWD ? rj < p : rj > p) {
-                const double x0 = out[3 * (size_t)j], x1 = out[3 * (size_t)j + 1], x2 = out[3 * (size_t)j + 2];
-                a0 += v[s] * x0 + v[3 * W + s] * x1 + v[6 * W + s] * x2;
-                a1 += v[W + s] * x0 + v[4 * W + s] * x1 + v[7 * W + s] * x2;
-                a2 += v[2 * W + s] * x0 + v[5 * W + s] * x1 + v[8 * W + s] * x2;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a0 += __shfl_down_sync(0xffffffffu, a0, o);
-            a1 += __shfl_down_sync(0xffffffffu, a1, o);
-            a2 += __shfl_down_sync(0xffffffffu, a2, o);
-        }
-        if (lane == 0) {
-            const double r0 = rhs[3 * (size_t)i] - a0, r1 = rhs[3 * (size_t)i + 1] - a1, r2 = rhs[3 * (size_t)i + 2] - a2;
-            const double* d = dinv + 9 * (size_t)i;
-            out[3 * (size_t)i] = d[0] * r0 + d[3] * r1 + d[6] * r2;
-            out[3 * (size_t)i + 1] = d[1] * r0 + d[4] * r1 + d[7] * r2;
-            out[3 * (size_t)i + 2] = d[2] * r0 + d[5] * r1 + d[8] * r2;
-        }
-        __syncwarp(); // orders lane 0's stores before the next node's loads of `out`
-    }
-}
-
-
 // One colour phase of gs_smooth, two-phase form (the version the V-cycle uses).  One CTA per 4^3 block, the block's
 // <= 64 nodes processed as two halves of <= 32 in sweep order; per half
 //   phase A (all warps, bandwidth-bound): every row streams its 125 slots once.  Couplings to nodes that are already final
