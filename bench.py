@@ -242,7 +242,57 @@ def solver_leg(sim, sc, args):
     out["vcycle"] = {"ms": vms, "levels": 3, "smoother": "GS(5)", "coarse": "PCG(2)", "times": 1, "coarse_cg_iters": cg_it,
                      "alg_bytes": vb, "alg_GBps": vb / vms / 1e6, "frac": vb / vms / 1e6 / peak,
                      "per_level_ms[smooth,restrict,prolongate,merge]": [[round(float(x), 4) for x in row] for row in table[:3]]}
+    out["hot_substep"] = substep_leg(sim, sc)
     return out
+
+
+HOT_FLAGS = dict(lsolver=3, mg_level=3, smoother=5, coarse_solver=2, project=1, linesearch=1, bcproject=1, usecn=1)  # tog.sh:38
+
+
+def substep_leg(sim, sc, steps=3):
+    """whole implicit substeps with the HOT configuration (L-BFGS + 3-level Galerkin MG): sort -> P2G -> BCs -> backwardEulerStep
+    (assembly, hierarchy, L-BFGS iterations with one V-cycle each) -> G2P.  Wall clock of the host call sequence; the first substep
+    carries first-use allocations and is reported separately."""
+    sim.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
+    sim.set_dt_gravity(SOLVER_DT, (0.0, 0.0, 0.0))
+    rows = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        sim.sortParticlesAndPolluteGrid()
+        n = sim.particlesToGrid()
+        bc = end_cap_bc(sim.get_id2coord())
+        sim.set_bc(bc, P=np.zeros((len(bc), 9)), dv_bc=np.zeros((len(bc), 3)))
+        log = sim.backwardEulerStep(**HOT_FLAGS)
+        sim.gridToParticles(SOLVER_DT)
+        rows.append({"ms": 1e3 * (time.perf_counter() - t0), "nodes": n, "converged": bool(log["converged"]),
+                     "lbfgs_iterations": int(log["iterations"]), "residual_first": float(log["residual_norm"][0]),
+                     "residual_last": float(log["residual_norm"][-1])})
+    return {"config": "HOT: -lsolver 3 -mg_level 3 -smoother 5 -coarseSolver 2 --project --linesearch --bcproject --usecn (tog.sh:38), dt 1/480",
+            "first_ms": rows[0]["ms"], "steady_ms": min(r["ms"] for r in rows[1:]), "substeps": rows}
+
+
+def cpu_substep_baseline():
+    """one HOT substep of the CPU oracle on the bounded slab sample (same flags)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as orc
+    from hot_b200 import scenes
+    sc = scenes.block((22, 40, 22), 0.12 / 22, ppc=12, origin_cells=(16, 16, 16), rho=2000.0, E=1e5, nu=0.3, seed=0)
+    o = orc.OracleSim(sc["dx"])
+    o.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
+    o.set_dt_gravity(SOLVER_DT, (0.0, 0.0, 0.0))
+    t0 = time.perf_counter()
+    o.sortParticlesAndPolluteGrid()
+    n = o.particlesToGrid()
+    bc = end_cap_bc(o.get_id2coord())
+    o.set_bc(bc, P=np.zeros((len(bc), 9)), dv_bc=np.zeros((len(bc), 3)))
+    log = o.backwardEulerStep(**HOT_FLAGS)
+    o.gridToParticles(SOLVER_DT)
+    ms = 1e3 * (time.perf_counter() - t0)
+    res = {"ms_sample": ms, "sample_particles": o.N, "sample_nodes": n, "lbfgs_iterations": int(log["iterations"]),
+           "converged": bool(log["converged"]), "cores": int(orc.lib.orc_num_threads()), "kind": "port",
+           "sample": "22x40x22-cell slab of the C2 bar, one HOT substep (not scaled)"}
+    o.close()
+    return res
 
 
 def dist_solver_leg(sim, sc, args):
@@ -401,6 +451,7 @@ def run_ours(args):
                    "sample": f"whole workload ({cn} particles), {args.cpu_reps} timed P2G+G2P steps of the OpenMP oracle after 1 warm-up"}
             if solver is not None:
                 cpu["vcycle"] = cpu_vcycle_baseline(n_nodes)
+                cpu["hot_substep"] = cpu_substep_baseline()
         else:
             cpu = None
         line = {
