@@ -103,6 +103,25 @@ class ClockSampler(threading.Thread):
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 
+    def sample_now(self):
+        """one sample taken by the calling thread (between two timed steps: every step has its own event pair, so the NVML call
+        is not inside any timed interval, but the GPU is in the middle of the timed loop)"""
+        try:
+            import pynvml as nv
+            if not hasattr(self, "_h"):
+                nv.nvmlInit()
+                self._h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            for bit, nm in ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")):
+                if r & bit:
+                    self.reasons.add(nm)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
     def result(self):
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
@@ -363,11 +382,13 @@ def run_ours(args):
     barrier()
     sampler.active = True
     wall0 = time.perf_counter()
-    for a, b in ev:
+    for k, (a, b) in enumerate(ev):
         flush.zero_()
         a.record(stream)
         sim.particlesToGrid(); sim.gridToParticles(0.0, want_flags=False)
         b.record(stream)
+        if k % 8 == 4:
+            sampler.sample_now()               # between two event pairs, GPU mid-loop
     barrier()
     wall = time.perf_counter() - wall0
     sampler.active = False
