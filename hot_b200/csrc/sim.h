@@ -188,6 +188,7 @@ struct Sim {
 
     int pf_dist = -1; // L2 prefetch distance of the per-group kernels in CTAs (-1: default = one wave of resident CTAs; 0: off; HOT_PF_DIST)
     DevBuf<int> flags; // g2p CFL flags
+    bool flags_zeroed = false; // hot_p2g's zero pass already cleared flags / the numbering's done-counter
     // plasticity applied after G2P + evolveStrain (MpmSimulationBase.cpp:1039-1064): 0 none, 1 VonMisesFixedCorotated, 2 SnowPlasticity
     int plastic_model = 0;
     double plastic_param[5] = {0, 0, 0, 0, 0};

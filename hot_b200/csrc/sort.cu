@@ -482,7 +482,7 @@ int number_nodes(Sim* s, bool flags_ready)
     // + normalisation (the serial running count of MpmGrid.h:148-161 over pages in list order x in-page element order)
     unsigned* mask = (unsigned*)s->scratch_i.p;
     int* base = s->scratch_i.p + NP;
-    HOT_CUDA(cudaMemsetAsync(s->dcount.p + 12, 0, sizeof(int), st));
+    if (!s->flags_zeroed) HOT_CUDA(cudaMemsetAsync(s->dcount.p + 12, 0, sizeof(int), st)); // (hot_p2g's zero pass resets the done-counter too)
     volatile int* hn = s->hcount + 4; // pinned + mapped (UVA): written by the last CTA of k_page_masks
     *hn = -1;
     k_page_masks<<<(NP + NM_WARPS - 1) / NM_WARPS, 32 * NM_WARPS, 0, st>>>(NP, s->g_m.p, flags_ready ? s->head_flag.p : nullptr, mask, base,

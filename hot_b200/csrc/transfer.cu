@@ -123,6 +123,19 @@ struct P2GPolicy {
     }
 };
 
+__global__ void k_step_zero(size_t gn, double* __restrict__ g_m, double* __restrict__ g_v, int* __restrict__ done, int* __restrict__ flags)
+{
+    const size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < gn) {
+        g_m[a] = 0.0;
+        g_v[a] = 0.0; g_v[gn + a] = 0.0; g_v[2 * gn + a] = 0.0;
+    }
+    if (a == 0) {
+        *done = 0;
+        flags[0] = 0; flags[1] = 0;
+    }
+}
+
 constexpr int G2P_THREADS = 128;
 static_assert(TILE <= 2 * G2P_THREADS && TILE >= G2P_THREADS, "tile staged in two rounds");
 
@@ -389,8 +402,12 @@ int p2g(Sim* s)
     cudaStream_t st = s->stream;
     const size_t gn = s->g_stride;
     // the pages are re-zeroed so the call is repeatable (the reference zeroes them in the sort, :1128-1136)
-    HOT_CUDA(cudaMemsetAsync(s->g_m.p, 0, gn * sizeof(double), st));
-    HOT_CUDA(cudaMemsetAsync(s->g_v.p, 0, 3 * gn * sizeof(double), st));
+    // one launch zeroes the four grid channels, the numbering's done-counter and the G2P flags (was four memsets)
+    HOT_CUDA(s->flags.reserve(2));
+    HOT_CUDA(s->dcount.reserve(16));
+    k_step_zero<<<(unsigned)((gn + 255) / 256), 256, 0, st>>>(gn, s->g_m.p, s->g_v.p, s->dcount.p + 12, s->flags.p);
+    HOT_LAUNCHED(s);
+    s->flags_zeroed = true;
     {
         KTime t(s, KC_P2G);
         P2GPolicy::Args a{s->P.stride, s->P.X.p, s->P.V.p, s->P.M.p, s->P.C.p, s->dx, 1.0 / s->dx, gn, s->g_m.p, s->g_v.p};
@@ -422,7 +439,8 @@ int g2p(Sim* s, double dt, int* flags)
     cudaStream_t st = s->stream;
     HOT_CUDA(s->flags.reserve(2));
     HOT_CUDA(s->P.gradV.reserve(9 * s->P.stride));
-    HOT_CUDA(cudaMemsetAsync(s->flags.p, 0, 2 * sizeof(int), st));
+    if (!s->flags_zeroed) HOT_CUDA(cudaMemsetAsync(s->flags.p, 0, 2 * sizeof(int), st)); // (hot_p2g's zero pass covers the first G2P after it)
+    s->flags_zeroed = false;
     {
         KTime t(s, KC_G2P);
         static const bool tma = !(getenv("HOT_G2P_TMA") && atoi(getenv("HOT_G2P_TMA")) == 0); // A/B switch, default on
