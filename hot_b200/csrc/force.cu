@@ -401,7 +401,9 @@ struct ForcePolicy {
     {
         TGradScatter::accumulate_col(rec, i, j, acc);
     }
-    __device__ __forceinline__ static void accumulate_plane(const double* __restrict__ rec, int i, double, double (&acc)[9][3])
+    static constexpr int RECP = REC, PMINB = 2; // plane form (A/B only): the column record, 92 KB per CTA
+    __device__ __forceinline__ static void prep_plane(const Args& a, size_t s, double* __restrict__ r) { prep(a, s, r); }
+    __device__ __forceinline__ static void accumulate_plane(const Args&, const double* __restrict__ rec, int i, double, double (&acc)[9][3])
     {
         TGradScatter::accumulate_plane(rec, i, acc);
     }
@@ -453,7 +455,9 @@ struct CNTolPolicy {
 #pragma unroll
         for (int k = 0; k < 3; ++k) acc[k][0] = fma(v, rec[6 + k], acc[k][0]);
     }
-    __device__ __forceinline__ static void accumulate_plane(const double* __restrict__ rec, int i, double, double (&acc)[9][1])
+    static constexpr int RECP = REC, PMINB = 3;
+    __device__ __forceinline__ static void prep_plane(const Args& a, size_t s, double* __restrict__ r) { prep(a, s, r); }
+    __device__ __forceinline__ static void accumulate_plane(const Args&, const double* __restrict__ rec, int i, double, double (&acc)[9][1])
     {
         const double v = rec[9] * rec[i];
 #pragma unroll

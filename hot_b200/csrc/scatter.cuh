@@ -257,13 +257,15 @@ constexpr int PS_CAP = 384; // particles per prep pass: a full page at 12 partic
 template <class Policy>
 constexpr size_t ps_smem_bytes()
 {
-    constexpr size_t rec = (size_t)Policy::REC * PS_CAP, con = (size_t)9 * Policy::NCH * PS_THREADS;
+    constexpr size_t rec = (size_t)Policy::RECP * PS_CAP, con = (size_t)9 * Policy::NCH * PS_THREADS;
     return (rec > con ? rec : con) * sizeof(double);
 }
-// Policy interface (plane form): NCH, REC, DOF, prep, prefetch, flush1 as for the column form and
-//   __device__ static void accumulate_plane(const double* rec, int i, double di, double (&acc)[9][NCH])
+// Policy interface (plane form): NCH, DOF, prefetch, flush1 as for the column form and
+//   static constexpr int RECP (doubles per plane-form record), PMINB (CTAs per SM its shared-memory footprint allows)
+//   __device__ static void prep_plane(const Args&, size_t s, double* rec)
+//   __device__ static void accumulate_plane(const Args&, const double* rec, int i, double di, double (&acc)[9][NCH])
 template <class Policy>
-__global__ void __launch_bounds__(PS_THREADS, 3) k_plane2_scatter(typename Policy::Args args, const int* __restrict__ cell_start,
+__global__ void __launch_bounds__(PS_THREADS, Policy::PMINB) k_plane2_scatter(typename Policy::Args args, const int* __restrict__ cell_start,
     const int* __restrict__ group_slot, const int* __restrict__ nbr8, const int* __restrict__ tile_dof,
     int pf_dist)
 {
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(PS_THREADS, 3) k_plane2_scatter(typename Polic
     for (int cb = first; cb < end; cb += PS_CAP) {
         const int cn = min(PS_CAP, end - cb);
         if (cb != first) __syncthreads(); // previous pass consumed
-        for (int k = tid; k < cn; k += THREADS) Policy::prep(args, (size_t)cb + k, cs_smem + (size_t)k * Policy::REC);
+        for (int k = tid; k < cn; k += THREADS) Policy::prep_plane(args, (size_t)cb + k, cs_smem + (size_t)k * Policy::RECP);
         __syncthreads(); // records (and, on the first pass, s_cs / s_nbr) visible
         if (cb == first) {
             // cells to lanes in order of decreasing particle count: the lanes of a warp then run loops of similar length
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(PS_THREADS, 3) k_plane2_scatter(typename Polic
         }
         const int my_b = s_cs[c], my_e = s_cs[c + 1];
         const int pb = max(my_b, cb) - cb, pe = min(my_e, cb + cn) - cb;
-        for (int p = pb; p < pe; ++p) Policy::accumulate_plane(cs_smem + (size_t)p * Policy::REC, i, di, acc);
+        for (int p = pb; p < pe; ++p) Policy::accumulate_plane(args, cs_smem + (size_t)p * Policy::RECP, i, di, acc);
     }
     Policy::prefetch(args, pf_first, pf_end, tid, THREADS);
     __syncthreads(); // records dead -> reuse as the contribution array [ch][jk][cell * 3 + i]
@@ -360,7 +362,7 @@ int launch_plane2_scatter(Sim* s, const typename Policy::Args& a)
     HOT_CUDA(attr);
     k_plane2_scatter<Policy><<<(unsigned)(s->g1 - s->g0), PS_THREADS, ps_smem_bytes<Policy>(), s->stream>>>(a,
         s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0, s->nbr8.p,
-        Policy::DOF ? s->tile_dof.p + (size_t)s->g0 * Geo::TILE : nullptr, pf_distance(s, 3));
+        Policy::DOF ? s->tile_dof.p + (size_t)s->g0 * Geo::TILE : nullptr, pf_distance(s, Policy::PMINB));
     HOT_LAUNCHED(s);
     return 0;
 }

@@ -85,30 +85,57 @@ struct P2GPolicy {
             }
         }
     }
-    // plane form: the 9 nodes (j, k) of x-plane i
-    __device__ __forceinline__ static void accumulate_plane(const double* __restrict__ rec, int i, double di, double (&acc)[9][4])
+    // ---- plane form.  COMPACT record (18 doubles: 55 KB for a full page of 384 particles, 4 CTAs per SM instead of 3):
+    //   [0..2] xi - base per axis (the argument of the B-spline weights) [3] m | [4..6] A | [7..15] Gx Gy Gz | pad
+    // the (cell, plane) thread re-derives the 9 weights in the reference's operation order (bspline_axis).
+    static constexpr int RECP = 18, PMINB = 4;
+    __device__ __forceinline__ static void prep_plane(const Args& a, size_t s, double* __restrict__ r)
     {
-        double wy[3], wz[3], m, A[3], gx[3], gy[3], gz[3];
-        const double wx = rec[i];
-        wy[0] = rec[3];
-        lds2(rec + 4, wy[1], wy[2]);
-        lds2(rec + 6, wz[0], wz[1]); lds2(rec + 8, wz[2], m);
-        lds2(rec + 10, A[0], A[1]); lds2(rec + 12, A[2], gx[0]); lds2(rec + 14, gx[1], gx[2]);
-        lds2(rec + 16, gy[0], gy[1]); lds2(rec + 18, gy[2], gz[0]); lds2(rec + 20, gz[1], gz[2]);
+        const double m = a.M[s];
+        double d0[3], d0n[3], v[3], Cm[9];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double Xd = a.X[d * a.ps + s];
+            v[d] = a.V[d * a.ps + s];
+            double xi;
+            const int b = base_node_of(Xd, a.one_over_dx, &xi);
+            d0[d] = xi - (double)b;
+            d0n[d] = (double)b * a.dx - Xd;
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) Cm[q] = m * a.C[q * a.ps + s];
+        double A[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) A[c] = m * v[c] + (Cm[c] * d0n[0] + Cm[c + 3] * d0n[1] + Cm[c + 6] * d0n[2]);
+        sts2(r + 0, d0[0], d0[1]); sts2(r + 2, d0[2], m);
+        sts2(r + 4, A[0], A[1]); sts2(r + 6, A[2], a.dx * Cm[0]); sts2(r + 8, a.dx * Cm[1], a.dx * Cm[2]);
+        sts2(r + 10, a.dx * Cm[3], a.dx * Cm[4]); sts2(r + 12, a.dx * Cm[5], a.dx * Cm[6]); sts2(r + 14, a.dx * Cm[7], a.dx * Cm[8]);
+    }
+    // the 9 nodes (j, k) of x-plane i
+    __device__ __forceinline__ static void accumulate_plane(const Args&, const double* __restrict__ rec, int i, double di, double (&acc)[9][4])
+    {
+        double d0[3], m, A[3], gx[3], gy[3], gz[3];
+        lds2(rec + 0, d0[0], d0[1]); lds2(rec + 2, d0[2], m);
+        lds2(rec + 4, A[0], A[1]); lds2(rec + 6, A[2], gx[0]); lds2(rec + 8, gx[1], gx[2]);
+        lds2(rec + 10, gy[0], gy[1]); lds2(rec + 12, gy[2], gz[0]); lds2(rec + 14, gz[1], gz[2]);
+        double w[3][3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) bspline_axis(d0[d], w[d], nullptr);
+        const double wx = i == 0 ? w[0][0] : (i == 1 ? w[0][1] : w[0][2]);
         double b[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) b[c] = fma(di, gx[c], A[c]);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            const double wij = wx * wy[j];
+            const double wij = wx * w[1][j];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const double w = wij * wz[k];
-                acc[j * 3 + k][0] = fma(w, m, acc[j * 3 + k][0]);
+                const double ww = wij * w[2][k];
+                acc[j * 3 + k][0] = fma(ww, m, acc[j * 3 + k][0]);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const double val = k == 0 ? b[c] : (k == 1 ? b[c] + gz[c] : fma(2.0, gz[c], b[c]));
-                    acc[j * 3 + k][1 + c] = fma(w, val, acc[j * 3 + k][1 + c]);
+                    acc[j * 3 + k][1 + c] = fma(ww, val, acc[j * 3 + k][1 + c]);
                 }
             }
             if (j < 2) {
