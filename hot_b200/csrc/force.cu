@@ -347,14 +347,38 @@ struct TGradScatter {
             for (int r = 0; r < 3; ++r) acc[k][r] = fma(cc[r], gz[k], fma(ab[r], wz[k], acc[k][r]));
         }
     }
-    // plane form: the 9 nodes (j, k) of x-plane i
-    __device__ __forceinline__ static void accumulate_plane(const double* __restrict__ rec, int i, double (&acc)[9][3])
+    // plane form: COMPACT record (14 doubles: 42 KB for a full page, 5 CTAs per SM): [0..2] xi - base per axis, [3..11] T, pad;
+    // the (cell, plane) thread re-derives weights and weight derivatives in the reference's operation order
+    static constexpr int RECP = 14;
+    __device__ __forceinline__ static void prep_plane(const double* X, size_t ps, size_t s, double one_over_dx, const double (&T)[9], double* __restrict__ r)
     {
-        double wx, gx, wy[3], gy[3], wz[3], gz[3], T[10];
-        lds2(rec + 2 * i, wx, gx);
-        lds2(rec + 6, wy[0], gy[0]); lds2(rec + 8, wy[1], gy[1]); lds2(rec + 10, wy[2], gy[2]);
-        lds2(rec + 12, wz[0], wz[1]); lds2(rec + 14, wz[2], gz[0]); lds2(rec + 16, gz[1], gz[2]);
-        lds2(rec + 18, T[0], T[1]); lds2(rec + 20, T[2], T[3]); lds2(rec + 22, T[4], T[5]); lds2(rec + 24, T[6], T[7]); lds2(rec + 26, T[8], T[9]);
+        double d0[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double xi;
+            const int b = base_node_of(X[d * ps + s], one_over_dx, &xi);
+            d0[d] = xi - (double)b;
+        }
+        sts2(r + 0, d0[0], d0[1]); sts2(r + 2, d0[2], T[0]);
+        sts2(r + 4, T[1], T[2]); sts2(r + 6, T[3], T[4]); sts2(r + 8, T[5], T[6]); sts2(r + 10, T[7], T[8]);
+    }
+    // the 9 nodes (j, k) of x-plane i
+    __device__ __forceinline__ static void accumulate_plane(const double* __restrict__ rec, double one_over_dx, int i, double (&acc)[9][3])
+    {
+        double d0[3], T[9];
+        lds2(rec + 0, d0[0], d0[1]); lds2(rec + 2, d0[2], T[0]);
+        lds2(rec + 4, T[1], T[2]); lds2(rec + 6, T[3], T[4]); lds2(rec + 8, T[5], T[6]); lds2(rec + 10, T[7], T[8]);
+        double w[3][3], dw[3][3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) bspline_axis(d0[d], w[d], dw[d]);
+        const double wx = i == 0 ? w[0][0] : (i == 1 ? w[0][1] : w[0][2]);
+        const double gx = one_over_dx * (i == 0 ? dw[0][0] : (i == 1 ? dw[0][1] : dw[0][2]));
+        double wy[3], gy[3], wz[3], gz[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            wy[t] = w[1][t]; gy[t] = one_over_dx * dw[1][t];
+            wz[t] = w[2][t]; gz[t] = one_over_dx * dw[2][t];
+        }
         double tx[3], ty[3], tz[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -389,7 +413,7 @@ struct ForcePolicy {
         double* out; // DOF vector
     };
     static constexpr int REC = TGradScatter::REC, MINB = 4; // 45 KB of records per CTA
-    static constexpr bool PLANE = false; // measured: column 0.107 ms, plane 0.137 ms (its 92 KB of records leave 2 CTAs per SM)
+    static constexpr bool PLANE = true; // measured (C2): plane with compact records 0.089 ms (5 CTAs per SM), column 0.103 ms
     __device__ __forceinline__ static void prep(const Args& a, size_t s, double* __restrict__ r)
     {
         double T[9];
@@ -401,11 +425,17 @@ struct ForcePolicy {
     {
         TGradScatter::accumulate_col(rec, i, j, acc);
     }
-    static constexpr int RECP = REC, PMINB = 2; // plane form (A/B only): the column record, 92 KB per CTA
-    __device__ __forceinline__ static void prep_plane(const Args& a, size_t s, double* __restrict__ r) { prep(a, s, r); }
-    __device__ __forceinline__ static void accumulate_plane(const Args&, const double* __restrict__ rec, int i, double, double (&acc)[9][3])
+    static constexpr int RECP = TGradScatter::RECP, PMINB = 5;
+    __device__ __forceinline__ static void prep_plane(const Args& a, size_t s, double* __restrict__ r)
     {
-        TGradScatter::accumulate_plane(rec, i, acc);
+        double T[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) T[q] = -a.scale * a.stress[q * a.ps + s];
+        TGradScatter::prep_plane(a.X, a.ps, s, a.one_over_dx, T, r);
+    }
+    __device__ __forceinline__ static void accumulate_plane(const Args& a, const double* __restrict__ rec, int i, double, double (&acc)[9][3])
+    {
+        TGradScatter::accumulate_plane(rec, a.one_over_dx, i, acc);
     }
     static constexpr bool DOF = true;
     __device__ __forceinline__ static void prefetch(const Args& a, int first, int end, int tid, int nt)

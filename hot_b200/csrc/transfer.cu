@@ -35,7 +35,7 @@ struct P2GPolicy {
     //   [0..2] wx  [3..5] wy | [6..8] wz [9] m | [10..12] A = m v + m C (x_node0 - x_p) | [13..15] Gx [16..18] Gy [19..21] Gz,
     //   G* = dx * m C(:, d): the node value of stencil node (i, j, k) is A + i Gx + j Gy + k Gz.
     static constexpr int REC = 22, MINB = 5; // column form: 33 KB of records per CTA, plane form 66 KB
-    static constexpr bool PLANE = true; // measured: plane 0.104 ms, column 0.109 ms (C2)
+    static constexpr bool PLANE = true; // measured (C2): plane with compact records 0.096 ms (4 CTAs per SM), column 0.109 ms
     static constexpr bool DOF = false;
     __device__ __forceinline__ static void prefetch(const Args& a, int first, int end, int tid, int nt)
     {

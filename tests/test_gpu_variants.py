@@ -1,6 +1,6 @@
 """The A/B switches of the kernels (measured alternatives kept selectable through environment variables) must stay
 parity-green too: every variant re-runs the operator parity tests in a fresh process, because the switches are read once
-per process.  Default configuration: plane scatter for P2G, column scatter for the force / Hessian scatters, TMA-staged
+per process.  Default configuration: plane scatter (compact records) for P2G and the force / Hessian scatters, column scatter for the CN tolerance, TMA-staged
 G2P / Hessian gather, per-direction Gauss-Seidel row stream with the stream-based residual update."""
 import os
 import subprocess
