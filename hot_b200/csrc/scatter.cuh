@@ -54,20 +54,21 @@ __device__ __forceinline__ int tile_base(int bx, int by, int bz)
 }
 
 // ---- column scatter -----------------------------------------------------------------
-// One CTA per HALF page group (SPLIT = 2: the 16 cells of one x-layer of the 2x4x4 page), thread = (cell, (i, j) column of
+// One CTA per HALF page group (CS_SPLIT = 2: the 16 cells of one x-layer of the 2x4x4 page), thread = (cell, (i, j) column of
 // the 3x3x3 stencil): 9 threads per cell, each keeping the 3 nodes x NCH channels of its z-column in registers.
-// Compared with the plane skeleton above (ncu: 16.4 of 32 lanes active in its accumulate loop, 29 % of the stalls on the CTA
-// barrier behind the slowest cell, 128 registers -> 15 warps per SM):
-//   * a warp holds 3.6 cells instead of 10.7, so the per-cell particle loops of its lanes diverge far less;
-//   * everything that does not depend on the stencil node is computed ONCE per particle by a thread-per-particle prep
-//     pass (B-spline weights of the three axes in the reference's operation order, the policy's payload) and parked in
-//     shared memory field-major, so the (cell, column) threads issue ~30 fp64 instructions per particle instead of ~145;
-//   * 12 accumulators instead of 36: <= 72 registers; a half page of the usual 8-12 particles per cell is ONE prep pass of
-//     CHUNK = 192 particles (a second pass serialises a DRAM round trip behind a quarter-full accumulate loop), 34-42 KB of
-//     shared memory, 5 CTAs per SM at different phases;
-//   * combine is a gather: every thread parks its 3 x NCH sums, then thread (node) adds the contributions of its node in a
-//     fixed order (closed-form walk over the (cell, column, k) triples that feed the node) - no
-//     shared-memory atomics, no warp tiles, deterministic inside the CTA - and issues one RED per channel.
+// History (ncu): the first skeleton of this file had thread = (cell, x-plane) re-deriving the weights per thread
+// (16.4 of 32 lanes active in its accumulate loop, 29 % of the stalls on the CTA barrier behind the slowest cell, 128
+// registers -> 15 warps per SM).  Against that the column form has
+//   * a warp holding 3.6 cells instead of 10.7, so the per-cell particle loops of its lanes diverge far less;
+//   * everything that does not depend on the stencil node computed ONCE per particle by the prep pass, so the (cell, column)
+//     threads issue ~30 fp64 instructions per particle instead of ~145;
+//   * 12 accumulators instead of 36: <= 72-96 registers; a half page of the usual 8-12 particles per cell is ONE prep pass of
+//     CS_CHUNK = 192 particles, 34-46 KB of shared memory, 4-5 CTAs per SM at different phases;
+//   * a gather combine: every thread parks its 3 x NCH sums, then thread (node) adds the contributions of its node in a fixed
+//     order (closed-form walk over the (cell, column, k) triples that feed the node) - no shared-memory atomics, no warp
+//     tiles, deterministic inside the CTA - and issues one RED per channel.
+// Its weakness is shared-memory bandwidth (9 lanes fetch the same per-particle words), which is why the plane form below, with
+// compact records, is the default of the P2G and force scatters; the column form serves the CN-tolerance scatter and A/B runs.
 // HBM traffic is the algorithmic minimum: every particle attribute is read once (coalesced runs of the sorted SoA rows),
 // every touched node receives one RED per channel and half page.
 template <int SPLIT>
@@ -251,7 +252,10 @@ int launch_column_scatter(Sim* s, const typename Policy::Args& a)
 // keeping what the column form established: per-particle prep pass (weights once per particle), particle-major records,
 // gather combine.  The plane form's own weakness - a warp holds 10.7 cells whose particle counts differ, 16 of
 // 32 lanes active in the first plane kernel - is removed by handing the cells to the lanes in order of DECREASING particle
-// count, which the gather combine permits (any thread may own any cell).
+// count, which the gather combine permits (any thread may own any cell).  What then bounds the kernel is the serial phase
+// chain of a page group at few resident CTAs: the records are COMPACT (the three B-spline arguments instead of nine weights,
+// Policy::RECP doubles; the thread re-derives the weights) so that 4-5 CTAs fit per SM (P2G 104 -> 96 us, force scatter
+// 103 -> 89 us at C2).
 constexpr int PS_THREADS = 3 * Geo::E; // 96
 constexpr int PS_CAP = 384; // particles per prep pass: a full page at 12 particles per cell
 template <class Policy>
