@@ -39,3 +39,13 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "libhot_oracle" not in text and "oracle_binding" not in text and "orc_" not in text, f
+
+
+def test_host_mirror_header_compiles():
+    """include/hot_b200_host.hpp (the C++ mirror of the reference's operator surface) must stay a valid, warning-free C++17
+    translation unit against include/hot_b200.h; the GPU test links and runs it."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["g++", "-std=c++17", "-O0", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-fsyntax-only",
+                        os.path.join(root, "tests", "cpp", "host_step.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
