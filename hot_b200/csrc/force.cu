@@ -19,7 +19,7 @@
 //    gather(27) -> 81 FMA -> scatter(27) and the same H~ feeds the matrix assembly (a15).
 //  * scatters use the shared prep / accumulate / gather-combine skeletons of scatter.cuh: no colour passes, no atomics in
 //    the particle loop.
-#include "scatter.cuh"
+#include "scatter_ws.cuh"
 #include "dense3.cuh"
 #include "reduce.cuh"
 #include <cstdlib>
@@ -365,9 +365,14 @@ struct TGradScatter {
     // the 9 nodes (j, k) of x-plane i
     __device__ __forceinline__ static void accumulate_plane(const double* __restrict__ rec, double one_over_dx, int i, double (&acc)[9][3])
     {
-        double d0[3], T[9];
-        lds2(rec + 0, d0[0], d0[1]); lds2(rec + 2, d0[2], T[0]);
-        lds2(rec + 4, T[1], T[2]); lds2(rec + 6, T[3], T[4]); lds2(rec + 8, T[5], T[6]); lds2(rec + 10, T[7], T[8]);
+        double v[12];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) lds2(rec + 2 * u, v[2 * u], v[2 * u + 1]);
+        accumulate_rec(v, one_over_dx, i, acc);
+    }
+    __device__ __forceinline__ static void accumulate_rec(const double (&v)[12], double one_over_dx, int i, double (&acc)[9][3])
+    {
+        const double d0[3] = {v[0], v[1], v[2]}, T[9] = {v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]};
         double w[3][3], dw[3][3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) bspline_axis(d0[d], w[d], dw[d]);
@@ -436,6 +441,29 @@ struct ForcePolicy {
     __device__ __forceinline__ static void accumulate_plane(const Args& a, const double* __restrict__ rec, int i, double, double (&acc)[9][3])
     {
         TGradScatter::accumulate_plane(rec, a.one_over_dx, i, acc);
+    }
+    // ---- ws form (scatter_ws.cuh): 12 raw rows X, T staged by TMA; record = the compact one above (12 doubles = 6 units) in place
+    static constexpr int ROWS = 12, UNITS = 6, WS_ID = 1;
+    __device__ __forceinline__ static const double* row(const Args& a, int r)
+    {
+        return r < 3 ? a.X + (size_t)r * a.ps : a.stress + (size_t)(r - 3) * a.ps;
+    }
+    __device__ __forceinline__ static int prep_ws(const Args& a, const double (&raw)[12], double (&r)[12])
+    {
+        int cb[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double xi;
+            cb[d] = base_node_of(raw[d], a.one_over_dx, &xi);
+            r[d] = xi - (double)cb[d];
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) r[3 + q] = -a.scale * raw[3 + q];
+        return (((cb[0] & (Geo::BX - 1)) << Geo::yb | (cb[1] & (Geo::BY - 1))) << Geo::zb) | (cb[2] & (Geo::BZ - 1));
+    }
+    __device__ __forceinline__ static void accumulate_rec(const Args& a, const double (&v)[12], int i, double, double (&acc)[9][3])
+    {
+        TGradScatter::accumulate_rec(v, a.one_over_dx, i, acc);
     }
     static constexpr bool DOF = true;
     __device__ __forceinline__ static void prefetch(const Args& a, int first, int end, int tid, int nt)
@@ -696,6 +724,10 @@ int update_state(Sim* s, bool want_energy, double* energy)
 // holds the node-local terms).  Partitioned: into a zeroed scratch array, summed over the ranks on the interface nodes, then
 // added to `out` - so node-local terms are counted once.
 template <class Policy>
+int scatter_dispatch(Sim* s, const typename Policy::Args& a) { return launch_scatter_best<Policy>(s, a); }
+template <>
+int scatter_dispatch<CNTolPolicy>(Sim* s, const CNTolPolicy::Args& a) { return launch_scatter<CNTolPolicy>(s, a); } // once per step: round-1 column form
+template <class Policy>
 int scatter_to_dofs(Sim* s, typename Policy::Args a, double* Policy::Args::*target, double* out, int comps)
 {
     cudaStream_t st = s->stream;
@@ -708,7 +740,7 @@ int scatter_to_dofs(Sim* s, typename Policy::Args a, double* Policy::Args::*targ
     }
     a.*target = dst;
     if (s->g1 > s->g0) {
-        int rc = launch_scatter<Policy>(s, a);
+        int rc = scatter_dispatch<Policy>(s, a);
         if (rc) return rc;
     }
     if (s->world > 1) {

@@ -181,6 +181,14 @@ struct Sim {
     int num_nodes = 0;
     DevBuf<int> dof_slot; // inverse of g_idx
     DevBuf<int> tile_dof; // n_groups x Geo::TILE: DOF id of every node of a page group's (B+2)^3 tile (sort.cu: k_tile_dof)
+    // work items of the persistent scatter (scatter_ws.cuh), built once per sort (sort.cu: build_scatter_items)
+    DevBuf<unsigned char> ws_items; // WsItem records: item g = (first chunk of) page group g, extra chunks of oversized groups behind
+    DevBuf<int> ws_order, ws_key, ws_key_alt, ws_idx; // this rank's items by decreasing particle count (+ sort scratch)
+    DevBuf<int> ws_count; // [0] own items [1] extra chunks [2] work counter [3] finished teams [4] error flag
+    long ws_own_items = 0;
+    bool ws_ok = false; // false: a cell exceeds the item format (scatters fall back to the round-1 skeleton)
+    bool ws_attr_set[4] = {false, false, false, false};
+    int n_sm = 0;
     bool p2g_done = false;
 
     // ---- DOF vectors
@@ -275,6 +283,7 @@ struct KTime { // RAII: times everything launched on s->stream in its scope unde
 // sort.cu
 int sort_and_activate(Sim* s);
 int number_nodes(Sim* s, bool flags_ready = false); // a7, after the P2G scatter (flags_ready: head_flag already holds the non-zero node flags)
+int build_scatter_items(Sim* s); // work items of the persistent scatter, after the sort and the partition (dist_after_sort)
 // transfer.cu
 int p2g(Sim* s);
 int g2p(Sim* s, double dt, int* flags);

@@ -11,7 +11,7 @@
 //              = stable sort by page id -> run heads (min position) -> sort heads by position;
 //   DOF ids    = exclusive scan of (m != 0) over (page list order x in-page element order).
 // Radix sort / scan / select come from CUB (CUDA toolkit headers); everything else is ours.
-#include "sim.h"
+#include "scatter_ws.cuh"
 #include <cub/cub.cuh>
 
 namespace hot {
@@ -340,6 +340,70 @@ __global__ void __launch_bounds__(160) k_tile_dof(const int* __restrict__ group_
     tile_dof[(size_t)g * Geo::TILE + n] = slot < 0 ? -1 : g_idx[(size_t)slot * Geo::E + e];
 }
 
+// Work items of the persistent scatter (scatter_ws.cuh), one warp per page group, lane = in-page cell.  A group with more than
+// WS_CAP particles is cut greedily into cell ranges (its first chunk keeps item index g, the others are appended behind the
+// groups).  Per item: cells ranked by decreasing particle count, jagged-diagonal offsets jd[p] = sum_c min(n_c, p), cell starts
+// relative to the run, the 8 neighbour page slots, and a sort key (WS_CAP - count for this rank's groups) for the dispatch order.
+__global__ void k_scatter_items(int n_groups, int g0, int g1, int max_items, const int* __restrict__ cell_start, const int* __restrict__ group_slot,
+    const int* __restrict__ nbr8, WsItem* __restrict__ items, int* __restrict__ keys, int* __restrict__ count)
+{
+    const int g = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (g >= n_groups) return;
+    const unsigned full = 0xffffffffu;
+    const int* cs = cell_start + (size_t)g * (Geo::E + 1);
+    const int start = cs[lane], n = cs[lane + 1] - start;
+    if (__any_sync(full, n > WS_MAXC - 1)) { // a cell beyond the item format: the scatters keep the round-1 skeleton this step
+        if (lane == 0) atomicOr(count + 4, 1);
+        return;
+    }
+    int chunk = 0, run = 0, myc = 0;
+    for (int c = 0; c < Geo::E; ++c) {
+        const int nc = __shfl_sync(full, n, c);
+        if (run + nc > WS_CAP && run > 0) { ++chunk; run = 0; }
+        run += nc;
+        if (c == lane) myc = chunk;
+    }
+    const int slot = group_slot[g];
+    for (int k = 0; k <= chunk; ++k) {
+        int idx = g;
+        if (k > 0) {
+            if (lane == 0) idx = n_groups + atomicAdd(count + 1, 1);
+            idx = __shfl_sync(full, idx, 0);
+            if (idx >= max_items) {
+                if (lane == 0) atomicOr(count + 4, 2);
+                return;
+            }
+        }
+        const bool act = myc == k;
+        const int na = act ? n : 0;
+        int rank = 0, j0 = 0, j1 = 0, cnt = 0;
+        for (int c = 0; c < Geo::E; ++c) {
+            const int nc = __shfl_sync(full, na, c);
+            rank += (nc > na) || (nc == na && c < lane);
+            j0 += min(nc, lane);
+            j1 += min(nc, lane + 32);
+            cnt += nc;
+        }
+        const unsigned am = __ballot_sync(full, act);
+        const int c0 = __ffs(am) - 1, c1 = 32 - __clz(am);
+        const int first = __shfl_sync(full, start, c0);
+        WsItem* it = items + idx;
+        if (lane == 0) {
+            it->first = first; it->count = cnt; it->g = g; it->cells = c0 | (c1 << 8);
+            const bool own = g >= g0 && g < g1;
+            keys[idx] = own ? WS_CAP - cnt : 0x7fff;
+            if (own) atomicAdd(count, 1);
+        }
+        if (lane < 8) it->nbr[lane] = nbr8[(size_t)slot * 8 + lane];
+        it->cnt[rank] = (unsigned short)na;
+        it->order[rank] = (unsigned char)lane;
+        it->rank[lane] = (unsigned char)rank;
+        it->cs[lane] = (unsigned short)(act ? start - first : 0);
+        it->jd[lane] = (unsigned short)j0;
+        it->jd[lane + 32] = (unsigned short)j1;
+    }
+}
+
 template <class F>
 int with_tmp(Sim* s, F f)
 {
@@ -465,7 +529,41 @@ int sort_and_activate(Sim* s)
     s->num_nodes = 0;
     s->sorted = true;
     s->p2g_done = false;
-    return dist_after_sort(s);
+    rc = dist_after_sort(s);
+    if (rc) return rc;
+    return build_scatter_items(s);
+}
+
+int build_scatter_items(Sim* s)
+{
+    cudaStream_t st = s->stream;
+    const long G = s->n_groups, cap = 2 * G + 1024;
+    s->ws_ok = false;
+    s->ws_own_items = 0;
+    if (!s->n_sm) HOT_CUDA(cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, s->device));
+    HOT_CUDA(s->ws_items.reserve((size_t)cap * sizeof(WsItem)));
+    HOT_CUDA(s->ws_key.reserve(cap));
+    HOT_CUDA(s->ws_key_alt.reserve(cap));
+    HOT_CUDA(s->ws_idx.reserve(cap));
+    HOT_CUDA(s->ws_order.reserve(cap));
+    HOT_CUDA(s->ws_count.reserve(8));
+    HOT_CUDA(cudaMemsetAsync(s->ws_count.p, 0, 8 * sizeof(int), st));
+    k_scatter_items<<<nblk(G * 32), TPB, 0, st>>>((int)G, (int)s->g0, (int)s->g1, (int)cap, s->cell_start.p, s->group_slot.p, s->nbr8.p,
+        reinterpret_cast<WsItem*>(s->ws_items.p), s->ws_key.p, s->ws_count.p);
+    HOT_LAUNCHED(s);
+    HOT_CUDA(cudaMemcpyAsync(s->hcount + 24, s->ws_count.p, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    HOT_CUDA(cudaStreamSynchronize(st));
+    if (s->hcount[28]) return 0; // keep the round-1 skeleton for this step
+    const long total = G + s->hcount[25];
+    k_iota<<<nblk(total), TPB, 0, st>>>(total, s->ws_idx.p);
+    HOT_LAUNCHED(s);
+    int rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceRadixSort::SortPairs(t, b, (const unsigned*)s->ws_key.p, (unsigned*)s->ws_key_alt.p, s->ws_idx.p, s->ws_order.p, (int)total, 0, 16, st);
+    });
+    if (rc) return rc;
+    s->ws_own_items = s->hcount[24];
+    s->ws_ok = true;
+    return 0;
 }
 
 int number_nodes(Sim* s, bool flags_ready)

@@ -11,7 +11,7 @@
 // no atomics in the particle loop - see scatter.cuh for the prep / accumulate / gather-combine structure it shares with the
 // force and Hessian scatters.  G2P is the matching gather: CTA per page group, the group's (v + dv) node tile staged in
 // shared memory through the per-step tile -> DOF table, one thread per particle, tensor-product contraction, F update fused.
-#include "scatter.cuh"
+#include "scatter_ws.cuh"
 #include "dense3.cuh"
 #include <cstdlib>
 
@@ -112,12 +112,44 @@ struct P2GPolicy {
         sts2(r + 10, a.dx * Cm[3], a.dx * Cm[4]); sts2(r + 12, a.dx * Cm[5], a.dx * Cm[6]); sts2(r + 14, a.dx * Cm[7], a.dx * Cm[8]);
     }
     // the 9 nodes (j, k) of x-plane i
-    __device__ __forceinline__ static void accumulate_plane(const Args&, const double* __restrict__ rec, int i, double di, double (&acc)[9][4])
+    __device__ __forceinline__ static void accumulate_plane(const Args& a, const double* __restrict__ rec, int i, double di, double (&acc)[9][4])
     {
-        double d0[3], m, A[3], gx[3], gy[3], gz[3];
-        lds2(rec + 0, d0[0], d0[1]); lds2(rec + 2, d0[2], m);
-        lds2(rec + 4, A[0], A[1]); lds2(rec + 6, A[2], gx[0]); lds2(rec + 8, gx[1], gx[2]);
-        lds2(rec + 10, gy[0], gy[1]); lds2(rec + 12, gy[2], gz[0]); lds2(rec + 14, gz[1], gz[2]);
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) lds2(rec + 2 * u, v[2 * u], v[2 * u + 1]);
+        accumulate_rec(a, v, i, di, acc);
+    }
+    // ---- ws form (scatter_ws.cuh): 16 raw rows X V M C staged by TMA, the compact record above (16 doubles = 8 units) in place
+    static constexpr int ROWS = 16, UNITS = 8, WS_ID = 0;
+    __device__ __forceinline__ static const double* row(const Args& a, int r)
+    {
+        return r < 3 ? a.X + (size_t)r * a.ps : (r < 6 ? a.V + (size_t)(r - 3) * a.ps : (r == 6 ? a.M : a.C + (size_t)(r - 7) * a.ps));
+    }
+    __device__ __forceinline__ static int prep_ws(const Args& a, const double (&raw)[16], double (&r)[16])
+    {
+        const double m = raw[6];
+        double d0n[3], Cm[9];
+        int cb[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double xi;
+            cb[d] = base_node_of(raw[d], a.one_over_dx, &xi);
+            r[d] = xi - (double)cb[d];
+            d0n[d] = (double)cb[d] * a.dx - raw[d];
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) Cm[q] = m * raw[7 + q];
+        r[3] = m;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) r[4 + c] = m * raw[3 + c] + (Cm[c] * d0n[0] + Cm[c + 3] * d0n[1] + Cm[c + 6] * d0n[2]);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) r[7 + q] = a.dx * Cm[q];
+        return (((cb[0] & (Geo::BX - 1)) << Geo::yb | (cb[1] & (Geo::BY - 1))) << Geo::zb) | (cb[2] & (Geo::BZ - 1));
+    }
+    __device__ __forceinline__ static void accumulate_rec(const Args&, const double (&v)[16], int i, double di, double (&acc)[9][4])
+    {
+        const double d0[3] = {v[0], v[1], v[2]}, m = v[3], A[3] = {v[4], v[5], v[6]}, gx[3] = {v[7], v[8], v[9]}, gy[3] = {v[10], v[11], v[12]},
+                     gz[3] = {v[13], v[14], v[15]};
         double w[3][3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) bspline_axis(d0[d], w[d], nullptr);
@@ -439,7 +471,7 @@ int p2g(Sim* s)
         KTime t(s, KC_P2G);
         P2GPolicy::Args a{s->P.stride, s->P.X.p, s->P.V.p, s->P.M.p, s->P.C.p, s->dx, 1.0 / s->dx, gn, s->g_m.p, s->g_v.p};
         if (s->g1 > s->g0) {
-            int rc = launch_scatter<P2GPolicy>(s, a);
+            int rc = launch_scatter_best<P2GPolicy>(s, a);
             if (rc) return rc;
         }
     }
