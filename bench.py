@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the hot path (BASELINE.json metric: Mparticles/s for P2G+G2P).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4|c5]
 
 A step = one pass of the transfer hot path over the workload: hot_p2g (APIC scatter + DOF numbering + mass
 normalisation, a6+a7) followed by hot_g2p (gather + X/V/C/gradV write + F update, a23), particle state resident
@@ -42,10 +42,12 @@ def make_workload(name, rank=0, world=1):
         cells = (cells[0], cells[1] * world, cells[2])
         sc = scenes.block(cells, dx, ppc=ppc, origin_cells=(16, 16, 16), seed=0, **kw)
         return sc, f"{name.upper()} object extended {world}x along y: {cells[0]}x{cells[1]}x{cells[2]} cells ppc {ppc} ({len(sc['mass'])} particles), ONE object partitioned over {world} GPUs"
-    sc = {"c1": scenes.config_c1, "c2": scenes.config_c2, "c4": scenes.config_c4}[name](seed=rank)
-    desc = {"c1": "C1 box drop 18^3 cells ppc 8 (46 656 particles)",
-            "c2": "C2 twisting-bar block 22x165x22 cells ppc 12 (958 320 particles, 256^3-class SPGrid)",
-            "c4": "C4 column 100x400x25 cells ppc 8 (8.0 M particles, 512^3-class SPGrid)"}[name]
+    sc = {"c1": scenes.config_c1, "c2": scenes.config_c2, "c3": scenes.config_c3, "c4": scenes.config_c4, "c5": scenes.config_c5}[name](seed=rank)
+    desc = {"c1": "C1 box drop 18^3 cells ppc 8, reference Poisson-tile sampling",
+            "c2": "C2 twisting bar (test 777001): 3 boxes 0.12x0.3x0.12 at dx 0.12/23, ppc 12, reference Poisson-tile sampling, 256^3-class SPGrid",
+            "c3": "C3 faceless stand-in (sphere + box, dx 0.01, ppc 20)",
+            "c4": "C4 column 100x400x25 cells ppc 8, 512^3-class SPGrid",
+            "c5": "C5 stiff wheel stand-in (analytic torus R .25 r .06, E 200 GPa, ppc 12)"}[name] + f" ({len(sc['mass'])} particles)"
     return sc, desc
 
 
@@ -399,32 +401,61 @@ def run_ours(args):
     sim.timing(0)
 
     # ---- end-to-end leg: host buffers through the public API ------------------------------------------
-    host_in = [torch.from_numpy(np.ascontiguousarray(sc[k])).pin_memory() for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam")]
+    # Every step: H2D of that step's particle state (X, V, C, F from pinned host memory), sort, P2G, G2P(dt), D2H of the new
+    # state.  Masses, volumes and material parameters are uploaded once (hot_set_particles) and stay resident.  The state
+    # exchange is the pipelined one of the C ABI (hot_upload_state_async / hot_commit_state / hot_download_state_async /
+    # hot_wait_download): the upload of step k+1 and the download of step k run on the library's copy streams, one per PCIe
+    # direction, while step k computes; every step's copies are inside the timed region.
+    host_in = [torch.from_numpy(np.ascontiguousarray(sc[k])).pin_memory() for k in ("X", "V", "C", "F")]
     host_out = [torch.empty((n, c), dtype=torch.float64).pin_memory() for c in (3, 3, 9, 9)]
+    in_ptrs = [t.data_ptr() for t in host_in]
+    out_ptrs = [t.data_ptr() for t in host_out]
     h2d = sum(t.numel() * 8 for t in host_in)
     d2h = sum(t.numel() * 8 for t in host_out)
     dt = 1e-4
     e2e_steps = max(3, min(args.steps, 10))
+    sim.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
 
-    def e2e_step():
-        sim.set_particles_ptr(n, [t.data_ptr() for t in host_in])
-        sim.sortParticlesAndPolluteGrid()
-        sim.particlesToGrid()
-        sim.gridToParticles(dt, want_flags=False)
-        sim.get_particles_ptr([t.data_ptr() for t in host_out] + [None])
+    def e2e_run(steps):
+        sim.upload_state_async(in_ptrs)
+        for k in range(steps):
+            sim.commit_state()
+            if k + 1 < steps:
+                sim.upload_state_async(in_ptrs)           # next step's inputs: overlaps this step's compute and download
+            sim.sortParticlesAndPolluteGrid()
+            sim.particlesToGrid()
+            sim.gridToParticles(dt, want_flags=False)
+            sim.download_state_async(out_ptrs)            # (waits on the device for the previous download to drain the staging area)
+        sim.wait_download()
 
-    e2e_step()
+    e2e_run(2)
     barrier()
     n_kernel_leg_samples = len(sampler.samples)
     sampler.active = True                      # the e2e leg is a timed region as well
     ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_e2e0 = time.perf_counter()
     ea.record(stream)
-    for _ in range(e2e_steps):
-        e2e_step()
+    e2e_run(e2e_steps)                         # returns after the last download has landed in host memory (hot_wait_download)
     eb.record(stream)
+    torch.cuda.synchronize()
+    e2e_wall_ms = 1e3 * (time.perf_counter() - t_e2e0) / e2e_steps
+    e2e_ms = max(ea.elapsed_time(eb) / e2e_steps, e2e_wall_ms)   # device clock on the compute stream vs host clock around the whole run: the larger
     barrier()
     sampler.active = False
-    e2e_ms = ea.elapsed_time(eb) / e2e_steps
+    # serial variant of the same step for reference (round-1 definition: everything on one stream, all attributes re-uploaded)
+    host_all = [torch.from_numpy(np.ascontiguousarray(sc[k])).pin_memory() for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam")]
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record(stream)
+    for _ in range(3):
+        sim.set_particles_ptr(n, [t.data_ptr() for t in host_all])
+        sim.sortParticlesAndPolluteGrid()
+        sim.particlesToGrid()
+        sim.gridToParticles(dt, want_flags=False)
+        sim.get_particles_ptr(out_ptrs + [None])
+    eb.record(stream)
+    torch.cuda.synchronize()
+    e2e_serial_ms = ea.elapsed_time(eb) / 3
+    host_in = host_all
     # sort alone (reported, not part of the metric)
     sim.set_particles_ptr(n, [t.data_ptr() for t in host_in])
     sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -486,7 +517,9 @@ def run_ours(args):
                                        f"(interface nodes per rank pair boundary: {part['n_interface']})")},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "includes": "H2D from pinned host, sort, P2G, G2P(dt), D2H of X,V,C,F"},
+                    "ms_per_step": e2e_ms, "serial_ms_per_step": e2e_serial_ms,
+                    "includes": "per step: H2D of X,V,C,F from pinned host, sort, P2G, G2P(dt), D2H of X,V,C,F; upload of step k+1 / download of step k overlap step k "
+                                "(copy streams of the C ABI's pipelined state exchange); mass, vol, mu, lambda resident; wall clock over the whole pipelined run"},
             "gpu_launches": launches, "clocks": dict(sampler.result(), samples_kernel_leg=n_kernel_leg_samples), "sort_ms": sort_ms, "wall_s_timed_loop": wall,
             "vcycle_ms": (solver or {}).get("vcycle", {}).get("ms"), "hessian_apply_mf_ms": (solver or {}).get("hessian_apply_mf", {}).get("ms"),
             "solver_kernels": solver,
@@ -505,7 +538,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--cpu-reps", type=int, default=5)
     ap.add_argument("--no-solver", action="store_true", help="skip the solver-side kernel timings (V-cycle ms, Hessian apply ...)")
     args = ap.parse_args()

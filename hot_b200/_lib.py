@@ -78,6 +78,10 @@ def load_library(path=LIB_PATH):
         "hot_packed_add": (C.c_int, [vp, C.c_long, _c_u64_p, _c_u64_p, _c_u64_p]),
         "hot_set_particles": (C.c_int, [vp, C.c_long] + [vp] * 8),
         "hot_get_particles": (C.c_int, [vp] + [vp] * 5),
+        "hot_upload_state_async": (C.c_int, [vp] + [vp] * 4),
+        "hot_commit_state": (C.c_int, [vp]),
+        "hot_download_state_async": (C.c_int, [vp] + [vp] * 4),
+        "hot_wait_download": (C.c_int, [vp]),
         "hot_num_particles": (C.c_long, [vp]),
         "hot_sort_and_activate": (C.c_int, [vp]),
         "hot_num_groups": (C.c_long, [vp]),

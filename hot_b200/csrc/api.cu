@@ -29,6 +29,16 @@ __global__ void k_soa_to_aos(long n, int comps, const double* __restrict__ soa, 
     int c = (int)(t - s * comps);
     aos[(size_t)orig_id[s] * comps + c] = soa[c * stride + s];
 }
+// AoS in original order -> SoA rows in the CURRENT particle order (sorted slot s holds original particle orig_id[s])
+__global__ void k_aos_to_soa_perm(long n, int comps, const double* __restrict__ aos, size_t stride, const int* __restrict__ orig_id,
+    double* __restrict__ soa)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * comps) return;
+    long s = t / comps;
+    int c = (int)(t - s * comps);
+    soa[c * stride + s] = aos[(size_t)orig_id[s] * comps + c];
+}
 __global__ void k_fill1(long n, double a, double* v)
 {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,6 +134,10 @@ hot_sim* hot_create(double dx, double apic_rpic_ratio, double cfl, int device)
 void hot_destroy(hot_sim* s)
 {
     if (!s) return;
+    if (s->copy_in) cudaStreamDestroy(s->copy_in);
+    if (s->copy_out) cudaStreamDestroy(s->copy_out);
+    for (cudaEvent_t e : {s->ev_in_done, s->ev_in_free, s->ev_out_ready, s->ev_out_done})
+        if (e) cudaEventDestroy(e);
     if (s->hcount) cudaFreeHost(s->hcount);
     if (s->h_red) cudaFreeHost(s->h_red);
     delete s;
@@ -220,6 +234,97 @@ int hot_set_particles(hot_sim* s, long n, const double* X, const double* V, cons
     HOT_LAUNCHED(s);
     s->sorted = false;
     s->p2g_done = false;
+    HOT_CUDA(cudaStreamSynchronize(st)); // the caller's arrays may be released / overwritten when the call returns (pinned memory is copied asynchronously)
+    return 0;
+}
+
+// ---- pipelined particle state: upload of the next step and download of the previous one overlap the current step -------------
+static int ensure_copy_streams(hot_sim* s)
+{
+    if (s->copy_in) return 0;
+    HOT_CUDA(cudaStreamCreateWithFlags(&s->copy_in, cudaStreamNonBlocking));
+    HOT_CUDA(cudaStreamCreateWithFlags(&s->copy_out, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&s->ev_in_done, &s->ev_in_free, &s->ev_out_ready, &s->ev_out_done}) HOT_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return 0;
+}
+int hot_upload_state_async(hot_sim* s, const double* X, const double* V, const double* C, const double* F)
+{
+    const long n = s->N;
+    if (n <= 0) return fail(s, "hot_upload_state_async: call hot_set_particles first (masses, volumes and material parameters stay resident)");
+    if (!X || !V || !C || !F) return fail(s, "hot_upload_state_async: null array");
+    if (s->in_pending) return fail(s, "hot_upload_state_async: the previous upload has not been committed (hot_commit_state)");
+    int rc = ensure_copy_streams(s);
+    if (rc) return rc;
+    HOT_CUDA(s->stage_in.reserve(24 * (size_t)n));
+    if (s->in_free_recorded) HOT_CUDA(cudaStreamWaitEvent(s->copy_in, s->ev_in_free, 0)); // the last commit has read the staging area
+    const double* h[4] = {X, V, C, F};
+    const int comps[4] = {3, 3, 9, 9};
+    size_t off = 0;
+    for (int k = 0; k < 4; ++k) {
+        HOT_CUDA(cudaMemcpyAsync(s->stage_in.p + off, h[k], (size_t)n * comps[k] * sizeof(double), cudaMemcpyHostToDevice, s->copy_in));
+        off += (size_t)n * comps[k];
+    }
+    HOT_CUDA(cudaEventRecord(s->ev_in_done, s->copy_in));
+    s->in_pending = true;
+    return 0;
+}
+int hot_commit_state(hot_sim* s)
+{
+    if (!s->in_pending) return fail(s, "hot_commit_state: no upload in flight (hot_upload_state_async)");
+    const long n = s->N;
+    cudaStream_t st = s->stream;
+    HOT_CUDA(cudaStreamWaitEvent(st, s->ev_in_done, 0));
+    double* soa[4] = {s->P.X.p, s->P.V.p, s->P.C.p, s->P.F.p};
+    const int comps[4] = {3, 3, 9, 9};
+    size_t off = 0;
+    for (int k = 0; k < 4; ++k) {
+        k_aos_to_soa_perm<<<nblk(n * comps[k]), TPB, 0, st>>>(n, comps[k], s->stage_in.p + off, s->P.stride, s->P.orig_id.p, soa[k]);
+        HOT_LAUNCHED(s);
+        off += (size_t)n * comps[k];
+    }
+    HOT_CUDA(cudaEventRecord(s->ev_in_free, st));
+    s->in_free_recorded = true;
+    s->in_pending = false;
+    s->sorted = false;
+    s->p2g_done = false;
+    s->state_valid = s->hessian_valid = false;
+    return 0;
+}
+int hot_download_state_async(hot_sim* s, double* X, double* V, double* C, double* F)
+{
+    const long n = s->N;
+    if (n <= 0) return fail(s, "hot_download_state_async: no particles");
+    if (!X || !V || !C || !F) return fail(s, "hot_download_state_async: null array");
+    int rc = ensure_copy_streams(s);
+    if (rc) return rc;
+    HOT_CUDA(s->stage_out.reserve(24 * (size_t)n));
+    cudaStream_t st = s->stream;
+    if (s->out_pending) HOT_CUDA(cudaStreamWaitEvent(st, s->ev_out_done, 0)); // the previous download has drained the staging area
+    double* h[4] = {X, V, C, F};
+    const double* soa[4] = {s->P.X.p, s->P.V.p, s->P.C.p, s->P.F.p};
+    const int comps[4] = {3, 3, 9, 9};
+    size_t off = 0;
+    for (int k = 0; k < 4; ++k) {
+        k_soa_to_aos<<<nblk(n * comps[k]), TPB, 0, st>>>(n, comps[k], soa[k], s->P.stride, s->P.orig_id.p, s->stage_out.p + off);
+        HOT_LAUNCHED(s);
+        off += (size_t)n * comps[k];
+    }
+    HOT_CUDA(cudaEventRecord(s->ev_out_ready, st));
+    HOT_CUDA(cudaStreamWaitEvent(s->copy_out, s->ev_out_ready, 0));
+    off = 0;
+    for (int k = 0; k < 4; ++k) {
+        HOT_CUDA(cudaMemcpyAsync(h[k], s->stage_out.p + off, (size_t)n * comps[k] * sizeof(double), cudaMemcpyDeviceToHost, s->copy_out));
+        off += (size_t)n * comps[k];
+    }
+    HOT_CUDA(cudaEventRecord(s->ev_out_done, s->copy_out));
+    s->out_pending = true;
+    return 0;
+}
+int hot_wait_download(hot_sim* s)
+{
+    if (!s->out_pending) return 0;
+    HOT_CUDA(cudaEventSynchronize(s->ev_out_done));
+    s->out_pending = false;
     return 0;
 }
 
@@ -344,6 +449,7 @@ int hot_set_dv(hot_sim* s, const double* dv)
 {
     if (!s->p2g_done) return fail(s, "hot_set_dv: call hot_p2g first");
     HOT_CUDA(cudaMemcpyAsync(s->dv.p, dv, 3 * (size_t)s->num_nodes * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    HOT_CUDA(cudaStreamSynchronize(s->stream)); // caller's buffer may be released when the call returns
     return 0;
 }
 
@@ -459,7 +565,10 @@ int hot_restore_strain(hot_sim* s) { return restore_strain(s); }
 int hot_update_state(hot_sim* s, const double* dv, double* energy)
 {
     if (!s->p2g_done) return fail(s, "hot_update_state: call hot_p2g first");
-    if (dv) HOT_CUDA(cudaMemcpyAsync(s->dv.p, dv, 3 * (size_t)s->num_nodes * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (dv) {
+        HOT_CUDA(cudaMemcpyAsync(s->dv.p, dv, 3 * (size_t)s->num_nodes * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        HOT_CUDA(cudaStreamSynchronize(s->stream)); // caller's buffer may be released when the call returns
+    }
     return update_state(s, energy != nullptr, energy);
 }
 

@@ -108,6 +108,19 @@ class MpmSimulationB200:
         self._check(self._lib.hot_set_particles(self._h, n, *[C.c_void_p(int(p)) for p in ptrs]))
         self.N = n
 
+    # pipelined state exchange (hot_upload_state_async ... hot_wait_download): raw pointers of pinned host buffers X, V, C, F
+    def upload_state_async(self, ptrs):
+        self._check(self._lib.hot_upload_state_async(self._h, *[C.c_void_p(int(p)) for p in ptrs]))
+
+    def commit_state(self):
+        self._check(self._lib.hot_commit_state(self._h))
+
+    def download_state_async(self, ptrs):
+        self._check(self._lib.hot_download_state_async(self._h, *[C.c_void_p(int(p)) for p in ptrs]))
+
+    def wait_download(self):
+        self._check(self._lib.hot_wait_download(self._h))
+
     def get_particles_ptr(self, ptrs):
         self._check(self._lib.hot_get_particles(self._h, *[None if p is None else C.c_void_p(int(p)) for p in ptrs]))
 

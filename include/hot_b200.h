@@ -61,6 +61,18 @@ int hot_set_particles(hot_sim* h, long n, const double* X, const double* V, cons
     const double* F, const double* vol, const double* mu, const double* lambda);
 /* read back particle state in original order; any pointer may be NULL */
 int hot_get_particles(hot_sim* h, double* X, double* V, double* C, double* F, double* gradV);
+/* Pipelined exchange of the particle STATE (X, V, C, F; AoS, original order) with host buffers for a caller that keeps the
+ * particles on the host between steps (the reference owns them in DataManager arrays, Lib/Ziran/CS/DataStructure/DataManager.h;
+ * mass, volume and material parameters stay resident from hot_set_particles).  The transfers run on the library's own copy
+ * streams: hot_upload_state_async of step k+1 may be issued as soon as hot_commit_state of step k has been called, and
+ * hot_download_state_async returns at once, so both PCIe directions work while a step computes.
+ *   upload:   the host arrays must stay valid until hot_commit_state (which makes the handle's stream wait for the copy and
+ *             scatters the rows into the current particle order; the next call must be hot_sort_and_activate);
+ *   download: the host arrays are complete after hot_wait_download. */
+int hot_upload_state_async(hot_sim* h, const double* X, const double* V, const double* C, const double* F);
+int hot_commit_state(hot_sim* h);
+int hot_download_state_async(hot_sim* h, double* X, double* V, double* C, double* F);
+int hot_wait_download(hot_sim* h);
 long hot_num_particles(hot_sim* h);
 
 /* ---- a5: MpmSimulationBase::sortParticlesAndPolluteGrid (Lib/MPM/MpmSimulationBase.cpp:1066-1137) ---- */
