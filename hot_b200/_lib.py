@@ -76,6 +76,9 @@ def load_library(path=LIB_PATH):
         "hot_linear_offset": (C.c_int, [vp, C.c_long, _c_int_p, _c_u64_p]),
         "hot_linear_to_coord": (C.c_int, [vp, C.c_long, _c_u64_p, _c_int_p]),
         "hot_packed_add": (C.c_int, [vp, C.c_long, _c_u64_p, _c_u64_p, _c_u64_p]),
+        "hot_linear_offset_f32": (C.c_int, [vp, C.c_long, _c_int_p, _c_u64_p]),
+        "hot_linear_to_coord_f32": (C.c_int, [vp, C.c_long, _c_u64_p, _c_int_p]),
+        "hot_packed_add_f32": (C.c_int, [vp, C.c_long, _c_u64_p, _c_u64_p, _c_u64_p]),
         "hot_set_particles": (C.c_int, [vp, C.c_long] + [vp] * 8),
         "hot_get_particles": (C.c_int, [vp] + [vp] * 5),
         "hot_upload_state_async": (C.c_int, [vp] + [vp] * 4),

@@ -49,18 +49,33 @@ __global__ void k_iota_i(long n, int* v)
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) v[t] = (int)t;
 }
+// SPGrid_Mask of GridState<float,3> (64-byte record: data_bits 6, block 4x4x4; Lib/MPM/MpmGrid.h:14-34, SPGrid_Mask.h:31-52).  The
+// compute kernels are built for the reference binary's T = double (main.cpp:12); the float geometry is served for addressing only.
+struct GeoF32 {
+    static constexpr uint64_t xmask = 0x4924924924924c00ull, ymask = 0x2492492492492300ull, zmask = 0x92492492492490c0ull;
+};
+template <class G>
+__device__ inline uint64_t packed_add_g(uint64_t a, uint64_t b)
+{
+    const uint64_t w = ~(G::xmask | G::ymask | G::zmask);
+    return (((a | ~G::xmask) + (b & G::xmask)) & G::xmask) | (((a | ~G::ymask) + (b & G::ymask)) & G::ymask)
+        | (((a | ~G::zmask) + (b & G::zmask)) & G::zmask) | (((a | ~w) + (b & w)) & w);
+}
+template <class G>
 __global__ void k_mask_ops(int op, long n, const int* __restrict__ ijk_in, const unsigned long long* __restrict__ a,
     const unsigned long long* __restrict__ b, unsigned long long* __restrict__ out, int* __restrict__ ijk_out)
 {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    if (op == 0) out[t] = linear_offset(ijk_in[3 * t], ijk_in[3 * t + 1], ijk_in[3 * t + 2]);
+    if (op == 0)
+        out[t] = bit_spread((uint32_t)ijk_in[3 * t], G::xmask) | bit_spread((uint32_t)ijk_in[3 * t + 1], G::ymask)
+            | bit_spread((uint32_t)ijk_in[3 * t + 2], G::zmask);
     else if (op == 1) {
-        ijk_out[3 * t] = (int)bit_pack(a[t], Geo::xmask);
-        ijk_out[3 * t + 1] = (int)bit_pack(a[t], Geo::ymask);
-        ijk_out[3 * t + 2] = (int)bit_pack(a[t], Geo::zmask);
+        ijk_out[3 * t] = (int)bit_pack(a[t], G::xmask);
+        ijk_out[3 * t + 1] = (int)bit_pack(a[t], G::ymask);
+        ijk_out[3 * t + 2] = (int)bit_pack(a[t], G::zmask);
     }
-    else out[t] = packed_add(a[t], b[t]);
+    else out[t] = packed_add_g<G>(a[t], b[t]);
 }
 // particle_sorter / particle_order / particle_base_offset views of the device state
 __global__ void k_export_sort(long n, const uint64_t* __restrict__ keys, int* __restrict__ order, unsigned long long* __restrict__ base_offset)
@@ -183,7 +198,7 @@ const char* hot_timing_name(int c)
 }
 
 static int mask_op(hot_sim* s, int op, long n, const int* ijk_in, const unsigned long long* a, const unsigned long long* b,
-    unsigned long long* out, int* ijk_out)
+    unsigned long long* out, int* ijk_out, bool f32 = false)
 {
     if (n <= 0) return 0;
     HOT_CUDA(s->stage_u.reserve(3 * n));
@@ -192,7 +207,8 @@ static int mask_op(hot_sim* s, int op, long n, const int* ijk_in, const unsigned
     if (ijk_in) HOT_CUDA(cudaMemcpyAsync(s->stage_i.p, ijk_in, 3 * n * sizeof(int), cudaMemcpyHostToDevice, s->stream));
     if (a) HOT_CUDA(cudaMemcpyAsync(da, a, n * sizeof(*a), cudaMemcpyHostToDevice, s->stream));
     if (b) HOT_CUDA(cudaMemcpyAsync(db, b, n * sizeof(*b), cudaMemcpyHostToDevice, s->stream));
-    k_mask_ops<<<nblk(n), TPB, 0, s->stream>>>(op, n, s->stage_i.p, da, db, dout, s->stage_i.p);
+    if (f32) k_mask_ops<GeoF32><<<nblk(n), TPB, 0, s->stream>>>(op, n, s->stage_i.p, da, db, dout, s->stage_i.p);
+    else k_mask_ops<Geo><<<nblk(n), TPB, 0, s->stream>>>(op, n, s->stage_i.p, da, db, dout, s->stage_i.p);
     HOT_LAUNCHED(s);
     if (out) return d2h(s, out, dout, n);
     return d2h(s, ijk_out, s->stage_i.p, 3 * n);
@@ -202,6 +218,12 @@ int hot_linear_to_coord(hot_sim* s, long n, const unsigned long long* off, int* 
 int hot_packed_add(hot_sim* s, long n, const unsigned long long* a, const unsigned long long* b, unsigned long long* out)
 {
     return mask_op(s, 2, n, nullptr, a, b, out, nullptr);
+}
+int hot_linear_offset_f32(hot_sim* s, long n, const int* ijk, unsigned long long* out) { return mask_op(s, 0, n, ijk, nullptr, nullptr, out, nullptr, true); }
+int hot_linear_to_coord_f32(hot_sim* s, long n, const unsigned long long* off, int* ijk) { return mask_op(s, 1, n, nullptr, off, nullptr, nullptr, ijk, true); }
+int hot_packed_add_f32(hot_sim* s, long n, const unsigned long long* a, const unsigned long long* b, unsigned long long* out)
+{
+    return mask_op(s, 2, n, nullptr, a, b, out, nullptr, true);
 }
 
 int hot_set_particles(hot_sim* s, long n, const double* X, const double* V, const double* mass, const double* C, const double* F,

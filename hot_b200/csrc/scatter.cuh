@@ -257,6 +257,37 @@ int launch_column_scatter(Sim* s, const typename Policy::Args& a)
 // Policy::RECP doubles; the thread re-derives the weights) so that 4-5 CTAs fit per SM (P2G 104 -> 96 us, force scatter
 // 103 -> 89 us at C2).
 constexpr int PS_THREADS = 3 * Geo::E; // 96
+constexpr int PS_NCHP = 4; // parked channels per (node, thread), padded
+// Straight-line gather combine of the plane form.  Parked sums lie as [node (j,k) of the thread's plane][cell * 3 + plane][channel];
+// lane (tz, ch) of a warp adds up the tile nodes (tx = 0..3, TY, tz): node (tx, ty, tz) receives node (j, k) of plane i of cell
+// (tx - i, ty - j, tz - k).  Every shared-memory offset is a compile-time constant plus one per-lane term (12 tz + ch), the
+// three z-sources are predicated per lane: no loops, no index arithmetic (the nested-loop form this replaces was 20 % of the
+// kernel's instructions).  Lanes (tz, ch) of a half warp hit 16 different 8-byte banks.
+template <int TY>
+__device__ __forceinline__ void plane_combine(const double* __restrict__ park, int lane_off, bool pk0, bool pk1, bool pk2, double* __restrict__ out)
+{
+#pragma unroll
+    for (int tx = 0; tx < 4; ++tx) {
+        double sum = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int cx = tx - i;
+            if (cx < 0 || cx >= Geo::BX) continue;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int cy = TY - j;
+                if (cy < 0 || cy >= Geo::BY) continue;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int off = ((j * 3 + k) * PS_THREADS + (cx * Geo::BY + cy) * Geo::BZ * 3 + i) * PS_NCHP - k * 3 * PS_NCHP;
+                    const bool pk = k == 0 ? pk0 : (k == 1 ? pk1 : pk2);
+                    if (pk) sum += park[off + lane_off];
+                }
+            }
+        }
+        out[tx] = sum;
+    }
+}
 constexpr int PS_CAP = 384; // particles per prep pass: a full page at 12 particles per cell
 template <class Policy>
 constexpr size_t ps_smem_bytes()
@@ -321,39 +352,40 @@ __global__ void __launch_bounds__(PS_THREADS, Policy::PMINB) k_plane2_scatter(ty
         for (int p = pb; p < pe; ++p) Policy::accumulate_plane(args, cs_smem + (size_t)p * Policy::RECP, i, di, acc);
     }
     Policy::prefetch(args, pf_first, pf_end, tid, THREADS);
-    __syncthreads(); // records dead -> reuse as the contribution array [ch][jk][cell * 3 + i]
+    __syncthreads(); // records dead -> reuse as the parked sums [jk][cell * 3 + i][ch]
+    {
+        double* park = cs_smem + (size_t)(c * 3 + i) * PS_NCHP;
 #pragma unroll
-    for (int a = 0; a < 9; ++a)
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) cs_smem[(ch * 9 + a) * THREADS + c * 3 + i] = acc[a][ch];
+        for (int a = 0; a < 9; ++a) {
+            double* d = park + (size_t)a * THREADS * PS_NCHP;
+            sts2(d, acc[a][0], NCH > 1 ? acc[a][1 % NCH] : 0.0);
+            if (NCH > 2) sts2(d + 2, acc[a][2 % NCH], NCH > 3 ? acc[a][3 % NCH] : 0.0);
+        }
+    }
     __syncthreads();
-    // gather combine: tile node (tx, ty, tz) receives node (j, k) of plane i of cell (tx - i, ty - j, tz - k); the source index
-    // moves by a constant per loop step (no index table, no dependent loads).  Work item = (node, half of the channels):
-    // 2 x 144 items over 96 threads.
-    constexpr int CH2 = (NCH + 1) / 2;
-    for (int it = tid; it < 2 * Geo::TILE; it += THREADS) {
-        const int n = it % Geo::TILE, c0 = (it / Geo::TILE) * CH2;
-        if (c0 >= NCH) break;
-        const int tz = n % Geo::TZ, ty = (n / Geo::TZ) % Geo::TY, tx = n / (Geo::TZ * Geo::TY);
-        const int i0 = max(0, tx - (Geo::BX - 1)), i1 = min(2, tx), j0 = max(0, ty - (Geo::BY - 1)), j1 = min(2, ty),
-                  k0 = max(0, tz - (Geo::BZ - 1)), k1 = min(2, tz);
-        double sum[CH2];
+    // static gather combine: warp w owns the tile rows ty in {2,0} / {3,5} / {1,4} (24 source pairs each), lane = (tz, channel)
+    static_assert(Geo::BX == 2 && Geo::BY == 4 && Geo::BZ == 4 && NCH <= PS_NCHP, "the combine is written for the 2x4x4 page");
+    const int w = tid >> 5, lane = tid & 31;
+    const int ctz = lane / PS_NCHP, cch = lane - ctz * PS_NCHP;
+    const bool c_on = ctz < Geo::TZ && cch < NCH;
+    const int lane_off = 3 * PS_NCHP * ctz + cch;
+    const bool pk0 = c_on && ctz < Geo::BZ, pk1 = c_on && ctz >= 1 && ctz - 1 < Geo::BZ, pk2 = c_on && ctz >= 2 && ctz - 2 < Geo::BZ;
+    double out[8];
+    int tya, tyb;
+    if (w == 0) { plane_combine<2>(cs_smem, lane_off, pk0, pk1, pk2, out); plane_combine<0>(cs_smem, lane_off, pk0, pk1, pk2, out + 4); tya = 2; tyb = 0; }
+    else if (w == 1) { plane_combine<3>(cs_smem, lane_off, pk0, pk1, pk2, out); plane_combine<5>(cs_smem, lane_off, pk0, pk1, pk2, out + 4); tya = 3; tyb = 5; }
+    else { plane_combine<1>(cs_smem, lane_off, pk0, pk1, pk2, out); plane_combine<4>(cs_smem, lane_off, pk0, pk1, pk2, out + 4); tya = 1; tyb = 4; }
+    if (!c_on) return;
 #pragma unroll
-        for (int ch = 0; ch < CH2; ++ch) sum[ch] = 0.0;
-        for (int pi = i0; pi <= i1; ++pi)
-            for (int j = j0; j <= j1; ++j) {
-                int src = (j * 3 + k0) * THREADS + (((((tx - pi) << Geo::yb) | (ty - j)) << Geo::zb) | (tz - k0)) * 3 + pi;
-                for (int k = k0; k <= k1; ++k, src += THREADS - 3) {
+    for (int h = 0; h < 2; ++h) {
+        const int ty = h == 0 ? tya : tyb;
 #pragma unroll
-                    for (int ch = 0; ch < CH2; ++ch)
-                        if (c0 + ch < NCH) sum[ch] += cs_smem[(c0 + ch) * 9 * THREADS + src];
-                }
-            }
-        const long a = Policy::DOF ? (long)tile_dof[(size_t)g * Geo::TILE + n] : tile_to_grid(n, s_nbr);
-        if (a >= 0) {
-#pragma unroll
-            for (int ch = 0; ch < CH2; ++ch)
-                if (c0 + ch < NCH && sum[ch] != 0.0) Policy::flush1(args, a, c0 + ch, sum[ch]);
+        for (int tx = 0; tx < 4; ++tx) {
+            const double v = out[h * 4 + tx];
+            if (v == 0.0) continue;
+            const int n = (tx * Geo::TY + ty) * Geo::TZ + ctz;
+            const long a = Policy::DOF ? (long)tile_dof[(size_t)g * Geo::TILE + n] : tile_to_grid(n, s_nbr);
+            if (a >= 0) Policy::flush1(args, a, cch, v);
         }
     }
 }

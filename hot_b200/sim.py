@@ -73,26 +73,27 @@ class MpmSimulationB200:
         return {self._lib.hot_timing_name(i).decode(): (ms[i], int(cnt[i])) for i in range(k) if cnt[i]}
 
     # ---- SPGrid addressing
-    def linear_offset(self, ijk):
+    def linear_offset(self, ijk, fp32=False):
         ijk = np.ascontiguousarray(ijk, dtype=np.int32).reshape(-1, 3)
         out = np.empty(len(ijk), dtype=np.uint64)
-        self._check(self._lib.hot_linear_offset(self._h, len(ijk), ijk.ctypes.data_as(C.POINTER(C.c_int)),
+        self._check((self._lib.hot_linear_offset_f32 if fp32 else self._lib.hot_linear_offset)(self._h, len(ijk), ijk.ctypes.data_as(C.POINTER(C.c_int)),
                                                 out.ctypes.data_as(C.POINTER(C.c_ulonglong))))
         return out
 
-    def linear_to_coord(self, off):
+    def linear_to_coord(self, off, fp32=False):
         off = np.ascontiguousarray(off, dtype=np.uint64)
         out = np.empty((len(off), 3), dtype=np.int32)
-        self._check(self._lib.hot_linear_to_coord(self._h, len(off), off.ctypes.data_as(C.POINTER(C.c_ulonglong)),
+        self._check((self._lib.hot_linear_to_coord_f32 if fp32 else self._lib.hot_linear_to_coord)(self._h, len(off), off.ctypes.data_as(C.POINTER(C.c_ulonglong)),
                                                   out.ctypes.data_as(C.POINTER(C.c_int))))
         return out
 
-    def packed_add(self, a, b):
+    def packed_add(self, a, b, fp32=False):
         a = np.ascontiguousarray(a, dtype=np.uint64)
         b = np.ascontiguousarray(b, dtype=np.uint64)
         out = np.empty(len(a), dtype=np.uint64)
         p = C.POINTER(C.c_ulonglong)
-        self._check(self._lib.hot_packed_add(self._h, len(a), a.ctypes.data_as(p), b.ctypes.data_as(p), out.ctypes.data_as(p)))
+        self._check((self._lib.hot_packed_add_f32 if fp32 else self._lib.hot_packed_add)(self._h, len(a), a.ctypes.data_as(p), b.ctypes.data_as(p),
+                                                                                          out.ctypes.data_as(p)))
         return out
 
     # ---- particles

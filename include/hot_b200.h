@@ -51,6 +51,11 @@ int hot_linear_offset(hot_sim* h, long n, const int* ijk, unsigned long long* ou
 int hot_linear_to_coord(hot_sim* h, long n, const unsigned long long* off, int* ijk);
 /* Packed_Add :237-245 */
 int hot_packed_add(hot_sim* h, long n, const unsigned long long* a, const unsigned long long* b, unsigned long long* out);
+/* the same three operations for SPGrid_Mask of GridState<float,3> (64-byte record, data_bits 6, 4x4x4 pages: Lib/MPM/MpmGrid.h:14-34).
+ * Addressing only: the compute kernels follow the reference binary's T = double (Projects/multigrid/main.cpp:12). */
+int hot_linear_offset_f32(hot_sim* h, long n, const int* ijk, unsigned long long* out);
+int hot_linear_to_coord_f32(hot_sim* h, long n, const unsigned long long* off, int* ijk);
+int hot_packed_add_f32(hot_sim* h, long n, const unsigned long long* a, const unsigned long long* b, unsigned long long* out);
 
 /* ---- particles --------------------------------------------------------------------------------- */
 /* Upload of particles.X/V/mass ("P","V","m": Lib/Ziran/Math/Geometry/Particles.h:8-45), the APIC matrix C,

@@ -23,13 +23,14 @@ def _pair(hot, oracle, sc, **kw):
     return g, o
 
 
-@pytest.mark.parametrize("fp32", [False])
+@pytest.mark.parametrize("fp32", [False, True])
 def test_spgrid_addressing_golden(hot, fp32):
-    g = np.load(os.path.join(ROOT, "tests", "golden", "spgrid_fp64.npz"))
+    """golden vectors generated from the reference's own SPGrid core (tests/golden/make_spgrid_golden.py), both GridState geometries"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "spgrid_fp32.npz" if fp32 else "spgrid_fp64.npz"))
     s = hot.MpmSimulationB200(0.1)
-    assert (s.linear_offset(g["ijk"]) == g["off"]).all()
-    assert (s.linear_to_coord(g["off"]) == g["ijk"]).all()
-    assert (s.packed_add(g["add_a"], g["add_b"]) == g["add_sum"]).all()
+    assert (s.linear_offset(g["ijk"], fp32) == g["off"]).all()
+    assert (s.linear_to_coord(g["off"], fp32) == g["ijk"]).all()
+    assert (s.packed_add(g["add_a"], g["add_b"], fp32) == g["add_sum"]).all()
 
 
 CASES = {
