@@ -315,8 +315,10 @@ int launch_scatter_ws(Sim* s, const typename Policy::Args& a)
     return 0;
 }
 
-// which skeleton a scatter uses: the policy's measured default (scatter.cuh), HOT_SCATTER = plane | column to force one of the
-// CTA-per-group forms, HOT_SCATTER = ws for the persistent TMA form (measured slower so far)
+// which skeleton a scatter uses: the policy's measured default of scatter.cuh (CTA per page group, register-staged rows),
+// HOT_SCATTER = plane | column to force one of its two forms, HOT_SCATTER = ws for the persistent TMA form above.
+// Measured on C2 (P2G, B200): plane form 81 us, persistent TMA form 101 us, a CTA-per-item variant of it with register-staged
+// rows 85 us (profiles/r2_scatter_experiments.md) - the persistent form stays selectable for A/B runs.
 template <class Policy>
 int launch_scatter_best(Sim* s, const typename Policy::Args& a)
 {
