@@ -581,6 +581,29 @@ int hot_get_dv(hot_sim* s, double* dv)
     if (!s->p2g_done) return fail(s, "hot_get_dv: call hot_p2g first");
     return d2h(s, dv, s->dv.p, 3 * (size_t)s->num_nodes);
 }
+// CorotatedIsotropic<T,3>::{updateScratch, psi, firstPiola, firstPiolaDifferential, firstPiolaDerivative} on n deformation gradients
+int hot_corotated_eval(hot_sim* s, long n, const double* F, double mu, double lambda, int project, const double* dF, double* psi, double* P,
+    double* dP, double* dPdF, double* U, double* sigma, double* V)
+{
+    if (n <= 0 || !F) return fail(s, "hot_corotated_eval: need n > 0 deformation gradients");
+    if (dP && !dF) return fail(s, "hot_corotated_eval: dP requested without dF");
+    if ((U != nullptr) != (V != nullptr)) return fail(s, "hot_corotated_eval: U and V come together");
+    // layout of the staging area: F 9 | dF 9 | psi 1 | P 9 | dP 9 | dPdF 81 | U 9 | sigma 3 | V 9  = 139 doubles per item
+    HOT_CUDA(s->stage.reserve(139 * (size_t)n));
+    double* d = s->stage.p;
+    double *dF_ = d + 9 * n, *psi_ = d + 18 * n, *P_ = d + 19 * n, *dP_ = d + 28 * n, *H_ = d + 37 * n, *U_ = d + 118 * n, *s_ = d + 127 * n, *V_ = d + 130 * n;
+    HOT_CUDA(cudaMemcpyAsync(d, F, 9 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (dF) HOT_CUDA(cudaMemcpyAsync(dF_, dF, 9 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    int rc = corotated_eval(s, n, d, mu, lambda, project, dF ? dF_ : nullptr, psi ? psi_ : nullptr, P ? P_ : nullptr, dP ? dP_ : nullptr,
+        dPdF ? H_ : nullptr, U ? U_ : nullptr, sigma ? s_ : nullptr, V ? V_ : nullptr);
+    if (rc) return rc;
+    struct Item { double* h; const double* dev; size_t per; };
+    const Item items[] = {{psi, psi_, 1}, {P, P_, 9}, {dP, dP_, 9}, {dPdF, H_, 81}, {U, U_, 9}, {sigma, s_, 3}, {V, V_, 9}};
+    for (const Item& it : items)
+        if (it.h) HOT_CUDA(cudaMemcpyAsync(it.h, it.dev, it.per * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
 int hot_backup_strain(hot_sim* s) { return backup_strain(s); }
 int hot_restore_strain(hot_sim* s) { return restore_strain(s); }
 

@@ -603,7 +603,74 @@ __global__ void k_cn_finish(int n, const double* __restrict__ mass, double facto
 
 } // namespace
 
+// CorotatedIsotropic<T,3> evaluated per deformation gradient with the device routines of the force kernels (svd3, cofactor3,
+// corotated_blocks, blocks_contract): updateScratch + psi + firstPiola + firstPiolaDifferential + firstPiolaDerivative
+// (CorotatedIsotropic.h:78-230).  Arrays are column-major per item; any output may be null.
+__global__ void k_corotated_eval(long n, const double* __restrict__ F, double mu, double lambda, int project, const double* __restrict__ dF,
+    double* __restrict__ psi, double* __restrict__ P, double* __restrict__ dP, double* __restrict__ dPdF, double* __restrict__ Uo,
+    double* __restrict__ sigo, double* __restrict__ Vo)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double Fm[9], U[9], V[9], sig[3], R[9], cof[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) Fm[q] = F[9 * t + q];
+    svd3(Fm, U, sig, V);
+    mm_bt(U, V, R);
+    cofactor3(Fm, cof);
+    const double J = sig[0] * sig[1] * sig[2];
+    double n2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        const double d = Fm[q] - R[q];
+        n2 += d * d;
+        if (P) P[9 * t + q] = 2.0 * mu * d + lambda * (J - 1.0) * cof[q];
+    }
+    if (psi) psi[t] = mu * n2 + 0.5 * lambda * (J - 1.0) * (J - 1.0);
+    if (Uo)
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { Uo[9 * t + q] = U[q]; Vo[9 * t + q] = V[q]; }
+    if (sigo)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) sigo[3 * t + d] = sig[d];
+    if (!dP && !dPdF) return;
+    HessBlocks hb;
+    corotated_blocks(sig, mu, lambda, project != 0, hb);
+    auto differential = [&](const double* dFm, double* out) { // dP = U (dPdF_Sigma : (U^T dF V)) V^T
+        double T1[9], D[9], K[9], T2[9];
+        mm_at(U, dFm, T1);
+        mm(T1, V, D);
+        blocks_contract(hb, D, K);
+        mm(U, K, T2);
+        mm_bt(T2, V, out);
+    };
+    if (dP) {
+        double d[9], o[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) d[q] = dF[9 * t + q];
+        differential(d, o);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) dP[9 * t + q] = o[q];
+    }
+    if (dPdF)
+        for (int rs = 0; rs < 9; ++rs) {
+            double d[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, o[9];
+            d[rs] = 1.0;
+            differential(d, o);
+            for (int ij = 0; ij < 9; ++ij) dPdF[81 * t + ij + 9 * rs] = o[ij];
+        }
+}
+
 // FBasedMpmForceHelper::backupStrain / restoreStrain, FBasedMpmForceHelper.cpp:25-44
+int corotated_eval(Sim* s, long n, const double* F, double mu, double lambda, int project, const double* dF, double* psi, double* P,
+    double* dP, double* dPdF, double* U, double* sigma, double* V)
+{
+    if (n <= 0) return 0;
+    k_corotated_eval<<<nblk(n), TPB, 0, s->stream>>>(n, F, mu, lambda, project, dF, psi, P, dP, dPdF, U, sigma, V);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+
 int backup_strain(Sim* s)
 {
     if (!s->sorted) return fail(s, "backupStrain: call hot_sort_and_activate first");

@@ -219,6 +219,20 @@ class MpmSimulationB200:
         self._check(self._lib.hot_get_dv(self._h, _ptr(out)))
         return out
 
+    def corotated_eval(self, F, mu, lam, project=True, dF=None, single=False):
+        """CorotatedIsotropic<T,3> on deformation gradients F (n x 3 x 3, numpy row-major): psi, P, dP(dF), dense dPdF, U, sigma, V"""
+        F = np.ascontiguousarray(np.asarray(F, dtype=np.float64).reshape(-1, 3, 3).transpose(0, 2, 1))   # column-major per item
+        n = len(F)
+        dFb = None if dF is None else np.ascontiguousarray(np.asarray(dF, dtype=np.float64).reshape(-1, 3, 3).transpose(0, 2, 1))
+        psi = np.empty(n); P = np.empty((n, 9)); dP = np.empty((n, 9)); H = np.empty((n, 81)); U = np.empty((n, 9)); sg = np.empty((n, 3)); V = np.empty((n, 9))
+        self._check(self._lib.hot_corotated_eval(self._h, n, _ptr(F), float(mu), float(lam), int(project), _ptr(dFb), _ptr(psi), _ptr(P),
+                                                 _ptr(dP) if dF is not None else None, _ptr(H), _ptr(U), _ptr(sg), _ptr(V)))
+        t = lambda a: a.reshape(n, 3, 3).transpose(0, 2, 1).copy()
+        out = dict(psi=psi, P=t(P), dP=t(dP) if dF is not None else None, dPdF=H.reshape(n, 9, 9).transpose(0, 2, 1).copy(), U=t(U), sigma=sg, V=t(V))
+        if single:
+            out = {k: (v[0] if v is not None else None) for k, v in out.items()}
+        return out
+
     def backupStrain(self):
         self._check(self._lib.hot_backup_strain(self._h))
 

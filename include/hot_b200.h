@@ -146,6 +146,12 @@ int hot_set_project(hot_sim* h, int project);
 int hot_set_bc(hot_sim* h, int mode, int n_bc, const int* node_id, const double* P, const double* R, const double* Rinv,
     const int* slip, const double* dv_bc);
 int hot_get_dv(hot_sim* h, double* dv);
+/* CorotatedIsotropic<T,3> as an operator on n deformation gradients (Lib/Ziran/Physics/ConstitutiveModel/CorotatedIsotropic.h:78-230):
+ * updateScratch (QR-SVD conventions of ImplicitQRSVD.h: det U = det V = +1, sigma sorted, sign on the last) + psi + firstPiola +
+ * firstPiolaDifferential (dP for the given dF) + firstPiolaDerivative (dense 9x9 dPdF, column-major, index ij = i + 3 j), with or
+ * without the PSD projection of --project.  3x3 blocks are column-major like Eigen's; every output pointer may be NULL. */
+int hot_corotated_eval(hot_sim* h, long n, const double* F, double mu, double lambda, int project, const double* dF, double* psi,
+    double* P, double* dP, double* dPdF, double* U, double* sigma, double* V);
 /* FBasedMpmForceHelper::backupStrain / restoreStrain (Lib/MPM/Force/FBasedMpmForceHelper.cpp:25-44) */
 int hot_backup_strain(hot_sim* h);
 int hot_restore_strain(hot_sim* h);
