@@ -111,6 +111,8 @@ def load_library(path=LIB_PATH):
         "hot_set_bc": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
         "hot_get_dv": (C.c_int, [vp, vp]),
         "hot_corotated_eval": (C.c_int, [vp, C.c_long, vp, C.c_double, C.c_double, C.c_int] + [vp] * 8),
+        "hot_strain_energy": (C.c_int, [vp, vp]),
+        "hot_get_strain_backup": (C.c_int, [vp, vp]),
         "hot_backup_strain": (C.c_int, [vp]),
         "hot_restore_strain": (C.c_int, [vp]),
         "hot_update_state": (C.c_int, [vp, vp, _c_double_p]),

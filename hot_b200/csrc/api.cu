@@ -637,6 +637,22 @@ int hot_get_stress(hot_sim* s, double* vPFnT, double* F)
     return 0;
 }
 
+int hot_strain_energy(hot_sim* s, double* energy)
+{
+    if (!energy) return fail(s, "hot_strain_energy: null output");
+    return strain_energy(s, energy);
+}
+// Fn of FBasedMpmForceHelper (the strain saved by backupStrain), original particle order
+int hot_get_strain_backup(hot_sim* s, double* Fn)
+{
+    if (!s->strain_backed_up) return fail(s, "hot_get_strain_backup: call hot_backup_strain first");
+    const long n = s->N;
+    HOT_CUDA(s->stage.reserve(28 * (size_t)n));
+    k_soa_to_aos<<<nblk(n * 9), TPB, 0, s->stream>>>(n, 9, s->P.Fn.p, s->P.stride, s->P.orig_id.p, s->stage.p);
+    HOT_LAUNCHED(s);
+    return d2h(s, Fn, s->stage.p, 9 * (size_t)n);
+}
+
 int hot_compute_residual(hot_sim* s, double* r)
 {
     int rc = upload_dof(s, s->work[1], nullptr);

@@ -787,6 +787,20 @@ int update_state(Sim* s, bool want_energy, double* energy)
     return 0;
 }
 
+// FBasedMpmForceHelper::totalEnergy (FBasedMpmForceHelper.cpp:116-136): sum_p vol psi(F_p) of the last updateState (this rank's particles)
+int strain_energy(Sim* s, double* e)
+{
+    if (!s->state_valid) return fail(s, "totalEnergy: call hot_update_state first");
+    HOT_CUDA(s->red_out.reserve(64));
+    if (!s->h_red) HOT_CUDA(cudaMallocHost((void**)&s->h_red, 64 * sizeof(double)));
+    int rc = reduce_to<1>(s, s->g1 - s->g0, SumF{s->group_psi.p}, s->red_out.p + 8, nullptr);
+    if (rc) return rc;
+    HOT_CUDA(cudaMemcpyAsync(s->h_red, s->red_out.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
+    *e = s->h_red[0];
+    return 0;
+}
+
 // One particle->grid scatter of this rank's page groups into a DOF array.  Single GPU: straight into `out` (which already
 // holds the node-local terms).  Partitioned: into a zeroed scratch array, summed over the ranks on the interface nodes, then
 // added to `out` - so node-local terms are counted once.

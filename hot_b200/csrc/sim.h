@@ -291,6 +291,7 @@ int apply_plasticity(Sim* s);
 // force.cu -- all pointers are DEVICE pointers to DOF vectors (n_nodes x 3)
 int corotated_eval(Sim* s, long n, const double* F, double mu, double lambda, int project, const double* dF, double* psi, double* P,
     double* dP, double* dPdF, double* U, double* sigma, double* V); // device arrays
+int strain_energy(Sim* s, double* e);
 int backup_strain(Sim* s);
 int restore_strain(Sim* s);
 int set_bc(Sim* s, int mode, int n_bc, const int* node_id, const double* P, const double* R, const double* Rinv, const int* slip,

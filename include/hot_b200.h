@@ -160,6 +160,10 @@ int hot_restore_strain(hot_sim* h);
 int hot_update_state(hot_sim* h, const double* dv, double* energy);
 /* scratch_stress = vol P Fn^T and the trial F, original particle order (FBasedMpmForceHelper.cpp:72-97) */
 int hot_get_stress(hot_sim* h, double* vPFnT, double* F);
+/* FBasedMpmForceHelper::totalEnergy (Lib/MPM/Force/FBasedMpmForceHelper.cpp:116-136): sum_p vol psi(F_p) of the last updateState */
+int hot_strain_energy(hot_sim* h, double* energy);
+/* FBasedMpmForceHelper::Fn (FBasedMpmForceHelper.h:29): the strain saved by backupStrain, original particle order, 9 per particle */
+int hot_get_strain_backup(hot_sim* h, double* Fn);
 /* ImplicitSolverObjective::computeResidual (ImplicitSolver.h:128-155) */
 int hot_compute_residual(hot_sim* h, double* residual);
 /* objective.project (MultigridSimulation.h:104-125), in place */

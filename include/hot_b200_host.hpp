@@ -403,6 +403,120 @@ private:
     long N = 0;
 };
 
+// ---- MpmForceHelperBase surface (Lib/MPM/Force/MpmForceHelperBase.h:18-46) of FBasedMpmForceHelper<CorotatedIsotropic<T,3>> ----------
+// The helper virtuals the reference's MpmForceBase / ImplicitSolverObjective call.  On the device the helper's per-particle state
+// (F, Fn, scratch = SVD, vol P Fn^T) lives in sorted SoA rows of the handle, so the methods are thin: what the reference computes
+// in a helper call is computed by the fused kernels behind the C ABI, and a method that has no separate device stage says so.
+class FBasedMpmForceHelperB200 {
+public:
+    using Hessian = std::array<double, 81>; // Eigen::Matrix<T, 9, 9>, column-major, index ij = i + 3 j (CorotatedIsotropic.h:198-227)
+    explicit FBasedMpmForceHelperB200(MpmSimulationB200& sim_) : sim(sim_) {}
+    void reinitialize() {}                                                                   // FBasedMpmForceHelper.cpp:20-23 (scratch is per step here)
+    void backupStrain() { sim.check(hot_backup_strain(sim.handle())); }                     // :25-33
+    void restoreStrain() { sim.check(hot_restore_strain(sim.handle())); }                   // :35-44
+    bool needGradVn() { return false; }
+    // updateImplicitState (:72-97): scratch update + vol P Fn^T of every particle; vPFnT (9 N, original order) is optional.
+    // evolveStrain with the trial dv precedes it in ImplicitSolverObjective::updateState; both are one kernel here.
+    void updateImplicitState(double* vPFnT = nullptr)
+    {
+        sim.check(hot_update_state(sim.handle(), nullptr, nullptr));
+        if (vPFnT) sim.check(hot_get_stress(sim.handle(), vPFnT, nullptr));
+    }
+    // evolveStrain (:100-114): F = (I + dt gradV) Fn.  Fused into hot_update_state (trial states) and hot_g2p (end of step): no stage of its own.
+    void evolveStrain(double /*dt*/) {}
+    double totalEnergy() // :116-136
+    {
+        double e = 0;
+        sim.check(hot_strain_energy(sim.handle(), &e));
+        return e;
+    }
+    // computeStressDifferential (:138-160) + the rasterisation that follows it in MpmForceBase::addScaledForceDifferential
+    // (MpmForceBase.cpp:261-306): f += scale * df(x) for a DOF field x
+    void computeStressDifferential(double scale, const TVStack& x, TVStack& f)
+    {
+        sim.check(hot_add_scaled_force_differentials(sim.handle(), scale, x.data(), f.data()));
+    }
+    // runLambdaWithDifferential (FBasedMpmForceHelper.h:63-120): func(i, dPdF_i, Fn_i, -1, -1, false) for every particle, in the
+    // reference's order (8 colour passes over the page groups, sorted order inside a group).  dPdF comes from the device model
+    // (hot_corotated_eval); opt 1 stores it, opt 2 reuses the stored one.
+    void runLambdaWithDifferential(const std::function<void(int, const Hessian&, const TM&, double, double, bool)>& func, int opt = 0)
+    {
+        hot_sim* h = sim.handle();
+        const long n = sim.particleCount();
+        std::vector<double> F(9 * (size_t)n), Fn(9 * (size_t)n);
+        sim.check(hot_get_particles(h, nullptr, nullptr, nullptr, F.data(), nullptr));
+        sim.check(hot_get_strain_backup(h, Fn.data()));
+        if (opt < 2) evaluate(F, stored);
+        walk([&](int i) {
+            Hessian H;
+            TM fn;
+            std::copy(stored.begin() + 81 * (size_t)i, stored.begin() + 81 * (size_t)(i + 1), H.begin());
+            std::copy(Fn.begin() + 9 * (size_t)i, Fn.begin() + 9 * (size_t)(i + 1), fn.begin());
+            func(i, H, fn, -1.0, -1.0, false);
+        });
+        if (opt == 0) stored.clear();
+    }
+    // computePerNodeCNTolerance (:123-157): func(i, dPdF(F = I), -1, false)
+    void computePerNodeCNTolerance(const std::function<void(int, const Hessian&, double, bool)>& func)
+    {
+        const long n = sim.particleCount();
+        std::vector<double> F(9 * (size_t)n, 0.0), H;
+        for (long i = 0; i < n; ++i) F[9 * i] = F[9 * i + 4] = F[9 * i + 8] = 1.0;
+        evaluate(F, H);
+        walk([&](int i) {
+            Hessian Hi;
+            std::copy(H.begin() + 81 * (size_t)i, H.begin() + 81 * (size_t)(i + 1), Hi.begin());
+            func(i, Hi, -1.0, false);
+        });
+    }
+
+private:
+    MpmSimulationB200& sim;
+    std::vector<double> stored; // the function-static dPdF cache of the reference (FBasedMpmForceHelper.h:71)
+    // dPdF of every particle: one device evaluation per distinct (mu, lambda)
+    void evaluate(const std::vector<double>& F, std::vector<double>& H)
+    {
+        hot_sim* h = sim.handle();
+        const long n = sim.particleCount();
+        std::vector<double> mu(n), lam(n);
+        sim.check(hot_get_plastic_state(h, nullptr, mu.data(), lam.data()));
+        H.assign(81 * (size_t)n, 0.0);
+        std::vector<char> done(n, 0);
+        std::vector<double> Fb, Hb;
+        std::vector<long> ids;
+        for (long a = 0; a < n; ++a) {
+            if (done[a]) continue;
+            ids.clear(); Fb.clear();
+            for (long i = a; i < n; ++i)
+                if (!done[i] && mu[i] == mu[a] && lam[i] == lam[a]) {
+                    done[i] = 1;
+                    ids.push_back(i);
+                    Fb.insert(Fb.end(), F.begin() + 9 * (size_t)i, F.begin() + 9 * (size_t)(i + 1));
+                }
+            Hb.resize(81 * ids.size());
+            sim.check(hot_corotated_eval(h, (long)ids.size(), Fb.data(), mu[a], lam[a], HOTSettings::project ? 1 : 0, nullptr, nullptr, nullptr, nullptr,
+                Hb.data(), nullptr, nullptr, nullptr));
+            for (size_t k = 0; k < ids.size(); ++k) std::copy(Hb.begin() + 81 * k, Hb.begin() + 81 * (k + 1), H.begin() + 81 * (size_t)ids[k]);
+        }
+    }
+    // the reference's particle walk: colour passes over the page groups (MpmSimulationBase.h:251-264)
+    template <class Fn_>
+    void walk(Fn_ f)
+    {
+        hot_sim* h = sim.handle();
+        const long n = sim.particleCount(), G = hot_num_groups(h);
+        std::vector<int> order(n), first(G), last(G);
+        std::vector<unsigned long long> block(G);
+        sim.check(hot_get_sort(h, nullptr, order.data(), nullptr));
+        sim.check(hot_get_groups(h, first.data(), last.data(), block.data()));
+        for (unsigned long long colour = 0; colour < 8; ++colour)
+            for (long g = 0; g < G; ++g) {
+                if ((block[g] & 7ull) != colour) continue;
+                for (int idx = first[g]; idx <= last[g]; ++idx) f(order[idx]);
+            }
+    }
+};
+
 // ---- Krylov / Newton objective concept ---------------------------------------------------------------------------------------
 class ImplicitSolverObjectiveB200 {
 public:

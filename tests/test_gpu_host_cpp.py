@@ -110,3 +110,46 @@ def test_cpp_host_rejects_unknown_flag(host_step, tmp_path):
             f.write(np.ascontiguousarray(sc[k], dtype=np.float64).tobytes())
     out = subprocess.run([host_step, fin, str(tmp_path / "o.bin"), "1", "1e-3", "0.2", "1", "--l2norm"], capture_output=True, text=True)
     assert out.returncode == 1 and "Unknown flag" in out.stderr      # like the reference
+
+
+def test_force_helper_mirror(hot, tmp_path):
+    """FBasedMpmForceHelperB200 (MpmForceHelperBase.h:18-46 surface) against the ctypes path: strain energy, the per-particle dPdF walk
+    in the reference's colour-pass order, Fn, stored / reused Hessians, dPdF(F = I)."""
+    exe = str(tmp_path / "force_helper")
+    lib = os.path.join(ROOT, "hot_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "force_helper.cpp"), "-o", exe, "-L", lib, "-lhot_b200",
+                           f"-Wl,-rpath,{lib}", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    sc = scenes.block((5, 6, 4), 1.0 / 32, ppc=6, origin_cells=(8, 8, 8), rho=1000.0, E=2.5e4, nu=0.4, seed=7)
+    sc["mu"][::3] *= 2.0                                             # two materials: the helper evaluates per distinct (mu, lambda)
+    n = len(sc["mass"]); dt = 2e-3
+    inp = tmp_path / "in.bin"
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<qd", n, sc["dx"]))
+        for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam"):
+            f.write(np.ascontiguousarray(sc[k], dtype=np.float64).tobytes())
+    out = dict(line.split(" ", 1) for line in subprocess.check_output([exe, str(inp), str(dt)], text=True).strip().splitlines())
+    g = hot.MpmSimulationB200(sc["dx"])
+    g.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
+    g.set_dt_gravity(dt, (0, -9.8, 0))
+    g.sortParticlesAndPolluteGrid(); g.particlesToGrid()
+    g.set_bc(np.zeros(0, dtype=np.int32))
+    g.backupStrain(); g.updateState()
+    _, F = g.get_stress()
+    e = 0.0; sh = 0.0; si = 0.0
+    for mu in np.unique(sc["mu"]):
+        sel = sc["mu"] == mu
+        c = g.corotated_eval(F[sel].reshape(-1, 3, 3).transpose(0, 2, 1), mu, sc["lam"][0], project=True)
+        e += (sc["vol"][sel] * c["psi"]).sum(); sh += c["dPdF"][:, 0, 0].sum()
+        ci = g.corotated_eval(np.tile(np.eye(3), (int(sel.sum()), 1, 1)), mu, sc["lam"][0], project=True)
+        si += ci["dPdF"][:, 0, 0].sum()
+    assert int(out["visited"]) == n
+    assert abs(float(out["energy"]) - e) <= 1e-11 * abs(e)
+    assert abs(float(out["sum_dPdF00"]) - sh) <= 1e-11 * abs(sh)
+    assert float(out["sum_dPdF00_reused"]) == float(out["sum_dPdF00"])
+    assert abs(float(out["sum_dPdF00_identity"]) - si) <= 1e-11 * abs(si)
+    assert abs(float(out["sum_Fn00"]) - sc["F"][:, 0].sum()) <= 1e-12 * n
+    sorter, order, _ = g.get_sort()
+    first, last, block = g.get_groups()
+    colour0 = [gi for gi in range(len(block)) if (int(block[gi]) & 7) == min(int(b) & 7 for b in block)]
+    assert int(out["first_visited"]) == order[first[colour0[0]]]
