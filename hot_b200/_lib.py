@@ -110,6 +110,9 @@ def load_library(path=LIB_PATH):
         "hot_set_project": (C.c_int, [vp, C.c_int]),
         "hot_set_bc": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
         "hot_get_dv": (C.c_int, [vp, vp]),
+        "hot_set_colliders": (C.c_int, [vp, C.c_int, vp]),
+        "hot_build_bc": (C.c_int, [vp, C.c_int, _c_int_p]),
+        "hot_get_bc": (C.c_int, [vp, _c_int_p, vp, vp, vp, vp, vp]),
         "hot_corotated_eval": (C.c_int, [vp, C.c_long, vp, C.c_double, C.c_double, C.c_int] + [vp] * 8),
         "hot_strain_energy": (C.c_int, [vp, vp]),
         "hot_get_strain_backup": (C.c_int, [vp, vp]),

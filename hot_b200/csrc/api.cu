@@ -576,6 +576,21 @@ int hot_set_bc(hot_sim* s, int mode, int n_bc, const int* node_id, const double*
 {
     return set_bc(s, mode, n_bc, node_id, P, R, Rinv, slip, dv_bc);
 }
+int hot_set_colliders(hot_sim* s, int n, const hot_collider* objects) { return set_colliders(s, n, objects); }
+int hot_build_bc(hot_sim* s, int mode, int* n_bc) { return build_bc_from_colliders(s, mode, n_bc); }
+int hot_get_bc(hot_sim* s, int* n_bc, int* node_id, double* P, double* R, double* Rinv, int* slip)
+{
+    const size_t n = (size_t)s->n_bc;
+    if (n_bc) *n_bc = s->n_bc;
+    if (n == 0) return 0;
+    int rc = 0;
+    if (node_id) rc = d2h(s, node_id, s->bc_node.p, n);
+    if (!rc && slip) rc = d2h(s, slip, s->bc_slip.p, n);
+    if (!rc && P) rc = d2h(s, P, s->bc_P.p, 9 * n);
+    if (!rc && R) rc = d2h(s, R, s->bc_R.p, 9 * n);
+    if (!rc && Rinv) rc = d2h(s, Rinv, s->bc_Rinv.p, 9 * n);
+    return rc;
+}
 int hot_get_dv(hot_sim* s, double* dv)
 {
     if (!s->p2g_done) return fail(s, "hot_get_dv: call hot_p2g first");

@@ -17,6 +17,8 @@
 #include <string>
 #include <vector>
 
+struct hot_collider; // include/hot_b200.h
+
 namespace hot {
 
 // ---- SPGrid geometry for GridState<double,3> (128 B record): data_bits 7, block 2x4x4 -------------
@@ -215,6 +217,11 @@ struct Sim {
     int bc_mode = 0, n_bc = 0;
     DevBuf<int> bc_node, bc_slip;
     DevBuf<double> bc_P, bc_R, bc_Rinv;
+    // device-resident collision objects (colliders.cu) and the dense-by-node scratch of the BC build
+    DevBuf<unsigned char> colliders;
+    int n_colliders = 0;
+    DevBuf<int> col_coord, col_flag, col_pos, col_slip;
+    DevBuf<double> col_P, col_R, col_dv;
     DevBuf<double> cn_tol; // per-node CN tolerance (a18)
     DevBuf<double> work[8]; // DOF-sized scratch vectors of the host-buffer entry points
 
@@ -312,6 +319,9 @@ int dist_after_numbering(Sim* s); // page ownership, DOF ranges, interface node 
 int dist_allreduce_buffer(Sim* s, double* dev, long count, int op); // whole device array, in place
 int dist_exchange_iface(Sim* s, double* v, int comps); // sum over ranks on the interface nodes of a DOF array with `comps` per node
 int dist_allreduce_host(Sim* s, double* host, int count, int op); // a few scalars
+// colliders.cu
+int set_colliders(Sim* s, int n, const ::hot_collider* objs);
+int build_bc_from_colliders(Sim* s, int mode, int* n_bc);
 // matrix.cu
 int fill_id2coord(Sim* s, int* coord_dev);
 int build_matrix(Sim* s, bool bcproject);

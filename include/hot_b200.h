@@ -146,6 +146,29 @@ int hot_set_project(hot_sim* h, int project);
 int hot_set_bc(hot_sim* h, int mode, int n_bc, const int* node_id, const double* P, const double* R, const double* Rinv,
     const int* slip, const double* dv_bc);
 int hot_get_dv(hot_sim* h, double* dv);
+/* a8 on the device: AnalyticCollisionObject (Lib/Ziran/Math/Geometry/CollisionObject.h:46-120, .cpp:384-452) over an analytic level set
+ * (AnalyticLevelSet.h:122-310), as plain data.  Object transform x = R s X + b with rates omega, dsdt, dbdt (the caller's
+ * updateState(t) of MultigridSimulation.h:292-295 rewrites them between steps and calls hot_set_colliders again).  3x3 column-major. */
+enum { HOT_COLLIDER_STICKY = 1, HOT_COLLIDER_SLIP = 2, HOT_COLLIDER_SEPARATE = 3, HOT_COLLIDER_GHOST = 4 };          /* COLLISION_OBJECT_TYPE */
+enum { HOT_SHAPE_HALFSPACE = 0, HOT_SHAPE_SPHERE = 1, HOT_SHAPE_BOX = 2, HOT_SHAPE_CAPPED_CYLINDER = 3 };
+typedef struct hot_collider {
+    int type, shape;
+    double friction;
+    double p[8];        /* HalfSpace: origin[3], outward_normal[3] | Sphere: center[3], radius | AnalyticBox: half_edges[3] |
+                           CappedCylinder (axis y): radius, height */
+    double shape_R[9];  /* AnalyticBox / CappedCylinder own rigid transform: X_primitive = shape_R^-1 (X - shape_b) */
+    double shape_b[3];
+    double R[9], s, b[3];            /* object transform */
+    double omega[3], dsdt, dbdt[3];  /* and its rates */
+} hot_collider;
+int hot_set_colliders(hot_sim* h, int n, const hot_collider* objects);
+/* buildInitialDvAndVnForNewton (Lib/MPM/MpmSimulationBase.cpp:1139-1184) with the device-resident objects: multiObjectCollision
+ * (CollisionObject.cpp:108-149) per grid node, the CollisionNode table {node, P = I - K K^T, R, R^-1, shouldRotate} in node order and
+ * the Newton initial guess (dv = gravity dt on free nodes, collider velocity difference on collision nodes), all on the device;
+ * `mode` as in hot_set_bc.  Replaces the host evaluation + hot_set_bc; hot_get_bc reads the table back. */
+int hot_build_bc(hot_sim* h, int mode, int* n_bc);
+/* the current BC table (from hot_set_bc or hot_build_bc); any pointer may be NULL; returns the number of rows through *n_bc */
+int hot_get_bc(hot_sim* h, int* n_bc, int* node_id, double* P, double* R, double* Rinv, int* slip);
 /* CorotatedIsotropic<T,3> as an operator on n deformation gradients (Lib/Ziran/Physics/ConstitutiveModel/CorotatedIsotropic.h:78-230):
  * updateScratch (QR-SVD conventions of ImplicitQRSVD.h: det U = det V = +1, sigma sorted, sign on the last) + psi + firstPiola +
  * firstPiolaDifferential (dP for the given dF) + firstPiolaDerivative (dense 9x9 dPdF, column-major, index ij = i + 3 j), with or

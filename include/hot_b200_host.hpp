@@ -95,11 +95,23 @@ inline TM identity() { return {1, 0, 0, 0, 1, 0, 0, 0, 1}; }
 // ---- a8: collision objects, evaluated on the host (O(N_nodes) analytic tests per step) ------------------------------------
 enum COLLISION_OBJECT_TYPE { STICKY = 1, SLIP = 2, SEPARATE = 3, GHOST = 4 }; // CollisionObject.h:51-56
 
-// AnalyticLevelSet (Lib/Ziran/Math/Geometry/AnalyticLevelSet.h): signed distance + outward normal
+// AnalyticLevelSet (Lib/Ziran/Math/Geometry/AnalyticLevelSet.h): queryInside = signed distance <= 0 + outward normal, in the level
+// set's material space; describe() fills the plain-data form the device evaluation takes (hot_collider, hot_b200.h)
 struct AnalyticLevelSet {
     virtual ~AnalyticLevelSet() = default;
     virtual bool query(const TV& X, double& phi, TV& n) const = 0; // true when inside (phi <= 0)
+    virtual void describe(hot_collider& c) const = 0;
 };
+inline TV matVec(const TM& M, const TV& x) { return {M[0] * x[0] + M[3] * x[1] + M[6] * x[2], M[1] * x[0] + M[4] * x[1] + M[7] * x[2], M[2] * x[0] + M[5] * x[1] + M[8] * x[2]}; }
+inline TV matTVec(const TM& M, const TV& x) { return {M[0] * x[0] + M[1] * x[1] + M[2] * x[2], M[3] * x[0] + M[4] * x[1] + M[5] * x[2], M[6] * x[0] + M[7] * x[1] + M[8] * x[2]}; }
+// Eigen::Quaternion<T>(w, x, y, z).normalized().toRotationMatrix(), column-major
+inline TM quaternionToMatrix(double w, double x, double y, double z)
+{
+    const double l = std::sqrt(w * w + x * x + y * y + z * z);
+    w /= l; x /= l; y /= l; z /= l;
+    return {1 - 2 * (y * y + z * z), 2 * (x * y + w * z), 2 * (x * z - w * y), 2 * (x * y - w * z), 1 - 2 * (x * x + z * z), 2 * (y * z + w * x),
+        2 * (x * z + w * y), 2 * (y * z - w * x), 1 - 2 * (x * x + y * y)};
+}
 struct HalfSpace : AnalyticLevelSet { // AnalyticLevelSet.cpp:259-304
     TV origin, outward_normal;
     HalfSpace(const TV& o, const TV& n_in) : origin(o)
@@ -113,41 +125,129 @@ struct HalfSpace : AnalyticLevelSet { // AnalyticLevelSet.cpp:259-304
         n = outward_normal;
         return phi <= 0;
     }
+    void describe(hot_collider& c) const override
+    {
+        c.shape = HOT_SHAPE_HALFSPACE;
+        for (int d = 0; d < 3; ++d) { c.p[d] = origin[d]; c.p[3 + d] = outward_normal[d]; }
+    }
 };
-struct Sphere : AnalyticLevelSet { // AnalyticLevelSet.h Sphere: phi = |X - c| - r
+struct Sphere : AnalyticLevelSet { // Sphere::queryInside, AnalyticLevelSet.cpp:435-452
     TV center;
     double radius;
     Sphere(const TV& c, double r) : center(c), radius(r) {}
     bool query(const TV& X, double& phi, TV& n) const override
     {
         const TV d = sub(X, center);
-        const double l = norm(d);
+        const double l2 = dot(d, d);
+        if (!(l2 < radius * radius)) return false;
+        const double l = std::sqrt(l2);
         phi = l - radius;
-        n = l > 0 ? TV{d[0] / l, d[1] / l, d[2] / l} : TV{0, 1, 0};
-        return phi <= 0;
+        n = l < 1e-7 ? TV{1, 0, 0} : TV{d[0] / l, d[1] / l, d[2] / l};
+        return true;
+    }
+    void describe(hot_collider& c) const override
+    {
+        c.shape = HOT_SHAPE_SPHERE;
+        for (int d = 0; d < 3; ++d) c.p[d] = center[d];
+        c.p[3] = radius;
+    }
+};
+// AnalyticBox (AnalyticLevelSet.h:311-365, .cpp:504-539): primitive box [-half_edges, half_edges], placed by rotation q = <w,x,y,z> and
+// translation b; AxisAlignedAnalyticBox(min, max) (.cpp:353-368) is the q = identity case
+struct AnalyticBox : AnalyticLevelSet {
+    TV half_edges, b;
+    TM R;
+    AnalyticBox(const TV& h, const std::array<double, 4>& q, const TV& b_in) : half_edges(h), b(b_in), R(quaternionToMatrix(q[0], q[1], q[2], q[3])) {}
+    static AnalyticBox axisAligned(const TV& lo, const TV& hi)
+    {
+        return AnalyticBox({(hi[0] - lo[0]) / 2, (hi[1] - lo[1]) / 2, (hi[2] - lo[2]) / 2}, {1, 0, 0, 0}, {(lo[0] + hi[0]) / 2, (lo[1] + hi[1]) / 2, (lo[2] + hi[2]) / 2});
+    }
+    bool query(const TV& X, double& phi, TV& n) const override
+    {
+        const TV Xp = matTVec(R, sub(X, b));
+        const double d[3] = {std::fabs(Xp[0]) - half_edges[0], std::fabs(Xp[1]) - half_edges[1], std::fabs(Xp[2]) - half_edges[2]};
+        int a = 0;
+        if (d[1] > d[a]) a = 1;
+        if (d[2] > d[a]) a = 2;
+        const double q0 = std::max(d[0], 0.0), q1 = std::max(d[1], 0.0), q2 = std::max(d[2], 0.0);
+        phi = std::min(d[a], 0.0) + std::sqrt(q0 * q0 + q1 * q1 + q2 * q2);
+        if (!(phi <= 0)) return false;
+        TV Np{0, 0, 0};
+        Np[a] = Xp[a] < 0 ? -1.0 : 1.0; // d phi / d X_primitive inside the box: the arg-max axis
+        n = matVec(R, Np);
+        return true;
+    }
+    void describe(hot_collider& c) const override
+    {
+        c.shape = HOT_SHAPE_BOX;
+        for (int d = 0; d < 3; ++d) { c.p[d] = half_edges[d]; c.shape_b[d] = b[d]; }
+        std::copy(R.begin(), R.end(), c.shape_R);
+    }
+};
+// CappedCylinder (AnalyticLevelSet.h:220-309): primitive along y, centred at the origin, placed by q = <w,x,y,z> and b
+struct CappedCylinder : AnalyticLevelSet {
+    double radius, height;
+    TV b;
+    TM R;
+    CappedCylinder(double r, double h, const std::array<double, 4>& q, const TV& b_in) : radius(r), height(h), b(b_in), R(quaternionToMatrix(q[0], q[1], q[2], q[3])) {}
+    bool query(const TV& X, double& phi, TV& n) const override
+    {
+        const TV Xp = matTVec(R, sub(X, b));
+        const double rxz = std::sqrt(Xp[0] * Xp[0] + Xp[2] * Xp[2]);
+        const double d0 = rxz - radius, d1 = std::fabs(Xp[1]) - 0.5 * height;
+        const double q0 = std::max(d0, 0.0), q1 = std::max(d1, 0.0);
+        phi = std::min(std::max(d0, d1), 0.0) + std::sqrt(q0 * q0 + q1 * q1);
+        if (!(phi <= 0)) return false;
+        TV Np{0, 0, 0};
+        if (d0 >= d1) {
+            if (rxz > 0) { Np[0] = Xp[0] / rxz; Np[2] = Xp[2] / rxz; }
+            else Np[0] = 1.0;
+        }
+        else Np[1] = Xp[1] < 0 ? -1.0 : 1.0;
+        n = matVec(R, Np);
+        return true;
+    }
+    void describe(hot_collider& c) const override
+    {
+        c.shape = HOT_SHAPE_CAPPED_CYLINDER;
+        c.p[0] = radius; c.p[1] = height;
+        for (int d = 0; d < 3; ++d) c.shape_b[d] = b[d];
+        std::copy(R.begin(), R.end(), c.shape_R);
     }
 };
 
-// AnalyticCollisionObject restricted to translating objects (R = I, s = 1, omega = 0): CollisionObject.cpp:384-452
+// AnalyticCollisionObject (CollisionObject.h:46-120): level set under x = R s X + b with rates omega, dsdt, dbdt
 struct AnalyticCollisionObject {
     std::shared_ptr<AnalyticLevelSet> ls;
     COLLISION_OBJECT_TYPE type;
     double friction = 0;
-    TV b{0, 0, 0}, dbdt{0, 0, 0};
+    TM R{1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double s = 1, dsdt = 0;
+    TV b{0, 0, 0}, dbdt{0, 0, 0}, omega{0, 0, 0};
     std::function<void(double, AnalyticCollisionObject&)> updateState; // collision_objects[k]->updateState(t + dt), MultigridSimulation.h:292-295
     AnalyticCollisionObject(std::shared_ptr<AnalyticLevelSet> l, COLLISION_OBJECT_TYPE t) : ls(std::move(l)), type(t) {}
+    void setRotation(const std::array<double, 4>& q) { R = quaternionToMatrix(q[0], q[1], q[2], q[3]); } // <w, x, y, z>
+    void setAngularVelocity(const TV& w) { omega = w; }
+    void setTranslation(const TV& b_in, const TV& dbdt_in) { b = b_in; dbdt = dbdt_in; }
 
+    // detectAndResolveCollision, CollisionObject.cpp:384-452 (material velocity 0)
     bool detectAndResolveCollision(const TV& x, TV& v, TV& n) const
     {
         if (type == GHOST) return false;
         n = {NAN, NAN, NAN};
+        const TV xb = sub(x, b);
+        const TV Xr = matTVec(R, xb);
+        const TV X{Xr[0] / s, Xr[1] / s, Xr[2] / s};
         double phi;
         TV N;
-        if (!ls->query(sub(x, b), phi, N)) return false;
-        for (int d = 0; d < 3; ++d) v[d] -= dbdt[d];
+        if (!ls->query(X, phi, N)) return false;
+        const double k = dsdt / s;
+        const TV vo{omega[1] * xb[2] - omega[2] * xb[1] + k * xb[0] + dbdt[0], omega[2] * xb[0] - omega[0] * xb[2] + k * xb[1] + dbdt[1],
+            omega[0] * xb[1] - omega[1] * xb[0] + k * xb[2] + dbdt[2]};
+        for (int d = 0; d < 3; ++d) v[d] -= vo[d];
         if (type == STICKY) v = {0, 0, 0};
         else {
-            n = N;
+            n = matVec(R, N);
             const double dn = dot(v, n);
             if (type == SLIP || dn < 0) {
                 for (int d = 0; d < 3; ++d) v[d] -= n[d] * dn;
@@ -159,8 +259,21 @@ struct AnalyticCollisionObject {
                 }
             }
         }
-        for (int d = 0; d < 3; ++d) v[d] += dbdt[d];
+        for (int d = 0; d < 3; ++d) v[d] += vo[d];
         return true;
+    }
+    hot_collider describe() const
+    {
+        hot_collider c;
+        std::memset(&c, 0, sizeof c);
+        c.type = (int)type;
+        c.friction = friction;
+        c.shape_R[0] = c.shape_R[4] = c.shape_R[8] = 1.0;
+        ls->describe(c);
+        std::copy(R.begin(), R.end(), c.R);
+        c.s = s; c.dsdt = dsdt;
+        for (int d = 0; d < 3; ++d) { c.b[d] = b[d]; c.dbdt[d] = dbdt[d]; c.omega[d] = omega[d]; }
+        return c;
     }
 };
 
@@ -260,8 +373,46 @@ public:
         mass_matrix.resize(num_nodes);
         if (num_nodes) check(hot_get_mass_matrix(h, mass_matrix.data()));
     }
-    // :1139-1184 - collider tests on the host, the BC table crosses the boundary once per step
+    // a8 on the device (hot_set_colliders + hot_build_bc): the objects cross the boundary as plain data, nothing comes back but the
+    // count; collision_nodes is filled on demand by fetchCollisionNodes().  false: the host evaluation below + hot_set_bc.
+    bool device_colliders = true;
+    void fetchCollisionNodes()
+    {
+        int n_bc = 0;
+        check(hot_get_bc(h, &n_bc, nullptr, nullptr, nullptr, nullptr, nullptr));
+        std::vector<int> node(n_bc), slip(n_bc);
+        std::vector<double> P(9 * (size_t)n_bc), R(9 * (size_t)n_bc), Rinv(9 * (size_t)n_bc);
+        check(hot_get_bc(h, &n_bc, node.data(), P.data(), R.data(), Rinv.data(), slip.data()));
+        collision_nodes.resize(n_bc);
+        for (int k = 0; k < n_bc; ++k) {
+            CollisionNode& Z = collision_nodes[k];
+            Z.node_id = node[k];
+            Z.shouldRotate = slip[k] != 0;
+            std::copy(P.begin() + 9 * (size_t)k, P.begin() + 9 * (size_t)(k + 1), Z.P.begin());
+            std::copy(R.begin() + 9 * (size_t)k, R.begin() + 9 * (size_t)(k + 1), Z.R.begin());
+            std::copy(Rinv.begin() + 9 * (size_t)k, Rinv.begin() + 9 * (size_t)(k + 1), Z.Rinv.begin());
+        }
+    }
+    int num_collision_nodes = 0;
+    // :1139-1184
     void buildInitialDvAndVnForNewton()
+    {
+        const int bc_mode = (HOTSettings::systemBCProject && HOTSettings::boundaryType == 1) ? 1 : 0; // MultigridSimulation.h:104-125
+        if (device_colliders) {
+            std::vector<hot_collider> objs;
+            for (const auto& o : collision_objects) objs.push_back(o.describe());
+            check(hot_set_dt_gravity(h, dt, gravity.data()));
+            check(hot_set_colliders(h, (int)objs.size(), objs.data()));
+            check(hot_build_bc(h, bc_mode, &num_collision_nodes));
+            collision_nodes.clear();
+            dv.resize(3 * (size_t)num_nodes); // (host copies of dv / vn are refreshed by whoever reads them: hot_get_dv)
+            return;
+        }
+        buildInitialDvAndVnForNewtonOnHost();
+        num_collision_nodes = (int)collision_nodes.size();
+    }
+    // the same with the collider tests on the host (O(N_n) analytic tests, the whole grid read back): kept as the comparator
+    void buildInitialDvAndVnForNewtonOnHost()
     {
         std::vector<int> coord(3 * (size_t)num_nodes);
         std::vector<long long> idx((size_t)hot_num_pages(h) * 32);

@@ -28,6 +28,7 @@ int main(int argc, char** argv)
         parseFlags((int)flags.size(), flags.data());
 
         MpmSimulationB200 sim(dx);
+        sim.device_colliders = std::getenv("HOT_HOST_COLLIDERS") == nullptr; // a8 on the device (default) or on the host
         sim.gravity = {0, -9.8, 0};
         sim.collision_objects.emplace_back(std::make_shared<HalfSpace>(TV{0, ground, 0}, TV{0, 1, 0}), (COLLISION_OBJECT_TYPE)gtype);
         sim.setParticles(n, X.data(), V.data(), m.data(), C.data(), F.data(), vol.data(), mu.data(), lam.data());
@@ -37,7 +38,7 @@ int main(int argc, char** argv)
         for (int s = 0; s < steps; ++s) {
             sim.advanceOneTimeStep(dt);
             const hot_solve_log& L = sim.last_log;
-            rec.push_back(L.iterations); rec.push_back(L.converged); rec.push_back(sim.num_nodes); rec.push_back((double)sim.collision_nodes.size());
+            rec.push_back(L.iterations); rec.push_back(L.converged); rec.push_back(sim.num_nodes); rec.push_back((double)sim.num_collision_nodes);
             rec.push_back(L.n_log ? L.residual_norm[L.n_log - 1] : 0.0);
         }
         sim.getParticles(X.data(), V.data(), C.data(), F.data());
@@ -52,7 +53,7 @@ int main(int argc, char** argv)
             TVStack u(3 * (size_t)sim.num_nodes, 0.0), r(3 * (size_t)sim.num_nodes, 1.0), du, dAu;
             selectSmoother(HOTSettings::smoother)(u, r, du, dAu, A, 1, 0.0);
         }
-        std::printf("ok %lld particles, %d nodes, %zu bc nodes, %d iterations\n", n, sim.num_nodes, sim.collision_nodes.size(), sim.last_log.iterations);
+        std::printf("ok %lld particles, %d nodes, %d bc nodes, %d iterations\n", n, sim.num_nodes, sim.num_collision_nodes, sim.last_log.iterations);
     }
     catch (const std::exception& e) {
         std::fprintf(stderr, "host_step: %s\n", e.what());

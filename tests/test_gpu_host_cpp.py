@@ -153,3 +153,26 @@ def test_force_helper_mirror(hot, tmp_path):
     first, last, block = g.get_groups()
     colour0 = [gi for gi in range(len(block)) if (int(block[gi]) & 7) == min(int(b) & 7 for b in block)]
     assert int(out["first_visited"]) == order[first[colour0[0]]]
+
+
+def test_device_colliders_match_host_evaluation(tmp_path):
+    """hot_set_colliders + hot_build_bc (a8 on the device: half-space, sphere, rotated box, rotating capped cylinder; STICKY / SLIP /
+    SEPARATE / GHOST, friction, moving and rotating objects) against the host evaluation of the C++ mirror on the same grid."""
+    exe = str(tmp_path / "colliders")
+    lib = os.path.join(ROOT, "hot_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "colliders.cpp"), "-o", exe, "-L", lib, "-lhot_b200",
+                           f"-Wl,-rpath,{lib}", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    sc = scenes.block((9, 12, 8), 1.0 / 32, ppc=6, origin_cells=(10, 10, 10), rho=1000.0, E=2.5e4, nu=0.4, seed=11)
+    n = len(sc["mass"])
+    inp = tmp_path / "in.bin"
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<qd", n, sc["dx"]))
+        for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam"):
+            f.write(np.ascontiguousarray(sc[k], dtype=np.float64).tobytes())
+    out = dict(line.split(" ", 1) for line in subprocess.check_output([exe, str(inp), "2e-3"], text=True).strip().splitlines())
+    assert out["match"] == "1" and int(out["host_bc"]) == int(out["device_bc"]) > 100
+    assert int(out["bad_id"]) == 0 and int(out["bad_slip"]) == 0 and int(out["slip_nodes"]) > 10
+    for k in ("err_P", "err_R", "err_Rinv"):
+        assert float(out[k]) <= 1e-13, (k, out[k])
+    assert float(out["err_dv"]) <= 1e-13 * max(float(out["scale_dv"]), 1.0)
