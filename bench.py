@@ -31,24 +31,42 @@ METRIC = "Mparticles/s P2G+G2P"
 UNIT = "Mparticles/s"
 
 
-def make_workload(name, rank=0, world=1):
-    """N = 1: the named configuration.  N > 1 (weak scaling): ONE object N times as long (the bar / column extended along y),
-    partitioned over the N GPUs by page ranges with ghost exchange - every rank builds the same object (seed 0)."""
+def make_workload(name, rank=0, world=1, scaling="weak"):
+    """The particles of THIS rank and a description of the whole job.
+    N = 1: the named configuration.  N > 1, weak scaling: ONE object made of N copies of the configuration stacked end to end along
+    y, rank r holds copy r (fixed work per GPU).  Strong scaling: the named configuration cut into N slabs of equal particle count
+    along y (fixed total work).  Either way a rank holds only its own particles; pages at the seams are shared (NCCL inside the library)."""
     from hot_b200 import scenes
-    if world > 1:
-        cells, dx, ppc, kw = {"c1": ((18, 18, 18), 1.0 / 64, 8, dict(rho=1000.0, E=2.5e4, nu=0.4)),
-                              "c2": ((22, 165, 22), 0.12 / 22, 12, dict(rho=2000.0, E=1e5, nu=0.3)),
-                              "c4": ((100, 400, 25), 1.0 / 512, 8, dict(rho=1600.0, E=1e6, nu=0.3))}[name]
-        cells = (cells[0], cells[1] * world, cells[2])
-        sc = scenes.block(cells, dx, ppc=ppc, origin_cells=(16, 16, 16), seed=0, **kw)
-        return sc, f"{name.upper()} object extended {world}x along y: {cells[0]}x{cells[1]}x{cells[2]} cells ppc {ppc} ({len(sc['mass'])} particles), ONE object partitioned over {world} GPUs"
-    sc = {"c1": scenes.config_c1, "c2": scenes.config_c2, "c3": scenes.config_c3, "c4": scenes.config_c4, "c5": scenes.config_c5}[name](seed=rank)
+    from hot_b200.dist import split_slabs
+    gen = {"c1": scenes.config_c1, "c2": scenes.config_c2, "c3": scenes.config_c3, "c4": scenes.config_c4, "c5": scenes.config_c5}[name]
     desc = {"c1": "C1 box drop 18^3 cells ppc 8, reference Poisson-tile sampling",
             "c2": "C2 twisting bar (test 777001): 3 boxes 0.12x0.3x0.12 at dx 0.12/23, ppc 12, reference Poisson-tile sampling, 256^3-class SPGrid",
             "c3": "C3 faceless stand-in (sphere + box, dx 0.01, ppc 20)",
             "c4": "C4 column 100x400x25 cells ppc 8, 512^3-class SPGrid",
-            "c5": "C5 stiff wheel stand-in (analytic torus R .25 r .06, E 200 GPa, ppc 12)"}[name] + f" ({len(sc['mass'])} particles)"
-    return sc, desc
+            "c5": "C5 stiff wheel stand-in (analytic torus R .25 r .06, E 200 GPa, ppc 12)"}[name]
+    if world == 1:
+        sc = gen(seed=0)
+        return sc, desc + f" ({len(sc['mass'])} particles)"
+    if scaling == "weak":
+        if name == "c2":
+            sc = scenes.config_c2(seed=0, copy=rank)
+        elif name == "c4":
+            sc = scenes.block((100, 400, 25), 1.0 / 512, ppc=8, origin_cells=(16, 8 + 400 * rank, 16), rho=1600.0, E=1e6, nu=0.3, seed=rank)
+        else:   # generic: the configuration shifted by its own (cell-rounded) height
+            sc = gen(seed=0)
+            h = np.ceil((sc["X"][:, 1].max() - sc["X"][:, 1].min()) / sc["dx"]) * sc["dx"]
+            sc["X"] = sc["X"] + np.array([0.0, rank * h, 0.0])
+        return sc, desc + f": ONE object of {world} copies end to end along y, one copy ({len(sc['mass'])} particles) per GPU"
+    full = gen(seed=0)
+    sel = split_slabs(full["X"], world)[rank]
+    sc = {k: (v[sel] if isinstance(v, np.ndarray) and v.ndim >= 1 and len(v) == len(full["mass"]) else v) for k, v in full.items()}
+    return sc, desc + f" ({len(full['mass'])} particles) cut into {world} slabs of equal particle count along y"
+
+
+def config_block(desc, args, world):
+    """the `config` keys both arms emit (identical keys and workload string for the same command line)"""
+    return {"workload": desc, "workload_name": args.workload, "n_gpus": world, "scaling": args.scaling if world > 1 else "n/a (1 GPU)",
+            "l2": "flushed before every timed step (256 MiB memset)"}
 
 
 def peaks():
@@ -191,15 +209,21 @@ def run_reference(args):
         return
     # torchrun pins OMP_NUM_THREADS to 1 per process: the CPU arm gets all the host cores back (set before libgomp loads)
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    # same object as the GPU arm at this N (N > 1: the bar / column extended N times along y)
-    sc, desc = make_workload(args.workload, 0, max(1, args.gpus))
+    # the same object as the GPU arm at this N: the CPU arm runs the WHOLE job (all copies / all slabs) in one process
+    world = max(1, args.gpus)
+    if world == 1:
+        sc, desc = make_workload(args.workload, 0, 1)
+    else:
+        parts = [make_workload(args.workload, r, world, args.scaling) for r in range(world)]
+        desc = parts[0][1]
+        sc = {k: (np.concatenate([p[0][k] for p in parts]) if isinstance(parts[0][0][k], np.ndarray) else parts[0][0][k]) for k in parts[0][0]}
     n, times, cores, t_sort = cpu_baseline(sc, args.steps, args.warmup)
     ms = 1e3 * float(np.mean(times))
     val = n / (ms * 1e-3) / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "l2": "n/a (CPU)"},
+        "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_block(desc, args, world),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"whole workload, {args.steps} steps of P2G+G2P (OpenMP restatement of the reference's 8-colour TBB schedule; sort {1e3 * t_sort:.1f} ms untimed)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -316,22 +340,39 @@ def cpu_substep_baseline():
     return res
 
 
-def dist_solver_leg(sim, sc, args):
-    """partitioned solver-side kernels (matrix-free path): Hessian apply / updateState / residual with interface-only exchange"""
-    n = len(sc["mass"])
+def dist_solver_leg(sim, sc, args, dev):
+    """partitioned solver-side kernels (matrix-free path): Hessian apply / updateState / residual, shared pages exchanged after every
+    scatter; a matrix-free PN-PCG substep of the whole object"""
+    import torch
+    import torch.distributed as dist
     sim.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
     sim.set_dt_gravity(SOLVER_DT, (0.0, 0.0, 0.0))
-    sim.sortParticlesAndPolluteGrid()
-    nn = sim.particlesToGrid()
-    bc = end_cap_bc(sim.get_id2coord())
-    sim.set_bc(bc, P=np.zeros((len(bc), 9)), dv_bc=np.zeros((len(bc), 3)))
+
+    def begin():
+        sim.sortParticlesAndPolluteGrid()
+        nn = sim.particlesToGrid()
+        coord = sim.get_id2coord()
+        yr = torch.tensor([float(-coord[:, 1].min()), float(coord[:, 1].max())], dtype=torch.float64, device=dev)
+        dist.all_reduce(yr, op=dist.ReduceOp.MAX)                  # the end caps of the WHOLE object
+        y = coord[:, 1]
+        bc = np.nonzero((y <= -float(yr[0]) + 8) | (y >= float(yr[1]) - 8))[0].astype(np.int32)
+        sim.set_bc(bc, P=np.zeros((len(bc), 9)), dv_bc=np.zeros((len(bc), 3)))
+        return nn
+    nn = begin()
     sim.backupStrain()
     sim.updateState()
     reps = max(3, min(args.steps, 20))
     part = sim.get_partition()
-    out = {"dt": SOLVER_DT, "grid_nodes": nn, "interface_nodes": part["n_interface"], "own_particles": part["particle1"] - part["particle0"]}
+    out = {"dt": SOLVER_DT, "grid_nodes_rank0": nn, "partition_rank0": part}
     for op in ("hessian_apply", "update_state", "residual"):
         out[op] = {"ms": sim.op_bench(op, reps)}
+    sim.restoreStrain()
+    t0 = time.perf_counter()
+    begin()
+    log = sim.backwardEulerStep(lsolver=2, matfree=1, bcproject=0, mg_level=1, project=1, linesearch=1, usecn=1, max_newton_iterations=20)
+    sim.gridToParticles(SOLVER_DT)
+    out["pn_pcg_mf_substep"] = {"ms": 1e3 * (time.perf_counter() - t0), "newton_iterations": int(log["iterations"]), "pcg_iterations": int(log["total_linear_iterations"]),
+                                "converged": bool(log["converged"]), "residual_first": float(log["residual_norm"][0]), "residual_last": float(log["residual_norm"][-1])}
     return out
 
 
@@ -354,15 +395,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    # weak scaling on ONE object: N GPUs carry an object N times as long, cut into contiguous page-group ranges; the data-path
-    # exchange is the per-step all-reduce of the grid mass / momentum (P2G) through NCCL; G2P gathers need none
-    sc, desc = make_workload(args.workload, rank, world)
+    # ONE object over N GPUs: every rank holds its own particles (a copy of the configuration in weak scaling, a slab of it in strong
+    # scaling), sorts and numbers locally; the data-path exchange is one grouped ncclSend / ncclRecv of the shared pages' mass and
+    # momentum per P2G (NCCL communicator inside the library, its id carried by torch.distributed); G2P gathers need none
+    sc, desc = make_workload(args.workload, rank, world, args.scaling)
     n = len(sc["mass"])
     stream = torch.cuda.current_stream()
     sim = hot_b200.MpmSimulationB200(sc["dx"], device=local, stream=stream.cuda_stream)
     if world > 1:
-        from hot_b200.dist import torch_partition
-        torch_partition(sim, dev)
+        from hot_b200.dist import nccl_partition
+        nccl_partition(sim, dev)
     sim.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
     sim.sortParticlesAndPolluteGrid()
     n_nodes = sim.particlesToGrid()
@@ -470,22 +512,24 @@ def run_ours(args):
     elif world == 1:
         solver = solver_leg(sim, sc, args)
     else:
-        solver = dist_solver_leg(sim, sc, args)
+        solver = dist_solver_leg(sim, sc, args, dev)
     part = sim.get_partition() if world > 1 else None
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(n), float(n_nodes)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     total_ms, e2e_ms = [float(x) for x in t.tolist()]
-    n_total = float(n)                         # one object: every rank holds the same particle count n = whole job
+    n_total = float(cnt[0])                    # whole job: the ranks' particles add up
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = n_total / (ms_per_step * 1e-3) / 1e6
         peak, peak_src = peaks()
         # roofline of the dominant kernel; algorithmic bytes per SURVEY.md 8d (fp64)
-        n_own = n // world                       # particle kernels run on this rank's share; the grid terms are whole-object
-        alg = {"p2g": 128 * n_own + 32 * n_nodes, "g2p": 288 * n_own + 24 * n_nodes}
+        # (rank 0's kernels on rank 0's particles and rank 0's nodes: a per-GPU roofline at every N)
+        alg = {"p2g": 128 * n + 32 * n_nodes, "g2p": 288 * n + 24 * n_nodes}
         per = {k: (kt[k][0] / kt[k][1]) for k in ("p2g", "g2p", "number_nodes") if k in kt}
         dom = max(("p2g", "g2p"), key=lambda k: per.get(k, 0.0))
         ach = alg[dom] / (per[dom] * 1e-3) / 1e9
@@ -508,13 +552,13 @@ def run_ours(args):
             cpu = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": desc, "particles_per_gpu": n // world, "grid_nodes": n_nodes, "pages": sim.num_pages,
-                       "l2": "flushed before every timed step (256 MiB memset)",
-                       "parallelism": ("single GPU" if world == 1 else
-                                       f"one object over {world} GPUs: contiguous page-group ranges, replicated sort / DOF numbering, NCCL all-reduce of the interface pages (mass+momentum) + one mask per page per P2G "
-                                       f"(interface nodes per rank pair boundary: {part['n_interface']})")},
+            "config": dict(config_block(desc, args, world), particles_rank0=n, grid_nodes_rank0=n_nodes, pages_rank0=sim.num_pages,
+                           parallelism=("single GPU" if world == 1 else
+                                        f"{world} GPUs, one process each, particles partitioned (rank 0: {part['particles']} particles, {part['neighbors']} neighbour ranks, "
+                                        f"{part['shared_pages']} shared pages, {part['owned_nodes']} of {part['global_nodes']} nodes counted here); per P2G one grouped "
+                                        f"ncclSend/ncclRecv of {part['exchange_pages'] * 4 * 32 * 8} bytes per direction")),
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "serial_ms_per_step": e2e_serial_ms,
@@ -539,6 +583,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = N copies of the workload end to end, one per GPU; strong = the workload cut into N slabs")
     ap.add_argument("--cpu-reps", type=int, default=5)
     ap.add_argument("--no-solver", action="store_true", help="skip the solver-side kernel timings (V-cycle ms, Hessian apply ...)")
     args = ap.parse_args()

@@ -13,7 +13,16 @@ class LibraryMissing(RuntimeError):
 
 
 _lib = None
-ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_long)
+# hot_transport (include/hot_b200.h): the caller's collectives for a partitioned object
+T_ALL_REDUCE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_long, C.c_int)
+T_ALL_GATHER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long)
+T_NEIGHBOR_EXCHANGE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_long))
+
+
+class Transport(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("all_reduce", T_ALL_REDUCE), ("all_gather", T_ALL_GATHER), ("neighbor_exchange", T_NEIGHBOR_EXCHANGE)]
+
+
 
 HOT_LOG_CAP = 256
 
@@ -103,8 +112,12 @@ def load_library(path=LIB_PATH):
         "hot_apply_plasticity": (C.c_int, [vp]),
         "hot_get_plastic_state": (C.c_int, [vp, vp, vp, vp]),
         "hot_set_plastic_state": (C.c_int, [vp, vp]),
-        "hot_set_partition": (C.c_int, [vp, C.c_int, C.c_int, ALLREDUCE_FN, vp]),
-        "hot_set_exchange_buffer": (C.c_int, [vp, vp, C.c_long]),
+        "hot_comm_unique_id": (C.c_int, [vp]),
+        "hot_comm_init_nccl": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+        "hot_set_partition": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+        "hot_share_tables": (C.c_int, [C.c_int, C.c_int, C.c_int] + [vp] * 3 + [vp] * 11),
+        "hot_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_long]),
+        "hot_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_long]),
         "hot_get_partition": (C.c_int, [vp, C.POINTER(C.c_long)]),
         "hot_set_dt_gravity": (C.c_int, [vp, C.c_double, vp]),
         "hot_set_project": (C.c_int, [vp, C.c_int]),

@@ -1,5 +1,6 @@
 // extern "C" entry points of include/hot_b200.h: argument checking, host<->device marshalling, dispatch.
 #include "api_internal.h"
+#include <algorithm>
 
 using namespace hot;
 
@@ -149,6 +150,7 @@ hot_sim* hot_create(double dx, double apic_rpic_ratio, double cfl, int device)
 void hot_destroy(hot_sim* s)
 {
     if (!s) return;
+    comm_destroy(s);
     if (s->copy_in) cudaStreamDestroy(s->copy_in);
     if (s->copy_out) cudaStreamDestroy(s->copy_out);
     for (cudaEvent_t e : {s->ev_in_done, s->ev_in_free, s->ev_out_ready, s->ev_out_done})
@@ -522,29 +524,68 @@ int hot_set_plastic_state(hot_sim* s, const double* Jp)
 }
 
 // ---- row (e): one object over several GPUs (dist.cu) ---------------------------------------------------------------
-int hot_set_partition(hot_sim* s, int rank, int world, hot_allreduce_fn fn, void* user)
+int hot_comm_unique_id(void* id128) { return comm_unique_id(id128); }
+int hot_comm_init_nccl(hot_sim* s, int rank, int world, const void* id128)
 {
-    if (world < 1 || world > 32 || rank < 0 || rank >= world) return fail(s, "hot_set_partition: need 0 <= rank < world <= 32");
-    if (world > 1 && !fn) return fail(s, "hot_set_partition: an all-reduce callback is required for world > 1");
+    if (!id128) return fail(s, "hot_comm_init_nccl: null id");
+    return comm_init_nccl(s, rank, world, id128);
+}
+int hot_set_partition(hot_sim* s, int rank, int world, const hot_transport* t)
+{
+    if (world < 1 || rank < 0 || rank >= world) return fail(s, "hot_set_partition: need 0 <= rank < world");
+    if (world > 1 && (!t || !t->all_reduce || !t->all_gather || !t->neighbor_exchange))
+        return fail(s, "hot_set_partition: world > 1 needs the three transport callbacks (or use hot_comm_init_nccl)");
+    comm_destroy(s);
     s->rank = rank;
     s->world = world;
-    s->allreduce = fn;
-    s->allreduce_user = user;
-    s->sorted = false; // the partition is computed by the next hot_sort_and_activate
+    s->has_transport = world > 1;
+    if (world > 1) {
+        s->transport.user = t->user;
+        s->transport.all_reduce = t->all_reduce;
+        s->transport.all_gather = t->all_gather;
+        s->transport.neighbor_exchange = t->neighbor_exchange;
+    }
+    s->sorted = false; // the shared-page tables are built by the next hot_sort_and_activate
     s->p2g_done = false;
-    return 0;
-}
-int hot_set_exchange_buffer(hot_sim* s, void* device_ptr, long capacity_doubles)
-{
-    s->xbuf = (double*)device_ptr;
-    s->xbuf_cap = device_ptr ? capacity_doubles : 0;
     return 0;
 }
 int hot_get_partition(hot_sim* s, long* out8)
 {
-    if (!s->sorted) return fail(s, "hot_get_partition: call hot_sort_and_activate first");
-    out8[0] = s->g0; out8[1] = s->g1; out8[2] = s->p0; out8[3] = s->p1;
-    out8[4] = s->dof0; out8[5] = s->dof1; out8[6] = s->n_iface; out8[7] = s->world;
+    if (s->n_pages <= 0) return fail(s, "hot_get_partition: call hot_sort_and_activate first");
+    // (the tables describe the last sort, also after hot_g2p moved the particles)
+    out8[0] = s->rank; out8[1] = s->world; out8[2] = (long)s->nbr_rank.size(); out8[3] = s->n_sh;
+    out8[4] = s->x_total; out8[5] = s->num_nodes > 0 ? s->n_owned_nodes : -1; out8[6] = s->num_nodes > 0 ? (s->world > 1 ? s->global_nodes : s->num_nodes) : -1;
+    out8[7] = s->N;
+    return 0;
+}
+// the host logic of the shared-page tables on host arrays (no device, no handle): what dist_after_sort runs after its all-gather.
+// Output arrays are caller-allocated for the worst case: nbr_* world entries, x_slot (world - 1) * counts[rank], sh_slot / sh_owned
+// counts[rank], sh_ptr counts[rank] + 1, sh_entry world * counts[rank].
+int hot_share_tables(int rank, int world, int max_pages, const int* counts, const unsigned* all_pids, const int* slot_sorted, int* n_nbr, int* nbr_rank,
+    long* nbr_off, long* nbr_cnt, int* n_x, int* x_slot, int* n_sh, int* sh_slot, int* sh_ptr, int* sh_entry, int* sh_owned)
+{
+    if (world < 1 || rank < 0 || rank >= world || !counts || !all_pids || !slot_sorted) return -1;
+    std::vector<int> nr, xs, ss, sp, se, so;
+    std::vector<long> no, nc;
+    share_tables(rank, world, max_pages, counts, all_pids, slot_sorted, nr, no, nc, xs, ss, sp, se, so);
+    *n_nbr = (int)nr.size(); *n_x = (int)xs.size(); *n_sh = (int)ss.size();
+    std::copy(nr.begin(), nr.end(), nbr_rank); std::copy(no.begin(), no.end(), nbr_off); std::copy(nc.begin(), nc.end(), nbr_cnt);
+    std::copy(xs.begin(), xs.end(), x_slot); std::copy(ss.begin(), ss.end(), sh_slot); std::copy(sp.begin(), sp.end(), sh_ptr);
+    std::copy(se.begin(), se.end(), sh_entry); std::copy(so.begin(), so.end(), sh_owned);
+    return 0;
+}
+// raw copies between host and device memory on the handle's stream, synchronous (for transport callbacks written in a host
+// language that has no CUDA binding of its own: tests/dist_worker.py moves the exchange buffers through gloo with these)
+int hot_memcpy_d2h(hot_sim* s, void* host, const void* dev, long bytes)
+{
+    HOT_CUDA(cudaMemcpyAsync(host, dev, (size_t)bytes, cudaMemcpyDeviceToHost, s->stream));
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+int hot_memcpy_h2d(hot_sim* s, void* dev, const void* host, long bytes)
+{
+    HOT_CUDA(cudaMemcpyAsync(dev, host, (size_t)bytes, cudaMemcpyHostToDevice, s->stream));
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
 

@@ -1,267 +1,407 @@
-// Row (e): one object partitioned over the GPUs of a box.
+// Row (e): one object over the GPUs of a box, one process per GPU, particles partitioned, grid pages shared at the seams.
 //
-// The reference has no distributed path; this is the B200-side design of SURVEY 8e, first stage:
-//  * every rank holds all particle POSITIONS and runs the same sort / page activation / DOF numbering, so keys, page list
-//    and DOF ids are bit-identical to the single-GPU (and reference) result on every rank;
-//  * the sorted page-group list is cut into `world` contiguous ranges balanced by particle count (the key order is Morton
-//    over pages, so ranges are spatially compact); a rank runs the particle kernels (P2G, G2P, updateState, Hessian build,
-//    force / Hessian / tolerance scatters) only on its groups;
-//  * a node belongs to the rank whose groups touch its page first; because the page list is in first-touch order, owned DOF
-//    ids are one contiguous range per rank, so reductions over owned nodes are plain sub-ranges;
-//  * scatter results are summed across ranks ONLY on interface nodes (nodes of pages touched by >= 2 ranks): pack ->
-//    all-reduce -> unpack.  The all-reduce itself is the caller's (torch.distributed / NCCL over NVLink in bench.py and the
-//    tests, ncclAllReduce in a C++ host) through a callback on a caller-owned device buffer: the library stays free of a
-//    communicator and of any process-group assumption.
-//  * grid-side vector algebra is replicated (N_n << N_p), dots are taken over owned nodes and all-reduced.
+// The reference has no distributed path; this is the design of SURVEY 8e:
+//  * every rank holds ITS particles only (whatever the caller gives it: bench.py cuts the object into slabs) and is, locally, a
+//    complete single-GPU object: own sort, own page list (its particles' pages and their +1 neighbours,
+//    MpmSimulationBase.cpp:1104-1124), own DOF numbering.  Nothing is replicated, nothing scales with the whole object;
+//  * a page that two or more ranks activate is SHARED: after every particle->grid scatter (P2G mass / momentum, forces, Hessian
+//    products, CN tolerances, block diagonals) the partial sums on shared pages are exchanged between the sharing ranks only
+//    (grouped ncclSend / ncclRecv over NVLink, one message per neighbour) and added in ascending rank order on every sharer, so
+//    all sharers hold bit-identical totals.  Gathers (G2P, updateState, Hessian gather) then need no communication;
+//  * the shared-page tables are built once per sort: all-gather of the ranks' ascending page-id lists, intersections on the host
+//    (a few thousand ids), per-neighbour slot lists + a CSR of (sharer, offset) per shared page on the device;
+//  * DOF vectors are local (own + shared nodes, shared ones replicated and consistent); dots / norms / energies count a shared
+//    node on its lowest-ranked sharer only (own_node mask) and all-reduce 1-3 scalars;
+//  * particles stay with their rank while they move (correct for any distribution: sharing is recomputed every sort);
+//    re-balancing by migration is a performance matter, not one of correctness.
+// Transport: NCCL inside the library (hot_comm_init_nccl; the symbols are resolved with dlopen so the library loads without NCCL),
+// or the caller's callbacks (hot_set_partition with a hot_transport: the one-GPU tests run several ranks on one device through gloo).
+#include "../../include/hot_b200.h"
 #include "sim.h"
-#include <cub/cub.cuh>
+#include "reduce.cuh"
 #include <algorithm>
+#include <cub/cub.cuh>
+#include <dlfcn.h>
+#include <nccl.h>
 
 namespace hot {
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static const char* load_nccl()
+{
+    if (g_nccl.lib) return nullptr;
+    // the process may already carry an NCCL (torch bundles one): reuse it, else load the system library
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return "libnccl.so.2 not found (dlopen)";
+#define HOT_NCCL_SYM(name)                                                         \
+    *reinterpret_cast<void**>(&g_nccl.name) = dlsym(lib, "nccl" #name);            \
+    if (!g_nccl.name) return "NCCL symbol nccl" #name " missing";
+    HOT_NCCL_SYM(GetUniqueId) HOT_NCCL_SYM(CommInitRank) HOT_NCCL_SYM(CommDestroy) HOT_NCCL_SYM(AllReduce) HOT_NCCL_SYM(AllGather)
+    HOT_NCCL_SYM(Send) HOT_NCCL_SYM(Recv) HOT_NCCL_SYM(GroupStart) HOT_NCCL_SYM(GroupEnd) HOT_NCCL_SYM(GetErrorString)
+#undef HOT_NCCL_SYM
+    g_nccl.lib = lib;
+    return nullptr;
+}
+
+#define HOT_NCCL(call)                                                                                        \
+    do {                                                                                                      \
+        ncclResult_t r__ = (call);                                                                            \
+        if (r__ != ncclSuccess) return fail(s, std::string("NCCL error: ") + g_nccl.GetErrorString(r__) + " in " #call); \
+    } while (0)
+
+int comm_unique_id(void* out128)
+{
+    if (const char* e = load_nccl()) {
+        fprintf(stderr, "hot_comm_unique_id: %s\n", e);
+        return -1;
+    }
+    static_assert(sizeof(ncclUniqueId) == 128, "the C ABI passes the id as 128 bytes");
+    return g_nccl.GetUniqueId(reinterpret_cast<ncclUniqueId*>(out128)) == ncclSuccess ? 0 : -1;
+}
+int comm_init_nccl(Sim* s, int rank, int world, const void* id128)
+{
+    if (world < 1 || rank < 0 || rank >= world) return fail(s, "hot_comm_init_nccl: need 0 <= rank < world");
+    if (const char* e = load_nccl()) return fail(s, std::string("hot_comm_init_nccl: ") + e);
+    if (s->nccl_comm) {
+        g_nccl.CommDestroy((ncclComm_t)s->nccl_comm);
+        s->nccl_comm = nullptr;
+    }
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    ncclComm_t c;
+    HOT_CUDA(cudaSetDevice(s->device));
+    HOT_NCCL(g_nccl.CommInitRank(&c, world, id, rank));
+    s->nccl_comm = c;
+    s->rank = rank;
+    s->world = world;
+    s->has_transport = false;
+    s->sorted = false;
+    s->p2g_done = false;
+    return 0;
+}
+void comm_destroy(Sim* s)
+{
+    if (s->nccl_comm && g_nccl.lib) g_nccl.CommDestroy((ncclComm_t)s->nccl_comm);
+    s->nccl_comm = nullptr;
+}
+
 namespace {
 
 constexpr int TPB = 256;
 inline int nblk(long n) { return (int)((n + TPB - 1) / TPB); }
 
-// every page a group's particles can touch (its own page and the 7 +1 neighbours) gets the group's rank bit
-__global__ void k_page_touch(long n_groups, const int* __restrict__ group_slot, const int* __restrict__ group_rank, const int* __restrict__ nbr8,
-    unsigned* __restrict__ mask)
+// ---- transport: NCCL or the caller's callbacks; every operation is enqueued on (or ordered with) the handle's stream ---------
+int comm_all_reduce(Sim* s, double* dev, long count, int op)
 {
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_groups * 8) return;
-    const long g = t >> 3;
-    const int slot = nbr8[(size_t)group_slot[g] * 8 + (t & 7)];
-    if (slot >= 0) atomicOr(mask + slot, 1u << group_rank[g]);
-}
-// per node: owner rank = lowest touching rank (first touch), interface = touched by >= 2 ranks
-__global__ void k_node_owner(long gn, const int* __restrict__ g_idx, const unsigned* __restrict__ mask, int rank, int* __restrict__ iface_flag,
-    int* __restrict__ range /* [0] min own id, [1] max own id */)
-{
-    const long a = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= gn) return;
-    const int id = g_idx[a];
-    if (id < 0) return;
-    const unsigned m = mask[a / Geo::E];
-    iface_flag[id] = __popc(m) >= 2;
-    if (m && (__ffs(m) - 1) == rank) {
-        atomicMin(range, id);
-        atomicMax(range + 1, id);
+    if (s->nccl_comm) {
+        HOT_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclDouble, op ? ncclMax : ncclSum, (ncclComm_t)s->nccl_comm, s->stream));
+        return 0;
     }
+    if (!s->has_transport) return fail(s, "partitioned run without a transport (hot_comm_init_nccl or hot_set_partition)");
+    return s->transport.all_reduce(s->transport.user, dev, count, op) ? fail(s, "transport all_reduce failed") : 0;
 }
-// grid channels of the interface pages <-> exchange buffer: [page k][channel 0..3][element e]
-__global__ void k_pack_pages(int n_ip, const int* __restrict__ ipage, size_t gs, const double* __restrict__ g_m, const double* __restrict__ g_v,
-    double* __restrict__ buf)
+int comm_all_gather(Sim* s, const void* send, void* recv, long bytes_per_rank)
 {
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long)n_ip * 4 * Geo::E) return;
-    const int e = (int)(t % Geo::E), ch = (int)((t / Geo::E) % 4), k = (int)(t / (4 * Geo::E));
-    const size_t a = (size_t)ipage[k] * Geo::E + e;
-    buf[t] = ch == 0 ? g_m[a] : g_v[(size_t)(ch - 1) * gs + a];
+    if (s->nccl_comm) {
+        HOT_NCCL(g_nccl.AllGather(send, recv, (size_t)bytes_per_rank, ncclChar, (ncclComm_t)s->nccl_comm, s->stream));
+        return 0;
+    }
+    if (!s->has_transport) return fail(s, "partitioned run without a transport (hot_comm_init_nccl or hot_set_partition)");
+    return s->transport.all_gather(s->transport.user, send, recv, bytes_per_rank) ? fail(s, "transport all_gather failed") : 0;
 }
-__global__ void k_unpack_pages(int n_ip, const int* __restrict__ ipage, size_t gs, const double* __restrict__ buf, double* __restrict__ g_m,
-    double* __restrict__ g_v)
+// send[j] -> peer j, recv[j] <- peer j, `count[j]` doubles each way (the shared-page lists are symmetric)
+int comm_exchange(Sim* s, int n_peers, const int* peers, double* const* send, double* const* recv, const long* count)
 {
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long)n_ip * 4 * Geo::E) return;
-    const int e = (int)(t % Geo::E), ch = (int)((t / Geo::E) % 4), k = (int)(t / (4 * Geo::E));
-    const size_t a = (size_t)ipage[k] * Geo::E + e;
-    if (ch == 0) g_m[a] = buf[t];
-    else g_v[(size_t)(ch - 1) * gs + a] = buf[t];
-}
-// per page: bit e set when node e carries mass (as a double: exact for 32 bits; the MAX over ranks is the complete mask
-// because every rank that touches a page holds its complete mass after the interface exchange, the others hold 0)
-// node masks of the pages that exactly ONE rank touches, contributed by that rank (the others add 0: a SUM all-reduce carries
-// them next to the interface pages' mass / momentum); pages touched by >= 2 ranks get their mask from the summed mass instead
-__global__ void k_page_nonzero(long n_pages, const double* __restrict__ g_m, const unsigned* __restrict__ mask, int rank, double* __restrict__ out)
-{
-    const long pg = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pg >= n_pages) return;
-    unsigned bits = 0;
-    if (mask[pg] == (1u << rank))
-        for (int e = 0; e < Geo::E; ++e) bits |= (g_m[(size_t)pg * Geo::E + e] != 0.0 ? 1u : 0u) << e;
-    out[pg] = (double)bits;
-}
-__global__ void k_flags_from_bits(long gn, const double* __restrict__ bits, const unsigned* __restrict__ mask, const double* __restrict__ g_m,
-    int* __restrict__ flag)
-{
-    const long a = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= gn) return;
-    const long pg = a / Geo::E;
-    flag[a] = __popc(mask[pg]) >= 2 ? (g_m[a] != 0.0) : ((((unsigned)bits[pg]) >> (a % Geo::E)) & 1u);
-}
-__global__ void k_ipage_flags(long n_pages, const unsigned* __restrict__ mask, int* __restrict__ flag)
-{
-    const long pg = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pg < n_pages) flag[pg] = __popc(mask[pg]) >= 2;
-}
-__global__ void k_pack(int n, int comps, const int* __restrict__ dof, const double* __restrict__ v, double* __restrict__ buf)
-{
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long)n * comps) return;
-    const int k = (int)(t / comps), c = (int)(t - (long)k * comps);
-    buf[t] = v[(size_t)dof[k] * comps + c];
-}
-__global__ void k_unpack(int n, int comps, const int* __restrict__ dof, const double* __restrict__ buf, double* __restrict__ v)
-{
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long)n * comps) return;
-    const int k = (int)(t / comps), c = (int)(t - (long)k * comps);
-    v[(size_t)dof[k] * comps + c] = buf[t];
+    if (n_peers <= 0) return 0;
+    if (s->nccl_comm) {
+        HOT_NCCL(g_nccl.GroupStart());
+        for (int j = 0; j < n_peers; ++j) {
+            HOT_NCCL(g_nccl.Send(send[j], (size_t)count[j], ncclDouble, peers[j], (ncclComm_t)s->nccl_comm, s->stream));
+            HOT_NCCL(g_nccl.Recv(recv[j], (size_t)count[j], ncclDouble, peers[j], (ncclComm_t)s->nccl_comm, s->stream));
+        }
+        HOT_NCCL(g_nccl.GroupEnd());
+        return 0;
+    }
+    if (!s->has_transport) return fail(s, "partitioned run without a transport (hot_comm_init_nccl or hot_set_partition)");
+    return s->transport.neighbor_exchange(s->transport.user, n_peers, peers, send, recv, count) ? fail(s, "transport neighbor_exchange failed") : 0;
 }
 
-int reserve_xbuf(Sim* s, long count)
+// ---- pack / unpack of shared pages ------------------------------------------------------------------------------------------
+// exchange buffer layout: [exchange page k][component c][element e]; a component is a grid channel (m, v0, v1, v2) or a
+// component of a DOF vector looked up through g_idx (inactive node: 0)
+struct PageSource {
+    int comps;
+    const double *g_m, *g_v; // grid channels (P2G) ...
+    size_t gs;
+    const int* g_idx; // ... or a DOF vector
+    const double* v;
+    __device__ double load(int slot, int c, int e) const
+    {
+        const size_t a = (size_t)slot * Geo::E + e;
+        if (!g_idx) return c == 0 ? g_m[a] : g_v[(size_t)(c - 1) * gs + a];
+        const int id = g_idx[a];
+        return id >= 0 ? v[(size_t)id * comps + c] : 0.0;
+    }
+};
+__global__ void k_pack_shared(long n_x, PageSource src, const int* __restrict__ x_slot, double* __restrict__ buf)
 {
-    if (count <= s->xbuf_cap) return 0;
-    if (!s->allreduce) return fail(s, "distributed run without an all-reduce callback (hot_set_partition)");
-    if (s->allreduce(s->allreduce_user, 2, count) != 0 || s->xbuf_cap < count || !s->xbuf)
-        return fail(s, "the all-reduce callback did not provide an exchange buffer of the requested size (hot_set_exchange_buffer)");
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_x * src.comps * Geo::E) return;
+    const int e = (int)(t % Geo::E), c = (int)((t / Geo::E) % src.comps);
+    const long k = t / ((long)Geo::E * src.comps);
+    buf[t] = src.load(x_slot[k], c, e);
+}
+// every sharer adds the partial sums in ascending rank order (entry -1 = this rank's own partial): identical totals everywhere
+__global__ void k_unpack_shared(int n_sh, int comps, const int* __restrict__ sh_slot, const int* __restrict__ sh_ptr, const int* __restrict__ sh_entry,
+    const double* __restrict__ recv, double* __restrict__ g_m, double* __restrict__ g_v, size_t gs, const int* __restrict__ g_idx, double* __restrict__ v)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)n_sh * comps * Geo::E) return;
+    const int e = (int)(t % Geo::E), c = (int)((t / Geo::E) % comps), p = (int)(t / ((long)Geo::E * comps));
+    const size_t a = (size_t)sh_slot[p] * Geo::E + e;
+    double* dst;
+    if (!g_idx) dst = c == 0 ? g_m + a : g_v + (size_t)(c - 1) * gs + a;
+    else {
+        const int id = g_idx[a];
+        if (id < 0) return;
+        dst = v + (size_t)id * comps + c;
+    }
+    const double mine = *dst;
+    double sum = 0.0;
+    bool first = true;
+    for (int q = sh_ptr[p]; q < sh_ptr[p + 1]; ++q) {
+        const int en = sh_entry[q];
+        const double x = en < 0 ? mine : recv[((size_t)en * comps + c) * Geo::E + e];
+        sum = first ? x : sum + x;
+        first = false;
+    }
+    *dst = sum;
+}
+// a node counts in dots / norms on the lowest-ranked sharer of its page
+__global__ void k_own_nodes(int n_sh, const int* __restrict__ sh_slot, const int* __restrict__ sh_owned, const int* __restrict__ g_idx,
+    unsigned char* __restrict__ own)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)n_sh * Geo::E) return;
+    const int p = (int)(t / Geo::E), e = (int)(t % Geo::E);
+    const int id = g_idx[(size_t)sh_slot[p] * Geo::E + e];
+    if (id >= 0) own[id] = (unsigned char)sh_owned[p];
+}
+
+struct CountOwnF {
+    const unsigned char* own;
+    __device__ void operator()(long i, double (&acc)[1]) const { acc[0] += own[i] ? 1.0 : 0.0; }
+};
+
+int exchange_pages(Sim* s, const PageSource& src, double* g_m, double* g_v, double* v)
+{
+    if (s->x_total <= 0) return 0;
+    cudaStream_t st = s->stream;
+    const long cnt = s->x_total * src.comps * Geo::E;
+    HOT_CUDA(s->x_send.reserve(cnt));
+    HOT_CUDA(s->x_recv.reserve(cnt));
+    k_pack_shared<<<nblk(cnt), TPB, 0, st>>>(s->x_total, src, s->x_slot.p, s->x_send.p);
+    HOT_LAUNCHED(s);
+    std::vector<double*> sp(s->nbr_rank.size()), rp(s->nbr_rank.size());
+    std::vector<long> cn(s->nbr_rank.size());
+    for (size_t j = 0; j < s->nbr_rank.size(); ++j) {
+        sp[j] = s->x_send.p + s->nbr_off[j] * src.comps * Geo::E;
+        rp[j] = s->x_recv.p + s->nbr_off[j] * src.comps * Geo::E;
+        cn[j] = s->nbr_cnt[j] * src.comps * Geo::E;
+    }
+    int rc = comm_exchange(s, (int)s->nbr_rank.size(), s->nbr_rank.data(), sp.data(), rp.data(), cn.data());
+    if (rc) return rc;
+    const long un = (long)s->n_sh * src.comps * Geo::E;
+    k_unpack_shared<<<nblk(un), TPB, 0, st>>>(s->n_sh, src.comps, s->sh_slot.p, s->sh_ptr.p, s->sh_entry.p, s->x_recv.p, g_m, g_v, src.gs, src.g_idx, v);
+    HOT_LAUNCHED(s);
     return 0;
 }
 
 } // namespace
 
+// Which of this rank's pages other ranks activate too, from everyone's ascending page-id list (all_pids: world rows of max_pages,
+// counts[r] valid entries each; slot_sorted: local slot of this rank's i-th smallest page id).
+//   per neighbour r (ascending): the shared pages in ascending id order - the same order on both sides - as local slots, appended
+//                                to x_slot (segment nbr_off / nbr_cnt): the exchange list;
+//   per shared local page:       the contributions in ascending rank order, sh_entry = index into the concatenated exchange list
+//                                (where that neighbour's partial sum arrives) or -1 for this rank's own partial; sh_owned = 1 when
+//                                this rank is the lowest sharer (it counts the page's nodes in reductions).
+void share_tables(int rank, int world, int max_pages, const int* counts, const uint32_t* all_pids, const int* slot_sorted, std::vector<int>& nbr_rank,
+    std::vector<long>& nbr_off, std::vector<long>& nbr_cnt, std::vector<int>& x_slot, std::vector<int>& sh_slot, std::vector<int>& sh_ptr,
+    std::vector<int>& sh_entry, std::vector<int>& sh_owned)
+{
+    nbr_rank.clear(); nbr_off.clear(); nbr_cnt.clear(); x_slot.clear(); sh_slot.clear(); sh_entry.clear(); sh_owned.clear();
+    sh_ptr.assign(1, 0);
+    const uint32_t* my = all_pids + (size_t)rank * max_pages;
+    const int nm = counts[rank];
+    std::vector<std::vector<std::pair<int, int>>> sharers(nm); // per local page (ascending-id index): (rank, index in the exchange list)
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        const uint32_t* other = all_pids + (size_t)r * max_pages;
+        const int no = counts[r];
+        const long off = (long)x_slot.size();
+        int i = 0, j = 0;
+        while (i < nm && j < no) {
+            if (my[i] < other[j]) ++i;
+            else if (my[i] > other[j]) ++j;
+            else {
+                sharers[i].emplace_back(r, (int)x_slot.size());
+                x_slot.push_back(slot_sorted[i]);
+                ++i; ++j;
+            }
+        }
+        if ((long)x_slot.size() > off) {
+            nbr_rank.push_back(r);
+            nbr_off.push_back(off);
+            nbr_cnt.push_back((long)x_slot.size() - off);
+        }
+    }
+    for (int i = 0; i < nm; ++i) {
+        if (sharers[i].empty()) continue;
+        sh_slot.push_back(slot_sorted[i]);
+        bool self_done = false;
+        for (const auto& pr : sharers[i]) { // neighbours were visited in ascending rank order
+            if (!self_done && pr.first > rank) { sh_entry.push_back(-1); self_done = true; }
+            sh_entry.push_back(pr.second);
+        }
+        if (!self_done) sh_entry.push_back(-1);
+        sh_ptr.push_back((int)sh_entry.size());
+        sh_owned.push_back(sharers[i].front().first > rank ? 1 : 0);
+    }
+}
+
+// shared-page tables for the pages of the current sort
 int dist_after_sort(Sim* s)
 {
     s->g0 = 0; s->g1 = s->n_groups; s->p0 = 0; s->p1 = s->N;
-    s->dof0 = 0; s->dof1 = 0; s->n_iface = 0;
-    s->iface_valid = false;
+    s->x_total = 0; s->n_sh = 0; s->n_owned_nodes = 0;
+    s->nbr_rank.clear(); s->nbr_off.clear(); s->nbr_cnt.clear();
+    s->own_valid = false;
     if (s->world <= 1) return 0;
-    // balanced contiguous split of the page groups by particle count (host: n_groups + 1 ints)
-    std::vector<int> first((size_t)s->n_groups + 1);
-    HOT_CUDA(cudaMemcpyAsync(first.data(), s->group_first.p, first.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    HOT_CUDA(cudaStreamSynchronize(s->stream));
-    std::vector<long> cut(s->world + 1, 0);
-    cut[s->world] = s->n_groups;
-    for (int r = 1; r < s->world; ++r) {
-        const long target = (long)((double)s->N * r / s->world);
-        cut[r] = std::lower_bound(first.begin(), first.end(), (int)target) - first.begin();
-        if (cut[r] > s->n_groups) cut[r] = s->n_groups;
-        if (cut[r] < cut[r - 1]) cut[r] = cut[r - 1];
-    }
-    std::vector<int> gr(s->n_groups);
-    for (int r = 0; r < s->world; ++r)
-        for (long g = cut[r]; g < cut[r + 1]; ++g) gr[g] = r;
-    HOT_CUDA(s->group_rank.reserve(s->n_groups));
-    HOT_CUDA(cudaMemcpyAsync(s->group_rank.p, gr.data(), gr.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
-    HOT_CUDA(cudaStreamSynchronize(s->stream));
-    s->g0 = cut[s->rank]; s->g1 = cut[s->rank + 1];
-    s->p0 = first[s->g0]; s->p1 = first[s->g1];
-    // which ranks touch which page, and the interface pages (touched by >= 2 ranks)
     cudaStream_t st = s->stream;
-    HOT_CUDA(s->page_mask.reserve(s->n_pages));
-    HOT_CUDA(s->iface_page.reserve(s->n_pages));
-    HOT_CUDA(s->head_flag.reserve(s->n_pages));
-    HOT_CUDA(s->dcount.reserve(16));
-    HOT_CUDA(cudaMemsetAsync(s->page_mask.p, 0, s->n_pages * sizeof(unsigned), st));
-    k_page_touch<<<nblk(s->n_groups * 8), TPB, 0, st>>>(s->n_groups, s->group_slot.p, s->group_rank.p, s->nbr8.p, s->page_mask.p);
-    HOT_LAUNCHED(s);
-    k_ipage_flags<<<nblk(s->n_pages), TPB, 0, st>>>(s->n_pages, s->page_mask.p, s->head_flag.p);
-    HOT_LAUNCHED(s);
-    size_t bytes = 0;
-    cub::DeviceSelect::Flagged(nullptr, bytes, cub::CountingInputIterator<int>(0), s->head_flag.p, s->iface_page.p, s->dcount.p, (int)s->n_pages, st);
-    HOT_CUDA(s->cub_tmp.reserve(bytes + 16));
-    HOT_CUDA(cub::DeviceSelect::Flagged(s->cub_tmp.p, bytes, cub::CountingInputIterator<int>(0), s->head_flag.p, s->iface_page.p, s->dcount.p,
-        (int)s->n_pages, st));
-    s->launches++;
-    HOT_CUDA(cudaMemcpyAsync(s->hcount + 20, s->dcount.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    HOT_CUDA(cudaStreamSynchronize(st));
-    s->n_iface_pages = s->hcount[20];
-    return 0;
-}
-
-// P2G of a partitioned object: sum the partial mass / momentum of the interface pages, then agree on which nodes carry mass
-// (one 32-bit mask per page) so that every rank computes the same DOF numbering as a single GPU would
-int dist_p2g_exchange(Sim* s, int* node_flags /* n_pages * E, out */)
-{
-    cudaStream_t st = s->stream;
-    const long cnt = (long)s->n_iface_pages * 4 * Geo::E;
-    KTime t(s, KC_TRANSFER);
-    // ONE sum all-reduce: [interface pages: m, mv] [one node mask per page from the page's only toucher]
-    int rc = reserve_xbuf(s, cnt + s->n_pages);
+    const int W = s->world;
+    // 1. everyone's page count, then everyone's ascending page-id list (padded to the largest)
+    HOT_CUDA(s->x_counts.reserve(2 * (size_t)W));
+    int np_local = (int)s->n_pages;
+    HOT_CUDA(cudaMemcpyAsync(s->x_counts.p + W, &np_local, sizeof(int), cudaMemcpyHostToDevice, st));
+    int rc = comm_all_gather(s, s->x_counts.p + W, s->x_counts.p, sizeof(int));
     if (rc) return rc;
-    if (cnt > 0) {
-        k_pack_pages<<<nblk(cnt), TPB, 0, st>>>(s->n_iface_pages, s->iface_page.p, s->g_stride, s->g_m.p, s->g_v.p, s->xbuf);
-        HOT_LAUNCHED(s);
-    }
-    k_page_nonzero<<<nblk(s->n_pages), TPB, 0, st>>>(s->n_pages, s->g_m.p, s->page_mask.p, s->rank, s->xbuf + cnt);
-    HOT_LAUNCHED(s);
-    if (s->allreduce(s->allreduce_user, 0, cnt + s->n_pages) != 0) return fail(s, "all-reduce callback failed");
-    if (cnt > 0) {
-        k_unpack_pages<<<nblk(cnt), TPB, 0, st>>>(s->n_iface_pages, s->iface_page.p, s->g_stride, s->xbuf, s->g_m.p, s->g_v.p);
-        HOT_LAUNCHED(s);
-    }
-    k_flags_from_bits<<<nblk((long)s->g_stride), TPB, 0, st>>>((long)s->g_stride, s->xbuf + cnt, s->page_mask.p, s->g_m.p, node_flags);
-    HOT_LAUNCHED(s);
+    std::vector<int> counts(W);
+    HOT_CUDA(cudaMemcpyAsync(counts.data(), s->x_counts.p, W * sizeof(int), cudaMemcpyDeviceToHost, st));
+    HOT_CUDA(cudaStreamSynchronize(st));
+    const int maxp = *std::max_element(counts.begin(), counts.end());
+    HOT_CUDA(s->x_pids.reserve((size_t)(W + 1) * maxp));
+    uint32_t* mine = s->x_pids.p + (size_t)W * maxp;
+    HOT_CUDA(cudaMemsetAsync(mine, 0xff, (size_t)maxp * sizeof(uint32_t), st));
+    HOT_CUDA(cudaMemcpyAsync(mine, s->pid_sorted.p, (size_t)s->n_pages * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    rc = comm_all_gather(s, mine, s->x_pids.p, (long)maxp * sizeof(uint32_t));
+    if (rc) return rc;
+    std::vector<uint32_t> all((size_t)W * maxp);
+    std::vector<int> slot_sorted(s->n_pages);
+    HOT_CUDA(cudaMemcpyAsync(all.data(), s->x_pids.p, all.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    HOT_CUDA(cudaMemcpyAsync(slot_sorted.data(), s->slot_sorted.p, slot_sorted.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    HOT_CUDA(cudaStreamSynchronize(st));
+    // 2. + 3. intersections and the CSR of contributions (host logic, also exported for the CPU tests: hot_share_tables)
+    std::vector<int> x_slot, sh_slot, sh_ptr, sh_entry, sh_owned;
+    share_tables(s->rank, W, maxp, counts.data(), all.data(), slot_sorted.data(), s->nbr_rank, s->nbr_off, s->nbr_cnt, x_slot, sh_slot, sh_ptr, sh_entry,
+        sh_owned);
+    s->x_total = (long)x_slot.size();
+    s->n_sh = (int)sh_slot.size();
+    auto up = [&](DevBuf<int>& d, const std::vector<int>& h) -> cudaError_t {
+        cudaError_t e = d.reserve(h.size() > 0 ? h.size() : 1);
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st);
+    };
+    HOT_CUDA(up(s->x_slot, x_slot));
+    HOT_CUDA(up(s->sh_slot, sh_slot));
+    HOT_CUDA(up(s->sh_ptr, sh_ptr));
+    HOT_CUDA(up(s->sh_entry, sh_entry));
+    HOT_CUDA(up(s->sh_owned, sh_owned));
+    HOT_CUDA(cudaStreamSynchronize(st)); // the host vectors go out of scope
     return 0;
 }
 
+// P2G of a partitioned object: complete mass / momentum on the shared pages (all sharers end with identical values)
+int dist_p2g_exchange(Sim* s)
+{
+    if (s->world <= 1) return 0;
+    KTime t(s, KC_TRANSFER);
+    PageSource src{4, s->g_m.p, s->g_v.p, s->g_stride, nullptr, nullptr};
+    return exchange_pages(s, src, s->g_m.p, s->g_v.p, nullptr);
+}
+
+// after the numbering: which nodes this rank counts in reductions
 int dist_after_numbering(Sim* s)
 {
     if (s->world <= 1) {
-        s->dof0 = 0; s->dof1 = s->num_nodes;
+        s->n_owned_nodes = s->num_nodes;
         return 0;
     }
-    if (s->iface_valid) return 0; // same sort -> same pages, same numbering
+    if (s->own_valid) return 0; // same sort -> same pages, same numbering
     cudaStream_t st = s->stream;
-    const long gn = (long)s->g_stride;
     const int nn = s->num_nodes;
-    HOT_CUDA(s->head_flag.reserve(nn > 0 ? nn : 1));
-    HOT_CUDA(s->iface_dof.reserve(nn > 0 ? nn : 1));
-    HOT_CUDA(s->dcount.reserve(16));
-    HOT_CUDA(cudaMemsetAsync(s->head_flag.p, 0, (size_t)nn * sizeof(int), st));
-    const int init[2] = {0x7fffffff, -1};
-    HOT_CUDA(cudaMemcpyAsync(s->dcount.p + 8, init, sizeof init, cudaMemcpyHostToDevice, st));
-    k_node_owner<<<nblk(gn), TPB, 0, st>>>(gn, s->g_idx.p, s->page_mask.p, s->rank, s->head_flag.p, s->dcount.p + 8);
-    HOT_LAUNCHED(s);
-    size_t bytes = 0;
-    cub::DeviceSelect::Flagged(nullptr, bytes, cub::CountingInputIterator<int>(0), s->head_flag.p, s->iface_dof.p, s->dcount.p, nn, st);
-    HOT_CUDA(s->cub_tmp.reserve(bytes + 16));
-    HOT_CUDA(cub::DeviceSelect::Flagged(s->cub_tmp.p, bytes, cub::CountingInputIterator<int>(0), s->head_flag.p, s->iface_dof.p, s->dcount.p, nn, st));
-    s->launches++;
-    HOT_CUDA(cudaMemcpyAsync(s->hcount + 16, s->dcount.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    HOT_CUDA(cudaMemcpyAsync(s->hcount + 17, s->dcount.p + 8, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    HOT_CUDA(s->own_node.reserve(nn > 0 ? nn : 1));
+    HOT_CUDA(cudaMemsetAsync(s->own_node.p, 1, (size_t)nn, st));
+    if (s->n_sh > 0) {
+        k_own_nodes<<<nblk((long)s->n_sh * Geo::E), TPB, 0, st>>>(s->n_sh, s->sh_slot.p, s->sh_owned.p, s->g_idx.p, s->own_node.p);
+        HOT_LAUNCHED(s);
+    }
+    // owned nodes of this rank and nodes of the whole object (N_n of the convergence tests, ImplicitSolver.h:192-202)
+    HOT_CUDA(s->x_scalars.reserve(64));
+    int rc = reduce_to<1>(s, nn, CountOwnF{s->own_node.p}, s->x_scalars.p, nullptr);
+    if (rc) return rc;
+    HOT_CUDA(cudaMemcpyAsync(s->x_scalars.p + 1, s->x_scalars.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    rc = comm_all_reduce(s, s->x_scalars.p + 1, 1, 0);
+    if (rc) return rc;
+    double h[2];
+    HOT_CUDA(cudaMemcpyAsync(h, s->x_scalars.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     HOT_CUDA(cudaStreamSynchronize(st));
-    s->n_iface = s->hcount[16];
-    s->dof0 = s->hcount[18] >= 0 ? s->hcount[17] : 0;
-    s->dof1 = s->hcount[18] >= 0 ? s->hcount[18] + 1 : 0;
-    s->iface_valid = true;
+    s->n_owned_nodes = (int)h[0];
+    s->global_nodes = (long)h[1];
+    s->own_valid = true;
     return 0;
+}
+
+// sum over the sharers on the shared nodes of a DOF array with `comps` per node
+int dist_exchange_shared(Sim* s, double* v, int comps)
+{
+    if (s->world <= 1) return 0;
+    KTime t(s, KC_TRANSFER);
+    PageSource src{comps, nullptr, nullptr, 0, s->g_idx.p, v};
+    return exchange_pages(s, src, nullptr, nullptr, v);
 }
 
 int dist_allreduce_buffer(Sim* s, double* dev, long count, int op)
 {
     if (s->world <= 1 || count <= 0) return 0;
-    int rc = reserve_xbuf(s, count);
-    if (rc) return rc;
-    HOT_CUDA(cudaMemcpyAsync(s->xbuf, dev, count * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
-    if (s->allreduce(s->allreduce_user, op, count) != 0) return fail(s, "all-reduce callback failed");
-    HOT_CUDA(cudaMemcpyAsync(dev, s->xbuf, count * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
-    return 0;
-}
-
-int dist_exchange_iface(Sim* s, double* v, int comps)
-{
-    if (s->world <= 1 || s->n_iface <= 0) return 0;
-    const long count = (long)s->n_iface * comps;
-    int rc = reserve_xbuf(s, count);
-    if (rc) return rc;
-    KTime t(s, KC_TRANSFER);
-    k_pack<<<nblk(count), TPB, 0, s->stream>>>(s->n_iface, comps, s->iface_dof.p, v, s->xbuf);
-    HOT_LAUNCHED(s);
-    if (s->allreduce(s->allreduce_user, 0, count) != 0) return fail(s, "all-reduce callback failed");
-    k_unpack<<<nblk(count), TPB, 0, s->stream>>>(s->n_iface, comps, s->iface_dof.p, s->xbuf, v);
-    HOT_LAUNCHED(s);
-    return 0;
+    return comm_all_reduce(s, dev, count, op);
 }
 
 int dist_allreduce_host(Sim* s, double* host, int count, int op)
 {
     if (s->world <= 1) return 0;
-    int rc = reserve_xbuf(s, count);
+    HOT_CUDA(s->x_scalars.reserve(64));
+    if (count > 64) return fail(s, "dist_allreduce_host: at most 64 scalars");
+    HOT_CUDA(cudaMemcpyAsync(s->x_scalars.p, host, count * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    int rc = comm_all_reduce(s, s->x_scalars.p, count, op);
     if (rc) return rc;
-    HOT_CUDA(cudaMemcpyAsync(s->xbuf, host, count * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    if (s->allreduce(s->allreduce_user, op, count) != 0) return fail(s, "all-reduce callback failed");
-    HOT_CUDA(cudaMemcpyAsync(host, s->xbuf, count * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    HOT_CUDA(cudaMemcpyAsync(host, s->x_scalars.p, count * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     HOT_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }

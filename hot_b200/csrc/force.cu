@@ -157,9 +157,11 @@ __global__ void __launch_bounds__(US_THREADS) k_update_state(const int* __restri
 // inertia + gravity terms of totalEnergy (ImplicitSolver.h:254-275, Inertia.cpp:16-30): [sum m |dv|^2, sum m g.dv]
 struct EnergyNodesF {
     const double *dv, *mass;
+    const unsigned char* own; // partitioned object: shared nodes count on one rank
     double g0, g1, g2;
     __device__ void operator()(long i, double (&acc)[2]) const
     {
+        if (own && !own[i]) return;
         const double a = dv[3 * i], b = dv[3 * i + 1], c = dv[3 * i + 2], m = mass[i];
         acc[0] += (a * a + b * b + c * c) * m;
         acc[1] += (g0 * a + g1 * b + g2 * c) * m;
@@ -773,8 +775,7 @@ int update_state(Sim* s, bool want_energy, double* energy)
         // own particles' strain energy + own nodes' inertia / gravity terms, summed over the ranks
         int rc = reduce_to<1>(s, s->g1 - s->g0, SumF{s->group_psi.p}, s->red_out.p + 8, nullptr);
         if (rc) return rc;
-        const int d0 = s->world > 1 ? s->dof0 : 0, d1 = s->world > 1 ? s->dof1 : s->num_nodes;
-        rc = reduce_to<2>(s, d1 - d0, EnergyNodesF{s->dv.p + 3 * (size_t)d0, s->mass_matrix.p + d0, s->gravity[0], s->gravity[1], s->gravity[2]},
+        rc = reduce_to<2>(s, s->num_nodes, EnergyNodesF{s->dv.p, s->mass_matrix.p, s->world > 1 ? s->own_node.p : nullptr, s->gravity[0], s->gravity[1], s->gravity[2]},
             s->red_out.p + 9, nullptr);
         if (rc) return rc;
         HOT_CUDA(cudaMemcpyAsync(s->h_red, s->red_out.p + 8, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -825,7 +826,7 @@ int scatter_to_dofs(Sim* s, typename Policy::Args a, double* Policy::Args::*targ
         if (rc) return rc;
     }
     if (s->world > 1) {
-        int rc = dist_exchange_iface(s, dst, comps);
+        int rc = dist_exchange_shared(s, dst, comps);
         if (rc) return rc;
         k_add<<<nblk((long)m), TPB, 0, st>>>((long)m, dst, out);
         HOT_LAUNCHED(s);

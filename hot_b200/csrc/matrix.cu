@@ -362,7 +362,7 @@ int build_diagonal_mf(Sim* s, int Ainv)
         HOT_LAUNCHED(s);
     }
     if (s->world > 1) {
-        rc = dist_exchange_iface(s, dst, 9);
+        rc = dist_exchange_shared(s, dst, 9);
         if (rc) return rc;
         k_add9<<<nblk(9 * (long)nn), TPB, 0, st>>>(9 * (long)nn, dst, s->diag_mf.p);
         HOT_LAUNCHED(s);

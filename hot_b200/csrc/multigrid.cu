@@ -1232,8 +1232,7 @@ int vec_dot(Sim* s, long n, const double* a, const double* b, double* dev_out, d
     if (s->world <= 1 || n != 3L * s->num_nodes) return reduce_to<1>(s, n, DotF{a, b}, dev_out, host_out);
     HOT_CUDA(s->red_out.reserve(64));
     if (!dev_out) dev_out = s->red_out.p;
-    const size_t o = 3 * (size_t)s->dof0;
-    int rc = reduce_to<1>(s, 3L * (s->dof1 - s->dof0), DotF{a + o, b + o}, dev_out, nullptr);
+    int rc = reduce_to<1>(s, n, OwnDotF{a, b, s->own_node.p}, dev_out, nullptr);
     if (!rc) rc = dist_allreduce_buffer(s, dev_out, 1, 0);
     if (rc || !host_out) return rc;
     HOT_CUDA(cudaMemcpyAsync(s->h_red, dev_out, sizeof(double), cudaMemcpyDeviceToHost, s->stream));

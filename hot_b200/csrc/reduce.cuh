@@ -95,4 +95,13 @@ struct DotF { // sum a_i b_i
     __device__ void operator()(long i, double (&acc)[1]) const { acc[0] += a[i] * b[i]; }
 };
 
+struct OwnDotF { // the same over the nodes this rank counts (partitioned object)
+    const double *a, *b;
+    const unsigned char* own;
+    __device__ void operator()(long i, double (&acc)[1]) const
+    {
+        if (own[i / 3]) acc[0] += a[i] * b[i];
+    }
+};
+
 } // namespace hot

@@ -18,6 +18,13 @@
 #include <vector>
 
 struct hot_collider; // include/hot_b200.h
+// mirror of hot_transport (include/hot_b200.h) so that this header does not need the C ABI header
+struct hot_transport_fwd {
+    void* user = nullptr;
+    int (*all_reduce)(void* user, double* dev, long count, int op) = nullptr;
+    int (*all_gather)(void* user, const void* dev_send, void* dev_recv, long bytes_per_rank) = nullptr;
+    int (*neighbor_exchange)(void* user, int n_peers, const int* peers, double* const* send, double* const* recv, const long* count) = nullptr;
+};
 
 namespace hot {
 
@@ -235,22 +242,24 @@ struct Sim {
     // HOTSettings (Projects/multigrid/Configurations.h:18-42)
     int mg_smoother = 5, mg_coarse = 2, mg_Ainv = 1, mg_levels = 3, mg_times = 1, mg_levelscale = 0;
     double mg_topomega = 0.1;
-    // ---- multi-GPU partition of ONE object (dist.cu): the sort / page table / DOF numbering are replicated on every rank
-    // (identical to the single-GPU result), particle work is split by contiguous page-group ranges, nodes are owned by
-    // the rank whose groups touch their page first (= contiguous DOF ranges), and scatter results are summed over the ranks
-    // on the interface nodes only (pages touched by >= 2 ranks) through the caller-provided all-reduce.
+    // ---- one object over several GPUs (dist.cu): this rank's particles only; pages activated by >= 2 ranks are shared, scatter
+    // results are summed over the sharers after every scatter, reductions count a shared node on its lowest-ranked sharer
     int rank = 0, world = 1;
-    int (*allreduce)(void* user, int op, long count) = nullptr; // (user, op 0 sum / 1 max / 2 reserve, count of doubles in the exchange buffer)
-    void* allreduce_user = nullptr;
-    double* xbuf = nullptr; // caller-owned device exchange buffer
-    long xbuf_cap = 0;
-    long g0 = 0, g1 = 0, p0 = 0, p1 = 0; // own page groups [g0, g1) and sorted particles [p0, p1)
-    int dof0 = 0, dof1 = 0; // own DOF ids
-    int n_iface = 0;
-    bool iface_valid = false; // interface list built for the current sort
-    DevBuf<int> iface_dof, group_rank, iface_page;
-    int n_iface_pages = 0;
-    DevBuf<unsigned> page_mask;
+    void* nccl_comm = nullptr; // ncclComm_t (hot_comm_init_nccl) ...
+    hot_transport_fwd transport; // ... or the caller's callbacks (hot_set_partition)
+    bool has_transport = false;
+    long g0 = 0, g1 = 0, p0 = 0, p1 = 0; // page groups / sorted particles the particle kernels run on: all of this rank's
+    std::vector<int> nbr_rank; // neighbours (ranks sharing pages with this one), ascending
+    std::vector<long> nbr_off, nbr_cnt; // their segments of the exchange lists, in pages
+    long x_total = 0; // exchange pages over all neighbours
+    int n_sh = 0; // shared local pages
+    int n_owned_nodes = 0;
+    long global_nodes = 0; // nodes of the whole object = sum of the ranks' owned nodes
+    bool own_valid = false;
+    DevBuf<int> x_counts, x_slot, sh_slot, sh_ptr, sh_entry, sh_owned;
+    DevBuf<uint32_t> x_pids;
+    DevBuf<double> x_send, x_recv, x_scalars;
+    DevBuf<unsigned char> own_node; // 1: this rank counts the node in dots / norms
     DevBuf<double> scat_tmp;
     DevBuf<double> sv[32]; // solver work vectors (solver.cu)
     bool dv0_valid = false;
@@ -313,12 +322,18 @@ int add_scaled_force_differentials(Sim* s, double scale, const double* x, double
 int hessian_apply_mf(Sim* s, const double* x, double* b);
 int eval_cn_tolerance(Sim* s, double eps, double dt, double* tol);
 // dist.cu
-int dist_after_sort(Sim* s); // group / particle ranges of this rank
-int dist_p2g_exchange(Sim* s, int* node_flags); // interface-page sum of (m, mv) + global non-zero node flags
-int dist_after_numbering(Sim* s); // page ownership, DOF ranges, interface node list
-int dist_allreduce_buffer(Sim* s, double* dev, long count, int op); // whole device array, in place
-int dist_exchange_iface(Sim* s, double* v, int comps); // sum over ranks on the interface nodes of a DOF array with `comps` per node
-int dist_allreduce_host(Sim* s, double* host, int count, int op); // a few scalars
+int comm_unique_id(void* out128);
+int comm_init_nccl(Sim* s, int rank, int world, const void* id128);
+void comm_destroy(Sim* s);
+void share_tables(int rank, int world, int max_pages, const int* counts, const uint32_t* all_pids, const int* slot_sorted, std::vector<int>& nbr_rank,
+    std::vector<long>& nbr_off, std::vector<long>& nbr_cnt, std::vector<int>& x_slot, std::vector<int>& sh_slot, std::vector<int>& sh_ptr,
+    std::vector<int>& sh_entry, std::vector<int>& sh_owned);
+int dist_after_sort(Sim* s); // shared-page tables of the current sort
+int dist_p2g_exchange(Sim* s); // complete (m, mv) on the shared pages
+int dist_after_numbering(Sim* s); // node ownership for reductions
+int dist_allreduce_buffer(Sim* s, double* dev, long count, int op); // a few device scalars, in place
+int dist_exchange_shared(Sim* s, double* v, int comps); // sum over the sharers on the shared nodes of a DOF array with `comps` per node
+int dist_allreduce_host(Sim* s, double* host, int count, int op); // a few host scalars
 // colliders.cu
 int set_colliders(Sim* s, int n, const ::hot_collider* objs);
 int build_bc_from_colliders(Sim* s, int mode, int* n_bc);

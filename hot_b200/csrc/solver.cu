@@ -31,8 +31,10 @@ inline int nblk(long n) { return (int)((n + TPB - 1) / TPB); }
 // sum_i |r_i|^2 / tol_i^2  (shouldExitByCN, ImplicitSolver.h:192-197) and sum |r_i|^2
 struct CNNormF {
     const double *r, *tol;
+    const unsigned char* own; // partitioned object: shared nodes count on one rank
     __device__ void operator()(long i, double (&acc)[2]) const
     {
+        if (own && !own[i]) return;
         const double a = r[3 * i], b = r[3 * i + 1], c = r[3 * i + 2], n2 = a * a + b * b + c * c, t = tol ? tol[i] : 1.0;
         acc[0] += n2 / (t * t);
         acc[1] += n2;
@@ -92,8 +94,7 @@ int residual_norms(Objective& O, const double* r, double* l2, double* scaled)
 {
     Sim* s = O.s;
     double h[2];
-    const int d0 = s->world > 1 ? s->dof0 : 0, d1 = s->world > 1 ? s->dof1 : s->num_nodes;
-    RC(reduce_to<2>(s, d1 - d0, CNNormF{r + 3 * (size_t)d0, O.opt.usecn ? s->cn_tol.p + d0 : nullptr}, s->red_out.p + 16, h));
+    RC(reduce_to<2>(s, s->num_nodes, CNNormF{r, O.opt.usecn ? s->cn_tol.p : nullptr, s->world > 1 ? s->own_node.p : nullptr}, s->red_out.p + 16, h));
     RC(dist_allreduce_host(s, h, 2, 0));
     *l2 = sqrt(h[1]);
     *scaled = h[0];
@@ -104,7 +105,7 @@ int residual_norms(Objective& O, const double* r, double* l2, double* scaled)
 int should_exit_by_cn(Objective& O, const double* residual, bool* exit, double* l2_out)
 {
     Sim* s = O.s;
-    const int nn = s->num_nodes;
+    const long nn = s->world > 1 ? s->global_nodes : s->num_nodes; // N_n of the whole object
     double l2, scaled;
     RC(residual_norms(O, residual, &l2, &scaled));
     if (l2_out) *l2_out = l2;
@@ -444,7 +445,7 @@ int hot_backward_euler_step(hot_sim* s, const hot_solver_options* opt, hot_solve
         double nmax = s->h_red[0];
         rc = dist_allreduce_host(s, &nmax, 1, 1);
         if (rc) return rc;
-        tol = opt->cneps * s->dt * 24 * std::sqrt((double)s->num_nodes) * s->dx * s->dx * nmax;
+        tol = opt->cneps * s->dt * 24 * std::sqrt((double)(s->world > 1 ? s->global_nodes : s->num_nodes)) * s->dx * s->dx * nmax;
     }
     if (log) log->tolerance = tol;
     const double cg_tol = opt->usecn ? tol : 1.0; // cg.setTolerance(1) in the objective ctor, maxcntol with --usecn

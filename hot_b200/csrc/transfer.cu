@@ -475,15 +475,11 @@ int p2g(Sim* s)
             if (rc) return rc;
         }
     }
-    int rc;
-    if (s->world > 1) { // ghost-layer exchange: interface pages only (+ one mask per page so that the numbering is global)
-        HOT_CUDA(s->head_flag.reserve(gn));
-        rc = dist_p2g_exchange(s, s->head_flag.p);
-        if (rc) return rc;
-    }
+    int rc = dist_p2g_exchange(s); // shared pages: partial sums exchanged between the sharing ranks, added in rank order
+    if (rc) return rc;
     {
         KTime t(s, KC_NUMBER);
-        rc = number_nodes(s, s->world > 1);
+        rc = number_nodes(s, false);
     }
     if (rc) return rc;
     rc = dist_after_numbering(s);

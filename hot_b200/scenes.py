@@ -125,13 +125,14 @@ def config_c1(seed=0):
     return assemble([(X, (18 * dx) ** 3, 1000.0, 2.5e4, 0.4)], dx, seed)
 
 
-def config_c2(seed=0, dx=0.12 / 23, E_mid=1e9):
+def config_c2(seed=0, dx=0.12 / 23, E_mid=1e9, copy=0):
     """twisting bar, test 777001 (MultigridInit3D.h:571-664): three stacked boxes 0.12 x 0.3 x 0.12 at (2 +- .06, 2.8 .. 3.7, 2 +- .06),
     E = 1e5 / -cmd0 (1e9) / 1e5, nu .3, rho 2e3, ppc 12, each sampled separately with the reference's Poisson-tile recipe;
-    dx = 0.12 / 23 (reference 0.0075) for the ~1 M particles BASELINE.json names: 951 k particles"""
+    dx = 0.12 / 23 (reference 0.0075) for the ~1 M particles BASELINE.json names: 951 k particles.  copy = k shifts the bar by k bar lengths."""
     half = 0.06
     parts = []
     for y0, E in ((2.8, 1e5), (3.1, E_mid), (3.4, 1e5)):
+        y0 += 0.9 * copy          # copy k: the same bar stacked on top of copy k - 1 (weak scaling: one object of N bars end to end)
         X = poisson_box((2 - half, y0, 2 - half), (2 + half, y0 + 0.3, 2 + half), dx, 12)
         parts.append((X, 0.12 * 0.3 * 0.12, 2e3, E, 0.3))
     return assemble(parts, dx, seed)

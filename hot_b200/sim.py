@@ -7,7 +7,7 @@ libhot_b200.so on the GPU; numpy arrays are only the caller-owned host buffers o
 import ctypes as C
 import numpy as np
 
-from ._lib import load_library, SolverOptions, SolveLog, ALLREDUCE_FN
+from ._lib import load_library, SolverOptions, SolveLog, Transport, T_ALL_REDUCE, T_ALL_GATHER, T_NEIGHBOR_EXCHANGE
 
 
 class HotError(RuntimeError):
@@ -430,32 +430,64 @@ class MpmSimulationB200:
         self._check(self._lib.hot_add_scaled_force_differentials(self._h, float(scale), _ptr(x), _ptr(f)))
         return f
 
-    # ---- one object over several GPUs (include/hot_b200.h "row (e)")
-    def set_partition(self, rank, world, allreduce=None, alloc=None):
-        """allreduce(buffer, op, count): sum (op 0) / max (op 1) of buffer[:count] over the ranks, in place, on the handle's stream.
-        alloc(n_doubles) -> (object keeping the memory alive, device pointer).  See hot_b200.dist.torch_partition."""
-        self._xkeep = None
+    # ---- one object over several GPUs (include/hot_b200.h "one object over the GPUs of a box")
+    def init_nccl(self, rank, world, unique_id):
+        """NCCL inside the library: `unique_id` = the 128 bytes of hot_b200.comm_unique_id() from rank 0, distributed by the caller"""
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._lib.hot_comm_init_nccl(self._h, int(rank), int(world), buf))
 
-        def cb(user, op, count):
-            try:
-                if op == 2:
-                    self._xkeep, ptr = alloc(int(count) + int(count) // 4 + 1024)
-                    self._xcap = int(count) + int(count) // 4 + 1024
-                    self._lib.hot_set_exchange_buffer(self._h, C.c_void_p(int(ptr)), self._xcap)
-                else:
-                    allreduce(self._xkeep, int(op), int(count))
-                return 0
-            except Exception as e:  # pragma: no cover - surfaces as HotError through the return code
-                import traceback; traceback.print_exc()
-                return 1
+    def set_partition(self, rank, world, all_reduce=None, all_gather=None, neighbor_exchange=None):
+        """the caller's collectives, on HOST numpy arrays (this wrapper stages the device buffers with hot_memcpy_d2h / h2d):
+        all_reduce(array f64, op 0 sum / 1 max) -> array; all_gather(array u8) -> array of world x len;
+        neighbor_exchange(peers, [array f64 per peer]) -> [array f64 per peer] (same lengths)."""
+        lib, h = self._lib, self._h
 
-        self._cb = ALLREDUCE_FN(cb) if world > 1 else ALLREDUCE_FN(0)
-        self._check(self._lib.hot_set_partition(self._h, int(rank), int(world), self._cb, None))
+        def d2h(ptr, nbytes, dtype):
+            a = np.empty(nbytes // np.dtype(dtype).itemsize, dtype=dtype)
+            if nbytes:
+                self._check(lib.hot_memcpy_d2h(h, a.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), nbytes))
+            return a
+
+        def h2d(ptr, a):
+            a = np.ascontiguousarray(a)
+            if a.nbytes:
+                self._check(lib.hot_memcpy_h2d(h, C.c_void_p(ptr), a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+        def guard(f):
+            def g(*args):
+                try:
+                    f(*args)
+                    return 0
+                except Exception:  # pragma: no cover - surfaces as HotError through the return code
+                    import traceback; traceback.print_exc()
+                    return 1
+            return g
+
+        @guard
+        def cb_all_reduce(user, dev, count, op):
+            h2d(dev, np.asarray(all_reduce(d2h(dev, 8 * count, np.float64), int(op)), dtype=np.float64))
+
+        @guard
+        def cb_all_gather(user, send, recv, nbytes):
+            h2d(recv, np.asarray(all_gather(d2h(send, nbytes, np.uint8)), dtype=np.uint8).reshape(-1))
+
+        @guard
+        def cb_exchange(user, n_peers, peers, send, recv, count):
+            ps = [int(peers[j]) for j in range(n_peers)]
+            out = neighbor_exchange(ps, [d2h(send[j], 8 * count[j], np.float64) for j in range(n_peers)])
+            for j in range(n_peers):
+                h2d(recv[j], np.asarray(out[j], dtype=np.float64))
+
+        if world > 1:
+            self._transport = Transport(None, T_ALL_REDUCE(cb_all_reduce), T_ALL_GATHER(cb_all_gather), T_NEIGHBOR_EXCHANGE(cb_exchange))
+            self._check(lib.hot_set_partition(h, int(rank), int(world), C.byref(self._transport)))
+        else:
+            self._check(lib.hot_set_partition(h, int(rank), int(world), None))
 
     def get_partition(self):
         out = (C.c_long * 8)()
         self._check(self._lib.hot_get_partition(self._h, out))
-        return dict(zip(("group0", "group1", "particle0", "particle1", "dof0", "dof1", "n_interface", "world"), [int(v) for v in out]))
+        return dict(zip(("rank", "world", "neighbors", "shared_pages", "exchange_pages", "owned_nodes", "global_nodes", "particles"), [int(v) for v in out]))
 
     # ---- plasticity (PlasticityApplier.cpp): applied by gridToParticles after evolveStrain
     def set_plasticity(self, model, params=()):

@@ -117,20 +117,44 @@ int hot_get_plastic_state(hot_sim* h, double* Jp, double* mu, double* lambda);
 int hot_set_plastic_state(hot_sim* h, const double* Jp);
 
 /* ---- one object over the GPUs of a box (no counterpart in the reference, which is single-process: SURVEY 2a / 8e) ------
- * Every rank holds all particle positions and runs the same sort / page activation / DOF numbering (bit-identical on
- * every rank and to the single-GPU result).  Page groups are cut into `world` contiguous ranges balanced by particle count;
- * a rank runs the particle kernels on its range only, owns the nodes whose pages its groups touch first, and scatter results
- * are summed over the ranks on the interface nodes only (pages touched by >= 2 ranks) through the caller's all-reduce:
- * op 0 = sum, 1 = max over `count` doubles at the start of the exchange buffer, enqueued on the handle's stream (e.g.
- * ncclAllReduce, or torch.distributed.all_reduce on a tensor aliasing the buffer); op 2 = "make the exchange buffer at
- * least `count` doubles" (the callback answers with hot_set_exchange_buffer).  Returns non-zero on failure.
- * Supported partitioned path: sort, P2G, G2P, updateState, residual, matrix-free Hessian apply, block-Jacobi diagonal, CN
- * tolerance and the matrix-free PN-PCG solve (-lsolver 2 --matfree); the assembled-matrix / multigrid path is single-GPU. */
-typedef int (*hot_allreduce_fn)(void* user, int op, long count);
-int hot_set_partition(hot_sim* h, int rank, int world, hot_allreduce_fn fn, void* user);
-int hot_set_exchange_buffer(hot_sim* h, void* device_ptr, long capacity_doubles);
-/* {group0, group1, particle0, particle1 (sorted index ranges), dof0, dof1 (owned DOF ids), interface nodes, world} */
+ * One process and one handle per GPU.  Every rank gives ITS particles to hot_set_particles (any distribution is correct; compact
+ * slabs keep the seams small) and is locally a complete single-GPU object: own sort, own page list (its particles' pages + the
+ * +1 neighbours of MpmSimulationBase.cpp:1104-1124), own DOF numbering.  Pages activated by two or more ranks are SHARED: after
+ * every particle->grid scatter the partial sums of the shared pages travel between the sharing ranks only and are added in
+ * ascending rank order on every sharer, so shared nodes carry bit-identical values on all their ranks and the gathers need no
+ * communication.  DOF vectors are local (shared nodes replicated); dots / norms count a shared node on its lowest-ranked sharer
+ * and all-reduce 1-3 scalars.  Node ids differ between ranks and from a single-GPU run: identify nodes by hot_get_id2coord.
+ * Partitioned solver path: matrix-free PN-PCG (-lsolver 2 --matfree); the assembled-matrix / multigrid path is single-GPU.
+ *
+ * Transport, one of:
+ *  - NCCL inside the library: rank 0 calls hot_comm_unique_id, the caller distributes the 128 bytes (MPI / torch.distributed / a
+ *    file), every rank calls hot_comm_init_nccl.  The shared-page exchange is one grouped ncclSend / ncclRecv per neighbour on the
+ *    handle's stream; NCCL is resolved with dlopen("libnccl.so.2") at that point, so the library loads without it.
+ *  - the caller's callbacks (hot_set_partition): all pointers are device pointers, the calls are ordered after everything enqueued
+ *    on the handle's stream and must be complete (or enqueued on that stream) when they return; non-zero = failure. */
+typedef struct hot_transport {
+    void* user;
+    int (*all_reduce)(void* user, double* dev, long count, int op);                                  /* in place; op 0 sum, 1 max */
+    int (*all_gather)(void* user, const void* dev_send, void* dev_recv, long bytes_per_rank);       /* recv = world x bytes_per_rank, by rank */
+    int (*neighbor_exchange)(void* user, int n_peers, const int* peers, double* const* send, double* const* recv,
+        const long* count);                                                                      /* count[j] doubles to AND from peers[j] */
+} hot_transport;
+int hot_comm_unique_id(void* id128);
+int hot_comm_init_nccl(hot_sim* h, int rank, int world, const void* id128);
+int hot_set_partition(hot_sim* h, int rank, int world, const hot_transport* transport);
+/* {rank, world, neighbour ranks, shared local pages, pages exchanged per scatter (sum over neighbours), nodes this rank counts
+ * in reductions, nodes of the whole object (the last two -1 before hot_p2g), local particles} */
 int hot_get_partition(hot_sim* h, long* out8);
+/* The host logic behind the shared-page tables, callable without a device (CPU tests of the N > 1 path): from every rank's
+ * ascending page-id list (all_pids: world rows of max_pages, counts[r] valid) builds this rank's neighbour list, exchange list
+ * (x_slot: local slots, per neighbour in ascending page id) and, per shared local page, the contributions in ascending rank order
+ * (sh_entry: index into the exchange list, -1 = own partial) + whether this rank is the page's lowest sharer (sh_owned).
+ * Output arrays are caller-allocated for the worst case (see api.cu). */
+int hot_share_tables(int rank, int world, int max_pages, const int* counts, const unsigned* all_pids, const int* slot_sorted, int* n_nbr,
+    int* nbr_rank, long* nbr_off, long* nbr_cnt, int* n_x, int* x_slot, int* n_sh, int* sh_slot, int* sh_ptr, int* sh_entry, int* sh_owned);
+/* synchronous raw copies on the handle's stream, for transport callbacks written without a CUDA binding */
+int hot_memcpy_d2h(hot_sim* h, void* host, const void* dev, long bytes);
+int hot_memcpy_h2d(hot_sim* h, void* dev, const void* host, long bytes);
 
 /* ---- force model: the operator surface ImplicitSolverObjective drives (Projects/multigrid/ImplicitSolver.h) ------- */
 /* simulation.dt / simulation.gravity (MpmSimulationBase.h:69-131) */

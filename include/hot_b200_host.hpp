@@ -487,30 +487,23 @@ public:
     }
     void applyPlasticity() { check(hot_apply_plasticity(h)); }
 
-    // One object over the GPUs of a box (include/hot_b200.h "one object over the GPUs"; no counterpart in the single-process
-    // reference): one MpmSimulationB200 per process / GPU.  `allreduce(op, count)` sums (op 0) or maximises (op 1) the first
-    // `count` doubles of the exchange buffer over the ranks on the handle's stream (e.g. ncclAllReduce); op 2 asks for a buffer of
-    // at least `count` doubles, which the callback hands over through setExchangeBuffer.
-    std::function<int(int, long)> allreduce;
-    void setPartition(int rank, int world, std::function<int(int, long)> fn)
+    // One object over the GPUs of a box (include/hot_b200.h "one object over the GPUs of a box"; no counterpart in the single-process
+    // reference): one MpmSimulationB200 per process / GPU, each holding its own particles.  Either NCCL inside the library
+    // (commUniqueId on rank 0 -> distribute the 128 bytes -> initNccl on every rank) or the caller's collectives (setPartition).
+    static std::array<unsigned char, 128> commUniqueId()
     {
-        allreduce = std::move(fn);
-        check(hot_set_partition(h, rank, world, world > 1 ? &MpmSimulationB200::allreduce_trampoline : nullptr, this));
+        std::array<unsigned char, 128> id;
+        if (hot_comm_unique_id(id.data()) != 0) throw HotError("hot_comm_unique_id failed (NCCL not loadable)");
+        return id;
     }
-    void setExchangeBuffer(void* device_ptr, long capacity_doubles) { check(hot_set_exchange_buffer(h, device_ptr, capacity_doubles)); }
-    struct Partition { long group0, group1, particle0, particle1, dof0, dof1, interface_nodes, world; };
+    void initNccl(int rank, int world, const std::array<unsigned char, 128>& id) { check(hot_comm_init_nccl(h, rank, world, id.data())); }
+    void setPartition(int rank, int world, const hot_transport* transport) { check(hot_set_partition(h, rank, world, transport)); }
+    struct Partition { long rank, world, neighbors, shared_pages, exchange_pages, owned_nodes, global_nodes, particles; };
     Partition partition()
     {
         long o[8];
         check(hot_get_partition(h, o));
         return Partition{o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]};
-    }
-
-private:
-    static int allreduce_trampoline(void* user, int op, long count)
-    {
-        auto* self = static_cast<MpmSimulationB200*>(user);
-        return self->allreduce ? self->allreduce(op, count) : -1;
     }
 
 public:

@@ -34,6 +34,6 @@ def test_reference_arm_under_torchrun_env():
     assert r0.returncode == 0, r0.stderr[-2000:]
     j = json.loads(r0.stdout.strip())
     assert j["n_gpus"] == 2 and j["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
-    assert "extended 2x" in j["config"]["workload"]
+    assert "2 copies end to end" in j["config"]["workload"] and j["config"]["n_gpus"] == 2 and j["scaling"] == "weak"
     r1 = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1", "OMP_NUM_THREADS": "1"}, gpus=2)
     assert r1.returncode == 0 and r1.stdout.strip() == ""

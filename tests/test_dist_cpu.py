@@ -1,5 +1,6 @@
-"""world_size-2 / 3 gloo tests on CPU of the host-side logic of the partitioned path (hot_b200/dist.py): the balanced
-contiguous cut of the page groups and the interface-only exchange protocol (pack -> all-reduce -> unpack)."""
+"""world_size-2 / 3 gloo tests on CPU of the host-side logic of the partitioned path: the slab split of the particles
+(hot_b200/dist.py), the library's shared-page tables (hot_share_tables = the code dist_after_sort runs after its all-gather) and
+the exchange protocol (pack -> neighbour send / recv -> add in ascending rank order) emulated over gloo."""
 import os
 import socket
 import subprocess
@@ -8,7 +9,7 @@ import sys
 import numpy as np
 import pytest
 
-from hot_b200.dist import split_groups
+from hot_b200.dist import split_slabs
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -27,24 +28,21 @@ def launch(kind, world, out_dir, timeout=300):
     return [np.load(os.path.join(out_dir, f"rank{r}.npz")) for r in range(world)]
 
 
-def test_split_groups_properties():
+def test_split_slabs_properties():
     rng = np.random.default_rng(1)
+    X = rng.random((10007, 3))
     for world in (1, 2, 3, 8):
-        sizes = rng.integers(1, 300, size=1000)
-        first = np.concatenate([[0], np.cumsum(sizes)]).tolist()
-        cut = split_groups(first, first[-1], world)
-        assert cut[0] == 0 and cut[-1] == len(sizes) and all(a <= b for a, b in zip(cut, cut[1:]))
-        loads = [first[cut[r + 1]] - first[cut[r]] for r in range(world)]
-        assert sum(loads) == first[-1]
-        assert max(loads) - min(loads) <= 2 * sizes.max()            # balanced up to one group
-    # degenerate: fewer groups than ranks
-    cut = split_groups([0, 10, 20], 20, 8)
-    assert cut[0] == 0 and cut[-1] == 2 and all(a <= b for a, b in zip(cut, cut[1:]))
+        parts = split_slabs(X, world)
+        allp = np.concatenate(parts)
+        assert len(allp) == len(X) and len(np.unique(allp)) == len(X)                 # a partition
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1            # balanced
+        for a, b in zip(parts, parts[1:]):
+            assert X[a, 1].max() <= X[b, 1].min()                                      # slabs along y
+        assert all((np.diff(p) > 0).all() for p in parts)                              # original order kept inside a slab
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_interface_exchange_protocol_gloo(tmp_path, world):
+def test_shared_page_tables_and_exchange_protocol_gloo(tmp_path, world):
     res = launch("cpu", world, tmp_path)
     assert all(bool(r["ok"]) for r in res)
-    assert all((r["cut"] == res[0]["cut"]).all() for r in res)
-    assert res[0]["n_iface"] > 0
+    assert all(int(r["n_shared"]) > 0 and int(r["n_nbr"]) == world - 1 for r in res)
