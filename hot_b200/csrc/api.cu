@@ -258,6 +258,8 @@ int hot_set_particles(hot_sim* s, long n, const double* X, const double* V, cons
     HOT_LAUNCHED(s);
     s->sorted = false;
     s->p2g_done = false;
+    s->dpdf_norm_max = -1.0; // new material parameters: computeCharacteristicNorm's cache starts over
+    s->dv0_valid = false;
     HOT_CUDA(cudaStreamSynchronize(st)); // the caller's arrays may be released / overwritten when the call returns (pinned memory is copied asynchronously)
     return 0;
 }

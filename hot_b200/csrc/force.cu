@@ -888,8 +888,7 @@ static int hessian_scatter(Sim* s, double scale, const double* x, double* out)
     if (s->g1 > s->g0) {
         static const bool tma = !(getenv("HOT_HG_TMA") && atoi(getenv("HOT_HG_TMA")) == 0); // A/B switch, default on
         if (tma) {
-            static const cudaError_t attr = cudaFuncSetAttribute(k_hessian_gather<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HG_SMEM);
-            HOT_CUDA(attr);
+            HOT_FUNC_ATTR_ONCE(s, k_hessian_gather<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HG_SMEM);
             k_hessian_gather<true><<<(unsigned)(s->g1 - s->g0), US_THREADS, HG_SMEM, s->stream>>>(s->group_first.p + s->g0,
                 s->tile_dof.p + (size_t)s->g0 * TILE, ps, s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, scale, x, s->f_T.p, 0);
         }

@@ -1078,10 +1078,13 @@ int smooth_cg(Sim* s, int level, double* u, double* r, int iterations)
 template <int THREADS, bool STREAM>
 int launch_gs_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
 {
-    static int per_sm = -1, n_sm = 0;
+    static int per_sm_dev[64], n_sm_dev[64];
+    static bool init_dev[64] = {false};
+    const int dslot = s->device & 63; // occupancy and the cooperative-launch capability are per device
+    if (!init_dev[dslot]) { per_sm_dev[dslot] = -1; n_sm_dev[dslot] = 0; init_dev[dslot] = true; }
+    int &per_sm = per_sm_dev[dslot], &n_sm = n_sm_dev[dslot];
     if (per_sm < 0) {
-        int dev = 0, coop = 0;
-        cudaGetDevice(&dev);
+        int dev = s->device, coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gs_sweep<THREADS, STREAM>, THREADS, 0) != cudaSuccess || !coop) per_sm = 0;
@@ -1365,7 +1368,8 @@ int vcycle(Sim* s, const double* in, double* out, bool timed)
         RC(vec_zero(s, 3L * lv[level + 1]->n, lv[level + 1]->sol.p));
     }
     begin(level, 0);
-    RC(level_smooth(s, level, s->mg_coarse, level == 0 ? out : lv[level]->sol.p, lv[level]->residual.p, top_iters(s, level), 0.0));
+    // top.tolFunc(level) = cneps * cneps (MultigridPreconditioner.h:529,399): optimal Jacobi stops early on it, PCG derives its own
+    RC(level_smooth(s, level, s->mg_coarse, level == 0 ? out : lv[level]->sol.p, lv[level]->residual.p, top_iters(s, level), s->mg_cneps * s->mg_cneps));
     end();
     for (--level; level >= 0; --level) {
         double* sol = level == 0 ? out : lv[level]->sol.p;

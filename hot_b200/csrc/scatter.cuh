@@ -213,15 +213,11 @@ template <class Policy>
 int launch_column_scatter(Sim* s, const typename Policy::Args& a)
 {
     if (s->g1 <= s->g0) return 0;
-    static const cudaError_t attr = cudaFuncSetAttribute(k_column_scatter<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        (int)cs_smem_bytes<Policy>());
-    HOT_CUDA(attr);
+    HOT_FUNC_ATTR_ONCE(s, (k_column_scatter<Policy>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem_bytes<Policy>());
     static int dbg_runs = getenv("HOT_CS_DEBUG") ? atoi(getenv("HOT_CS_DEBUG")) : 0;
     if (dbg_runs > 0) {
         --dbg_runs;
-        static const cudaError_t attr2 = cudaFuncSetAttribute(k_column_scatter<Policy, Policy::MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (int)cs_smem_bytes<Policy>());
-        HOT_CUDA(attr2);
+        HOT_FUNC_ATTR_ONCE(s, (k_column_scatter<Policy, Policy::MINB, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem_bytes<Policy>());
         unsigned long long* d = nullptr;
         unsigned long long h[8] = {0};
         HOT_CUDA(cudaMalloc((void**)&d, sizeof h));
@@ -393,9 +389,7 @@ template <class Policy>
 int launch_plane2_scatter(Sim* s, const typename Policy::Args& a)
 {
     if (s->g1 <= s->g0) return 0;
-    static const cudaError_t attr = cudaFuncSetAttribute(k_plane2_scatter<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        (int)ps_smem_bytes<Policy>());
-    HOT_CUDA(attr);
+    HOT_FUNC_ATTR_ONCE(s, (k_plane2_scatter<Policy>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_smem_bytes<Policy>());
     k_plane2_scatter<Policy><<<(unsigned)(s->g1 - s->g0), PS_THREADS, ps_smem_bytes<Policy>(), s->stream>>>(a,
         s->cell_start.p + s->g0 * (Geo::E + 1), s->group_slot.p + s->g0, s->nbr8.p,
         Policy::DOF ? s->tile_dof.p + (size_t)s->g0 * Geo::TILE : nullptr, pf_distance(s, Policy::PMINB));

@@ -242,6 +242,8 @@ struct Sim {
     // HOTSettings (Projects/multigrid/Configurations.h:18-42)
     int mg_smoother = 5, mg_coarse = 2, mg_Ainv = 1, mg_levels = 3, mg_times = 1, mg_levelscale = 0;
     double mg_topomega = 0.1;
+    double mg_cneps = 0.0; // HOTSettings::cneps of the running solve: tolerance of the coarsest-level smoother
+    double dpdf_norm_max = -1.0; // computeCharacteristicNorm's function-static cache (MultigridSimulation.h:131-133): first solve after hot_set_particles
     // ---- one object over several GPUs (dist.cu): this rank's particles only; pages activated by >= 2 ranks are shared, scatter
     // results are summed over the sharers after every scatter, reductions count a shared node on its lowest-ranked sharer
     int rank = 0, world = 1;
@@ -263,6 +265,7 @@ struct Sim {
     DevBuf<double> scat_tmp;
     DevBuf<double> sv[32]; // solver work vectors (solver.cu)
     bool dv0_valid = false;
+    DevBuf<double> dv0_keep; // the accepted iterate of the last hot_backward_euler_step (hot_get_dv0)
     double vc_ms[10][4]; // per-level [smooth, restrict, prolongate, merge] of the last timed V-cycle
     int last_cg_iters = 0;
     ~Sim();
@@ -275,6 +278,18 @@ int cuda_fail(Sim* s, cudaError_t e, const char* what);
     do {                                                               \
         cudaError_t e__ = (call);                                      \
         if (e__ != cudaSuccess) return cuda_fail(s, e__, #call);       \
+    } while (0)
+
+// cudaFuncSetAttribute applies to the CURRENT device: remember per device what has been set (a process may open handles on
+// several GPUs; the calling thread's current device must be the handle's, hot_create sets it)
+#define HOT_FUNC_ATTR_ONCE(s, func, attr, value)                                    \
+    do {                                                                           \
+        static bool done__[64] = {false};                                          \
+        const int d__ = (s)->device & 63;                                          \
+        if (!done__[d__]) {                                                        \
+            HOT_CUDA(cudaFuncSetAttribute(func, attr, value));                     \
+            done__[d__] = true;                                                    \
+        }                                                                          \
     } while (0)
 
 #define HOT_LAUNCHED(s)                                                \

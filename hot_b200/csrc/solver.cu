@@ -425,6 +425,7 @@ int hot_backward_euler_step(hot_sim* s, const hot_solver_options* opt, hot_solve
     O.dv0 = s->sv[V_DV0].p;
     O.dvnew = s->sv[V_DVNEW].p;
     s->project_pd = opt->project != 0;
+    s->mg_cneps = opt->cneps; // top.tolFunc of the V-cycles of this solve
     rc = backup_strain(s); // startBackwardEuler, MultigridSimulation.h:167-186
     if (rc) return rc;
     // computeCharacteristicNorm :128-165 and the tolerances of :199-211
@@ -433,18 +434,24 @@ int hot_backward_euler_step(hot_sim* s, const hot_solver_options* opt, hot_solve
         HOT_CUDA(s->cn_tol.reserve(s->num_nodes > 0 ? s->num_nodes : 1));
         rc = eval_cn_tolerance(s, opt->cneps, s->dt, s->cn_tol.p);
         if (rc) return rc;
-        unsigned long long* mx = (unsigned long long*)(s->red_out.p + 32);
-        HOT_CUDA(cudaMemsetAsync(mx, 0, sizeof(*mx), s->stream));
-        if (s->p1 > s->p0) {
-            k_max_dpdf_norm<<<nblk(s->p1 - s->p0), TPB, 0, s->stream>>>(s->p1 - s->p0, s->P.mu.p + s->p0, s->P.lam.p + s->p0, s->project_pd ? 1 : 0, mx);
-            HOT_LAUNCHED(s);
+        // dPdFNorm_max is a function-static in the reference (computed on the first step, reused afterwards even when hardening
+        // changes mu / lambda): the cache lives until the next hot_set_particles
+        if (s->dpdf_norm_max < 0.0) {
+            unsigned long long* mx = (unsigned long long*)(s->red_out.p + 32);
+            HOT_CUDA(cudaMemsetAsync(mx, 0, sizeof(*mx), s->stream));
+            if (s->p1 > s->p0) {
+                k_max_dpdf_norm<<<nblk(s->p1 - s->p0), TPB, 0, s->stream>>>(s->p1 - s->p0, s->P.mu.p + s->p0, s->P.lam.p + s->p0, s->project_pd ? 1 : 0, mx);
+                HOT_LAUNCHED(s);
+            }
+            if (!s->h_red) HOT_CUDA(cudaMallocHost((void**)&s->h_red, 64 * sizeof(double)));
+            HOT_CUDA(cudaMemcpyAsync(s->h_red, mx, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+            HOT_CUDA(cudaStreamSynchronize(s->stream));
+            double nm = s->h_red[0];
+            rc = dist_allreduce_host(s, &nm, 1, 1);
+            if (rc) return rc;
+            s->dpdf_norm_max = nm;
         }
-        if (!s->h_red) HOT_CUDA(cudaMallocHost((void**)&s->h_red, 64 * sizeof(double)));
-        HOT_CUDA(cudaMemcpyAsync(s->h_red, mx, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-        HOT_CUDA(cudaStreamSynchronize(s->stream));
-        double nmax = s->h_red[0];
-        rc = dist_allreduce_host(s, &nmax, 1, 1);
-        if (rc) return rc;
+        const double nmax = s->dpdf_norm_max;
         tol = opt->cneps * s->dt * 24 * std::sqrt((double)(s->world > 1 ? s->global_nodes : s->num_nodes)) * s->dx * s->dx * nmax;
     }
     if (log) log->tolerance = tol;
@@ -456,7 +463,8 @@ int hot_backward_euler_step(hot_sim* s, const hot_solver_options* opt, hot_solve
     rc = opt->lsolver != 3 ? newton_solve(O, cg_tol) : lbfgs_solve(O);
     if (rc) return rc;
     // keep ImplicitSolverObjective::dv0 readable (hot_get_dv0)
-    rc = vec_copy(s, O.m, opt->linesearch ? O.dv0 : s->dv.p, s->sv[V_STEP].p);
+    HOT_CUDA(s->dv0_keep.reserve(O.m > 0 ? O.m : 1));
+    rc = vec_copy(s, O.m, opt->linesearch ? O.dv0 : s->dv.p, s->dv0_keep.p);
     if (rc) return rc;
     s->dv0_valid = true;
     rc = restore_strain(s);
@@ -468,7 +476,7 @@ int hot_backward_euler_step(hot_sim* s, const hot_solver_options* opt, hot_solve
 int hot_get_dv0(hot_sim* s, double* dv0)
 {
     if (!s->dv0_valid) return fail(s, "hot_get_dv0: no solve yet");
-    HOT_CUDA(cudaMemcpyAsync(dv0, s->sv[V_STEP].p, 3 * (size_t)s->num_nodes * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    HOT_CUDA(cudaMemcpyAsync(dv0, s->dv0_keep.p, 3 * (size_t)s->num_nodes * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     HOT_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }

@@ -57,6 +57,7 @@ struct Sim {
     uint64_t lin27[27];
 
     int num_nodes = 0;
+    double dpdf_norm_max = -1; // computeCharacteristicNorm's function-static cache (MultigridSimulation.h:131-133), per particle set here
     std::vector<double> dv, vn, mass_matrix;
     void* force_state = nullptr; // oracle_force.inl
     void* matrix_state = nullptr; // oracle_matrix.inl
@@ -207,6 +208,7 @@ int orc_set_particles(void* h, long n, const double* X, const double* V, const d
     s->lambda.assign(lambda, lambda + n);
     s->gradV.assign(9 * n, 0.0);
     s->Jp.assign(n, 1.0);
+    s->dpdf_norm_max = -1;
     return 0;
 }
 int orc_get_particles(void* h, double* X, double* V, double* C, double* F, double* gradV)

@@ -176,6 +176,7 @@ struct MatrixState {
     // HOTSettings (Configurations.h:18-42)
     int smoother = 5, coarseSolver = 2, Ainv = 1, levelCnt = 3, times = 1, levelscale = 0;
     double topomega = 0.1;
+    double cneps = 0.0; // HOTSettings::cneps of the running solve (0 outside a solve): top.tolFunc = cneps^2
     bool bcproject = true;
     // MultigridOperator state (MultigridPreconditioner.h:53-77)
     std::vector<int> dofs;
@@ -384,7 +385,7 @@ int mg_vcycle(Sim* s, MatrixState& M, const double* in, double* out)
     else M.initialResiduals[0] = M.residuals[0];
     for (int l = 1; l < L - 1; ++l) sq_multiply(M.resmats[l], M.initialResiduals[l].data(), M.initialResiduals[l + 1].data());
     int level, rc = 0;
-    const double top_tol = 0.0;
+    const double top_tol = M.cneps * M.cneps; // top.tolFunc (MultigridPreconditioner.h:529): optimal Jacobi stops early on it
     for (level = 0; level < L - 1; ++level) {
         Vd& sol = level == 0 ? outv : M.sols[level];
         double t0 = now();

@@ -335,6 +335,7 @@ int orc_backward_euler_step(void* h, const hot_solver_options* opt, hot_solve_lo
     if (opt->lsolver != 2 && opt->lsolver != 3) return fail(s, "lsolver must be 2 (Newton + PCG) or 3 (L-BFGS)");
     if (opt->lsolver == 3 && opt->matfree) return fail(s, "LBFGS only works with project & with-matrix (Projects/multigrid/README:13-15)");
     f.project = opt->project != 0;
+    matrix_of(s).cneps = opt->cneps;
     orc_backup_strain(s); // startBackwardEuler :167-186
     // computeCharacteristicNorm :128-165
     double tol = opt->cneps;
@@ -342,16 +343,21 @@ int orc_backward_euler_step(void* h, const hot_solver_options* opt, hot_solve_lo
         O.nodeCNTol.assign(s->num_nodes, 0.0);
         int rc = orc_eval_cn_tolerance(s, opt->cneps, s->dt, O.nodeCNTol.data());
         if (rc) return rc;
-        double nmax = -1;
-        const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-        for (long i = 0; i < s->N; ++i) {
-            Scratch sc;
-            double Hd[81], nrm = 0;
-            update_scratch(I, s->mu[i], s->lambda[i], f.project, sc);
-            first_piola_derivative(sc, Hd);
-            for (int q = 0; q < 81; ++q) nrm += Hd[q] * Hd[q];
-            nmax = std::max(nmax, std::sqrt(nrm));
+        // `static bool first` / `static double dPdFNorm_max` (:131-133): evaluated on the first step only, reused afterwards
+        if (s->dpdf_norm_max < 0) {
+            double nmax = -1;
+            const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            for (long i = 0; i < s->N; ++i) {
+                Scratch sc;
+                double Hd[81], nrm = 0;
+                update_scratch(I, s->mu[i], s->lambda[i], f.project, sc);
+                first_piola_derivative(sc, Hd);
+                for (int q = 0; q < 81; ++q) nrm += Hd[q] * Hd[q];
+                nmax = std::max(nmax, std::sqrt(nrm));
+            }
+            s->dpdf_norm_max = nmax;
         }
+        const double nmax = s->dpdf_norm_max;
         tol = opt->cneps * s->dt * 24 * std::sqrt((double)s->num_nodes) * s->dx * s->dx * nmax;
     }
     if (log) log->tolerance = tol;
