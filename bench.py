@@ -530,7 +530,7 @@ def run_ours(args):
         # roofline of the dominant kernel; algorithmic bytes per SURVEY.md 8d (fp64)
         # (rank 0's kernels on rank 0's particles and rank 0's nodes: a per-GPU roofline at every N)
         alg = {"p2g": 128 * n + 32 * n_nodes, "g2p": 288 * n + 24 * n_nodes}
-        per = {k: (kt[k][0] / kt[k][1]) for k in ("p2g", "g2p", "number_nodes") if k in kt}
+        per = {k: (kt[k][0] / kt[k][1]) for k in ("p2g", "g2p", "number_nodes", "transfer") if k in kt}   # transfer = shared-page exchange (N > 1; includes waiting for the neighbours)
         dom = max(("p2g", "g2p"), key=lambda k: per.get(k, 0.0))
         ach = alg[dom] / (per[dom] * 1e-3) / 1e9
         kernel_name = {"p2g": "k_plane2_scatter<P2GPolicy>", "g2p": "k_g2p<true>"}[dom]
@@ -557,8 +557,8 @@ def run_ours(args):
             "config": dict(config_block(desc, args, world), particles_rank0=n, grid_nodes_rank0=n_nodes, pages_rank0=sim.num_pages,
                            parallelism=("single GPU" if world == 1 else
                                         f"{world} GPUs, one process each, particles partitioned (rank 0: {part['particles']} particles, {part['neighbors']} neighbour ranks, "
-                                        f"{part['shared_pages']} shared pages, {part['owned_nodes']} of {part['global_nodes']} nodes counted here); per P2G one grouped "
-                                        f"ncclSend/ncclRecv of {part['exchange_pages'] * 4 * 32 * 8} bytes per direction")),
+                                        f"{part['shared_pages']} shared pages, {part['owned_nodes']} of {part['global_nodes']} nodes counted here); per P2G one shared-page exchange of "
+                                        f"{part['exchange_pages'] * 4 * 32 * 8} bytes per direction, transport: {sim.get_transport()}")),
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "serial_ms_per_step": e2e_serial_ms,

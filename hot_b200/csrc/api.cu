@@ -560,6 +560,12 @@ int hot_get_partition(hot_sim* s, long* out8)
     out8[7] = s->N;
     return 0;
 }
+int hot_get_transport(hot_sim* s)
+{
+    if (s->world <= 1) return 0;
+    if (s->xp_state == 1) return 3;
+    return s->nccl_comm ? 1 : (s->has_transport ? 2 : 0);
+}
 // the host logic of the shared-page tables on host arrays (no device, no handle): what dist_after_sort runs after its all-gather.
 // Output arrays are caller-allocated for the worst case: nbr_* world entries, x_slot (world - 1) * counts[rank], sh_slot / sh_owned
 // counts[rank], sh_ptr counts[rank] + 1, sh_entry world * counts[rank].

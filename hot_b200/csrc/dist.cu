@@ -21,6 +21,7 @@
 #include "reduce.cuh"
 #include <algorithm>
 #include <cub/cub.cuh>
+#include <cstring>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -95,8 +96,25 @@ int comm_init_nccl(Sim* s, int rank, int world, const void* id128)
     s->p2g_done = false;
     return 0;
 }
+static void xp_release(Sim* s)
+{
+    for (void*& m : s->xp_peer) {
+        if (m) cudaIpcCloseMemHandle(m);
+        m = nullptr;
+    }
+    if (s->xp_mem) cudaFree(s->xp_mem);
+    s->xp_mem = nullptr;
+    s->xp_cap = 0;
+    s->xp_state = 0;
+    s->xp_seq = 0;
+}
 void comm_destroy(Sim* s)
 {
+    if (s->xp_mem || !s->xp_peer.empty()) {
+        cudaStreamSynchronize(s->stream);
+        xp_release(s);
+        s->xp_peer.clear();
+    }
     if (s->nccl_comm && g_nccl.lib) g_nccl.CommDestroy((ncclComm_t)s->nccl_comm);
     s->nccl_comm = nullptr;
 }
@@ -167,10 +185,69 @@ __global__ void k_pack_shared(long n_x, PageSource src, const int* __restrict__ 
     const long k = t / ((long)Geo::E * src.comps);
     buf[t] = src.load(x_slot[k], c, e);
 }
+
+// ---- peer-memory transport (NVLink P2P) ---------------------------------------------------------------------------------------
+// Arena of a rank: XP_FLAGS u64 flags (flag[r] = number of the last exchange whose data from rank r has landed), then two data
+// areas of xp_cap doubles (exchange n uses area n & 1: a sender can only be one exchange ahead of a receiver, because its pack of
+// exchange n+2 comes after its unpack of n+1, which waited for the receiver's pack of n+1, which came after the receiver's unpack of n).
+constexpr int XP_MAX_NBR = 16;
+constexpr size_t XP_FLAGS = 64; // u64 words, >= world
+struct XpPeers {
+    int n;
+    int rank[XP_MAX_NBR]; // neighbour ranks
+    long off[XP_MAX_NBR], cnt[XP_MAX_NBR]; // their segments of this rank's exchange list, in pages
+    long peer_off[XP_MAX_NBR]; // where this rank's segment starts over there, in pages
+    double* peer_data[XP_MAX_NBR]; // the neighbour's data area of this exchange
+    unsigned long long* peer_flag[XP_MAX_NBR]; // this rank's flag over there
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// pack + send: every value goes straight into the sharer's arena; the last CTA to finish raises this rank's flag at every neighbour
+__global__ void k_pack_peer(long n_x, PageSource src, const int* __restrict__ x_slot, XpPeers pr, unsigned long long seq, unsigned int* done)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_x * src.comps * Geo::E) {
+        const int e = (int)(t % Geo::E), c = (int)((t / Geo::E) % src.comps);
+        const long k = t / ((long)Geo::E * src.comps);
+        int j = 0;
+        while (j + 1 < pr.n && k >= pr.off[j + 1]) ++j;
+        const long at = ((pr.peer_off[j] + (k - pr.off[j])) * src.comps + c) * Geo::E + e;
+        pr.peer_data[j][at] = src.load(x_slot[k], c, e);
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        if (threadIdx.x < pr.n) st_release_sys(pr.peer_flag[threadIdx.x], seq);
+        if (threadIdx.x == 0) *done = 0;
+    }
+}
+struct XpWait {
+    int n;
+    int rank[XP_MAX_NBR];
+    const unsigned long long* flags; // this rank's own flags; nullptr: nothing to wait for (NCCL / callback transport)
+    unsigned long long seq;
+};
 // every sharer adds the partial sums in ascending rank order (entry -1 = this rank's own partial): identical totals everywhere
 __global__ void k_unpack_shared(int n_sh, int comps, const int* __restrict__ sh_slot, const int* __restrict__ sh_ptr, const int* __restrict__ sh_entry,
-    const double* __restrict__ recv, double* __restrict__ g_m, double* __restrict__ g_v, size_t gs, const int* __restrict__ g_idx, double* __restrict__ v)
+    const double* recv, double* __restrict__ g_m, double* __restrict__ g_v, size_t gs, const int* __restrict__ g_idx, double* __restrict__ v, XpWait w)
 {
+    if (w.flags) { // peer-memory transport: the neighbours' partial sums of this exchange have landed when their flags say so
+        if (threadIdx.x < w.n)
+            while (ld_acquire_sys(w.flags + w.rank[threadIdx.x]) < w.seq) __nanosleep(64);
+        __syncthreads();
+    }
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long)n_sh * comps * Geo::E) return;
     const int e = (int)(t % Geo::E), c = (int)((t / Geo::E) % comps), p = (int)(t / ((long)Geo::E * comps));
@@ -187,7 +264,7 @@ __global__ void k_unpack_shared(int n_sh, int comps, const int* __restrict__ sh_
     bool first = true;
     for (int q = sh_ptr[p]; q < sh_ptr[p + 1]; ++q) {
         const int en = sh_entry[q];
-        const double x = en < 0 ? mine : recv[((size_t)en * comps + c) * Geo::E + e];
+        const double x = en < 0 ? mine : __ldcg(recv + ((size_t)en * comps + c) * Geo::E + e);
         sum = first ? x : sum + x;
         first = false;
     }
@@ -209,26 +286,177 @@ struct CountOwnF {
     __device__ void operator()(long i, double (&acc)[1]) const { acc[0] += own[i] ? 1.0 : 0.0; }
 };
 
+// ---- peer transport set-up (host; collective over the ranks, called from dist_after_sort and when an exchange needs more room) ----
+// all-gather of `bytes` host bytes per rank through the active transport
+int host_all_gather(Sim* s, const void* mine, void* all, long bytes)
+{
+    const int W = s->world;
+    HOT_CUDA(s->x_pids.reserve((size_t)(W + 1) * ((bytes + 3) / 4)));
+    unsigned char* d = (unsigned char*)s->x_pids.p;
+    HOT_CUDA(cudaMemcpyAsync(d + (size_t)W * bytes, mine, bytes, cudaMemcpyHostToDevice, s->stream));
+    int rc = comm_all_gather(s, d + (size_t)W * bytes, d, bytes);
+    if (rc) return rc;
+    HOT_CUDA(cudaMemcpyAsync(all, d, (size_t)W * bytes, cudaMemcpyDeviceToHost, s->stream));
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+// (re)allocate this rank's arena for `doubles` per data area and (re)open every rank's arena; all ranks take the same decisions
+int xp_open(Sim* s, size_t doubles)
+{
+    const int W = s->world;
+    HOT_CUDA(cudaStreamSynchronize(s->stream));
+    for (void*& m : s->xp_peer) { // nobody may keep a mapping of an arena that is about to be freed
+        if (m) cudaIpcCloseMemHandle(m);
+        m = nullptr;
+    }
+    s->xp_peer.assign(W, nullptr);
+    char dummy = 0, dall[64];
+    if (W > 64) return fail(s, "peer transport: at most 64 ranks");
+    int rc = host_all_gather(s, &dummy, dall, 1); // barrier: every rank has closed its mappings
+    if (rc) return rc;
+    if (s->xp_mem) cudaFree(s->xp_mem);
+    s->xp_mem = nullptr;
+    const size_t want = doubles + doubles / 4 + 4096;
+    bool ok = cudaMalloc(&s->xp_mem, XP_FLAGS * sizeof(unsigned long long) + 2 * want * sizeof(double)) == cudaSuccess;
+    cudaIpcMemHandle_t hd;
+    std::memset(&hd, 0, sizeof hd);
+    // (device-wide synchronise: the flags must be zero before any peer can reach them; the handle's stream may be non-blocking)
+    if (ok) ok = cudaMemset(s->xp_mem, 0, XP_FLAGS * sizeof(unsigned long long)) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess
+            && cudaIpcGetMemHandle(&hd, s->xp_mem) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    s->xp_cap = ok ? want : 0;
+    s->xp_seq = 0; // fresh flags everywhere
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    struct Rec { unsigned char handle[64]; long cap; long ok; };
+    Rec me;
+    std::memcpy(me.handle, &hd, 64);
+    me.cap = (long)s->xp_cap;
+    me.ok = ok ? 1 : 0;
+    std::vector<Rec> all(W);
+    rc = host_all_gather(s, &me, all.data(), sizeof(Rec));
+    if (rc) return rc;
+    s->xp_peer_cap.assign(W, 0);
+    long good = 1;
+    for (int r = 0; r < W; ++r) good &= all[r].ok;
+    for (int r = 0; r < W && good; ++r) {
+        s->xp_peer_cap[r] = all[r].cap;
+        if (r == s->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, all[r].handle, 64);
+        if (cudaIpcOpenMemHandle(&s->xp_peer[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            s->xp_peer[r] = nullptr;
+            good = 0;
+        }
+    }
+    // usable only when it works on every rank
+    char mine_ok = good ? 1 : 0, oks[64];
+    rc = host_all_gather(s, &mine_ok, oks, 1);
+    if (rc) return rc;
+    for (int r = 0; r < W; ++r) good &= oks[r];
+    if (!good) {
+        for (void*& m : s->xp_peer) {
+            if (m) cudaIpcCloseMemHandle(m);
+            m = nullptr;
+        }
+        if (s->xp_mem) cudaFree(s->xp_mem);
+        s->xp_mem = nullptr;
+        s->xp_cap = 0;
+        s->xp_state = -1;
+        return 0;
+    }
+    s->xp_state = 1;
+    return 0;
+}
+// after the share tables of a sort: every rank learns where its segments start in its neighbours' arenas
+int xp_after_sort(Sim* s)
+{
+    if (!s->nccl_comm || s->xp_state < 0) return 0;
+    if (s->xp_state == 0) {
+        const char* e = getenv("HOT_XCHG");
+        if (e && !strcmp(e, "nccl")) {
+            s->xp_state = -1;
+            return 0;
+        }
+    }
+    const int W = s->world;
+    // row r of the table: off_for[src] = first page of src's segment in r's exchange list (-1: not a neighbour); last entry: r's total
+    std::vector<long> mine(W + 1, -1), all((size_t)W * (W + 1));
+    for (size_t j = 0; j < s->nbr_rank.size(); ++j) mine[s->nbr_rank[j]] = s->nbr_off[j];
+    mine[W] = s->x_total;
+    int rc = host_all_gather(s, mine.data(), all.data(), (long)((W + 1) * sizeof(long)));
+    if (rc) return rc;
+    s->xp_gmax_pages = 0;
+    for (int r = 0; r < W; ++r) s->xp_gmax_pages = std::max(s->xp_gmax_pages, all[(size_t)r * (W + 1) + W]);
+    s->xp_peer_off.assign(s->nbr_rank.size(), 0);
+    for (size_t j = 0; j < s->nbr_rank.size(); ++j) s->xp_peer_off[j] = all[(size_t)s->nbr_rank[j] * (W + 1) + s->rank];
+    if (s->xp_state == 0 || s->xp_gmax_pages * 4 * Geo::E > (long)s->xp_cap) { // room for the 4-channel P2G exchange at least
+        rc = xp_open(s, (size_t)std::max(1L, s->xp_gmax_pages) * 4 * Geo::E);
+        if (rc) return rc;
+    }
+    HOT_CUDA(s->xp_done.reserve(4));
+    HOT_CUDA(cudaMemsetAsync(s->xp_done.p, 0, 4 * sizeof(unsigned int), s->stream));
+    return 0;
+}
+
 int exchange_pages(Sim* s, const PageSource& src, double* g_m, double* g_v, double* v)
 {
-    if (s->x_total <= 0) return 0;
+    if (s->world <= 1) return 0;
     cudaStream_t st = s->stream;
-    const long cnt = s->x_total * src.comps * Geo::E;
-    HOT_CUDA(s->x_send.reserve(cnt));
-    HOT_CUDA(s->x_recv.reserve(cnt));
-    k_pack_shared<<<nblk(cnt), TPB, 0, st>>>(s->x_total, src, s->x_slot.p, s->x_send.p);
-    HOT_LAUNCHED(s);
-    std::vector<double*> sp(s->nbr_rank.size()), rp(s->nbr_rank.size());
-    std::vector<long> cn(s->nbr_rank.size());
-    for (size_t j = 0; j < s->nbr_rank.size(); ++j) {
-        sp[j] = s->x_send.p + s->nbr_off[j] * src.comps * Geo::E;
-        rp[j] = s->x_recv.p + s->nbr_off[j] * src.comps * Geo::E;
-        cn[j] = s->nbr_cnt[j] * src.comps * Geo::E;
+    const int n_nbr = (int)s->nbr_rank.size();
+    bool peer = s->xp_state == 1 && n_nbr <= XP_MAX_NBR;
+    if (s->xp_state == 1 && s->xp_gmax_pages * src.comps * Geo::E > (long)s->xp_cap) { // the same on every rank: grow together
+        int rc = xp_open(s, (size_t)s->xp_gmax_pages * src.comps * Geo::E);
+        if (rc) return rc;
+        peer = s->xp_state == 1 && n_nbr <= XP_MAX_NBR;
     }
-    int rc = comm_exchange(s, (int)s->nbr_rank.size(), s->nbr_rank.data(), sp.data(), rp.data(), cn.data());
-    if (rc) return rc;
+    if (s->xp_state == 1) ++s->xp_seq; // counted on every rank, whether or not it has neighbours
+    if (s->x_total <= 0) return 0;
+    const long cnt = s->x_total * src.comps * Geo::E;
+    XpWait w;
+    w.n = 0;
+    w.flags = nullptr;
+    w.seq = 0;
+    const double* recv = nullptr;
+    if (peer) {
+        XpPeers pr;
+        pr.n = n_nbr;
+        w.n = n_nbr;
+        w.seq = s->xp_seq;
+        w.flags = (const unsigned long long*)s->xp_mem;
+        const size_t area = (s->xp_seq & 1) * s->xp_cap;
+        for (int j = 0; j < n_nbr; ++j) {
+            const int r = s->nbr_rank[j];
+            pr.rank[j] = w.rank[j] = r;
+            pr.off[j] = s->nbr_off[j];
+            pr.cnt[j] = s->nbr_cnt[j];
+            pr.peer_off[j] = s->xp_peer_off[j];
+            unsigned long long* base = (unsigned long long*)s->xp_peer[r];
+            pr.peer_flag[j] = base + s->rank;
+            pr.peer_data[j] = (double*)(base + XP_FLAGS) + (s->xp_seq & 1) * (size_t)s->xp_peer_cap[r];
+        }
+        k_pack_peer<<<nblk(cnt), TPB, 0, st>>>(s->x_total, src, s->x_slot.p, pr, s->xp_seq, s->xp_done.p);
+        HOT_LAUNCHED(s);
+        recv = (const double*)((unsigned long long*)s->xp_mem + XP_FLAGS) + area;
+    }
+    else {
+        HOT_CUDA(s->x_send.reserve(cnt));
+        HOT_CUDA(s->x_recv.reserve(cnt));
+        k_pack_shared<<<nblk(cnt), TPB, 0, st>>>(s->x_total, src, s->x_slot.p, s->x_send.p);
+        HOT_LAUNCHED(s);
+        std::vector<double*> sp(n_nbr), rp(n_nbr);
+        std::vector<long> cn(n_nbr);
+        for (int j = 0; j < n_nbr; ++j) {
+            sp[j] = s->x_send.p + s->nbr_off[j] * src.comps * Geo::E;
+            rp[j] = s->x_recv.p + s->nbr_off[j] * src.comps * Geo::E;
+            cn[j] = s->nbr_cnt[j] * src.comps * Geo::E;
+        }
+        int rc = comm_exchange(s, n_nbr, s->nbr_rank.data(), sp.data(), rp.data(), cn.data());
+        if (rc) return rc;
+        recv = s->x_recv.p;
+    }
     const long un = (long)s->n_sh * src.comps * Geo::E;
-    k_unpack_shared<<<nblk(un), TPB, 0, st>>>(s->n_sh, src.comps, s->sh_slot.p, s->sh_ptr.p, s->sh_entry.p, s->x_recv.p, g_m, g_v, src.gs, src.g_idx, v);
+    k_unpack_shared<<<nblk(un), TPB, 0, st>>>(s->n_sh, src.comps, s->sh_slot.p, s->sh_ptr.p, s->sh_entry.p, recv, g_m, g_v, src.gs, src.g_idx, v, w);
     HOT_LAUNCHED(s);
     return 0;
 }
@@ -334,7 +562,7 @@ int dist_after_sort(Sim* s)
     HOT_CUDA(up(s->sh_entry, sh_entry));
     HOT_CUDA(up(s->sh_owned, sh_owned));
     HOT_CUDA(cudaStreamSynchronize(st)); // the host vectors go out of scope
-    return 0;
+    return xp_after_sort(s);
 }
 
 // P2G of a partitioned object: complete mass / momentum on the shared pages (all sharers end with identical values)

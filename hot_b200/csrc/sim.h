@@ -262,6 +262,20 @@ struct Sim {
     DevBuf<uint32_t> x_pids;
     DevBuf<double> x_send, x_recv, x_scalars;
     DevBuf<unsigned char> own_node; // 1: this rank counts the node in dots / norms
+    // peer-memory transport of the shared-page exchange (dist.cu, NVLink P2P through cudaIpc; needs the NCCL communicator only for
+    // the set-up): every rank owns a receive arena [flags: one u64 per source rank | parity 0 | parity 1]; the pack kernel of a
+    // sharer stores its partial sums straight into the neighbours' arenas and raises its flag there, the unpack kernel waits on
+    // the flags of this rank's neighbours - no collective kernel, no host work between the two launches
+    int xp_state = 0; // 0 untried, 1 in use, -1 unavailable (no P2P between the ranks' devices, or HOT_XCHG=nccl)
+    void* xp_mem = nullptr; // own arena (cudaMalloc, exported with cudaIpcGetMemHandle)
+    size_t xp_cap = 0; // doubles per parity
+    std::vector<void*> xp_peer; // peers' arenas as mapped here, by rank (nullptr: not a neighbour yet / self)
+    std::vector<unsigned char> xp_handles; // world x 64 bytes: the handle every xp_peer entry was opened from
+    std::vector<long> xp_peer_cap; // peers' capacities
+    std::vector<long> xp_peer_off; // per neighbour j: where this rank's segment starts in that neighbour's arena, in pages
+    long xp_gmax_pages = 0; // largest exchange list over the ranks (sizes every arena alike)
+    unsigned long long xp_seq = 0; // exchanges done; the same on every rank (exchanges are collective)
+    DevBuf<unsigned int> xp_done; // CTA counter of the pack kernel
     DevBuf<double> scat_tmp;
     DevBuf<double> sv[32]; // solver work vectors (solver.cu)
     bool dv0_valid = false;

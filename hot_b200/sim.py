@@ -489,6 +489,9 @@ class MpmSimulationB200:
         self._check(self._lib.hot_get_partition(self._h, out))
         return dict(zip(("rank", "world", "neighbors", "shared_pages", "exchange_pages", "owned_nodes", "global_nodes", "particles"), [int(v) for v in out]))
 
+    def get_transport(self):
+        return {0: "single rank", 1: "grouped ncclSend/ncclRecv", 2: "caller callbacks", 3: "peer memory (NVLink P2P stores + flags)"}[int(self._lib.hot_get_transport(self._h))]
+
     # ---- plasticity (PlasticityApplier.cpp): applied by gridToParticles after evolveStrain
     def set_plasticity(self, model, params=()):
         m = {"none": 0, "von_mises": 1, "snow": 2}.get(model, model)

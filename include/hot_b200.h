@@ -145,6 +145,11 @@ int hot_set_partition(hot_sim* h, int rank, int world, const hot_transport* tran
 /* {rank, world, neighbour ranks, shared local pages, pages exchanged per scatter (sum over neighbours), nodes this rank counts
  * in reductions, nodes of the whole object (the last two -1 before hot_p2g), local particles} */
 int hot_get_partition(hot_sim* h, long* out8);
+/* how the shared pages travel after the last hot_sort_and_activate: 0 single rank, 1 grouped ncclSend / ncclRecv, 2 the caller's
+ * callbacks, 3 peer memory (with hot_comm_init_nccl, when every rank can map every other rank's receive arena through cudaIpc:
+ * the pack kernel stores the partial sums straight into the neighbours' HBM over NVLink and raises a flag there, the unpack kernel
+ * waits on the flags - no collective kernel and no host work in between; HOT_XCHG=nccl keeps transport 1) */
+int hot_get_transport(hot_sim* h);
 /* The host logic behind the shared-page tables, callable without a device (CPU tests of the N > 1 path): from every rank's
  * ascending page-id list (all_pids: world rows of max_pages, counts[r] valid) builds this rank's neighbour list, exchange list
  * (x_slot: local slots, per neighbour in ascending page id) and, per shared local page, the contributions in ascending rank order

@@ -95,6 +95,27 @@ def gpu_worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+def nccl_worker(rank, world, port, out_dir):
+    """one rank per physical GPU, NCCL communicator inside the library (hot_comm_init_nccl); HOT_XCHG selects the transport of the
+    shared-page exchange (peer memory by default, `nccl` = grouped ncclSend / ncclRecv)"""
+    import torch
+    import torch.distributed as dist
+    import hot_b200
+    from hot_b200.dist import nccl_partition, split_slabs
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    sc = scene()
+    sel = split_slabs(sc["X"], world)[rank]
+    sim = hot_b200.MpmSimulationB200(sc["dx"], device=rank)
+    nccl_partition(sim, torch.device("cuda", rank))
+    ymin = int(np.floor(sc["X"][:, 1].min() / sc["dx"] - 0.5))
+    res = run_object(sim, sc, sel, ymin)
+    res["sel"] = sel
+    res["transport"] = np.array(sim.get_transport())
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)
+    dist.destroy_process_group()
+
+
 def cpu_worker(rank, world, port, out_dir):
     """the N > 1 host logic without a GPU: the library's shared-page tables (hot_share_tables, the code dist_after_sort runs) on page
     sets that overlap between ranks, then pack -> neighbour exchange -> unpack in ascending rank order emulated in numpy over gloo
@@ -177,4 +198,4 @@ def cpu_worker(rank, world, port, out_dir):
 
 if __name__ == "__main__":
     kind, rank, world, port, out_dir = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
-    (gpu_worker if kind == "gpu" else cpu_worker)(rank, world, port, out_dir)
+    {"gpu": gpu_worker, "nccl": nccl_worker, "cpu": cpu_worker}[kind](rank, world, port, out_dir)

@@ -19,9 +19,10 @@ def free_port():
     return p
 
 
-def launch(kind, world, out_dir, timeout=300):
+def launch(kind, world, out_dir, timeout=300, env=None):
     port = free_port()
-    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dist_worker.py"), kind, str(r), str(world), str(port), str(out_dir)])
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dist_worker.py"), kind, str(r), str(world), str(port), str(out_dir)],
+                              env=dict(os.environ, **(env or {})))
              for r in range(world)]
     for p in procs:
         assert p.wait(timeout=timeout) == 0

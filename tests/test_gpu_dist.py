@@ -61,3 +61,37 @@ def test_partitioned_object_matches_single_gpu(single, tmp_path, world):
         for k in ("X", "V", "F", "C"):                                             # after TWO steps
             _close(r["P_" + k], single["P_" + k][r["sel"]], 1e-7)
     assert (seen >= 1).all() and (seen > 1).any()                                  # all nodes covered, some shared
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="one rank per physical GPU: needs >= 2 GPUs (gpurun --gpus 2)")
+def test_peer_memory_transport_equals_nccl_transport(single, tmp_path):
+    """the shared-page exchange through peer memory (P2P stores into the neighbours' arenas + flags) and through grouped
+    ncclSend / ncclRecv add the same partial sums in the same order; the scatters themselves add page-group sums with RED atomics,
+    so two runs agree to rounding, not bitwise: 1e-13 between the transports, the usual tolerances against the single-GPU object"""
+    world = min(_n_gpus(), 4)
+    (tmp_path / "peer").mkdir(); (tmp_path / "nccl").mkdir()
+    peer = launch("nccl", world, tmp_path / "peer", timeout=900)
+    nccl = launch("nccl", world, tmp_path / "nccl", timeout=900, env={"HOT_XCHG": "nccl"})
+    order = np.argsort(_key(single["coord"])); skey = _key(single["coord"])[order]
+    for a, b in zip(peer, nccl):
+        assert "peer memory" in str(a["transport"]) and "ncclSend" in str(b["transport"])
+        for k in ("grid_m", "grid_v", "residual", "multiply", "cn_tol", "diag"):
+            _close(a[k], b[k], 1e-13)
+        for k in ("dv0", "P_X", "P_V", "P_F", "P_C"):
+            _close(a[k], b[k], 1e-9)
+        assert (a["log_iters"] == b["log_iters"]).all()
+        assert (a["log_iters"] == single["log_iters"]).all()
+        at = order[np.searchsorted(skey, _key(a["coord"]))]
+        _close(a["grid_m"], single["grid_m"][at], 1e-13); _close(a["grid_v"], single["grid_v"][at])
+        for k in ("residual", "multiply", "cn_tol", "diag"):
+            _close(a[k], single[k][at])
+        for k in ("X", "V", "F", "C"):
+            _close(a["P_" + k], single["P_" + k][a["sel"]], 1e-7)
