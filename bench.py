@@ -420,19 +420,24 @@ def run_ours(args):
         flush.zero_()
         sim.particlesToGrid(); sim.gridToParticles(0.0, want_flags=False)
     sampler = ClockSampler(local); sampler.start()
+    sampler.sample_now(); sampler.samples.clear()   # NVML initialised before the timed loop (the first call costs milliseconds)
     sim.timing(2)
     l0 = sim.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     sampler.active = True
     wall0 = time.perf_counter()
+    step_barrier = world > 1 and os.environ.get("HOT_BENCH_STEP_BARRIER") == "1"   # diagnosis: no skew between the ranks at the start of a step
     for k, (a, b) in enumerate(ev):
         flush.zero_()
+        if step_barrier:
+            barrier()
         a.record(stream)
         sim.particlesToGrid(); sim.gridToParticles(0.0, want_flags=False)
         b.record(stream)
-        if k % 8 == 4:
-            sampler.sample_now()               # between two event pairs, GPU mid-loop
+        if k % 8 == 4 and world == 1:
+            sampler.sample_now()               # between two event pairs, GPU mid-loop (N > 1: the sampler thread alone - a rank that stops
+                                               # to query NVML makes its neighbours wait inside THEIR timed step at the page exchange)
     barrier()
     wall = time.perf_counter() - wall0
     sampler.active = False
@@ -441,6 +446,8 @@ def run_ours(args):
     total_ms = float(np.sum(step_ms))
     kt = sim.get_timings()
     sim.timing(0)
+    if world > 1 and os.environ.get("HOT_BENCH_VERBOSE") == "1":
+        print(f"[rank {rank}] steps ms {[round(x, 3) for x in step_ms]} classes {({k: round(v[0] / v[1], 4) for k, v in kt.items()})} wall {wall:.4f}", file=sys.stderr, flush=True)
 
     # ---- end-to-end leg: host buffers through the public API ------------------------------------------
     # Every step: H2D of that step's particle state (X, V, C, F from pinned host memory), sort, P2G, G2P(dt), D2H of the new
