@@ -78,6 +78,15 @@ __global__ void __launch_bounds__(AS_THREADS) k_assemble(const int* __restrict__
     // work item: node a of the cell's 27-stencil, x-plane bp of the partner nodes b
     const int a = tid / 3, bp = tid - 3 * a; // a < 27 for tid < 81
     const int ai = a / 9, aj = (a / 3) % 3, ak = a % 3;
+    // Only the blocks of the upper triangle (offset a - b lexicographically >= 0, slot >= 62) are computed and added; k_mirror fills the
+    // rest with the transposes (the reference, too, visits each node pair once and writes both blocks, ImplicitSolver.h:516-547):
+    // half the REDs and half the block products.  bmask: which of the thread's 9 partner nodes (bj, bk) are on the upper side.
+    unsigned bmask = 0;
+    if (tid < 81)
+        for (int b = 0; b < 9; ++b) {
+            const int slot = (ai - bp + 2) * 25 + (aj - b / 3 + 2) * 5 + (ak - b % 3 + 2);
+            if (slot >= 62) bmask |= 1u << b;
+        }
     for (int c = 0; c < E; ++c) {
         const int cb = s_cs[c], ce = s_cs[c + 1];
         if (ce == cb) continue; // uniform over the CTA
@@ -107,7 +116,7 @@ __global__ void __launch_bounds__(AS_THREADS) k_assemble(const int* __restrict__
                 rec[p][81 + e] = H[(size_t)e * ps + p0 + p];
             }
             __syncthreads();
-            if (tid < 81) {
+            if (bmask) {
                 for (int p = 0; p < pn; ++p) {
                     const double* r = rec[p];
                     const double* Hh = r + 81;
@@ -121,6 +130,7 @@ __global__ void __launch_bounds__(AS_THREADS) k_assemble(const int* __restrict__
                             U[rr + 3 * cc] = Hh[tri(rr, cc)] * ga[0] + Hh[tri(rr + 3, cc)] * ga[1] + Hh[tri(rr + 6, cc)] * ga[2];
 #pragma unroll
                     for (int b = 0; b < 9; ++b) {
+                        if (!(bmask >> b & 1)) continue;
                         const double* gb = r + 3 * (bp * 9 + b);
                         const double g0 = gb[0], g1 = gb[1], g2 = gb[2];
 #pragma unroll
@@ -143,12 +153,354 @@ __global__ void __launch_bounds__(AS_THREADS) k_assemble(const int* __restrict__
                     if (idb < 0) continue;
                     const int slot = (ai - bp + 2) * 25 + (aj - bj + 2) * 5 + (ak - bk + 2);
                     col[(size_t)ida * W + slot] = idb;
+                    if (!(bmask >> b & 1)) continue;
 #pragma unroll
                     for (int q = 0; q < 9; ++q) atomicAdd(val + ((size_t)ida * 9 + q) * W + slot, dt2 * acc[b][q]);
                 }
             }
         }
     }
+}
+
+
+// ---- assembly, default form: upper triangle, balanced threads, double-buffered staging ------------------------------------------
+// Same arithmetic as k_assemble (per cell: U_a = H~ . grad w_a once per thread and particle, 27 FMA per node pair, per-cell sums in
+// registers, REDs per cell), but
+//  * only the 405 blocks per cell with offset a - b >= 0 (slot >= 62) are computed; k_mirror writes the transposes.  Threads own
+//    (a, x-plane bp) with ai >= bp only: 54 busy threads instead of 81 of which a third would idle;
+//  * the records of the NEXT chunk of particles (H~ rows by 8-byte cp.async, weight gradients computed by the staging threads) land
+//    in the second buffer while the current chunk is contracted: one barrier per chunk, no exposed DRAM round trip;
+//  * 64-thread CTAs: 4 per SM at 252 registers.
+constexpr int AU_THREADS = 64;
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(smem)), "l"(gmem) : "memory");
+}
+__global__ void __launch_bounds__(AU_THREADS) k_assemble_upper(const int* __restrict__ cell_start, const int* __restrict__ group_slot,
+    const int* __restrict__ nbr8, size_t ps, const double* __restrict__ X, const double* __restrict__ H, double dx, double one_over_dx,
+    double dt2, const int* __restrict__ g_idx, int* __restrict__ col, double* __restrict__ val)
+{
+    __shared__ __align__(16) double rec[2][AS_CHUNK][AS_REC];
+    __shared__ int s_cs[E + 1];
+    __shared__ int s_nbr[8];
+    __shared__ int s_id[TILE];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (tid <= E) s_cs[tid] = cell_start[(size_t)g * (E + 1) + tid];
+    if (tid < 8) s_nbr[tid] = nbr8[(size_t)group_slot[g] * 8 + tid];
+    __syncthreads();
+    for (int n = tid; n < TILE; n += AU_THREADS) {
+        long a = tile_to_grid(n, s_nbr);
+        s_id[n] = a >= 0 ? g_idx[a] : -1;
+    }
+    // work item: node a = (ai, aj, ak) of the cell's stencil x x-plane bp <= ai of the partner nodes
+    const bool worker = tid < 54;
+    const int u = worker ? tid / 9 : 0, rj = tid % 9;
+    const int ai = u == 0 ? 1 : (u == 1 || u == 2 ? 2 : u - 3), bp = u == 0 || u == 1 ? 0 : (u == 2 ? 1 : u - 3);
+    const int aj = rj / 3, ak = rj % 3, a = ai * 9 + aj * 3 + ak;
+    unsigned bmask = 0;
+    if (worker)
+        for (int b = 0; b < 9; ++b) {
+            const int slot = (ai - bp + 2) * 25 + (aj - b / 3 + 2) * 5 + (ak - b % 3 + 2);
+            if (slot >= 62) bmask |= 1u << b;
+        }
+    auto stage = [&](int buf, int p0, int pn) {
+        for (int it = tid; it < pn * 45; it += AU_THREADS) {
+            const int p = it / 45, e = it - 45 * p;
+            cp_async8(&rec[buf][p][81 + e], H + (size_t)e * ps + p0 + p);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int it = tid; it < pn * 27; it += AU_THREADS) {
+            const int p = it / 27, nd = it - 27 * p;
+            const int ijk[3] = {nd / 9, (nd / 3) % 3, nd % 3};
+            double w[3], dws[3]; // weight and weight derivative / dx of this node per axis (few live registers next to acc / U)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                double xi, wa[3], dwa[3];
+                const int bn = base_node_of(X[d * ps + p0 + p], one_over_dx, &xi);
+                bspline_axis(xi - (double)bn, wa, dwa);
+                const int t = ijk[d];
+                w[d] = t == 0 ? wa[0] : (t == 1 ? wa[1] : wa[2]);
+                dws[d] = t == 0 ? dwa[0] : (t == 1 ? dwa[1] : dwa[2]);
+            }
+            rec[buf][p][3 * nd] = ((one_over_dx * dws[0]) * w[1]) * w[2];
+            rec[buf][p][3 * nd + 1] = (w[0] * one_over_dx * dws[1]) * w[2];
+            rec[buf][p][3 * nd + 2] = (w[0] * w[1]) * one_over_dx * dws[2];
+        }
+    };
+    int c = 0;
+    while (c < E && s_cs[c + 1] == s_cs[c]) ++c;
+    if (c >= E) return; // (a group has particles; uniform)
+    int p0 = s_cs[c], buf = 0;
+    __syncthreads(); // s_id
+    stage(0, p0, min(AS_CHUNK, s_cs[c + 1] - p0));
+    double acc[9][9];
+#pragma unroll
+    for (int b = 0; b < 9; ++b)
+#pragma unroll
+        for (int q = 0; q < 9; ++q) acc[b][q] = 0.0;
+    while (c < E) {
+        const int ce = s_cs[c + 1], pn = min(AS_CHUNK, ce - p0);
+        int nc = c, np0 = p0 + pn;
+        if (np0 >= ce) {
+            ++nc;
+            while (nc < E && s_cs[nc + 1] == s_cs[nc]) ++nc;
+            np0 = nc < E ? s_cs[nc] : 0;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads(); // this chunk's records visible; everybody is done with the other buffer
+        if (nc < E) stage(buf ^ 1, np0, min(AS_CHUNK, s_cs[nc + 1] - np0));
+        if (bmask) {
+            for (int p = 0; p < pn; ++p) {
+                const double* r = rec[buf][p];
+                const double* Hh = r + 81;
+                const double ga[3] = {r[3 * a], r[3 * a + 1], r[3 * a + 2]};
+                double U[27];
+#pragma unroll
+                for (int cc = 0; cc < 9; ++cc)
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr)
+                        U[rr + 3 * cc] = Hh[tri(rr, cc)] * ga[0] + Hh[tri(rr + 3, cc)] * ga[1] + Hh[tri(rr + 6, cc)] * ga[2];
+#pragma unroll
+                for (int b = 0; b < 9; ++b) {
+                    if (!(bmask >> b & 1)) continue;
+                    const double* gb = r + 3 * (bp * 9 + b);
+                    const double g0 = gb[0], g1 = gb[1], g2 = gb[2];
+#pragma unroll
+                    for (int ss = 0; ss < 3; ++ss)
+#pragma unroll
+                        for (int rr = 0; rr < 3; ++rr)
+                            acc[b][rr + 3 * ss] += U[rr + 3 * ss] * g0 + U[rr + 3 * (ss + 3)] * g1 + U[rr + 3 * (ss + 6)] * g2;
+                }
+            }
+            if (nc != c) { // the cell is complete: its sums go to the matrix
+                const int cz = c & (Geo::BZ - 1), cy = (c >> Geo::zb) & (Geo::BY - 1), cx = c >> (Geo::zb + Geo::yb);
+                const int ida = s_id[((cx + ai) * Geo::TY + (cy + aj)) * Geo::TZ + (cz + ak)];
+#pragma unroll
+                for (int b = 0; b < 9; ++b) {
+                    if (!(bmask >> b & 1)) continue;
+                    const int bj = b / 3, bk = b % 3;
+                    const int idb = s_id[((cx + bp) * Geo::TY + (cy + bj)) * Geo::TZ + (cz + bk)];
+                    if (ida >= 0 && idb >= 0) {
+                        const int slot = (ai - bp + 2) * 25 + (aj - bj + 2) * 5 + (ak - bk + 2);
+                        col[(size_t)ida * W + slot] = idb;
+                        col[(size_t)idb * W + 124 - slot] = ida; // the mirrored entry (k_mirror reads it)
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) atomicAdd(val + ((size_t)ida * 9 + q) * W + slot, dt2 * acc[b][q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) acc[b][q] = 0.0;
+                }
+            }
+        }
+        c = nc; p0 = np0; buf ^= 1;
+    }
+}
+
+// ---- row-gather assembly (HOT_ASSEMBLE=rows) -----------------------------------------------------------------------------------------
+// The scatter form above adds every (cell, node pair) block with 9 global REDs: 840 M atomics at C2, 3.8 GB of DRAM writes for a
+// 0.97 GB matrix (ncu, round 1).  Here a WARP owns a block row: it walks the 27 cells whose particles reach its node, lane b < 27
+// evaluates the 3x3 block towards stencil node b of every particle (sum over the particles of a cell in registers), the row is
+// built in shared memory (slot = (a - b) + 2 per axis) and written ONCE, coalesced, together with its column ids - no atomics,
+// DRAM writes = the matrix.  Per visit (particle, a): U = H~ . grad w_a by 27 lanes (3 DFMA each, H~ rows read through L1),
+// broadcast through shared memory, then 27 DFMA per lane.
+constexpr int AR_ROWS = 4; // rows (warps) per CTA
+constexpr int AR_REC = 128; // doubles per particle record: H~ (45, packed upper triangle), grad w of the 27 stencil nodes (81), pad
+struct ArWarp {
+    double tile[9 * W]; // entry q of slot s at tile[q * W + s]
+    double rec[2][AR_REC]; // the particle record of this and the next visit (cp.async)
+    double ubuf[2][28];
+    int col[W];
+    int cfirst[28], cend[28]; // particle range of the 27 cells around the row's node
+};
+__device__ inline int find_slot_m(uint32_t pid, long n_pages, const uint32_t* __restrict__ pid_sorted, const int* __restrict__ slot_sorted)
+{
+    long lo = 0, hi = n_pages;
+    while (lo < hi) {
+        long mid = (lo + hi) >> 1;
+        if (pid_sorted[mid] < pid) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < n_pages && pid_sorted[lo] == pid) ? slot_sorted[lo] : -1;
+}
+// page slot of page + (dx, dy, dz) pages, d in {-1, 0, 1}: nbr27[slot * 27 + (dx + 1) * 9 + (dy + 1) * 3 + dz + 1]
+__global__ void k_nbr27(long n_pages, const uint32_t* __restrict__ page_id, const uint32_t* __restrict__ pid_sorted, const int* __restrict__ slot_sorted,
+    int* __restrict__ nbr27)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pages * 27) return;
+    const long slot = t / 27;
+    const int q = (int)(t - slot * 27);
+    const uint64_t off = (uint64_t)page_id[slot] << 12;
+    const int x = (int)bit_pack(off, Geo::xmask) + Geo::BX * (q / 9 - 1), y = (int)bit_pack(off, Geo::ymask) + Geo::BY * ((q / 3) % 3 - 1),
+              z = (int)bit_pack(off, Geo::zmask) + Geo::BZ * (q % 3 - 1);
+    int r = -1;
+    if (x >= 0 && y >= 0 && z >= 0 && x < 4096 && y < 4096 && z < 4096) r = find_slot_m((uint32_t)(linear_offset(x, y, z) >> 12), n_pages, pid_sorted, slot_sorted);
+    nbr27[t] = r;
+}
+__global__ void k_group_of_slot(long n_groups, const int* __restrict__ group_slot, int* __restrict__ group_of_slot)
+{
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_groups) group_of_slot[group_slot[g]] = (int)g;
+}
+// per particle one 1 KB record: H~ (45 entries, packed upper triangle) and the weight gradients of its 27 stencil nodes (reference
+// association, MpmGrid.h:272-291) - a warp stages it with two 16-byte cp.async per lane
+__global__ void k_assemble_prep(long n, size_t ps, const double* __restrict__ X, const double* __restrict__ H, double dx, double one_over_dx,
+    double* __restrict__ rec)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * AR_REC) return;
+    const long p = t / AR_REC;
+    const int e = (int)(t - p * AR_REC);
+    double v = 0.0;
+    if (e < 45) v = H[(size_t)e * ps + p];
+    else if (e < 126) {
+        const int nd = (e - 45) / 3, c = (e - 45) - 3 * nd;
+        const int ijk[3] = {nd / 9, (nd / 3) % 3, nd % 3};
+        double w[3], dws[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double xi, wa[3], dwa[3];
+            const int bn = base_node_of(X[d * ps + p], one_over_dx, &xi);
+            bspline_axis(xi - (double)bn, wa, dwa);
+            w[d] = wa[ijk[d]];
+            dws[d] = one_over_dx * dwa[ijk[d]];
+        }
+        v = c == 0 ? (dws[0] * w[1]) * w[2] : (c == 1 ? (w[0] * dws[1]) * w[2] : (w[0] * w[1]) * dws[2]);
+    }
+    rec[t] = v;
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem)), "l"(gmem) : "memory");
+}
+__global__ void __launch_bounds__(32 * AR_ROWS) k_assemble_rows(int n_nodes, const int* __restrict__ dof_slot, const int* __restrict__ nbr27,
+    const int* __restrict__ group_of_slot, const int* __restrict__ cell_start, const double* __restrict__ rec,
+    double dt2, const double* __restrict__ mass, const int* __restrict__ g_idx, int* __restrict__ col, double* __restrict__ val)
+{
+    extern __shared__ __align__(16) unsigned char ar_smem[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int id = blockIdx.x * AR_ROWS + w;
+    if (id >= n_nodes) return; // (whole warp)
+    ArWarp& S = reinterpret_cast<ArWarp*>(ar_smem)[w];
+    for (int t = lane; t < 9 * W; t += 32) S.tile[t] = 0.0;
+    for (int t = lane; t < W; t += 32) S.col[t] = id;
+    const int at = dof_slot[id];
+    const int pslot = at / E, e = at - pslot * E;
+    const int ex = e >> (Geo::yb + Geo::zb), ey = (e >> Geo::zb) & (Geo::BY - 1), ez = e & (Geo::BZ - 1);
+    // lane = stencil index: as `a` the cell whose stencil node a is this row's node, as `b` the partner node of a particle's stencil
+    const int ln = lane < 27 ? lane : 26; // lanes 27..31 shadow lane 26 (no divergence in the particle loop; they never flush)
+    const int bi = ln / 9, bj = (ln / 3) % 3, bk = ln % 3;
+    {
+        int cx = ex - bi, cy = ey - bj, cz = ez - bk;
+        const int px = cx < 0 ? -1 : 0, py = cy < 0 ? -1 : 0, pz = cz < 0 ? -1 : 0;
+        cx -= px * Geo::BX; cy -= py * Geo::BY; cz -= pz * Geo::BZ;
+        const int cslot = nbr27[(size_t)pslot * 27 + (px + 1) * 9 + (py + 1) * 3 + pz + 1];
+        const int g = cslot >= 0 ? group_of_slot[cslot] : -1;
+        int first = 0, end = 0;
+        if (g >= 0) {
+            const int ce = (cx * Geo::BY + cy) * Geo::BZ + cz;
+            first = cell_start[(size_t)g * (E + 1) + ce];
+            end = cell_start[(size_t)g * (E + 1) + ce + 1];
+        }
+        if (lane < 27) { S.cfirst[lane] = first; S.cend[lane] = end; }
+    }
+    // the column id of slot (a - b): node at coord - (a - b), looked up per (a, lane b) at flush time through the 27 neighbour pages
+    const int rr = ln % 3, cc = ln / 3;
+    const int t0 = tri(rr, cc), t1 = tri(rr + 3, cc), t2 = tri(rr + 6, cc);
+    __syncwarp();
+    // flat visit list over the non-empty cells; the record of the next visit is always in flight
+    int a = 0;
+    while (a < 27 && S.cend[a] <= S.cfirst[a]) ++a;
+    int p = a < 27 ? S.cfirst[a] : 0;
+    int ub = 0;
+    auto stage = [&](int buf, int pp) {
+        const double* src = rec + (size_t)pp * AR_REC + 4 * lane; // 2 x 16 bytes per lane and half record
+        cp_async16(&S.rec[buf][4 * lane], src);
+        cp_async16(&S.rec[buf][4 * lane + 2], src + 2);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (a < 27) stage(0, p);
+    double acc[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+    while (a < 27) {
+        // next visit
+        int na = a, np = p + 1;
+        if (np >= S.cend[a]) {
+            ++na;
+            while (na < 27 && S.cend[na] <= S.cfirst[na]) ++na;
+            np = na < 27 ? S.cfirst[na] : 0;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (na < 27) stage(ub ^ 1, np);
+        const double* R = S.rec[ub];
+        const double g0 = R[45 + 3 * ln], g1 = R[46 + 3 * ln], g2 = R[47 + 3 * ln];
+        const double ga0 = R[45 + 3 * a], ga1 = R[46 + 3 * a], ga2 = R[47 + 3 * a];
+        S.ubuf[ub][ln] = fma(R[t2], ga2, fma(R[t1], ga1, R[t0] * ga0)); // U(rr, cc) = sum_c H~(rr + 3 c, cc) ga[c]  (lanes >= 27 rewrite entry 26 with the same value)
+        __syncwarp();
+        {
+            const double2* u2 = reinterpret_cast<const double2*>(S.ubuf[ub]);
+            double U[28];
+#pragma unroll
+            for (int t = 0; t < 14; ++t) {
+                const double2 v = u2[t];
+                U[2 * t] = v.x; U[2 * t + 1] = v.y;
+            }
+#pragma unroll
+            for (int ss = 0; ss < 3; ++ss)
+#pragma unroll
+                for (int r3 = 0; r3 < 3; ++r3) acc[r3 + 3 * ss] = fma(U[r3 + 3 * (ss + 6)], g2, fma(U[r3 + 3 * (ss + 3)], g1, fma(U[r3 + 3 * ss], g0, acc[r3 + 3 * ss])));
+        }
+        ub ^= 1;
+        if (na != a) {
+            // cell a done -> into the row: slot (a - b) + 2 per axis; the column id of that slot is the node at coord - (a - b)
+            const int ai = a / 9, aj = (a / 3) % 3, ak = a % 3;
+            if (lane < 27) {
+                const int dx_ = ai - bi, dy_ = aj - bj, dz_ = ak - bk;
+                int nx = ex - dx_, ny = ey - dy_, nz = ez - dz_;
+                const int qx = nx < 0 ? -1 : (nx >= Geo::BX ? 1 : 0), qy = ny < 0 ? -1 : (ny >= Geo::BY ? 1 : 0), qz = nz < 0 ? -1 : (nz >= Geo::BZ ? 1 : 0);
+                nx -= qx * Geo::BX; ny -= qy * Geo::BY; nz -= qz * Geo::BZ;
+                const int nslot = nbr27[(size_t)pslot * 27 + (qx + 1) * 9 + (qy + 1) * 3 + qz + 1];
+                const int idb = nslot >= 0 ? g_idx[(size_t)nslot * E + (nx * Geo::BY + ny) * Geo::BZ + nz] : -1;
+                if (idb >= 0) {
+                    const int slot = (dx_ + 2) * 25 + (dy_ + 2) * 5 + dz_ + 2;
+                    S.col[slot] = idb;
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) S.tile[q * W + slot] += dt2 * acc[q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+            __syncwarp();
+        }
+        a = na; p = np;
+    }
+    // inertia term m_i I on the self slot (ImplicitSolver.h:485-493), then the row goes out once
+    if (lane == 0) {
+        const double m = mass[id];
+        S.tile[0 * W + 62] += m; S.tile[4 * W + 62] += m; S.tile[8 * W + 62] += m;
+    }
+    __syncwarp();
+    for (int t = lane; t < W; t += 32) col[(size_t)id * W + t] = S.col[t];
+    double* vrow = val + (size_t)id * 9 * W;
+    for (int t = lane; t < 9 * W; t += 32) vrow[t] = S.tile[t];
+}
+
+// lower triangle of the assembled matrix: block (j, i) = block (i, j)^T; slot s' < 62 of row j mirrors slot 124 - s' of row col[j][s']
+__global__ void k_mirror(int n, const int* __restrict__ col, double* __restrict__ val)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)n * 62) return;
+    const int j = (int)(t / 62), s = (int)(t - (long)j * 62);
+    const int i = col[(size_t)j * W + s];
+    if (i == j) return; // empty slot (slot 62 is the only one that addresses the node itself)
+    const double* src = val + (size_t)i * 9 * W + (124 - s);
+    double* dst = val + (size_t)j * 9 * W + s;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) dst[(r + 3 * c) * W] = src[(c + 3 * r) * W];
 }
 
 __global__ void k_bc_of(int n_bc, const int* __restrict__ node, int* __restrict__ bc_of)
@@ -318,11 +670,40 @@ int build_matrix(Sim* s, bool bcproject)
     KTime t(s, KC_ASSEMBLE);
     rc = fill_id2coord(s, L.coord.p);
     if (rc) return rc;
-    k_matrix_init<<<nblk((long)nn * W), TPB, 0, st>>>(nn, s->mass_matrix.p, L.col.p, L.val.p);
-    HOT_LAUNCHED(s);
-    k_assemble<<<(unsigned)s->n_groups, AS_THREADS, 0, st>>>(s->cell_start.p, s->group_slot.p, s->nbr8.p, s->P.stride, s->P.X.p, s->f_H.p,
-        s->dx, 1.0 / s->dx, s->dt * s->dt, s->g_idx.p, L.col.p, L.val.p);
-    HOT_LAUNCHED(s);
+    // default: cell-aggregated scatter of the upper triangle + mirror pass; HOT_ASSEMBLE=rows: the atomics-free row-gather form
+    // (DRAM writes = the matrix, but bound by the shared-memory broadcast of U: 6.6 + 1.8 ms against 3.x ms at C2, profiles/r2_assemble.md)
+    static const bool scatter_form = !(getenv("HOT_ASSEMBLE") && !strcmp(getenv("HOT_ASSEMBLE"), "rows"));
+    static const bool round1_form = getenv("HOT_ASSEMBLE") && !strcmp(getenv("HOT_ASSEMBLE"), "scatter81"); // the round-1 kernel (+ upper-only)
+    if (scatter_form) {
+        k_matrix_init<<<nblk((long)nn * W), TPB, 0, st>>>(nn, s->mass_matrix.p, L.col.p, L.val.p);
+        HOT_LAUNCHED(s);
+        if (round1_form)
+            k_assemble<<<(unsigned)s->n_groups, AS_THREADS, 0, st>>>(s->cell_start.p, s->group_slot.p, s->nbr8.p, s->P.stride, s->P.X.p, s->f_H.p,
+                s->dx, 1.0 / s->dx, s->dt * s->dt, s->g_idx.p, L.col.p, L.val.p);
+        else
+            k_assemble_upper<<<(unsigned)s->n_groups, AU_THREADS, 0, st>>>(s->cell_start.p, s->group_slot.p, s->nbr8.p, s->P.stride, s->P.X.p, s->f_H.p,
+                s->dx, 1.0 / s->dx, s->dt * s->dt, s->g_idx.p, L.col.p, L.val.p);
+        HOT_LAUNCHED(s);
+        k_mirror<<<nblk((long)nn * 62), TPB, 0, st>>>(nn, L.col.p, L.val.p);
+        HOT_LAUNCHED(s);
+    }
+    else {
+        const long NP = s->n_pages;
+        HOT_CUDA(s->asm_nbr27.reserve(27 * (size_t)NP));
+        HOT_CUDA(s->asm_group_of_slot.reserve((size_t)NP));
+        HOT_CUDA(s->asm_wrec.reserve(AR_REC * (size_t)s->N));
+        k_nbr27<<<nblk(NP * 27), TPB, 0, st>>>(NP, s->page_id.p, s->pid_sorted.p, s->slot_sorted.p, s->asm_nbr27.p);
+        HOT_LAUNCHED(s);
+        HOT_CUDA(cudaMemsetAsync(s->asm_group_of_slot.p, 0xff, (size_t)NP * sizeof(int), st));
+        k_group_of_slot<<<nblk(s->n_groups), TPB, 0, st>>>(s->n_groups, s->group_slot.p, s->asm_group_of_slot.p);
+        HOT_LAUNCHED(s);
+        k_assemble_prep<<<nblk(s->N * AR_REC), TPB, 0, st>>>(s->N, s->P.stride, s->P.X.p, s->f_H.p, s->dx, 1.0 / s->dx, s->asm_wrec.p);
+        HOT_LAUNCHED(s);
+        HOT_FUNC_ATTR_ONCE(s, k_assemble_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AR_ROWS * sizeof(ArWarp)));
+        k_assemble_rows<<<(unsigned)((nn + AR_ROWS - 1) / AR_ROWS), 32 * AR_ROWS, AR_ROWS * sizeof(ArWarp), st>>>(nn, s->dof_slot.p, s->asm_nbr27.p,
+            s->asm_group_of_slot.p, s->cell_start.p, s->asm_wrec.p, s->dt * s->dt, s->mass_matrix.p, s->g_idx.p, L.col.p, L.val.p);
+        HOT_LAUNCHED(s);
+    }
     if (bcproject && s->n_bc > 0) {
         HOT_CUDA(s->bc_of.reserve(nn));
         HOT_CUDA(cudaMemsetAsync(s->bc_of.p, 0xff, (size_t)nn * sizeof(int), st));

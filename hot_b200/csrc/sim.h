@@ -238,6 +238,8 @@ struct Sim {
     DevBuf<uint64_t> mg_ckey, mg_ckey_sorted, mg_heads_key; // coarsening scratch (multigrid.cu: coarsen)
     DevBuf<int> mg_cpos, mg_cpos_sorted, mg_heads_pos, mg_order;
     DevBuf<int> bc_of; // node -> BC table row or -1
+    DevBuf<int> asm_nbr27, asm_group_of_slot; // row-gather assembly (matrix.cu): 27 page neighbours per page, page slot -> page group
+    DevBuf<double> asm_wrec; // 64 per particle: H~ (45), w[3][3], dw[3][3] / dx, pad
     DevBuf<double> diag_mf; // 9n: inverse diagonal blocks of the matrix-free operator (buildDiagonal)
     // HOTSettings (Projects/multigrid/Configurations.h:18-42)
     int mg_smoother = 5, mg_coarse = 2, mg_Ainv = 1, mg_levels = 3, mg_times = 1, mg_levelscale = 0;
