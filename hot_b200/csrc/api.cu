@@ -560,6 +560,28 @@ int hot_get_partition(hot_sim* s, long* out8)
     out8[7] = s->N;
     return 0;
 }
+int hot_set_ghost_ring(hot_sim* s, int on)
+{
+    s->ghost_ring = on != 0;
+    s->sorted = false; // takes effect with the next hot_sort_and_activate
+    s->p2g_done = false;
+    return 0;
+}
+int hot_halo_pages(int rank, int world, int max_pages, const int* counts, const unsigned* all_pids, int* n_out, unsigned* out)
+{
+    if (world < 1 || world > 64 || rank < 0 || rank >= world || !counts || !all_pids || !n_out) return -1;
+    std::vector<uint32_t> ext;
+    halo_pages(rank, world, max_pages, counts, all_pids, ext);
+    *n_out = (int)ext.size();
+    if (out) std::copy(ext.begin(), ext.end(), out);
+    return 0;
+}
+int hot_page_authority(int world, int max_pages, const int* counts, const unsigned* all_pids, int n, const unsigned* pids, int* auth)
+{
+    if (world < 1 || world > 64 || !counts || !all_pids || (n > 0 && (!pids || !auth))) return -1;
+    page_authority(world, max_pages, counts, all_pids, n, pids, auth);
+    return 0;
+}
 int hot_get_transport(hot_sim* s)
 {
     if (s->world <= 1) return 0;
@@ -575,7 +597,7 @@ int hot_share_tables(int rank, int world, int max_pages, const int* counts, cons
     if (world < 1 || rank < 0 || rank >= world || !counts || !all_pids || !slot_sorted) return -1;
     std::vector<int> nr, xs, ss, sp, se, so;
     std::vector<long> no, nc;
-    share_tables(rank, world, max_pages, counts, all_pids, slot_sorted, nr, no, nc, xs, ss, sp, se, so);
+    share_tables(rank, world, max_pages, counts, all_pids, slot_sorted, nr, no, nc, xs, ss, sp, se, so, nullptr);
     *n_nbr = (int)nr.size(); *n_x = (int)xs.size(); *n_sh = (int)ss.size();
     std::copy(nr.begin(), nr.end(), nbr_rank); std::copy(no.begin(), no.end(), nbr_off); std::copy(nc.begin(), nc.end(), nbr_cnt);
     std::copy(xs.begin(), xs.end(), x_slot); std::copy(ss.begin(), ss.end(), sh_slot); std::copy(sp.begin(), sp.end(), sh_ptr);

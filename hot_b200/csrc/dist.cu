@@ -167,14 +167,15 @@ struct PageSource {
     int comps;
     const double *g_m, *g_v; // grid channels (P2G) ...
     size_t gs;
-    const int* g_idx; // ... or a DOF vector
+    const int* g_idx; // ... or a DOF array: components [c0, c0 + comps) of `stride` per node
     const double* v;
+    int stride, c0;
     __device__ double load(int slot, int c, int e) const
     {
         const size_t a = (size_t)slot * Geo::E + e;
         if (!g_idx) return c == 0 ? g_m[a] : g_v[(size_t)(c - 1) * gs + a];
         const int id = g_idx[a];
-        return id >= 0 ? v[(size_t)id * comps + c] : 0.0;
+        return id >= 0 ? v[(size_t)id * stride + c0 + c] : 0.0;
     }
 };
 __global__ void k_pack_shared(long n_x, PageSource src, const int* __restrict__ x_slot, double* __restrict__ buf)
@@ -240,8 +241,11 @@ struct XpWait {
     unsigned long long seq;
 };
 // every sharer adds the partial sums in ascending rank order (entry -1 = this rank's own partial): identical totals everywhere
+// sh_auth == nullptr: every sharer adds the partial sums in ascending rank order (entry -1 = this rank's own partial): identical
+// totals everywhere.  sh_auth != nullptr: take-over - the holders of a page replace their values by the authority's.
 __global__ void k_unpack_shared(int n_sh, int comps, const int* __restrict__ sh_slot, const int* __restrict__ sh_ptr, const int* __restrict__ sh_entry,
-    const double* recv, double* __restrict__ g_m, double* __restrict__ g_v, size_t gs, const int* __restrict__ g_idx, double* __restrict__ v, XpWait w)
+    const int* __restrict__ sh_auth, const double* recv, double* __restrict__ g_m, double* __restrict__ g_v, size_t gs, const int* __restrict__ g_idx,
+    double* __restrict__ v, int stride, int c0, XpWait w)
 {
     if (w.flags) { // peer-memory transport: the neighbours' partial sums of this exchange have landed when their flags say so
         if (threadIdx.x < w.n)
@@ -257,7 +261,12 @@ __global__ void k_unpack_shared(int n_sh, int comps, const int* __restrict__ sh_
     else {
         const int id = g_idx[a];
         if (id < 0) return;
-        dst = v + (size_t)id * comps + c;
+        dst = v + (size_t)id * stride + c0 + c;
+    }
+    if (sh_auth) {
+        const int en = sh_auth[p];
+        if (en >= 0) *dst = __ldcg(recv + ((size_t)en * comps + c) * Geo::E + e);
+        return;
     }
     const double mine = *dst;
     double sum = 0.0;
@@ -399,7 +408,7 @@ int xp_after_sort(Sim* s)
     return 0;
 }
 
-int exchange_pages(Sim* s, const PageSource& src, double* g_m, double* g_v, double* v)
+int exchange_pages(Sim* s, const PageSource& src, double* g_m, double* g_v, double* v, bool takeover = false)
 {
     if (s->world <= 1) return 0;
     cudaStream_t st = s->stream;
@@ -456,7 +465,8 @@ int exchange_pages(Sim* s, const PageSource& src, double* g_m, double* g_v, doub
         recv = s->x_recv.p;
     }
     const long un = (long)s->n_sh * src.comps * Geo::E;
-    k_unpack_shared<<<nblk(un), TPB, 0, st>>>(s->n_sh, src.comps, s->sh_slot.p, s->sh_ptr.p, s->sh_entry.p, recv, g_m, g_v, src.gs, src.g_idx, v, w);
+    k_unpack_shared<<<nblk(un), TPB, 0, st>>>(s->n_sh, src.comps, s->sh_slot.p, s->sh_ptr.p, s->sh_entry.p, takeover ? s->sh_auth.p : nullptr, recv, g_m, g_v,
+        src.gs, src.g_idx, v, src.stride, src.c0, w);
     HOT_LAUNCHED(s);
     return 0;
 }
@@ -472,9 +482,10 @@ int exchange_pages(Sim* s, const PageSource& src, double* g_m, double* g_v, doub
 //                                this rank is the lowest sharer (it counts the page's nodes in reductions).
 void share_tables(int rank, int world, int max_pages, const int* counts, const uint32_t* all_pids, const int* slot_sorted, std::vector<int>& nbr_rank,
     std::vector<long>& nbr_off, std::vector<long>& nbr_cnt, std::vector<int>& x_slot, std::vector<int>& sh_slot, std::vector<int>& sh_ptr,
-    std::vector<int>& sh_entry, std::vector<int>& sh_owned)
+    std::vector<int>& sh_entry, std::vector<int>& sh_owned, std::vector<int>* sh_rank)
 {
     nbr_rank.clear(); nbr_off.clear(); nbr_cnt.clear(); x_slot.clear(); sh_slot.clear(); sh_entry.clear(); sh_owned.clear();
+    if (sh_rank) sh_rank->clear();
     sh_ptr.assign(1, 0);
     const uint32_t* my = all_pids + (size_t)rank * max_pages;
     const int nm = counts[rank];
@@ -505,13 +516,100 @@ void share_tables(int rank, int world, int max_pages, const int* counts, const u
         sh_slot.push_back(slot_sorted[i]);
         bool self_done = false;
         for (const auto& pr : sharers[i]) { // neighbours were visited in ascending rank order
-            if (!self_done && pr.first > rank) { sh_entry.push_back(-1); self_done = true; }
+            if (!self_done && pr.first > rank) {
+                sh_entry.push_back(-1);
+                if (sh_rank) sh_rank->push_back(rank);
+                self_done = true;
+            }
             sh_entry.push_back(pr.second);
+            if (sh_rank) sh_rank->push_back(pr.first);
         }
-        if (!self_done) sh_entry.push_back(-1);
+        if (!self_done) {
+            sh_entry.push_back(-1);
+            if (sh_rank) sh_rank->push_back(rank);
+        }
         sh_ptr.push_back((int)sh_entry.size());
         sh_owned.push_back(sharers[i].front().first > rank ? 1 : 0);
     }
+}
+
+
+// ---- ghost ring for the assembled-matrix / multigrid path (host logic, exported for the CPU tests) ----------------------------
+// Block rows (a15) reach two nodes around a node: a row on a page that another rank's particles also touch has columns on pages
+// this rank never activated.  With the ghost ring on, a rank additionally holds every page of the 27-neighbourhood of its SHARED
+// pages that some rank activates (no particles of its own there: its partial sums are zero, the page is simply one more shared
+// page, summed and numbered like the others).  Rows on the rank's own ("base") pages then have all their columns locally.
+// Authority of a page = the rank whose values count (reductions, Galerkin sums, the values every other holder takes over after a
+// Gauss-Seidel colour phase or an SpMV): the lowest rank that has the page AND the other page of its 4^3 Gauss-Seidel block (the
+// x-neighbour with which it forms the block) among its base pages; if nobody has both, the halves do not couple and the lowest
+// base holder of the page takes it.
+static inline void page_origin(uint32_t pid, int& x, int& y, int& z)
+{
+    const uint64_t off = (uint64_t)pid << 12;
+    x = (int)bit_pack(off, Geo::xmask); y = (int)bit_pack(off, Geo::ymask); z = (int)bit_pack(off, Geo::zmask);
+}
+static inline uint32_t page_at(int x, int y, int z) { return (uint32_t)(linear_offset(x, y, z) >> 12); }
+
+struct PageHolders { // page id -> bit mask of the ranks that activate it (world <= 64)
+    std::vector<uint32_t> pid; // ascending, unique
+    std::vector<uint64_t> mask;
+    uint64_t find(uint32_t p) const
+    {
+        auto it = std::lower_bound(pid.begin(), pid.end(), p);
+        return (it != pid.end() && *it == p) ? mask[it - pid.begin()] : 0ull;
+    }
+};
+static PageHolders page_holders(int world, int max_pages, const int* counts, const uint32_t* all_pids)
+{
+    std::vector<std::pair<uint32_t, int>> pr;
+    for (int r = 0; r < world; ++r)
+        for (int i = 0; i < counts[r]; ++i) pr.emplace_back(all_pids[(size_t)r * max_pages + i], r);
+    std::sort(pr.begin(), pr.end());
+    PageHolders h;
+    for (const auto& q : pr) {
+        if (h.pid.empty() || h.pid.back() != q.first) { h.pid.push_back(q.first); h.mask.push_back(0ull); }
+        h.mask.back() |= 1ull << q.second;
+    }
+    return h;
+}
+// ghost pages of `rank`, ascending
+void halo_pages(int rank, int world, int max_pages, const int* counts, const uint32_t* all_pids, std::vector<uint32_t>& ext)
+{
+    ext.clear();
+    const PageHolders h = page_holders(world, max_pages, counts, all_pids);
+    const uint32_t* my = all_pids + (size_t)rank * max_pages;
+    const uint64_t me = 1ull << rank;
+    for (int i = 0; i < counts[rank]; ++i) {
+        if ((h.find(my[i]) & ~me) == 0) continue; // not shared
+        int x, y, z;
+        page_origin(my[i], x, y, z);
+        for (int q = 0; q < 27; ++q) {
+            const int nx = x + Geo::BX * (q / 9 - 1), ny = y + Geo::BY * ((q / 3) % 3 - 1), nz = z + Geo::BZ * (q % 3 - 1);
+            if (nx < 0 || ny < 0 || nz < 0 || nx >= 4096 || ny >= 4096 || nz >= 4096) continue;
+            const uint32_t np = page_at(nx, ny, nz);
+            const uint64_t m = h.find(np);
+            if (m != 0 && !(m & me)) ext.push_back(np);
+        }
+    }
+    std::sort(ext.begin(), ext.end());
+    ext.erase(std::unique(ext.begin(), ext.end()), ext.end());
+}
+// authority rank of page `pid` from the BASE lists
+static int page_authority_of(const PageHolders& h, uint32_t pid)
+{
+    const uint64_t m = h.find(pid);
+    if (!m) return -1;
+    int x, y, z;
+    page_origin(pid, x, y, z);
+    const uint64_t mp = h.find(page_at(x ^ Geo::BX, y, z)); // the other half of the 4^3 block
+    const uint64_t both = m & mp;
+    const uint64_t pick = both ? both : m;
+    return __builtin_ctzll(pick);
+}
+void page_authority(int world, int max_pages, const int* counts, const uint32_t* all_pids, int n, const uint32_t* pids, int* auth)
+{
+    const PageHolders h = page_holders(world, max_pages, counts, all_pids);
+    for (int i = 0; i < n; ++i) auth[i] = page_authority_of(h, pids[i]);
 }
 
 // shared-page tables for the pages of the current sort
@@ -545,10 +643,74 @@ int dist_after_sort(Sim* s)
     HOT_CUDA(cudaMemcpyAsync(all.data(), s->x_pids.p, all.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     HOT_CUDA(cudaMemcpyAsync(slot_sorted.data(), s->slot_sorted.p, slot_sorted.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
     HOT_CUDA(cudaStreamSynchronize(st));
-    // 2. + 3. intersections and the CSR of contributions (host logic, also exported for the CPU tests: hot_share_tables)
-    std::vector<int> x_slot, sh_slot, sh_ptr, sh_entry, sh_owned;
-    share_tables(s->rank, W, maxp, counts.data(), all.data(), slot_sorted.data(), s->nbr_rank, s->nbr_off, s->nbr_cnt, x_slot, sh_slot, sh_ptr, sh_entry,
-        sh_owned);
+    std::vector<int> sh_auth;
+    std::vector<int> x_slot, sh_slot, sh_ptr, sh_entry, sh_owned, sh_rank;
+    s->n_base_pages = s->n_pages;
+    if (s->ghost_ring) {
+        // 1b. ghost ring: every rank derives everybody's ghost pages from the base lists (same inputs, same result everywhere)
+        std::vector<std::vector<uint32_t>> ext(W);
+        int maxe = 0;
+        for (int r = 0; r < W; ++r) {
+            halo_pages(r, W, maxp, counts.data(), all.data(), ext[r]);
+            maxe = std::max(maxe, counts[r] + (int)ext[r].size());
+        }
+        // this rank's page table grows by its ghost pages (slots n_pages ..., no particles, no page groups)
+        const std::vector<uint32_t>& mine_ext = ext[s->rank];
+        const long NP0 = s->n_pages, NE = (long)mine_ext.size(), NP1 = NP0 + NE;
+        if (NE > 0) {
+            DevBuf<uint32_t> grown;
+            HOT_CUDA(grown.reserve((size_t)NP1));
+            HOT_CUDA(cudaMemcpyAsync(grown.p, s->page_id.p, (size_t)NP0 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+            HOT_CUDA(cudaMemcpyAsync(grown.p + NP0, mine_ext.data(), (size_t)NE * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            HOT_CUDA(cudaStreamSynchronize(st));
+            s->page_id.swap(grown);
+        }
+        // merged ascending lists of every rank; this rank's with its slots
+        std::vector<uint32_t> all2((size_t)W * maxe, 0xffffffffu);
+        std::vector<int> counts2(W), slot2(NP1);
+        for (int r = 0; r < W; ++r) {
+            const uint32_t* base = all.data() + (size_t)r * maxp;
+            uint32_t* out = all2.data() + (size_t)r * maxe;
+            int i = 0, j = 0, k = 0;
+            const int nb = counts[r], ne = (int)ext[r].size();
+            while (i < nb || j < ne) {
+                const bool take_base = j >= ne || (i < nb && base[i] < ext[r][j]);
+                if (r == s->rank) slot2[k] = take_base ? slot_sorted[i] : (int)(NP0 + j);
+                out[k++] = take_base ? base[i++] : ext[r][j++];
+            }
+            counts2[r] = k;
+        }
+        s->n_pages = NP1;
+        HOT_CUDA(s->pid_sorted.reserve((size_t)NP1));
+        HOT_CUDA(s->slot_sorted.reserve((size_t)NP1));
+        HOT_CUDA(cudaMemcpyAsync(s->pid_sorted.p, all2.data() + (size_t)s->rank * maxe, (size_t)NP1 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        HOT_CUDA(cudaMemcpyAsync(s->slot_sorted.p, slot2.data(), (size_t)NP1 * sizeof(int), cudaMemcpyHostToDevice, st));
+        HOT_CUDA(cudaStreamSynchronize(st));
+        rc = rebuild_neighbours(s); // nbr8 over the grown table
+        if (rc) return rc;
+        share_tables(s->rank, W, maxe, counts2.data(), all2.data(), slot2.data(), s->nbr_rank, s->nbr_off, s->nbr_cnt, x_slot, sh_slot, sh_ptr, sh_entry,
+            sh_owned, &sh_rank);
+        // authority per shared page (from the BASE lists): who counts the page, and where its values arrive in the exchange list
+        const PageHolders h = page_holders(W, maxp, counts.data(), all.data());
+        std::vector<int> slot_to_sorted(NP1);
+        for (long k = 0; k < NP1; ++k) slot_to_sorted[slot2[k]] = (int)k;
+        const uint32_t* mine2 = all2.data() + (size_t)s->rank * maxe;
+        sh_auth.assign(sh_slot.size(), -1);
+        for (size_t p = 0; p < sh_slot.size(); ++p) {
+            const int a = page_authority_of(h, mine2[slot_to_sorted[sh_slot[p]]]);
+            sh_owned[p] = a == s->rank ? 1 : 0;
+            if (a != s->rank)
+                for (int q = sh_ptr[p]; q < sh_ptr[p + 1]; ++q)
+                    if (sh_rank[q] == a) sh_auth[p] = sh_entry[q];
+            if (a != s->rank && sh_auth[p] < 0) return fail(s, "ghost ring: the authority of a shared page is not among its sharers");
+        }
+    }
+    else {
+        // 2. + 3. intersections and the CSR of contributions (host logic, also exported for the CPU tests: hot_share_tables)
+        share_tables(s->rank, W, maxp, counts.data(), all.data(), slot_sorted.data(), s->nbr_rank, s->nbr_off, s->nbr_cnt, x_slot, sh_slot, sh_ptr, sh_entry,
+            sh_owned, nullptr);
+        sh_auth.assign(sh_slot.size(), -1); // (lowest sharer counts; no take-over exchange without the ghost ring)
+    }
     s->x_total = (long)x_slot.size();
     s->n_sh = (int)sh_slot.size();
     auto up = [&](DevBuf<int>& d, const std::vector<int>& h) -> cudaError_t {
@@ -561,6 +723,7 @@ int dist_after_sort(Sim* s)
     HOT_CUDA(up(s->sh_ptr, sh_ptr));
     HOT_CUDA(up(s->sh_entry, sh_entry));
     HOT_CUDA(up(s->sh_owned, sh_owned));
+    HOT_CUDA(up(s->sh_auth, sh_auth));
     HOT_CUDA(cudaStreamSynchronize(st)); // the host vectors go out of scope
     return xp_after_sort(s);
 }
@@ -570,7 +733,7 @@ int dist_p2g_exchange(Sim* s)
 {
     if (s->world <= 1) return 0;
     KTime t(s, KC_TRANSFER);
-    PageSource src{4, s->g_m.p, s->g_v.p, s->g_stride, nullptr, nullptr};
+    PageSource src{4, s->g_m.p, s->g_v.p, s->g_stride, nullptr, nullptr, 0, 0};
     return exchange_pages(s, src, s->g_m.p, s->g_v.p, nullptr);
 }
 
@@ -611,8 +774,28 @@ int dist_exchange_shared(Sim* s, double* v, int comps)
 {
     if (s->world <= 1) return 0;
     KTime t(s, KC_TRANSFER);
-    PageSource src{comps, nullptr, nullptr, 0, s->g_idx.p, v};
+    PageSource src{comps, nullptr, nullptr, 0, s->g_idx.p, v, comps, 0};
     return exchange_pages(s, src, nullptr, nullptr, v);
+}
+
+// every holder of a shared page replaces its values by those of the page's authority (after a Gauss-Seidel colour phase, an SpMV
+// ... on the assembled-matrix path, where only the authority's rows have all their columns)
+int dist_takeover_shared(Sim* s, double* v, int comps)
+{
+    if (s->world <= 1) return 0;
+    if (!s->ghost_ring) return fail(s, "take-over exchange without the ghost ring (hot_set_ghost_ring)");
+    KTime t(s, KC_TRANSFER);
+    PageSource src{comps, nullptr, nullptr, 0, s->g_idx.p, v, comps, 0};
+    return exchange_pages(s, src, nullptr, nullptr, v, true);
+}
+
+// sum over the sharers of components [c0, c0 + nc) of a DOF array with `stride` doubles per node (block rows in slices)
+int dist_exchange_rows(Sim* s, double* val, int stride, int c0, int nc)
+{
+    if (s->world <= 1) return 0;
+    KTime t(s, KC_TRANSFER);
+    PageSource src{nc, nullptr, nullptr, 0, s->g_idx.p, val, stride, c0};
+    return exchange_pages(s, src, nullptr, nullptr, val);
 }
 
 int dist_allreduce_buffer(Sim* s, double* dev, long count, int op)
@@ -620,6 +803,16 @@ int dist_allreduce_buffer(Sim* s, double* dev, long count, int op)
     if (s->world <= 1 || count <= 0) return 0;
     return comm_all_reduce(s, dev, count, op);
 }
+
+int dist_all_gather_host(Sim* s, const void* mine, void* all, long bytes)
+{
+    if (s->world <= 1) {
+        std::memcpy(all, mine, (size_t)bytes);
+        return 0;
+    }
+    return host_all_gather(s, mine, all, bytes);
+}
+int dist_all_gather_dev(Sim* s, const void* send, void* recv, long bytes) { return comm_all_gather(s, send, recv, bytes); }
 
 int dist_allreduce_host(Sim* s, double* host, int count, int op)
 {

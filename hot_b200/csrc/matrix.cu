@@ -50,7 +50,7 @@ __global__ void k_matrix_init(int n, const double* __restrict__ mass, int* __res
     if (t >= (long)n * W) return;
     const int i = (int)(t / W), s = (int)(t - (long)i * W);
     col[t] = i;
-    const double m = s == 62 ? mass[i] : 0.0;
+    const double m = (s == 62 && mass) ? mass[i] : 0.0; // (partitioned: the inertia term is added after the rows have been summed)
 #pragma unroll
     for (int q = 0; q < 9; ++q) val[((size_t)i * 9 + q) * W + s] = (q == 0 || q == 4 || q == 8) ? m : 0.0;
 }
@@ -503,6 +503,15 @@ __global__ void k_mirror(int n, const int* __restrict__ col, double* __restrict_
         for (int r = 0; r < 3; ++r) dst[(r + 3 * c) * W] = src[(c + 3 * r) * W];
 }
 
+__global__ void k_add_mass(int n, const double* __restrict__ mass, double* __restrict__ val)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double m = mass[i];
+    double* v = val + (size_t)i * 9 * W + 62;
+    v[0] += m; v[4 * W] += m; v[8 * W] += m;
+}
+
 __global__ void k_bc_of(int n_bc, const int* __restrict__ node, int* __restrict__ bc_of)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -655,7 +664,8 @@ int fill_id2coord(Sim* s, int* coord_dev)
 
 int build_matrix(Sim* s, bool bcproject)
 {
-    if (s->world > 1) return fail(s, "buildMatrix: the assembled-matrix / multigrid path is single-GPU in this version; partitioned runs use --matfree (lsolver 2)");
+    if (s->world > 1 && !s->ghost_ring)
+        return fail(s, "buildMatrix on a partitioned object needs the ghost ring: hot_set_ghost_ring(h, 1) before hot_sort_and_activate");
     int rc = ensure_hessian(s);
     if (rc) return rc;
     cudaStream_t st = s->stream;
@@ -675,7 +685,7 @@ int build_matrix(Sim* s, bool bcproject)
     static const bool scatter_form = !(getenv("HOT_ASSEMBLE") && !strcmp(getenv("HOT_ASSEMBLE"), "rows"));
     static const bool round1_form = getenv("HOT_ASSEMBLE") && !strcmp(getenv("HOT_ASSEMBLE"), "scatter81"); // the round-1 kernel (+ upper-only)
     if (scatter_form) {
-        k_matrix_init<<<nblk((long)nn * W), TPB, 0, st>>>(nn, s->mass_matrix.p, L.col.p, L.val.p);
+        k_matrix_init<<<nblk((long)nn * W), TPB, 0, st>>>(nn, s->world > 1 ? nullptr : s->mass_matrix.p, L.col.p, L.val.p);
         HOT_LAUNCHED(s);
         if (round1_form)
             k_assemble<<<(unsigned)s->n_groups, AS_THREADS, 0, st>>>(s->cell_start.p, s->group_slot.p, s->nbr8.p, s->P.stride, s->P.X.p, s->f_H.p,
@@ -703,6 +713,22 @@ int build_matrix(Sim* s, bool bcproject)
         k_assemble_rows<<<(unsigned)((nn + AR_ROWS - 1) / AR_ROWS), 32 * AR_ROWS, AR_ROWS * sizeof(ArWarp), st>>>(nn, s->dof_slot.p, s->asm_nbr27.p,
             s->asm_group_of_slot.p, s->cell_start.p, s->asm_wrec.p, s->dt * s->dt, s->mass_matrix.p, s->g_idx.p, L.col.p, L.val.p);
         HOT_LAUNCHED(s);
+    }
+    if (s->world > 1) {
+        // Partitioned object: the rows hold this rank's particles only.  Sum them over the holders of the shared pages (slot-wise:
+        // a slot is a coordinate offset, the same on every rank), 128 of the 1152 doubles of a row per exchange; then the inertia
+        // term, once; then the column ids from the node coordinates (another rank's particles couple nodes this rank's do not).
+        if (!scatter_form) return fail(s, "buildMatrix on a partitioned object uses the scatter form (unset HOT_ASSEMBLE)");
+        for (int q = 0; q < 9; ++q) {
+            rc = dist_exchange_rows(s, L.val.p, 9 * W, q * W, W);
+            if (rc) return rc;
+        }
+        k_add_mass<<<nblk(nn), TPB, 0, st>>>(nn, s->mass_matrix.p, L.val.p);
+        HOT_LAUNCHED(s);
+        rc = build_coord_map(s, L);
+        if (rc) return rc;
+        rc = columns_from_coords(s, L);
+        if (rc) return rc;
     }
     if (bcproject && s->n_bc > 0) {
         HOT_CUDA(s->bc_of.reserve(nn));

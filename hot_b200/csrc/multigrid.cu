@@ -227,6 +227,56 @@ __global__ void k_level_diagonal(int n, int Ainv, const double* __restrict__ val
     }
 }
 
+
+// partitioned assembly (matrix.cu): after the rows have been summed over the ranks, a non-zero block may sit in a slot whose column
+// this rank's own particles never set - the column of slot s is the node at coord_i - offset(s)
+__global__ void k_cols_from_coords(int n, const int* __restrict__ coord, const uint64_t* __restrict__ keys, const int* __restrict__ ids,
+    int* __restrict__ col, double* __restrict__ val)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)n * W) return;
+    const int i = (int)(t / W), s = (int)(t - (long)i * W);
+    int j = i;
+    if (s < 125 && s != 62) {
+        double* v = val + (size_t)i * 9 * W + s;
+        bool nz = false;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) nz = nz || v[q * W] != 0.0;
+        if (nz) {
+            const int x = coord[3 * i] - (s / 25 - 2), y = coord[3 * i + 1] - ((s / 5) % 5 - 2), z = coord[3 * i + 2] - (s % 5 - 2);
+            const int f = (x >= 0 && y >= 0 && z >= 0) ? find_node(keys, ids, n, coord_key(x, y, z)) : -1;
+            if (f >= 0) j = f;
+            else { // a column this rank does not hold: only on ghost pages, whose rows are never used (their values are taken over)
+#pragma unroll
+                for (int q = 0; q < 9; ++q) v[q * W] = 0.0;
+            }
+        }
+    }
+    col[t] = j;
+}
+// replicated coarse level of a partitioned object: node c = the c-th smallest coordinate key of the union over the ranks
+__global__ void k_coarse_from_keys(int nc, const uint64_t* __restrict__ key_asc, int* __restrict__ coord, int* __restrict__ id_sorted)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    const uint64_t k = key_asc[c];
+    coord[3 * c] = (int)(k >> 24);
+    coord[3 * c + 1] = (int)((k >> 12) & 0xfff);
+    coord[3 * c + 2] = (int)(k & 0xfff);
+    id_sorted[c] = c;
+}
+// R rows restricted to the fine nodes this rank counts: partial sums over the ranks add up to the whole restriction / Galerkin product
+__global__ void k_mask_R(long n, const int* __restrict__ rcol, const unsigned char* __restrict__ own, double* __restrict__ rw)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && rw[t] != 0.0 && !own[rcol[t]]) rw[t] = 0.0;
+}
+__global__ void k_fill_u64(long n, uint64_t v, uint64_t* __restrict__ p)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) p[t] = v;
+}
+
 // ---- Gauss-Seidel schedule ---------------------------------------------------------------------------------------------
 __global__ void k_block_keys(int n, const int* __restrict__ coord, uint32_t* __restrict__ key, int* __restrict__ id)
 {
@@ -902,7 +952,9 @@ int build_gs_schedule(Sim* s, MGLevel& L)
     return 0;
 }
 
-int coarsen(Sim* s, MGLevel& F, MGLevel& C)
+// candidates of the coarse node set of level F: ascending unique keys in s->mg_heads_key, first candidate position of each in
+// s->mg_heads_pos; the count in *nc_out
+int coarse_candidates(Sim* s, MGLevel& F, int* nc_out)
 {
     cudaStream_t st = s->stream;
     const int nf = F.n;
@@ -938,6 +990,21 @@ int coarsen(Sim* s, MGLevel& F, MGLevel& C)
     if (rc) return rc;
     HOT_CUDA(cudaMemcpyAsync(s->hcount, s->dcount.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     HOT_CUDA(cudaStreamSynchronize(st));
+    *nc_out = s->hcount[0];
+    return 0;
+}
+
+int coarsen(Sim* s, MGLevel& F, MGLevel& C)
+{
+    cudaStream_t st = s->stream;
+    const int nf = F.n;
+    const long nc8 = (long)nf * 8;
+    DevBuf<uint64_t>& heads_key = s->mg_heads_key;
+    DevBuf<int>&cpos = s->mg_cpos, &heads_pos = s->mg_heads_pos, &order = s->mg_order;
+    int nc_cand = 0;
+    int rc = coarse_candidates(s, F, &nc_cand);
+    if (rc) return rc;
+    s->hcount[0] = nc_cand;
     const int nc = s->hcount[0];
     if (nc <= 0) return fail(s, "multigrid: empty coarse level");
     C.n = nc;
@@ -971,6 +1038,72 @@ int coarsen(Sim* s, MGLevel& F, MGLevel& C)
     k_galerkin<<<nc, W, 0, st>>>(nc, C.coord.p, C.key_sorted.p, C.id_sorted.p, F.rcol.p, F.rw.p, F.val.p, C.col.p, C.val.p);
     HOT_LAUNCHED(s);
     return 0;
+}
+
+// Level 0 -> 1 of a PARTITIONED object: level 0 stays distributed (local nodes incl. the ghost ring), level 1 and everything coarser
+// is REPLICATED on every rank (1/7 of the fine level; its smoothers then need no exchange at all):
+//  * coarse node set = union over the ranks of the local candidate sets (all-gather of the coordinate keys), node c = c-th smallest key
+//    on every rank alike;
+//  * R rows over this rank's fine nodes, masked to the nodes it counts (own_node = page authority): restriction and the Galerkin
+//    product R A P become partial sums, completed by an all-reduce (the rows of authority nodes are complete and have all their columns);
+//  * P rows of the local fine nodes point at the replicated coarse ids: prolongation needs no exchange.
+int coarsen_dist(Sim* s, MGLevel& F, MGLevel& C)
+{
+    cudaStream_t st = s->stream;
+    const int nf = F.n, Wd = s->world;
+    int nc_local = 0;
+    int rc = coarse_candidates(s, F, &nc_local);
+    if (rc) return rc;
+    std::vector<int> counts(Wd);
+    rc = dist_all_gather_host(s, &nc_local, counts.data(), sizeof(int));
+    if (rc) return rc;
+    long maxc = 1;
+    for (int c : counts) maxc = std::max<long>(maxc, c);
+    // all-gather of the padded key lists, sort, unique
+    DevBuf<uint64_t>&ckey = s->mg_ckey, &ckey_sorted = s->mg_ckey_sorted;
+    const long tot = maxc * Wd;
+    HOT_CUDA(ckey.reserve((size_t)tot + maxc));
+    HOT_CUDA(ckey_sorted.reserve((size_t)tot));
+    HOT_CUDA(s->head_flag.reserve((size_t)tot));
+    uint64_t* mine = ckey.p + tot;
+    k_fill_u64<<<nblk(maxc), TPB, 0, st>>>(maxc, NOKEY, mine);
+    HOT_LAUNCHED(s);
+    HOT_CUDA(cudaMemcpyAsync(mine, s->mg_heads_key.p, (size_t)nc_local * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    rc = dist_all_gather_dev(s, mine, ckey.p, maxc * (long)sizeof(uint64_t));
+    if (rc) return rc;
+    rc = with_tmp(s, [&](void* t, size_t& b) { return cub::DeviceRadixSort::SortKeys(t, b, ckey.p, ckey_sorted.p, (int)tot, 0, 64, st); });
+    if (rc) return rc;
+    k_head_flags64<<<nblk(tot), TPB, 0, st>>>(tot, ckey_sorted.p, s->head_flag.p);
+    HOT_LAUNCHED(s);
+    HOT_CUDA(C.key_sorted.reserve((size_t)tot));
+    rc = with_tmp(s, [&](void* t, size_t& b) {
+        return cub::DeviceSelect::Flagged(t, b, ckey_sorted.p, s->head_flag.p, C.key_sorted.p, s->dcount.p, (int)tot, st);
+    });
+    if (rc) return rc;
+    HOT_CUDA(cudaMemcpyAsync(s->hcount, s->dcount.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HOT_CUDA(cudaStreamSynchronize(st));
+    const int nc = s->hcount[0];
+    if (nc <= 0) return fail(s, "multigrid: empty coarse level");
+    C.n = nc;
+    HOT_CUDA(C.coord.reserve(3 * (size_t)nc));
+    HOT_CUDA(C.id_sorted.reserve(nc));
+    k_coarse_from_keys<<<nblk(nc), TPB, 0, st>>>(nc, C.key_sorted.p, C.coord.p, C.id_sorted.p);
+    HOT_LAUNCHED(s);
+    HOT_CUDA(F.pcol.reserve((size_t)nf * 8));
+    HOT_CUDA(F.pw.reserve((size_t)nf * 8));
+    HOT_CUDA(F.rcol.reserve((size_t)nc * 32));
+    HOT_CUDA(F.rw.reserve((size_t)nc * 32));
+    k_build_P<<<nblk(nf), TPB, 0, st>>>(nf, F.coord.p, C.key_sorted.p, C.id_sorted.p, nc, F.pcol.p, F.pw.p);
+    HOT_LAUNCHED(s);
+    k_build_R<<<nblk((long)nc * 32), TPB, 0, st>>>(nc, C.coord.p, F.key_sorted.p, F.id_sorted.p, nf, F.rcol.p, F.rw.p);
+    HOT_LAUNCHED(s);
+    k_mask_R<<<nblk((long)nc * 32), TPB, 0, st>>>((long)nc * 32, F.rcol.p, s->own_node.p, F.rw.p);
+    HOT_LAUNCHED(s);
+    HOT_CUDA(C.col.reserve((size_t)nc * W));
+    HOT_CUDA(C.val.reserve((size_t)nc * 9 * W));
+    k_galerkin<<<nc, W, 0, st>>>(nc, C.coord.p, C.key_sorted.p, C.id_sorted.p, F.rcol.p, F.rw.p, F.val.p, C.col.p, C.val.p);
+    HOT_LAUNCHED(s);
+    return dist_allreduce_buffer(s, C.val.p, (long)nc * 9 * W, 0);
 }
 
 int finish_level(Sim* s, MGLevel& L, int Ainv, bool colors)
@@ -1149,7 +1282,9 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         // (many blocks per colour: the per-phase launches below keep 3 CTAs per SM busy, which measures faster than the
         //  cooperative form whose register budget allows only 2)
         static const bool force_coop = getenv("HOT_GS_COOP") != nullptr;
-        if (max_blocks <= 2 * 148) RC((use_stream ? launch_gs_sweep<512, true>(s, a, max_blocks, &launched) : launch_gs_sweep<512, false>(s, a, max_blocks, &launched)));
+        const bool dist0 = level == 0 && s->world > 1; // partitioned level 0: a take-over exchange follows every colour phase
+        if (dist0) {}
+        else if (max_blocks <= 2 * 148) RC((use_stream ? launch_gs_sweep<512, true>(s, a, max_blocks, &launched) : launch_gs_sweep<512, false>(s, a, max_blocks, &launched)));
         else if (force_coop)
             RC((use_stream ? launch_gs_sweep<GS_THREADS, true>(s, a, max_blocks, &launched) : launch_gs_sweep<GS_THREADS, false>(s, a, max_blocks, &launched)));
         if (!launched) {
@@ -1158,17 +1293,20 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
                 if (b1 == b0) continue;
                 (use_stream ? k_gs_block<true, true> : k_gs_block<true, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
                 HOT_LAUNCHED(s);
+                if (dist0) RC(dist_takeover_shared(s, a.hdu, 3)); // later colours read this colour's values on pages other ranks own
             }
             for (int c = 7; c >= 0; --c) {
                 const int b0 = a.cfb[c], b1 = a.cfb[c + 1];
                 if (b1 == b0) continue;
                 (use_stream ? k_gs_block<false, true> : k_gs_block<false, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
                 HOT_LAUNCHED(s);
+                if (dist0) RC(dist_takeover_shared(s, a.du, 3));
             }
             if (!project) {
                 if (a.stream_update) k_gs_stream_update<<<nblk(32L * L.n), TPB, 0, st>>>(a);
                 else k_spmv_update<<<nblk(32L * L.n), TPB, 0, st>>>(L.n, L.col.p, L.val.p, L.du.p, u, r);
                 HOT_LAUNCHED(s);
+                if (dist0) RC(dist_takeover_shared(s, r, 3)); // (u += du is pointwise on consistent vectors)
             }
         }
         if (project) {
@@ -1232,7 +1370,7 @@ int vec_scale(Sim* s, long n, double a, double* y)
 // dot over the DOF vectors of level 0 (n = 3 num_nodes): own nodes + all-reduce when the object is partitioned
 int vec_dot(Sim* s, long n, const double* a, const double* b, double* dev_out, double* host_out)
 {
-    if (s->world <= 1 || n != 3L * s->num_nodes) return reduce_to<1>(s, n, DotF{a, b}, dev_out, host_out);
+    if (s->world <= 1 || s->dot_plain || n != 3L * s->num_nodes) return reduce_to<1>(s, n, DotF{a, b}, dev_out, host_out);
     HOT_CUDA(s->red_out.reserve(64));
     if (!dev_out) dev_out = s->red_out.p;
     int rc = reduce_to<1>(s, n, OwnDotF{a, b, s->own_node.p}, dev_out, nullptr);
@@ -1260,6 +1398,13 @@ int build_coord_map(Sim* s, MGLevel& L)
 }
 
 // MultigridBuilder::build
+int columns_from_coords(Sim* s, MGLevel& L)
+{
+    k_cols_from_coords<<<nblk((long)L.n * W), TPB, 0, s->stream>>>(L.n, L.coord.p, L.key_sorted.p, L.id_sorted.p, L.col.p, L.val.p);
+    HOT_LAUNCHED(s);
+    return 0;
+}
+
 int build_mg(Sim* s, int levels, int smoother, int coarse_solver, int Ainv, int times, int levelscale, double topomega)
 {
     if (!s->matrix_built) return fail(s, "buildMultigrid: call hot_build_matrix first");
@@ -1276,8 +1421,10 @@ int build_mg(Sim* s, int levels, int smoother, int coarse_solver, int Ainv, int 
     const bool colors = smoother == 5 || coarse_solver == 5;
     RC(build_coord_map(s, *s->levels[0]));
     RC(finish_level(s, *s->levels[0], Ainv, colors));
+    if (s->world > 1 && !s->ghost_ring) return fail(s, "buildMultigrid on a partitioned object needs the ghost ring (hot_set_ghost_ring)");
     for (int l = 0; l + 1 < levels; ++l) {
-        RC(coarsen(s, *s->levels[l], *s->levels[l + 1]));
+        if (l == 0 && s->world > 1) RC(coarsen_dist(s, *s->levels[0], *s->levels[1]));
+        else RC(coarsen(s, *s->levels[l], *s->levels[l + 1]));
         RC(finish_level(s, *s->levels[l + 1], Ainv, colors));
     }
     for (int l = 0; l < levels; ++l)
@@ -1292,6 +1439,8 @@ int level_spmv(Sim* s, int level, const double* x, double* b)
     KTime t(s, KC_SPMV);
     k_spmv<0><<<nblk(32L * L.n), TPB, 0, s->stream>>>(L.n, L.col.p, L.val.p, x, b);
     HOT_LAUNCHED(s);
+    // partitioned level 0: rows on ghost pages lack columns - every holder takes the authority's result (coarser levels are replicated)
+    if (level == 0 && s->world > 1) return dist_takeover_shared(s, b, 3);
     return 0;
 }
 static int level_spmv_sub(Sim* s, int level, const double* x, double* b)
@@ -1300,6 +1449,7 @@ static int level_spmv_sub(Sim* s, int level, const double* x, double* b)
     KTime t(s, KC_SPMV);
     k_spmv<1><<<nblk(32L * L.n), TPB, 0, s->stream>>>(L.n, L.col.p, L.val.p, x, b);
     HOT_LAUNCHED(s);
+    if (level == 0 && s->world > 1) return dist_takeover_shared(s, b, 3);
     return 0;
 }
 int level_restrict(Sim* s, int level, const double* fine, double* coarse)
@@ -1309,6 +1459,8 @@ int level_restrict(Sim* s, int level, const double* fine, double* coarse)
     KTime t(s, KC_TRANSFER);
     k_restrict<<<nblk(32L * nc), TPB, 0, s->stream>>>(nc, F.rcol.p, F.rw.p, fine, coarse);
     HOT_LAUNCHED(s);
+    // partitioned level 0: the R rows are masked to the fine nodes this rank counts, the replicated coarse vector is the sum over the ranks
+    if (level == 0 && s->world > 1) return dist_allreduce_buffer(s, coarse, 3L * nc, 0);
     return 0;
 }
 int level_prolong(Sim* s, int level, const double* coarse, double* fine)
@@ -1324,13 +1476,17 @@ int level_prolong(Sim* s, int level, const double* coarse, double* fine)
 int level_smooth(Sim* s, int level, int kind, double* u, double* r, int iterations, double tolerance)
 {
     KTime t(s, KC_GS);
+    s->dot_plain = level > 0; // partitioned object: the coarse levels are replicated, their dots need no mask / all-reduce
+    int rc;
     switch (kind) {
-    case 0: return smooth_jacobi(s, level, u, r, iterations);
-    case 1: return smooth_optimal_jacobi(s, level, u, r, iterations, tolerance);
-    case 2: return smooth_cg(s, level, u, r, iterations);
-    case 5: return smooth_gs(s, level, u, r, iterations);
-    default: return fail(s, "No proper smoother is selected! (supported: 0 Jacobi, 1 optimal Jacobi, 2 PCG, 5 GS)");
+    case 0: rc = smooth_jacobi(s, level, u, r, iterations); break;
+    case 1: rc = smooth_optimal_jacobi(s, level, u, r, iterations, tolerance); break;
+    case 2: rc = smooth_cg(s, level, u, r, iterations); break;
+    case 5: rc = smooth_gs(s, level, u, r, iterations); break;
+    default: rc = fail(s, "No proper smoother is selected! (supported: 0 Jacobi, 1 optimal Jacobi, 2 PCG, 5 GS)");
     }
+    s->dot_plain = false;
+    return rc;
 }
 
 // MultigridOperator::operator(), MultigridPreconditioner.h:362-421.  `out` must not alias `in`.

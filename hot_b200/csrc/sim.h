@@ -261,6 +261,10 @@ struct Sim {
     long global_nodes = 0; // nodes of the whole object = sum of the ranks' owned nodes
     bool own_valid = false;
     DevBuf<int> x_counts, x_slot, sh_slot, sh_ptr, sh_entry, sh_owned;
+    DevBuf<int> sh_auth; // per shared page: exchange-list entry where the AUTHORITY's values arrive, -1 when this rank is the authority
+    bool dot_plain = false; // vec_dot without the ownership mask / all-reduce (replicated coarse levels of a partitioned object)
+    bool ghost_ring = false; // hot_set_ghost_ring: hold the 27-neighbourhood of the shared pages too (assembled-matrix / multigrid path)
+    long n_base_pages = 0; // pages this rank's own particles activate (the first n_base_pages slots); the rest are ghost pages
     DevBuf<uint32_t> x_pids;
     DevBuf<double> x_send, x_recv, x_scalars;
     DevBuf<unsigned char> own_node; // 1: this rank counts the node in dots / norms
@@ -358,13 +362,20 @@ int comm_init_nccl(Sim* s, int rank, int world, const void* id128);
 void comm_destroy(Sim* s);
 void share_tables(int rank, int world, int max_pages, const int* counts, const uint32_t* all_pids, const int* slot_sorted, std::vector<int>& nbr_rank,
     std::vector<long>& nbr_off, std::vector<long>& nbr_cnt, std::vector<int>& x_slot, std::vector<int>& sh_slot, std::vector<int>& sh_ptr,
-    std::vector<int>& sh_entry, std::vector<int>& sh_owned);
+    std::vector<int>& sh_entry, std::vector<int>& sh_owned, std::vector<int>* sh_rank = nullptr);
+void halo_pages(int rank, int world, int max_pages, const int* counts, const uint32_t* all_pids, std::vector<uint32_t>& ext); // ghost ring of a rank
+void page_authority(int world, int max_pages, const int* counts, const uint32_t* all_pids, int n, const uint32_t* pids, int* auth);
+int rebuild_neighbours(Sim* s); // sort.cu: nbr8 after the page table grew
+int dist_takeover_shared(Sim* s, double* v, int comps); // every holder of a shared page takes the authority's values of a DOF array
+int dist_exchange_rows(Sim* s, double* val, int stride, int c0, int nc); // sum of components [c0, c0 + nc) of a DOF array with `stride` per node;
 int dist_after_sort(Sim* s); // shared-page tables of the current sort
 int dist_p2g_exchange(Sim* s); // complete (m, mv) on the shared pages
 int dist_after_numbering(Sim* s); // node ownership for reductions
 int dist_allreduce_buffer(Sim* s, double* dev, long count, int op); // a few device scalars, in place
 int dist_exchange_shared(Sim* s, double* v, int comps); // sum over the sharers on the shared nodes of a DOF array with `comps` per node
 int dist_allreduce_host(Sim* s, double* host, int count, int op); // a few host scalars
+int dist_all_gather_host(Sim* s, const void* mine, void* all, long bytes); // `bytes` host bytes per rank
+int dist_all_gather_dev(Sim* s, const void* send, void* recv, long bytes); // device buffers
 // colliders.cu
 int set_colliders(Sim* s, int n, const ::hot_collider* objs);
 int build_bc_from_colliders(Sim* s, int mode, int* n_bc);
@@ -381,6 +392,7 @@ int level_prolong(Sim* s, int level, const double* coarse, double* fine);
 int level_smooth(Sim* s, int level, int kind, double* u, double* r, int iterations, double tolerance);
 int vcycle(Sim* s, const double* in, double* out, bool timed);
 int build_coord_map(Sim* s, MGLevel& L);
+int columns_from_coords(Sim* s, MGLevel& L); // partitioned assembly: column ids of the non-zero blocks from the node coordinates
 // vector ops (multigrid.cu)
 int vec_axpy(Sim* s, long n, double a, const double* x, double* y); // y += a x
 int vec_axpy_dev(Sim* s, long n, const double* num, const double* den, double sign, const double* x, double* y); // y += sign*(num/den) x

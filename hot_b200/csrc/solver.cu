@@ -413,8 +413,8 @@ int hot_backward_euler_step(hot_sim* s, const hot_solver_options* opt, hot_solve
     if (!s->p2g_done) return fail(s, "backwardEulerStep: call hot_p2g (and hot_set_bc) first");
     if (opt->lsolver != 2 && opt->lsolver != 3) return fail(s, "lsolver must be 2 (Newton + PCG) or 3 (L-BFGS)");
     if (opt->lsolver == 3 && opt->matfree) return fail(s, "LBFGS only works with project & with-matrix (Projects/multigrid/README:13-15)");
-    if (s->world > 1 && !(opt->lsolver == 2 && opt->matfree))
-        return fail(s, "partitioned runs support the matrix-free PN-PCG solver (-lsolver 2 --matfree); the multigrid path is single-GPU in this version");
+    if (s->world > 1 && !(opt->lsolver == 2 && opt->matfree) && !s->ghost_ring)
+        return fail(s, "partitioned runs with an assembled matrix (-lsolver 3, -lsolver 2 without --matfree) need the ghost ring: hot_set_ghost_ring(h, 1) before the sort");
     Objective O;
     O.s = s;
     O.opt = *opt;

@@ -516,8 +516,12 @@ int sort_and_activate(Sim* s)
     k_cell_start<<<nblk(G * (Geo::E + 1)), TPB, 0, st>>>(G, s->group_first.p, s->group_block.p, s->keys.p, s->cell_start.p);
     HOT_LAUNCHED(s);
 
+    // the partition may add ghost pages to the table (dist.cu): the grid arrays are sized after it
+    s->num_nodes = 0;
+    rc = dist_after_sort(s);
+    if (rc) return rc;
     // zero the pages, idx = -1 (MpmSimulationBase.cpp:1128-1136)
-    const size_t gn = (size_t)NP * Geo::E;
+    const size_t gn = (size_t)s->n_pages * Geo::E;
     HOT_CUDA(s->g_m.reserve(gn));
     HOT_CUDA(s->g_v.reserve(3 * gn));
     HOT_CUDA(s->g_idx.reserve(gn));
@@ -526,12 +530,18 @@ int sort_and_activate(Sim* s)
     HOT_CUDA(cudaMemsetAsync(s->g_m.p, 0, gn * sizeof(double), st));
     HOT_CUDA(cudaMemsetAsync(s->g_v.p, 0, 3 * gn * sizeof(double), st));
     HOT_CUDA(cudaMemsetAsync(s->g_idx.p, 0xff, gn * sizeof(int), st));
-    s->num_nodes = 0;
     s->sorted = true;
     s->p2g_done = false;
-    rc = dist_after_sort(s);
-    if (rc) return rc;
     return build_scatter_items(s);
+}
+
+int rebuild_neighbours(Sim* s)
+{
+    const long NP = s->n_pages;
+    HOT_CUDA(s->nbr8.reserve(8 * (size_t)NP));
+    k_neighbours<<<nblk(NP * 8), TPB, 0, s->stream>>>(NP, s->page_id.p, s->pid_sorted.p, s->slot_sorted.p, s->nbr8.p);
+    HOT_LAUNCHED(s);
+    return 0;
 }
 
 int build_scatter_items(Sim* s)

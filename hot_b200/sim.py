@@ -489,6 +489,11 @@ class MpmSimulationB200:
         self._check(self._lib.hot_get_partition(self._h, out))
         return dict(zip(("rank", "world", "neighbors", "shared_pages", "exchange_pages", "owned_nodes", "global_nodes", "particles"), [int(v) for v in out]))
 
+    def set_ghost_ring(self, on=True):
+        """partitioned objects: hold the 27-neighbourhood of the shared pages too (needed by buildMatrix / buildMultigrid / vcycle and
+        the solvers with an assembled matrix when world > 1); takes effect with the next sortParticlesAndPolluteGrid"""
+        self._check(self._lib.hot_set_ghost_ring(self._h, 1 if on else 0))
+
     def get_transport(self):
         return {0: "single rank", 1: "grouped ncclSend/ncclRecv", 2: "caller callbacks", 3: "peer memory (NVLink P2P stores + flags)"}[int(self._lib.hot_get_transport(self._h))]
 

@@ -145,6 +145,17 @@ int hot_set_partition(hot_sim* h, int rank, int world, const hot_transport* tran
 /* {rank, world, neighbour ranks, shared local pages, pages exchanged per scatter (sum over neighbours), nodes this rank counts
  * in reductions, nodes of the whole object (the last two -1 before hot_p2g), local particles} */
 int hot_get_partition(hot_sim* h, long* out8);
+/* Ghost ring for the assembled-matrix / multigrid path of a partitioned object (SquareMatrix rows reach two nodes around a node,
+ * Projects/multigrid/ImplicitSolver.h:465-468): with on != 0 a rank also holds every page of the 27-neighbourhood of its shared
+ * pages that some rank activates.  Needed by hot_build_matrix / hot_build_mg / hot_vcycle / the -lsolver 2 and 3 solves with a
+ * matrix when world > 1; the transfers alone (hot_p2g / hot_g2p) and the matrix-free solver run without it (fewer pages to exchange).
+ * Takes effect with the next hot_sort_and_activate. */
+int hot_set_ghost_ring(hot_sim* h, int on);
+/* host logic of the ghost ring, callable without a device (CPU tests): ghost pages of `rank` (ascending; out may be NULL to count),
+ * and the authority rank of pages (the rank whose rows count: lowest rank that activates the page and the other half of its 4^3
+ * Gauss-Seidel block; inputs as for hot_share_tables, the BASE lists without ghost pages) */
+int hot_halo_pages(int rank, int world, int max_pages, const int* counts, const unsigned* all_pids, int* n_out, unsigned* out);
+int hot_page_authority(int world, int max_pages, const int* counts, const unsigned* all_pids, int n, const unsigned* pids, int* auth);
 /* how the shared pages travel after the last hot_sort_and_activate: 0 single rank, 1 grouped ncclSend / ncclRecv, 2 the caller's
  * callbacks, 3 peer memory (with hot_comm_init_nccl, when every rank can map every other rank's receive arena through cudaIpc:
  * the pack kernel stores the partial sums straight into the neighbours' HBM over NVLink and raises a flag there, the unpack kernel

@@ -77,6 +77,75 @@ def run_object(sim, sc, sel, ymin):
     return res
 
 
+HOT_FLAGS = dict(lsolver=3, mg_level=3, smoother=5, coarse_solver=2, project=1, linesearch=1, bcproject=1, usecn=1, cneps=1e-7)  # tog.sh:38
+
+
+def run_mg(sim, sc, sel, ymin):
+    """assembled matrix / Galerkin hierarchy / V-cycle / HOT solve; everything per LOCAL node (level 0) or per coarse node with its
+    coordinates, so that a partitioned run can be matched against the single-GPU one"""
+    res = {}
+    n, coord = setup(sim, sc, sel, ymin)
+    res["coord"] = coord
+    res["global_nodes"] = np.array(sim.get_partition()["global_nodes"])
+    sim.backupStrain()
+    sim.updateState(sim.get_dv() + 0.2 * node_field(coord, 0.3))
+    sim.buildMatrix(True)
+    x = node_field(coord, 1.7)
+    # order-independent smoother first: Jacobi V-cycle (smoother 0) with the PCG coarse solve must agree to rounding
+    sim.buildMultigrid(levels=3, smoother=0, coarseSolver=2, Ainv=1, times=2)
+    res["dofs"] = np.array(sim.level_dofs())
+    res["spmv0"] = sim.spmv(0, x)
+    c1 = sim.level_coords(1); c2 = sim.level_coords(2)
+    res["coord1"] = c1; res["coord2"] = c2
+    res["spmv1"] = sim.spmv(1, node_field(c1, 0.9))
+    res["spmv2"] = sim.spmv(2, node_field(c2, 0.4))
+    res["restrict0"] = sim.restrict(0, x)
+    res["prolong0"] = sim.prolong(0, node_field(c1, 0.5))
+    r = sim.spmv(0, node_field(coord, 2.1))          # a right-hand side in the range of the (BC-projected) operator
+    res["rhs"] = r
+    res["vcycle_jacobi"] = sim.vcycle(r)
+    # the HOT smoother: coloured block Gauss-Seidel (in-block order follows the LOCAL numbering: compared as a solver, not entry-wise)
+    sim.buildMultigrid(levels=3, smoother=5, coarseSolver=2, Ainv=1, times=1)
+    z = sim.vcycle(r)
+    res["vcycle_gs"] = z
+    res["vcycle_gs_residual"] = r - sim.spmv(0, z)
+    sim.restoreStrain()
+    log = sim.backwardEulerStep(**HOT_FLAGS)
+    res["hot_log"] = np.array([log["iterations"], int(log["converged"])])
+    res["hot_res"] = np.array(log["residual_norm"])
+    res["hot_dv0"] = sim.get_dv0()
+    sim.gridToParticles(DT)
+    # second step: PN-MGPCG (Newton + PCG on the assembled matrix, V-cycle preconditioner, tog.sh:49)
+    n, coord = begin_step(sim, ymin)
+    log = sim.backwardEulerStep(lsolver=2, matfree=0, mg_level=3, smoother=5, coarse_solver=2, project=1, linesearch=1, bcproject=1, usecn=1, cneps=1e-7)
+    res["pn_log"] = np.array([log["iterations"], log["total_linear_iterations"], int(log["converged"])])
+    sim.gridToParticles(DT)
+    p = sim.get_particles()
+    for k in ("X", "V", "F"):
+        res["P_" + k] = p[k]
+    return res
+
+
+def gpu_mg_worker(rank, world, port, out_dir):
+    """like gpu_worker, with the ghost ring on: assembled matrix, replicated coarse levels, take-over exchanges"""
+    import torch.distributed as dist
+    import hot_b200
+    from hot_b200.dist import host_partition, split_slabs
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    sc = scene()
+    sel = split_slabs(sc["X"], world)[rank]
+    sim = hot_b200.MpmSimulationB200(sc["dx"], device=0)
+    host_partition(sim)
+    sim.set_ghost_ring(True)
+    ymin = int(np.floor(sc["X"][:, 1].min() / sc["dx"] - 0.5))
+    res = run_mg(sim, sc, sel, ymin)
+    res["sel"] = sel
+    part = sim.get_partition()
+    res["part"] = np.array([part[k] for k in ("rank", "world", "neighbors", "shared_pages", "exchange_pages", "owned_nodes", "global_nodes", "particles")])
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)
+    dist.destroy_process_group()
+
+
 def gpu_worker(rank, world, port, out_dir):
     """partitioned run on ONE physical GPU: every rank opens its own handle on cuda:0 with ITS slab of the particles; the library's
     collectives are served by gloo on host copies (hot_b200.dist.host_partition) - NCCL cannot run two ranks on one device"""
@@ -198,4 +267,4 @@ def cpu_worker(rank, world, port, out_dir):
 
 if __name__ == "__main__":
     kind, rank, world, port, out_dir = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
-    {"gpu": gpu_worker, "nccl": nccl_worker, "cpu": cpu_worker}[kind](rank, world, port, out_dir)
+    {"gpu": gpu_worker, "gpu_mg": gpu_mg_worker, "nccl": nccl_worker, "cpu": cpu_worker}[kind](rank, world, port, out_dir)
