@@ -178,7 +178,11 @@ def nccl_worker(rank, world, port, out_dir):
     sim = hot_b200.MpmSimulationB200(sc["dx"], device=rank)
     nccl_partition(sim, torch.device("cuda", rank))
     ymin = int(np.floor(sc["X"][:, 1].min() / sc["dx"] - 0.5))
-    res = run_object(sim, sc, sel, ymin)
+    if os.environ.get("HOT_TEST_MG") == "1":                       # the assembled-matrix / multigrid path (ghost ring on)
+        sim.set_ghost_ring(True)
+        res = run_mg(sim, sc, sel, ymin)
+    else:
+        res = run_object(sim, sc, sel, ymin)
     res["sel"] = sel
     res["transport"] = np.array(sim.get_transport())
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)

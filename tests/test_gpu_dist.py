@@ -13,6 +13,14 @@ import dist_worker
 pytestmark = pytest.mark.gpu
 
 
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
 @pytest.fixture(scope="module")
 def single(hot):
     sc = dist_worker.scene()
@@ -63,14 +71,6 @@ def test_partitioned_object_matches_single_gpu(single, tmp_path, world):
     assert (seen >= 1).all() and (seen > 1).any()                                  # all nodes covered, some shared
 
 
-def _n_gpus():
-    try:
-        import torch
-        return torch.cuda.device_count()
-    except Exception:
-        return 0
-
-
 @pytest.mark.skipif(_n_gpus() < 2, reason="one rank per physical GPU: needs >= 2 GPUs (gpurun --gpus 2)")
 def test_peer_memory_transport_equals_nccl_transport(single, tmp_path):
     """the shared-page exchange through peer memory (P2P stores into the neighbours' arenas + flags) and through grouped
@@ -112,7 +112,7 @@ def _match(skey_order, coord):
     return order[pos], pos
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, -2])
 def test_partitioned_multigrid_path_matches_single_gpu(single_mg, tmp_path, world):
     """Assembled matrix, Galerkin hierarchy and V-cycle of a partitioned object (ghost ring on): level 0 distributed (rows summed over
     the sharers, take-over exchange after every SpMV / Gauss-Seidel colour phase), levels >= 1 replicated (all-reduced Galerkin
@@ -120,7 +120,13 @@ def test_partitioned_multigrid_path_matches_single_gpu(single_mg, tmp_path, worl
     PCG coarse solve) must agree with the single-GPU object to rounding (1e-10); the Gauss-Seidel V-cycle sweeps blocks in the LOCAL
     node order, so it is compared as a solver: same contraction, HOT / PN-MGPCG converge to the same state with the same or nearly
     the same iteration counts."""
-    res = launch("gpu_mg", world, tmp_path, timeout=900)
+    if world < 0:                                                            # one rank per physical GPU, NCCL + peer-memory transport
+        if _n_gpus() < -world:
+            pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+        res = launch("nccl", -world, tmp_path, timeout=900, env={"HOT_TEST_MG": "1"})
+        assert all("peer memory" in str(r["transport"]) for r in res)
+    else:
+        res = launch("gpu_mg", world, tmp_path, timeout=900)
     S = single_mg
     def keyed(c):
         o = np.argsort(_key(c)); return _key(c)[o], o
