@@ -148,6 +148,7 @@ def load_library(path=LIB_PATH):
         "hot_build_diagonal": (C.c_int, [vp, C.c_int, vp]),
         "hot_build_mg": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
         "hot_mg_levels": (C.c_int, [vp]),
+        "hot_estimate_2norm": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double)]),
         "hot_get_level_dofs": (C.c_int, [vp, _c_int_p]),
         "hot_level_nnz_blocks": (C.c_int, [vp, C.c_int, _c_i64_p]),
         "hot_get_level_coords": (C.c_int, [vp, C.c_int, vp]),

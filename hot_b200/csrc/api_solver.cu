@@ -86,6 +86,7 @@ int hot_build_mg(hot_sim* s, int levels, int smoother, int coarse_solver, int Ai
     return build_mg(s, levels, smoother, coarse_solver, Ainv, times, levelscale, topomega);
 }
 int hot_mg_levels(hot_sim* s) { return s->mg_built ? s->mg_levels : 0; }
+int hot_estimate_2norm(hot_sim* s, int level, double* lmax_lmin) { return level_estimate_2norm(s, level, lmax_lmin); }
 int hot_get_level_dofs(hot_sim* s, int* dofs)
 {
     if (!s->mg_built) return fail(s, "hot_get_level_dofs: call hot_build_mg first");

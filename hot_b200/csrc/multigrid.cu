@@ -843,6 +843,22 @@ __global__ void k_xpay_dev(long n, const double* __restrict__ x, const double* _
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = x[i] + (num[0] / den[0]) * y[i];
 }
+__global__ void k_xpay(long n, const double* __restrict__ x, double b, double* __restrict__ y)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = x[i] + b * y[i];
+}
+__global__ void k_abs(long n, double* __restrict__ y)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fabs(y[i]);
+}
+// +-1 start vector of estimate2norm: a fixed hash of the entry index (the reference seeds rand() with the wall clock)
+__global__ void k_sign_pattern(long n, double* __restrict__ y)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = ((uint32_t)((size_t)i * 2654435761u) >> 16) & 1u ? 1.0 : -1.0;
+}
 __global__ void k_scale(long n, double a, double* __restrict__ y)
 {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1208,6 +1224,73 @@ int smooth_cg(Sim* s, int level, double* u, double* r, int iterations)
     s->last_cg_iters = cnt;
     return 0;
 }
+// chebyshev_smooth, MultigridPreconditioner.h:227-264
+int smooth_chebyshev(Sim* s, int level, double* u, double* r, int iterations)
+{
+    MGLevel& L = *s->levels[level];
+    const long m = 3L * L.n;
+    double* p = L.tmp.p;
+    const double d = (L.lMax + L.lMin) / 2, c = (L.lMax - L.lMin) / 2;
+    int cnt = 1;
+    iterations--;
+    RC(mg_scale(s, L, r, p));
+    double alpha = 1 / d, beta;
+    RC(vec_copy(s, m, p, L.du.p));
+    RC(level_spmv(s, level, L.du.p, L.dAu.p));
+    RC(level_project(s, level, L.dAu.p));
+    RC(vec_axpy(s, m, alpha, L.du.p, u));
+    RC(vec_axpy(s, m, -alpha, L.dAu.p, r));
+    for (; iterations-- > 0; ++cnt) {
+        RC(mg_scale(s, L, r, p));
+        beta = 0.5 * c * c * alpha * alpha;
+        if (cnt > 1) beta *= 0.5;
+        alpha = 1 / (d - beta / alpha);
+        k_xpay<<<nblk(m), TPB, 0, s->stream>>>(m, p, beta, L.du.p);
+        HOT_LAUNCHED(s);
+        RC(level_spmv(s, level, L.du.p, L.dAu.p));
+        RC(level_project(s, level, L.dAu.p));
+        RC(vec_axpy(s, m, alpha, L.du.p, u));
+        RC(vec_axpy(s, m, -alpha, L.dAu.p, r));
+    }
+    return 0;
+}
+// SquareMatrix::estimate2norm, SquareMatrix.h:375-475 (power iteration on A A; lMin = lMax / 30 "experience")
+int estimate2norm(Sim* s, int level, double tol = 1e-6)
+{
+    MGLevel& L = *s->levels[level];
+    const long m = 3L * L.n;
+    double *v = L.du.p, *x = L.dAu.p, *sc = s->red_out.p;
+    const bool plain = s->dot_plain;
+    s->dot_plain = level > 0;
+    k_sign_pattern<<<nblk(m), TPB, 0, s->stream>>>(m, v);
+    HOT_LAUNCHED(s);
+    RC(level_spmv(s, level, v, x));
+    k_abs<<<nblk(m), TPB, 0, s->stream>>>(m, x);
+    HOT_LAUNCHED(s);
+    double xx, vv;
+    RC(vec_dot(s, m, x, x, sc, &xx));
+    double e = sqrt(xx), e0 = 0;
+    if (e == 0) {
+        L.lMin = L.lMax = 0;
+        s->dot_plain = plain;
+        return 0;
+    }
+    RC(vec_scale(s, m, 1.0 / e, x));
+    for (int iter = 0; iter < 512 && fabs(e - e0) > tol * e; ++iter) {
+        e0 = e;
+        RC(level_spmv(s, level, x, v));
+        RC(level_spmv(s, level, v, x));
+        RC(vec_dot(s, m, x, x, sc, &xx));
+        RC(vec_dot(s, m, v, v, sc + 1, &vv));
+        const double normx = sqrt(xx);
+        e = normx / sqrt(vv);
+        RC(vec_scale(s, m, 1.0 / normx, x));
+    }
+    L.lMax = e;
+    L.lMin = e / 30;
+    s->dot_plain = plain;
+    return 0;
+}
 template <int THREADS, bool STREAM>
 int launch_gs_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
 {
@@ -1405,13 +1488,24 @@ int columns_from_coords(Sim* s, MGLevel& L)
     return 0;
 }
 
+int level_estimate_2norm(Sim* s, int level, double* lmax_lmin)
+{
+    if (!s->mg_built || level < 0 || level >= s->mg_levels) return fail(s, "estimate2norm: bad level (call hot_build_mg first)");
+    int rc = estimate2norm(s, level);
+    if (rc) return rc;
+    lmax_lmin[0] = s->levels[level]->lMax;
+    lmax_lmin[1] = s->levels[level]->lMin;
+    return 0;
+}
+
 int build_mg(Sim* s, int levels, int smoother, int coarse_solver, int Ainv, int times, int levelscale, double topomega)
 {
     if (!s->matrix_built) return fail(s, "buildMultigrid: call hot_build_matrix first");
     if (levels < 1 || levels > 10) return fail(s, "Level depth exceeds 10! Too Deep!");
     if (!s->matrix_bcproject && levels > 1) return fail(s, "multigrid needs the BC-projected system (ImplicitSolver.h:339)");
     for (int k : {smoother, coarse_solver})
-        if (!(k == 0 || k == 1 || k == 2 || k == 5)) return fail(s, "No proper smoother is selected! (supported: 0 Jacobi, 1 optimal Jacobi, 2 PCG, 5 GS)");
+        if (!(k == 0 || k == 1 || k == 2 || k == 5 || k == 6))
+            return fail(s, "No proper smoother is selected! (supported: 0 Jacobi, 1 optimal Jacobi, 2 PCG, 5 GS, 6 Chebyshev)");
     if (!(Ainv == 0 || Ainv == 1)) return fail(s, "The Dinv function picked doesn't exist.");
     KTime t(s, KC_TRANSFER);
     s->mg_levels = levels; s->mg_smoother = smoother; s->mg_coarse = coarse_solver; s->mg_Ainv = Ainv; s->mg_times = times;
@@ -1421,11 +1515,14 @@ int build_mg(Sim* s, int levels, int smoother, int coarse_solver, int Ainv, int 
     const bool colors = smoother == 5 || coarse_solver == 5;
     RC(build_coord_map(s, *s->levels[0]));
     RC(finish_level(s, *s->levels[0], Ainv, colors));
+    // estimate2norm where the Chebyshev smoother will run (MultigridPreconditioner.h:610-611,682-683)
+    if ((coarse_solver == 6 && levels == 1) || (smoother == 6 && levels > 1)) RC(estimate2norm(s, 0));
     if (s->world > 1 && !s->ghost_ring) return fail(s, "buildMultigrid on a partitioned object needs the ghost ring (hot_set_ghost_ring)");
     for (int l = 0; l + 1 < levels; ++l) {
         if (l == 0 && s->world > 1) RC(coarsen_dist(s, *s->levels[0], *s->levels[1]));
         else RC(coarsen(s, *s->levels[l], *s->levels[l + 1]));
         RC(finish_level(s, *s->levels[l + 1], Ainv, colors));
+        if ((coarse_solver == 6 && l + 2 == levels) || (smoother == 6 && l + 2 < levels)) RC(estimate2norm(s, l + 1));
     }
     for (int l = 0; l < levels; ++l)
         if (!colors) s->levels[l]->n_blocks = 0;
@@ -1483,7 +1580,8 @@ int level_smooth(Sim* s, int level, int kind, double* u, double* r, int iteratio
     case 1: rc = smooth_optimal_jacobi(s, level, u, r, iterations, tolerance); break;
     case 2: rc = smooth_cg(s, level, u, r, iterations); break;
     case 5: rc = smooth_gs(s, level, u, r, iterations); break;
-    default: rc = fail(s, "No proper smoother is selected! (supported: 0 Jacobi, 1 optimal Jacobi, 2 PCG, 5 GS)");
+    case 6: rc = smooth_chebyshev(s, level, u, r, iterations); break;
+    default: rc = fail(s, "No proper smoother is selected! (supported: 0 Jacobi, 1 optimal Jacobi, 2 PCG, 5 GS, 6 Chebyshev)");
     }
     s->dot_plain = false;
     return rc;

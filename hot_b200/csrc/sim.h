@@ -110,6 +110,7 @@ struct MGLevel {
     DevBuf<double> gs_sval[2];
     int gs_chunks[2] = {0, 0};
     DevBuf<int> gs_seq, gs_rank, gs_block_start; // node ids in sweep order; rank of a node; block b = gs_seq[start[b]..start[b+1])
+    double lMax = 1e2, lMin = 1e-8; // SquareMatrix::lMax / lMin (SquareMatrix.h:37), set by estimate2norm for the Chebyshev smoother
     int n_blocks = 0;
     int color_first_block[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     // transfer to the next coarser level: P rows (8 parents per fine node), R = P^T rows (<= 27 children, padded to 32)
@@ -392,6 +393,7 @@ int level_prolong(Sim* s, int level, const double* coarse, double* fine);
 int level_smooth(Sim* s, int level, int kind, double* u, double* r, int iterations, double tolerance);
 int vcycle(Sim* s, const double* in, double* out, bool timed);
 int build_coord_map(Sim* s, MGLevel& L);
+int level_estimate_2norm(Sim* s, int level, double* lmax_lmin); // SquareMatrix::estimate2norm of a level, [lMax, lMin]
 int columns_from_coords(Sim* s, MGLevel& L); // partitioned assembly: column ids of the non-zero blocks from the node coordinates
 // vector ops (multigrid.cu)
 int vec_axpy(Sim* s, long n, double a, const double* x, double* y); // y += a x

@@ -215,6 +215,109 @@ int inexact_pcg(Objective& O, double* x, const double* b, double tolerance, int 
     return 0;
 }
 
+
+// Minres::solve, Lib/Ziran/Math/Linear/Minres.h:71-176 (-lsolver 1); Givens rotations of Givens.h:73-141 on the host, the seven
+// Lanczos / direction vectors in HBM (the L-BFGS ring slots, unused by a Newton solve); two scalar read-backs per iteration
+__global__ void k_minres_m(long n, double delta, double epsilon, double inv_gamma, const double* __restrict__ mkm1, const double* __restrict__ mkm2,
+    double tk, double* __restrict__ mk, double* __restrict__ x)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = (mk[i] - delta * mkm1[i] - epsilon * mkm2[i]) * inv_gamma;
+    mk[i] = v;
+    x[i] += tk * v;
+}
+struct GivensRot {
+    double c = 1, s = 0;
+    void compute(double a, double b)
+    {
+        const double d = a * a + b * b, sq = std::sqrt(d);
+        c = 1; s = 0;
+        if (sq) { const double t = 1 / sq; c = a * t; s = -b * t; }
+    }
+    void row_rotation(double (&v)[2]) const
+    {
+        const double t1 = v[0], t2 = v[1];
+        v[0] = c * t1 - s * t2;
+        v[1] = s * t1 + c * t2;
+    }
+};
+int minres_solve(Objective& O, double* x, const double* b, double relative_tolerance, double tolerance, int max_iterations, int* iters)
+{
+    Sim* s = O.s;
+    const long m = O.m;
+    double *mk = O.vec(V_RING0), *mkm1 = O.vec(V_RING0 + 1), *mkm2 = O.vec(V_RING0 + 2), *z = O.vec(V_RING0 + 3), *qkp1 = O.vec(V_RING0 + 4),
+           *qk = O.vec(V_RING0 + 5), *qkm1 = O.vec(V_RING0 + 6);
+    double* sc = s->red_out.p + 24;
+    KTime t(s, KC_BLAS1);
+    for (double* v : {mk, mkm1, mkm2, qk, qkm1}) RC(vec_zero(s, m, v));
+    GivensRot Gk, Gkm1, Gkm2;
+    double gamma = 0, delta = 0, epsilon = 0, beta_kp1 = 0, alpha_k = 0, beta_k = 0, tk = 0, d;
+    RC(obj_multiply(O, x, qkp1));
+    k_sub<<<nblk(m), TPB, 0, s->stream>>>(m, b, qkp1, qkp1);
+    HOT_LAUNCHED(s);
+    RC(bc_project(s, qkp1));
+    RC(obj_precondition(O, qkp1, z));
+    RC(vec_dot(s, m, z, qkp1, sc, &d));
+    double rpn = std::sqrt(d);
+    beta_kp1 = rpn;
+    const double local_tolerance = std::min(relative_tolerance * rpn, tolerance);
+    if (iters) *iters = 0;
+    if (rpn < local_tolerance) return 0;
+    if (rpn > 0) {
+        RC(vec_scale(s, m, 1.0 / beta_kp1, qkp1));
+        RC(vec_scale(s, m, 1.0 / beta_kp1, z));
+    }
+    double rhs2[2] = {rpn, 0};
+    for (int k = 0; k < max_iterations; k++) {
+        if (rpn < local_tolerance) {
+            if (iters) *iters = k;
+            return 0;
+        }
+        std::swap(mkm2, mkm1);
+        std::swap(mkm1, mk);
+        RC(vec_copy(s, m, z, mk));
+        beta_k = beta_kp1;
+        std::swap(qkm1, qkp1);
+        std::swap(qkm1, qk);
+        RC(obj_multiply(O, mk, qkp1));
+        RC(bc_project(s, qkp1));
+        RC(vec_dot(s, m, mk, qkp1, sc, &alpha_k));
+        RC(vec_axpy(s, m, -alpha_k, qk, qkp1));
+        RC(vec_axpy(s, m, -beta_k, qkm1, qkp1));
+        RC(obj_precondition(O, qkp1, z));
+        RC(vec_dot(s, m, z, qkp1, sc + 1, &d));
+        beta_kp1 = std::sqrt(std::max(0.0, d));
+        if (beta_kp1 > 0) {
+            RC(vec_scale(s, m, 1.0 / beta_kp1, qkp1));
+            RC(vec_scale(s, m, 1.0 / beta_kp1, z));
+        }
+        { // applyAllPreviousGivensRotationsAndDetermineNewGivens, :147-176
+            Gkm2 = Gkm1;
+            Gkm1 = Gk;
+            double ep[2] = {0, beta_k};
+            Gkm2.row_rotation(ep);
+            epsilon = ep[0];
+            double dz[2] = {ep[1], alpha_k};
+            Gkm1.row_rotation(dz);
+            delta = dz[0];
+            double tmp[2] = {dz[1], beta_kp1};
+            Gk.compute(tmp[0], tmp[1]);
+            Gk.row_rotation(tmp);
+            gamma = tmp[0];
+            Gk.row_rotation(rhs2);
+            tk = rhs2[0];
+            const double res = rhs2[1];
+            rhs2[0] = res; rhs2[1] = 0;
+            rpn = res < 0 ? -res : res;
+        }
+        k_minres_m<<<nblk(m), TPB, 0, s->stream>>>(m, delta, epsilon, 1.0 / gamma, mkm1, mkm2, tk, mk, x);
+        HOT_LAUNCHED(s);
+    }
+    if (iters) *iters = max_iterations;
+    return 0;
+}
+
 // force_project: HinvApproxInit always assembles buildMatrix<true> (ImplicitSolver.h:337); --bcproject then only decides
 // whether level 0 additionally carries objective.project (MultigridPreconditioner.h:695-699)
 int rebuild_matrix_and_preconditioner(Objective& O, bool force_project = false)
@@ -229,7 +332,7 @@ int rebuild_matrix_and_preconditioner(Objective& O, bool force_project = false)
 }
 
 // computeStep, ImplicitSolver.h:355-432 (lsolver 2)
-int compute_step(Objective& O, double* ddv, double* residual, double cg_tolerance)
+int compute_step(Objective& O, double* ddv, double* residual, double cg_tolerance, double rel_tol)
 {
     Sim* s = O.s;
     const hot_solver_options& o = O.opt;
@@ -243,7 +346,9 @@ int compute_step(Objective& O, double* ddv, double* residual, double cg_toleranc
         O.precond = 1;
     }
     int iters = 0;
-    RC(inexact_pcg(O, ddv, residual, cg_tolerance, o.max_cg_iterations, &iters));
+    // -lsolver 1: MINRES with minres.setTolerance(1) of the objective's constructor (ImplicitSolver.h:87,406-411); 2: inexact PCG
+    if (o.lsolver == 1) RC(minres_solve(O, ddv, residual, rel_tol, 1.0, o.max_cg_iterations, &iters));
+    else RC(inexact_pcg(O, ddv, residual, cg_tolerance, o.max_cg_iterations, &iters));
     if (O.log) {
         O.log->total_linear_iterations += iters;
         if (O.log->n_log > 0) O.log->linear_iterations[O.log->n_log - 1] = iters;
@@ -253,7 +358,7 @@ int compute_step(Objective& O, double* ddv, double* residual, double cg_toleranc
 }
 
 // ExtendedNewtonsMethod::solve; x is simulation.dv itself like in the reference
-int newton_solve(Objective& O, double cg_tolerance)
+int newton_solve(Objective& O, double cg_tolerance, double tolerance)
 {
     Sim* s = O.s;
     double* x = s->dv.p;
@@ -263,12 +368,14 @@ int newton_solve(Objective& O, double cg_tolerance)
         RC(obj_compute_residual(O, residual));
         if (O.log) O.log->iterations = it;
         bool exit = false;
-        RC(should_exit_by_cn(O, residual, &exit, nullptr));
+        double l2 = 0;
+        RC(should_exit_by_cn(O, residual, &exit, &l2));
         if (exit) {
             if (O.log) O.log->converged = 1;
             return 0;
         }
-        RC(compute_step(O, step, residual, cg_tolerance));
+        // "gast15" suggested relative tolerance of the linear solve (ExtendedNewtonsMethod.h:58), used by MINRES
+        RC(compute_step(O, step, residual, cg_tolerance, std::min(0.5, std::sqrt(std::max(l2, tolerance)))));
         RC(bc_rotate(s, step, true));
         RC(vec_axpy(s, O.m, 1.0, step, x));
         RC(bc_rotate(s, step, false));
@@ -411,9 +518,9 @@ int hot_backward_euler_step(hot_sim* s, const hot_solver_options* opt, hot_solve
     if (!opt) return fail(s, "hot_backward_euler_step: null options");
     if (log) std::memset(log, 0, sizeof *log);
     if (!s->p2g_done) return fail(s, "backwardEulerStep: call hot_p2g (and hot_set_bc) first");
-    if (opt->lsolver != 2 && opt->lsolver != 3) return fail(s, "lsolver must be 2 (Newton + PCG) or 3 (L-BFGS)");
+    if (opt->lsolver != 1 && opt->lsolver != 2 && opt->lsolver != 3) return fail(s, "lsolver must be 1 (Newton + MINRES), 2 (Newton + PCG) or 3 (L-BFGS)");
     if (opt->lsolver == 3 && opt->matfree) return fail(s, "LBFGS only works with project & with-matrix (Projects/multigrid/README:13-15)");
-    if (s->world > 1 && !(opt->lsolver == 2 && opt->matfree) && !s->ghost_ring)
+    if (s->world > 1 && !(opt->lsolver != 3 && opt->matfree) && !s->ghost_ring)
         return fail(s, "partitioned runs with an assembled matrix (-lsolver 3, -lsolver 2 without --matfree) need the ghost ring: hot_set_ghost_ring(h, 1) before the sort");
     Objective O;
     O.s = s;
@@ -460,7 +567,7 @@ int hot_backward_euler_step(hot_sim* s, const hot_solver_options* opt, hot_solve
     O.updated = false;
     rc = vec_copy(s, O.m, s->dv.p, O.dv0);
     if (rc) return rc;
-    rc = opt->lsolver != 3 ? newton_solve(O, cg_tol) : lbfgs_solve(O);
+    rc = opt->lsolver != 3 ? newton_solve(O, cg_tol, tol) : lbfgs_solve(O);
     if (rc) return rc;
     // keep ImplicitSolverObjective::dv0 readable (hot_get_dv0)
     HOT_CUDA(s->dv0_keep.reserve(O.m > 0 ? O.m : 1));

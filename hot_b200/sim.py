@@ -290,6 +290,12 @@ class MpmSimulationB200:
     def buildMultigrid(self, levels=3, smoother=5, coarseSolver=2, Ainv=1, times=1, levelscale=0, topomega=0.1):
         self._check(self._lib.hot_build_mg(self._h, levels, smoother, coarseSolver, Ainv, times, levelscale, float(topomega)))
 
+    def estimate2norm(self, level):
+        """(lMax, lMin) of A_level: SquareMatrix::estimate2norm"""
+        out = (C.c_double * 2)()
+        self._check(self._lib.hot_estimate_2norm(self._h, level, out))
+        return float(out[0]), float(out[1])
+
     def level_dofs(self):
         L = self._lib.hot_mg_levels(self._h)
         out = (C.c_int * max(L, 1))()

@@ -256,6 +256,11 @@ int hot_build_diagonal(hot_sim* h, int Ainv, double* diag_inv /* 9 per node, nul
  * 2 PCG, 5 GS as in setup_logic :480-522; 6 Chebyshev / 7 IC are not provided) */
 int hot_build_mg(hot_sim* h, int levels, int smoother, int coarse_solver, int Ainv, int times, int levelscale, double topomega);
 int hot_mg_levels(hot_sim* h);
+/* SquareMatrix::estimate2norm (Projects/multigrid/SquareMatrix.h:375-475): power iteration for the 2-norm of A_level, out = {lMax,
+ * lMin = lMax / 30}; the Chebyshev smoother (-smoother 6, MultigridPreconditioner.h:227-264) uses them.  hot_build_mg runs it on the
+ * levels where Chebyshev will be applied (:610-611, :682-683); the start vector is a fixed +-1 pattern (the reference seeds rand()
+ * with the wall clock). */
+int hot_estimate_2norm(hot_sim* h, int level, double* lmax_lmin);
 int hot_get_level_dofs(hot_sim* h, int* dofs);
 int hot_get_level_coords(hot_sim* h, int level, int* coord3);
 /* number of structurally non-zero 3x3 blocks of A_level (the reference stores 125 per row regardless) */
@@ -292,7 +297,7 @@ int hot_op_bench(hot_sim* h, int op, int level, int reps, double* ms_total);
  * (MultigridSimulation.h:97-99: newton(objective, 1, 3), lbfgs(objective, 1, 10000); ImplicitSolver.h:78: cg(10000)).
  * Field names follow the command-line flags of Projects/multigrid/main.cpp:40-84. */
 typedef struct hot_solver_options {
-    int lsolver;        /* -lsolver: 2 = Newton + inexact PCG (PN-PCG / PN-MGPCG), 3 = L-BFGS around the V-cycle (HOT) */
+    int lsolver;        /* -lsolver: 1 = Newton + MINRES, 2 = Newton + inexact PCG (PN-PCG / PN-MGPCG), 3 = L-BFGS around the V-cycle (HOT) */
     int matfree;        /* --matfree: matrix-free apply + block-Jacobi (lsolver 2 only, README:13-15) */
     int project;        /* --project: PSD-project the particle Hessians */
     int bcproject;      /* --bcproject: BC-project the assembled system */

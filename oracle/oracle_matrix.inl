@@ -18,6 +18,7 @@ struct SqMat {
     std::vector<double> diagonalVal, diagonalEntry, diagonalBlock;
     std::array<std::vector<std::vector<int>>, 8> coloredBlockDofs;
     std::vector<std::array<int, 3>> colorOrder;
+    double lMin = 1e-8, lMax = 1e2; // SquareMatrix.h:37, set by estimate2norm
     int rows() const { return colsize ? (int)(entryCol.size() / colsize) : 0; }
 };
 
@@ -265,6 +266,63 @@ void optimal_jacobi_smooth(Sim* s, MatrixState& M, int level, Vd& u, Vd& r, Vd& 
         vec_axpy(r, -omega, dAu);
     }
 }
+// chebyshev_smooth, MultigridPreconditioner.h:227-264: d, c from the 2-norm estimate of A (lMax, lMin = lMax / 30), applied to D^-1 A
+void chebyshev_smooth(Sim* s, MatrixState& M, int level, Vd& u, Vd& r, Vd& du, Vd& dAu, int iterations)
+{
+    const SqMat& A = M.sysmats[level];
+    Vd& p = M.tmps[level];
+    const double d = (A.lMax + A.lMin) / 2, c = (A.lMax - A.lMin) / 2;
+    int cnt = 1;
+    iterations--;
+    mg_scale(M, A, r, p);
+    double alpha = 1 / d, beta;
+    du = p;
+    sq_multiply(A, du.data(), dAu.data());
+    mg_project(s, M, level, dAu);
+    vec_axpy(u, alpha, du);
+    vec_axpy(r, -alpha, dAu);
+    for (; iterations-- > 0; ++cnt) {
+        mg_scale(M, A, r, p);
+        beta = 0.5 * c * c * alpha * alpha;
+        if (cnt > 1) beta *= 0.5;
+        alpha = 1 / (d - beta / alpha);
+        for (size_t i = 0; i < du.size(); ++i) du[i] = p[i] + beta * du[i];
+        sq_multiply(A, du.data(), dAu.data());
+        mg_project(s, M, level, dAu);
+        vec_axpy(u, alpha, du);
+        vec_axpy(r, -alpha, dAu);
+    }
+}
+// SquareMatrix::estimate2norm (SquareMatrix.h:375-475): power iteration on A A from a +-1 start vector.  The reference seeds the
+// start with srand(time(NULL)); any start converges to the same 2-norm within `tol`, here a fixed hash of the entry index.
+inline double sign_pattern(size_t t) { return ((uint32_t)(t * 2654435761u) >> 16) & 1u ? 1.0 : -1.0; }
+void estimate2norm(SqMat& A, double tol = 1e-6)
+{
+    const int MaxIters = 512;
+    const size_t m = 3 * (size_t)A.rows();
+    Vd v(m), x(m);
+    for (size_t t = 0; t < m; ++t) v[t] = sign_pattern(t);
+    sq_multiply(A, v.data(), x.data());
+    for (auto& a : x) a = std::fabs(a);
+    double e = std::sqrt(vec_dot(x, x));
+    if (e == 0) {
+        A.lMin = A.lMax = 0;
+        return;
+    }
+    for (auto& a : x) a /= e;
+    double e0 = 0;
+    for (int iter = 0; iter < MaxIters && std::fabs(e - e0) > tol * e; iter++) {
+        e0 = e;
+        sq_multiply(A, x.data(), v.data());
+        sq_multiply(A, v.data(), x.data());
+        const double normx = std::sqrt(vec_dot(x, x));
+        e = normx / std::sqrt(vec_dot(v, v));
+        for (auto& a : x) a /= normx;
+    }
+    A.lMax = e;
+    A.lMin = A.lMax / 30; // "experience"
+}
+
 // cg_smooth, :190-226
 void cg_smooth(Sim* s, MatrixState& M, int level, Vd& u, Vd& r, Vd& du, Vd& dAu, int iterations)
 {
@@ -359,7 +417,8 @@ int run_smoother(Sim* s, MatrixState& M, int kind, int level, Vd& u, Vd& r, Vd& 
     case 1: optimal_jacobi_smooth(s, M, level, u, r, du, dAu, iterations, tolerance); return 0;
     case 2: cg_smooth(s, M, level, u, r, du, dAu, iterations); return 0;
     case 5: gs_smooth(s, M, level, u, r, du, dAu, iterations); return 0;
-    default: return fail(s, "No proper smoother is selected! (supported: 0 Jacobi, 1 optimal Jacobi, 2 PCG, 5 GS)");
+    case 6: chebyshev_smooth(s, M, level, u, r, du, dAu, iterations); return 0;
+    default: return fail(s, "No proper smoother is selected! (supported: 0 Jacobi, 1 optimal Jacobi, 2 PCG, 5 GS, 6 Chebyshev)");
     }
 }
 
@@ -605,6 +664,7 @@ int orc_build_mg(void* h, int levels, int smoother, int coarseSolver, int Ainv, 
     M.coords[0] = M.id2coord;
     const bool colors = coarseSolver == 5 || smoother == 5;
     if (colors) mark_colors(M.coords[0], M.sysmats[0]);
+    if ((coarseSolver == 6 && levels == 1) || (smoother == 6 && levels > 1)) estimate2norm(M.sysmats[0]); // :610-611
     M.dofs.assign(1, (int)M.id2coord.size() / 3);
     const double w1d[2][3] = {{0.0, 1.0, 0.0}, {0.0, 0.5, 0.5}}; // linear_weight_template :445-466
     const unsigned long long seed = 100007;
@@ -647,6 +707,7 @@ int orc_build_mg(void* h, int levels, int smoother, int coarseSolver, int Ainv, 
         sq_build_product(M.sysmats[level + 1], M.resmats[level], AP);
         sq_build_diagonal(M.sysmats[level + 1], Ainv);
         if (colors) mark_colors(M.coords[level + 1], M.sysmats[level + 1]);
+        if ((coarseSolver == 6 && level + 2 == levels) || (smoother == 6 && level + 2 < levels)) estimate2norm(M.sysmats[level + 1]); // :682-683
         M.dofs.push_back(nc);
     }
     // MultigridOperator::init :83-118
@@ -660,6 +721,14 @@ int orc_build_mg(void* h, int levels, int smoother, int coarseSolver, int Ainv, 
 }
 
 int orc_mg_levels(void* h) { return (int)matrix_of((Sim*)h).sysmats.size(); }
+int orc_estimate_2norm(void* h, int level, double* lmax_lmin)
+{
+    MatrixState& M = matrix_of((Sim*)h);
+    if (level < 0 || level >= (int)M.sysmats.size()) return -1;
+    estimate2norm(M.sysmats[level]);
+    lmax_lmin[0] = M.sysmats[level].lMax; lmax_lmin[1] = M.sysmats[level].lMin;
+    return 0;
+}
 int orc_get_level_dofs(void* h, int* dofs)
 {
     MatrixState& M = matrix_of((Sim*)h);

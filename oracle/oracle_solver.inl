@@ -152,6 +152,91 @@ int inexact_pcg(Sim* s, ObjectiveState& O, Vd& x, const Vd& b, double tolerance,
     return 0;
 }
 
+
+// Minres::solve, Lib/Ziran/Math/Linear/Minres.h:71-176 (Givens rotations: Givens.h:73-141); tolerance = min(relative * |r0|_Minv, absolute)
+struct GivensRot {
+    double c = 1, s = 0;
+    void compute(double a, double b)
+    {
+        const double d = a * a + b * b, sq = std::sqrt(d);
+        c = 1; s = 0;
+        if (sq) { const double t = 1 / sq; c = a * t; s = -b * t; }
+    }
+    void row_rotation(double (&v)[2]) const
+    {
+        const double t1 = v[0], t2 = v[1];
+        v[0] = c * t1 - s * t2;
+        v[1] = s * t1 + c * t2;
+    }
+};
+int minres_solve(Sim* s, ObjectiveState& O, Vd& x, const Vd& b, double relative_tolerance, double tolerance, int max_iterations, int* iters)
+{
+    const size_t m = b.size();
+    Vd mk(m, 0.0), mkm1(m, 0.0), mkm2(m, 0.0), z(m, 0.0), qkp1(m, 0.0), qk(m, 0.0), qkm1(m, 0.0);
+    GivensRot Gk, Gkm1, Gkm2;
+    double gamma = 0, delta = 0, epsilon = 0, beta_kp1 = 0, alpha_k = 0, beta_k = 0, tk = 0;
+    int rc = obj_multiply(s, O, x, qkp1);
+    if (rc) return rc;
+    for (size_t i = 0; i < m; ++i) qkp1[i] = b[i] - qkp1[i];
+    bc_project(s, qkp1.data());
+    rc = obj_precondition(s, O, qkp1, z);
+    if (rc) return rc;
+    double rpn = std::sqrt(vec_dot(z, qkp1));
+    beta_kp1 = rpn;
+    const double local_tolerance = std::min(relative_tolerance * rpn, tolerance);
+    if (iters) *iters = 0;
+    if (rpn < local_tolerance) return 0;
+    if (rpn > 0)
+        for (size_t i = 0; i < m; ++i) { qkp1[i] /= beta_kp1; z[i] /= beta_kp1; }
+    double rhs2[2] = {rpn, 0};
+    for (int k = 0; k < max_iterations; k++) {
+        if (rpn < local_tolerance) {
+            if (iters) *iters = k;
+            return 0;
+        }
+        mkm2.swap(mkm1);
+        mkm1.swap(mk);
+        mk = z;
+        beta_k = beta_kp1;
+        qkm1.swap(qkp1);
+        qkm1.swap(qk);
+        rc = obj_multiply(s, O, mk, qkp1);
+        if (rc) return rc;
+        bc_project(s, qkp1.data());
+        alpha_k = vec_dot(mk, qkp1);
+        for (size_t i = 0; i < m; ++i) qkp1[i] -= alpha_k * qk[i];
+        for (size_t i = 0; i < m; ++i) qkp1[i] -= beta_k * qkm1[i];
+        rc = obj_precondition(s, O, qkp1, z);
+        if (rc) return rc;
+        beta_kp1 = std::sqrt(std::max(0.0, vec_dot(z, qkp1)));
+        if (beta_kp1 > 0)
+            for (size_t i = 0; i < m; ++i) { qkp1[i] /= beta_kp1; z[i] /= beta_kp1; }
+        { // applyAllPreviousGivensRotationsAndDetermineNewGivens :147-176
+            Gkm2 = Gkm1;
+            Gkm1 = Gk;
+            double ep[2] = {0, beta_k};
+            Gkm2.row_rotation(ep);
+            epsilon = ep[0];
+            double dz[2] = {ep[1], alpha_k};
+            Gkm1.row_rotation(dz);
+            delta = dz[0];
+            double tmp[2] = {dz[1], beta_kp1};
+            Gk.compute(tmp[0], tmp[1]);
+            Gk.row_rotation(tmp);
+            gamma = tmp[0];
+            Gk.row_rotation(rhs2);
+            tk = rhs2[0];
+            const double res = rhs2[1];
+            rhs2[0] = res; rhs2[1] = 0;
+            rpn = res < 0 ? -res : res;
+        }
+        for (size_t i = 0; i < m; ++i) mk[i] = (mk[i] - delta * mkm1[i] - epsilon * mkm2[i]) / gamma;
+        for (size_t i = 0; i < m; ++i) x[i] += tk * mk[i];
+    }
+    if (iters) *iters = max_iterations;
+    return 0;
+}
+
 // force_project: HinvApproxInit always assembles buildMatrix<true> (ImplicitSolver.h:337); the --bcproject flag then only
 // decides whether level 0 additionally carries objective.project (MultigridPreconditioner.h:695-699)
 int rebuild_matrix_and_preconditioner(Sim* s, ObjectiveState& O, bool force_project = false)
@@ -166,7 +251,7 @@ int rebuild_matrix_and_preconditioner(Sim* s, ObjectiveState& O, bool force_proj
 }
 
 // computeStep, ImplicitSolver.h:355-432 (lsolver 2)
-int compute_step(Sim* s, ObjectiveState& O, Vd& ddv, Vd& residual, double /*rel_tol: stored but unused by the inexact CG*/, double cg_tolerance)
+int compute_step(Sim* s, ObjectiveState& O, Vd& ddv, Vd& residual, double rel_tol /* used by MINRES; the inexact CG derives its own */, double cg_tolerance)
 {
     std::fill(ddv.begin(), ddv.end(), 0.0);
     const hot_solver_options& o = O.opt;
@@ -181,7 +266,9 @@ int compute_step(Sim* s, ObjectiveState& O, Vd& ddv, Vd& residual, double /*rel_
         O.precond = 1;
     }
     int iters = 0;
-    int rc = inexact_pcg(s, O, ddv, residual, cg_tolerance, o.max_cg_iterations, &iters);
+    // -lsolver 1: MINRES with minres.setTolerance(1) of the objective's constructor (ImplicitSolver.h:87,406-411); -lsolver 2: inexact PCG
+    int rc = o.lsolver == 1 ? minres_solve(s, O, ddv, residual, rel_tol, 1.0, o.max_cg_iterations, &iters)
+                            : inexact_pcg(s, O, ddv, residual, cg_tolerance, o.max_cg_iterations, &iters);
     if (rc) return rc;
     if (O.log) {
         O.log->total_linear_iterations += iters;
@@ -332,7 +419,7 @@ int orc_backward_euler_step(void* h, const hot_solver_options* opt, hot_solve_lo
     O.opt = *opt;
     O.log = log;
     if (log) std::memset(log, 0, sizeof *log);
-    if (opt->lsolver != 2 && opt->lsolver != 3) return fail(s, "lsolver must be 2 (Newton + PCG) or 3 (L-BFGS)");
+    if (opt->lsolver != 1 && opt->lsolver != 2 && opt->lsolver != 3) return fail(s, "lsolver must be 1 (Newton + MINRES), 2 (Newton + PCG) or 3 (L-BFGS)");
     if (opt->lsolver == 3 && opt->matfree) return fail(s, "LBFGS only works with project & with-matrix (Projects/multigrid/README:13-15)");
     f.project = opt->project != 0;
     matrix_of(s).cneps = opt->cneps;

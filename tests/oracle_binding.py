@@ -269,6 +269,11 @@ def _add_matrix_methods(cls):
     def buildMultigrid(self, levels=3, smoother=5, coarseSolver=2, Ainv=1, times=1, levelscale=0, topomega=0.1):
         self._check(_lib.orc_build_mg(_vp(self._h), levels, smoother, coarseSolver, Ainv, times, levelscale, C.c_double(topomega)))
 
+    def estimate2norm(self, level):
+        out = (C.c_double * 2)()
+        self._check(_lib.orc_estimate_2norm(_vp(self._h), level, out))
+        return float(out[0]), float(out[1])
+
     def level_dofs(self):
         L = _lib.orc_mg_levels(_vp(self._h))
         out = (C.c_int * L)()

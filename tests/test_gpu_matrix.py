@@ -115,7 +115,24 @@ def test_smoother_parity(mg, level, kind, iters):
     _close(ug, uo); _close(rg, ro)
 
 
-@pytest.mark.parametrize("smoother,coarse", [(5, 2), (5, 5), (0, 2), (1, 0)])
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_chebyshev_smoother_and_2norm_estimate_parity(mg, level):
+    """-smoother 6 (chebyshev_smooth, MultigridPreconditioner.h:227-264) with the 2-norm estimate of SquareMatrix::estimate2norm
+    (SquareMatrix.h:375-475): same fixed start vector on both sides, so the power iterations agree step by step"""
+    g, o = mg
+    (gmax, gmin), (omax, omin) = g.estimate2norm(level), o.estimate2norm(level)
+    assert abs(gmax - omax) <= 1e-9 * omax and abs(gmin - omax / 30) <= 1e-9 * omax
+    n = o.level_dofs()[level]
+    rng = np.random.default_rng(60 + level)
+    r0 = rng.random((n, 3)) - 0.5
+    u0 = 0.01 * (rng.random((n, 3)) - 0.5)
+    for iters in (1, 4):
+        ug, rg = g.smooth(level, 6, u0, r0, iters)
+        uo, ro = o.smooth(level, 6, u0, r0, iters)
+        _close(ug, uo); _close(rg, ro)
+
+
+@pytest.mark.parametrize("smoother,coarse", [(5, 2), (5, 5), (0, 2), (1, 0), (6, 2)])
 def test_vcycle_parity(hot, oracle, smoother, coarse):
     g, o, _ = _pair(hot, oracle)
     for s in (g, o):

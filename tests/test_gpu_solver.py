@@ -46,6 +46,8 @@ CONFIGS = {
     "pn_pcg_mf": dict(lsolver=2, matfree=1, bcproject=0, mg_level=1),
     "pn_pcg": dict(lsolver=2, matfree=0, bcproject=0, mg_level=1),
     "pn_mgpcg": dict(lsolver=2, matfree=0, bcproject=1, mg_level=3),
+    "pn_minres_mf": dict(lsolver=1, matfree=1, bcproject=0, mg_level=1),            # -lsolver 1: Newton + MINRES (Minres.h)
+    "pn_mgminres": dict(lsolver=1, matfree=0, bcproject=1, mg_level=3),
     "hot": dict(lsolver=3, bcproject=1, mg_level=3),
     "hot_nolinesearch": dict(lsolver=3, bcproject=1, mg_level=3, linesearch=0, usecn=0, cneps=1e-6),
     "lbfgs_h": dict(lsolver=3, bcproject=0, mg_level=1, mg_times=10000, smoother=2, coarse_solver=2),

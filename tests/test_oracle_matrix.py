@@ -231,6 +231,32 @@ def test_jacobi_smoothers(mg):
     assert np.allclose(u.reshape(-1), x, rtol=1e-11, atol=1e-13 * np.abs(x).max())
 
 
+def test_chebyshev_smoother_and_2norm_estimate(mg):
+    """estimate2norm (SquareMatrix.h:375-475) against scipy's largest eigenvalue; chebyshev_smooth (MultigridPreconditioner.h:227-264)
+    against the recurrence written out in numpy"""
+    import scipy.sparse.linalg as spla
+    o, _ = mg
+    n = o.level_dofs()[1]
+    A = ell_to_csr(*o.level_matrix(1, 0), n)
+    lmax, lmin = o.estimate2norm(1)
+    exact = spla.eigsh(A, k=1, which="LA", return_eigenvectors=False)[0]
+    assert abs(lmax - exact) <= 2e-3 * exact and lmin == lmax / 30           # power iteration stopped at |de| <= 1e-6 e
+    _, Di = o.level_diagonal(1)
+    Minv = sp.block_diag(list(Di.reshape(n, 3, 3).transpose(0, 2, 1)), format="csr")
+    r0 = np.random.default_rng(19).random((n, 3)) - 0.5
+    u, r = o.smooth(1, 6, np.zeros((n, 3)), r0, iterations=4)
+    d, c = (lmax + lmin) / 2, (lmax - lmin) / 2
+    x = np.zeros(3 * n); rr = r0.reshape(-1).copy()
+    p = Minv @ rr; alpha = 1 / d; du = p.copy(); q = A @ du; x += alpha * du; rr -= alpha * q
+    for cnt in range(1, 4):
+        p = Minv @ rr
+        beta = 0.5 * c * c * alpha * alpha * (0.5 if cnt > 1 else 1.0)
+        alpha = 1 / (d - beta / alpha)
+        du = p + beta * du; q = A @ du; x += alpha * du; rr -= alpha * q
+    assert np.allclose(u.reshape(-1), x, rtol=1e-11, atol=1e-13 * np.abs(x).max())
+    assert np.allclose(r.reshape(-1), rr, rtol=1e-11, atol=1e-13 * np.abs(r0).max())
+
+
 def test_vcycle_is_spd_preconditioner(oracle):
     sc, o, bc = _setup(oracle, cells=(9, 10, 9))
     o.buildMatrix(bcproject=True)

@@ -51,6 +51,8 @@ CONFIGS = {
     "pn_pcg_mf": dict(lsolver=2, matfree=1, bcproject=0, mg_level=1),
     "pn_pcg": dict(lsolver=2, matfree=0, bcproject=0, mg_level=1),
     "pn_mgpcg": dict(lsolver=2, matfree=0, bcproject=1, mg_level=3),
+    "pn_minres_mf": dict(lsolver=1, matfree=1, bcproject=0, mg_level=1),            # -lsolver 1: Newton + MINRES (Minres.h)
+    "pn_mgminres": dict(lsolver=1, matfree=0, bcproject=1, mg_level=3),
     "hot": dict(lsolver=3, bcproject=1, mg_level=3),
     "lbfgs_h": dict(lsolver=3, bcproject=0, mg_level=1, mg_times=10000, smoother=2, coarse_solver=2),
 }
@@ -74,7 +76,7 @@ def test_backward_euler_converges(solves, name):
     assert log["residual_norm"][-1] < 1e-3 * log["residual_norm"][0]
     e = log["energy"]
     assert all(e[i + 1] <= e[i] + 1e-12 * abs(e[i]) for i in range(1, len(e) - 1))   # line search: monotone energy
-    assert log["matrix_builds"] == (0 if name == "pn_pcg_mf" else (1 if name in ("hot", "lbfgs_h") else log["iterations"]))
+    assert log["matrix_builds"] == (0 if name in ("pn_pcg_mf", "pn_minres_mf") else (1 if name in ("hot", "lbfgs_h") else log["iterations"]))
 
 
 def test_all_solvers_agree(solves):
