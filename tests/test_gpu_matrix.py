@@ -165,6 +165,6 @@ def test_mg_argument_errors(hot, oracle):
         g.buildMultigrid(levels=3)         # multigrid needs --bcproject (ImplicitSolver.h:339)
     g.buildMatrix(True)
     with pytest.raises(hot.HotError):
-        g.buildMultigrid(smoother=6)       # Chebyshev not provided
+        g.buildMultigrid(smoother=7)       # incomplete Cholesky (Eigen IncompleteCholesky) is not provided
     with pytest.raises(hot.HotError):
         g.buildMultigrid(levels=11)
