@@ -484,7 +484,7 @@ int hot_g2p(hot_sim* s, double dt, int* flags) { return g2p(s, dt, flags); }
 // ---- plasticity (rank 2 of SURVEY 8f): return mapping applied by hot_g2p after evolveStrain -------------------------------
 int hot_set_plasticity(hot_sim* s, int model, const double* params)
 {
-    if (model < 0 || model > 2) return fail(s, "hot_set_plasticity: model must be 0 (none), 1 (VonMisesFixedCorotated) or 2 (SnowPlasticity)");
+    if (model < 0 || model > 3) return fail(s, "hot_set_plasticity: model must be 0 (none), 1 (VonMisesFixedCorotated), 2 (SnowPlasticity) or 3 (Drucker-Prager extension)");
     if (model && !params) return fail(s, "hot_set_plasticity: null parameters");
     if (model == 1 && !(params[0] >= 0)) return fail(s, "yield_stress must be non-negative (PlasticityApplier.cpp:99)");
     s->plastic_model = model;

@@ -232,6 +232,7 @@ struct Sim {
     DevBuf<double> col_P, col_R, col_dv;
     DevBuf<double> cn_tol; // per-node CN tolerance (a18)
     DevBuf<double> work[8]; // DOF-sized scratch vectors of the host-buffer entry points
+    DevBuf<unsigned char> l2_flush; // 256 MiB written between the timed repetitions of hot_op_bench / hot_vcycle_bench
 
     // ---- assembled system + multigrid hierarchy (matrix.cu, multigrid.cu)
     std::vector<MGLevel*> levels; // levels[0] = assembled matrix

@@ -417,6 +417,36 @@ __global__ void k_plasticity(long n, size_t ps, int model, double p0, double p1,
             sn[d] = (m_ + sqrt(b2m4ac)) / (2.0 * m_);
         }
     }
+    else if (model == 3) {
+        // Drucker-Prager (extension, not in the reference; BASELINE C4): return mapping of Klar et al. 2016 in Hencky strain,
+        // eps = log sigma, yield ||dev eps|| + (3 lambda + 2 mu) / (2 mu) tr(eps) alpha <= 0 with alpha = sqrt(2/3) 2 sin(phi) / (3 - sin(phi));
+        // expansion (tr eps > 0) projects to the tip (sigma = 1, optionally shifted by the cohesion p1)
+        const double m_ = mu[s], l_ = lam[s], sphi = sin(p0 * 0.017453292519943295), alpha = sqrt(2.0 / 3.0) * 2.0 * sphi / (3.0 - sphi), coh = p1;
+        double eps[3], tr = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            eps[d] = log(fmax(sig[d], 1e-6)) - coh;
+            tr += eps[d];
+        }
+        double dev[3], n2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            dev[d] = eps[d] - tr / 3.0;
+            n2 += dev[d] * dev[d];
+        }
+        const double nrm = sqrt(n2);
+        if (tr >= 0.0) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) sn[d] = exp(coh);
+        }
+        else if (nrm == 0.0) return; // hydrostatic compression: inside the cone
+        else {
+            const double dgamma = nrm + (3.0 * l_ + 2.0 * m_) / (2.0 * m_) * tr * alpha;
+            if (dgamma <= 0.0) return; // elastic
+#pragma unroll
+            for (int d = 0; d < 3; ++d) sn[d] = exp(eps[d] - dgamma * dev[d] / nrm + coh);
+        }
+    }
     else {
         const double psi = p0, theta_c = p1, theta_s = p2, min_Jp = p3, max_Jp = p4;
         double Fe_det = 1.0;

@@ -505,7 +505,7 @@ class MpmSimulationB200:
 
     # ---- plasticity (PlasticityApplier.cpp): applied by gridToParticles after evolveStrain
     def set_plasticity(self, model, params=()):
-        m = {"none": 0, "von_mises": 1, "snow": 2}.get(model, model)
+        m = {"none": 0, "von_mises": 1, "snow": 2, "drucker_prager": 3}.get(model, model)
         p = _f64(list(params) + [0.0] * (5 - len(params)), (5,))
         self._check(self._lib.hot_set_plasticity(self._h, int(m), _ptr(p)))
 

@@ -110,7 +110,10 @@ int hot_g2p(hot_sim* h, double dt, int* flags /* [0] faster than dx, [1] faster 
 /* ---- plasticity: MpmSimulationBase::applyPlasticity (Lib/MPM/MpmSimulationBase.cpp:1044-1064), run by hot_g2p right after
  * evolveStrain like :1039-1041.  model 0 none; 1 VonMisesFixedCorotated::projectStrain (Lib/Ziran/Physics/PlasticityApplier.cpp:94-131),
  * params = {yield_stress}; 2 SnowPlasticity::projectStrain (:16-50), params = {psi, theta_c, theta_s, min_Jp, max_Jp}
- * (defaults 10, 2e-2, 7.5e-3, 0.6, 20: PlasticityApplier.h:61), hardening mu / lambda and Jp kept per particle on the device. */
+ * (defaults 10, 2e-2, 7.5e-3, 0.6, 20: PlasticityApplier.h:61), hardening mu / lambda and Jp kept per particle on the device;
+ * 3 Drucker-Prager, an EXTENSION (the reference ships no sand model; BASELINE's sand-column configuration names it): the Hencky-strain
+ * return mapping of Klar et al. 2016 on the singular values at the same hook, params = {friction angle in degrees, cohesion (log-strain
+ * shift, 0 for dry sand)}; parity is against the closed form in numpy (tests/test_oracle_plasticity.py), not against reference code. */
 int hot_set_plasticity(hot_sim* h, int model, const double* params);
 int hot_apply_plasticity(hot_sim* h);
 int hot_get_plastic_state(hot_sim* h, double* Jp, double* mu, double* lambda);

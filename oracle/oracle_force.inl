@@ -577,6 +577,31 @@ int orc_apply_plasticity(void* h)
                 sn[d] = (mu + std::sqrt(b2m4ac)) / (2 * mu);
             }
         }
+        else if (s->plastic_model == 3) {
+            // Drucker-Prager extension (Klar et al. 2016, Hencky-strain return mapping); not in the reference, see hot_b200.h
+            const double mu = s->mu[i], lambda = s->lambda[i], sphi = std::sin(q[0] * 0.017453292519943295),
+                         alpha = std::sqrt(2.0 / 3.0) * 2.0 * sphi / (3.0 - sphi), coh = q[1];
+            double eps[3], tr = 0;
+            for (int d = 0; d < 3; ++d) {
+                eps[d] = std::log(std::max(sig[d], 1e-6)) - coh;
+                tr += eps[d];
+            }
+            double dev[3], n2 = 0;
+            for (int d = 0; d < 3; ++d) {
+                dev[d] = eps[d] - tr / 3;
+                n2 += dev[d] * dev[d];
+            }
+            const double nrm = std::sqrt(n2);
+            if (tr >= 0) {
+                for (int d = 0; d < 3; ++d) sn[d] = std::exp(coh);
+            }
+            else if (nrm == 0) continue; // hydrostatic compression: inside the cone
+            else {
+                const double dgamma = nrm + (3 * lambda + 2 * mu) / (2 * mu) * tr * alpha;
+                if (dgamma <= 0) continue;
+                for (int d = 0; d < 3; ++d) sn[d] = std::exp(eps[d] - dgamma * dev[d] / nrm + coh);
+            }
+        }
         else {
             double Fe_det = 1;
             for (int d = 0; d < 3; ++d) {

@@ -223,7 +223,7 @@ def _add_force_methods(cls):
         return b
 
     def set_plasticity(self, model, params=()):
-        m = {"none": 0, "von_mises": 1, "snow": 2}.get(model, model)
+        m = {"none": 0, "von_mises": 1, "snow": 2, "drucker_prager": 3}.get(model, model)
         p = np.ascontiguousarray(list(params) + [0.0] * (5 - len(params)), dtype=np.float64)
         self._check(_lib.orc_set_plasticity(_vp(self._h), int(m), _p(p)))
 

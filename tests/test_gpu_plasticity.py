@@ -9,7 +9,7 @@ from hot_b200 import scenes
 
 pytestmark = pytest.mark.gpu
 
-MODELS = {"von_mises": [50.0], "snow": [10.0, 2e-2, 7.5e-3, 0.6, 20.0]}
+MODELS = {"von_mises": [50.0], "snow": [10.0, 2e-2, 7.5e-3, 0.6, 20.0], "drucker_prager": [30.0, 0.0]}   # DP: extension (hot_b200.h)
 
 
 def _pair(hot, oracle, sc, vscale):

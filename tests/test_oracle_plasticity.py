@@ -103,3 +103,39 @@ def test_g2p_applies_plasticity_after_evolve_strain(oracle):
     o = outs[0]
     o.set_plasticity("von_mises", [1.0]); o.applyPlasticity()  # same thing by hand
     np.testing.assert_allclose(o.get_particles()["F"], F1, atol=1e-14)
+
+
+def test_drucker_prager_return_mapping(oracle):
+    """Drucker-Prager extension (Klar et al. 2016): Hencky strain eps = log sigma, yield ||dev eps|| + (3 lam + 2 mu)/(2 mu) tr(eps) alpha <= 0.
+    Elastic states untouched, expansion goes to the tip (sigma = 1), the rest lands ON the cone along the old deviator."""
+    F = _rand_F(300, 0.5, 7)
+    F[0] = np.eye(3) * 0.9                                # hydrostatic compression: inside the cone for any friction angle ...
+    F[1] = np.diag([0.95, 0.9, 0.93])                     # ... mild shear under pressure: inside the cone
+    F[2] = np.eye(3) * 1.2                                # expansion: tip
+    o, mu, lam = _sim(oracle, F)
+    phi = 30.0
+    o.set_plasticity("drucker_prager", [phi, 0.0])
+    o.applyPlasticity()
+    Fn = _mat(o.get_particles()["F"])
+    alpha = np.sqrt(2.0 / 3.0) * 2 * np.sin(np.radians(phi)) / (3 - np.sin(np.radians(phi)))
+    k = (3 * lam + 2 * mu) / (2 * mu)
+    kinds = {"elastic": 0, "tip": 0, "cone": 0}
+    for a, b in zip(F, Fn):
+        U, s, Vt = np.linalg.svd(a)
+        eps = np.log(s); tr = eps.sum(); dev = eps - tr / 3; nrm = np.linalg.norm(dev)
+        sb = np.linalg.svd(b, compute_uv=False)
+        if tr >= 0:
+            kinds["tip"] += 1
+            np.testing.assert_allclose(sb, 1.0, atol=1e-12)
+            continue
+        y = nrm + k * tr * alpha
+        if y <= 0 or nrm < 1e-14:
+            kinds["elastic"] += 1
+            np.testing.assert_array_equal(a, b)
+            continue
+        kinds["cone"] += 1
+        np.testing.assert_allclose(b, U @ np.diag(np.exp(eps - y * dev / nrm)) @ Vt, atol=1e-11)
+        eb = np.log(np.sort(sb)[::-1]); db = eb - eb.sum() / 3
+        assert abs(eb.sum() - tr) < 1e-11                                     # volume-preserving plastic flow
+        assert abs(np.linalg.norm(db) + k * eb.sum() * alpha) < 1e-10          # on the yield surface
+    assert kinds["elastic"] >= 1 and kinds["tip"] >= 1 and kinds["cone"] >= 50
