@@ -121,6 +121,7 @@ def load_library(path=LIB_PATH):
         "hot_get_partition": (C.c_int, [vp, C.POINTER(C.c_long)]),
         "hot_get_transport": (C.c_int, [vp]),
         "hot_set_ghost_ring": (C.c_int, [vp, C.c_int]),
+        "hot_set_constitutive_model": (C.c_int, [vp, C.c_int]),
         "hot_halo_pages": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int), vp]),
         "hot_page_authority": (C.c_int, [C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]),
         "hot_set_dt_gravity": (C.c_int, [vp, C.c_double, vp]),

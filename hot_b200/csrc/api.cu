@@ -560,6 +560,15 @@ int hot_get_partition(hot_sim* s, long* out8)
     out8[7] = s->N;
     return 0;
 }
+int hot_set_constitutive_model(hot_sim* s, int model)
+{
+    if (model != 0 && model != 1) return fail(s, "hot_set_constitutive_model: 0 (CorotatedIsotropic) or 1 (neo-Hookean extension)");
+    s->constitutive_model = model;
+    s->state_valid = s->hessian_valid = false;
+    s->matrix_built = s->mg_built = false;
+    s->dpdf_norm_max = -1.0;
+    return 0;
+}
 int hot_set_ghost_ring(hot_sim* s, int on)
 {
     s->ghost_ring = on != 0;

@@ -209,6 +209,22 @@ __device__ __forceinline__ void pd2_equal_diagonal(double* B)
 struct HessBlocks {
     double A[9], B01[4], B12[4], B20[4];
 };
+// projectABBlock (SvdBasedIsotropicHelper.h:239-247) = makePD (EigenDecomposition.h:126-135) of the four blocks.  The 2x2 blocks have
+// equal diagonal entries [[a, b], [b, a]]: eigenvalues a + b, a - b on the fixed eigenvectors (1, +-1)/sqrt(2), so the clamp is closed-form
+// (no iteration, no sqrt / divide).  The 3x3 block is positive definite for all but strongly compressed / inverted states: a Sylvester
+// test skips the Jacobi iteration then (fp64 divide / sqrt sequences cost ~1k dependent cycles each on this part).
+__device__ inline void project_blocks(HessBlocks& h)
+{
+    pd2_equal_diagonal(h.B01);
+    pd2_equal_diagonal(h.B12);
+    pd2_equal_diagonal(h.B20);
+    const double m2 = h.A[0] * h.A[4] - h.A[1] * h.A[1];
+    const double m3 = h.A[0] * (h.A[4] * h.A[8] - h.A[5] * h.A[5]) - h.A[1] * (h.A[1] * h.A[8] - h.A[5] * h.A[2])
+        + h.A[2] * (h.A[1] * h.A[5] - h.A[4] * h.A[2]);
+    const double scale = fabs(h.A[0]) + fabs(h.A[4]) + fabs(h.A[8]);
+    const bool pd = h.A[0] > 1e-12 * scale && m2 > 1e-12 * scale * scale && m3 > 1e-12 * scale * scale * scale;
+    if (!pd) make_pd<3>(h.A);
+}
 __device__ inline void corotated_blocks(const double* sig, double mu, double lambda, bool project, HessBlocks& h)
 {
     const double J = sig[0] * sig[1] * sig[2];
@@ -230,21 +246,63 @@ __device__ inline void corotated_blocks(const double* sig, double mu, double lam
     h.B01[0] = h.B01[3] = (m01 + p01) * 0.5; h.B01[1] = h.B01[2] = (m01 - p01) * 0.5;
     h.B12[0] = h.B12[3] = (m12 + p12) * 0.5; h.B12[1] = h.B12[2] = (m12 - p12) * 0.5;
     h.B20[0] = h.B20[3] = (m02 + p02) * 0.5; h.B20[1] = h.B20[2] = (m02 - p02) * 0.5;
-    if (project) {
-        // makePD (EigenDecomposition.h:126-135).  The 2x2 blocks have equal diagonal entries [[a, b], [b, a]]: eigenvalues
-        // a + b, a - b on the fixed eigenvectors (1, +-1)/sqrt(2), so the clamp is closed-form (no iteration, no sqrt / divide).
-        // The 3x3 block is positive definite for all but strongly compressed / inverted states: a Sylvester test skips the
-        // Jacobi iteration then (fp64 divide / sqrt sequences cost ~1k dependent cycles each on this part).
-        pd2_equal_diagonal(h.B01);
-        pd2_equal_diagonal(h.B12);
-        pd2_equal_diagonal(h.B20);
-        const double m2 = h.A[0] * h.A[4] - h.A[1] * h.A[1];
-        const double m3 = h.A[0] * (h.A[4] * h.A[8] - h.A[5] * h.A[5]) - h.A[1] * (h.A[1] * h.A[8] - h.A[5] * h.A[2])
-            + h.A[2] * (h.A[1] * h.A[5] - h.A[4] * h.A[2]);
-        const double scale = fabs(h.A[0]) + fabs(h.A[4]) + fabs(h.A[8]);
-        const bool pd = h.A[0] > 1e-12 * scale && m2 > 1e-12 * scale * scale && m3 > 1e-12 * scale * scale * scale;
-        if (!pd) make_pd<3>(h.A);
+    if (project) project_blocks(h);
+}
+// Neo-Hookean (EXTENSION: the reference ships CorotatedIsotropic and LinearCorotated only; BASELINE's box-drop configuration names it):
+// psi = mu/2 (|F|^2 - 3) - mu log J + lambda/2 log^2 J in the same SVD-based isotropic framework (SvdBasedIsotropicHelper.h):
+// psi_i = mu s_i + c / s_i, c = lambda log J - mu; psi_ii = mu + (lambda - c) / s_i^2; psi_ij = lambda / (s_i s_j);
+// (psi_i - psi_j) / (s_i - s_j) = mu - c / (s_i s_j)
+__device__ inline void neohookean_blocks(const double* sig, double mu, double lambda, bool project, HessBlocks& h)
+{
+    const double J = sig[0] * sig[1] * sig[2], c = lambda * log(J) - mu, eps = 1e-6;
+    const double i0 = 1.0 / sig[0], i1 = 1.0 / sig[1], i2 = 1.0 / sig[2];
+    const double psi0 = mu * sig[0] + c * i0, psi1 = mu * sig[1] + c * i1, psi2 = mu * sig[2] + c * i2;
+    h.A[0] = mu + (lambda - c) * i0 * i0;
+    h.A[4] = mu + (lambda - c) * i1 * i1;
+    h.A[8] = mu + (lambda - c) * i2 * i2;
+    h.A[3] = h.A[1] = lambda * i0 * i1;
+    h.A[6] = h.A[2] = lambda * i0 * i2;
+    h.A[7] = h.A[5] = lambda * i1 * i2;
+    const double m01 = mu - c * i0 * i1, m02 = mu - c * i0 * i2, m12 = mu - c * i1 * i2;
+    const double p01 = (psi0 + psi1) / clamp_small_magnitude(sig[0] + sig[1], eps);
+    const double p02 = (psi0 + psi2) / clamp_small_magnitude(sig[0] + sig[2], eps);
+    const double p12 = (psi1 + psi2) / clamp_small_magnitude(sig[1] + sig[2], eps);
+    h.B01[0] = h.B01[3] = (m01 + p01) * 0.5; h.B01[1] = h.B01[2] = (m01 - p01) * 0.5;
+    h.B12[0] = h.B12[3] = (m12 + p12) * 0.5; h.B12[1] = h.B12[2] = (m12 - p12) * 0.5;
+    h.B20[0] = h.B20[3] = (m02 + p02) * 0.5; h.B20[1] = h.B20[2] = (m02 - p02) * 0.5;
+    if (project) project_blocks(h);
+}
+// flags: bit 0 = --project (PSD blocks), bits 1.. = constitutive model (0 fixed corotated, 1 neo-Hookean)
+__device__ __forceinline__ void model_blocks(const double* sig, double mu, double lambda, int flags, HessBlocks& h)
+{
+    if ((flags >> 1) == 1) neohookean_blocks(sig, mu, lambda, (flags & 1) != 0, h);
+    else corotated_blocks(sig, mu, lambda, (flags & 1) != 0, h);
+}
+// energy density and first Piola stress of the selected model from F and its SVD (R = U V^T, cof = J F^-T)
+__device__ __forceinline__ double model_stress(int model, const double* F, const double* U, const double* sig, const double* V, double mu, double lambda,
+    double* P)
+{
+    const double J = sig[0] * sig[1] * sig[2];
+    if (model == 1) {
+        const double lj = log(J), c = lambda * lj - mu;
+        const double p0 = mu * sig[0] + c / sig[0], p1 = mu * sig[1] + c / sig[1], p2 = mu * sig[2] + c / sig[2];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) P[r + 3 * cc] = U[r] * p0 * V[cc] + U[r + 3] * p1 * V[cc + 3] + U[r + 6] * p2 * V[cc + 6];
+        return 0.5 * mu * (sig[0] * sig[0] + sig[1] * sig[1] + sig[2] * sig[2] - 3.0) - mu * lj + 0.5 * lambda * lj * lj;
     }
+    double R[9], cof[9];
+    mm_bt(U, V, R);
+    cofactor3(F, cof);
+    double n2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        const double d = F[q] - R[q];
+        n2 += d * d;
+        P[q] = 2.0 * mu * d + lambda * (J - 1.0) * cof[q]; // firstPiola, CorotatedIsotropic.h:157-160
+    }
+    return mu * n2 + 0.5 * lambda * (J - 1.0) * (J - 1.0); // psi, :151-155
 }
 // dPdFOfSigmaContract(Projected), SvdBasedIsotropicHelper.h:256-282: K = dPdF_Sigma : D (both in SVD space)
 __device__ __forceinline__ void blocks_contract(const HessBlocks& h, const double* D, double* K)

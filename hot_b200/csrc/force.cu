@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(US_THREADS) k_update_state(const int* __restri
     const double* __restrict__ X, const double* __restrict__ Fn, double* __restrict__ F, const double* __restrict__ vol,
     const double* __restrict__ mu, const double* __restrict__ lam, double* __restrict__ stress, double* __restrict__ Uo, double* __restrict__ Vo,
     double* __restrict__ sigo, double* __restrict__ gradV, double dx, double one_over_dx, double dt, const double* __restrict__ vn,
-    const double* __restrict__ dv, double* __restrict__ group_psi, int pf_dist)
+    const double* __restrict__ dv, double* __restrict__ group_psi, int pf_dist, int model)
 {
     __shared__ double tile[3 * TILE];
     __shared__ double s_res[1];
@@ -124,19 +124,10 @@ __global__ void __launch_bounds__(US_THREADS) k_update_state(const int* __restri
         }
         A[0] += 1.0; A[4] += 1.0; A[8] += 1.0;
         mm(A, Fo, Fnew); // evolveStrain: F = (I + dt gradV) Fn, FBasedMpmForceHelper.cpp:100-114
-        double U[9], V[9], sig[3], R[9], cof[9], P[9], T[9];
+        double U[9], V[9], sig[3], P[9], T[9];
         svd3(Fnew, U, sig, V);
-        mm_bt(U, V, R);
-        cofactor3(Fnew, cof);
-        const double J = sig[0] * sig[1] * sig[2], m_ = mu[s], l_ = lam[s], vo = vol[s];
-        double n2 = 0.0;
-#pragma unroll
-        for (int q = 0; q < 9; ++q) {
-            const double d = Fnew[q] - R[q];
-            n2 += d * d;
-            P[q] = 2.0 * m_ * d + l_ * (J - 1.0) * cof[q]; // firstPiola, CorotatedIsotropic.h:157-160
-        }
-        e[0] += vo * (m_ * n2 + 0.5 * l_ * (J - 1.0) * (J - 1.0)); // psi, :151-155
+        const double m_ = mu[s], l_ = lam[s], vo = vol[s];
+        e[0] += vo * model_stress(model, Fnew, U, sig, V, m_, l_, P);
         mm_bt(P, Fo, T); // updateImplicitState: vol P Fn^T, FBasedMpmForceHelper.cpp:72-97
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
@@ -189,7 +180,7 @@ __global__ void __launch_bounds__(128) k_build_hessian(long n, size_t ps, const 
 #pragma unroll
     for (int d = 0; d < 3; ++d) sig[d] = sigi[d * ps + s];
     HessBlocks hb;
-    corotated_blocks(sig, mu[s], lam[s], project != 0, hb);
+    model_blocks(sig, mu[s], lam[s], project, hb);
     const double vo = vol[s];
     // FV = Fn V (3x3): D for the basis gradient e_a e_d^T is  (U^T e_a) (row d of Fn V)
     double FV[9];
@@ -495,7 +486,7 @@ struct CNTolPolicy {
     {
         const double one[3] = {1.0, 1.0, 1.0};
         HessBlocks hb;
-        corotated_blocks(one, a.mu[s], a.lam[s], a.project != 0, hb);
+        model_blocks(one, a.mu[s], a.lam[s], a.project, hb);
         double n2 = 0.0;
 #pragma unroll
         for (int q = 0; q < 9; ++q) n2 += hb.A[q] * hb.A[q];
@@ -614,21 +605,15 @@ __global__ void k_corotated_eval(long n, const double* __restrict__ F, double mu
 {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    double Fm[9], U[9], V[9], sig[3], R[9], cof[9];
+    double Fm[9], U[9], V[9], sig[3], Pm[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) Fm[q] = F[9 * t + q];
     svd3(Fm, U, sig, V);
-    mm_bt(U, V, R);
-    cofactor3(Fm, cof);
-    const double J = sig[0] * sig[1] * sig[2];
-    double n2 = 0.0;
+    const double e = model_stress(project >> 1, Fm, U, sig, V, mu, lambda, Pm);
+    if (P)
 #pragma unroll
-    for (int q = 0; q < 9; ++q) {
-        const double d = Fm[q] - R[q];
-        n2 += d * d;
-        if (P) P[9 * t + q] = 2.0 * mu * d + lambda * (J - 1.0) * cof[q];
-    }
-    if (psi) psi[t] = mu * n2 + 0.5 * lambda * (J - 1.0) * (J - 1.0);
+        for (int q = 0; q < 9; ++q) P[9 * t + q] = Pm[q];
+    if (psi) psi[t] = e;
     if (Uo)
 #pragma unroll
         for (int q = 0; q < 9; ++q) { Uo[9 * t + q] = U[q]; Vo[9 * t + q] = V[q]; }
@@ -637,7 +622,7 @@ __global__ void k_corotated_eval(long n, const double* __restrict__ F, double mu
         for (int d = 0; d < 3; ++d) sigo[3 * t + d] = sig[d];
     if (!dP && !dPdF) return;
     HessBlocks hb;
-    corotated_blocks(sig, mu, lambda, project != 0, hb);
+    model_blocks(sig, mu, lambda, project, hb);
     auto differential = [&](const double* dFm, double* out) { // dP = U (dPdF_Sigma : (U^T dF V)) V^T
         double T1[9], D[9], K[9], T2[9];
         mm_at(U, dFm, T1);
@@ -668,7 +653,8 @@ int corotated_eval(Sim* s, long n, const double* F, double mu, double lambda, in
     double* dP, double* dPdF, double* U, double* sigma, double* V)
 {
     if (n <= 0) return 0;
-    k_corotated_eval<<<nblk(n), TPB, 0, s->stream>>>(n, F, mu, lambda, project, dF, psi, P, dP, dPdF, U, sigma, V);
+    // (flags: bit 0 project, bits 1.. the handle's constitutive model)
+    k_corotated_eval<<<nblk(n), TPB, 0, s->stream>>>(n, F, mu, lambda, (project ? 1 : 0) | (s->constitutive_model << 1), dF, psi, P, dP, dPdF, U, sigma, V);
     HOT_LAUNCHED(s);
     return 0;
 }
@@ -764,7 +750,7 @@ int update_state(Sim* s, bool want_energy, double* energy)
         if (s->g1 > s->g0)
         k_update_state<<<(unsigned)(s->g1 - s->g0), US_THREADS, 0, st>>>(s->group_first.p + s->g0, s->tile_dof.p + (size_t)s->g0 * TILE, ps, s->P.X.p,
             s->P.Fn.p, s->P.F.p, s->P.vol.p, s->P.mu.p, s->P.lam.p, s->f_stress.p, s->f_U.p, s->f_V.p, s->f_sig.p, s->P.gradV.p, s->dx, 1.0 / s->dx,
-            s->dt, s->vn.p, s->dv.p, s->group_psi.p, pf_distance(s, 4));
+            s->dt, s->vn.p, s->dv.p, s->group_psi.p, pf_distance(s, 4), s->constitutive_model);
         HOT_LAUNCHED(s);
     }
     s->state_valid = true;
@@ -871,7 +857,7 @@ int ensure_hessian(Sim* s)
     const long np = s->p1 - s->p0, o = s->p0; // own particles: every row pointer shifted by p0
     if (np > 0) {
         k_build_hessian<<<(unsigned)((np + 127) / 128), 128, 0, s->stream>>>(np, ps, s->P.Fn.p + o, s->P.vol.p + o, s->P.mu.p + o, s->P.lam.p + o,
-            s->f_U.p + o, s->f_V.p + o, s->f_sig.p + o, s->project_pd ? 1 : 0, s->f_H.p + o);
+            s->f_U.p + o, s->f_V.p + o, s->f_sig.p + o, model_flags(s), s->f_H.p + o);
         HOT_LAUNCHED(s);
     }
     s->hessian_valid = true;
@@ -932,7 +918,7 @@ int eval_cn_tolerance(Sim* s, double eps, double dt, double* tol)
     const int nn = s->num_nodes;
     KTime t(s, KC_FORCE);
     HOT_CUDA(cudaMemsetAsync(tol, 0, (size_t)nn * sizeof(double), st));
-    CNTolPolicy::Args a{s->P.stride, s->P.X.p, s->P.M.p, s->P.mu.p, s->P.lam.p, s->dx, 1.0 / s->dx, s->project_pd ? 1 : 0, s->g_idx.p, tol};
+    CNTolPolicy::Args a{s->P.stride, s->P.X.p, s->P.M.p, s->P.mu.p, s->P.lam.p, s->dx, 1.0 / s->dx, model_flags(s), s->g_idx.p, tol};
     int rc = scatter_to_dofs<CNTolPolicy>(s, a, &CNTolPolicy::Args::out, tol, 1);
     if (rc) return rc;
     k_cn_finish<<<nblk(nn), TPB, 0, st>>>(nn, s->mass_matrix.p, eps * 24 * s->dx * s->dx * dt, tol);

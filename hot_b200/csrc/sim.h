@@ -213,6 +213,7 @@ struct Sim {
 
     // ---- force model state (force.cu); particle arrays are in sorted order and live for one time step
     bool project_pd = true; // CorotatedIsotropic::project (CorotatedIsotropic.h:60)
+    int constitutive_model = 0; // 0 CorotatedIsotropic (the reference's model), 1 neo-Hookean (extension, hot_set_constitutive_model)
     bool strain_backed_up = false, state_valid = false, hessian_valid = false;
     DevBuf<double> f_stress; // vol P Fn^T, 9 rows
     DevBuf<double> f_U, f_V, f_sig; // SVD of the trial F
@@ -293,6 +294,7 @@ struct Sim {
     ~Sim();
 };
 
+inline int model_flags(const Sim* s) { return (s->project_pd ? 1 : 0) | (s->constitutive_model << 1); } // kernels' `project` argument
 int fail(Sim* s, const std::string& msg);
 int cuda_fail(Sim* s, cudaError_t e, const char* what);
 

@@ -47,7 +47,7 @@ __global__ void k_max_dpdf_norm(long n, const double* __restrict__ mu, const dou
     if (s >= n) return;
     const double one[3] = {1.0, 1.0, 1.0};
     HessBlocks hb;
-    corotated_blocks(one, mu[s], lam[s], project != 0, hb);
+    model_blocks(one, mu[s], lam[s], project, hb);
     double n2 = 0.0;
 #pragma unroll
     for (int q = 0; q < 9; ++q) n2 += hb.A[q] * hb.A[q];
@@ -547,7 +547,7 @@ int hot_backward_euler_step(hot_sim* s, const hot_solver_options* opt, hot_solve
             unsigned long long* mx = (unsigned long long*)(s->red_out.p + 32);
             HOT_CUDA(cudaMemsetAsync(mx, 0, sizeof(*mx), s->stream));
             if (s->p1 > s->p0) {
-                k_max_dpdf_norm<<<nblk(s->p1 - s->p0), TPB, 0, s->stream>>>(s->p1 - s->p0, s->P.mu.p + s->p0, s->P.lam.p + s->p0, s->project_pd ? 1 : 0, mx);
+                k_max_dpdf_norm<<<nblk(s->p1 - s->p0), TPB, 0, s->stream>>>(s->p1 - s->p0, s->P.mu.p + s->p0, s->P.lam.p + s->p0, model_flags(s), mx);
                 HOT_LAUNCHED(s);
             }
             if (!s->h_red) HOT_CUDA(cudaMallocHost((void**)&s->h_red, 64 * sizeof(double)));

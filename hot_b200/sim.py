@@ -495,6 +495,10 @@ class MpmSimulationB200:
         self._check(self._lib.hot_get_partition(self._h, out))
         return dict(zip(("rank", "world", "neighbors", "shared_pages", "exchange_pages", "owned_nodes", "global_nodes", "particles"), [int(v) for v in out]))
 
+    def set_constitutive_model(self, model):
+        m = {"corotated": 0, "fixed_corotated": 0, "neo_hookean": 1}.get(model, model)
+        self._check(self._lib.hot_set_constitutive_model(self._h, int(m)))
+
     def set_ghost_ring(self, on=True):
         """partitioned objects: hold the 27-neighbourhood of the shared pages too (needed by buildMatrix / buildMultigrid / vcycle and
         the solvers with an assembled matrix when world > 1); takes effect with the next sortParticlesAndPolluteGrid"""

@@ -148,6 +148,11 @@ int hot_set_partition(hot_sim* h, int rank, int world, const hot_transport* tran
 /* {rank, world, neighbour ranks, shared local pages, pages exchanged per scatter (sum over neighbours), nodes this rank counts
  * in reductions, nodes of the whole object (the last two -1 before hot_p2g), local particles} */
 int hot_get_partition(hot_sim* h, long* out8);
+/* Constitutive model of the F-based force helper: 0 = CorotatedIsotropic (fixed corotated, the reference's model,
+ * Lib/Ziran/Physics/ConstitutiveModel/CorotatedIsotropic.h), 1 = neo-Hookean, an EXTENSION in the same SvdBasedIsotropicHelper framework
+ * (psi = mu/2 (|F|^2 - 3) - mu log J + lambda/2 log^2 J; the reference ships no such model, BASELINE's box-drop configuration names it).
+ * Parity for model 1 is against the oracle's restatement, which is pinned by finite differences and numpy (tests/test_oracle_force.py). */
+int hot_set_constitutive_model(hot_sim* h, int model);
 /* Ghost ring for the assembled-matrix / multigrid path of a partitioned object (SquareMatrix rows reach two nodes around a node,
  * Projects/multigrid/ImplicitSolver.h:465-468): with on != 0 a rank also holds every page of the 27-neighbourhood of its shared
  * pages that some rank activates.  Needed by hot_build_matrix / hot_build_mg / hot_vcycle / the -lsolver 2 and 3 solves with a

@@ -134,7 +134,12 @@ inline void cofactor3(const double* F, double* A)
 }
 
 // CorotatedIsotropic<T,3>::Scratch + SvdBasedIsotropicHelper<T,3>
+// 0 = CorotatedIsotropic (the reference's model), 1 = neo-Hookean (extension, see include/hot_b200.h: hot_set_constitutive_model).
+// Process-wide in the oracle (test infrastructure: one model per test), set by orc_set_constitutive_model.
+static int g_constitutive_model = 0;
+
 struct Scratch {
+    int model = 0;
     double J, F[9], U[9], V[9], R[9], JFinvT[9], sigma[3];
     double psi0, psi1, psi2, psi00, psi11, psi22, psi01, psi02, psi12, m01, p01, m02, p02, m12, p12;
     double Aij[9], B01[4], B12[4], B20[4];
@@ -148,8 +153,19 @@ void update_scratch(const double* F, double mu, double lambda, bool project, Scr
     mat_mul_bt(s.U, s.V, s.R);
     cofactor3(s.F, s.JFinvT);
     s.J = s.sigma[0] * s.sigma[1] * s.sigma[2];
-    const double _2mu = mu * 2, _lambda = lambda * (s.J - 1), eps = 1e-6;
+    s.model = g_constitutive_model;
+    const double eps = 1e-6;
+    if (s.model == 1) {
+        // neo-Hookean in the SvdBasedIsotropicHelper framework: psi_i = mu s_i + c / s_i with c = lambda log J - mu
+        const double c = lambda * std::log(s.J) - mu, i0 = 1 / s.sigma[0], i1 = 1 / s.sigma[1], i2 = 1 / s.sigma[2];
+        s.psi0 = mu * s.sigma[0] + c * i0; s.psi1 = mu * s.sigma[1] + c * i1; s.psi2 = mu * s.sigma[2] + c * i2;
+        s.psi00 = mu + (lambda - c) * i0 * i0; s.psi11 = mu + (lambda - c) * i1 * i1; s.psi22 = mu + (lambda - c) * i2 * i2;
+        s.psi01 = lambda * i0 * i1; s.psi02 = lambda * i0 * i2; s.psi12 = lambda * i1 * i2;
+        s.m01 = mu - c * i0 * i1; s.m02 = mu - c * i0 * i2; s.m12 = mu - c * i1 * i2;
+    }
+    const double _2mu = mu * 2, _lambda = lambda * (s.J - 1);
     const double Sprod[3] = {s.sigma[1] * s.sigma[2], s.sigma[0] * s.sigma[2], s.sigma[0] * s.sigma[1]};
+    if (s.model == 0) {
     s.psi0 = _2mu * (s.sigma[0] - 1) + _lambda * Sprod[0];
     s.psi1 = _2mu * (s.sigma[1] - 1) + _lambda * Sprod[1];
     s.psi2 = _2mu * (s.sigma[2] - 1) + _lambda * Sprod[2];
@@ -162,6 +178,7 @@ void update_scratch(const double* F, double mu, double lambda, bool project, Scr
     s.m01 = _2mu - _lambda * s.sigma[2];
     s.m02 = _2mu - _lambda * s.sigma[1];
     s.m12 = _2mu - _lambda * s.sigma[0];
+    }
     s.p01 = (s.psi0 + s.psi1) / clamp_small_magnitude(s.sigma[0] + s.sigma[1], eps);
     s.p02 = (s.psi0 + s.psi2) / clamp_small_magnitude(s.sigma[0] + s.sigma[2], eps);
     s.p12 = (s.psi1 + s.psi2) / clamp_small_magnitude(s.sigma[1] + s.sigma[2], eps);
@@ -182,6 +199,10 @@ void update_scratch(const double* F, double mu, double lambda, bool project, Scr
 // CorotatedIsotropic.h:151-155
 inline double psi_of(const Scratch& s, double mu, double lambda)
 {
+    if (s.model == 1) {
+        const double lj = std::log(s.J);
+        return 0.5 * mu * (s.sigma[0] * s.sigma[0] + s.sigma[1] * s.sigma[1] + s.sigma[2] * s.sigma[2] - 3) - mu * lj + 0.5 * lambda * lj * lj;
+    }
     double n2 = 0;
     for (int q = 0; q < 9; ++q) n2 += (s.F[q] - s.R[q]) * (s.F[q] - s.R[q]);
     double Jm1 = s.J - 1;
@@ -190,6 +211,11 @@ inline double psi_of(const Scratch& s, double mu, double lambda)
 // :157-160
 inline void first_piola(const Scratch& s, double mu, double lambda, double* P)
 {
+    if (s.model == 1) { // P = U diag(psi_i) V^T
+        for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r) P[r + 3 * c] = s.U[r] * s.psi0 * s.V[c] + s.U[r + 3] * s.psi1 * s.V[c + 3] + s.U[r + 6] * s.psi2 * s.V[c + 6];
+        return;
+    }
     for (int q = 0; q < 9; ++q) P[q] = 2 * mu * (s.F[q] - s.R[q]) + lambda * (s.J - 1) * s.JFinvT[q];
 }
 // :162-171 with dPdFOfSigmaContractProjected (SvdBasedIsotropicHelper.h:271-282).  After buildMatrixBlock the
@@ -537,6 +563,11 @@ int orc_eval_cn_tolerance(void* h, double eps, double dt, double* tol)
 
 // MpmSimulationBase::applyPlasticity (MpmSimulationBase.cpp:1044-1064): VonMisesFixedCorotated::projectStrain
 // (PlasticityApplier.cpp:94-131) or SnowPlasticity::projectStrain (:16-50) on every particle's F
+int orc_set_constitutive_model(void* /*h*/, int model)
+{
+    g_constitutive_model = model;
+    return 0;
+}
 int orc_set_plasticity(void* h, int model, const double* params)
 {
     Sim* s = (Sim*)h;

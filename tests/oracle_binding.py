@@ -167,6 +167,11 @@ def constitutive(F, mu, lam, project=True, dF=None):
     return dict(psi=psi.value, P=cm(P), dPdF=H.reshape(9, 9).T.copy(), dP=cm(dP) if dF is not None else None, U=cm(U), sigma=sg, V=cm(V))
 
 
+def set_constitutive_model_global(model):
+    """the oracle's constitutive model switch is process-wide (0 CorotatedIsotropic, 1 neo-Hookean extension)"""
+    _lib.orc_set_constitutive_model(None, int(model))
+
+
 def _add_force_methods(cls):
     def set_dt_gravity(self, dt, g):
         g = np.ascontiguousarray(g, dtype=np.float64)
@@ -221,6 +226,10 @@ def _add_force_methods(cls):
         b = np.empty_like(x)
         self._check(_lib.orc_hessian_apply_mf(_vp(self._h), _p(x), _p(b)))
         return b
+
+    def set_constitutive_model(self, model):
+        m = {"corotated": 0, "fixed_corotated": 0, "neo_hookean": 1}.get(model, model)
+        self._check(_lib.orc_set_constitutive_model(_vp(self._h), int(m)))
 
     def set_plasticity(self, model, params=()):
         m = {"none": 0, "von_mises": 1, "snow": 2, "drucker_prager": 3}.get(model, model)

@@ -72,6 +72,45 @@ def test_update_state_residual_multiply_parity(hot, oracle, case, project):
     _close(g.project(x), o.project(x), 1e-15)
 
 
+@pytest.mark.parametrize("project", [True, False])
+def test_neo_hookean_extension_parity(hot, oracle, project):
+    """hot_set_constitutive_model(1): neo-Hookean in the SvdBasedIsotropicHelper framework (extension; the oracle's restatement is pinned
+    by numpy / finite differences in tests/test_oracle_force.py): energy, stress, residual, matrix-free and assembled Hessian, one HOT solve"""
+    sc = CASES["small"]()
+    oracle.set_constitutive_model_global(1)
+    try:
+        g, o = _pair(hot, oracle, sc, project=project)
+        g.set_constitutive_model("neo_hookean")
+        n = o.num_nodes
+        bc = _floor_bc(o)
+        rng = np.random.default_rng(21)
+        for s in (g, o):
+            s.set_bc(bc, P=np.zeros((len(bc), 9)), dv_bc=np.zeros((len(bc), 3)))
+        dv = o.get_dv() + 0.2 * (rng.random((n, 3)) - 0.5)
+        eg, eo = g.updateState(dv), o.updateState(dv)
+        assert abs(eg - eo) <= 1e-12 * abs(eo)
+        Sg, Fg = g.get_stress(); So, Fo = o.get_stress()
+        _close(Fg, Fo, 1e-13); _close(Sg, So)
+        _close(g.computeResidual(), o.computeResidual())
+        x = rng.random((n, 3)) - 0.5
+        yg, yo = g.multiply(x), o.multiply(x)
+        _close(yg, yo)
+        g2, _ = _pair(hot, oracle, sc, project=project)                      # the model matters: fixed corotated gives another product
+        g2.set_bc(bc, P=np.zeros((len(bc), 9)), dv_bc=np.zeros((len(bc), 3))); g2.updateState(dv)
+        assert np.abs(g2.multiply(x) - yg).max() > 1e-6 * np.abs(yg).max()
+        if project:
+            for s in (g, o):
+                s.buildMatrix(True)
+            _close(g.spmv(0, x), o.spmv(0, x), 1e-10)
+            for s in (g, o):
+                s.restoreStrain()
+            lg, lo = g.backwardEulerStep(), o.backwardEulerStep()
+            assert lg["converged"] and lo["converged"] and lg["iterations"] == lo["iterations"]
+            assert np.abs(np.array(lg["residual_norm"]) - np.array(lo["residual_norm"])).max() <= 1e-5 * max(lo["residual_norm"])
+    finally:
+        oracle.set_constitutive_model_global(0)
+
+
 def test_slip_bc_mode_parity(hot, oracle):
     sc = CASES["small"]()
     g, o = _pair(hot, oracle, sc)

@@ -148,3 +148,35 @@ def test_cn_tolerance_formula(oracle):
     # uniform material: sum_p w m_p = m_i, so tol_i = ||dPdF(I)||_F * eps * 24 dx^2 dt (ImplicitSolver.h:667-696)
     H = oracle.constitutive(np.eye(3), sc["mu"][0], sc["lam"][0])["dPdF"]
     np.testing.assert_allclose(tol, np.linalg.norm(H) * eps * 24 * sc["dx"] ** 2 * dt, rtol=1e-10)
+
+
+# ---- neo-Hookean extension (hot_set_constitutive_model 1): closed form + finite differences ---------------------------------
+def _nh_numpy(F):
+    J = np.linalg.det(F)
+    FinvT = np.linalg.inv(F).T
+    psi = 0.5 * MU * ((F * F).sum() - 3) - MU * np.log(J) + 0.5 * LAM * np.log(J) ** 2
+    P = MU * (F - FinvT) + LAM * np.log(J) * FinvT
+    return psi, P
+
+
+def test_neo_hookean_extension_vs_numpy_and_finite_differences(oracle):
+    rng = np.random.default_rng(5)
+    oracle.set_constitutive_model_global(1)
+    try:
+        for F in [F for F in _cases()[:43] if np.linalg.det(F) > 0.2]:
+            dF = rng.random((3, 3)) - 0.5
+            c = oracle.constitutive(F, MU, LAM, project=False, dF=dF)
+            psi, P = _nh_numpy(F)
+            np.testing.assert_allclose(c["psi"], psi, rtol=1e-11, atol=1e-9)
+            np.testing.assert_allclose(c["P"], P, rtol=1e-10, atol=1e-8 * MU)
+            h = 1e-6
+            fd = (_nh_numpy(F + h * dF)[1] - _nh_numpy(F - h * dF)[1]) / (2 * h)
+            np.testing.assert_allclose(c["dP"], fd, rtol=5e-6, atol=5e-6 * MU)
+            vec = lambda M: M.T.reshape(9)
+            np.testing.assert_allclose(c["dPdF"] @ vec(dF), vec(c["dP"]), rtol=1e-11, atol=1e-9 * MU)
+            np.testing.assert_allclose(c["dPdF"], c["dPdF"].T, atol=1e-9 * MU)
+            cp = oracle.constitutive(F, MU, LAM, project=True, dF=dF)
+            w = np.linalg.eigvalsh(cp["dPdF"])
+            assert w.min() > -1e-8 * abs(w).max()
+    finally:
+        oracle.set_constitutive_model_global(0)
