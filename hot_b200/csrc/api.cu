@@ -488,7 +488,8 @@ int hot_set_plasticity(hot_sim* s, int model, const double* params)
     if (model && !params) return fail(s, "hot_set_plasticity: null parameters");
     if (model == 1 && !(params[0] >= 0)) return fail(s, "yield_stress must be non-negative (PlasticityApplier.cpp:99)");
     s->plastic_model = model;
-    for (int k = 0; k < 5; ++k) s->plastic_param[k] = (model == 2 || (model == 1 && k == 0)) ? params[k] : 0.0;
+    if (model == 3 && !(params[0] >= 0 && params[0] < 90)) return fail(s, "Drucker-Prager: friction angle in degrees, [0, 90)");
+    for (int k = 0; k < 5; ++k) s->plastic_param[k] = (model == 2 || (model == 1 && k == 0) || (model == 3 && k < 2)) ? params[k] : 0.0;
     return 0;
 }
 int hot_apply_plasticity(hot_sim* s)
