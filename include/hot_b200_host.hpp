@@ -15,9 +15,12 @@
 #include "hot_b200.h"
 #include <array>
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <functional>
+#include <istream>
 #include <memory>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -362,8 +365,11 @@ public:
     {
         check(hot_set_particles(h, n, X, V, mass, C, F, vol, mu, lambda));
         N = n;
+        mass_p.assign(mass, mass + n); // constants of the particle set, needed by writeState
+        vol_p.assign(vol, vol + n);
     }
     void getParticles(double* X, double* V, double* C, double* F) { check(hot_get_particles(h, X, V, C, F, nullptr)); }
+    std::vector<double> mass_p, vol_p;
     long particleCount() const { return N; }
 
     void sortParticlesAndPolluteGrid() { check(hot_sort_and_activate(h)); } // MpmSimulationBase.cpp:1066-1137
@@ -486,6 +492,96 @@ public:
         check(hot_set_plasticity(h, 2, q));
     }
     void applyPlasticity() { check(hot_apply_plasticity(h)); }
+
+    // ---- restart state: MpmSimulationBase::writeState / readState (Lib/MPM/MpmSimulationBase.cpp:755-785) in the reference's
+    // binary layout (binary_ver 1), so that a restart_N.dat written here is read by the reference's readState and vice versa:
+    //   Scene::writeState (Lib/Ziran/Sim/Scene.h:189-206) = particles.writeData + (no element managers for MPM) + two empty
+    //   mesh index vectors; DataManager::writeData (DataManager.h:263-273) = int count, u64 #arrays, then per array its name
+    //   (u64 length + bytes, BinaryIO.h:167-172) and DataArray::writeData (DataArray.h:100-105) = int lg2_grain_size (7),
+    //   StdVector<Range{int lower, upper}>, StdVector<T> (u64 size, u64 sizeof(T), entries).  Arrays of this path: "X", "V" (TV),
+    //   "m", "element measure" (T), "F" (TM, column-major), "CorotatedIsotropic" (entries written as mu, lambda with sizeof 24,
+    //   CorotatedIsotropic.h:330-342).  The reader looks arrays up by NAME (DataManager.h:280-293), the order is free.
+    //   The APIC matrix (scratch_gradV in the reference, written there only for interpolation_degree 1) follows as a trailing
+    //   StdVector<TM>; a reader that does not expect it stops before it.
+    void writeState(std::ostream& out)
+    {
+        const long n = N;
+        std::vector<double> X(3 * n), V(3 * n), C(9 * n), F(9 * n), mu(n), lam(n);
+        getParticles(X.data(), V.data(), C.data(), F.data());
+        check(hot_get_plastic_state(h, nullptr, mu.data(), lam.data()));
+        auto w = [&](const void* p, size_t bytes) { out.write(reinterpret_cast<const char*>(p), (std::streamsize)bytes); };
+        auto u64 = [&](uint64_t v) { w(&v, 8); };
+        auto i32 = [&](int v) { w(&v, 4); };
+        auto header = [&](const char* name, uint64_t elem_bytes) {
+            const uint64_t len = std::strlen(name);
+            u64(len); w(name, len);
+            i32(7);                                  // DisjointRanges::lg2_grain_size
+            u64(1); u64(8); i32(0); i32((int)n);     // ranges = {[0, n)}
+            u64((uint64_t)n); u64(elem_bytes);
+        };
+        i32((int)n);
+        u64(6);
+        header("X", 24); w(X.data(), X.size() * 8);
+        header("V", 24); w(V.data(), V.size() * 8);
+        header("m", 8); w(mass_p.data(), (size_t)n * 8);
+        header("element measure", 8); w(vol_p.data(), (size_t)n * 8);
+        header("F", 72); w(F.data(), F.size() * 8);
+        header("CorotatedIsotropic", 24);
+        for (long i = 0; i < n; ++i) { w(&mu[i], 8); w(&lam[i], 8); }
+        u64(0); u64(12);                             // trimesh_to_write.indices (Vector<int, 3>)
+        u64(0); u64(8);                              // segmesh_to_write.indices (Vector<int, 2>)
+        u64((uint64_t)n); u64(72); w(C.data(), C.size() * 8);
+    }
+    void readState(std::istream& in)
+    {
+        auto r = [&](void* p, size_t bytes) {
+            in.read(reinterpret_cast<char*>(p), (std::streamsize)bytes);
+            if (!in) throw HotError("readState: truncated restart file");
+        };
+        auto u64 = [&]() { uint64_t v; r(&v, 8); return v; };
+        auto i32 = [&]() { int v; r(&v, 4); return v; };
+        const int n = i32();
+        const uint64_t arrays = u64();
+        std::vector<double> X, V, m, vol, F, mu, lam, C;
+        for (uint64_t a = 0; a < arrays; ++a) {
+            std::string name(u64(), '\0');
+            r(&name[0], name.size());
+            (void)i32();
+            const uint64_t nr = u64(), rb = u64();
+            if (rb != 8) throw HotError("readState: Range size mismatch");
+            std::vector<int> ranges(2 * nr);
+            r(ranges.data(), nr * 8);
+            const uint64_t size = u64(), bytes = u64();
+            if ((long)size != n) throw HotError("readState: array " + name + " does not cover all particles");
+            auto take = [&](std::vector<double>& dst, uint64_t expect) {
+                if (bytes != expect) throw HotError("Read error: The size of the types don't match (" + name + ")");
+                dst.resize(size * expect / 8);
+                r(dst.data(), size * expect);
+            };
+            if (name == "X") take(X, 24);
+            else if (name == "V") take(V, 24);
+            else if (name == "m") take(m, 8);
+            else if (name == "element measure") take(vol, 8);
+            else if (name == "F") take(F, 72);
+            else if (name == "CorotatedIsotropic") {
+                if (bytes != 24) throw HotError("Read error: The size of the types don't match (CorotatedIsotropic)");
+                mu.resize(size); lam.resize(size);
+                for (uint64_t i = 0; i < size; ++i) { r(&mu[i], 8); r(&lam[i], 8); }
+            }
+            else throw HotError("Array " + name + " was not initialized before reading.");
+        }
+        for (int k = 0; k < 2; ++k) { // mesh index vectors
+            const uint64_t size = u64(), bytes = u64();
+            in.ignore((std::streamsize)(size * bytes));
+        }
+        C.assign(9 * (size_t)n, 0.0);
+        if (in.peek() != std::char_traits<char>::eof()) { // trailing APIC matrices (see writeState)
+            const uint64_t size = u64(), bytes = u64();
+            if ((long)size == n && bytes == 72) r(C.data(), (size_t)n * 72);
+        }
+        if (X.empty() || V.empty() || m.empty() || vol.empty() || F.empty() || mu.empty()) throw HotError("readState: missing particle arrays");
+        setParticles(n, X.data(), V.data(), m.data(), C.data(), F.data(), vol.data(), mu.data(), lam.data());
+    }
 
     // One object over the GPUs of a box (include/hot_b200.h "one object over the GPUs of a box"; no counterpart in the single-process
     // reference): one MpmSimulationB200 per process / GPU, each holding its own particles.  Either NCCL inside the library

@@ -3,6 +3,7 @@
 //   host_step <in.bin> <out.bin> <n_steps> <dt> <ground_y> <ground_type 1|2> [reference flags ...]
 // in.bin : i64 n, f64 dx, then X[3n] V[3n] m[n] C[9n] F[9n] vol[n] mu[n] lam[n]
 // out.bin: i64 n, X V C F, then per step {i32 iterations, i32 converged, i32 n_nodes, i32 n_bc, f64 last residual norm}
+#include <fstream>
 #include "hot_b200_host.hpp"
 #include <cstdio>
 #include <cstdlib>
@@ -52,6 +53,20 @@ int main(int argc, char** argv)
             MPMSpMatB200 A{&sim, 0};
             TVStack u(3 * (size_t)sim.num_nodes, 0.0), r(3 * (size_t)sim.num_nodes, 1.0), du, dAu;
             selectSmoother(HOTSettings::smoother)(u, r, du, dAu, A, 1, 0.0);
+        }
+        if (const char* rf = std::getenv("HOT_RESTART_FILE")) { // writeState -> readState into a second simulation: identical particle state
+            {
+                std::ofstream os(rf, std::ios::binary);
+                sim.writeState(os);
+            }
+            MpmSimulationB200 sim2(dx);
+            std::ifstream is(rf, std::ios::binary);
+            sim2.readState(is);
+            std::vector<double> X2(3 * n), V2(3 * n), C2(9 * n), F2(9 * n);
+            sim2.getParticles(X2.data(), V2.data(), C2.data(), F2.data());
+            if (sim2.particleCount() != n || X2 != X || V2 != V || C2 != C || F2 != F || sim2.mass_p != m || sim2.vol_p != vol)
+                throw HotError("restart round trip changed the particle state");
+            std::printf("restart ok\n");
         }
         std::printf("ok %lld particles, %d nodes, %d bc nodes, %d iterations\n", n, sim.num_nodes, sim.num_collision_nodes, sim.last_log.iterations);
     }

@@ -101,6 +101,46 @@ def test_cpp_host_time_steps_match_oracle(host_step, oracle, tmp_path, case):
         assert np.abs(a - b).max() < 1e-6 * np.abs(b).max()
 
 
+def test_restart_state_layout_and_round_trip(host_step, tmp_path):
+    """MpmSimulationB200::writeState / readState: the reference's restart layout (Scene.h:189-206, DataManager.h:263-273,
+    DataArray.h:100-105, BinaryIO.h:82-88,167-172), parsed here byte by byte, and a write -> read round trip in the C++ driver"""
+    gtype, flags, _ = CASES[next(iter(CASES))]
+    sc = scenes.block((4, 4, 4), 1.0 / 32, ppc=4, origin_cells=(8, 8, 8), rho=1000.0, E=2.5e4, nu=0.4, seed=5)
+    n = len(sc["mass"])
+    fin, fout, frs = str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), str(tmp_path / "restart_1.dat")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<qd", n, sc["dx"]))
+        for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam"):
+            f.write(np.ascontiguousarray(sc[k], dtype=np.float64).tobytes())
+    out = subprocess.run([host_step, fin, fout, "1", "2e-3", repr(9.0 / 32), str(gtype)] + flags, capture_output=True, text=True,
+                         env=dict(os.environ, HOT_RESTART_FILE=frs))
+    assert out.returncode == 0 and "restart ok" in out.stdout, out.stderr
+    raw = np.fromfile(fout, dtype=np.float64, offset=8)
+    X = raw[:3 * n].reshape(n, 3); F = raw[15 * n:24 * n].reshape(n, 9)
+    b = open(frs, "rb").read()
+    pos = 0
+    def take(fmt):
+        nonlocal pos
+        v = struct.unpack_from("<" + fmt, b, pos); pos += struct.calcsize("<" + fmt)
+        return v[0] if len(v) == 1 else v
+    assert take("i") == n and take("Q") == 6
+    arrays = {}
+    for _ in range(6):
+        ln = take("Q"); name = b[pos:pos + ln].decode(); pos += ln
+        assert take("i") == 7                                               # DisjointRanges lg2_grain_size
+        assert take("Q") == 1 and take("Q") == 8 and take("ii") == (0, n)   # one Range [0, n)
+        size, eb = take("Q"), take("Q")
+        assert size == n
+        arrays[name] = (eb, np.frombuffer(b, dtype=np.float64, count=n * (16 if name == "CorotatedIsotropic" else eb) // 8, offset=pos))
+        pos += n * (16 if name == "CorotatedIsotropic" else eb)
+    assert {k: v[0] for k, v in arrays.items()} == {"X": 24, "V": 24, "m": 8, "element measure": 8, "F": 72, "CorotatedIsotropic": 24}
+    assert np.array_equal(arrays["X"][1].reshape(n, 3), X) and np.array_equal(arrays["F"][1].reshape(n, 9), F)
+    assert np.array_equal(arrays["m"][1], sc["mass"]) and np.array_equal(arrays["element measure"][1], sc["vol"])
+    assert np.array_equal(arrays["CorotatedIsotropic"][1].reshape(n, 2), np.stack([sc["mu"], sc["lam"]], 1))
+    assert take("QQ") == (0, 12) and take("QQ") == (0, 8)                    # empty trimesh / segmesh index vectors
+    assert take("QQ") == (n, 72) and len(b) - pos == 72 * n                  # trailing APIC matrices
+
+
 def test_cpp_host_rejects_unknown_flag(host_step, tmp_path):
     fin = str(tmp_path / "in.bin")
     sc = scenes.block((3, 3, 3), 1.0 / 32, ppc=2, seed=1)
