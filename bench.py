@@ -79,10 +79,11 @@ def peaks():
 def ncu_traffic(kernel):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r1_traffic.json,
     written by profiles/ncu_traffic.py from the .ncu-rep of the same workload); None if the capture is absent."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if not os.path.exists(p):
-        return None
-    return json.load(open(p)).get(kernel, {}).get("dram_bytes")
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p)).get(kernel, {}).get("dram_bytes")
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -584,7 +585,7 @@ def run_ours(args):
         ach = alg[dom] / (per[dom] * 1e-3) / 1e9
         kernel_name = {"p2g": "k_plane2_scatter<P2GPolicy>", "g2p": "k_g2p<true>"}[dom]
         roof = {"bound": "hbm", "kernel": kernel_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": ncu_traffic(dom), "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json)",
+                "traffic": ncu_traffic(dom), "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r2_traffic.json)",
                 "alg_bytes_per_launch": alg[dom], "peak_source": peak_src,
                 "per_kernel": {k: {"ms": per[k], "alg_GBps": (alg[k] / (per[k] * 1e-3) / 1e9 if k in alg else None),
                                    "frac": (alg[k] / (per[k] * 1e-3) / 1e9 / peak if k in alg else None)} for k in per},
