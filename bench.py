@@ -300,6 +300,11 @@ def solver_leg(sim, sc, args):
     vms2 = sim.vcycle_bench(reps)
     vb2 = 7 * (spmv_bytes[0] + spmv_bytes[1]) + cg_it2 * spmv_bytes[2] + 30 * 24 * dofs[0]
     out["vcycle_smooth_rhs"] = {"ms": vms2, "coarse_cg_iters": cg_it2, "alg_bytes": vb2, "frac": vb2 / vms2 / 1e6 / peak}
+    # the coarsest-level PCG on its own (it runs 0 iterations inside the V-cycles above): right-hand side = the restricted initial residual
+    cms = sim.op_bench("coarse_solve", reps, level=2)
+    _, cg_it3 = sim.vcycle_timing()
+    out["coarse_pcg_alone"] = {"level": 2, "ms": cms, "cg_iters": cg_it3, "alg_bytes": cg_it3 * spmv_bytes[2],
+                               "note": "cg_smooth (MultigridPreconditioner.h:190-225) on level 2 with r = initialResiduals[2]: z.r starts at z0.r0 and has to fall below 0.25 z0.r0"}
     out["l2"] = "flushed before every timed operator application and V-cycle (256 MiB memset outside the event pairs)"
     out["hot_substep"] = substep_leg(sim, sc)
     return out
@@ -604,7 +609,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": dict(config_block(desc, args, world), particles_rank0=n, grid_nodes_rank0=n_nodes, pages_rank0=sim.num_pages,
+            "config": config_block(desc, args, world),   # the same keys and values as the reference arm's config
+            "partition": dict(particles_rank0=n, grid_nodes_rank0=n_nodes, pages_rank0=sim.num_pages,
                            parallelism=("single GPU" if world == 1 else
                                         f"{world} GPUs, one process each, particles partitioned (rank 0: {part['particles']} particles, {part['neighbors']} neighbour ranks, "
                                         f"{part['shared_pages']} shared pages, {part['owned_nodes']} of {part['global_nodes']} nodes counted here); per P2G one shared-page exchange of "

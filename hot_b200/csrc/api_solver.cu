@@ -274,18 +274,27 @@ int hot_vcycle_bench(hot_sim* s, int reps, double* ms_total)
 // `reps` device-resident applications of one operator of the path, timed with CUDA events on the handle's stream:
 // op 0 matrix-free Hessian apply (a13), 1 block SpMV on `level` (a16), 2 updateState without energy (a9-a11),
 // 3 computeResidual (a12), 4 one smoother call of the configured -smoother on `level` (a18), 5 hot_build_matrix (a15),
-// 6 hot_build_mg with the current settings (a17)
+// 6 hot_build_mg with the current settings (a17), 7 one -coarseSolver call on `level` with the level's restricted initial
+// residual of the last V-cycle as right-hand side (a19; the iteration count is returned by hot_vcycle_timing)
 int hot_op_bench(hot_sim* s, int op, int level, int reps, double* ms_total)
 {
     if (!s->state_valid) return fail(s, "hot_op_bench: call hot_update_state first");
-    if ((op == 1 || op == 4) && (level < 0 || level >= (int)s->levels.size() || !s->matrix_built || (op == 4 && !s->mg_built)))
+    const bool on_level = op == 1 || op == 4 || op == 7;
+    if (on_level && (level < 0 || level >= (int)s->levels.size() || !s->matrix_built || (op != 1 && !s->mg_built)))
         return fail(s, "hot_op_bench: matrix / hierarchy not built or bad level");
     if (op == 6 && !s->matrix_built) return fail(s, "hot_op_bench: matrix not built");
-    const size_t m = 3 * (size_t)((op == 1 || op == 4) ? s->levels[level]->n : s->num_nodes);
+    const size_t m = 3 * (size_t)(on_level ? s->levels[level]->n : s->num_nodes);
     HOT_CUDA(s->work[3].reserve(m));
     HOT_CUDA(s->work[4].reserve(m));
     HOT_CUDA(cudaMemsetAsync(s->work[4].p, 0, m * sizeof(double), s->stream));
-    if (op != 4) HOT_CUDA(cudaMemcpyAsync(s->work[3].p, s->dv.p, std::min(m, 3 * (size_t)s->num_nodes) * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    if (op != 4 && op != 7) HOT_CUDA(cudaMemcpyAsync(s->work[3].p, s->dv.p, std::min(m, 3 * (size_t)s->num_nodes) * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    if (op == 7) {
+        // the -coarseSolver call on its own: the level's restricted initial residual of the last V-cycle is both the right-hand
+        // side and cg_smooth's stopping reference, so z.r starts AT z0.r0 and the solver has to bring it below the 0.25 z0.r0
+        // of MultigridPreconditioner.h:209 (inside a V-cycle the pre-smoothing usually achieves that already: 0 iterations)
+        HOT_CUDA(s->work[5].reserve(m));
+        HOT_CUDA(cudaMemcpyAsync(s->work[5].p, s->levels[level]->initial_residual.p, m * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    }
     // iteration -1 is an untimed warm-up: first-use allocations (cudaMalloc blocks the host while the stream idles) and
     // once-per-linearisation work (the contracted particle Hessian of ensure_hessian) stay out of the per-application time.
     // L2 (126 MB) is flushed before every timed application (256 MiB memset, outside the event pair of the application): the
@@ -293,6 +302,10 @@ int hot_op_bench(hot_sim* s, int op, int level, int reps, double* ms_total)
     HOT_CUDA(s->l2_flush.reserve((size_t)256 << 20));
     std::vector<cudaEvent_t> ev;
     for (int i = -1; i < reps; ++i) {
+        if (op == 7) { // fresh right-hand side / zero solution for every application (outside the event pair)
+            HOT_CUDA(cudaMemcpyAsync(s->work[3].p, s->work[5].p, m * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+            HOT_CUDA(cudaMemsetAsync(s->work[4].p, 0, m * sizeof(double), s->stream));
+        }
         if (i >= 0) {
             HOT_CUDA(cudaMemsetAsync(s->l2_flush.p, i & 0xff, (size_t)256 << 20, s->stream));
             ev.push_back(s->timers.get());
@@ -300,6 +313,8 @@ int hot_op_bench(hot_sim* s, int op, int level, int reps, double* ms_total)
         }
         int rc = 0;
         switch (op) {
+        case 7: rc = level_smooth(s, level, s->mg_coarse, s->work[4].p, s->work[3].p, (s->mg_coarse == 2 || s->mg_coarse == 6) ? 10000 : 3 * s->mg_times,
+                                  s->mg_cneps * s->mg_cneps); break;
         case 0: rc = hessian_apply_mf(s, s->work[3].p, s->work[4].p); break;
         case 1: rc = level_spmv(s, level, s->work[3].p, s->work[4].p); break;
         case 2: rc = update_state(s, false, nullptr); break;

@@ -668,6 +668,12 @@ struct GSArgs {
     const double* sval[2];
     const int* pblock; // block of every sweep position
     int stream_update; // the tail uses r_new = L (hdu - du) from the forward stream
+    // block-inverse form (k_gx_*): per-direction stream [external rows | inverse section] per half block, indexed by sweep
+    // position in DIRECTION order (backward: n - 1 - p); forward in-half couplings for the residual update
+    const int* xoff[2];
+    const double* xdata[2]; // chunk records of GX_REC doubles
+    const int* ioff;
+    const double* idata;
 };
 
 // Tail of gs_smooth (u += du, r -= A du, MultigridPreconditioner.h:311-314) from the forward stream.  With (D + L) hdu = r and
@@ -680,16 +686,29 @@ __device__ __forceinline__ void gs_stream_update_row(const GSArgs& a, int p, int
     const int i = a.seq[p], ps = a.block_start[a.pblock[p]];
     const int c0 = a.soff[0][p], c1 = a.soff[0][p + 1];
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int c = c0; c < c1; ++c) {
-        const int code = a.scode[0][(size_t)c * 32 + lane];
-        if (code != GS_PAD) {
-            const int j = code >= 0 ? code : a.seq[ps - code - 1];
-            const double x0 = a.hdu[3 * (size_t)j] - a.du[3 * (size_t)j], x1 = a.hdu[3 * (size_t)j + 1] - a.du[3 * (size_t)j + 1],
-                         x2 = a.hdu[3 * (size_t)j + 2] - a.du[3 * (size_t)j + 2];
-            const double* v = a.sval[0] + (size_t)c * 9 * 32 + lane;
-            a0 += v[0] * x0 + v[3 * 32] * x1 + v[6 * 32] * x2;
-            a1 += v[32] * x0 + v[4 * 32] * x1 + v[7 * 32] * x2;
-            a2 += v[2 * 32] * x0 + v[5 * 32] * x1 + v[8 * 32] * x2;
+    // two chunks per trip, codes AND values requested together (padding entries are zero blocks in valid memory, so the value
+    // loads need not wait for the code): the row's dependent chain is offsets -> (codes, values) -> gathers
+    for (int c = c0; c < c1; c += 2) {
+        int code[2];
+        double v[2][9];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const bool on = c + u < c1;
+            code[u] = on ? a.scode[0][(size_t)(c + u) * 32 + lane] : GS_PAD;
+            const double* vp = a.sval[0] + (size_t)(c + u) * 9 * 32 + lane;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) v[u][q] = on ? vp[q * 32] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (code[u] != GS_PAD) {
+                const int j = code[u] >= 0 ? code[u] : a.seq[ps - code[u] - 1];
+                const double x0 = a.hdu[3 * (size_t)j] - a.du[3 * (size_t)j], x1 = a.hdu[3 * (size_t)j + 1] - a.du[3 * (size_t)j + 1],
+                             x2 = a.hdu[3 * (size_t)j + 2] - a.du[3 * (size_t)j + 2];
+                a0 += v[u][0] * x0 + v[u][3] * x1 + v[u][6] * x2;
+                a1 += v[u][1] * x0 + v[u][4] * x1 + v[u][7] * x2;
+                a2 += v[u][2] * x0 + v[u][5] * x1 + v[u][8] * x2;
+            }
         }
     }
 #pragma unroll
@@ -746,6 +765,778 @@ __global__ void __launch_bounds__(THREADS) k_gs_sweep(GSArgs a)
     const long nwarps = (long)gridDim.x * (THREADS / 32);
     if (STREAM && a.stream_update) {
         for (long p = (long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); p < a.n; p += nwarps) gs_stream_update_row(a, (int)p, lane);
+        return;
+    }
+    for (long row = (long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); row < a.n; row += nwarps) {
+        const int* c = a.col + (size_t)row * W;
+        const double* v = a.val + (size_t)row * 9 * W;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int t = 0; t < W / 32; ++t) {
+            const int s = lane + 32 * t;
+            const int j = c[s];
+            const double x0 = a.du[3 * (size_t)j], x1 = a.du[3 * (size_t)j + 1], x2 = a.du[3 * (size_t)j + 2];
+            a0 += v[s] * x0 + v[3 * W + s] * x1 + v[6 * W + s] * x2;
+            a1 += v[W + s] * x0 + v[4 * W + s] * x1 + v[7 * W + s] * x2;
+            a2 += v[2 * W + s] * x0 + v[5 * W + s] * x1 + v[8 * W + s] * x2;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_down_sync(0xffffffffu, a0, o);
+            a1 += __shfl_down_sync(0xffffffffu, a1, o);
+            a2 += __shfl_down_sync(0xffffffffu, a2, o);
+        }
+        if (lane == 0) {
+            const size_t o = 3 * (size_t)row;
+            a.r[o] -= a0; a.r[o + 1] -= a1; a.r[o + 2] -= a2;
+            a.u[o] += a.du[o]; a.u[o + 1] += a.du[o + 1]; a.u[o + 2] += a.du[o + 2];
+        }
+    }
+}
+
+// ---- ring form of a colour phase (default) ------------------------------------------------------------------------------
+// Same arithmetic as gs_block_body<STREAM>, but the row stream of a block reaches shared memory through a ring of TMA bulk
+// copies (cp.async.bulk onto an mbarrier per stage) instead of per-lane global loads, so that no warp ever waits for a DRAM
+// round trip of stream data:
+//   * a block's chunks are contiguous in the stream (chunk offsets are a prefix sum over the sweep positions), so a stage of
+//     GS_KC chunks is two bulk copies (GS_KC x 2 304 B of values, GS_KC x 128 B of codes);
+//   * warp 0 is the producer during phase A (one lane: wait for the slot's "empty" barrier, expect_tx, two bulk copies) and the
+//     on-chip substitution warp during phase B; it runs up to NST stages ahead, ACROSS the half boundary, so the first stages of
+//     the second half arrive while the first half's substitution runs;
+//   * the other warps consume whole chunks (one warp per chunk, round robin): values and codes from shared memory, x of final
+//     neighbours from L2, in-block couplings parked in Lt, one partial sum per chunk; the row sums are formed in chunk order by
+//     the substitution warp (deterministic);
+//   * per block the only dependent global round trips left are block_start -> (chunk offsets, node ids) -> stream / Dinv / rhs.
+constexpr int GS_KC = 4;                               // chunks per ring stage
+constexpr int GS_MAX_HALF_CHUNKS = GS_HALF * (W / 32); // a row has at most W / 32 chunks per direction
+template <int NST>
+struct __align__(16) GSRingShared {
+    double Lt[9][GS_PAIRS];
+    double val[NST][GS_KC][9][32];
+    int code[NST][GS_KC][32];
+    double s_x[2 * GS_HALF][3];
+    double s_dinv[GS_HALF][9];
+    double s_part[GS_MAX_HALF_CHUNKS][3];
+    int s_off[2 * GS_HALF + 1];
+    int s_seq[2 * GS_HALF];
+    unsigned char s_crow[GS_MAX_HALF_CHUNKS];
+    unsigned long long full[NST], empty[NST];
+};
+
+template <int THREADS, int NST>
+__device__ __forceinline__ void gs_ring_init(GSRingShared<NST>& sh)
+{
+    if (threadIdx.x == 0)
+        for (int k = 0; k < NST; ++k) {
+            mbar_init(&sh.full[k], 1);
+            mbar_init(&sh.empty[k], THREADS / 32 - 1);
+        }
+    __syncthreads();
+}
+
+// `gn`: ring stages this CTA has used so far (identical in every thread; slot = gn % NST, barrier parity from gn / NST)
+template <bool FWD, int THREADS, int NST>
+__device__ __forceinline__ void gs_block_ring(GSRingShared<NST>& sh, unsigned& gn, int b, const GSArgs& a)
+{
+    constexpr int NCW = THREADS / 32 - 1;
+    const int* __restrict__ soff = a.soff[FWD ? 0 : 1];
+    const int* __restrict__ scode = a.scode[FWD ? 0 : 1];
+    const double* __restrict__ sval = a.sval[FWD ? 0 : 1];
+    const double* rhs = FWD ? a.r : a.dhdu;
+    double* out = FWD ? a.hdu : a.du;
+    double* out_scaled = FWD ? a.dhdu : nullptr;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ps = a.block_start[b], pe = a.block_start[b + 1], nb = pe - ps;
+    __syncthreads(); // (coop form: the previous block of this CTA is done with s_off / s_seq / s_x)
+    for (int t = tid; t <= nb; t += THREADS) sh.s_off[t] = soff[ps + t];
+    for (int t = tid; t < nb; t += THREADS) sh.s_seq[t] = a.seq[FWD ? ps + t : pe - 1 - t]; // node of sweep-local index t
+    __syncthreads();
+    // chunk ranges of the two halves.  FWD: half h covers positions ps + h0 ..; BWD: positions pe - 1 - h0 downwards
+    const int nhalf = nb > GS_HALF ? 2 : 1;
+    int cb[2], nch[2], nst[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int h0 = h * GS_HALF, hn = min(GS_HALF, nb - h0);
+        if (h < nhalf) {
+            cb[h] = FWD ? sh.s_off[h0] : sh.s_off[nb - h0 - hn];
+            nch[h] = (FWD ? sh.s_off[h0 + hn] : sh.s_off[nb - h0]) - cb[h];
+        }
+        else { cb[h] = 0; nch[h] = 0; }
+        nst[h] = (nch[h] + GS_KC - 1) / GS_KC;
+    }
+    const unsigned base = gn;
+    const int total = nst[0] + nst[1];
+    int pi = 0; // producer: stages of this block issued so far
+    auto advance = [&](int limit) { // producer lane only
+        for (; pi < limit; ++pi) {
+            const int h = pi < nst[0] ? 0 : 1, n = pi - (h ? nst[0] : 0);
+            const unsigned g = base + (unsigned)pi, slot = g % NST, use = g / NST;
+            if (use > 0) mbar_wait(&sh.empty[slot], (use - 1) & 1);
+            const int k = min(GS_KC, nch[h] - GS_KC * n);
+            const size_t c0 = (size_t)cb[h] + (size_t)GS_KC * n;
+            mbar_expect_tx(&sh.full[slot], (unsigned)k * (9 * 32 * 8 + 32 * 4));
+            bulk_load(&sh.val[slot][0][0][0], sval + c0 * 9 * 32, (unsigned)k * 9 * 32 * 8, &sh.full[slot]);
+            bulk_load(&sh.code[slot][0][0], scode + c0 * 32, (unsigned)k * 32 * 4, &sh.full[slot]);
+        }
+    };
+    if (tid == 0) advance(min(total, NST));
+    for (int h = 0; h < nhalf; ++h) {
+        const int h0 = h * GS_HALF, hn = min(GS_HALF, nb - h0);
+        const int hbase = h ? nst[0] : 0;
+        __syncthreads(); // previous half's substitution is done: Lt free, its s_x visible
+        for (int e = tid; e < 9 * GS_PAIRS; e += THREADS) (&sh.Lt[0][0])[e] = 0.0;
+        for (int e = tid; e < hn * 9; e += THREADS) {
+            const int il = e / 9;
+            sh.s_dinv[il][e - 9 * il] = a.dinv[9 * (size_t)sh.s_seq[h0 + il] + (e - 9 * il)];
+        }
+        // position (relative to ps) of local row il, its chunk range relative to the half's first chunk
+        int my_o0 = 0, my_o1 = 0;
+        if (tid < hn) {
+            const int p = FWD ? h0 + tid : nb - 1 - h0 - tid;
+            my_o0 = sh.s_off[p] - cb[h];
+            my_o1 = sh.s_off[p + 1] - cb[h];
+            for (int c = my_o0; c < my_o1; ++c) sh.s_crow[c] = (unsigned char)tid;
+        }
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0; // right-hand side of this lane's row (substitution warp)
+        int node = -1;
+        if (warp == 0 && lane < hn) {
+            node = sh.s_seq[h0 + lane];
+            g0 = rhs[3 * (size_t)node]; g1 = rhs[3 * (size_t)node + 1]; g2 = rhs[3 * (size_t)node + 2];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            if (lane == 0) advance(min(total, hbase + nst[h] + NST));
+            __syncwarp();
+        }
+        else {
+            const int cw = warp - 1;
+            for (int n = 0; n < nst[h]; ++n) {
+                const unsigned g = base + (unsigned)(hbase + n), slot = g % NST;
+                mbar_wait(&sh.full[slot], (g / NST) & 1);
+                const int kn = min(GS_KC, nch[h] - GS_KC * n);
+                for (int kk = 0; kk < kn; ++kk) {
+                    const int ci = GS_KC * n + kk;
+                    if (ci % NCW != cw) continue; // warp-uniform
+                    const int il = sh.s_crow[ci];
+                    const int code = sh.code[slot][kk][lane];
+                    const double* vp = &sh.val[slot][kk][0][lane];
+                    const double v0 = vp[0], v1 = vp[32], v2 = vp[64], v3 = vp[96], v4 = vp[128], v5 = vp[160], v6 = vp[192], v7 = vp[224],
+                                 v8 = vp[256];
+                    double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+                    if (code != GS_PAD) {
+                        if (code >= 0) {
+                            x0 = out[3 * (size_t)code]; x1 = out[3 * (size_t)code + 1]; x2 = out[3 * (size_t)code + 2];
+                        }
+                        else {
+                            const int kl = -code - 1; // sweep-local index of an in-block neighbour (earlier in this direction)
+                            if (kl < h0) {
+                                x0 = sh.s_x[kl][0]; x1 = sh.s_x[kl][1]; x2 = sh.s_x[kl][2];
+                            }
+                            else { // same half: park Dinv_i * A_ik for the on-chip substitution
+                                const int e = gs_pair(il, kl - h0);
+                                const double* D = sh.s_dinv[il];
+                                const double D0 = D[0], D1 = D[1], D2 = D[2], D3 = D[3], D4 = D[4], D5 = D[5], D6 = D[6], D7 = D[7], D8 = D[8];
+                                sh.Lt[0][e] = D0 * v0 + D3 * v1 + D6 * v2; sh.Lt[1][e] = D1 * v0 + D4 * v1 + D7 * v2;
+                                sh.Lt[2][e] = D2 * v0 + D5 * v1 + D8 * v2; sh.Lt[3][e] = D0 * v3 + D3 * v4 + D6 * v5;
+                                sh.Lt[4][e] = D1 * v3 + D4 * v4 + D7 * v5; sh.Lt[5][e] = D2 * v3 + D5 * v4 + D8 * v5;
+                                sh.Lt[6][e] = D0 * v6 + D3 * v7 + D6 * v8; sh.Lt[7][e] = D1 * v6 + D4 * v7 + D7 * v8;
+                                sh.Lt[8][e] = D2 * v6 + D5 * v7 + D8 * v8;
+                            }
+                        }
+                    }
+                    double a0 = v0 * x0 + v3 * x1 + v6 * x2;
+                    double a1 = v1 * x0 + v4 * x1 + v7 * x2;
+                    double a2 = v2 * x0 + v5 * x1 + v8 * x2;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        a0 += __shfl_down_sync(0xffffffffu, a0, o);
+                        a1 += __shfl_down_sync(0xffffffffu, a1, o);
+                        a2 += __shfl_down_sync(0xffffffffu, a2, o);
+                    }
+                    if (lane == 0) { sh.s_part[ci][0] = a0; sh.s_part[ci][1] = a1; sh.s_part[ci][2] = a2; }
+                }
+                __syncwarp(); // every lane has read its slot entries
+                if (lane == 0) mbar_arrive(&sh.empty[slot]);
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // r~ = Dinv (rhs - external couplings), the row's chunk partials added in chunk order
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+            const bool row = lane < hn;
+            if (row) {
+                double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+                for (int c = my_o0; c < my_o1; ++c) { e0 += sh.s_part[c][0]; e1 += sh.s_part[c][1]; e2 += sh.s_part[c][2]; }
+                const double* D = sh.s_dinv[lane];
+                const double q0 = g0 - e0, q1 = g1 - e1, q2 = g2 - e2;
+                r0 = D[0] * q0 + D[3] * q1 + D[6] * q2;
+                r1 = D[1] * q0 + D[4] * q1 + D[7] * q2;
+                r2 = D[2] * q0 + D[5] * q1 + D[8] * q2;
+            }
+            // right-looking block forward substitution, one row per lane (as in gs_block_body)
+            double l[9], ln[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) l[q] = (row && lane > 0) ? sh.Lt[q][gs_pair(lane, 0)] : 0.0;
+            int en = lane - 1;
+            for (int k = 0; k < hn; ++k) {
+                const bool nxt = row && lane > k + 1 && k + 1 < hn;
+                en += GS_HALF - 2 - k;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) ln[q] = nxt ? sh.Lt[q][en] : 0.0;
+                const double x0 = __shfl_sync(0xffffffffu, r0, k);
+                const double x1 = __shfl_sync(0xffffffffu, r1, k);
+                const double x2 = __shfl_sync(0xffffffffu, r2, k);
+                if (lane > k) {
+                    r0 = fma(-l[6], x2, fma(-l[3], x1, fma(-l[0], x0, r0)));
+                    r1 = fma(-l[7], x2, fma(-l[4], x1, fma(-l[1], x0, r1)));
+                    r2 = fma(-l[8], x2, fma(-l[5], x1, fma(-l[2], x0, r2)));
+                }
+#pragma unroll
+                for (int q = 0; q < 9; ++q) l[q] = ln[q];
+            }
+            if (row) {
+                sh.s_x[h0 + lane][0] = r0; sh.s_x[h0 + lane][1] = r1; sh.s_x[h0 + lane][2] = r2;
+                out[3 * (size_t)node] = r0; out[3 * (size_t)node + 1] = r1; out[3 * (size_t)node + 2] = r2;
+                if (FWD && out_scaled) {
+                    const double* d = a.diag + 9 * (size_t)node;
+                    out_scaled[3 * (size_t)node] = d[0] * r0 + d[3] * r1 + d[6] * r2;
+                    out_scaled[3 * (size_t)node + 1] = d[1] * r0 + d[4] * r1 + d[7] * r2;
+                    out_scaled[3 * (size_t)node + 2] = d[2] * r0 + d[5] * r1 + d[8] * r2;
+                }
+            }
+        }
+    }
+    gn = base + (unsigned)total;
+}
+
+extern __shared__ __align__(16) unsigned char gs_dyn_smem[];
+constexpr int GS_RING_NST = 3;      // per-phase launches: 3 CTAs of 8 warps per SM, 3 x 9.5 KB of stream in flight each
+constexpr int GS_RING_NST_COOP = 6; // cooperative form (one 16-warp CTA per SM)
+
+template <bool FWD>
+__global__ void __launch_bounds__(GS_THREADS, 3) k_gs_block_ring(int b0, GSArgs a)
+{
+    GSRingShared<GS_RING_NST>& sh = *reinterpret_cast<GSRingShared<GS_RING_NST>*>(gs_dyn_smem);
+    gs_ring_init<GS_THREADS, GS_RING_NST>(sh);
+    unsigned gn = 0;
+    gs_block_ring<FWD, GS_THREADS, GS_RING_NST>(sh, gn, b0 + blockIdx.x, a);
+}
+
+// the whole symmetric sweep in one cooperative launch (k_gs_sweep with the ring form of the colour phases)
+template <int THREADS, int NST>
+__global__ void __launch_bounds__(THREADS) k_gs_sweep_ring(GSArgs a)
+{
+    GSRingShared<NST>& sh = *reinterpret_cast<GSRingShared<NST>*>(gs_dyn_smem);
+    cg::grid_group grid = cg::this_grid();
+    gs_ring_init<THREADS, NST>(sh);
+    unsigned gn = 0;
+    for (int c = 0; c < 8; ++c) {
+        for (int b = a.cfb[c] + blockIdx.x; b < a.cfb[c + 1]; b += gridDim.x) gs_block_ring<true, THREADS, NST>(sh, gn, b, a);
+        grid.sync();
+    }
+    for (int c = 7; c >= 0; --c) {
+        for (int b = a.cfb[c] + blockIdx.x; b < a.cfb[c + 1]; b += gridDim.x) gs_block_ring<false, THREADS, NST>(sh, gn, b, a);
+        grid.sync();
+    }
+    if (!a.fuse_update) return;
+    const int lane = threadIdx.x & 31;
+    const long nwarps = (long)gridDim.x * (THREADS / 32);
+    if (a.stream_update) {
+        for (long p = (long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); p < a.n; p += nwarps) gs_stream_update_row(a, (int)p, lane);
+        return;
+    }
+    for (long row = (long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); row < a.n; row += nwarps) {
+        const int* c = a.col + (size_t)row * W;
+        const double* v = a.val + (size_t)row * 9 * W;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int t = 0; t < W / 32; ++t) {
+            const int s = lane + 32 * t;
+            const int j = c[s];
+            const double x0 = a.du[3 * (size_t)j], x1 = a.du[3 * (size_t)j + 1], x2 = a.du[3 * (size_t)j + 2];
+            a0 += v[s] * x0 + v[3 * W + s] * x1 + v[6 * W + s] * x2;
+            a1 += v[W + s] * x0 + v[4 * W + s] * x1 + v[7 * W + s] * x2;
+            a2 += v[2 * W + s] * x0 + v[5 * W + s] * x1 + v[8 * W + s] * x2;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_down_sync(0xffffffffu, a0, o);
+            a1 += __shfl_down_sync(0xffffffffu, a1, o);
+            a2 += __shfl_down_sync(0xffffffffu, a2, o);
+        }
+        if (lane == 0) {
+            const size_t o = 3 * (size_t)row;
+            a.r[o] -= a0; a.r[o + 1] -= a1; a.r[o + 2] -= a2;
+            a.u[o] += a.du[o]; a.u[o + 1] += a.du[o + 1]; a.u[o + 2] += a.du[o + 2];
+        }
+    }
+}
+
+// ---- block-inverse form of the colour phases (default) --------------------------------------------------------------------
+// The on-chip substitution of a half block is a serial chain: 32 steps x (shuffle + 3 dependent fp64 FMA) ~ 7-8 k cycles per half,
+// ~16 k cycles (8 us) per block and colour phase that no amount of bandwidth removes (profiles/r1_gs_phase_stamps.txt) - more
+// than the whole stream of a block takes at the SM's share of HBM bandwidth.  But the matrix of that chain does not depend on the
+// iterate: with q = rhs - (couplings to nodes that are final before this half), the half's solution is
+//     x = (I + L~)^-1 Dinv q,   L~_ik = Dinv_i A_ik  (i, k in the half, k earlier),
+// so N = (I + L~)^-1 Dinv (lower block-triangular, diagonal blocks Dinv_i) is computed ONCE per hierarchy build
+// (k_gx_inverse) and a sweep applies it as a dense product: x_i = Dinv_i q_i + sum_{k<i} N_ik q_k.  No dependent chain is left in
+// a colour phase; it is a stream like the SpMV.  Rows i and hn-1-i of the strict lower triangle have i + (hn-1-i) = hn-1 <= 31
+// blocks together, so the inverse of a half packs into ceil(hn/2) stream chunks (chunk m: lanes [0,m) row m, lanes [m,hn-1)
+// row hn-1-m) - the same bytes as the in-half couplings it replaces.
+// Stream of one block, contiguous, in processing order:  [ext rows of half 0][inverse of half 0][ext rows of half 1][inverse 1]
+// ("ext" = couplings to other blocks, code = DOF id, and to the other half, code = -(local index) - 1).  A chunk is ONE record of
+// GX_REC doubles (9 x 32 values, then 32 codes), so it moves with one TMA bulk copy.  Both directions index their offsets by
+// sweep position in DIRECTION order (backward: n-1-p), so a block's chunks are consumed in ascending order.
+// Kernel structure: chunk ci of a block belongs to consumer warp ci % NCW.  Every consumer warp has its own ring of GX_D chunk
+// slots with a full / empty mbarrier pair per slot; lane w of warp 0 is the producer of consumer warp w (wait empty, expect_tx,
+// one cp.async.bulk) and runs ahead freely - it never joins the consumers' named barriers, so the stream keeps flowing through
+// the section boundaries, and in the cooperative form it requests the next colour's first chunks before the grid barrier.
+constexpr int GX_REC = 9 * 32 + 16;       // doubles per chunk record (2 432 bytes)
+constexpr int GX_D = 3;                   // ring slots per consumer warp
+__device__ __forceinline__ const int* gx_codes(const double* rec) { return reinterpret_cast<const int*>(rec + 9 * 32); }
+__device__ __forceinline__ int* gx_codes(double* rec) { return reinterpret_cast<int*>(rec + 9 * 32); }
+template <int NCW>
+struct __align__(16) GXShared {
+    double ring[NCW][GX_D][GX_REC];
+    double s_x[2 * GS_HALF][3];
+    double s_q[GS_HALF][3];
+    double s_dinv[GS_HALF][9];
+    double s_part[GS_MAX_HALF_CHUNKS][3];
+    int s_off[2 * GS_HALF + 1];
+    int s_seq[2 * GS_HALF];
+    unsigned char s_crow[GS_MAX_HALF_CHUNKS];
+    unsigned long long full[NCW][GX_D], empty[NCW][GX_D];
+};
+
+// pass 0 (FILL == false): chunk counts per direction-order position t (dir 0: p = t, dir 1: p = n-1-t); pass 1: the entries.
+// One warp per position.  The inverse sections are left to k_gx_inverse.  dir 0 also writes the in-half stream (dataI).
+template <bool FILL>
+__global__ void __launch_bounds__(TPB) k_gx_stream(int n, int dir, const int* __restrict__ seq, const int* __restrict__ rank,
+    const int* __restrict__ pblock, const int* __restrict__ block_start, const int* __restrict__ col, const double* __restrict__ val,
+    int* __restrict__ cntX, int* __restrict__ cntI, const int* __restrict__ offX, const int* __restrict__ offI, double* __restrict__ dataX,
+    double* __restrict__ dataI)
+{
+    const int t = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (t >= n) return;
+    const int p = dir ? n - 1 - t : t;
+    const int i = seq[p], b = pblock[p], ps = block_start[b], pe = block_start[b + 1];
+    const int gl = dir ? pe - 1 - p : p - ps, half = gl >> 5, h0 = half << 5, hn = min(GS_HALF, pe - ps - h0);
+    const bool last = gl == h0 + hn - 1;
+    int nX = 0, nI = 0;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int tt = 0; tt < W / 32; ++tt) {
+        const int sl = lane + 32 * tt;
+        const int j = col[(size_t)i * W + sl];
+        const int rj = (sl < 125 && j != i) ? rank[j] : p; // self / absent / padding slots: in neither set
+        const bool earlier = dir ? rj > p : rj < p;
+        const bool inblock = rj >= ps && rj < pe;
+        const int kl = dir ? pe - 1 - rj : rj - ps;
+        const bool same = earlier && inblock && (kl >> 5) == half;
+        const bool x = earlier && !same;
+        const unsigned mx = __ballot_sync(0xffffffffu, x), mi = __ballot_sync(0xffffffffu, same);
+        if (FILL) {
+            if (x || (same && dir == 0)) {
+                const int e = x ? nX + __popc(mx & lt) : nI + __popc(mi & lt);
+                const size_t c = (size_t)(x ? offX[t] : offI[t]) + (e >> 5);
+                const int l = e & 31;
+                double* rec = (x ? dataX : dataI) + c * GX_REC;
+                gx_codes(rec)[l] = inblock ? -(kl + 1) : j;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) rec[q * 32 + l] = val[((size_t)i * 9 + q) * W + sl];
+            }
+        }
+        nX += __popc(mx);
+        nI += __popc(mi);
+    }
+    if (!FILL) {
+        if (lane == 0) {
+            cntX[t] = ((nX + 31) >> 5) + (last ? (hn + 1) >> 1 : 0);
+            if (dir == 0) cntI[t] = (nI + 31) >> 5;
+        }
+        return;
+    }
+    for (int d = 0; d < (dir == 0 ? 2 : 1); ++d) { // pad the last chunk of the ext rows / the in-half rows
+        const int cnt = d ? nI : nX, e = cnt + lane;
+        if ((cnt & 31) != 0 && (e >> 5) == (cnt >> 5)) {
+            const size_t c = (size_t)(d ? offI[t] : offX[t]) + (e >> 5);
+            const int l = e & 31;
+            double* rec = (d ? dataI : dataX) + c * GX_REC;
+            gx_codes(rec)[l] = GS_PAD;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) rec[q * 32 + l] = 0.0;
+        }
+    }
+}
+
+// N = (I + L~)^-1 Dinv of one half block and direction, written into the half's inverse section of the stream.
+// CTA = (block, half), 128 threads: the in-half couplings Dinv_i A_ik are gathered from the fixed rows into shared memory (same
+// layout as gs_block_body's Lt), then thread (k, c) carries column (k, c) of N through a right-looking substitution: it starts
+// as column c of Dinv_k in block row k, and block row i > k receives -L~_ij t_j from every finished row j.
+constexpr int GXI_THREADS = 128;
+struct GXInvShared {
+    double Lt[9][GS_PAIRS];
+    double t[3 * GS_HALF][3 * GS_HALF]; // t[3 i + r][column]
+    double dinv[GS_HALF][9];
+};
+__global__ void __launch_bounds__(GXI_THREADS) k_gx_inverse(int dir, int n, const int* __restrict__ block_start, const int* __restrict__ seq,
+    const int* __restrict__ colrank, const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ dinv,
+    const int* __restrict__ xoff, double* __restrict__ xdata)
+{
+    GXInvShared& sh = *reinterpret_cast<GXInvShared*>(gs_dyn_smem);
+    const int b = blockIdx.x >> 1, half = blockIdx.x & 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ps = block_start[b], pe = block_start[b + 1], nb = pe - ps, h0 = half * GS_HALF;
+    if (h0 >= nb) return;
+    const int hn = min(GS_HALF, nb - h0);
+    for (int e = tid; e < 9 * GS_PAIRS; e += GXI_THREADS) (&sh.Lt[0][0])[e] = 0.0;
+    for (int e = tid; e < hn * 9; e += GXI_THREADS) {
+        const int il = e / 9, gl = h0 + il;
+        sh.dinv[il][e - 9 * il] = dinv[9 * (size_t)seq[dir ? pe - 1 - gl : ps + gl] + (e - 9 * il)];
+    }
+    __syncthreads();
+    for (int il = warp; il < hn; il += GXI_THREADS / 32) {
+        const int gl = h0 + il, p = dir ? pe - 1 - gl : ps + gl, i = seq[p];
+        const double* D = sh.dinv[il];
+#pragma unroll
+        for (int tt = 0; tt < W / 32; ++tt) {
+            const int sl = lane + 32 * tt;
+            const int j = col[(size_t)i * W + sl];
+            const int rj = (sl < 125 && j != i) ? colrank[(size_t)i * W + sl] : p;
+            const bool earlier = dir ? rj > p : rj < p;
+            const bool inblock = rj >= ps && rj < pe;
+            const int kl = dir ? pe - 1 - rj : rj - ps;
+            if (earlier && inblock && (kl >> 5) == half) {
+                const double* v = val + (size_t)i * 9 * W + sl;
+                const double v0 = v[0], v1 = v[W], v2 = v[2 * W], v3 = v[3 * W], v4 = v[4 * W], v5 = v[5 * W], v6 = v[6 * W], v7 = v[7 * W],
+                             v8 = v[8 * W];
+                const int e = gs_pair(il, kl - h0);
+                sh.Lt[0][e] = D[0] * v0 + D[3] * v1 + D[6] * v2; sh.Lt[1][e] = D[1] * v0 + D[4] * v1 + D[7] * v2;
+                sh.Lt[2][e] = D[2] * v0 + D[5] * v1 + D[8] * v2; sh.Lt[3][e] = D[0] * v3 + D[3] * v4 + D[6] * v5;
+                sh.Lt[4][e] = D[1] * v3 + D[4] * v4 + D[7] * v5; sh.Lt[5][e] = D[2] * v3 + D[5] * v4 + D[8] * v5;
+                sh.Lt[6][e] = D[0] * v6 + D[3] * v7 + D[6] * v8; sh.Lt[7][e] = D[1] * v6 + D[4] * v7 + D[7] * v8;
+                sh.Lt[8][e] = D[2] * v6 + D[5] * v7 + D[8] * v8;
+            }
+        }
+    }
+    // the inverse section of this half: the last ceil(hn / 2) chunks before the next half / block starts
+    const int T0 = dir ? n - pe : ps, mch = (hn + 1) >> 1;
+    double* M = xdata + ((size_t)xoff[T0 + h0 + hn] - mch) * GX_REC;
+    for (int e = tid; e < mch * GX_REC; e += GXI_THREADS) M[e] = 0.0;
+    __syncthreads();
+    for (int e = tid; e < mch * 32; e += GXI_THREADS) gx_codes(M + (size_t)(e >> 5) * GX_REC)[e & 31] = GS_PAD; // (unused by the sweeps)
+    const int tcol = tid, k = tcol / 3, c = tcol - 3 * k;
+    const bool valid = tcol < 3 * hn;
+    if (tcol < 3 * GS_HALF) {
+        for (int i = 0; i < hn; ++i)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) sh.t[3 * i + r][tcol] = (valid && i == k) ? sh.dinv[k][r + 3 * c] : 0.0;
+        // (all columns of a warp run the same j range, so the Lt reads are broadcasts; rows j < k of a column are zero)
+        const int j0 = (warp * 32) / 3;
+        for (int j = j0; j < hn - 1; ++j) {
+            const double t0 = sh.t[3 * j][tcol], t1 = sh.t[3 * j + 1][tcol], t2 = sh.t[3 * j + 2][tcol];
+            for (int i = j + 1; i < hn; ++i) {
+                const int e = gs_pair(i, j);
+                sh.t[3 * i][tcol] -= sh.Lt[0][e] * t0 + sh.Lt[3][e] * t1 + sh.Lt[6][e] * t2;
+                sh.t[3 * i + 1][tcol] -= sh.Lt[1][e] * t0 + sh.Lt[4][e] * t1 + sh.Lt[7][e] * t2;
+                sh.t[3 * i + 2][tcol] -= sh.Lt[2][e] * t0 + sh.Lt[5][e] * t1 + sh.Lt[8][e] * t2;
+            }
+        }
+        if (valid)
+            for (int i = k + 1; i < hn; ++i) {
+                const int m = i < mch ? i : hn - 1 - i, l = i < mch ? k : m + k;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) M[(size_t)m * GX_REC + (r + 3 * c) * 32 + l] = sh.t[3 * i + r][tcol];
+            }
+    }
+}
+
+// producer lane w (warp 0): the chunks of block b that belong to consumer warp w, from its `first`-th on, at most `limit` of them.
+// pn = chunks this lane has requested so far (slot = pn % GX_D).  Returns how many chunks of the block belong to warp w.
+template <bool FWD, int NCW>
+__device__ __forceinline__ int gx_produce(GXShared<NCW>& sh, unsigned& pn, int w, int b, const GSArgs& a, int first, int limit)
+{
+    const int d = FWD ? 0 : 1;
+    const int ps = a.block_start[b], pe = a.block_start[b + 1], T0 = FWD ? ps : a.n - pe;
+    const int C0 = a.xoff[d][T0], C = a.xoff[d][T0 + (pe - ps)] - C0;
+    const int mine = C > w ? (C - w + NCW - 1) / NCW : 0;
+    const int end = min(mine, limit);
+    for (int k = first; k < end; ++k) {
+        const unsigned slot = pn % GX_D, use = pn / GX_D;
+        if (use > 0) mbar_wait(&sh.empty[w][slot], (use - 1) & 1);
+        mbar_expect_tx(&sh.full[w][slot], (unsigned)(GX_REC * 8));
+        bulk_load(&sh.ring[w][slot][0], a.xdata[d] + ((size_t)C0 + (size_t)w + (size_t)k * NCW) * GX_REC, (unsigned)(GX_REC * 8), &sh.full[w][slot]);
+        ++pn;
+    }
+    return mine;
+}
+
+template <int NCT>
+__device__ __forceinline__ void gx_cbar() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
+
+#define GX_STAMP(k)                                  \
+    do {                                             \
+        if (dbg_st) g_gs_dbg[k] = clock64();         \
+    } while (0)
+// consumer warps (all warps but warp 0): one block of one colour phase.  wn: chunks this warp has consumed so far.
+template <bool FWD, int THREADS>
+__device__ __forceinline__ void gx_consume(GXShared<THREADS / 32 - 1>& sh, unsigned& wn, int b, const GSArgs& a)
+{
+    constexpr int NCW = THREADS / 32 - 1, NCT = NCW * 32;
+    const int d = FWD ? 0 : 1;
+    const double* rhs = FWD ? a.r : a.dhdu;
+    double* out = FWD ? a.hdu : a.du;
+    const int ct = threadIdx.x - 32, lane = threadIdx.x & 31, cw = (threadIdx.x >> 5) - 1;
+    const int ps = a.block_start[b], pe = a.block_start[b + 1], nb = pe - ps, T0 = FWD ? ps : a.n - pe;
+    const bool dbg_st = g_gs_dbg && b == g_gs_dbg[31] && threadIdx.x == 32; // profiling: clock stamps of the watched block
+    GX_STAMP(0);
+    gx_cbar<NCT>(); // the previous block of this CTA is done with the block tables
+    for (int t = ct; t <= nb; t += NCT) sh.s_off[t] = a.xoff[d][T0 + t];
+    for (int t = ct; t < nb; t += NCT) sh.s_seq[t] = a.seq[FWD ? ps + t : pe - 1 - t]; // node of sweep-local index t
+    gx_cbar<NCT>();
+    const int C0 = sh.s_off[0];
+    GX_STAMP(1);
+    // this warp's next chunk of the block; its record once it has arrived
+    int ci = cw;
+    auto acquire = [&]() -> const double* {
+        const unsigned slot = wn % GX_D;
+        mbar_wait(&sh.full[cw][slot], (wn / GX_D) & 1);
+        return &sh.ring[cw][slot][0];
+    };
+    auto release = [&]() {
+        __syncwarp(); // every lane has read its entries of the record
+        if (lane == 0) mbar_arrive(&sh.empty[cw][wn % GX_D]);
+        ++wn;
+        ci += NCW;
+    };
+    const int nhalf = nb > GS_HALF ? 2 : 1;
+    for (int h = 0; h < nhalf; ++h) {
+        const int h0 = h * GS_HALF, hn = min(GS_HALF, nb - h0), mch = (hn + 1) >> 1;
+        const int e0 = sh.s_off[h0] - C0, m1 = sh.s_off[h0 + hn] - C0, e1 = m1 - mch; // ext chunks [e0, e1), inverse [e1, m1)
+        for (int e = ct; e < hn * 9; e += NCT) {
+            const int il = e / 9;
+            sh.s_dinv[il][e - 9 * il] = a.dinv[9 * (size_t)sh.s_seq[h0 + il] + (e - 9 * il)];
+        }
+        int o0 = 0, o1 = 0;
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+        if (ct < hn) { // local row ct: its ext chunks, its right-hand side
+            o0 = sh.s_off[h0 + ct] - C0;
+            o1 = ct == hn - 1 ? e1 : sh.s_off[h0 + ct + 1] - C0;
+            for (int c = o0; c < o1; ++c) sh.s_crow[c - e0] = (unsigned char)ct;
+            const int node = sh.s_seq[h0 + ct];
+            g0 = rhs[3 * (size_t)node]; g1 = rhs[3 * (size_t)node + 1]; g2 = rhs[3 * (size_t)node + 2];
+        }
+        gx_cbar<NCT>();
+        GX_STAMP(h ? 7 : 2);
+        for (; ci < e1; release()) {
+            const double* rec = acquire();
+            const int code = gx_codes(rec)[lane];
+            const double* vp = rec + lane;
+            const double v0 = vp[0], v1 = vp[32], v2 = vp[64], v3 = vp[96], v4 = vp[128], v5 = vp[160], v6 = vp[192], v7 = vp[224], v8 = vp[256];
+            double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+            if (code != GS_PAD) {
+                if (code >= 0) {
+                    x0 = out[3 * (size_t)code]; x1 = out[3 * (size_t)code + 1]; x2 = out[3 * (size_t)code + 2];
+                }
+                else { // a node of the first half (final)
+                    const int kl = -code - 1;
+                    x0 = sh.s_x[kl][0]; x1 = sh.s_x[kl][1]; x2 = sh.s_x[kl][2];
+                }
+            }
+            double a0 = v0 * x0 + v3 * x1 + v6 * x2;
+            double a1 = v1 * x0 + v4 * x1 + v7 * x2;
+            double a2 = v2 * x0 + v5 * x1 + v8 * x2;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a0 += __shfl_down_sync(0xffffffffu, a0, o);
+                a1 += __shfl_down_sync(0xffffffffu, a1, o);
+                a2 += __shfl_down_sync(0xffffffffu, a2, o);
+            }
+            if (lane == 0) { sh.s_part[ci - e0][0] = a0; sh.s_part[ci - e0][1] = a1; sh.s_part[ci - e0][2] = a2; }
+        }
+        GX_STAMP(h ? 8 : 3);
+        gx_cbar<NCT>();
+        if (ct < hn) { // q = rhs - external couplings, the row's chunk partials added in chunk order
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            for (int c = o0; c < o1; ++c) { s0 += sh.s_part[c - e0][0]; s1 += sh.s_part[c - e0][1]; s2 += sh.s_part[c - e0][2]; }
+            sh.s_q[ct][0] = g0 - s0; sh.s_q[ct][1] = g1 - s1; sh.s_q[ct][2] = g2 - s2;
+        }
+        gx_cbar<NCT>();
+        GX_STAMP(h ? 9 : 4);
+        for (; ci < m1; release()) {
+            const double* rec = acquire();
+            const int m = ci - e1, rowB = hn - 1 - m;
+            const bool bvalid = rowB != m;
+            const bool inA = lane < m, inB = bvalid && lane >= m && lane < hn - 1;
+            const int k = inA ? lane : lane - m;
+            const double* vp = rec + lane;
+            const double v0 = vp[0], v1 = vp[32], v2 = vp[64], v3 = vp[96], v4 = vp[128], v5 = vp[160], v6 = vp[192], v7 = vp[224], v8 = vp[256];
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+            if (inA || inB) { q0 = sh.s_q[k][0]; q1 = sh.s_q[k][1]; q2 = sh.s_q[k][2]; }
+            const double p0 = v0 * q0 + v3 * q1 + v6 * q2;
+            const double p1 = v1 * q0 + v4 * q1 + v7 * q2;
+            const double p2 = v2 * q0 + v5 * q1 + v8 * q2;
+            double a0 = inA ? p0 : 0.0, a1 = inA ? p1 : 0.0, a2 = inA ? p2 : 0.0;
+            double b0 = inB ? p0 : 0.0, b1 = inB ? p1 : 0.0, b2 = inB ? p2 : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                b0 += __shfl_xor_sync(0xffffffffu, b0, o); b1 += __shfl_xor_sync(0xffffffffu, b1, o); b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+            }
+            if (lane == 0 || (lane == 1 && bvalid)) { // lane 0 finishes row m, lane 1 row hn-1-m: x = Dinv q + N q
+                const int il = lane == 0 ? m : rowB;
+                const double* D = sh.s_dinv[il];
+                const double u0 = sh.s_q[il][0], u1 = sh.s_q[il][1], u2 = sh.s_q[il][2];
+                const double x0 = (D[0] * u0 + D[3] * u1 + D[6] * u2) + (lane == 0 ? a0 : b0);
+                const double x1 = (D[1] * u0 + D[4] * u1 + D[7] * u2) + (lane == 0 ? a1 : b1);
+                const double x2 = (D[2] * u0 + D[5] * u1 + D[8] * u2) + (lane == 0 ? a2 : b2);
+                const int node = sh.s_seq[h0 + il];
+                sh.s_x[h0 + il][0] = x0; sh.s_x[h0 + il][1] = x1; sh.s_x[h0 + il][2] = x2;
+                out[3 * (size_t)node] = x0; out[3 * (size_t)node + 1] = x1; out[3 * (size_t)node + 2] = x2;
+                if (FWD) { // dhdu = D hdu (the "hdu = D hdu" pass of :292-293 fused)
+                    const double* dg = a.diag + 9 * (size_t)node;
+                    a.dhdu[3 * (size_t)node] = dg[0] * x0 + dg[3] * x1 + dg[6] * x2;
+                    a.dhdu[3 * (size_t)node + 1] = dg[1] * x0 + dg[4] * x1 + dg[7] * x2;
+                    a.dhdu[3 * (size_t)node + 2] = dg[2] * x0 + dg[5] * x1 + dg[8] * x2;
+                }
+            }
+        }
+        GX_STAMP(h ? 10 : 5);
+        gx_cbar<NCT>(); // s_x of this half visible to the next half's cross-half reads
+        GX_STAMP(h ? 11 : 6);
+    }
+}
+
+template <int THREADS>
+__device__ __forceinline__ void gx_init(GXShared<THREADS / 32 - 1>& sh)
+{
+    constexpr int NCW = THREADS / 32 - 1;
+    for (int e = threadIdx.x; e < NCW * GX_D; e += THREADS) {
+        mbar_init(&sh.full[e / GX_D][e % GX_D], 1);
+        mbar_init(&sh.empty[e / GX_D][e % GX_D], 1);
+    }
+    __syncthreads();
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(GS_THREADS, 3) k_gx_block(int b0, GSArgs a)
+{
+    constexpr int NCW = GS_THREADS / 32 - 1;
+    GXShared<NCW>& sh = *reinterpret_cast<GXShared<NCW>*>(gs_dyn_smem);
+    gx_init<GS_THREADS>(sh);
+    const int b = b0 + blockIdx.x;
+    if (threadIdx.x < 32) {
+        unsigned pn = 0;
+        if (threadIdx.x < NCW) gx_produce<FWD, NCW>(sh, pn, (int)threadIdx.x, b, a, 0, 1 << 30);
+    }
+    else {
+        unsigned wn = 0;
+        gx_consume<FWD, GS_THREADS>(sh, wn, b, a);
+    }
+}
+
+// The residual update r = L (hdu - du), u += du from the forward stream of the block-inverse form: a row's ext chunks plus its
+// in-half chunks (together the strictly-lower couplings of the sweep order)
+__device__ __forceinline__ void gx_update_chunks(const GSArgs& a, const double* __restrict__ data, int c0, int c1, int ps, int lane, double& a0,
+    double& a1, double& a2)
+{
+    for (int c = c0; c < c1; c += 2) {
+        int code[2];
+        double v[2][9];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const bool on = c + u < c1;
+            const double* rec = data + (size_t)(c + u) * GX_REC;
+            code[u] = on ? gx_codes(rec)[lane] : GS_PAD;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) v[u][q] = on ? rec[q * 32 + lane] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (code[u] != GS_PAD) {
+                const int j = code[u] >= 0 ? code[u] : a.seq[ps - code[u] - 1];
+                const double x0 = a.hdu[3 * (size_t)j] - a.du[3 * (size_t)j], x1 = a.hdu[3 * (size_t)j + 1] - a.du[3 * (size_t)j + 1],
+                             x2 = a.hdu[3 * (size_t)j + 2] - a.du[3 * (size_t)j + 2];
+                a0 += v[u][0] * x0 + v[u][3] * x1 + v[u][6] * x2;
+                a1 += v[u][1] * x0 + v[u][4] * x1 + v[u][7] * x2;
+                a2 += v[u][2] * x0 + v[u][5] * x1 + v[u][8] * x2;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void gx_update_row(const GSArgs& a, int p, int lane)
+{
+    const int i = a.seq[p], b = a.pblock[p], ps = a.block_start[b], pe = a.block_start[b + 1];
+    const int gl = p - ps, h0 = gl & ~(GS_HALF - 1), hn = min(GS_HALF, pe - ps - h0);
+    const int c0 = a.xoff[0][p], c1 = a.xoff[0][p + 1] - (gl == h0 + hn - 1 ? (hn + 1) >> 1 : 0);
+    const int i0 = a.ioff[p], i1 = a.ioff[p + 1];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    gx_update_chunks(a, a.xdata[0], c0, c1, ps, lane, a0, a1, a2);
+    gx_update_chunks(a, a.idata, i0, i1, ps, lane, a0, a1, a2);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o);
+        a1 += __shfl_down_sync(0xffffffffu, a1, o);
+        a2 += __shfl_down_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+        const size_t o = 3 * (size_t)i;
+        a.r[o] = a0; a.r[o + 1] = a1; a.r[o + 2] = a2;
+        a.u[o] += a.du[o]; a.u[o + 1] += a.du[o + 1]; a.u[o + 2] += a.du[o + 2];
+    }
+}
+__global__ void __launch_bounds__(TPB) k_gx_update(GSArgs a)
+{
+    const int p = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (p < a.n) gx_update_row(a, p, threadIdx.x & 31);
+}
+
+// the whole symmetric sweep in one cooperative launch.  The producer lanes run ahead of the grid barriers: the stream is static
+// data, so the first chunks of the next colour's first block are requested BEFORE the barrier that ends the current colour.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_gx_sweep(GSArgs a)
+{
+    constexpr int NCW = THREADS / 32 - 1;
+    GXShared<NCW>& sh = *reinterpret_cast<GXShared<NCW>*>(gs_dyn_smem);
+    cg::grid_group grid = cg::this_grid();
+    gx_init<THREADS>(sh);
+    unsigned cnt = 0; // consumer warp: chunks consumed; producer lane: chunks requested
+    int pre = 0;      // producer lane: chunks of the NEXT block already requested
+    for (int phase = 0; phase < 16; ++phase) {
+        const bool fwd = phase < 8;
+        const int c = fwd ? phase : 15 - phase;
+        if (threadIdx.x >= 32) {
+            for (int b = a.cfb[c] + blockIdx.x; b < a.cfb[c + 1]; b += gridDim.x) {
+                if (fwd) gx_consume<true, THREADS>(sh, cnt, b, a);
+                else gx_consume<false, THREADS>(sh, cnt, b, a);
+            }
+        }
+        else {
+            if (threadIdx.x < NCW) {
+                const int w = (int)threadIdx.x;
+                for (int b = a.cfb[c] + blockIdx.x; b < a.cfb[c + 1]; b += gridDim.x) {
+                    if (fwd) gx_produce<true, NCW>(sh, cnt, w, b, a, pre, 1 << 30);
+                    else gx_produce<false, NCW>(sh, cnt, w, b, a, pre, 1 << 30);
+                    pre = 0;
+                }
+                if (phase < 15) { // first block of the next phase
+                    const bool nf = phase + 1 < 8;
+                    const int nc = nf ? phase + 1 : 15 - (phase + 1);
+                    const int b = a.cfb[nc] + blockIdx.x;
+                    if (b < a.cfb[nc + 1]) {
+                        const int mine = nf ? gx_produce<true, NCW>(sh, cnt, w, b, a, 0, GX_D) : gx_produce<false, NCW>(sh, cnt, w, b, a, 0, GX_D);
+                        pre = min(mine, GX_D);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        grid.sync();
+    }
+    if (!a.fuse_update) return;
+    const int lane = threadIdx.x & 31;
+    const long nwarps = (long)gridDim.x * (THREADS / 32);
+    if (a.stream_update) {
+        for (long p = (long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); p < a.n; p += nwarps) gx_update_row(a, (int)p, lane);
         return;
     }
     for (long row = (long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); row < a.n; row += nwarps) {
@@ -878,6 +1669,51 @@ int reserve_level_vectors(Sim* s, MGLevel& L)
 }
 
 // (colour, first-seen block, node id) sweep order of markColors, MultigridPreconditioner.h:582-605
+// A/B switch, default on: Gauss-Seidel colour phases in block-inverse form (k_gx_*); 0: the substitution forms (k_gs_*)
+bool gs_inv_mode()
+{
+    static const bool on = !(getenv("HOT_GS_INV") && atoi(getenv("HOT_GS_INV")) == 0);
+    return on;
+}
+// streams of the block-inverse form: counts -> offsets -> entries -> inverse sections (once per hierarchy build)
+int build_gx_streams(Sim* s, MGLevel& L)
+{
+    cudaStream_t st = s->stream;
+    const int n = L.n;
+    int* cnt[3] = {s->scratch_i.p, s->scratch_i.p + n + 1, s->scratch_i.p + 2 * ((size_t)n + 1)}; // ext fwd, ext bwd, in-half fwd
+    HOT_CUDA(cudaMemsetAsync(s->scratch_i.p, 0, (3 * (size_t)n + 3) * sizeof(int), st));
+    for (int d = 0; d < 2; ++d) {
+        HOT_CUDA(L.gx_off[d].reserve((size_t)n + 1));
+        k_gx_stream<false><<<nblk(32L * n), TPB, 0, st>>>(n, d, L.gs_seq.p, L.gs_rank.p, L.gs_pblock.p, L.gs_block_start.p, L.col.p, L.val.p, cnt[d],
+            cnt[2], nullptr, nullptr, nullptr, nullptr);
+        HOT_LAUNCHED(s);
+    }
+    HOT_CUDA(L.gi_off.reserve((size_t)n + 1));
+    int* off[3] = {L.gx_off[0].p, L.gx_off[1].p, L.gi_off.p};
+    for (int k = 0; k < 3; ++k) {
+        int rc = with_tmp(s, [&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt[k], off[k], n + 1, st); });
+        if (rc) return rc;
+        HOT_CUDA(cudaMemcpyAsync(s->hcount + 12 + k, off[k] + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    HOT_CUDA(cudaStreamSynchronize(st));
+    for (int d = 0; d < 2; ++d) {
+        L.gx_chunks[d] = s->hcount[12 + d];
+        HOT_CUDA(L.gx_data[d].reserve((size_t)L.gx_chunks[d] * GX_REC + GX_REC));
+    }
+    L.gi_chunks = s->hcount[14];
+    HOT_CUDA(L.gi_data.reserve((size_t)L.gi_chunks * GX_REC + GX_REC));
+    HOT_FUNC_ATTR_ONCE(s, k_gx_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GXInvShared));
+    for (int d = 0; d < 2; ++d) {
+        k_gx_stream<true><<<nblk(32L * n), TPB, 0, st>>>(n, d, L.gs_seq.p, L.gs_rank.p, L.gs_pblock.p, L.gs_block_start.p, L.col.p, L.val.p, nullptr,
+            nullptr, L.gx_off[d].p, L.gi_off.p, L.gx_data[d].p, L.gi_data.p);
+        HOT_LAUNCHED(s);
+        k_gx_inverse<<<2 * L.n_blocks, GXI_THREADS, sizeof(GXInvShared), st>>>(d, n, L.gs_block_start.p, L.gs_seq.p, L.gs_colrank.p, L.col.p, L.val.p,
+            L.dinv.p, L.gx_off[d].p, L.gx_data[d].p);
+        HOT_LAUNCHED(s);
+    }
+    return 0;
+}
+
 int build_gs_schedule(Sim* s, MGLevel& L)
 {
     cudaStream_t st = s->stream;
@@ -887,7 +1723,7 @@ int build_gs_schedule(Sim* s, MGLevel& L)
     HOT_CUDA(s->cand_val.reserve(n));
     HOT_CUDA(s->cand_val_alt.reserve(n));
     HOT_CUDA(s->head_flag.reserve(n));
-    HOT_CUDA(s->scratch_i.reserve(2 * (size_t)n + 4));
+    HOT_CUDA(s->scratch_i.reserve(3 * (size_t)n + 8));
     HOT_CUDA(s->keys_alt.reserve(2 * (size_t)n));
     HOT_CUDA(s->dcount.reserve(16));
     HOT_CUDA(L.gs_seq.reserve(n));
@@ -938,14 +1774,15 @@ int build_gs_schedule(Sim* s, MGLevel& L)
     HOT_CUDA(cudaStreamSynchronize(st)); // &n is a stack variable
     L.color_first_block[0] = 0;
     for (int c = 0; c < 8; ++c) L.color_first_block[c + 1] = L.color_first_block[c] + s->hcount[1 + c];
-    // the per-direction row stream of the sweeps
     HOT_CUDA(L.gs_pblock.reserve(n));
+    k_gs_pblock<<<nblk(L.n_blocks), TPB, 0, st>>>(L.n_blocks, L.gs_block_start.p, L.gs_pblock.p);
+    HOT_LAUNCHED(s);
+    if (gs_inv_mode()) return build_gx_streams(s, L);
+    // the per-direction row stream of the sweeps
     HOT_CUDA(L.gs_off[0].reserve((size_t)n + 1));
     HOT_CUDA(L.gs_off[1].reserve((size_t)n + 1));
     int* cntF = s->scratch_i.p;
     int* cntB = s->scratch_i.p + n + 1;
-    k_gs_pblock<<<nblk(L.n_blocks), TPB, 0, st>>>(L.n_blocks, L.gs_block_start.p, L.gs_pblock.p);
-    HOT_LAUNCHED(s);
     HOT_CUDA(cudaMemsetAsync(s->scratch_i.p, 0, (2 * (size_t)n + 2) * sizeof(int), st));
     k_gs_stream<false><<<nblk(32L * n), TPB, 0, st>>>(n, L.gs_seq.p, L.gs_rank.p, L.gs_pblock.p, L.gs_block_start.p, L.col.p, L.val.p, cntF, cntB,
         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -1322,6 +2159,78 @@ int launch_gs_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
     return 0;
 }
 
+template <int THREADS, int NST>
+int launch_gs_sweep_ring(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
+{
+    static int per_sm_dev[64], n_sm_dev[64];
+    static bool init_dev[64] = {false};
+    const int dslot = s->device & 63;
+    if (!init_dev[dslot]) { per_sm_dev[dslot] = -1; n_sm_dev[dslot] = 0; init_dev[dslot] = true; }
+    int &per_sm = per_sm_dev[dslot], &n_sm = n_sm_dev[dslot];
+    constexpr size_t smem = sizeof(GSRingShared<NST>);
+    if (per_sm < 0) {
+        int dev = s->device, coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(k_gs_sweep_ring<THREADS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess
+            || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gs_sweep_ring<THREADS, NST>, THREADS, smem) != cudaSuccess || !coop) {
+            cudaGetLastError();
+            per_sm = 0;
+        }
+    }
+    *launched = false;
+    if (per_sm <= 0) return 0;
+    int grid = std::min(max_blocks_per_color, per_sm * n_sm);
+    if (a.fuse_update) grid = std::max(grid, std::min(per_sm * n_sm, (a.n + THREADS / 32 - 1) / (THREADS / 32)));
+    if (grid < 1) grid = 1;
+    void* params[] = {&a};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_gs_sweep_ring<THREADS, NST>, dim3(grid), dim3(THREADS), params, smem, s->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError(); // clear; fall back to per-phase launches
+        per_sm = 0;
+        return 0;
+    }
+    s->launches++;
+    *launched = true;
+    return 0;
+}
+
+template <int THREADS>
+int launch_gx_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
+{
+    static int per_sm_dev[64], n_sm_dev[64];
+    static bool init_dev[64] = {false};
+    const int dslot = s->device & 63;
+    if (!init_dev[dslot]) { per_sm_dev[dslot] = -1; n_sm_dev[dslot] = 0; init_dev[dslot] = true; }
+    int &per_sm = per_sm_dev[dslot], &n_sm = n_sm_dev[dslot];
+    constexpr size_t smem = sizeof(GXShared<THREADS / 32 - 1>);
+    if (per_sm < 0) {
+        int dev = s->device, coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(k_gx_sweep<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess
+            || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gx_sweep<THREADS>, THREADS, smem) != cudaSuccess || !coop) {
+            cudaGetLastError();
+            per_sm = 0;
+        }
+    }
+    *launched = false;
+    if (per_sm <= 0) return 0;
+    int grid = std::min(max_blocks_per_color, per_sm * n_sm);
+    if (a.fuse_update) grid = std::max(grid, std::min(per_sm * n_sm, (a.n + THREADS / 32 - 1) / (THREADS / 32)));
+    if (grid < 1) grid = 1;
+    void* params[] = {&a};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_gx_sweep<THREADS>, dim3(grid), dim3(THREADS), params, smem, s->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError(); // clear; fall back to per-phase launches
+        per_sm = 0;
+        return 0;
+    }
+    s->launches++;
+    *launched = true;
+    return 0;
+}
+
 // gs_smooth, MultigridPreconditioner.h:266-318
 int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
 {
@@ -1338,15 +2247,25 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
     a.val = L.val.p; a.dinv = L.dinv.p; a.diag = L.diag.p;
     a.r = r; a.hdu = L.tmp.p; a.dhdu = L.dAu.p; a.du = L.du.p; a.u = u; // hdu: unscaled forward solution; dhdu = D hdu
     a.fuse_update = project ? 0 : 1;
-    static const bool use_stream = !(getenv("HOT_GS_STREAM") && atoi(getenv("HOT_GS_STREAM")) == 0); // A/B switch, default on
+    const bool inv = gs_inv_mode(); // block-inverse form: its own streams (the substitution forms' streams are not built)
+    static const bool stream_env = !(getenv("HOT_GS_STREAM") && atoi(getenv("HOT_GS_STREAM")) == 0); // A/B switch, default on
+    const bool use_stream = stream_env && !inv;
+    for (int d = 0; d < 2; ++d) {
+        a.xoff[d] = inv ? L.gx_off[d].p : nullptr;
+        a.xdata[d] = inv ? L.gx_data[d].p : nullptr;
+    }
+    a.ioff = inv ? L.gi_off.p : nullptr; a.idata = inv ? L.gi_data.p : nullptr;
     for (int d = 0; d < 2; ++d) {
         a.soff[d] = use_stream ? L.gs_off[d].p : nullptr;
         a.scode[d] = use_stream ? L.gs_code[d].p : nullptr;
         a.sval[d] = use_stream ? L.gs_sval[d].p : nullptr;
     }
     a.pblock = L.gs_pblock.p;
+    // A/B switch, default on: the stream reaches shared memory through a ring of TMA bulk copies (gs_block_ring)
+    static const bool ring_env = !(getenv("HOT_GS_RING") && atoi(getenv("HOT_GS_RING")) == 0);
+    const bool use_ring = use_stream && ring_env;
     static const bool no_ident = getenv("HOT_GS_STREAM_UPDATE") && atoi(getenv("HOT_GS_STREAM_UPDATE")) == 0; // A/B switch
-    a.stream_update = (use_stream && !project && s->mg_Ainv == 1 && !no_ident) ? 1 : 0;
+    a.stream_update = ((use_stream || inv) && !project && s->mg_Ainv == 1 && !no_ident) ? 1 : 0;
     iterations = (iterations + 1) >> 1;
     static long long* dbg_dev = nullptr;
     const char* dbg_env = getenv("HOT_GS_DEBUG");
@@ -1364,29 +2283,51 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         // few blocks per colour: a big CTA per block (16 warps stream the rows) on one SM each; many: 3 CTAs of 8 warps per SM
         // (many blocks per colour: the per-phase launches below keep 3 CTAs per SM busy, which measures faster than the
         //  cooperative form whose register budget allows only 2)
-        static const bool force_coop = getenv("HOT_GS_COOP") != nullptr;
+        static const bool force_coop = getenv("HOT_GS_COOP") && atoi(getenv("HOT_GS_COOP")) != 0;
+        static const bool no_coop = getenv("HOT_GS_COOP") && atoi(getenv("HOT_GS_COOP")) == 0; // per-phase launches on every level
         const bool dist0 = level == 0 && s->world > 1; // partitioned level 0: a take-over exchange follows every colour phase
-        if (dist0) {}
-        else if (max_blocks <= 2 * 148) RC((use_stream ? launch_gs_sweep<512, true>(s, a, max_blocks, &launched) : launch_gs_sweep<512, false>(s, a, max_blocks, &launched)));
+        if (dist0 || no_coop) {}
+        else if (inv) {
+            if (max_blocks <= 2 * 148) RC((launch_gx_sweep<512>(s, a, max_blocks, &launched)));
+        }
+        else if (max_blocks <= 2 * 148) {
+            if (use_ring) RC((launch_gs_sweep_ring<512, GS_RING_NST_COOP>(s, a, max_blocks, &launched)));
+            else RC((use_stream ? launch_gs_sweep<512, true>(s, a, max_blocks, &launched) : launch_gs_sweep<512, false>(s, a, max_blocks, &launched)));
+        }
         else if (force_coop)
             RC((use_stream ? launch_gs_sweep<GS_THREADS, true>(s, a, max_blocks, &launched) : launch_gs_sweep<GS_THREADS, false>(s, a, max_blocks, &launched)));
         if (!launched) {
+            constexpr size_t ring_smem = sizeof(GSRingShared<GS_RING_NST>);
+            constexpr size_t gx_smem = sizeof(GXShared<GS_THREADS / 32 - 1>);
+            if (inv) {
+                HOT_FUNC_ATTR_ONCE(s, k_gx_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem);
+                HOT_FUNC_ATTR_ONCE(s, k_gx_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem);
+            }
+            if (use_ring) {
+                HOT_FUNC_ATTR_ONCE(s, k_gs_block_ring<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem);
+                HOT_FUNC_ATTR_ONCE(s, k_gs_block_ring<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem);
+            }
             for (int c = 0; c < 8; ++c) {
                 const int b0 = a.cfb[c], b1 = a.cfb[c + 1];
                 if (b1 == b0) continue;
-                (use_stream ? k_gs_block<true, true> : k_gs_block<true, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
+                if (inv) k_gx_block<true><<<b1 - b0, GS_THREADS, gx_smem, st>>>(b0, a);
+                else if (use_ring) k_gs_block_ring<true><<<b1 - b0, GS_THREADS, ring_smem, st>>>(b0, a);
+                else (use_stream ? k_gs_block<true, true> : k_gs_block<true, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
                 HOT_LAUNCHED(s);
                 if (dist0) RC(dist_takeover_shared(s, a.hdu, 3)); // later colours read this colour's values on pages other ranks own
             }
             for (int c = 7; c >= 0; --c) {
                 const int b0 = a.cfb[c], b1 = a.cfb[c + 1];
                 if (b1 == b0) continue;
-                (use_stream ? k_gs_block<false, true> : k_gs_block<false, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
+                if (inv) k_gx_block<false><<<b1 - b0, GS_THREADS, gx_smem, st>>>(b0, a);
+                else if (use_ring) k_gs_block_ring<false><<<b1 - b0, GS_THREADS, ring_smem, st>>>(b0, a);
+                else (use_stream ? k_gs_block<false, true> : k_gs_block<false, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
                 HOT_LAUNCHED(s);
                 if (dist0) RC(dist_takeover_shared(s, a.du, 3));
             }
             if (!project) {
-                if (a.stream_update) k_gs_stream_update<<<nblk(32L * L.n), TPB, 0, st>>>(a);
+                if (a.stream_update && inv) k_gx_update<<<nblk(32L * L.n), TPB, 0, st>>>(a);
+                else if (a.stream_update) k_gs_stream_update<<<nblk(32L * L.n), TPB, 0, st>>>(a);
                 else k_spmv_update<<<nblk(32L * L.n), TPB, 0, st>>>(L.n, L.col.p, L.val.p, L.du.p, u, r);
                 HOT_LAUNCHED(s);
                 if (dist0) RC(dist_takeover_shared(s, r, 3)); // (u += du is pointwise on consistent vectors)
@@ -1403,6 +2344,13 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         long long h[32];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, dbg_dev, sizeof h, cudaMemcpyDeviceToHost);
+        if (inv) {
+            fprintf(stderr, "[gx dbg] level %d n %d blocks/colour<=%d: entry->tables %lld | half0: prologue %lld ext %lld q %lld inverse %lld sync %lld | half1: prologue %lld ext %lld q %lld inverse %lld sync %lld | CTA 0 colour phases (work, grid.sync):",
+                level, L.n, max_blocks, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[8] - h[7], h[9] - h[8], h[10] - h[9], h[11] - h[10]);
+            for (int c = 0; c < 8; ++c) fprintf(stderr, " (%lld, %lld)", c ? h[12 + 2 * c] - h[11 + 2 * c] : 0LL, h[13 + 2 * c] - h[12 + 2 * c]);
+            fprintf(stderr, "\n");
+        }
+        else
         fprintf(stderr, "[gs dbg] level %d n %d blocks/colour<=%d: half0 wait %lld zero %lld phaseA %lld phaseB %lld | half1 wait %lld zero %lld phaseA %lld phaseB %lld cycles\n",
             level, L.n, max_blocks, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[8] - h[7]);
     }

@@ -413,7 +413,7 @@ class MpmSimulationB200:
         self._check(self._lib.hot_get_dv0(self._h, _ptr(out)))
         return out
 
-    OPS = {"hessian_apply": 0, "spmv": 1, "update_state": 2, "residual": 3, "smooth": 4, "build_matrix": 5, "build_mg": 6}
+    OPS = {"hessian_apply": 0, "spmv": 1, "update_state": 2, "residual": 3, "smooth": 4, "build_matrix": 5, "build_mg": 6, "coarse_solve": 7}
 
     def op_bench(self, op, reps=10, level=0):
         """milliseconds per application of one device-resident operator (CUDA events)"""

@@ -297,7 +297,9 @@ int hot_vcycle_timing(hot_sim* h, double* ms40, int* coarse_cg_iters);
 int hot_vcycle_bench(hot_sim* h, int reps, double* ms_total);
 /* `reps` device-resident applications of one operator (measurement hook of bench.py): op 0 matrix-free Hessian apply,
  * 1 block SpMV on `level`, 2 updateState, 3 computeResidual, 4 one -smoother call on `level`, 5 hot_build_matrix,
- * 6 hot_build_mg; total milliseconds (CUDA events on the handle's stream) */
+ * 6 hot_build_mg, 7 one -coarseSolver call on `level` (right-hand side: the level's restricted initial residual of the
+ * last hot_vcycle, so cg_smooth, MultigridPreconditioner.h:190-225, has to iterate; hot_vcycle_timing returns its count);
+ * total milliseconds (CUDA events on the handle's stream) */
 int hot_op_bench(hot_sim* h, int op, int level, int reps, double* ms_total);
 
 /* ---- a21, a22, a24: solvers and the time step ----------------------------------------------------------------------- */
