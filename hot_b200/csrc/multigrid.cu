@@ -1092,20 +1092,18 @@ __global__ void __launch_bounds__(THREADS) k_gs_sweep_ring(GSArgs a)
 // one cp.async.bulk) and runs ahead freely - it never joins the consumers' named barriers, so the stream keeps flowing through
 // the section boundaries, and in the cooperative form it requests the next colour's first chunks before the grid barrier.
 constexpr int GX_REC = 9 * 32 + 16;       // doubles per chunk record (2 432 bytes)
-constexpr int GX_D = 3;                   // ring slots per consumer warp
 __device__ __forceinline__ const int* gx_codes(const double* rec) { return reinterpret_cast<const int*>(rec + 9 * 32); }
 __device__ __forceinline__ int* gx_codes(double* rec) { return reinterpret_cast<int*>(rec + 9 * 32); }
-template <int NCW>
+template <int NCW, int D>
 struct __align__(16) GXShared {
-    double ring[NCW][GX_D][GX_REC];
+    double ring[NCW][D][GX_REC];
     double s_x[2 * GS_HALF][3];
     double s_q[GS_HALF][3];
     double s_dinv[GS_HALF][9];
-    double s_part[GS_MAX_HALF_CHUNKS][3];
     int s_off[2 * GS_HALF + 1];
     int s_seq[2 * GS_HALF];
-    unsigned char s_crow[GS_MAX_HALF_CHUNKS];
-    unsigned long long full[NCW][GX_D], empty[NCW][GX_D];
+    int p_off[2 * GS_HALF + 1]; // the producer warp's copy of its current block's chunk offsets (it runs ahead of the consumers)
+    unsigned long long full[NCW][D], empty[NCW][D];
 };
 
 // pass 0 (FILL == false): chunk counts per direction-order position t (dir 0: p = t, dir 1: p = n-1-t); pass 1: the entries.
@@ -1250,24 +1248,71 @@ __global__ void __launch_bounds__(GXI_THREADS) k_gx_inverse(int dir, int n, cons
     }
 }
 
-// producer lane w (warp 0): the chunks of block b that belong to consumer warp w, from its `first`-th on, at most `limit` of them.
-// pn = chunks this lane has requested so far (slot = pn % GX_D).  Returns how many chunks of the block belong to warp w.
-template <bool FWD, int NCW>
-__device__ __forceinline__ int gx_produce(GXShared<NCW>& sh, unsigned& pn, int w, int b, const GSArgs& a, int first, int limit)
+// producer lane w (warp 0): the chunks of block b that consumer warp w will ask for, in its order of consumption - per half the
+// ext chunks of rows w, w + NCW, ..., then the inverse chunks w, w + NCW, ... - from its `first`-th on, at most up to its
+// `limit`-th.  pn = chunks this lane has requested so far (slot = pn % D).  Returns how many of the block's chunks it passed.
+// The producer lanes share a warp: they walk one converged loop and only TEST their slot's empty barrier in it (a lane that
+// blocked on its consumer would hold up the requests of all the others).
+template <int NCW>
+struct GXIter {
+    const int* off;
+    int nb, w, h0, hn, mch, M0, il, c, c1, m;
+    bool inv;
+    __device__ __forceinline__ void half()
+    {
+        hn = min(GS_HALF, nb - h0); mch = (hn + 1) >> 1; M0 = off[h0 + hn] - mch;
+        il = w - NCW; c = c1 = 0; inv = false; m = w;
+    }
+    __device__ __forceinline__ void init(const int* off_, int nb_, int w_) { off = off_; nb = nb_; w = w_; h0 = 0; half(); }
+    __device__ __forceinline__ int next() // absolute chunk index, -1 when the block is exhausted
+    {
+        for (;;) {
+            if (!inv) {
+                if (c < c1) return c++;
+                il += NCW;
+                if (il < hn) { c = off[h0 + il]; c1 = il == hn - 1 ? M0 : off[h0 + il + 1]; }
+                else inv = true;
+            }
+            else {
+                if (m < mch) { const int r = M0 + m; m += NCW; return r; }
+                h0 += GS_HALF;
+                if (h0 >= nb) return -1;
+                half();
+            }
+        }
+    }
+};
+// (whole warp 0 calls this; lanes >= NCW only help loading the block's offsets into shared memory)
+template <bool FWD, int NCW, int D>
+__device__ __forceinline__ int gx_produce(GXShared<NCW, D>& sh, unsigned& pn, int w, int b, const GSArgs& a, int first, int limit)
 {
     const int d = FWD ? 0 : 1;
-    const int ps = a.block_start[b], pe = a.block_start[b + 1], T0 = FWD ? ps : a.n - pe;
-    const int C0 = a.xoff[d][T0], C = a.xoff[d][T0 + (pe - ps)] - C0;
-    const int mine = C > w ? (C - w + NCW - 1) / NCW : 0;
-    const int end = min(mine, limit);
-    for (int k = first; k < end; ++k) {
-        const unsigned slot = pn % GX_D, use = pn / GX_D;
-        if (use > 0) mbar_wait(&sh.empty[w][slot], (use - 1) & 1);
-        mbar_expect_tx(&sh.full[w][slot], (unsigned)(GX_REC * 8));
-        bulk_load(&sh.ring[w][slot][0], a.xdata[d] + ((size_t)C0 + (size_t)w + (size_t)k * NCW) * GX_REC, (unsigned)(GX_REC * 8), &sh.full[w][slot]);
-        ++pn;
+    const int ps = a.block_start[b], pe = a.block_start[b + 1], nb = pe - ps;
+    __syncwarp();
+    for (int t = w; t <= nb; t += 32) sh.p_off[t] = a.xoff[d][(FWD ? ps : a.n - pe) + t];
+    __syncwarp();
+    GXIter<NCW> it;
+    int k = 0, c = -1;
+    if (w < NCW) {
+        it.init(sh.p_off, nb, w);
+        c = it.next();
     }
-    return mine;
+    while (__any_sync(0xffffffffu, c >= 0 && k < limit)) {
+#pragma unroll 1
+        for (int rep = 0; rep < D; ++rep)
+            if (c >= 0 && k < limit) {
+                if (k < first) { ++k; c = it.next(); } // requested before (ahead of a grid barrier)
+                else {
+                    const unsigned slot = pn % D, use = pn / D;
+                    if (use == 0 || mbar_test(&sh.empty[w][slot], (use - 1) & 1)) {
+                        mbar_expect_tx(&sh.full[w][slot], (unsigned)(GX_REC * 8));
+                        bulk_load(&sh.ring[w][slot][0], a.xdata[d] + (size_t)c * GX_REC, (unsigned)(GX_REC * 8), &sh.full[w][slot]);
+                        ++pn; ++k; c = it.next();
+                    }
+                }
+            }
+    }
+    return k;
 }
 
 template <int NCT>
@@ -1278,8 +1323,10 @@ __device__ __forceinline__ void gx_cbar() { asm volatile("bar.sync 1, %0;" ::"n"
         if (dbg_st) g_gs_dbg[k] = clock64();         \
     } while (0)
 // consumer warps (all warps but warp 0): one block of one colour phase.  wn: chunks this warp has consumed so far.
-template <bool FWD, int THREADS>
-__device__ __forceinline__ void gx_consume(GXShared<THREADS / 32 - 1>& sh, unsigned& wn, int b, const GSArgs& a)
+// A warp owns whole rows: the (<= 4) ext chunks of a row are acquired together, their x gathers are in flight together, the lane
+// partials of all of them are summed in registers and reduced ONCE per row; q = rhs - sum goes straight to shared memory.
+template <bool FWD, int THREADS, int D>
+__device__ __forceinline__ void gx_consume(GXShared<THREADS / 32 - 1, D>& sh, unsigned& wn, int b, const GSArgs& a)
 {
     constexpr int NCW = THREADS / 32 - 1, NCT = NCW * 32;
     const int d = FWD ? 0 : 1;
@@ -1293,82 +1340,99 @@ __device__ __forceinline__ void gx_consume(GXShared<THREADS / 32 - 1>& sh, unsig
     for (int t = ct; t <= nb; t += NCT) sh.s_off[t] = a.xoff[d][T0 + t];
     for (int t = ct; t < nb; t += NCT) sh.s_seq[t] = a.seq[FWD ? ps + t : pe - 1 - t]; // node of sweep-local index t
     gx_cbar<NCT>();
-    const int C0 = sh.s_off[0];
     GX_STAMP(1);
-    // this warp's next chunk of the block; its record once it has arrived
-    int ci = cw;
-    auto acquire = [&]() -> const double* {
-        const unsigned slot = wn % GX_D;
-        mbar_wait(&sh.full[cw][slot], (wn / GX_D) & 1);
+    long long t_acq = 0, t_rows = 0; // profiling
+    int n_rows = 0, n_chunks = 0;
+    auto acquire = [&](unsigned k) -> const double* { // the k-th record from now on
+        const unsigned g = wn + k, slot = g % D;
+        const long long w0 = dbg_st ? clock64() : 0;
+        mbar_wait(&sh.full[cw][slot], (g / D) & 1);
+        if (dbg_st) t_acq += clock64() - w0;
         return &sh.ring[cw][slot][0];
     };
-    auto release = [&]() {
-        __syncwarp(); // every lane has read its entries of the record
-        if (lane == 0) mbar_arrive(&sh.empty[cw][wn % GX_D]);
-        ++wn;
-        ci += NCW;
+    auto release = [&](int n) {
+        __syncwarp(); // every lane has read its entries of the records
+        if (lane == 0)
+            for (int k = 0; k < n; ++k) mbar_arrive(&sh.empty[cw][(wn + (unsigned)k) % D]);
+        wn += (unsigned)n;
     };
     const int nhalf = nb > GS_HALF ? 2 : 1;
     for (int h = 0; h < nhalf; ++h) {
         const int h0 = h * GS_HALF, hn = min(GS_HALF, nb - h0), mch = (hn + 1) >> 1;
-        const int e0 = sh.s_off[h0] - C0, m1 = sh.s_off[h0 + hn] - C0, e1 = m1 - mch; // ext chunks [e0, e1), inverse [e1, m1)
+        const int M0 = sh.s_off[h0 + hn] - mch; // first inverse chunk of the half (absolute chunk index)
         for (int e = ct; e < hn * 9; e += NCT) {
             const int il = e / 9;
             sh.s_dinv[il][e - 9 * il] = a.dinv[9 * (size_t)sh.s_seq[h0 + il] + (e - 9 * il)];
         }
-        int o0 = 0, o1 = 0;
-        double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-        if (ct < hn) { // local row ct: its ext chunks, its right-hand side
-            o0 = sh.s_off[h0 + ct] - C0;
-            o1 = ct == hn - 1 ? e1 : sh.s_off[h0 + ct + 1] - C0;
-            for (int c = o0; c < o1; ++c) sh.s_crow[c - e0] = (unsigned char)ct;
-            const int node = sh.s_seq[h0 + ct];
-            g0 = rhs[3 * (size_t)node]; g1 = rhs[3 * (size_t)node + 1]; g2 = rhs[3 * (size_t)node + 2];
-        }
-        gx_cbar<NCT>();
         GX_STAMP(h ? 7 : 2);
-        for (; ci < e1; release()) {
-            const double* rec = acquire();
-            const int code = gx_codes(rec)[lane];
-            const double* vp = rec + lane;
-            const double v0 = vp[0], v1 = vp[32], v2 = vp[64], v3 = vp[96], v4 = vp[128], v5 = vp[160], v6 = vp[192], v7 = vp[224], v8 = vp[256];
-            double x0 = 0.0, x1 = 0.0, x2 = 0.0;
-            if (code != GS_PAD) {
-                if (code >= 0) {
-                    x0 = out[3 * (size_t)code]; x1 = out[3 * (size_t)code + 1]; x2 = out[3 * (size_t)code + 2];
-                }
-                else { // a node of the first half (final)
-                    const int kl = -code - 1;
-                    x0 = sh.s_x[kl][0]; x1 = sh.s_x[kl][1]; x2 = sh.s_x[kl][2];
-                }
+        for (int il = cw; il < hn; il += NCW) {
+            const int n = (il == hn - 1 ? M0 : sh.s_off[h0 + il + 1]) - sh.s_off[h0 + il]; // ext chunks of the row, <= W / 32
+            const long long rt0 = dbg_st ? clock64() : 0;
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+            if (lane == 0) {
+                const int node = sh.s_seq[h0 + il];
+                g0 = rhs[3 * (size_t)node]; g1 = rhs[3 * (size_t)node + 1]; g2 = rhs[3 * (size_t)node + 2];
             }
-            double a0 = v0 * x0 + v3 * x1 + v6 * x2;
-            double a1 = v1 * x0 + v4 * x1 + v7 * x2;
-            double a2 = v2 * x0 + v5 * x1 + v8 * x2;
+            // software pipeline over the row's chunks: the x gather of chunk k + 1 is in flight while chunk k is multiplied; a
+            // slot is released as soon as its values are in registers, so the producer stays D - 2 chunks ahead
+            auto fetch_x = [&](const double* rec, double& x0, double& x1, double& x2) {
+                const int code = gx_codes(rec)[lane];
+                x0 = x1 = x2 = 0.0;
+                if (code != GS_PAD) {
+                    if (code >= 0) {
+                        x0 = out[3 * (size_t)code]; x1 = out[3 * (size_t)code + 1]; x2 = out[3 * (size_t)code + 2];
+                    }
+                    else { // a node of the first half (final)
+                        const int kl = -code - 1;
+                        x0 = sh.s_x[kl][0]; x1 = sh.s_x[kl][1]; x2 = sh.s_x[kl][2];
+                    }
+                }
+            };
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0; // two accumulator sets (alternating chunks)
+            const double* rc = nullptr;
+            double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+            if (n > 0) {
+                rc = acquire(0u);
+                fetch_x(rc, x0, x1, x2);
+            }
+            for (int k = 0; k < n; ++k) {
+                const double* rn = nullptr;
+                double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+                if (k + 1 < n) {
+                    rn = acquire(1u);
+                    fetch_x(rn, y0, y1, y2);
+                }
+                const double* vp = rc + lane;
+                const double v0 = vp[0], v1 = vp[32], v2 = vp[64], v3 = vp[96], v4 = vp[128], v5 = vp[160], v6 = vp[192], v7 = vp[224], v8 = vp[256];
+                release(1);
+                if (k & 1) {
+                    b0 += v0 * x0 + v3 * x1 + v6 * x2; b1 += v1 * x0 + v4 * x1 + v7 * x2; b2 += v2 * x0 + v5 * x1 + v8 * x2;
+                }
+                else {
+                    a0 += v0 * x0 + v3 * x1 + v6 * x2; a1 += v1 * x0 + v4 * x1 + v7 * x2; a2 += v2 * x0 + v5 * x1 + v8 * x2;
+                }
+                rc = rn; x0 = y0; x1 = y1; x2 = y2;
+            }
+            a0 += b0; a1 += b1; a2 += b2;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 a0 += __shfl_down_sync(0xffffffffu, a0, o);
                 a1 += __shfl_down_sync(0xffffffffu, a1, o);
                 a2 += __shfl_down_sync(0xffffffffu, a2, o);
             }
-            if (lane == 0) { sh.s_part[ci - e0][0] = a0; sh.s_part[ci - e0][1] = a1; sh.s_part[ci - e0][2] = a2; }
+            if (lane == 0) { sh.s_q[il][0] = g0 - a0; sh.s_q[il][1] = g1 - a1; sh.s_q[il][2] = g2 - a2; } // q = rhs - external couplings
+            if (dbg_st) { t_rows += clock64() - rt0; ++n_rows; n_chunks += n; }
         }
         GX_STAMP(h ? 8 : 3);
-        gx_cbar<NCT>();
-        if (ct < hn) { // q = rhs - external couplings, the row's chunk partials added in chunk order
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-            for (int c = o0; c < o1; ++c) { s0 += sh.s_part[c - e0][0]; s1 += sh.s_part[c - e0][1]; s2 += sh.s_part[c - e0][2]; }
-            sh.s_q[ct][0] = g0 - s0; sh.s_q[ct][1] = g1 - s1; sh.s_q[ct][2] = g2 - s2;
-        }
-        gx_cbar<NCT>();
+        gx_cbar<NCT>(); // q of the half complete (and s_dinv)
         GX_STAMP(h ? 9 : 4);
-        for (; ci < m1; release()) {
-            const double* rec = acquire();
-            const int m = ci - e1, rowB = hn - 1 - m;
+        for (int m = cw; m < mch; m += NCW) {
+            const double* r0 = acquire(0u);
+            const int rowB = hn - 1 - m;
             const bool bvalid = rowB != m;
             const bool inA = lane < m, inB = bvalid && lane >= m && lane < hn - 1;
             const int k = inA ? lane : lane - m;
-            const double* vp = rec + lane;
+            const double* vp = r0 + lane;
             const double v0 = vp[0], v1 = vp[32], v2 = vp[64], v3 = vp[96], v4 = vp[128], v5 = vp[160], v6 = vp[192], v7 = vp[224], v8 = vp[256];
             double q0 = 0.0, q1 = 0.0, q2 = 0.0;
             if (inA || inB) { q0 = sh.s_q[k][0]; q1 = sh.s_q[k][1]; q2 = sh.s_q[k][2]; }
@@ -1399,38 +1463,42 @@ __device__ __forceinline__ void gx_consume(GXShared<THREADS / 32 - 1>& sh, unsig
                     a.dhdu[3 * (size_t)node + 2] = dg[2] * x0 + dg[5] * x1 + dg[8] * x2;
                 }
             }
+            release(1);
         }
         GX_STAMP(h ? 10 : 5);
-        gx_cbar<NCT>(); // s_x of this half visible to the next half's cross-half reads
+        gx_cbar<NCT>(); // s_x of this half visible to the next half's cross-half reads; s_q / s_dinv free
         GX_STAMP(h ? 11 : 6);
     }
+    if (dbg_st) { g_gs_dbg[12] = t_acq; g_gs_dbg[13] = t_rows; g_gs_dbg[14] = n_rows; g_gs_dbg[15] = n_chunks; }
 }
 
-template <int THREADS>
-__device__ __forceinline__ void gx_init(GXShared<THREADS / 32 - 1>& sh)
+template <int THREADS, int D>
+__device__ __forceinline__ void gx_init(GXShared<THREADS / 32 - 1, D>& sh)
 {
     constexpr int NCW = THREADS / 32 - 1;
-    for (int e = threadIdx.x; e < NCW * GX_D; e += THREADS) {
-        mbar_init(&sh.full[e / GX_D][e % GX_D], 1);
-        mbar_init(&sh.empty[e / GX_D][e % GX_D], 1);
+    for (int e = threadIdx.x; e < NCW * D; e += THREADS) {
+        mbar_init(&sh.full[e / D][e % D], 1);
+        mbar_init(&sh.empty[e / D][e % D], 1);
     }
     __syncthreads();
 }
 
-template <bool FWD>
-__global__ void __launch_bounds__(GS_THREADS, 3) k_gx_block(int b0, GSArgs a)
+// one colour phase per launch: (256 threads, depth 4) runs 3 CTAs per SM, (512, 4) one 15-consumer-warp CTA per SM - a phase lasts as
+// long as its largest block, so more warps per block beat more blocks per SM unless a colour has many waves of blocks
+template <bool FWD, int THREADS, int D, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_gx_block(int b0, GSArgs a)
 {
-    constexpr int NCW = GS_THREADS / 32 - 1;
-    GXShared<NCW>& sh = *reinterpret_cast<GXShared<NCW>*>(gs_dyn_smem);
-    gx_init<GS_THREADS>(sh);
+    constexpr int NCW = THREADS / 32 - 1;
+    GXShared<NCW, D>& sh = *reinterpret_cast<GXShared<NCW, D>*>(gs_dyn_smem);
+    gx_init<THREADS, D>(sh);
     const int b = b0 + blockIdx.x;
     if (threadIdx.x < 32) {
         unsigned pn = 0;
-        if (threadIdx.x < NCW) gx_produce<FWD, NCW>(sh, pn, (int)threadIdx.x, b, a, 0, 1 << 30);
+        gx_produce<FWD, NCW, D>(sh, pn, (int)threadIdx.x, b, a, 0, 1 << 30);
     }
     else {
         unsigned wn = 0;
-        gx_consume<FWD, GS_THREADS>(sh, wn, b, a);
+        gx_consume<FWD, THREADS, D>(sh, wn, b, a);
     }
 }
 
@@ -1492,13 +1560,13 @@ __global__ void __launch_bounds__(TPB) k_gx_update(GSArgs a)
 
 // the whole symmetric sweep in one cooperative launch.  The producer lanes run ahead of the grid barriers: the stream is static
 // data, so the first chunks of the next colour's first block are requested BEFORE the barrier that ends the current colour.
-template <int THREADS>
+template <int THREADS, int D>
 __global__ void __launch_bounds__(THREADS, 1) k_gx_sweep(GSArgs a)
 {
     constexpr int NCW = THREADS / 32 - 1;
-    GXShared<NCW>& sh = *reinterpret_cast<GXShared<NCW>*>(gs_dyn_smem);
+    GXShared<NCW, D>& sh = *reinterpret_cast<GXShared<NCW, D>*>(gs_dyn_smem);
     cg::grid_group grid = cg::this_grid();
-    gx_init<THREADS>(sh);
+    gx_init<THREADS, D>(sh);
     unsigned cnt = 0; // consumer warp: chunks consumed; producer lane: chunks requested
     int pre = 0;      // producer lane: chunks of the NEXT block already requested
     for (int phase = 0; phase < 16; ++phase) {
@@ -1506,16 +1574,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_gx_sweep(GSArgs a)
         const int c = fwd ? phase : 15 - phase;
         if (threadIdx.x >= 32) {
             for (int b = a.cfb[c] + blockIdx.x; b < a.cfb[c + 1]; b += gridDim.x) {
-                if (fwd) gx_consume<true, THREADS>(sh, cnt, b, a);
-                else gx_consume<false, THREADS>(sh, cnt, b, a);
+                if (fwd) gx_consume<true, THREADS, D>(sh, cnt, b, a);
+                else gx_consume<false, THREADS, D>(sh, cnt, b, a);
             }
         }
         else {
-            if (threadIdx.x < NCW) {
+            {
                 const int w = (int)threadIdx.x;
                 for (int b = a.cfb[c] + blockIdx.x; b < a.cfb[c + 1]; b += gridDim.x) {
-                    if (fwd) gx_produce<true, NCW>(sh, cnt, w, b, a, pre, 1 << 30);
-                    else gx_produce<false, NCW>(sh, cnt, w, b, a, pre, 1 << 30);
+                    if (fwd) gx_produce<true, NCW, D>(sh, cnt, w, b, a, pre, 1 << 30);
+                    else gx_produce<false, NCW, D>(sh, cnt, w, b, a, pre, 1 << 30);
                     pre = 0;
                 }
                 if (phase < 15) { // first block of the next phase
@@ -1523,8 +1591,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gx_sweep(GSArgs a)
                     const int nc = nf ? phase + 1 : 15 - (phase + 1);
                     const int b = a.cfb[nc] + blockIdx.x;
                     if (b < a.cfb[nc + 1]) {
-                        const int mine = nf ? gx_produce<true, NCW>(sh, cnt, w, b, a, 0, GX_D) : gx_produce<false, NCW>(sh, cnt, w, b, a, 0, GX_D);
-                        pre = min(mine, GX_D);
+                        const int mine = nf ? gx_produce<true, NCW, D>(sh, cnt, w, b, a, 0, D) : gx_produce<false, NCW, D>(sh, cnt, w, b, a, 0, D);
+                        pre = min(mine, D);
                     }
                 }
             }
@@ -2195,7 +2263,9 @@ int launch_gs_sweep_ring(Sim* s, GSArgs& a, int max_blocks_per_color, bool* laun
     return 0;
 }
 
-template <int THREADS>
+// cooperative form: one CTA per SM; every consumer warp owns about one row per half, so a block's critical path is one row
+constexpr int GX_COOP_THREADS = 1024, GX_COOP_D = 2;
+template <int THREADS, int D>
 int launch_gx_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
 {
     static int per_sm_dev[64], n_sm_dev[64];
@@ -2203,13 +2273,13 @@ int launch_gx_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
     const int dslot = s->device & 63;
     if (!init_dev[dslot]) { per_sm_dev[dslot] = -1; n_sm_dev[dslot] = 0; init_dev[dslot] = true; }
     int &per_sm = per_sm_dev[dslot], &n_sm = n_sm_dev[dslot];
-    constexpr size_t smem = sizeof(GXShared<THREADS / 32 - 1>);
+    constexpr size_t smem = sizeof(GXShared<THREADS / 32 - 1, D>);
     if (per_sm < 0) {
         int dev = s->device, coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(k_gx_sweep<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess
-            || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gx_sweep<THREADS>, THREADS, smem) != cudaSuccess || !coop) {
+        if (cudaFuncSetAttribute(k_gx_sweep<THREADS, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess
+            || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gx_sweep<THREADS, D>, THREADS, smem) != cudaSuccess || !coop) {
             cudaGetLastError();
             per_sm = 0;
         }
@@ -2220,7 +2290,7 @@ int launch_gx_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
     if (a.fuse_update) grid = std::max(grid, std::min(per_sm * n_sm, (a.n + THREADS / 32 - 1) / (THREADS / 32)));
     if (grid < 1) grid = 1;
     void* params[] = {&a};
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_gx_sweep<THREADS>, dim3(grid), dim3(THREADS), params, smem, s->stream);
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_gx_sweep<THREADS, D>, dim3(grid), dim3(THREADS), params, smem, s->stream);
     if (e != cudaSuccess) {
         cudaGetLastError(); // clear; fall back to per-phase launches
         per_sm = 0;
@@ -2288,7 +2358,11 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         const bool dist0 = level == 0 && s->world > 1; // partitioned level 0: a take-over exchange follows every colour phase
         if (dist0 || no_coop) {}
         else if (inv) {
-            if (max_blocks <= 2 * 148) RC((launch_gx_sweep<512>(s, a, max_blocks, &launched)));
+            static const int coop_cfg = getenv("HOT_GX_COOP") ? atoi(getenv("HOT_GX_COOP")) : 0; // A/B: consumer warps x ring depth
+            if (max_blocks > 2 * 148) {}
+            else if (coop_cfg == 0) RC((launch_gx_sweep<512, 4>(s, a, max_blocks, &launched)));
+            else if (coop_cfg == 2) RC((launch_gx_sweep<768, 3>(s, a, max_blocks, &launched)));
+            else RC((launch_gx_sweep<GX_COOP_THREADS, GX_COOP_D>(s, a, max_blocks, &launched)));
         }
         else if (max_blocks <= 2 * 148) {
             if (use_ring) RC((launch_gs_sweep_ring<512, GS_RING_NST_COOP>(s, a, max_blocks, &launched)));
@@ -2298,10 +2372,14 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
             RC((use_stream ? launch_gs_sweep<GS_THREADS, true>(s, a, max_blocks, &launched) : launch_gs_sweep<GS_THREADS, false>(s, a, max_blocks, &launched)));
         if (!launched) {
             constexpr size_t ring_smem = sizeof(GSRingShared<GS_RING_NST>);
-            constexpr size_t gx_smem = sizeof(GXShared<GS_THREADS / 32 - 1>);
+            constexpr size_t gx_smem = sizeof(GXShared<7, 4>), gx_smem_big = sizeof(GXShared<15, 4>);
+            static const int block_cfg = getenv("HOT_GX_BLOCK") ? atoi(getenv("HOT_GX_BLOCK")) : 1; // A/B: 0 = 3 x 256 threads per SM, 1 = 1 x 512
+            const bool big = block_cfg != 0;
             if (inv) {
-                HOT_FUNC_ATTR_ONCE(s, k_gx_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem);
-                HOT_FUNC_ATTR_ONCE(s, k_gx_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem);
+                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<true, 256, 4, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem);
+                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<false, 256, 4, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem);
+                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<true, 512, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem_big);
+                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<false, 512, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem_big);
             }
             if (use_ring) {
                 HOT_FUNC_ATTR_ONCE(s, k_gs_block_ring<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem);
@@ -2310,7 +2388,8 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
             for (int c = 0; c < 8; ++c) {
                 const int b0 = a.cfb[c], b1 = a.cfb[c + 1];
                 if (b1 == b0) continue;
-                if (inv) k_gx_block<true><<<b1 - b0, GS_THREADS, gx_smem, st>>>(b0, a);
+                if (inv && big) k_gx_block<true, 512, 4, 1><<<b1 - b0, 512, gx_smem_big, st>>>(b0, a);
+                else if (inv) k_gx_block<true, 256, 4, 3><<<b1 - b0, 256, gx_smem, st>>>(b0, a);
                 else if (use_ring) k_gs_block_ring<true><<<b1 - b0, GS_THREADS, ring_smem, st>>>(b0, a);
                 else (use_stream ? k_gs_block<true, true> : k_gs_block<true, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
                 HOT_LAUNCHED(s);
@@ -2319,7 +2398,8 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
             for (int c = 7; c >= 0; --c) {
                 const int b0 = a.cfb[c], b1 = a.cfb[c + 1];
                 if (b1 == b0) continue;
-                if (inv) k_gx_block<false><<<b1 - b0, GS_THREADS, gx_smem, st>>>(b0, a);
+                if (inv && big) k_gx_block<false, 512, 4, 1><<<b1 - b0, 512, gx_smem_big, st>>>(b0, a);
+                else if (inv) k_gx_block<false, 256, 4, 3><<<b1 - b0, 256, gx_smem, st>>>(b0, a);
                 else if (use_ring) k_gs_block_ring<false><<<b1 - b0, GS_THREADS, ring_smem, st>>>(b0, a);
                 else (use_stream ? k_gs_block<false, true> : k_gs_block<false, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
                 HOT_LAUNCHED(s);
@@ -2345,10 +2425,9 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         cudaStreamSynchronize(st);
         cudaMemcpy(h, dbg_dev, sizeof h, cudaMemcpyDeviceToHost);
         if (inv) {
-            fprintf(stderr, "[gx dbg] level %d n %d blocks/colour<=%d: entry->tables %lld | half0: prologue %lld ext %lld q %lld inverse %lld sync %lld | half1: prologue %lld ext %lld q %lld inverse %lld sync %lld | CTA 0 colour phases (work, grid.sync):",
+            fprintf(stderr, "[gx dbg] level %d n %d blocks/colour<=%d: entry->tables %lld | half0: prologue %lld ext %lld q %lld inverse %lld sync %lld | half1: prologue %lld ext %lld q %lld inverse %lld sync %lld |",
                 level, L.n, max_blocks, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[8] - h[7], h[9] - h[8], h[10] - h[9], h[11] - h[10]);
-            for (int c = 0; c < 8; ++c) fprintf(stderr, " (%lld, %lld)", c ? h[12 + 2 * c] - h[11 + 2 * c] : 0LL, h[13 + 2 * c] - h[12 + 2 * c]);
-            fprintf(stderr, "\n");
+            fprintf(stderr, " consumer warp 0: %lld rows, %lld ext chunks, %lld cycles in the row loop, %lld of them (+ inverse chunks) waiting for records\n", h[14], h[15], h[13], h[12]);
         }
         else
         fprintf(stderr, "[gs dbg] level %d n %d blocks/colour<=%d: half0 wait %lld zero %lld phaseA %lld phaseB %lld | half1 wait %lld zero %lld phaseA %lld phaseB %lld cycles\n",

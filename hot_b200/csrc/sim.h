@@ -483,6 +483,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
                      : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ bool mbar_test(unsigned long long* b, unsigned parity) // non-blocking
+{
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_addr(b)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_arrive(unsigned long long* b)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(b)) : "memory");
