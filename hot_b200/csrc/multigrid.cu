@@ -2358,7 +2358,9 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         const bool dist0 = level == 0 && s->world > 1; // partitioned level 0: a take-over exchange follows every colour phase
         if (dist0 || no_coop) {}
         else if (inv) {
-            static const int coop_cfg = getenv("HOT_GX_COOP") ? atoi(getenv("HOT_GX_COOP")) : 0; // A/B: consumer warps x ring depth
+            // A/B: consumer warps x ring depth of the cooperative form (measured at C2, GS level 1 / level 2: 0 = 15 x 4: 0.34 / 0.27 ms,
+            // 1 = 31 x 2: 0.45 / 0.34, 2 = 23 x 3: 0.39 / 0.32)
+            static const int coop_cfg = getenv("HOT_GX_COOP") ? atoi(getenv("HOT_GX_COOP")) : 0;
             if (max_blocks > 2 * 148) {}
             else if (coop_cfg == 0) RC((launch_gx_sweep<512, 4>(s, a, max_blocks, &launched)));
             else if (coop_cfg == 2) RC((launch_gx_sweep<768, 3>(s, a, max_blocks, &launched)));
@@ -2373,7 +2375,8 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         if (!launched) {
             constexpr size_t ring_smem = sizeof(GSRingShared<GS_RING_NST>);
             constexpr size_t gx_smem = sizeof(GXShared<7, 4>), gx_smem_big = sizeof(GXShared<15, 4>);
-            static const int block_cfg = getenv("HOT_GX_BLOCK") ? atoi(getenv("HOT_GX_BLOCK")) : 1; // A/B: 0 = 3 x 256 threads per SM, 1 = 1 x 512
+            // A/B: 0 = 3 CTAs of 256 threads per SM (measured: GS level 0 at C2 0.69 ms), 1 = one CTA of 512 threads (0.78 ms)
+            static const int block_cfg = getenv("HOT_GX_BLOCK") ? atoi(getenv("HOT_GX_BLOCK")) : 0;
             const bool big = block_cfg != 0;
             if (inv) {
                 HOT_FUNC_ATTR_ONCE(s, (k_gx_block<true, 256, 4, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem);
