@@ -127,7 +127,8 @@ int hot_set_plastic_state(hot_sim* h, const double* Jp);
  * ascending rank order on every sharer, so shared nodes carry bit-identical values on all their ranks and the gathers need no
  * communication.  DOF vectors are local (shared nodes replicated); dots / norms count a shared node on its lowest-ranked sharer
  * and all-reduce 1-3 scalars.  Node ids differ between ranks and from a single-GPU run: identify nodes by hot_get_id2coord.
- * Partitioned solver path: matrix-free PN-PCG (-lsolver 2 --matfree); the assembled-matrix / multigrid path is single-GPU.
+ * Partitioned solver paths: matrix-free PN-PCG (-lsolver 2 --matfree) as is; the assembled-matrix / multigrid / L-BFGS path with
+ * hot_set_ghost_ring (below).
  *
  * Transport, one of:
  *  - NCCL inside the library: rank 0 calls hot_comm_unique_id, the caller distributes the 128 bytes (MPI / torch.distributed / a
