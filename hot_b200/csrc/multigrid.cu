@@ -1099,11 +1099,13 @@ struct __align__(16) GXShared {
     double ring[NCW][D][GX_REC];
     double s_x[2 * GS_HALF][3];
     double s_q[GS_HALF][3];
-    double s_dinv[GS_HALF][9];
+    double s_dinv[2 * GS_HALF][9]; // Dinv and D of the block's nodes (sweep-local order), loaded once per block
+    double s_diag[2 * GS_HALF][9];
     int s_off[2 * GS_HALF + 1];
     int s_seq[2 * GS_HALF];
     int p_off[2 * GS_HALF + 1]; // the producer warp's copy of its current block's chunk offsets (it runs ahead of the consumers)
     unsigned long long full[NCW][D], empty[NCW][D];
+    unsigned long long cbar; // cluster form: barrier of the consumer warps of ALL CTAs of the cluster (count CL x NCW)
 };
 
 // pass 0 (FILL == false): chunk counts per direction-order position t (dir 0: p = t, dir 1: p = n-1-t); pass 1: the entries.
@@ -1256,25 +1258,29 @@ __global__ void __launch_bounds__(GXI_THREADS) k_gx_inverse(int dir, int n, cons
 template <int NCW>
 struct GXIter {
     const int* off;
-    int nb, w, h0, hn, mch, M0, il, c, c1, m;
+    int nb, w, stride, h0, hn, mch, M0, il, c, c1, m; // w: first row / inverse chunk of this worker, stride: number of workers
     bool inv;
     __device__ __forceinline__ void half()
     {
         hn = min(GS_HALF, nb - h0); mch = (hn + 1) >> 1; M0 = off[h0 + hn] - mch;
-        il = w - NCW; c = c1 = 0; inv = false; m = w;
+        il = w - stride; c = c1 = 0; inv = false; m = w;
     }
-    __device__ __forceinline__ void init(const int* off_, int nb_, int w_) { off = off_; nb = nb_; w = w_; h0 = 0; half(); }
+    __device__ __forceinline__ void init(const int* off_, int nb_, int w_, int stride_ = NCW)
+    {
+        off = off_; nb = nb_; w = w_; stride = stride_; h0 = 0;
+        half();
+    }
     __device__ __forceinline__ int next() // absolute chunk index, -1 when the block is exhausted
     {
         for (;;) {
             if (!inv) {
                 if (c < c1) return c++;
-                il += NCW;
+                il += stride;
                 if (il < hn) { c = off[h0 + il]; c1 = il == hn - 1 ? M0 : off[h0 + il + 1]; }
                 else inv = true;
             }
             else {
-                if (m < mch) { const int r = M0 + m; m += NCW; return r; }
+                if (m < mch) { const int r = M0 + m; m += stride; return r; }
                 h0 += GS_HALF;
                 if (h0 >= nb) return -1;
                 half();
@@ -1283,8 +1289,8 @@ struct GXIter {
     }
 };
 // (whole warp 0 calls this; lanes >= NCW only help loading the block's offsets into shared memory)
-template <bool FWD, int NCW, int D>
-__device__ __forceinline__ int gx_produce(GXShared<NCW, D>& sh, unsigned& pn, int w, int b, const GSArgs& a, int first, int limit)
+template <bool FWD, int NCW, int D, int CL = 1>
+__device__ __forceinline__ int gx_produce(GXShared<NCW, D>& sh, unsigned& pn, int w, int b, const GSArgs& a, int first, int limit, int crank = 0)
 {
     const int d = FWD ? 0 : 1;
     const int ps = a.block_start[b], pe = a.block_start[b + 1], nb = pe - ps;
@@ -1294,7 +1300,7 @@ __device__ __forceinline__ int gx_produce(GXShared<NCW, D>& sh, unsigned& pn, in
     GXIter<NCW> it;
     int k = 0, c = -1;
     if (w < NCW) {
-        it.init(sh.p_off, nb, w);
+        it.init(sh.p_off, nb, w * CL + crank, NCW * CL);
         c = it.next();
     }
     while (__any_sync(0xffffffffu, c >= 0 && k < limit)) {
@@ -1318,36 +1324,85 @@ __device__ __forceinline__ int gx_produce(GXShared<NCW, D>& sh, unsigned& pn, in
 template <int NCT>
 __device__ __forceinline__ void gx_cbar() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
 
+// ---- cluster form: one 4^3 block is swept by the CL CTAs of a thread-block cluster (rows il -> CTA il % CL), so CL SMs stream it.
+// q and x are replicated into every CTA's shared memory through distributed shared memory; the consumer warps of the whole cluster
+// meet on an mbarrier per CTA (every warp arrives remotely on all CL of them, release / acquire at cluster scope).
+__device__ __forceinline__ unsigned gx_cluster_rank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned gx_mapa(const void* p, unsigned cta)
+{
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr(p)), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void gx_st_cluster(unsigned addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+__device__ __forceinline__ void gx_cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int NCT, int CL>
+__device__ __forceinline__ void gx_csync(unsigned long long* cbar, unsigned& phase, int lane)
+{
+    if (CL == 1) { gx_cbar<NCT>(); return; }
+    __syncwarp();
+    if (lane == 0)
+        for (unsigned c = 0; c < (unsigned)CL; ++c)
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(gx_mapa(cbar, c)) : "memory");
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_addr(cbar)), "r"(phase & 1u)
+                     : "memory");
+    } while (!ok);
+    ++phase;
+}
+
+#ifdef HOT_GX_PROFILE // clock stamps of one watched block (HOT_GS_DEBUG=n), compiled in only for profiling builds
 #define GX_STAMP(k)                                  \
     do {                                             \
         if (dbg_st) g_gs_dbg[k] = clock64();         \
     } while (0)
+#else
+#define GX_STAMP(k) do { } while (0)
+#endif
 // consumer warps (all warps but warp 0): one block of one colour phase.  wn: chunks this warp has consumed so far.
 // A warp owns whole rows: the (<= 4) ext chunks of a row are acquired together, their x gathers are in flight together, the lane
 // partials of all of them are summed in registers and reduced ONCE per row; q = rhs - sum goes straight to shared memory.
-template <bool FWD, int THREADS, int D>
-__device__ __forceinline__ void gx_consume(GXShared<THREADS / 32 - 1, D>& sh, unsigned& wn, int b, const GSArgs& a)
+template <bool FWD, int THREADS, int D, int CL = 1>
+__device__ __forceinline__ void gx_consume(GXShared<THREADS / 32 - 1, D>& sh, unsigned& wn, int b, const GSArgs& a, int crank = 0)
 {
     constexpr int NCW = THREADS / 32 - 1, NCT = NCW * 32;
+    unsigned cphase = 0; // (cluster form: one block per kernel, so the barrier phases start at 0)
     const int d = FWD ? 0 : 1;
     const double* rhs = FWD ? a.r : a.dhdu;
     double* out = FWD ? a.hdu : a.du;
     const int ct = threadIdx.x - 32, lane = threadIdx.x & 31, cw = (threadIdx.x >> 5) - 1;
     const int ps = a.block_start[b], pe = a.block_start[b + 1], nb = pe - ps, T0 = FWD ? ps : a.n - pe;
-    const bool dbg_st = g_gs_dbg && b == g_gs_dbg[31] && threadIdx.x == 32; // profiling: clock stamps of the watched block
+#ifdef HOT_GX_PROFILE
+    const bool dbg_st = g_gs_dbg && b == g_gs_dbg[31] && threadIdx.x == 32;
+#endif
     GX_STAMP(0);
     gx_cbar<NCT>(); // the previous block of this CTA is done with the block tables
     for (int t = ct; t <= nb; t += NCT) sh.s_off[t] = a.xoff[d][T0 + t];
     for (int t = ct; t < nb; t += NCT) sh.s_seq[t] = a.seq[FWD ? ps + t : pe - 1 - t]; // node of sweep-local index t
     gx_cbar<NCT>();
     GX_STAMP(1);
-    long long t_acq = 0, t_rows = 0; // profiling
-    int n_rows = 0, n_chunks = 0;
+    // Dinv (and D for the fused dhdu = D hdu of the forward sweep) of every node of the block: requested now, first used after the
+    // first barrier of the half, so the round trip hides behind the ext rows
+    for (int e = ct; e < nb * 9; e += NCT) {
+        const int gl = e / 9, q = e - 9 * gl;
+        sh.s_dinv[gl][q] = a.dinv[9 * (size_t)sh.s_seq[gl] + q];
+        if (FWD) sh.s_diag[gl][q] = a.diag[9 * (size_t)sh.s_seq[gl] + q];
+    }
+
     auto acquire = [&](unsigned k) -> const double* { // the k-th record from now on
         const unsigned g = wn + k, slot = g % D;
-        const long long w0 = dbg_st ? clock64() : 0;
         mbar_wait(&sh.full[cw][slot], (g / D) & 1);
-        if (dbg_st) t_acq += clock64() - w0;
         return &sh.ring[cw][slot][0];
     };
     auto release = [&](int n) {
@@ -1360,16 +1415,11 @@ __device__ __forceinline__ void gx_consume(GXShared<THREADS / 32 - 1, D>& sh, un
     for (int h = 0; h < nhalf; ++h) {
         const int h0 = h * GS_HALF, hn = min(GS_HALF, nb - h0), mch = (hn + 1) >> 1;
         const int M0 = sh.s_off[h0 + hn] - mch; // first inverse chunk of the half (absolute chunk index)
-        for (int e = ct; e < hn * 9; e += NCT) {
-            const int il = e / 9;
-            sh.s_dinv[il][e - 9 * il] = a.dinv[9 * (size_t)sh.s_seq[h0 + il] + (e - 9 * il)];
-        }
         GX_STAMP(h ? 7 : 2);
-        for (int il = cw; il < hn; il += NCW) {
+        for (int il = cw * CL + crank; il < hn; il += NCW * CL) {
             const int n = (il == hn - 1 ? M0 : sh.s_off[h0 + il + 1]) - sh.s_off[h0 + il]; // ext chunks of the row, <= W / 32
-            const long long rt0 = dbg_st ? clock64() : 0;
             double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-            if (lane == 0) {
+            if (lane == 0) { // (a block-wide prefetch of the right-hand sides into shared memory costs a barrier: measured slower)
                 const int node = sh.s_seq[h0 + il];
                 g0 = rhs[3 * (size_t)node]; g1 = rhs[3 * (size_t)node + 1]; g2 = rhs[3 * (size_t)node + 2];
             }
@@ -1420,13 +1470,19 @@ __device__ __forceinline__ void gx_consume(GXShared<THREADS / 32 - 1, D>& sh, un
                 a1 += __shfl_down_sync(0xffffffffu, a1, o);
                 a2 += __shfl_down_sync(0xffffffffu, a2, o);
             }
-            if (lane == 0) { sh.s_q[il][0] = g0 - a0; sh.s_q[il][1] = g1 - a1; sh.s_q[il][2] = g2 - a2; } // q = rhs - external couplings
-            if (dbg_st) { t_rows += clock64() - rt0; ++n_rows; n_chunks += n; }
+            if (lane == 0) { // q = rhs - external couplings
+                if (CL == 1) { sh.s_q[il][0] = g0 - a0; sh.s_q[il][1] = g1 - a1; sh.s_q[il][2] = g2 - a2; }
+                else
+                    for (unsigned c = 0; c < (unsigned)CL; ++c) {
+                        const unsigned qa = gx_mapa(&sh.s_q[il][0], c);
+                        gx_st_cluster(qa, g0 - a0); gx_st_cluster(qa + 8, g1 - a1); gx_st_cluster(qa + 16, g2 - a2);
+                    }
+            }
         }
         GX_STAMP(h ? 8 : 3);
-        gx_cbar<NCT>(); // q of the half complete (and s_dinv)
+        gx_csync<NCT, CL>(&sh.cbar, cphase, lane); // q of the half complete (and s_dinv)
         GX_STAMP(h ? 9 : 4);
-        for (int m = cw; m < mch; m += NCW) {
+        for (int m = cw * CL + crank; m < mch; m += NCW * CL) {
             const double* r0 = acquire(0u);
             const int rowB = hn - 1 - m;
             const bool bvalid = rowB != m;
@@ -1448,16 +1504,21 @@ __device__ __forceinline__ void gx_consume(GXShared<THREADS / 32 - 1, D>& sh, un
             }
             if (lane == 0 || (lane == 1 && bvalid)) { // lane 0 finishes row m, lane 1 row hn-1-m: x = Dinv q + N q
                 const int il = lane == 0 ? m : rowB;
-                const double* D = sh.s_dinv[il];
+                const double* D = sh.s_dinv[h0 + il];
                 const double u0 = sh.s_q[il][0], u1 = sh.s_q[il][1], u2 = sh.s_q[il][2];
                 const double x0 = (D[0] * u0 + D[3] * u1 + D[6] * u2) + (lane == 0 ? a0 : b0);
                 const double x1 = (D[1] * u0 + D[4] * u1 + D[7] * u2) + (lane == 0 ? a1 : b1);
                 const double x2 = (D[2] * u0 + D[5] * u1 + D[8] * u2) + (lane == 0 ? a2 : b2);
                 const int node = sh.s_seq[h0 + il];
-                sh.s_x[h0 + il][0] = x0; sh.s_x[h0 + il][1] = x1; sh.s_x[h0 + il][2] = x2;
+                if (CL == 1) { sh.s_x[h0 + il][0] = x0; sh.s_x[h0 + il][1] = x1; sh.s_x[h0 + il][2] = x2; }
+                else
+                    for (unsigned c = 0; c < (unsigned)CL; ++c) {
+                        const unsigned xa = gx_mapa(&sh.s_x[h0 + il][0], c);
+                        gx_st_cluster(xa, x0); gx_st_cluster(xa + 8, x1); gx_st_cluster(xa + 16, x2);
+                    }
                 out[3 * (size_t)node] = x0; out[3 * (size_t)node + 1] = x1; out[3 * (size_t)node + 2] = x2;
                 if (FWD) { // dhdu = D hdu (the "hdu = D hdu" pass of :292-293 fused)
-                    const double* dg = a.diag + 9 * (size_t)node;
+                    const double* dg = sh.s_diag[h0 + il];
                     a.dhdu[3 * (size_t)node] = dg[0] * x0 + dg[3] * x1 + dg[6] * x2;
                     a.dhdu[3 * (size_t)node + 1] = dg[1] * x0 + dg[4] * x1 + dg[7] * x2;
                     a.dhdu[3 * (size_t)node + 2] = dg[2] * x0 + dg[5] * x1 + dg[8] * x2;
@@ -1466,10 +1527,9 @@ __device__ __forceinline__ void gx_consume(GXShared<THREADS / 32 - 1, D>& sh, un
             release(1);
         }
         GX_STAMP(h ? 10 : 5);
-        gx_cbar<NCT>(); // s_x of this half visible to the next half's cross-half reads; s_q / s_dinv free
+        gx_csync<NCT, CL>(&sh.cbar, cphase, lane); // s_x of this half visible to the next half's cross-half reads; s_q / s_dinv free
         GX_STAMP(h ? 11 : 6);
     }
-    if (dbg_st) { g_gs_dbg[12] = t_acq; g_gs_dbg[13] = t_rows; g_gs_dbg[14] = n_rows; g_gs_dbg[15] = n_chunks; }
 }
 
 template <int THREADS, int D>
@@ -1499,6 +1559,26 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gx_block(int b0, GSArgs a)
     else {
         unsigned wn = 0;
         gx_consume<FWD, THREADS, D>(sh, wn, b, a);
+    }
+}
+
+// cluster form of one colour phase: block b0 + blockIdx.x / CL is swept by the CL CTAs of a cluster
+template <bool FWD, int THREADS, int D, int MINB, int CL>
+__global__ void __launch_bounds__(THREADS, MINB) k_gx_block_cl(int b0, GSArgs a)
+{
+    constexpr int NCW = THREADS / 32 - 1;
+    GXShared<NCW, D>& sh = *reinterpret_cast<GXShared<NCW, D>*>(gs_dyn_smem);
+    if (threadIdx.x == 0) mbar_init(&sh.cbar, CL * NCW);
+    gx_init<THREADS, D>(sh);
+    gx_cluster_sync_all(); // every CTA's barriers exist before anybody arrives on them remotely
+    const int b = b0 + (int)blockIdx.x / CL, crank = (int)gx_cluster_rank();
+    if (threadIdx.x < 32) {
+        unsigned pn = 0;
+        gx_produce<FWD, NCW, D, CL>(sh, pn, (int)threadIdx.x, b, a, 0, 1 << 30, crank);
+    }
+    else {
+        unsigned wn = 0;
+        gx_consume<FWD, THREADS, D, CL>(sh, wn, b, a, crank);
     }
 }
 
@@ -1560,8 +1640,8 @@ __global__ void __launch_bounds__(TPB) k_gx_update(GSArgs a)
 
 // the whole symmetric sweep in one cooperative launch.  The producer lanes run ahead of the grid barriers: the stream is static
 // data, so the first chunks of the next colour's first block are requested BEFORE the barrier that ends the current colour.
-template <int THREADS, int D>
-__global__ void __launch_bounds__(THREADS, 1) k_gx_sweep(GSArgs a)
+template <int THREADS, int D, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_gx_sweep(GSArgs a)
 {
     constexpr int NCW = THREADS / 32 - 1;
     GXShared<NCW, D>& sh = *reinterpret_cast<GXShared<NCW, D>*>(gs_dyn_smem);
@@ -1737,6 +1817,11 @@ int reserve_level_vectors(Sim* s, MGLevel& L)
 }
 
 // (colour, first-seen block, node id) sweep order of markColors, MultigridPreconditioner.h:582-605
+int gx_cluster_cfg()
+{
+    static const int v = getenv("HOT_GX_CLUSTER") ? atoi(getenv("HOT_GX_CLUSTER")) : 0;
+    return (v == 2 || v == 4) ? v : 0;
+}
 // A/B switch, default on: Gauss-Seidel colour phases in block-inverse form (k_gx_*); 0: the substitution forms (k_gs_*)
 bool gs_inv_mode()
 {
@@ -2265,7 +2350,7 @@ int launch_gs_sweep_ring(Sim* s, GSArgs& a, int max_blocks_per_color, bool* laun
 
 // cooperative form: one CTA per SM; every consumer warp owns about one row per half, so a block's critical path is one row
 constexpr int GX_COOP_THREADS = 1024, GX_COOP_D = 2;
-template <int THREADS, int D>
+template <int THREADS, int D, int MINB>
 int launch_gx_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
 {
     static int per_sm_dev[64], n_sm_dev[64];
@@ -2278,19 +2363,19 @@ int launch_gx_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
         int dev = s->device, coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(k_gx_sweep<THREADS, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess
-            || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gx_sweep<THREADS, D>, THREADS, smem) != cudaSuccess || !coop) {
+        if (cudaFuncSetAttribute(k_gx_sweep<THREADS, D, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess
+            || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gx_sweep<THREADS, D, MINB>, THREADS, smem) != cudaSuccess || !coop) {
             cudaGetLastError();
             per_sm = 0;
         }
     }
     *launched = false;
-    if (per_sm <= 0) return 0;
+    if (per_sm <= 0 || max_blocks_per_color > per_sm * n_sm) return 0; // (every block of a colour needs its own resident CTA slot or a loop; keep one wave)
     int grid = std::min(max_blocks_per_color, per_sm * n_sm);
     if (a.fuse_update) grid = std::max(grid, std::min(per_sm * n_sm, (a.n + THREADS / 32 - 1) / (THREADS / 32)));
     if (grid < 1) grid = 1;
     void* params[] = {&a};
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_gx_sweep<THREADS, D>, dim3(grid), dim3(THREADS), params, smem, s->stream);
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_gx_sweep<THREADS, D, MINB>, dim3(grid), dim3(THREADS), params, smem, s->stream);
     if (e != cudaSuccess) {
         cudaGetLastError(); // clear; fall back to per-phase launches
         per_sm = 0;
@@ -2298,6 +2383,27 @@ int launch_gx_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
     }
     s->launches++;
     *launched = true;
+    return 0;
+}
+
+// one colour phase in cluster form: n_blocks clusters of CL CTAs
+template <bool FWD, int CL>
+int launch_gx_block_cl(Sim* s, int b0, int n_blocks, const GSArgs& a)
+{
+    constexpr int THREADS = 256, D = 4;
+    constexpr size_t smem = sizeof(GXShared<THREADS / 32 - 1, D>);
+    HOT_FUNC_ATTR_ONCE(s, (k_gx_block_cl<FWD, THREADS, D, 3, CL>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_blocks * CL));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HOT_CUDA(cudaLaunchKernelEx(&cfg, k_gx_block_cl<FWD, THREADS, D, 3, CL>, b0, a));
     return 0;
 }
 
@@ -2356,15 +2462,22 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         static const bool force_coop = getenv("HOT_GS_COOP") && atoi(getenv("HOT_GS_COOP")) != 0;
         static const bool no_coop = getenv("HOT_GS_COOP") && atoi(getenv("HOT_GS_COOP")) == 0; // per-phase launches on every level
         const bool dist0 = level == 0 && s->world > 1; // partitioned level 0: a take-over exchange follows every colour phase
-        if (dist0 || no_coop) {}
+        if (dist0 || no_coop || (inv && gx_cluster_cfg() > 1)) {}
         else if (inv) {
             // A/B: consumer warps x ring depth of the cooperative form (measured at C2, GS level 1 / level 2: 0 = 15 x 4: 0.34 / 0.27 ms,
             // 1 = 31 x 2: 0.45 / 0.34, 2 = 23 x 3: 0.39 / 0.32)
             static const int coop_cfg = getenv("HOT_GX_COOP") ? atoi(getenv("HOT_GX_COOP")) : 0;
-            if (max_blocks > 2 * 148) {}
-            else if (coop_cfg == 0) RC((launch_gx_sweep<512, 4>(s, a, max_blocks, &launched)));
-            else if (coop_cfg == 2) RC((launch_gx_sweep<768, 3>(s, a, max_blocks, &launched)));
-            else RC((launch_gx_sweep<GX_COOP_THREADS, GX_COOP_D>(s, a, max_blocks, &launched)));
+            // big levels (more than 2 blocks per SM and colour): the 3-CTAs-per-SM shape as ONE cooperative launch when a colour fits one wave
+            // (measured at C2, GS level 0: 0.80 ms against 0.66 ms for one launch per colour phase - register spills at 72 registers
+            //  and a 444-CTA grid barrier; off by default)
+            static const int coop0 = getenv("HOT_GX_COOP0") ? atoi(getenv("HOT_GX_COOP0")) : 0;
+            if (max_blocks > 2 * 148) {
+                if (coop0) RC((launch_gx_sweep<288, 3, 3>(s, a, max_blocks, &launched)));
+            }
+            else if (coop_cfg == 0) RC((launch_gx_sweep<512, 4, 1>(s, a, max_blocks, &launched)));
+            else if (coop_cfg == 2) RC((launch_gx_sweep<768, 3, 1>(s, a, max_blocks, &launched)));
+            else if (coop_cfg == 3) RC((launch_gx_sweep<288, 3, 3>(s, a, max_blocks, &launched)));
+            else RC((launch_gx_sweep<GX_COOP_THREADS, GX_COOP_D, 1>(s, a, max_blocks, &launched)));
         }
         else if (max_blocks <= 2 * 148) {
             if (use_ring) RC((launch_gs_sweep_ring<512, GS_RING_NST_COOP>(s, a, max_blocks, &launched)));
@@ -2374,13 +2487,17 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
             RC((use_stream ? launch_gs_sweep<GS_THREADS, true>(s, a, max_blocks, &launched) : launch_gs_sweep<GS_THREADS, false>(s, a, max_blocks, &launched)));
         if (!launched) {
             constexpr size_t ring_smem = sizeof(GSRingShared<GS_RING_NST>);
-            constexpr size_t gx_smem = sizeof(GXShared<7, 4>), gx_smem_big = sizeof(GXShared<15, 4>);
+            constexpr size_t gx_smem = sizeof(GXShared<8, 3>), gx_smem_big = sizeof(GXShared<15, 4>), gx_smem7 = sizeof(GXShared<7, 3>);
             // A/B: 0 = 3 CTAs of 256 threads per SM (measured: GS level 0 at C2 0.69 ms), 1 = one CTA of 512 threads (0.78 ms)
             static const int block_cfg = getenv("HOT_GX_BLOCK") ? atoi(getenv("HOT_GX_BLOCK")) : 0;
-            const bool big = block_cfg != 0;
+            const bool big = block_cfg == 1;
+            // A/B: sweep every block with a thread-block cluster of 2 / 4 CTAs (k_gx_block_cl); with it every level runs per-phase launches
+            const int cluster = gx_cluster_cfg();
             if (inv) {
-                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<true, 256, 4, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem);
-                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<false, 256, 4, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem);
+                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<true, 288, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem);
+                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<true, 256, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem7);
+                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<false, 288, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem);
+                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<false, 256, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem7);
                 HOT_FUNC_ATTR_ONCE(s, (k_gx_block<true, 512, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem_big);
                 HOT_FUNC_ATTR_ONCE(s, (k_gx_block<false, 512, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem_big);
             }
@@ -2391,8 +2508,11 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
             for (int c = 0; c < 8; ++c) {
                 const int b0 = a.cfb[c], b1 = a.cfb[c + 1];
                 if (b1 == b0) continue;
-                if (inv && big) k_gx_block<true, 512, 4, 1><<<b1 - b0, 512, gx_smem_big, st>>>(b0, a);
-                else if (inv) k_gx_block<true, 256, 4, 3><<<b1 - b0, 256, gx_smem, st>>>(b0, a);
+                if (inv && cluster == 2) RC((launch_gx_block_cl<true, 2>(s, b0, b1 - b0, a)));
+                else if (inv && cluster == 4) RC((launch_gx_block_cl<true, 4>(s, b0, b1 - b0, a)));
+                else if (inv && big) k_gx_block<true, 512, 4, 1><<<b1 - b0, 512, gx_smem_big, st>>>(b0, a);
+                else if (inv && block_cfg == 2) k_gx_block<true, 256, 3, 3><<<b1 - b0, 256, gx_smem7, st>>>(b0, a);
+                else if (inv) k_gx_block<true, 288, 3, 3><<<b1 - b0, 288, gx_smem, st>>>(b0, a);
                 else if (use_ring) k_gs_block_ring<true><<<b1 - b0, GS_THREADS, ring_smem, st>>>(b0, a);
                 else (use_stream ? k_gs_block<true, true> : k_gs_block<true, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
                 HOT_LAUNCHED(s);
@@ -2401,8 +2521,11 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
             for (int c = 7; c >= 0; --c) {
                 const int b0 = a.cfb[c], b1 = a.cfb[c + 1];
                 if (b1 == b0) continue;
-                if (inv && big) k_gx_block<false, 512, 4, 1><<<b1 - b0, 512, gx_smem_big, st>>>(b0, a);
-                else if (inv) k_gx_block<false, 256, 4, 3><<<b1 - b0, 256, gx_smem, st>>>(b0, a);
+                if (inv && cluster == 2) RC((launch_gx_block_cl<false, 2>(s, b0, b1 - b0, a)));
+                else if (inv && cluster == 4) RC((launch_gx_block_cl<false, 4>(s, b0, b1 - b0, a)));
+                else if (inv && big) k_gx_block<false, 512, 4, 1><<<b1 - b0, 512, gx_smem_big, st>>>(b0, a);
+                else if (inv && block_cfg == 2) k_gx_block<false, 256, 3, 3><<<b1 - b0, 256, gx_smem7, st>>>(b0, a);
+                else if (inv) k_gx_block<false, 288, 3, 3><<<b1 - b0, 288, gx_smem, st>>>(b0, a);
                 else if (use_ring) k_gs_block_ring<false><<<b1 - b0, GS_THREADS, ring_smem, st>>>(b0, a);
                 else (use_stream ? k_gs_block<false, true> : k_gs_block<false, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
                 HOT_LAUNCHED(s);
@@ -2430,7 +2553,7 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         if (inv) {
             fprintf(stderr, "[gx dbg] level %d n %d blocks/colour<=%d: entry->tables %lld | half0: prologue %lld ext %lld q %lld inverse %lld sync %lld | half1: prologue %lld ext %lld q %lld inverse %lld sync %lld |",
                 level, L.n, max_blocks, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[8] - h[7], h[9] - h[8], h[10] - h[9], h[11] - h[10]);
-            fprintf(stderr, " consumer warp 0: %lld rows, %lld ext chunks, %lld cycles in the row loop, %lld of them (+ inverse chunks) waiting for records\n", h[14], h[15], h[13], h[12]);
+            fprintf(stderr, "\n");
         }
         else
         fprintf(stderr, "[gs dbg] level %d n %d blocks/colour<=%d: half0 wait %lld zero %lld phaseA %lld phaseB %lld | half1 wait %lld zero %lld phaseA %lld phaseB %lld cycles\n",
