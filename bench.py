@@ -586,12 +586,15 @@ def run_ours(args):
         # (rank 0's kernels on rank 0's particles and rank 0's nodes: a per-GPU roofline at every N)
         alg = {"p2g": 128 * n + 32 * n_nodes, "g2p": 288 * n + 24 * n_nodes}
         per = {k: (kt[k][0] / kt[k][1]) for k in ("p2g", "g2p", "number_nodes", "transfer") if k in kt}   # transfer = shared-page exchange (N > 1; includes waiting for the neighbours)
-        dom = max(("p2g", "g2p"), key=lambda k: per.get(k, 0.0))
+        # dominant = the longer of the two transfer kernels; within 5 % of each other (they are at C2) the P2G scatter is reported, the
+        # kernel the round-1 review named and the one further from its roofline, so the headline fraction does not flip from run to run
+        dom = "g2p" if per.get("g2p", 0.0) > 1.05 * per.get("p2g", 0.0) else "p2g"
         ach = alg[dom] / (per[dom] * 1e-3) / 1e9
         kernel_name = {"p2g": "k_plane2_scatter<P2GPolicy>", "g2p": "k_g2p<true>"}[dom]
         roof = {"bound": "hbm", "kernel": kernel_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": ncu_traffic(dom), "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r2_traffic.json)",
                 "alg_bytes_per_launch": alg[dom], "peak_source": peak_src,
+                "selection": "longer of k_plane2_scatter<P2GPolicy> / k_g2p<true>; P2G when they are within 5 %",
                 "per_kernel": {k: {"ms": per[k], "alg_GBps": (alg[k] / (per[k] * 1e-3) / 1e9 if k in alg else None),
                                    "frac": (alg[k] / (per[k] * 1e-3) / 1e9 / peak if k in alg else None)} for k in per},
                 "combined_p2g_g2p": {"alg_bytes": alg["p2g"] + alg["g2p"], "frac": (alg["p2g"] + alg["g2p"]) / (ms_per_step * 1e-3) / 1e9 / peak}}

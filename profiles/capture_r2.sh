@@ -38,7 +38,7 @@ for key, n in seen.items():
 PY
 rm -f $O/r2_full_transfer.ncu-rep
 # full capture of the solver-side kernels: assembly, hierarchy, one V-cycle's worth of GS phases, SpMV
-timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:"k_gs_block|k_gs_sweep|k_gs_stream_update|k_spmv|k_assemble|k_mirror|k_galerkin" -c 30 \
+timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:"k_gx_block|k_gx_sweep|k_gx_update|k_gx_inverse|k_gx_stream|k_spmv|k_assemble|k_mirror|k_galerkin" -c 45 \
     -o $O/r2_full_solver -f python profiles/prof_gs.py > $O/r2_b_full2.log 2>&1
 python profiles/ncu_summary.py $O/r2_full_solver.ncu-rep $O/r2_ncu_full_solver.md > /dev/null
 rm -f $O/r2_full_solver.ncu-rep
@@ -50,12 +50,12 @@ fn = None; counts = collections.defaultdict(collections.Counter)
 for line in open("gpurun_out/all.sass", errors="replace"):
     m = re.search(r"Function : (\S+)", line)
     if m: fn = m.group(1); continue
-    for op in ("UBLKCP", "SYNCS", "LDGSTS", "UTMALDG", "RED.E", "ATOM", "ST.E.64.STRONG.SYS", "LD.E.64.STRONG.SYS", "DFMA", "DMMA", "HMMA"):
+    for op in ("UBLKCP", "SYNCS", "LDGSTS", "UTMALDG", "RED.E", "ATOM", "ST.E.64.STRONG.SYS", "LD.E.64.STRONG.SYS", "DFMA", "DMMA", "HMMA", "UCGABAR", "MAPA"):
         if fn and (" " + op) in line: counts[fn][op] += 1
 with open("gpurun_out/r2_sass_opcodes.md", "w") as f:
     f.write("| kernel (mangled, shortened) | opcode counts |\n|---|---|\n")
     for k, c in sorted(counts.items()):
-        if any(t in k for t in ("k_g2p", "k_hessian_gather", "k_plane2_scatter", "k_scatter_ws", "k_assemble", "k_pack_peer", "k_unpack_shared", "k_gs_block", "k_spmv", "k_update_state")):
+        if any(t in k for t in ("k_g2p", "k_hessian_gather", "k_plane2_scatter", "k_scatter_ws", "k_assemble", "k_pack_peer", "k_unpack_shared", "k_gs_block", "k_gx_block", "k_gx_sweep", "k_gx_update", "k_spmv", "k_update_state")):
             f.write(f"| {k[-70:]} | " + ", ".join(f"{o} {n}" for o, n in sorted(c.items())) + " |\n")
 PY
 rm -f $O/all.sass

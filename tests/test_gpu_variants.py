@@ -16,6 +16,7 @@ VARIANTS = [
     ({"HOT_G2P_TMA": "0", "HOT_HG_TMA": "0", "HOT_PF_DIST": "0"}, "test_gpu_transfer.py test_gpu_force.py",
      "g2p_parity or update_state_residual_multiply"),
     ({"HOT_GS_COOP": "0"}, "test_gpu_matrix.py", "smoother_parity or vcycle_parity"),       # block-inverse form, one launch per colour phase
+    ({"HOT_GX_CLUSTER": "2"}, "test_gpu_matrix.py", "smoother_parity or vcycle_parity"),    # a block swept by a cluster of 2 CTAs (DSMEM)
     ({"HOT_GS_STREAM_UPDATE": "0"}, "test_gpu_matrix.py", "smoother_parity or vcycle_parity"),
     ({"HOT_GS_INV": "0"}, "test_gpu_matrix.py", "smoother_parity or vcycle_parity"),        # substitution form, TMA ring
     ({"HOT_GS_INV": "0", "HOT_GS_COOP": "0"}, "test_gpu_matrix.py", "smoother_parity or vcycle_parity"),
