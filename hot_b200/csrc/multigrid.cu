@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(TPB) k_gs_stream(int n, const int* __restrict_
         const bool f = rj < p, bk = rj > p;
         const unsigned mf = __ballot_sync(0xffffffffu, f), mb = __ballot_sync(0xffffffffu, bk);
         if (FILL) {
-            if (f || bk) {
+            if (f || (bk && codeB)) { // (codeB == nullptr: forward stream only - the residual update of the block-inverse form)
                 const int e = f ? nF + __popc(mf & lt) : nB + __popc(mb & lt);
                 const size_t c = (size_t)(f ? offF[p] : offB[p]) + (e >> 5);
                 const int l = e & 31;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(TPB) k_gs_stream(int n, const int* __restrict_
         return;
     }
     // pad the last chunk of either direction
-    for (int d = 0; d < 2; ++d) {
+    for (int d = 0; d < (codeB ? 2 : 1); ++d) {
         const int cnt = d ? nB : nF, e = cnt + lane;
         if ((cnt & 31) != 0 && (e >> 5) == (cnt >> 5)) {
             const size_t c = (size_t)(d ? offB[p] : offF[p]) + (e >> 5);
@@ -1136,7 +1136,7 @@ __global__ void __launch_bounds__(TPB) k_gx_stream(int n, int dir, const int* __
         const bool x = earlier && !same;
         const unsigned mx = __ballot_sync(0xffffffffu, x), mi = __ballot_sync(0xffffffffu, same);
         if (FILL) {
-            if (x || (same && dir == 0)) {
+            if (x || (same && dir == 0 && dataI)) {
                 const int e = x ? nX + __popc(mx & lt) : nI + __popc(mi & lt);
                 const size_t c = (size_t)(x ? offX[t] : offI[t]) + (e >> 5);
                 const int l = e & 31;
@@ -1152,11 +1152,11 @@ __global__ void __launch_bounds__(TPB) k_gx_stream(int n, int dir, const int* __
     if (!FILL) {
         if (lane == 0) {
             cntX[t] = ((nX + 31) >> 5) + (last ? (hn + 1) >> 1 : 0);
-            if (dir == 0) cntI[t] = (nI + 31) >> 5;
+            if (dir == 0 && cntI) cntI[t] = (nI + 31) >> 5;
         }
         return;
     }
-    for (int d = 0; d < (dir == 0 ? 2 : 1); ++d) { // pad the last chunk of the ext rows / the in-half rows
+    for (int d = 0; d < ((dir == 0 && dataI) ? 2 : 1); ++d) { // pad the last chunk of the ext rows / the in-half rows
         const int cnt = d ? nI : nX, e = cnt + lane;
         if ((cnt & 31) != 0 && (e >> 5) == (cnt >> 5)) {
             const size_t c = (size_t)(d ? offI[t] : offX[t]) + (e >> 5);
@@ -1684,7 +1684,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gx_sweep(GSArgs a)
     const int lane = threadIdx.x & 31;
     const long nwarps = (long)gridDim.x * (THREADS / 32);
     if (a.stream_update) {
-        for (long p = (long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); p < a.n; p += nwarps) gx_update_row(a, (int)p, lane);
+        for (long p = (long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); p < a.n; p += nwarps) gs_stream_update_row(a, (int)p, lane);
         return;
     }
     for (long row = (long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); row < a.n; row += nwarps) {
@@ -1833,16 +1833,24 @@ int build_gx_streams(Sim* s, MGLevel& L)
 {
     cudaStream_t st = s->stream;
     const int n = L.n;
-    int* cnt[3] = {s->scratch_i.p, s->scratch_i.p + n + 1, s->scratch_i.p + 2 * ((size_t)n + 1)}; // ext fwd, ext bwd, in-half fwd
-    HOT_CUDA(cudaMemsetAsync(s->scratch_i.p, 0, (3 * (size_t)n + 3) * sizeof(int), st));
+    // cnt[0 / 1]: chunks per direction-order position of the block-inverse streams; cnt[2] / cnt[3]: chunks per sweep position of
+    // the FULL forward / backward row stream (k_gs_stream) - only the forward one is stored: the residual update r = L (hdu - du)
+    // reads every strictly-lower coupling of a row, and one stream with one partly filled last chunk per row (597 MB at C2 level 0)
+    // beats "ext rows + in-half rows" with two of them (837 MB measured)
+    HOT_CUDA(s->scratch_i.reserve(4 * (size_t)n + 8));
+    int* cnt[4] = {s->scratch_i.p, s->scratch_i.p + (n + 1), s->scratch_i.p + 2 * ((size_t)n + 1), s->scratch_i.p + 3 * ((size_t)n + 1)};
+    HOT_CUDA(cudaMemsetAsync(s->scratch_i.p, 0, (4 * (size_t)n + 4) * sizeof(int), st));
     for (int d = 0; d < 2; ++d) {
         HOT_CUDA(L.gx_off[d].reserve((size_t)n + 1));
         k_gx_stream<false><<<nblk(32L * n), TPB, 0, st>>>(n, d, L.gs_seq.p, L.gs_rank.p, L.gs_pblock.p, L.gs_block_start.p, L.col.p, L.val.p, cnt[d],
-            cnt[2], nullptr, nullptr, nullptr, nullptr);
+            nullptr, nullptr, nullptr, nullptr, nullptr);
         HOT_LAUNCHED(s);
     }
-    HOT_CUDA(L.gi_off.reserve((size_t)n + 1));
-    int* off[3] = {L.gx_off[0].p, L.gx_off[1].p, L.gi_off.p};
+    k_gs_stream<false><<<nblk(32L * n), TPB, 0, st>>>(n, L.gs_seq.p, L.gs_rank.p, L.gs_pblock.p, L.gs_block_start.p, L.col.p, L.val.p, cnt[2], cnt[3],
+        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    HOT_LAUNCHED(s);
+    HOT_CUDA(L.gs_off[0].reserve((size_t)n + 1));
+    int* off[3] = {L.gx_off[0].p, L.gx_off[1].p, L.gs_off[0].p};
     for (int k = 0; k < 3; ++k) {
         int rc = with_tmp(s, [&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, cnt[k], off[k], n + 1, st); });
         if (rc) return rc;
@@ -1853,17 +1861,22 @@ int build_gx_streams(Sim* s, MGLevel& L)
         L.gx_chunks[d] = s->hcount[12 + d];
         HOT_CUDA(L.gx_data[d].reserve((size_t)L.gx_chunks[d] * GX_REC + GX_REC));
     }
-    L.gi_chunks = s->hcount[14];
-    HOT_CUDA(L.gi_data.reserve((size_t)L.gi_chunks * GX_REC + GX_REC));
+    L.gs_chunks[0] = s->hcount[14];
+    L.gs_chunks[1] = 0;
+    HOT_CUDA(L.gs_code[0].reserve((size_t)L.gs_chunks[0] * 32 + 32));
+    HOT_CUDA(L.gs_sval[0].reserve((size_t)L.gs_chunks[0] * 9 * 32 + 32));
     HOT_FUNC_ATTR_ONCE(s, k_gx_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GXInvShared));
     for (int d = 0; d < 2; ++d) {
         k_gx_stream<true><<<nblk(32L * n), TPB, 0, st>>>(n, d, L.gs_seq.p, L.gs_rank.p, L.gs_pblock.p, L.gs_block_start.p, L.col.p, L.val.p, nullptr,
-            nullptr, L.gx_off[d].p, L.gi_off.p, L.gx_data[d].p, L.gi_data.p);
+            nullptr, L.gx_off[d].p, nullptr, L.gx_data[d].p, nullptr);
         HOT_LAUNCHED(s);
         k_gx_inverse<<<2 * L.n_blocks, GXI_THREADS, sizeof(GXInvShared), st>>>(d, n, L.gs_block_start.p, L.gs_seq.p, L.gs_colrank.p, L.col.p, L.val.p,
             L.dinv.p, L.gx_off[d].p, L.gx_data[d].p);
         HOT_LAUNCHED(s);
     }
+    k_gs_stream<true><<<nblk(32L * n), TPB, 0, st>>>(n, L.gs_seq.p, L.gs_rank.p, L.gs_pblock.p, L.gs_block_start.p, L.col.p, L.val.p, nullptr, nullptr,
+        L.gs_off[0].p, nullptr, L.gs_code[0].p, L.gs_sval[0].p, nullptr, nullptr);
+    HOT_LAUNCHED(s);
     return 0;
 }
 
@@ -2430,11 +2443,12 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         a.xoff[d] = inv ? L.gx_off[d].p : nullptr;
         a.xdata[d] = inv ? L.gx_data[d].p : nullptr;
     }
-    a.ioff = inv ? L.gi_off.p : nullptr; a.idata = inv ? L.gi_data.p : nullptr;
-    for (int d = 0; d < 2; ++d) {
-        a.soff[d] = use_stream ? L.gs_off[d].p : nullptr;
-        a.scode[d] = use_stream ? L.gs_code[d].p : nullptr;
-        a.sval[d] = use_stream ? L.gs_sval[d].p : nullptr;
+    a.ioff = nullptr; a.idata = nullptr; // (in-half forward stream: superseded by the full forward stream)
+    for (int d = 0; d < 2; ++d) { // (block-inverse form: the full forward stream only, for the residual update)
+        const bool have = use_stream || (inv && d == 0);
+        a.soff[d] = have ? L.gs_off[d].p : nullptr;
+        a.scode[d] = have ? L.gs_code[d].p : nullptr;
+        a.sval[d] = have ? L.gs_sval[d].p : nullptr;
     }
     a.pblock = L.gs_pblock.p;
     // A/B switch, default on: the stream reaches shared memory through a ring of TMA bulk copies (gs_block_ring)
@@ -2532,8 +2546,7 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
                 if (dist0) RC(dist_takeover_shared(s, a.du, 3));
             }
             if (!project) {
-                if (a.stream_update && inv) k_gx_update<<<nblk(32L * L.n), TPB, 0, st>>>(a);
-                else if (a.stream_update) k_gs_stream_update<<<nblk(32L * L.n), TPB, 0, st>>>(a);
+                if (a.stream_update) k_gs_stream_update<<<nblk(32L * L.n), TPB, 0, st>>>(a);
                 else k_spmv_update<<<nblk(32L * L.n), TPB, 0, st>>>(L.n, L.col.p, L.val.p, L.du.p, u, r);
                 HOT_LAUNCHED(s);
                 if (dist0) RC(dist_takeover_shared(s, r, 3)); // (u += du is pointwise on consistent vectors)
