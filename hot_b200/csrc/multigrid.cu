@@ -1399,7 +1399,10 @@ __device__ __forceinline__ void gx_consume(GXShared<THREADS / 32 - 1, D>& sh, un
         sh.s_dinv[gl][q] = a.dinv[9 * (size_t)sh.s_seq[gl] + q];
         if (FWD) sh.s_diag[gl][q] = a.diag[9 * (size_t)sh.s_seq[gl] + q];
     }
-
+    // Everything above (and the whole producer warp) touches only data that is static between hierarchy builds.  A colour phase
+    // launched as a programmatic dependent of the previous one (smooth_gs) gets this far while the previous colour still runs;
+    // the iterate (rhs, out) is read below.  Without a programmatic dependency this returns at once.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     auto acquire = [&](unsigned k) -> const double* { // the k-th record from now on
         const unsigned g = wn + k, slot = g % D;
         mbar_wait(&sh.full[cw][slot], (g / D) & 1);
@@ -1551,6 +1554,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gx_block(int b0, GSArgs a)
     constexpr int NCW = THREADS / 32 - 1;
     GXShared<NCW, D>& sh = *reinterpret_cast<GXShared<NCW, D>*>(gs_dyn_smem);
     gx_init<THREADS, D>(sh);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the next colour's CTAs may start their static prologue as slots free up
     const int b = b0 + blockIdx.x;
     if (threadIdx.x < 32) {
         unsigned pn = 0;
@@ -2399,6 +2403,28 @@ int launch_gx_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
     return 0;
 }
 
+// one colour phase of the default shape; `dependent`: launched with programmatic stream serialisation, i.e. its CTAs may start (and run
+// up to their griddepcontrol.wait) before the previous kernel of the stream has finished
+template <bool FWD>
+int launch_gx_block(Sim* s, int b0, int n_blocks, const GSArgs& a, bool dependent)
+{
+    constexpr int THREADS = 288, D = 3;
+    constexpr size_t smem = sizeof(GXShared<THREADS / 32 - 1, D>);
+    HOT_FUNC_ATTR_ONCE(s, (k_gx_block<FWD, THREADS, D, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_blocks);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = dependent ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HOT_CUDA(cudaLaunchKernelEx(&cfg, k_gx_block<FWD, THREADS, D, 3>, b0, a));
+    return 0;
+}
+
 // one colour phase in cluster form: n_blocks clusters of CL CTAs
 template <bool FWD, int CL>
 int launch_gx_block_cl(Sim* s, int b0, int n_blocks, const GSArgs& a)
@@ -2476,7 +2502,9 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         static const bool force_coop = getenv("HOT_GS_COOP") && atoi(getenv("HOT_GS_COOP")) != 0;
         static const bool no_coop = getenv("HOT_GS_COOP") && atoi(getenv("HOT_GS_COOP")) == 0; // per-phase launches on every level
         const bool dist0 = level == 0 && s->world > 1; // partitioned level 0: a take-over exchange follows every colour phase
-        if (dist0 || no_coop || (inv && gx_cluster_cfg() > 1)) {}
+        // block-inverse form: one launch per colour phase on EVERY level, phases 2..16 as programmatic dependents (measured at C2, GS level
+        // 1 / 2: 0.29 / 0.23 ms against 0.34 / 0.27 ms for the cooperative single-launch form, which stays behind HOT_GS_COOP=1)
+        if (dist0 || no_coop || (inv && (gx_cluster_cfg() > 1 || !force_coop))) {}
         else if (inv) {
             // A/B: consumer warps x ring depth of the cooperative form (measured at C2, GS level 1 / level 2: 0 = 15 x 4: 0.34 / 0.27 ms,
             // 1 = 31 x 2: 0.45 / 0.34, 2 = 23 x 3: 0.39 / 0.32)
@@ -2505,6 +2533,11 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
             // A/B: 0 = 3 CTAs of 256 threads per SM (measured: GS level 0 at C2 0.69 ms), 1 = one CTA of 512 threads (0.78 ms)
             static const int block_cfg = getenv("HOT_GX_BLOCK") ? atoi(getenv("HOT_GX_BLOCK")) : 0;
             const bool big = block_cfg == 1;
+            // colour phases 2..16 of a sweep as programmatic dependents of the phase before them (A/B: HOT_GX_PDL=0); not with the
+            // take-over exchanges of a partitioned level 0 in between
+            static const bool pdl_env = !(getenv("HOT_GX_PDL") && atoi(getenv("HOT_GX_PDL")) == 0);
+            const bool pdl = pdl_env && !dist0;
+            bool prev_phase = false; // the previous launch of this stream was a colour phase of this sweep
             // A/B: sweep every block with a thread-block cluster of 2 / 4 CTAs (k_gx_block_cl); with it every level runs per-phase launches
             const int cluster = gx_cluster_cfg();
             if (inv) {
@@ -2526,7 +2559,7 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
                 else if (inv && cluster == 4) RC((launch_gx_block_cl<true, 4>(s, b0, b1 - b0, a)));
                 else if (inv && big) k_gx_block<true, 512, 4, 1><<<b1 - b0, 512, gx_smem_big, st>>>(b0, a);
                 else if (inv && block_cfg == 2) k_gx_block<true, 256, 3, 3><<<b1 - b0, 256, gx_smem7, st>>>(b0, a);
-                else if (inv) k_gx_block<true, 288, 3, 3><<<b1 - b0, 288, gx_smem, st>>>(b0, a);
+                else if (inv) { RC((launch_gx_block<true>(s, b0, b1 - b0, a, pdl && prev_phase))); prev_phase = true; }
                 else if (use_ring) k_gs_block_ring<true><<<b1 - b0, GS_THREADS, ring_smem, st>>>(b0, a);
                 else (use_stream ? k_gs_block<true, true> : k_gs_block<true, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
                 HOT_LAUNCHED(s);
@@ -2539,7 +2572,7 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
                 else if (inv && cluster == 4) RC((launch_gx_block_cl<false, 4>(s, b0, b1 - b0, a)));
                 else if (inv && big) k_gx_block<false, 512, 4, 1><<<b1 - b0, 512, gx_smem_big, st>>>(b0, a);
                 else if (inv && block_cfg == 2) k_gx_block<false, 256, 3, 3><<<b1 - b0, 256, gx_smem7, st>>>(b0, a);
-                else if (inv) k_gx_block<false, 288, 3, 3><<<b1 - b0, 288, gx_smem, st>>>(b0, a);
+                else if (inv) { RC((launch_gx_block<false>(s, b0, b1 - b0, a, pdl && prev_phase))); prev_phase = true; }
                 else if (use_ring) k_gs_block_ring<false><<<b1 - b0, GS_THREADS, ring_smem, st>>>(b0, a);
                 else (use_stream ? k_gs_block<false, true> : k_gs_block<false, false>)<<<b1 - b0, GS_THREADS, 0, st>>>(b0, a);
                 HOT_LAUNCHED(s);

@@ -1,7 +1,7 @@
 """The A/B switches of the kernels (measured alternatives kept selectable through environment variables) must stay
 parity-green too: every variant re-runs the operator parity tests in a fresh process, because the switches are read once
 per process.  Default configuration: plane scatter (compact records) for P2G and the force / Hessian scatters, column scatter for the CN tolerance, TMA-staged
-G2P / Hessian gather, Gauss-Seidel colour phases in block-inverse form (stream through a ring of TMA bulk copies, one cooperative launch per sweep on small levels), stream-based residual update."""
+G2P / Hessian gather, Gauss-Seidel colour phases in block-inverse form (stream through per-warp rings of TMA bulk copies, one launch per colour phase with programmatic dependent launch), stream-based residual update."""
 import os
 import subprocess
 import sys
@@ -15,7 +15,8 @@ VARIANTS = [
     ({"HOT_SCATTER": "plane"}, "test_gpu_transfer.py test_gpu_force.py", "p2g_parity or update_state_residual_multiply or cn_tolerance"),
     ({"HOT_G2P_TMA": "0", "HOT_HG_TMA": "0", "HOT_PF_DIST": "0"}, "test_gpu_transfer.py test_gpu_force.py",
      "g2p_parity or update_state_residual_multiply"),
-    ({"HOT_GS_COOP": "0"}, "test_gpu_matrix.py", "smoother_parity or vcycle_parity"),       # block-inverse form, one launch per colour phase
+    ({"HOT_GS_COOP": "1"}, "test_gpu_matrix.py", "smoother_parity or vcycle_parity"),       # block-inverse form, one cooperative launch per sweep
+    ({"HOT_GX_PDL": "0"}, "test_gpu_matrix.py", "smoother_parity or vcycle_parity"),        # colour phases as fully serialised launches
     ({"HOT_GX_CLUSTER": "2"}, "test_gpu_matrix.py", "smoother_parity or vcycle_parity"),    # a block swept by a cluster of 2 CTAs (DSMEM)
     ({"HOT_GS_STREAM_UPDATE": "0"}, "test_gpu_matrix.py", "smoother_parity or vcycle_parity"),
     ({"HOT_GS_INV": "0"}, "test_gpu_matrix.py", "smoother_parity or vcycle_parity"),        # substitution form, TMA ring
