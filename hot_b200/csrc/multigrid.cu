@@ -669,11 +669,9 @@ struct GSArgs {
     const int* pblock; // block of every sweep position
     int stream_update; // the tail uses r_new = L (hdu - du) from the forward stream
     // block-inverse form (k_gx_*): per-direction stream [external rows | inverse section] per half block, indexed by sweep
-    // position in DIRECTION order (backward: n - 1 - p); forward in-half couplings for the residual update
+    // position in DIRECTION order (backward: n - 1 - p); the residual update reads the full forward row stream (soff[0] ...)
     const int* xoff[2];
     const double* xdata[2]; // chunk records of GX_REC doubles
-    const int* ioff;
-    const double* idata;
 };
 
 // Tail of gs_smooth (u += du, r -= A du, MultigridPreconditioner.h:311-314) from the forward stream.  With (D + L) hdu = r and
@@ -1109,12 +1107,11 @@ struct __align__(16) GXShared {
 };
 
 // pass 0 (FILL == false): chunk counts per direction-order position t (dir 0: p = t, dir 1: p = n-1-t); pass 1: the entries.
-// One warp per position.  The inverse sections are left to k_gx_inverse.  dir 0 also writes the in-half stream (dataI).
+// One warp per position.  In-half couplings are left out (the inverse sections, filled by k_gx_inverse, stand for them).
 template <bool FILL>
 __global__ void __launch_bounds__(TPB) k_gx_stream(int n, int dir, const int* __restrict__ seq, const int* __restrict__ rank,
     const int* __restrict__ pblock, const int* __restrict__ block_start, const int* __restrict__ col, const double* __restrict__ val,
-    int* __restrict__ cntX, int* __restrict__ cntI, const int* __restrict__ offX, const int* __restrict__ offI, double* __restrict__ dataX,
-    double* __restrict__ dataI)
+    int* __restrict__ cntX, const int* __restrict__ offX, double* __restrict__ dataX)
 {
     const int t = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (t >= n) return;
@@ -1122,7 +1119,7 @@ __global__ void __launch_bounds__(TPB) k_gx_stream(int n, int dir, const int* __
     const int i = seq[p], b = pblock[p], ps = block_start[b], pe = block_start[b + 1];
     const int gl = dir ? pe - 1 - p : p - ps, half = gl >> 5, h0 = half << 5, hn = min(GS_HALF, pe - ps - h0);
     const bool last = gl == h0 + hn - 1;
-    int nX = 0, nI = 0;
+    int nX = 0;
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
     for (int tt = 0; tt < W / 32; ++tt) {
@@ -1132,40 +1129,27 @@ __global__ void __launch_bounds__(TPB) k_gx_stream(int n, int dir, const int* __
         const bool earlier = dir ? rj > p : rj < p;
         const bool inblock = rj >= ps && rj < pe;
         const int kl = dir ? pe - 1 - rj : rj - ps;
-        const bool same = earlier && inblock && (kl >> 5) == half;
-        const bool x = earlier && !same;
-        const unsigned mx = __ballot_sync(0xffffffffu, x), mi = __ballot_sync(0xffffffffu, same);
-        if (FILL) {
-            if (x || (same && dir == 0 && dataI)) {
-                const int e = x ? nX + __popc(mx & lt) : nI + __popc(mi & lt);
-                const size_t c = (size_t)(x ? offX[t] : offI[t]) + (e >> 5);
-                const int l = e & 31;
-                double* rec = (x ? dataX : dataI) + c * GX_REC;
-                gx_codes(rec)[l] = inblock ? -(kl + 1) : j;
+        const bool x = earlier && !(inblock && (kl >> 5) == half);
+        const unsigned mx = __ballot_sync(0xffffffffu, x);
+        if (FILL && x) {
+            const int e = nX + __popc(mx & lt);
+            double* rec = dataX + ((size_t)offX[t] + (e >> 5)) * GX_REC;
+            gx_codes(rec)[e & 31] = inblock ? -(kl + 1) : j;
 #pragma unroll
-                for (int q = 0; q < 9; ++q) rec[q * 32 + l] = val[((size_t)i * 9 + q) * W + sl];
-            }
+            for (int q = 0; q < 9; ++q) rec[q * 32 + (e & 31)] = val[((size_t)i * 9 + q) * W + sl];
         }
         nX += __popc(mx);
-        nI += __popc(mi);
     }
     if (!FILL) {
-        if (lane == 0) {
-            cntX[t] = ((nX + 31) >> 5) + (last ? (hn + 1) >> 1 : 0);
-            if (dir == 0 && cntI) cntI[t] = (nI + 31) >> 5;
-        }
+        if (lane == 0) cntX[t] = ((nX + 31) >> 5) + (last ? (hn + 1) >> 1 : 0);
         return;
     }
-    for (int d = 0; d < ((dir == 0 && dataI) ? 2 : 1); ++d) { // pad the last chunk of the ext rows / the in-half rows
-        const int cnt = d ? nI : nX, e = cnt + lane;
-        if ((cnt & 31) != 0 && (e >> 5) == (cnt >> 5)) {
-            const size_t c = (size_t)(d ? offI[t] : offX[t]) + (e >> 5);
-            const int l = e & 31;
-            double* rec = (d ? dataI : dataX) + c * GX_REC;
-            gx_codes(rec)[l] = GS_PAD;
+    const int e = nX + lane; // pad the last chunk of the row
+    if ((nX & 31) != 0 && (e >> 5) == (nX >> 5)) {
+        double* rec = dataX + ((size_t)offX[t] + (e >> 5)) * GX_REC;
+        gx_codes(rec)[e & 31] = GS_PAD;
 #pragma unroll
-            for (int q = 0; q < 9; ++q) rec[q * 32 + l] = 0.0;
-        }
+        for (int q = 0; q < 9; ++q) rec[q * 32 + (e & 31)] = 0.0;
     }
 }
 
@@ -1586,62 +1570,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gx_block_cl(int b0, GSArgs a)
     }
 }
 
-// The residual update r = L (hdu - du), u += du from the forward stream of the block-inverse form: a row's ext chunks plus its
-// in-half chunks (together the strictly-lower couplings of the sweep order)
-__device__ __forceinline__ void gx_update_chunks(const GSArgs& a, const double* __restrict__ data, int c0, int c1, int ps, int lane, double& a0,
-    double& a1, double& a2)
-{
-    for (int c = c0; c < c1; c += 2) {
-        int code[2];
-        double v[2][9];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const bool on = c + u < c1;
-            const double* rec = data + (size_t)(c + u) * GX_REC;
-            code[u] = on ? gx_codes(rec)[lane] : GS_PAD;
-#pragma unroll
-            for (int q = 0; q < 9; ++q) v[u][q] = on ? rec[q * 32 + lane] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (code[u] != GS_PAD) {
-                const int j = code[u] >= 0 ? code[u] : a.seq[ps - code[u] - 1];
-                const double x0 = a.hdu[3 * (size_t)j] - a.du[3 * (size_t)j], x1 = a.hdu[3 * (size_t)j + 1] - a.du[3 * (size_t)j + 1],
-                             x2 = a.hdu[3 * (size_t)j + 2] - a.du[3 * (size_t)j + 2];
-                a0 += v[u][0] * x0 + v[u][3] * x1 + v[u][6] * x2;
-                a1 += v[u][1] * x0 + v[u][4] * x1 + v[u][7] * x2;
-                a2 += v[u][2] * x0 + v[u][5] * x1 + v[u][8] * x2;
-            }
-        }
-    }
-}
-__device__ __forceinline__ void gx_update_row(const GSArgs& a, int p, int lane)
-{
-    const int i = a.seq[p], b = a.pblock[p], ps = a.block_start[b], pe = a.block_start[b + 1];
-    const int gl = p - ps, h0 = gl & ~(GS_HALF - 1), hn = min(GS_HALF, pe - ps - h0);
-    const int c0 = a.xoff[0][p], c1 = a.xoff[0][p + 1] - (gl == h0 + hn - 1 ? (hn + 1) >> 1 : 0);
-    const int i0 = a.ioff[p], i1 = a.ioff[p + 1];
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    gx_update_chunks(a, a.xdata[0], c0, c1, ps, lane, a0, a1, a2);
-    gx_update_chunks(a, a.idata, i0, i1, ps, lane, a0, a1, a2);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_down_sync(0xffffffffu, a0, o);
-        a1 += __shfl_down_sync(0xffffffffu, a1, o);
-        a2 += __shfl_down_sync(0xffffffffu, a2, o);
-    }
-    if (lane == 0) {
-        const size_t o = 3 * (size_t)i;
-        a.r[o] = a0; a.r[o + 1] = a1; a.r[o + 2] = a2;
-        a.u[o] += a.du[o]; a.u[o + 1] += a.du[o + 1]; a.u[o + 2] += a.du[o + 2];
-    }
-}
-__global__ void __launch_bounds__(TPB) k_gx_update(GSArgs a)
-{
-    const int p = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (p < a.n) gx_update_row(a, p, threadIdx.x & 31);
-}
-
 // the whole symmetric sweep in one cooperative launch.  The producer lanes run ahead of the grid barriers: the stream is static
 // data, so the first chunks of the next colour's first block are requested BEFORE the barrier that ends the current colour.
 template <int THREADS, int D, int MINB>
@@ -1847,7 +1775,7 @@ int build_gx_streams(Sim* s, MGLevel& L)
     for (int d = 0; d < 2; ++d) {
         HOT_CUDA(L.gx_off[d].reserve((size_t)n + 1));
         k_gx_stream<false><<<nblk(32L * n), TPB, 0, st>>>(n, d, L.gs_seq.p, L.gs_rank.p, L.gs_pblock.p, L.gs_block_start.p, L.col.p, L.val.p, cnt[d],
-            nullptr, nullptr, nullptr, nullptr, nullptr);
+            nullptr, nullptr);
         HOT_LAUNCHED(s);
     }
     k_gs_stream<false><<<nblk(32L * n), TPB, 0, st>>>(n, L.gs_seq.p, L.gs_rank.p, L.gs_pblock.p, L.gs_block_start.p, L.col.p, L.val.p, cnt[2], cnt[3],
@@ -1872,7 +1800,7 @@ int build_gx_streams(Sim* s, MGLevel& L)
     HOT_FUNC_ATTR_ONCE(s, k_gx_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GXInvShared));
     for (int d = 0; d < 2; ++d) {
         k_gx_stream<true><<<nblk(32L * n), TPB, 0, st>>>(n, d, L.gs_seq.p, L.gs_rank.p, L.gs_pblock.p, L.gs_block_start.p, L.col.p, L.val.p, nullptr,
-            nullptr, L.gx_off[d].p, nullptr, L.gx_data[d].p, nullptr);
+            L.gx_off[d].p, L.gx_data[d].p);
         HOT_LAUNCHED(s);
         k_gx_inverse<<<2 * L.n_blocks, GXI_THREADS, sizeof(GXInvShared), st>>>(d, n, L.gs_block_start.p, L.gs_seq.p, L.gs_colrank.p, L.col.p, L.val.p,
             L.dinv.p, L.gx_off[d].p, L.gx_data[d].p);
@@ -2469,7 +2397,6 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         a.xoff[d] = inv ? L.gx_off[d].p : nullptr;
         a.xdata[d] = inv ? L.gx_data[d].p : nullptr;
     }
-    a.ioff = nullptr; a.idata = nullptr; // (in-half forward stream: superseded by the full forward stream)
     for (int d = 0; d < 2; ++d) { // (block-inverse form: the full forward stream only, for the residual update)
         const bool have = use_stream || (inv && d == 0);
         a.soff[d] = have ? L.gs_off[d].p : nullptr;

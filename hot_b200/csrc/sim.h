@@ -110,10 +110,10 @@ struct MGLevel {
     DevBuf<double> gs_sval[2];
     int gs_chunks[2] = {0, 0};
     // block-inverse form (multigrid.cu: k_gx_stream / k_gx_inverse): per-direction stream [ext rows | inverse] per half block,
-    // offsets by sweep position in direction order; forward in-half couplings (residual update only)
-    DevBuf<int> gx_off[2], gi_off;
-    DevBuf<double> gx_data[2], gi_data; // chunk records: 9 x 32 values + 32 codes (2 432 bytes)
-    int gx_chunks[2] = {0, 0}, gi_chunks = 0;
+    // offsets by sweep position in direction order (the residual update reads the full forward row stream gs_*[0])
+    DevBuf<int> gx_off[2];
+    DevBuf<double> gx_data[2]; // chunk records: 9 x 32 values + 32 codes (2 432 bytes)
+    int gx_chunks[2] = {0, 0};
     DevBuf<int> gs_seq, gs_rank, gs_block_start; // node ids in sweep order; rank of a node; block b = gs_seq[start[b]..start[b+1])
     double lMax = 1e2, lMin = 1e-8; // SquareMatrix::lMax / lMin (SquareMatrix.h:37), set by estimate2norm for the Chebyshev smoother
     int n_blocks = 0;
