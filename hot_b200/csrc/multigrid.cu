@@ -1491,11 +1491,11 @@ __device__ __forceinline__ void gx_consume(GXShared<THREADS / 32 - 1, D>& sh, un
             }
             if (lane == 0 || (lane == 1 && bvalid)) { // lane 0 finishes row m, lane 1 row hn-1-m: x = Dinv q + N q
                 const int il = lane == 0 ? m : rowB;
-                const double* D = sh.s_dinv[h0 + il];
+                const double* Di = sh.s_dinv[h0 + il];
                 const double u0 = sh.s_q[il][0], u1 = sh.s_q[il][1], u2 = sh.s_q[il][2];
-                const double x0 = (D[0] * u0 + D[3] * u1 + D[6] * u2) + (lane == 0 ? a0 : b0);
-                const double x1 = (D[1] * u0 + D[4] * u1 + D[7] * u2) + (lane == 0 ? a1 : b1);
-                const double x2 = (D[2] * u0 + D[5] * u1 + D[8] * u2) + (lane == 0 ? a2 : b2);
+                const double x0 = (Di[0] * u0 + Di[3] * u1 + Di[6] * u2) + (lane == 0 ? a0 : b0);
+                const double x1 = (Di[1] * u0 + Di[4] * u1 + Di[7] * u2) + (lane == 0 ? a1 : b1);
+                const double x2 = (Di[2] * u0 + Di[5] * u1 + Di[8] * u2) + (lane == 0 ? a2 : b2);
                 const int node = sh.s_seq[h0 + il];
                 if (CL == 1) { sh.s_x[h0 + il][0] = x0; sh.s_x[h0 + il][1] = x1; sh.s_x[h0 + il][2] = x2; }
                 else
@@ -2293,8 +2293,6 @@ int launch_gs_sweep_ring(Sim* s, GSArgs& a, int max_blocks_per_color, bool* laun
     return 0;
 }
 
-// cooperative form: one CTA per SM; every consumer warp owns about one row per half, so a block's critical path is one row
-constexpr int GX_COOP_THREADS = 1024, GX_COOP_D = 2;
 template <int THREADS, int D, int MINB>
 int launch_gx_sweep(Sim* s, GSArgs& a, int max_blocks_per_color, bool* launched)
 {
@@ -2433,20 +2431,10 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
         // 1 / 2: 0.29 / 0.23 ms against 0.34 / 0.27 ms for the cooperative single-launch form, which stays behind HOT_GS_COOP=1)
         if (dist0 || no_coop || (inv && (gx_cluster_cfg() > 1 || !force_coop))) {}
         else if (inv) {
-            // A/B: consumer warps x ring depth of the cooperative form (measured at C2, GS level 1 / level 2: 0 = 15 x 4: 0.34 / 0.27 ms,
-            // 1 = 31 x 2: 0.45 / 0.34, 2 = 23 x 3: 0.39 / 0.32)
-            static const int coop_cfg = getenv("HOT_GX_COOP") ? atoi(getenv("HOT_GX_COOP")) : 0;
-            // big levels (more than 2 blocks per SM and colour): the 3-CTAs-per-SM shape as ONE cooperative launch when a colour fits one wave
-            // (measured at C2, GS level 0: 0.80 ms against 0.66 ms for one launch per colour phase - register spills at 72 registers
-            //  and a 444-CTA grid barrier; off by default)
-            static const int coop0 = getenv("HOT_GX_COOP0") ? atoi(getenv("HOT_GX_COOP0")) : 0;
-            if (max_blocks > 2 * 148) {
-                if (coop0) RC((launch_gx_sweep<288, 3, 3>(s, a, max_blocks, &launched)));
-            }
-            else if (coop_cfg == 0) RC((launch_gx_sweep<512, 4, 1>(s, a, max_blocks, &launched)));
-            else if (coop_cfg == 2) RC((launch_gx_sweep<768, 3, 1>(s, a, max_blocks, &launched)));
-            else if (coop_cfg == 3) RC((launch_gx_sweep<288, 3, 3>(s, a, max_blocks, &launched)));
-            else RC((launch_gx_sweep<GX_COOP_THREADS, GX_COOP_D, 1>(s, a, max_blocks, &launched)));
+            // the cooperative single-launch form: 15 consumer warps x 4 slots, one CTA per SM, levels with at most 2 blocks per SM and colour
+            // (other shapes were measured and dropped: 31 warps x 2 slots, 23 x 3, and the 3-CTAs-per-SM shape for level 0 -
+            //  profiles/r2_gs_experiments.md)
+            if (max_blocks <= 2 * 148) RC((launch_gx_sweep<512, 4, 1>(s, a, max_blocks, &launched)));
         }
         else if (max_blocks <= 2 * 148) {
             if (use_ring) RC((launch_gs_sweep_ring<512, GS_RING_NST_COOP>(s, a, max_blocks, &launched)));
@@ -2456,10 +2444,14 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
             RC((use_stream ? launch_gs_sweep<GS_THREADS, true>(s, a, max_blocks, &launched) : launch_gs_sweep<GS_THREADS, false>(s, a, max_blocks, &launched)));
         if (!launched) {
             constexpr size_t ring_smem = sizeof(GSRingShared<GS_RING_NST>);
-            constexpr size_t gx_smem = sizeof(GXShared<8, 3>), gx_smem_big = sizeof(GXShared<15, 4>), gx_smem7 = sizeof(GXShared<7, 3>);
-            // A/B: 0 = 3 CTAs of 256 threads per SM (measured: GS level 0 at C2 0.69 ms), 1 = one CTA of 512 threads (0.78 ms)
+            constexpr size_t gx_smem7 = sizeof(GXShared<7, 3>);
+            // A/B: 0 = 3 CTAs of 288 threads (8 consumer warps) per SM, 2 = of 256 threads (7 consumer warps: 0.68 against 0.66 ms at C2 level 0;
+            // one 512-thread CTA per SM measured 0.78 ms and was dropped)
             static const int block_cfg = getenv("HOT_GX_BLOCK") ? atoi(getenv("HOT_GX_BLOCK")) : 0;
-            const bool big = block_cfg == 1;
+            if (inv && block_cfg == 2) {
+                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<true, 256, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem7);
+                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<false, 256, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem7);
+            }
             // colour phases 2..16 of a sweep as programmatic dependents of the phase before them (A/B: HOT_GX_PDL=0); not with the
             // take-over exchanges of a partitioned level 0 in between
             static const bool pdl_env = !(getenv("HOT_GX_PDL") && atoi(getenv("HOT_GX_PDL")) == 0);
@@ -2467,14 +2459,6 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
             bool prev_phase = false; // the previous launch of this stream was a colour phase of this sweep
             // A/B: sweep every block with a thread-block cluster of 2 / 4 CTAs (k_gx_block_cl); with it every level runs per-phase launches
             const int cluster = gx_cluster_cfg();
-            if (inv) {
-                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<true, 288, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem);
-                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<true, 256, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem7);
-                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<false, 288, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem);
-                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<false, 256, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem7);
-                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<true, 512, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem_big);
-                HOT_FUNC_ATTR_ONCE(s, (k_gx_block<false, 512, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gx_smem_big);
-            }
             if (use_ring) {
                 HOT_FUNC_ATTR_ONCE(s, k_gs_block_ring<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem);
                 HOT_FUNC_ATTR_ONCE(s, k_gs_block_ring<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem);
@@ -2484,7 +2468,6 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
                 if (b1 == b0) continue;
                 if (inv && cluster == 2) RC((launch_gx_block_cl<true, 2>(s, b0, b1 - b0, a)));
                 else if (inv && cluster == 4) RC((launch_gx_block_cl<true, 4>(s, b0, b1 - b0, a)));
-                else if (inv && big) k_gx_block<true, 512, 4, 1><<<b1 - b0, 512, gx_smem_big, st>>>(b0, a);
                 else if (inv && block_cfg == 2) k_gx_block<true, 256, 3, 3><<<b1 - b0, 256, gx_smem7, st>>>(b0, a);
                 else if (inv) { RC((launch_gx_block<true>(s, b0, b1 - b0, a, pdl && prev_phase))); prev_phase = true; }
                 else if (use_ring) k_gs_block_ring<true><<<b1 - b0, GS_THREADS, ring_smem, st>>>(b0, a);
@@ -2497,7 +2480,6 @@ int smooth_gs(Sim* s, int level, double* u, double* r, int iterations)
                 if (b1 == b0) continue;
                 if (inv && cluster == 2) RC((launch_gx_block_cl<false, 2>(s, b0, b1 - b0, a)));
                 else if (inv && cluster == 4) RC((launch_gx_block_cl<false, 4>(s, b0, b1 - b0, a)));
-                else if (inv && big) k_gx_block<false, 512, 4, 1><<<b1 - b0, 512, gx_smem_big, st>>>(b0, a);
                 else if (inv && block_cfg == 2) k_gx_block<false, 256, 3, 3><<<b1 - b0, 256, gx_smem7, st>>>(b0, a);
                 else if (inv) { RC((launch_gx_block<false>(s, b0, b1 - b0, a, pdl && prev_phase))); prev_phase = true; }
                 else if (use_ring) k_gs_block_ring<false><<<b1 - b0, GS_THREADS, ring_smem, st>>>(b0, a);
