@@ -1085,10 +1085,19 @@ __global__ void __launch_bounds__(THREADS) k_gs_sweep_ring(GSArgs a)
 // ("ext" = couplings to other blocks, code = DOF id, and to the other half, code = -(local index) - 1).  A chunk is ONE record of
 // GX_REC doubles (9 x 32 values, then 32 codes), so it moves with one TMA bulk copy.  Both directions index their offsets by
 // sweep position in DIRECTION order (backward: n-1-p), so a block's chunks are consumed in ascending order.
-// Kernel structure: chunk ci of a block belongs to consumer warp ci % NCW.  Every consumer warp has its own ring of GX_D chunk
-// slots with a full / empty mbarrier pair per slot; lane w of warp 0 is the producer of consumer warp w (wait empty, expect_tx,
-// one cp.async.bulk) and runs ahead freely - it never joins the consumers' named barriers, so the stream keeps flowing through
-// the section boundaries, and in the cooperative form it requests the next colour's first chunks before the grid barrier.
+// Kernel structure (k_gx_block, one launch per colour phase and CTA per block; measured alternatives in profiles/r2_gs_experiments.md):
+//  * consumer warps own whole rows (row il -> warp il % NCW, inverse chunk m -> warp m % NCW): the x gather of a row's chunk k+1 is in
+//    flight while chunk k is multiplied, lane partials are summed over the row's <= 4 chunks and reduced once per row;
+//  * every consumer warp has its own ring of D chunk slots with a full / empty mbarrier pair per slot; lane w of warp 0 is the
+//    producer of consumer warp w (empty barrier TESTED, expect_tx, one cp.async.bulk per chunk) in one converged loop over all
+//    lanes - cp.async.bulk is a uniform-datapath instruction, lanes on their own paths would be issued one after the other - and
+//    never joins the consumers' named barriers, so the stream keeps flowing through the section boundaries of a block;
+//  * Dinv and D of the block's nodes are prefetched into shared memory once per block;
+//  * everything up to that point reads data that is static between hierarchy builds, so colour phases 2..16 of a sweep are launched
+//    as programmatic dependents of the phase before them (griddepcontrol.launch_dependents / .wait): their static prologue and
+//    first TMA requests overlap the previous colour;
+//  * k_gx_sweep is the cooperative single-launch form (A/B), k_gx_block_cl sweeps a block with a thread-block cluster (A/B).
+// The residual update r - A du = L (hdu - du) reads the full forward row stream of k_gs_stream (k_gs_stream_update).
 constexpr int GX_REC = 9 * 32 + 16;       // doubles per chunk record (2 432 bytes)
 __device__ __forceinline__ const int* gx_codes(const double* rec) { return reinterpret_cast<const int*>(rec + 9 * 32); }
 __device__ __forceinline__ int* gx_codes(double* rec) { return reinterpret_cast<int*>(rec + 9 * 32); }
