@@ -410,6 +410,62 @@ int orc_pcg(void* h, const double* b, double* x, double tolerance, int max_itera
     return rc;
 }
 
+// The operator callbacks of orc_pcg / orc_minres on their own (tests drive the REFERENCE's Krylov solver classes with them:
+// oracle/ziran_krylov_shim.cpp): A.multiply, A.precondition with the same selection as orc_pcg; A.project is orc_project.
+static void krylov_objective(ObjectiveState& O, int matfree, int preconditioner)
+{
+    orc_default_options(&O.opt);
+    O.opt.matfree = matfree;
+    O.precond = preconditioner == 0 ? 0 : (preconditioner == 2 ? 3 : (matfree ? 1 : 2));
+}
+int orc_obj_multiply(void* h, int matfree, const double* x, double* b)
+{
+    Sim* s = (Sim*)h;
+    ObjectiveState O;
+    krylov_objective(O, matfree, 0);
+    const size_t m = 3 * (size_t)s->num_nodes;
+    Vd xv(x, x + m), bv(m);
+    int rc = obj_multiply(s, O, xv, bv);
+    std::copy(bv.begin(), bv.end(), b);
+    return rc;
+}
+int orc_obj_precondition(void* h, int matfree, int preconditioner, const double* in, double* out)
+{
+    Sim* s = (Sim*)h;
+    ObjectiveState O;
+    krylov_objective(O, matfree, preconditioner);
+    const size_t m = 3 * (size_t)s->num_nodes;
+    if (O.precond == 1 && matrix_of(s).diagVal.size() != 3 * m) { // (orc_pcg builds the matrix-free block diagonal before it iterates)
+        int rc0 = orc_build_diagonal(s, 1, nullptr);
+        if (rc0) return rc0;
+    }
+    if (O.precond == 2 && matrix_of(s).sysmats.empty()) return fail(s, "orc_obj_precondition: the Jacobi preconditioner of the assembled matrix needs orc_build_mg");
+    Vd iv(in, in + m), ov(m);
+    int rc = obj_precondition(s, O, iv, ov);
+    std::copy(ov.begin(), ov.end(), out);
+    return rc;
+}
+
+// Minres::solve on the current system as a stand-alone call (same operator / preconditioner selection as orc_pcg)
+int orc_minres(void* h, const double* b, double* x, double relative_tolerance, double tolerance, int max_iterations, int matfree, int preconditioner,
+    int* iters)
+{
+    Sim* s = (Sim*)h;
+    ObjectiveState O;
+    orc_default_options(&O.opt);
+    O.opt.matfree = matfree;
+    O.precond = preconditioner == 0 ? 0 : (preconditioner == 2 ? 3 : (matfree ? 1 : 2));
+    const size_t m = 3 * (size_t)s->num_nodes;
+    Vd xv(x, x + m), bv(b, b + m);
+    int rc = 0;
+    if (O.precond == 1) rc = orc_build_diagonal(s, 1, nullptr);
+    if (O.precond == 2 && matrix_of(s).sysmats.empty()) return fail(s, "orc_minres: the Jacobi preconditioner of the assembled matrix needs orc_build_mg");
+    if (rc) return rc;
+    rc = minres_solve(s, O, xv, bv, relative_tolerance, tolerance, max_iterations, iters);
+    std::copy(xv.begin(), xv.end(), x);
+    return rc;
+}
+
 // MultigridSimulation::backwardEulerStep (MultigridSimulation.h:188-233) after the caller has set the BC table
 int orc_backward_euler_step(void* h, const hot_solver_options* opt, hot_solve_log* log)
 {

@@ -378,6 +378,24 @@ def _add_solver_methods(cls):
                                  int(preconditioner), C.byref(it)))
         return x, it.value
 
+    def obj_multiply(self, x, matfree=False):
+        x = np.ascontiguousarray(x, dtype=np.float64); b = np.empty_like(x)
+        self._check(_lib.orc_obj_multiply(_vp(self._h), int(matfree), _p(x), _p(b)))
+        return b
+
+    def obj_precondition(self, r, matfree=False, preconditioner=1):
+        r = np.ascontiguousarray(r, dtype=np.float64); z = np.empty_like(r)
+        self._check(_lib.orc_obj_precondition(_vp(self._h), int(matfree), int(preconditioner), _p(r), _p(z)))
+        return z
+
+    def minres(self, b, x0=None, relative_tolerance=1.0, tolerance=1.0, max_iterations=10000, matfree=False, preconditioner=1):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros_like(b) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+        it = C.c_int(0)
+        self._check(_lib.orc_minres(_vp(self._h), _p(b), _p(x), C.c_double(relative_tolerance), C.c_double(tolerance), int(max_iterations),
+                                    int(matfree), int(preconditioner), C.byref(it)))
+        return x, it.value
+
     def backwardEulerStep(self, options=None, **kw):
         o = options if options is not None else self.default_options(**kw)
         log = SolveLog()
