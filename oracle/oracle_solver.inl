@@ -467,7 +467,9 @@ int orc_minres(void* h, const double* b, double* x, double relative_tolerance, d
 }
 
 // MultigridSimulation::backwardEulerStep (MultigridSimulation.h:188-233) after the caller has set the BC table
-int orc_backward_euler_step(void* h, const hot_solver_options* opt, hot_solve_log* log)
+// `lbfgs`: the L-BFGS loop to run for -lsolver 3 - lbfgs_solve below, or the reference's own ZIRAN::LBFGS::solve driven on this
+// objective (oracle/lbfgs_ref_shim.cpp, test infrastructure that pins lbfgs_solve to the reference's code)
+static int backward_euler_step_with(void* h, const hot_solver_options* opt, hot_solve_log* log, int (*lbfgs)(Sim*, ObjectiveState&))
 {
     Sim* s = (Sim*)h;
     ForceState& f = force_of(s);
@@ -508,12 +510,13 @@ int orc_backward_euler_step(void* h, const hot_solver_options* opt, hot_solve_lo
     // resetLSFlag :277-282
     O.updated = false;
     O.dv0 = s->dv;
-    int rc = opt->lsolver != 3 ? newton_solve(s, O, tol, cg_tol) : lbfgs_solve(s, O);
+    int rc = opt->lsolver != 3 ? newton_solve(s, O, tol, cg_tol) : lbfgs(s, O);
     if (rc) return rc;
     matrix_of(s).dv0 = opt->linesearch ? O.dv0 : s->dv;
     orc_restore_strain(s);
     return 0;
 }
+int orc_backward_euler_step(void* h, const hot_solver_options* opt, hot_solve_log* log) { return backward_euler_step_with(h, opt, log, lbfgs_solve); }
 
 // ImplicitSolverObjective::dv0 (ImplicitSolver.h:58): the last iterate the line search accepted.  With --linesearch the
 // reference leaves dv = dv0 + (one more copy of the last step) behind; without it dv0 == dv.

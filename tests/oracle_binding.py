@@ -5,7 +5,8 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-_lib = C.CDLL(os.path.join(ROOT, "oracle", "libhot_oracle.so"))
+# HOT_ORACLE_LIB: another build of the same oracle (oracle/_ref/libhot_oracle_lbfgsref.so = the oracle + the reference's own LBFGS loop)
+_lib = C.CDLL(os.environ.get("HOT_ORACLE_LIB") or os.path.join(ROOT, "oracle", "libhot_oracle.so"))
 _lib.orc_create.restype = C.c_void_p
 _lib.orc_create.argtypes = [C.c_double, C.c_double, C.c_double]
 _lib.orc_last_error.restype = C.c_char_p
@@ -400,6 +401,14 @@ def _add_solver_methods(cls):
         o = options if options is not None else self.default_options(**kw)
         log = SolveLog()
         self._check(_lib.orc_backward_euler_step(_vp(self._h), C.byref(o), C.byref(log)))
+        return log.as_dict()
+
+    def backwardEulerStepReferenceLBFGS(self, options=None, **kw):
+        """orc_backward_euler_step with the L-BFGS loop replaced by the reference's own ZIRAN::LBFGS::solve (oracle/lbfgs_ref_shim.cpp);
+        only in the library built from the reference (HOT_ORACLE_LIB=oracle/_ref/libhot_oracle_lbfgsref.so)"""
+        o = options if options is not None else self.default_options(**kw)
+        log = SolveLog()
+        self._check(_lib.zr_lbfgs_backward_euler_step(_vp(self._h), C.byref(o), C.byref(log)))
         return log.as_dict()
 
     def get_dv0(self):
