@@ -23,32 +23,8 @@ template <class T, int dim> class GridState;                     // named by deb
 template <class T, int dim, int degree = 2> class BSplineWeights;
 } // namespace ZIRAN
 #include <tbb/tbb.h>
-// LBFGS::solve has debugging branches (HOTSettings::debugMode > 0, never taken here) that assemble the preconditioner into an Eigen sparse
-// matrix: the stand-in Eigen only declares these two templates, so they get inert definitions that let those branches compile
-namespace Eigen {
-template <class T, class I>
-class Triplet {
-public:
-    Triplet() {}
-    Triplet(int, int, const T&) {}
-};
-template <class T, int Options, class Index>
-class SparseMatrix {
-public:
-    struct InnerIterator {
-        InnerIterator(const SparseMatrix&, int) {}
-        operator bool() const { return false; }
-        InnerIterator& operator++() { return *this; }
-        int row() const { return 0; }
-        int col() const { return 0; }
-        T value() const { return T(0); }
-    };
-    void resize(int, int) {}
-    template <class It> void setFromTriplets(It, It) {}
-    int outerSize() const { return 0; }
-    T coeffRef(int, int) { return T(0); }
-};
-} // namespace Eigen
+// (LBFGS::solve has debugging branches, HOTSettings::debugMode > 0, never taken here, that assemble the preconditioner into an Eigen sparse
+// matrix: the stand-in Eigen's inert SparseMatrix / Triplet let them compile)
 #include <Ziran/Math/Nonlinear/LBFGS.h>
 
 namespace {

@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE ONLY - stands in for Lib/Ziran/Sim/SimulationBase.h, which Projects/multigrid/MultigridPreconditioner.h includes without using anything of it
+// in the pinned code paths (MultigridBuilder::build, the smoothers, MultigridOperator::operator()).
+#pragma once

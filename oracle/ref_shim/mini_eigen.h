@@ -234,6 +234,31 @@ public:
             + m(0, 2) * (m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0));
     }
     DiagonalMatrix<Scalar, RowsAtCompileTime> asDiagonal() const { return DiagonalMatrix<Scalar, RowsAtCompileTime>(eval()); }
+    Matrix<Scalar, RowsAtCompileTime, 1> diagonal() const
+    {
+        Matrix<Scalar, RowsAtCompileTime, 1> d;
+        for (int i = 0; i < rows(); ++i) d(i) = (*this)(i, i);
+        return d;
+    }
+    // 3 x 3 inverse the way Eigen computes it (Eigen/src/LU/InverseImpl.h, compute_inverse_size3_helper): cofactors, determinant from
+    // the first column, one multiplication by 1 / det per entry
+    PlainObject inverse() const
+    {
+        static_assert(RowsAtCompileTime == 3 && ColsAtCompileTime == 3, "mini_eigen: inverse() is implemented for 3 x 3 only");
+        const MatrixBase& m = *this;
+        auto cof = [&m](int i, int j) {
+            const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            return m(i1, j1) * m(i2, j2) - m(i1, j2) * m(i2, j1);
+        };
+        const Scalar c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+        const Scalar det = (c00 * m(0, 0) + c10 * m(1, 0)) + c20 * m(2, 0);
+        const Scalar invdet = Scalar(1) / det;
+        PlainObject r;
+        r(0, 0) = c00 * invdet; r(0, 1) = c10 * invdet; r(0, 2) = c20 * invdet;
+        r(1, 0) = cof(0, 1) * invdet; r(1, 1) = cof(1, 1) * invdet; r(1, 2) = cof(2, 1) * invdet;
+        r(2, 0) = cof(0, 2) * invdet; r(2, 1) = cof(1, 2) * invdet; r(2, 2) = cof(2, 2) * invdet;
+        return r;
+    }
     template <class U>
     Matrix<U, RowsAtCompileTime, ColsAtCompileTime> cast() const
     {
@@ -316,6 +341,19 @@ public:
     DiagonalMatrix() {}
     template <class Od>
     explicit DiagonalMatrix(const MatrixBase<Od>& v) : d(v) {}
+    DiagonalMatrix inverse() const
+    {
+        DiagonalMatrix r;
+        for (int i = 0; i < N; ++i) r.d(i) = T(1) / d(i);
+        return r;
+    }
+    operator Matrix<T, N, N>() const
+    {
+        Matrix<T, N, N> r;
+        r.setZero();
+        for (int i = 0; i < N; ++i) r(i, i) = d(i);
+        return r;
+    }
 };
 
 // ---- operators: all eager --------------------------------------------------------------------------------------------------
@@ -467,3 +505,4 @@ typedef Matrix<float, 3, 3> Matrix3f;
 typedef Matrix<float, 3, 1> Vector3f;
 
 } // namespace Eigen
+#include "mini_eigen_dyn.h"
