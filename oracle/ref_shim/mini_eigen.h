@@ -293,7 +293,10 @@ public:
 
 template <class T, int R, int C, int O, int MR, int MC>
 class Matrix : public MatrixBase<Matrix<T, R, C, O, MR, MC>> {
-    T m_[(R > 0 ? R : 1) * (C > 0 ? C : 1)];
+    // Eigen aligns fixed-size objects whose byte size is a multiple of 16 (of 32 in an AVX build: EIGEN_MAX_STATIC_ALIGN_BYTES); GridState's "size is a power of
+    // two" static assertions (Lib/MPM/MpmGrid.h:39-42) rely on it for the 2D records
+    static constexpr std::size_t bytes_ = sizeof(T) * (R > 0 ? R : 1) * (C > 0 ? C : 1);
+    alignas(bytes_ % 32 == 0 ? 32 : bytes_ % 16 == 0 ? 16 : alignof(T)) T m_[(R > 0 ? R : 1) * (C > 0 ? C : 1)];
 
 public:
     typedef MatrixBase<Matrix> Base;
