@@ -60,6 +60,18 @@ DynArray<T> operator*(const DynArray<T>& a, const DynArray<T>& b)
     return r;
 }
 
+// Vec::segment(start, n), its transpose, (fixed column) * (segment transposed) and (fixed row) * middleCols  (ImplicitSolver.h:138,268-271)
+template <class T>
+struct DynSegment {
+    const T* p; int n;
+    struct Transposed { const T* p; int n; };
+    Transposed transpose() const { return Transposed{p, n}; }
+};
+template <class T>
+struct DynRow { // (1 x n) result of rowvector * middleCols
+    std::vector<T> v;
+    T dot(const DynSegment<T>& s) const { T r = 0; for (int j = 0; j < s.n; ++j) r += v[j] * s.p[j]; return r; }
+};
 template <class T, int R, int O, int MR, int MC>
 class Matrix<T, R, Dynamic, O, MR, MC> {
     std::vector<T> m_;
@@ -111,9 +123,41 @@ public:
             }
         };
         Colwise colwise() const { return Colwise{this}; }
+        // residual.middleCols(start, n) = dtg * mass.segment(start, n).transpose()  (ImplicitSolver.h:138): column j = dtg * mass(start + j)
+        template <int O2, int MR2, int MC2>
+        friend DynRow<T> operator*(const Matrix<T, 1, R, O2, MR2, MC2>& g, const Middle& b) // gravity.transpose() * dv.middleCols(..)
+        {
+            DynRow<T> r;
+            r.v.resize(b.n);
+            for (int j = 0; j < b.n; ++j) {
+                T s = 0;
+                for (int i = 0; i < R; ++i) s += g(0, i) * (*b.m)(i, b.start + j);
+                r.v[j] = s;
+            }
+            return r;
+        }
+        template <class OP>
+        const Middle& operator=(const OP& op) const
+        {
+            for (int j = 0; j < n; ++j)
+                for (int i = 0; i < R; ++i) const_cast<Matrix&>(*m)(i, start + j) = op.v[i] * op.p[j];
+            return *this;
+        }
     };
     Middle middleCols(int start, int n) const { return Middle{this, start, n}; }
 };
+template <class T, int R>
+struct DynOuter { T v[R]; const T* p; int n; };
+template <class T, int R, int O, int MR, int MC>
+DynOuter<T, R> operator*(const Matrix<T, R, 1, O, MR, MC>& v, const typename DynSegment<T>::Transposed& s)
+{
+    DynOuter<T, R> r;
+    for (int i = 0; i < R; ++i) r.v[i] = v(i);
+    r.p = s.p; r.n = s.n;
+    return r;
+}
+template <class T, int R, int O, int MR, int MC, class S, typename std::enable_if<std::is_arithmetic<S>::value, int>::type = 0>
+Matrix<T, R, Dynamic, O, MR, MC> operator/(const Matrix<T, R, Dynamic, O, MR, MC>& a, const S& s) { Matrix<T, R, Dynamic, O, MR, MC> r = a; r /= (T)s; return r; }
 template <class T, int R, int O, int MR, int MC, class S, typename std::enable_if<std::is_arithmetic<S>::value, int>::type = 0>
 Matrix<T, R, Dynamic, O, MR, MC> operator*(const Matrix<T, R, Dynamic, O, MR, MC>& a, const S& s) { Matrix<T, R, Dynamic, O, MR, MC> r = a; r *= (T)s; return r; }
 template <class T, int R, int O, int MR, int MC, class S, typename std::enable_if<std::is_arithmetic<S>::value, int>::type = 0>
@@ -156,6 +200,7 @@ public:
     T squaredNorm() const { T s = 0; for (const T& x : m_) s += x * x; return s; }
     T norm() const { return std::sqrt(squaredNorm()); }
     T dot(const Matrix& o) const { T s = 0; for (size_t k = 0; k < m_.size(); ++k) s += m_[k] * o.m_[k]; return s; }
+    DynSegment<T> segment(int start, int n) const { return DynSegment<T>{m_.data() + start, n}; }
 };
 
 // Map of a dynamic vector (EIGEN_EXT::vec() of DenseExt.h views a TVStack as one long vector; used by direct-solver paths only)

@@ -1,0 +1,186 @@
+"""Generates tests/golden/implicit_ref.npz: the REFERENCE'S OWN implicit-solver objective, ZIRAN::ImplicitSolverObjective<Simulation>
+(Projects/multigrid/ImplicitSolver.h: updateState / totalEnergy, computeResidual, buildMatrix<projectSystem>, buildDiagonal,
+evaluatePerNodeCNTolerance, multiply, shouldExitByCN), compiled where it lies and instantiated on a stand-in simulation whose grid is the
+reference's MpmGrid / SPGrid code and whose constitutive model is the reference's CorotatedIsotropic (oracle/implicit_ref_shim.cpp ->
+oracle/_ref/libimplicit_ref.so; the particle loops of MpmForceBase / FBasedMpmForceHelper / MassLumpedInertia that sit between them are written
+out in that file).  tests/test_oracle_implicit_ref.py compares the oracle's restatement of rows a9-a15 (oracle_force.inl, oracle_matrix.inl) and
+the CUDA path with these results.  Inputs are stored with the outputs.
+Run in the build container (needs /root/reference for `make -C oracle ref`):  python tests/golden/make_implicit_golden.py"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libimplicit_ref.so")
+OUT = os.path.join(ROOT, "tests", "golden", "implicit_ref.npz")
+GRAVITY = (0.0, -9.8, 0.0)
+CN_EPS = 1e-3
+# case -> scene arguments, dt, BC mode (0: P projection, all sticky; 1: BC-projected system with slip nodes), makePD on / off
+CASES = {
+    "sticky": (dict(cells=(5, 4, 4), dx=1.0 / 32, ppc=4, seed=3, E=2e5), 6e-3, 0, True),
+    "slip": (dict(cells=(4, 3, 3), dx=1.0 / 32, ppc=5, seed=4, E=5e4), 4e-3, 1, True),
+    "slip_noproject": (dict(cells=(4, 5, 3), dx=1.0 / 64, ppc=6, seed=7, E=1e5, origin_cells=(29, 14, 60)), 2e-3, 1, False),
+}
+
+
+FULL_MATRIX = ("slip",)        # cases whose block rows are stored entry by entry (the others: columns, block row sums, action on a vector)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def rotation(normal):
+    """rotation that takes `normal` to the x axis (the frame slip nodes are solved in: first component = normal component)"""
+    n = np.asarray(normal, dtype=np.float64); n = n / np.linalg.norm(n)
+    a = np.array([0.0, 0.0, 1.0]) if abs(n[2]) < 0.9 else np.array([0.0, 1.0, 0.0])
+    t1 = np.cross(n, a); t1 /= np.linalg.norm(t1)
+    t2 = np.cross(n, t1)
+    return np.stack([n, t1, t2])          # rows: R @ n = e_x
+
+
+def make_inputs(name):
+    from hot_b200 import scenes
+    kw, dt, mode, project = CASES[name]
+    sc = scenes.block(**kw)
+    rng = np.random.default_rng(17)
+    inp = {k: np.ascontiguousarray(sc[k]) for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam")}
+    inp["F"] = inp["F"] + 0.08 * (rng.random(inp["F"].shape) - 0.5)     # strained start of the step (some particles get a clamped Hessian)
+    return inp, sc["dx"], dt, mode, project
+
+
+def make_bc(coord, mode):
+    """floor nodes sticky; in mode 1 the nodes of one side wall slip along a tilted plane"""
+    ymin, xmax = coord[:, 1].min(), coord[:, 0].max()
+    sticky = np.nonzero(coord[:, 1] <= ymin + 1)[0]
+    node = sticky; slip = np.zeros(len(sticky), dtype=np.int32)
+    n = len(node)
+    I = np.tile(np.eye(3).reshape(1, 9), (n, 1))
+    P = np.zeros((n, 9)); R = I.copy(); Rinv = I.copy()
+    if mode == 1:
+        wall = np.nonzero((coord[:, 0] >= xmax - 1) & (coord[:, 1] > ymin + 1))[0]
+        Rm = rotation((1.0, 0.2, -0.1))
+        node = np.concatenate([sticky, wall]); slip = np.concatenate([slip, np.ones(len(wall), dtype=np.int32)])
+        Rw = np.tile(Rm.T.reshape(1, 9), (len(wall), 1))          # column-major buffers
+        Rwi = np.tile(Rm.reshape(1, 9), (len(wall), 1))           # R^-1 = R^T
+        nrm = Rm[0]
+        Pw = np.tile((np.eye(3) - np.outer(nrm, nrm)).T.reshape(1, 9), (len(wall), 1))
+        P = np.concatenate([P, Pw]); R = np.concatenate([R, Rw]); Rinv = np.concatenate([Rinv, Rwi])
+    return node.astype(np.int32), P, R, Rinv, slip.astype(np.int32)
+
+
+class Reference:
+    """ImplicitSolverObjective<stand-in simulation> (oracle/implicit_ref_shim.cpp)"""
+    def __init__(self, dx, dt, gravity=GRAVITY):
+        self.lib = C.CDLL(REF_LIB)
+        self.lib.implicit_ref_create.restype = C.c_void_p
+        self.lib.implicit_ref_create.argtypes = [C.c_double, C.c_double, C.c_void_p]
+        self.lib.implicit_ref_update_state.restype = C.c_double
+        g = np.ascontiguousarray(gravity, dtype=np.float64)
+        self.h = C.c_void_p(self.lib.implicit_ref_create(float(dx), float(dt), _p(g)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.implicit_ref_destroy(self.h)
+            self.h = None
+
+    def setup(self, inp, project):
+        a = [np.ascontiguousarray(inp[k], dtype=np.float64) for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam")]
+        self.N = len(a[2])
+        self.num_nodes = int(self.lib.implicit_ref_setup(self.h, C.c_long(self.N), *[_p(x) for x in a], int(project)))
+        return self.num_nodes
+
+    def set_bc(self, mode, node, P, R, Rinv, slip):
+        self.lib.implicit_ref_set_bc(self.h, int(mode), len(node), _p(node), _p(P), _p(R), _p(Rinv), _p(slip))
+
+    def set_dv(self, dv):
+        dv = np.ascontiguousarray(dv, dtype=np.float64)
+        self.lib.implicit_ref_set_dv(self.h, _p(dv))
+
+    def updateState(self, dv=None):
+        d = None if dv is None else np.ascontiguousarray(dv, dtype=np.float64)
+        return float(self.lib.implicit_ref_update_state(self.h, _p(d), 1))
+
+    def get_F(self):
+        F = np.empty((self.N, 9)); self.lib.implicit_ref_get_F(self.h, _p(F)); return F
+
+    def computeResidual(self):
+        r = np.empty((self.num_nodes, 3)); self.lib.implicit_ref_compute_residual(self.h, _p(r)); return r
+
+    def buildMatrix(self, bcproject):
+        col = np.empty((self.num_nodes, 125), dtype=np.int32); val = np.empty((self.num_nodes, 125, 9))
+        self.lib.implicit_ref_build_matrix(self.h, int(bcproject), _p(col), _p(val))
+        return col, val
+
+    def buildDiagonal(self, Ainv):
+        out = np.empty((self.num_nodes, 9)); self.lib.implicit_ref_build_diagonal(self.h, int(Ainv), _p(out)); return out
+
+    def evaluatePerNodeCNTolerance(self, eps, dt):
+        tol = np.empty(self.num_nodes); self.lib.implicit_ref_cn_tolerance(self.h, C.c_double(eps), C.c_double(dt), _p(tol)); return tol
+
+    def multiply(self, x, matfree):
+        x = np.ascontiguousarray(x, dtype=np.float64); b = np.empty_like(x)
+        self.lib.implicit_ref_multiply(self.h, int(matfree), _p(x), _p(b)); return b
+
+    def shouldExitByCN(self, r, useCN, cneps):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        return int(self.lib.implicit_ref_should_exit_by_cn(self.h, _p(r), int(useCN), C.c_double(cneps)))
+
+
+def vectors(n, seed):
+    rng = np.random.default_rng(seed)
+    return rng.random((n, 3)) - 0.5
+
+
+if __name__ == "__main__":
+    gold = {}
+    for name in CASES:
+        inp, dx, dt, mode, project = make_inputs(name)
+        ref = Reference(dx, dt)
+        n = ref.setup(inp, project)
+        # node coordinates for the BC sets come from the pinned transfer library's twin in this one: id2coord of buildMatrix
+        col0, _ = ref.buildMatrix(False)
+        import make_mpmgrid_golden as mg          # noqa: E402  (same directory)
+        g = mg.Reference(dx); g.set_particles(inp["X"], inp["V"], inp["mass"], inp["C"]); g.sortParticlesAndPolluteGrid(); g.particlesToGrid()
+        coord = g.get_id2coord()
+        node, P, R, Rinv, slip = make_bc(coord, mode)
+        ref.set_bc(mode, node, P, R, Rinv, slip)
+        dv = 0.05 * vectors(n, 21) + dt * np.asarray(GRAVITY)
+        dv[node[slip == 0]] = 0.0
+        out = dict(num_nodes=np.int64(n), bc_node=node, bc_P=P, bc_R=R, bc_Rinv=Rinv, bc_slip=slip, dv=dv)
+        out["energy"] = np.float64(ref.updateState(dv))
+        out["F"] = ref.get_F()
+        out["residual"] = ref.computeResidual()
+        for bc in (0, 1):
+            c, v = ref.buildMatrix(bc)
+            out[f"col{bc}"] = c
+            if name in FULL_MATRIX:
+                out[f"val{bc}"] = v
+            out[f"valsum{bc}"] = v.sum(1)          # block row sums (every entry enters once)
+            x = vectors(n, 30 + bc)
+            out[f"x{bc}"] = x
+            out[f"Ax{bc}"] = ref.multiply(x, False)
+        x = vectors(n, 40)
+        out["x_mf"] = x; out["Ax_mf"] = ref.multiply(x, True)
+        for a in (0, 1):
+            out[f"diag{a}"] = ref.buildDiagonal(a)
+        out["cntol"] = ref.evaluatePerNodeCNTolerance(CN_EPS, dt)
+        r = out["residual"]
+        scaled = (r ** 2).sum(1) / out["cntol"] ** 2
+        f = np.sqrt(n / scaled.sum())            # residual scaled to sit just below / above the CN exit threshold
+        out["exit"] = np.array([ref.shouldExitByCN(0.99 * f * r, 1, 0.0), ref.shouldExitByCN(1.01 * f * r, 1, 0.0),
+                                ref.shouldExitByCN(r, 0, 1.01 * np.sqrt((r ** 2).sum())), ref.shouldExitByCN(r, 0, 0.99 * np.sqrt((r ** 2).sum()))], dtype=np.int32)
+        out["exit_scale"] = np.float64(f)
+        gold[name + "/dx"] = np.float64(dx); gold[name + "/dt"] = np.float64(dt); gold[name + "/mode"] = np.int64(mode)
+        gold[name + "/project"] = np.int64(project)
+        for k, v in inp.items():
+            gold[f"{name}/in_{k}"] = v
+        for k, v in out.items():
+            gold[f"{name}/{k}"] = v
+        print(name, "particles", len(inp["mass"]), "nodes", n, "bc", len(node), "slip", int(slip.sum()), "energy", out["energy"], "exit", out["exit"])
+    np.savez_compressed(OUT, **gold)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")

@@ -1,0 +1,109 @@
+"""Pins rows a9-a15 (v / grad v gather + F update, fixed-corotated energy and stress, force scatter, matrix-free Hessian apply, residual, CN
+tolerance, line-search energy, buildMatrix with and without BC projection, buildDiagonal) to the REFERENCE'S OWN implicit-solver objective:
+tests/golden/implicit_ref.npz was produced by ZIRAN::ImplicitSolverObjective<Simulation> (Projects/multigrid/ImplicitSolver.h), compiled where
+it lies and instantiated on a stand-in simulation over the reference's MpmGrid / SPGrid grid code and its CorotatedIsotropic model
+(oracle/implicit_ref_shim.cpp -> oracle/_ref/libimplicit_ref.so; tests/golden/make_implicit_golden.py).  The oracle's restatement and the CUDA
+path through the C ABI must reproduce them; tolerances (relative to the largest magnitude of each field) are in TOL below - the sums run in
+another order than the reference's serial loops."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_spec = importlib.util.spec_from_file_location("make_implicit_golden", os.path.join(ROOT, "tests", "golden", "make_implicit_golden.py"))
+gen = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(gen)
+G = np.load(os.path.join(ROOT, "tests", "golden", "implicit_ref.npz"))
+TOL = dict(energy=1e-11, F=1e-13, residual=1e-11, matrix=1e-11, Ax=1e-10, diag=1e-10, cntol=1e-12)
+
+
+def _close(a, b, tol, what):
+    a = np.asarray(a); b = np.asarray(b)
+    assert a.shape == b.shape, what
+    err = np.abs(a - b).max()
+    assert err <= tol * max(np.abs(b).max(), 1e-300), (what, err, np.abs(b).max())
+
+
+def _csr(col, val, n):
+    blocks = val.reshape(-1, 3, 3).transpose(0, 2, 1)            # column-major 3 x 3 blocks
+    A = sp.bsr_matrix((blocks, col.reshape(-1), np.arange(0, n * 125 + 1, 125)), shape=(3 * n, 3 * n)).tocsr()
+    A.sum_duplicates()
+    return A
+
+
+def _check(make_sim, name, exact_slots):
+    g = lambda k: G[f"{name}/{k}"]
+    dt, mode, project = float(g("dt")), int(g("mode")), bool(g("project"))
+    s = make_sim(float(g("dx")))
+    s.set_particles(*[g("in_" + k) for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam")])
+    s.set_dt_gravity(dt, gen.GRAVITY)
+    s.set_project(project)
+    s.sortParticlesAndPolluteGrid()
+    n = s.particlesToGrid()
+    assert n == int(g("num_nodes"))
+    node, slip = g("bc_node"), g("bc_slip")
+    s.backupStrain()
+    if mode == 1:
+        s.set_bc(node, R=g("bc_R"), Rinv=g("bc_Rinv"), slip=slip, dv_bc=np.zeros((len(node), 3)), mode=1)
+    else:
+        s.set_bc(node, P=g("bc_P"), dv_bc=np.zeros((len(node), 3)), mode=0)
+    # a9-a11 + a14: moveNodes, grad v gather, F = (I + dt grad v) Fn, energy (elastic + kinetic - gravity work)
+    _close(s.updateState(g("dv")), g("energy"), TOL["energy"], "energy")
+    _close(s.get_stress()[1], g("F"), TOL["F"], "F")
+    # a12 + a14: dt g m + dt f - m dv, rotated / projected at the collision nodes
+    _close(s.computeResidual(), g("residual"), TOL["residual"], "residual")
+    # a13: matrix-free Hessian apply
+    _close(s.multiply(g("x_mf")), g("Ax_mf"), TOL["Ax"], "Ax_mf")
+    # a15: block rows without / with BC projection
+    for bc in (0, 1):
+        s.buildMatrix(bool(bc))
+        col, val = s.get_matrix()
+        if exact_slots:
+            assert np.array_equal(col, g(f"col{bc}")), f"col{bc}"        # slot layout incl. the "empty slot" column convention (:597-602)
+        _close(val.sum(1), g(f"valsum{bc}"), TOL["matrix"], f"valsum{bc}")
+        if name in gen.FULL_MATRIX:
+            A, B = _csr(col, val, n), _csr(g(f"col{bc}"), g(f"val{bc}"), n)
+            assert abs(A - B).max() <= TOL["matrix"] * abs(B).max(), f"val{bc}"
+        _close(s.spmv(0, g(f"x{bc}")), g(f"Ax{bc}"), TOL["Ax"], f"Ax{bc}")
+    for a in (0, 1):
+        _close(s.buildDiagonal(a), g(f"diag{a}"), TOL["diag"], f"diag{a}")
+    _close(s.evaluatePerNodeCNTolerance(gen.CN_EPS, dt), g("cntol"), TOL["cntol"], "cntol")
+
+
+@pytest.mark.parametrize("name", list(gen.CASES))
+def test_oracle_objective_against_reference_code(oracle, name):
+    _check(oracle.OracleSim, name, exact_slots=True)
+
+
+def test_golden_exit_tests_bracket_the_threshold():
+    """shouldExitByCN (ImplicitSolver.h:171-215) on a residual scaled just below / above the threshold, with and without the CN scaling"""
+    for name in gen.CASES:
+        assert list(G[f"{name}/exit"]) == [1, 0, 1, 0]
+        r, tol, n = G[f"{name}/residual"], G[f"{name}/cntol"], int(G[f"{name}/num_nodes"])
+        f = float(G[f"{name}/exit_scale"])
+        scaled = ((f * r) ** 2).sum(1) / tol ** 2                  # the rule the oracle's and the library's solvers apply (oracle_solver.inl:33-50)
+        assert abs(scaled.sum() / n - 1.0) < 1e-9
+
+
+@pytest.mark.skipif(not os.path.exists(gen.REF_LIB), reason="oracle/_ref/libimplicit_ref.so not built (needs /root/reference)")
+def test_reference_objective_reproduces_the_golden_vectors():
+    name = "slip"
+    g = lambda k: G[f"{name}/{k}"]
+    inp = {k: g("in_" + k) for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam")}
+    ref = gen.Reference(float(g("dx")), float(g("dt")))
+    n = ref.setup(inp, bool(g("project")))
+    ref.set_bc(int(g("mode")), g("bc_node"), g("bc_P"), g("bc_R"), g("bc_Rinv"), g("bc_slip"))
+    assert ref.updateState(g("dv")) == float(g("energy"))
+    assert np.array_equal(ref.computeResidual(), g("residual"))
+    col, val = ref.buildMatrix(1)
+    assert np.array_equal(col, g("col1")) and np.array_equal(val, g("val1"))
+    assert np.array_equal(ref.evaluatePerNodeCNTolerance(gen.CN_EPS, float(g("dt"))), g("cntol"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(gen.CASES))
+def test_cuda_objective_against_reference_code(hot, name):
+    _check(hot.MpmSimulationB200, name, exact_slots=False)
