@@ -58,6 +58,21 @@ public:
 } // namespace ZIRAN
 
 #include <ImplicitSolver.h>
+#include <Ziran/Math/Nonlinear/ExtendedNewtonsMethod.h>
+#include <Ziran/Math/Nonlinear/LBFGS.h>
+
+// SquareMatrix::comp (SquareMatrix.h:39-46) falls off its end without a return value for equal colour keys (undefined behaviour that GCC compiles
+// into a crash, see mg_ref_shim.cpp): defined as 0 here as there, the rest of the function is the reference's loop
+namespace ZIRAN {
+template <>
+inline int SquareMatrix<double, 3>::comp(const std::array<int, 3>& a, const std::array<int, 3>& b)
+{
+    for (int i = 0; i < 3; ++i)
+        if (a[i] < b[i]) return -1;
+        else if (a[i] > b[i]) return 1;
+    return 0;
+}
+} // namespace ZIRAN
 
 namespace {
 typedef Eigen::Matrix<T, 9, 9> Hessian9;
@@ -360,19 +375,35 @@ TM load9(const double* p)
 
 extern "C" {
 
+// ONE simulation and ONE objective per process, like the reference: MultigridBuilder::build keeps a function-static colour-marking lambda that
+// captured the id2coord vector of the first build by reference (MultigridPreconditioner.h:581) and SparseMatrix::rebuildPreconditioner a
+// function-static operator (SparseMatrixFast.h:49).  create() hands out that one object, re-initialised.
+static MockSim* g_sim = nullptr;
+
 void* implicit_ref_create(double dx, double dt, const double* gravity)
 {
-    MockSim* s = new MockSim();
+    if (!g_sim) {
+        g_sim = new MockSim();
+        g_sim->force.reset(new MockForce(*g_sim));
+        g_sim->forces.push_back(g_sim->force.get());
+        g_sim->inertia.reset(new MockInertia(*g_sim));
+        g_sim->objective.reset(new ImplicitSolverObjective<MockSim>(*g_sim));
+    }
+    MockSim* s = g_sim;
     s->dx = dx;
     s->D_inverse = 4 / (dx * dx);
     s->dt = dt;
     for (int d = 0; d < 3; ++d) s->gravity(d) = gravity[d];
-    s->force.reset(new MockForce(*s));
-    s->forces.push_back(s->force.get());
-    s->inertia.reset(new MockInertia(*s));
+    s->collision_nodes.clear();
+    s->objective->initialize([](TVStack&) {});
+    s->objective->setPreconditioner([](const TVStack& x, TVStack& b) { b = x; });
+    s->objective->matrix_free = false;
+    s->objective->updated = false;
+    s->objective->minres.setTolerance(1); // the constructor's values (ImplicitSolver.h:86-88): a --usecn solve overwrites them
+    s->objective->cg.setTolerance(1);
     return s;
 }
-void implicit_ref_destroy(void* h) { delete (MockSim*)h; }
+void implicit_ref_destroy(void*) {}
 
 // particles (the oracle's buffer layouts: matrices column-major) -> sort -> P2G on the reference grid code; F is the strain at the start of the step
 int implicit_ref_setup(void* h, long n, const double* X, const double* V, const double* mass, const double* C, const double* F, const double* vol,
@@ -394,7 +425,6 @@ int implicit_ref_setup(void* h, long n, const double* X, const double* V, const 
         s->mass_matrix(g.idx) = g.m;
         s->vn.col(g.idx) = g.v;
     });
-    s->objective.reset(new ImplicitSolverObjective<MockSim>(*s));
     return nn;
 }
 
@@ -536,6 +566,78 @@ int implicit_ref_should_exit_by_cn(void* h, const double* r, int useCN, double c
     HOTSettings::useCN = useCN != 0;
     HOTSettings::cneps = cneps;
     return O.shouldExitByCN(residual) ? 1 : 0;
+}
+
+// MultigridSimulation::backwardEulerStep (Projects/multigrid/MultigridSimulation.h:188-233) around the reference's own solver templates
+// ZIRAN::ExtendedNewtonsMethod<Objective> (Lib/Ziran/Math/Nonlinear/ExtendedNewtonsMethod.h:39-66: lsolver 2 = PN-PCG / PN-MGPCG through
+// ImplicitSolverObjective::computeStep, InexactConjugateGradient and MultigridBuilder / MultigridOperator) and ZIRAN::LBFGS<Objective>
+// (LBFGS.h:300-437: lsolver 3 = HOT) on the objective above.  The simulation's dv (already holding buildInitialDvAndVnForNewton's start value,
+// implicit_ref_set_dv) is the solution vector, as in :219-221.  out = {iterations (shouldExitByCN calls - 1), converged, final |residual|}
+int implicit_ref_backward_euler_step(void* h, int lsolver, int levels, int smoother, int coarse_solver, int Ainv, int linesearch, int usecn, double cneps,
+    int max_iterations, int adaptive_h, int matfree, double* dv_out, double* out)
+{
+    MockSim* s = (MockSim*)h;
+    auto& objective = *s->objective;
+    HOTSettings::lsolver = lsolver; HOTSettings::levelCnt = levels; HOTSettings::smoother = smoother; HOTSettings::coarseSolver = coarse_solver;
+    HOTSettings::Ainv = Ainv; HOTSettings::times = 1; HOTSettings::linesearch = linesearch != 0; HOTSettings::useCN = usecn != 0; HOTSettings::cneps = cneps;
+    HOTSettings::useAdaptiveHessian = adaptive_h != 0; HOTSettings::debugMode = 0; HOTSettings::useBaselineMultigrid = false;
+    HOTSettings::topDownMGS = false; HOTSettings::levelscale = 0; HOTSettings::matrixFree = matfree != 0;
+    objective.matrix_free = matfree != 0;
+    ExtendedNewtonsMethod<ImplicitSolverObjective<MockSim>> newton(objective, (T)1, max_iterations);
+    LBFGS<ImplicitSolverObjective<MockSim>> lbfgs(objective, (T)1, max_iterations);
+    // startBackwardEuler :166-186 (mass matrix, dv / vn and the collision nodes were set up by implicit_ref_setup / _set_bc / _set_dv)
+    objective.setPreconditioner([s](const TVStack& in, TVStack& out) {
+        for (int i = 0; i < s->num_nodes; i++) {
+            for (int d = 0; d < dim; d++) {
+                out(d, i) = in(d, i) / s->mass_matrix(i);
+            }
+        }
+    });
+    for (int i = 0; i < s->count; ++i) s->Fn[i] = s->F[i]; // force->backupStrain()
+    objective.reinitialize();
+    T maxcntol = -1;
+    if (HOTSettings::useCN) {
+        // computeCharacteristicNorm :128-164 (the function-static first-step cache is per process there: evaluated afresh here)
+        double dPdFNorm = -1, dPdFNorm_max = -1;
+        for (int i = 0; i < s->count; ++i) {
+            auto model = s->model(i);
+            CorotatedIsotropicScratch<T, 3> sc;
+            Hessian9 firstPiolaDerivative;
+            model.updateScratch(TM::Identity(), sc);
+            model.firstPiolaDerivative(sc, firstPiolaDerivative);
+            double curdPdFNorm = firstPiolaDerivative.norm();
+            if (dPdFNorm < 0 || curdPdFNorm < dPdFNorm)
+                dPdFNorm = curdPdFNorm;
+            if (dPdFNorm_max < 0 || curdPdFNorm > dPdFNorm_max)
+                dPdFNorm_max = curdPdFNorm;
+        }
+        objective.evaluatePerNodeCNTolerance(HOTSettings::cneps, s->dt);
+        if (dPdFNorm_max != -1)
+            maxcntol = HOTSettings::cneps * s->dt * 24 * std::sqrt(s->dv.cols()) * s->dx * s->dx * dPdFNorm_max;
+        newton.tolerance = maxcntol;
+        lbfgs.tolerance = maxcntol;
+        objective.minres.setTolerance(maxcntol);
+        objective.cg.setTolerance(maxcntol);
+    }
+    else {
+        lbfgs.tolerance = newton.tolerance = HOTSettings::cneps;
+    }
+    objective.isNewStep = true;
+    objective.curIter = 0;
+    if (HOTSettings::linesearch)
+        objective.resetLSFlag(s->dv);
+    bool converged;
+    if (HOTSettings::lsolver != 3)
+        converged = newton.solve(s->dv, false);
+    else
+        converged = lbfgs.solve(s->dv, false, HOTSettings::linesearch);
+    out[0] = converged ? objective.curIter - 1 : max_iterations; // (curIter counts the shouldExitByCN calls)
+    out[1] = converged ? 1 : 0;
+    out[2] = maxcntol;
+    for (int i = 0; i < s->num_nodes; ++i)
+        for (int d = 0; d < 3; ++d) dv_out[3 * i + d] = s->dv(d, i);
+    s->force->restoreStrain();
+    return 0;
 }
 
 } // extern "C"

@@ -136,6 +136,27 @@ public:
             }
             return r;
         }
+        // ((a.middleCols(..).transpose() * b.middleCols(..)).diagonal().array()).sum()  (ImplicitSolver.h:228): sum over the columns of a_j . b_j
+        struct MiddleT {
+            const Middle* a;
+            struct Prod {
+                const Middle *a, *b;
+                const Prod& diagonal() const { return *this; }
+                const Prod& array() const { return *this; }
+                T sum() const
+                {
+                    T s = 0;
+                    for (int j = 0; j < a->n; ++j) {
+                        T d = 0;
+                        for (int i = 0; i < R; ++i) d += (*a->m)(i, a->start + j) * (*b->m)(i, b->start + j);
+                        s += d;
+                    }
+                    return s;
+                }
+            };
+            Prod operator*(const Middle& b) const { return Prod{a, &b}; }
+        };
+        MiddleT transpose() const { return MiddleT{this}; }
         template <class OP>
         const Middle& operator=(const OP& op) const
         {

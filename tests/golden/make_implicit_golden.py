@@ -27,6 +27,17 @@ CASES = {
 }
 
 
+# whole implicit solves (MultigridSimulation::backwardEulerStep): scene arguments of tests/golden/make_lbfgs_golden.scene, solver options.
+# The first three are the substeps of lbfgs_ref.npz (there: the reference's L-BFGS loop on the ORACLE'S objective; here: on the reference's own).
+HOT = dict(lsolver=3, mg_level=3, smoother=5, coarse_solver=2, project=1, linesearch=1, bcproject=1, usecn=1)   # tog.sh:38
+STEPS = {
+    "hot_default": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT)),
+    "hot_no_linesearch": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, linesearch=0)),
+    "hot_stiff_long": (dict(cells=(7, 9, 6), E=2e6, dt=8e-3, seed=1), dict(HOT, cneps=1e-9)),
+    "pn_mgpcg": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=2, max_newton_iterations=10)),
+    "pn_pcg": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=2, mg_level=1, max_newton_iterations=10)),
+    "pn_pcg_no_cn": (dict(cells=(6, 5, 6), E=3e5, dt=5e-3, seed=2), dict(HOT, lsolver=2, mg_level=1, usecn=0, cneps=1e-6, linesearch=0, max_newton_iterations=10)),
+}
 FULL_MATRIX = ("slip",)        # cases whose block rows are stored entry by entry (the others: columns, block row sums, action on a vector)
 
 
@@ -126,9 +137,49 @@ class Reference:
         x = np.ascontiguousarray(x, dtype=np.float64); b = np.empty_like(x)
         self.lib.implicit_ref_multiply(self.h, int(matfree), _p(x), _p(b)); return b
 
+    def backwardEulerStep(self, lsolver=3, mg_level=3, smoother=5, coarse_solver=2, Ainv=1, linesearch=1, usecn=1, cneps=1e-7, max_iterations=10000,
+                          adaptive_h=0, matfree=0):
+        """the whole implicit solve in the reference's solver templates; returns dict(iterations, converged, tolerance, dv)"""
+        dv = np.empty((self.num_nodes, 3)); out = np.zeros(3)
+        self.lib.implicit_ref_backward_euler_step(self.h, int(lsolver), int(mg_level), int(smoother), int(coarse_solver), int(Ainv), int(linesearch), int(usecn),
+                                                  C.c_double(cneps), int(max_iterations), int(adaptive_h), int(matfree), _p(dv), _p(out))
+        return dict(iterations=int(out[0]), converged=int(out[1]), tolerance=float(out[2]), dv=dv)
+
     def shouldExitByCN(self, r, useCN, cneps):
         r = np.ascontiguousarray(r, dtype=np.float64)
         return int(self.lib.implicit_ref_should_exit_by_cn(self.h, _p(r), int(useCN), C.c_double(cneps)))
+
+
+def _sibling(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tests", "golden", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def step_scene(make_sim, cells, E, dt, seed):
+    """the substep scene of make_lbfgs_golden.scene (seeded block, perturbed F, sticky floor), returned with what the reference side needs"""
+    lg = _sibling("make_lbfgs_golden")
+    from hot_b200 import scenes
+    s = lg.scene(make_sim, cells=cells, E=E, dt=dt, seed=seed)
+    sc = scenes.block(cells, 1.0 / 32, ppc=6, seed=seed, E=E)
+    sc["F"] = sc["F"] + 0.08 * (np.random.default_rng(seed).random(sc["F"].shape) - 0.5)
+    coord = s.get_id2coord()
+    bc = np.nonzero(coord[:, 1] <= coord[:, 1].min() + 1)[0].astype(np.int32)
+    return s, sc, bc
+
+
+def reference_step(sc, bc, dv0, dt, opts):
+    ref = Reference(sc["dx"], dt)
+    ref.setup({k: sc[k] for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam")}, opts.get("project", 1))
+    ref.set_bc(0, bc, np.zeros((len(bc), 9)), None, None, np.zeros(len(bc), dtype=np.int32))
+    ref.set_dv(dv0)
+    lsolver = opts.get("lsolver", 3)
+    return ref.backwardEulerStep(lsolver=lsolver, mg_level=opts.get("mg_level", 3), smoother=opts.get("smoother", 5), coarse_solver=opts.get("coarse_solver", 2),
+                                 Ainv=opts.get("Ainv", 1), linesearch=opts.get("linesearch", 1), usecn=opts.get("usecn", 1), cneps=opts.get("cneps", 1e-7),
+                                 adaptive_h=opts.get("adaptive_h", 0), matfree=opts.get("matfree", 0),
+                                 max_iterations=opts.get("max_lbfgs_iterations", 10000) if lsolver == 3 else opts.get("max_newton_iterations", 3))
 
 
 def vectors(n, seed):
@@ -144,7 +195,7 @@ if __name__ == "__main__":
         n = ref.setup(inp, project)
         # node coordinates for the BC sets come from the pinned transfer library's twin in this one: id2coord of buildMatrix
         col0, _ = ref.buildMatrix(False)
-        import make_mpmgrid_golden as mg          # noqa: E402  (same directory)
+        mg = _sibling("make_mpmgrid_golden")
         g = mg.Reference(dx); g.set_particles(inp["X"], inp["V"], inp["mass"], inp["C"]); g.sortParticlesAndPolluteGrid(); g.particlesToGrid()
         coord = g.get_id2coord()
         node, P, R, Rinv, slip = make_bc(coord, mode)
@@ -182,5 +233,12 @@ if __name__ == "__main__":
         for k, v in out.items():
             gold[f"{name}/{k}"] = v
         print(name, "particles", len(inp["mass"]), "nodes", n, "bc", len(node), "slip", int(slip.sum()), "energy", out["energy"], "exit", out["exit"])
+    import oracle_binding
+    for name, (sc_args, opts) in STEPS.items():
+        o, sc, bc = step_scene(oracle_binding.OracleSim, **sc_args)      # (the oracle only supplies the start value buildInitialDvAndVnForNewton leaves in dv)
+        r = reference_step(sc, bc, o.get_dv(), sc_args["dt"], opts)
+        gold[f"step/{name}/iterations"] = np.int64(r["iterations"]); gold[f"step/{name}/converged"] = np.int64(r["converged"])
+        gold[f"step/{name}/tolerance"] = np.float64(r["tolerance"]); gold[f"step/{name}/dv"] = r["dv"]
+        print("step", name, "iterations", r["iterations"], "converged", r["converged"], "tolerance", r["tolerance"])
     np.savez_compressed(OUT, **gold)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

@@ -88,6 +88,36 @@ def test_golden_exit_tests_bracket_the_threshold():
         assert abs(scaled.sum() / n - 1.0) < 1e-9
 
 
+def _check_step(make_sim, name, rtol_dv):
+    """a whole implicit solve (row a24 + the Newton / L-BFGS outer loops a22): same number of nonlinear iterations, same tolerance, same dv"""
+    sc_args, opts = gen.STEPS[name]
+    s, _, _ = gen.step_scene(make_sim, **sc_args)
+    log = s.backwardEulerStep(**opts)
+    g = lambda k: G[f"step/{name}/{k}"]
+    assert log["iterations"] == int(g("iterations")), (name, log["iterations"], int(g("iterations")))
+    assert bool(log["converged"]) == bool(g("converged"))
+    if opts.get("usecn", 1):
+        assert abs(log["tolerance"] - float(g("tolerance"))) <= 1e-12 * float(g("tolerance"))
+    dv = s.get_dv()
+    assert np.abs(dv - g("dv")).max() <= rtol_dv * np.abs(g("dv")).max(), (name, np.abs(dv - g("dv")).max() / np.abs(g("dv")).max())
+    s.close()
+
+
+@pytest.mark.parametrize("name", list(gen.STEPS))
+def test_oracle_whole_solve_against_reference_code(oracle, name):
+    """the oracle's backwardEulerStep against MultigridSimulation::backwardEulerStep's sequence run in the reference's ExtendedNewtonsMethod / LBFGS /
+    ImplicitSolverObjective / InexactConjugateGradient / MultigridBuilder / MultigridOperator code"""
+    _check_step(oracle.OracleSim, name, 1e-9)
+
+
+def test_whole_solve_golden_agrees_with_the_lbfgs_golden():
+    """the same substeps with the reference's L-BFGS loop on the ORACLE'S objective (lbfgs_ref.npz) and on the REFERENCE'S objective (here)"""
+    L = np.load(os.path.join(ROOT, "tests", "golden", "lbfgs_ref.npz"))
+    for name in ("hot_default", "hot_no_linesearch", "hot_stiff_long"):
+        assert int(L[name + "_iterations"]) == int(G[f"step/{name}/iterations"])
+        assert np.abs(L[name + "_dv"] - G[f"step/{name}/dv"]).max() <= 1e-9 * np.abs(L[name + "_dv"]).max()
+
+
 @pytest.mark.skipif(not os.path.exists(gen.REF_LIB), reason="oracle/_ref/libimplicit_ref.so not built (needs /root/reference)")
 def test_reference_objective_reproduces_the_golden_vectors():
     name = "slip"
@@ -107,3 +137,10 @@ def test_reference_objective_reproduces_the_golden_vectors():
 @pytest.mark.parametrize("name", list(gen.CASES))
 def test_cuda_objective_against_reference_code(hot, name):
     _check(hot.MpmSimulationB200, name, exact_slots=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["hot_default", "hot_no_linesearch", "hot_stiff_long"])
+def test_cuda_whole_solve_against_reference_code(hot, name):
+    """hot_backward_euler_step against the reference's own solve (the substeps of test_oracle_lbfgs_ref.py, same bars)"""
+    _check_step(hot.MpmSimulationB200, name, 1e-5)
