@@ -2,11 +2,21 @@
 // product path (hot_b200/, include/).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs may use it, and only as the checker / reported baseline.
 //
-// Parity status: the SPGrid addressing part (this header, section 1) is PINNED against the reference's own
-// SPGrid core compiled from /root/reference (oracle/_ref/libspgrid_ref.so, tests/golden/spgrid_*.npz).
-// Everything else is a restatement of a reference that ships no tests/golden vectors and cannot be built
-// here (Eigen/TBB/OpenVDB/... absent): "parity unpinned" by the reference, pinned instead by the reference's
-// own in-code invariants (diff-test, matrix == matrix-free, symmetry/PD, BC zero) and numpy/scipy.
+// Parity status: PINNED against the reference's own code, compiled where it lies under /root/reference into oracle/_ref/ (oracle/Makefile,
+// golden vectors + generating scripts under tests/golden/, one tests/test_oracle_*_ref.py per library):
+//   SPGrid addressing (this header, section 1)                      SPGrid core                                 libspgrid_ref.so
+//   B-spline weights, QR-SVD, makePD, fixed-corotated psi / P / dP  BSplines.h, ImplicitQRSVD.h, CorotatedIsotropic.h ...   libziran_ref.so
+//   inexact PCG, MINRES                                             InexactConjugateGradient.h, Minres.h        libziran_ref.so
+//   Galerkin hierarchy, colouring, smoothers, V-cycle               MultigridPreconditioner.h, SquareMatrix.h   libziran_ref.so
+//   L-BFGS loop                                                     LBFGS.h                                     libhot_oracle_lbfgsref.so
+//   node record, sort + page activation, P2G, DOF numbering, G2P    MpmGrid.h over SPGrid_Page_Map              libmpmgrid_ref.so
+//   objective: state update, energy, residual, Hessian apply, CN tolerance, buildMatrix (+ BC projection), buildDiagonal, and whole
+//   implicit solves (Newton + PCG / MGPCG, HOT)                     ImplicitSolver.h, ExtendedNewtonsMethod.h, LBFGS.h, ...   libimplicit_ref.so
+// The member functions of MpmSimulationBase / MpmForceBase / FBasedMpmForceHelper themselves cannot be compiled here (Scene / DataManager /
+// Particles / TBB containers / Partio absent): their particle loops are written out in the shims around the reference's grid, model and
+// objective code (each shim's header lists exactly which lines).  Still "parity unpinned" by reference code: collision objects /
+// buildInitialDvAndVnForNewton (a8, AnalyticLevelSet.cpp needs OpenVDB), the plasticity return mappings, Chebyshev's seeded 2-norm estimate,
+// and the extensions (Drucker-Prager, neo-Hookean) - those rest on the reference's in-code invariants and numpy / scipy checks.
 //
 // Section 1: SPGrid addressing restated from Lib/SPGrid/Core/SPGrid_Mask.h:22-52,59-128,150-189,237-245.
 // Section 2: quadratic B-spline weights from Lib/Ziran/Math/Splines/BSplines.h:10-29,55-81 and
