@@ -7,4 +7,5 @@ template <class T> void writeEntry(std::ostream& out, const T& x) { out.write(re
 template <class T> T readEntry(std::istream& in) { T x; in.read(reinterpret_cast<char*>(&x), sizeof(T)); return x; }
 template <class T> struct RW;
 template <class T> struct NoWriteTag {};
+template <class T> struct CustomTypeTag {};
 } // namespace ZIRAN
