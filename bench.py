@@ -170,6 +170,39 @@ def cpu_baseline(sc, reps, warmup=1):
     return n, times, cores, t_sort
 
 
+def reference_code_baseline(sc, max_particles=250000, reps=2):
+    """P2G + G2P of the REFERENCE'S OWN grid code (Lib/MPM/MpmGrid.h over its SPGrid page map, compiled where it lies into
+    oracle/_ref/libmpmgrid_ref.so; its TBB loops run serially because TBB is not in this image) on a bounded spatial slab of the workload:
+    reported beside the OpenMP port so the port can be judged against the code it restates.  None when the library is absent."""
+    try:
+        import importlib.util
+        path = os.path.join(ROOT, "tests", "golden", "make_mpmgrid_golden.py")
+        spec = importlib.util.spec_from_file_location("make_mpmgrid_golden", path)
+        gen = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(gen)
+        if not os.path.exists(gen.REF_LIB):
+            return None
+        n = len(sc["mass"])
+        keep = np.argsort(sc["X"][:, 0], kind="stable")[:min(n, max_particles)]      # the lowest-x slab: a compact piece of the object
+        ref = gen.Reference(sc["dx"])
+        ref.set_particles(sc["X"][keep], sc["V"][keep], sc["mass"][keep], sc["C"][keep])
+        ref.sortParticlesAndPolluteGrid()
+        times = []
+        for it in range(1 + reps):
+            t0 = time.perf_counter()
+            nn = ref.particlesToGrid()
+            ref.set_dv(np.zeros((nn, 3)))
+            ref.gridToParticles(0.0)
+            if it >= 1:
+                times.append(time.perf_counter() - t0)
+        t = float(np.mean(times))
+        return {"value": len(keep) / t / 1e6, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": f"lowest-x slab of {len(keep)} particles, {reps} timed P2G+G2P steps of the reference's MpmGrid / SPGrid code "
+                          f"(oracle/_ref/libmpmgrid_ref.so; serial: TBB absent)"}
+    except Exception as e:          # a reported extra, never in the way of the line
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def cpu_vcycle_baseline(full_nodes, reps=3):
     """V-cycle ms of the CPU path (oracle = OpenMP restatement of the reference's block-ELL / coloured-GS code) on a BOUNDED
     sample of the C2 workload: a 22x40x22-cell slab of the same bar (same dx, ppc, material, end-cap BCs), scaled to the
@@ -230,6 +263,9 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    rc = reference_code_baseline(sc)
+    if rc is not None:
+        line["cpu_baseline"]["reference_code"] = rc
     print(json.dumps(line))
 
 
@@ -601,6 +637,9 @@ def run_ours(args):
             cms = float(np.mean(ctimes))
             cpu = {"value": cn / cms / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"whole workload ({cn} particles), {args.cpu_reps} timed P2G+G2P steps of the OpenMP oracle after 1 warm-up"}
+            rc = reference_code_baseline(sc)
+            if rc is not None:
+                cpu["reference_code"] = rc
             if solver is not None:
                 cpu["vcycle"] = cpu_vcycle_baseline(n_nodes)
                 cpu["hot_substep"] = cpu_substep_baseline()
