@@ -346,8 +346,9 @@ int compute_step(Objective& O, double* ddv, double* residual, double cg_toleranc
         O.precond = 1;
     }
     int iters = 0;
-    // -lsolver 1: MINRES with minres.setTolerance(1) of the objective's constructor (ImplicitSolver.h:87,406-411); 2: inexact PCG
-    if (o.lsolver == 1) RC(minres_solve(O, ddv, residual, rel_tol, 1.0, o.max_cg_iterations, &iters));
+    // -lsolver 1: MINRES (ImplicitSolver.h:406-411), 2: inexact PCG; both with the absolute tolerance backwardEulerStep gives them:
+    // minres.setTolerance(maxcntol) / cg.setTolerance(maxcntol) with --usecn (MultigridSimulation.h:206-207), else the constructor's 1 (:86-88)
+    if (o.lsolver == 1) RC(minres_solve(O, ddv, residual, rel_tol, cg_tolerance, o.max_cg_iterations, &iters));
     else RC(inexact_pcg(O, ddv, residual, cg_tolerance, o.max_cg_iterations, &iters));
     if (O.log) {
         O.log->total_linear_iterations += iters;

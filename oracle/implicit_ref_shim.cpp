@@ -574,7 +574,7 @@ int implicit_ref_should_exit_by_cn(void* h, const double* r, int useCN, double c
 // (LBFGS.h:300-437: lsolver 3 = HOT) on the objective above.  The simulation's dv (already holding buildInitialDvAndVnForNewton's start value,
 // implicit_ref_set_dv) is the solution vector, as in :219-221.  out = {iterations (shouldExitByCN calls - 1), converged, final |residual|}
 int implicit_ref_backward_euler_step(void* h, int lsolver, int levels, int smoother, int coarse_solver, int Ainv, int linesearch, int usecn, double cneps,
-    int max_iterations, int adaptive_h, int matfree, double* dv_out, double* out)
+    int max_iterations, int adaptive_h, int matfree, int bcproject, int max_linear_iterations, double* dv_out, double* out)
 {
     MockSim* s = (MockSim*)h;
     auto& objective = *s->objective;
@@ -583,6 +583,9 @@ int implicit_ref_backward_euler_step(void* h, int lsolver, int levels, int smoot
     HOTSettings::useAdaptiveHessian = adaptive_h != 0; HOTSettings::debugMode = 0; HOTSettings::useBaselineMultigrid = false;
     HOTSettings::topDownMGS = false; HOTSettings::levelscale = 0; HOTSettings::matrixFree = matfree != 0;
     objective.matrix_free = matfree != 0;
+    objective.minres.max_iterations = max_linear_iterations; // the scene set-up raises both from the constructor's 20 / 10000 (MultigridInit3D.h:85-87)
+    objective.cg.max_iterations = max_linear_iterations;
+    HOTSettings::systemBCProject = bcproject != 0; // (--matfree runs without --bcproject: computeStep adds dRhs, which only buildMatrix<true> sizes)
     ExtendedNewtonsMethod<ImplicitSolverObjective<MockSim>> newton(objective, (T)1, max_iterations);
     LBFGS<ImplicitSolverObjective<MockSim>> lbfgs(objective, (T)1, max_iterations);
     // startBackwardEuler :166-186 (mass matrix, dv / vn and the collision nodes were set up by implicit_ref_setup / _set_bc / _set_dv)

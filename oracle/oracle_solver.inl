@@ -266,8 +266,9 @@ int compute_step(Sim* s, ObjectiveState& O, Vd& ddv, Vd& residual, double rel_to
         O.precond = 1;
     }
     int iters = 0;
-    // -lsolver 1: MINRES with minres.setTolerance(1) of the objective's constructor (ImplicitSolver.h:87,406-411); -lsolver 2: inexact PCG
-    int rc = o.lsolver == 1 ? minres_solve(s, O, ddv, residual, rel_tol, 1.0, o.max_cg_iterations, &iters)
+    // -lsolver 1: MINRES (ImplicitSolver.h:406-411), -lsolver 2: inexact PCG; both with the absolute tolerance backwardEulerStep gives them:
+    // minres.setTolerance(maxcntol) / cg.setTolerance(maxcntol) with --usecn (MultigridSimulation.h:206-207), else the constructor's 1 (:86-88)
+    int rc = o.lsolver == 1 ? minres_solve(s, O, ddv, residual, rel_tol, cg_tolerance, o.max_cg_iterations, &iters)
                             : inexact_pcg(s, O, ddv, residual, cg_tolerance, o.max_cg_iterations, &iters);
     if (rc) return rc;
     if (O.log) {

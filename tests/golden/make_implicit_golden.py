@@ -37,6 +37,16 @@ STEPS = {
     "pn_mgpcg": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=2, max_newton_iterations=10)),
     "pn_pcg": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=2, mg_level=1, max_newton_iterations=10)),
     "pn_pcg_no_cn": (dict(cells=(6, 5, 6), E=3e5, dt=5e-3, seed=2), dict(HOT, lsolver=2, mg_level=1, usecn=0, cneps=1e-6, linesearch=0, max_newton_iterations=10)),
+    "pn_pcg_matfree": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=2, matfree=1, mg_level=1, bcproject=0, max_newton_iterations=10)),
+    "pn_pcg_entry_diagonal": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=2, mg_level=1, Ainv=0, max_newton_iterations=10)),
+    "pn_mgpcg_jacobi_levels": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=2, mg_level=2, smoother=1, coarse_solver=0, max_newton_iterations=10)),
+    "hot_jacobi_smoother": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, smoother=0)),
+    "hot_adaptive_hessian": (dict(cells=(7, 9, 6), E=2e6, dt=8e-3, seed=1), dict(HOT, cneps=1e-9, adaptive_h=1)),
+    # -lsolver 1 (f4): Newton + MINRES; its absolute tolerance is maxcntol with --usecn (MultigridSimulation.h:206), the constructor's 1 without
+    "pn_mgminres": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=1, max_newton_iterations=10)),
+    "pn_minres": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=1, mg_level=1, max_newton_iterations=10)),
+    "pn_minres_matfree": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=1, mg_level=1, matfree=1, bcproject=0, max_newton_iterations=10)),
+    "pn_minres_no_cn": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=1, mg_level=1, usecn=0, cneps=1e-6, linesearch=0, max_newton_iterations=10)),
 }
 FULL_MATRIX = ("slip",)        # cases whose block rows are stored entry by entry (the others: columns, block row sums, action on a vector)
 
@@ -138,11 +148,11 @@ class Reference:
         self.lib.implicit_ref_multiply(self.h, int(matfree), _p(x), _p(b)); return b
 
     def backwardEulerStep(self, lsolver=3, mg_level=3, smoother=5, coarse_solver=2, Ainv=1, linesearch=1, usecn=1, cneps=1e-7, max_iterations=10000,
-                          adaptive_h=0, matfree=0):
+                          adaptive_h=0, matfree=0, bcproject=1, max_linear_iterations=10000):
         """the whole implicit solve in the reference's solver templates; returns dict(iterations, converged, tolerance, dv)"""
         dv = np.empty((self.num_nodes, 3)); out = np.zeros(3)
         self.lib.implicit_ref_backward_euler_step(self.h, int(lsolver), int(mg_level), int(smoother), int(coarse_solver), int(Ainv), int(linesearch), int(usecn),
-                                                  C.c_double(cneps), int(max_iterations), int(adaptive_h), int(matfree), _p(dv), _p(out))
+                                                  C.c_double(cneps), int(max_iterations), int(adaptive_h), int(matfree), int(bcproject), int(max_linear_iterations), _p(dv), _p(out))
         return dict(iterations=int(out[0]), converged=int(out[1]), tolerance=float(out[2]), dv=dv)
 
     def shouldExitByCN(self, r, useCN, cneps):
@@ -178,7 +188,7 @@ def reference_step(sc, bc, dv0, dt, opts):
     lsolver = opts.get("lsolver", 3)
     return ref.backwardEulerStep(lsolver=lsolver, mg_level=opts.get("mg_level", 3), smoother=opts.get("smoother", 5), coarse_solver=opts.get("coarse_solver", 2),
                                  Ainv=opts.get("Ainv", 1), linesearch=opts.get("linesearch", 1), usecn=opts.get("usecn", 1), cneps=opts.get("cneps", 1e-7),
-                                 adaptive_h=opts.get("adaptive_h", 0), matfree=opts.get("matfree", 0),
+                                 adaptive_h=opts.get("adaptive_h", 0), matfree=opts.get("matfree", 0), bcproject=opts.get("bcproject", 1), max_linear_iterations=opts.get("max_cg_iterations", 10000),
                                  max_iterations=opts.get("max_lbfgs_iterations", 10000) if lsolver == 3 else opts.get("max_newton_iterations", 3))
 
 
