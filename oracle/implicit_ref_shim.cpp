@@ -574,14 +574,14 @@ int implicit_ref_should_exit_by_cn(void* h, const double* r, int useCN, double c
 // (LBFGS.h:300-437: lsolver 3 = HOT) on the objective above.  The simulation's dv (already holding buildInitialDvAndVnForNewton's start value,
 // implicit_ref_set_dv) is the solution vector, as in :219-221.  out = {iterations (shouldExitByCN calls - 1), converged, final |residual|}
 int implicit_ref_backward_euler_step(void* h, int lsolver, int levels, int smoother, int coarse_solver, int Ainv, int linesearch, int usecn, double cneps,
-    int max_iterations, int adaptive_h, int matfree, int bcproject, int max_linear_iterations, double* dv_out, double* out)
+    int max_iterations, int adaptive_h, int matfree, int bcproject, int max_linear_iterations, int times, int levelscale, double topomega, double* dv_out, double* out)
 {
     MockSim* s = (MockSim*)h;
     auto& objective = *s->objective;
     HOTSettings::lsolver = lsolver; HOTSettings::levelCnt = levels; HOTSettings::smoother = smoother; HOTSettings::coarseSolver = coarse_solver;
-    HOTSettings::Ainv = Ainv; HOTSettings::times = 1; HOTSettings::linesearch = linesearch != 0; HOTSettings::useCN = usecn != 0; HOTSettings::cneps = cneps;
+    HOTSettings::Ainv = Ainv; HOTSettings::times = times; HOTSettings::linesearch = linesearch != 0; HOTSettings::useCN = usecn != 0; HOTSettings::cneps = cneps;
     HOTSettings::useAdaptiveHessian = adaptive_h != 0; HOTSettings::debugMode = 0; HOTSettings::useBaselineMultigrid = false;
-    HOTSettings::topDownMGS = false; HOTSettings::levelscale = 0; HOTSettings::matrixFree = matfree != 0;
+    HOTSettings::topDownMGS = false; HOTSettings::levelscale = levelscale; HOTSettings::topomega = topomega; HOTSettings::matrixFree = matfree != 0;
     objective.matrix_free = matfree != 0;
     objective.minres.max_iterations = max_linear_iterations; // the scene set-up raises both from the constructor's 20 / 10000 (MultigridInit3D.h:85-87)
     objective.cg.max_iterations = max_linear_iterations;

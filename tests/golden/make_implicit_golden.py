@@ -42,6 +42,12 @@ STEPS = {
     "pn_mgpcg_jacobi_levels": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=2, mg_level=2, smoother=1, coarse_solver=0, max_newton_iterations=10)),
     "hot_jacobi_smoother": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, smoother=0)),
     "hot_adaptive_hessian": (dict(cells=(7, 9, 6), E=2e6, dt=8e-3, seed=1), dict(HOT, cneps=1e-9, adaptive_h=1)),
+    "hot_times3_jacobi": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, mg_times=3, smoother=0)),
+    "hot_levelscale2_times2": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, mg_scale=2, mg_times=2)),
+    "hot_optimal_jacobi_omega": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, smoother=1, coarse_solver=1, topomega=0.5)),
+    "hot_pcg_smoother": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, smoother=2)),
+    "lbfgs_h": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, bcproject=0, mg_level=1, mg_times=10000, smoother=2, coarse_solver=2)),
+    "hot_four_levels_no_pd": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, mg_level=4, project=0)),
     # -lsolver 1 (f4): Newton + MINRES; its absolute tolerance is maxcntol with --usecn (MultigridSimulation.h:206), the constructor's 1 without
     "pn_mgminres": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=1, max_newton_iterations=10)),
     "pn_minres": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=1, mg_level=1, max_newton_iterations=10)),
@@ -148,11 +154,12 @@ class Reference:
         self.lib.implicit_ref_multiply(self.h, int(matfree), _p(x), _p(b)); return b
 
     def backwardEulerStep(self, lsolver=3, mg_level=3, smoother=5, coarse_solver=2, Ainv=1, linesearch=1, usecn=1, cneps=1e-7, max_iterations=10000,
-                          adaptive_h=0, matfree=0, bcproject=1, max_linear_iterations=10000):
+                          adaptive_h=0, matfree=0, bcproject=1, max_linear_iterations=10000, mg_times=1, mg_scale=0, topomega=0.1):
         """the whole implicit solve in the reference's solver templates; returns dict(iterations, converged, tolerance, dv)"""
         dv = np.empty((self.num_nodes, 3)); out = np.zeros(3)
         self.lib.implicit_ref_backward_euler_step(self.h, int(lsolver), int(mg_level), int(smoother), int(coarse_solver), int(Ainv), int(linesearch), int(usecn),
-                                                  C.c_double(cneps), int(max_iterations), int(adaptive_h), int(matfree), int(bcproject), int(max_linear_iterations), _p(dv), _p(out))
+                                                  C.c_double(cneps), int(max_iterations), int(adaptive_h), int(matfree), int(bcproject), int(max_linear_iterations), int(mg_times), int(mg_scale), C.c_double(topomega),
+                                                  _p(dv), _p(out))
         return dict(iterations=int(out[0]), converged=int(out[1]), tolerance=float(out[2]), dv=dv)
 
     def shouldExitByCN(self, r, useCN, cneps):
@@ -188,7 +195,8 @@ def reference_step(sc, bc, dv0, dt, opts):
     lsolver = opts.get("lsolver", 3)
     return ref.backwardEulerStep(lsolver=lsolver, mg_level=opts.get("mg_level", 3), smoother=opts.get("smoother", 5), coarse_solver=opts.get("coarse_solver", 2),
                                  Ainv=opts.get("Ainv", 1), linesearch=opts.get("linesearch", 1), usecn=opts.get("usecn", 1), cneps=opts.get("cneps", 1e-7),
-                                 adaptive_h=opts.get("adaptive_h", 0), matfree=opts.get("matfree", 0), bcproject=opts.get("bcproject", 1), max_linear_iterations=opts.get("max_cg_iterations", 10000),
+                                 adaptive_h=opts.get("adaptive_h", 0), matfree=opts.get("matfree", 0), bcproject=opts.get("bcproject", 1), max_linear_iterations=opts.get("max_cg_iterations", 10000), mg_times=opts.get("mg_times", 1), mg_scale=opts.get("mg_scale", 0),
+                                 topomega=opts.get("topomega", 0.1),
                                  max_iterations=opts.get("max_lbfgs_iterations", 10000) if lsolver == 3 else opts.get("max_newton_iterations", 3))
 
 
