@@ -48,6 +48,8 @@ STEPS = {
     "hot_pcg_smoother": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, smoother=2)),
     "lbfgs_h": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, bcproject=0, mg_level=1, mg_times=10000, smoother=2, coarse_solver=2)),
     "hot_four_levels_no_pd": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, mg_level=4, project=0)),
+    "hot_two_materials": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0, stiff_layer=(25.0, 0.4)), dict(HOT)),     # tolerance from the stiffest dP/dF
+    "pn_mgpcg_two_materials": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0, stiff_layer=(25.0, 0.4)), dict(HOT, lsolver=2, max_newton_iterations=10)),
     # -lsolver 1 (f4): Newton + MINRES; its absolute tolerance is maxcntol with --usecn (MultigridSimulation.h:206), the constructor's 1 without
     "pn_mgminres": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=1, max_newton_iterations=10)),
     "pn_minres": (dict(cells=(6, 6, 6), E=4e5, dt=5e-3, seed=0), dict(HOT, lsolver=1, mg_level=1, max_newton_iterations=10)),
@@ -77,6 +79,9 @@ def make_inputs(name):
     rng = np.random.default_rng(17)
     inp = {k: np.ascontiguousarray(sc[k]) for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam")}
     inp["F"] = inp["F"] + 0.08 * (rng.random(inp["F"].shape) - 0.5)     # strained start of the step (some particles get a clamped Hessian)
+    if name == "slip_noproject":                                       # two materials: every third particle 20 x stiffer
+        inp["mu"] = inp["mu"].copy(); inp["lam"] = inp["lam"].copy()
+        inp["mu"][::3] *= 20.0; inp["lam"][::3] *= 20.0
     return inp, sc["dx"], dt, mode, project
 
 
@@ -175,15 +180,24 @@ def _sibling(name):
     return mod
 
 
-def step_scene(make_sim, cells, E, dt, seed):
-    """the substep scene of make_lbfgs_golden.scene (seeded block, perturbed F, sticky floor), returned with what the reference side needs"""
-    lg = _sibling("make_lbfgs_golden")
+def step_scene(make_sim, cells, E, dt, seed, stiff_layer=None):
+    """the substep scene of make_lbfgs_golden.scene (seeded block, perturbed F, sticky floor), returned with what the reference side needs;
+    stiff_layer = (factor, fraction): the particles of the upper `fraction` of the block get `factor` times the Lame parameters (two materials)"""
     from hot_b200 import scenes
-    s = lg.scene(make_sim, cells=cells, E=E, dt=dt, seed=seed)
     sc = scenes.block(cells, 1.0 / 32, ppc=6, seed=seed, E=E)
     sc["F"] = sc["F"] + 0.08 * (np.random.default_rng(seed).random(sc["F"].shape) - 0.5)
+    if stiff_layer is not None:
+        factor, fraction = stiff_layer
+        y = sc["X"][:, 1]
+        top = y > y.max() - fraction * (y.max() - y.min())
+        sc["mu"] = np.where(top, factor * sc["mu"], sc["mu"]); sc["lam"] = np.where(top, factor * sc["lam"], sc["lam"])
+    s = make_sim(sc["dx"])
+    s.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
+    s.set_dt_gravity(dt, GRAVITY)
+    s.sortParticlesAndPolluteGrid(); s.particlesToGrid()
     coord = s.get_id2coord()
     bc = np.nonzero(coord[:, 1] <= coord[:, 1].min() + 1)[0].astype(np.int32)
+    s.set_bc(bc, P=np.zeros((len(bc), 9)), dv_bc=np.zeros((len(bc), 3)))
     return s, sc, bc
 
 
