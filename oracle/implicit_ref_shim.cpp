@@ -35,25 +35,16 @@
 #include <Ziran/Physics/ConstitutiveModel/HyperelasticConstitutiveModel.h>
 #include <Ziran/Physics/ConstitutiveModel/CorotatedIsotropic.h>
 
-// names ImplicitSolver.h uses from headers that cannot be compiled here (DataManager.h, CollisionObject.h): same members, nothing else
+// names ImplicitSolver.h uses from headers that cannot be compiled here: AttributeName / DataManager (ref_shim/Ziran/CS/DataStructure/DataManager.h, shared
+// with PlasticityApplier.cpp below) and CollisionNode (CollisionObject.h: same members, nothing else)
+#include <Ziran/Physics/PlasticityApplier.cpp> // the reference's return mappings, compiled where they lie (see plasticity_ref_shim.cpp)
 namespace ZIRAN {
-template <class Type>
-struct AttributeName {
-    std::string name;
-    AttributeName(const char* n) : name(n) {}
-};
 template <class T_, int dim_>
 struct CollisionNode { // Lib/Ziran/Math/Geometry/CollisionObject.h:16-25
     int node_id;
     Matrix<T_, dim_, dim_> P;
     Matrix<T_, dim_, dim_> R, Rinv;
     bool shouldRotate;
-};
-class DataManager {
-public:
-    std::vector<double>* measure = nullptr;
-    std::vector<double>* m = nullptr;
-    std::vector<double>& get(const AttributeName<double>& a) { return a.name == "m" ? *m : *measure; }
 };
 } // namespace ZIRAN
 
@@ -132,7 +123,9 @@ struct MockSim : public RefSim {
     bool quasistatic = false, full_implicit = false, verbose = false, project_pd = true;
     std::vector<CollisionNode<T, 3>> collision_nodes;
     MockParticles particles;
-    std::vector<T> vol, mu, lam;
+    std::vector<T> vol, mu, lam, Jp;
+    bool cn_first = true;
+    double cn_dPdFNorm = -1, cn_dPdFNorm_max = -1;
     std::vector<TM> F, Fn;
     TVStack scratch_vp, scratch_fp;
     std::vector<TM> scratch_stress;
@@ -395,6 +388,7 @@ void* implicit_ref_create(double dx, double dt, const double* gravity)
     s->dt = dt;
     for (int d = 0; d < 3; ++d) s->gravity(d) = gravity[d];
     s->collision_nodes.clear();
+    s->cn_first = true; s->cn_dPdFNorm = -1; s->cn_dPdFNorm_max = -1;
     s->objective->initialize([](TVStack&) {});
     s->objective->setPreconditioner([](const TVStack& x, TVStack& b) { b = x; });
     s->objective->matrix_free = false;
@@ -404,6 +398,26 @@ void* implicit_ref_create(double dx, double dt, const double* gravity)
     return s;
 }
 void implicit_ref_destroy(void*) {}
+int implicit_ref_begin_step(void* h);
+void implicit_ref_get_F(void* h, double* F);
+
+// the first half of advanceOneTimeStep (MultigridSimulation.h:235-281): reinitialize -> sortParticlesAndPolluteGrid, particlesToGrid, and the part of
+// startBackwardEuler that does not need the collision objects (buildMassMatrix, dv / vn sized, vn = grid velocity, backupStrain); returns num_nodes
+int implicit_ref_begin_step(void* h)
+{
+    MockSim* s = (MockSim*)h;
+    s->collision_nodes.clear();
+    mpmgrid_ref_sort(s);
+    int nn = mpmgrid_ref_p2g(s);
+    s->mass_matrix.resize(nn); s->dv.resize(3, nn); s->vn.resize(3, nn);
+    s->dv.setZero();
+    s->grid.iterateGrid([&](IV node, GridState<T, dim>& g) { // buildMassMatrix :817-826, vn
+        s->mass_matrix(g.idx) = g.m;
+        s->vn.col(g.idx) = g.v;
+    });
+    for (int i = 0; i < s->count; ++i) s->Fn[i] = s->F[i]; // backupStrain
+    return nn;
+}
 
 // particles (the oracle's buffer layouts: matrices column-major) -> sort -> P2G on the reference grid code; F is the strain at the start of the step
 int implicit_ref_setup(void* h, long n, const double* X, const double* V, const double* mass, const double* C, const double* F, const double* vol,
@@ -417,15 +431,8 @@ int implicit_ref_setup(void* h, long n, const double* X, const double* V, const 
     s->project_pd = project != 0;
     s->scratch_vp.resize(3, (int)n); s->scratch_fp.resize(3, (int)n);
     s->particles.Xp = &s->X; s->particles.count = (int)n; s->particles.measure = &s->vol; s->particles.m = &s->mass;
-    mpmgrid_ref_sort(s);
-    int nn = mpmgrid_ref_p2g(s);
-    s->mass_matrix.resize(nn); s->dv.resize(3, nn); s->vn.resize(3, nn);
-    s->dv.setZero();
-    s->grid.iterateGrid([&](IV node, GridState<T, dim>& g) { // buildMassMatrix :817-826, vn
-        s->mass_matrix(g.idx) = g.m;
-        s->vn.col(g.idx) = g.v;
-    });
-    return nn;
+    s->Jp.assign(n, 1.0);
+    return implicit_ref_begin_step(h);
 }
 
 // collision nodes (the products of buildInitialDvAndVnForNewton) and the projection MultigridSimulation::initialize hands to the objective
@@ -600,20 +607,26 @@ int implicit_ref_backward_euler_step(void* h, int lsolver, int levels, int smoot
     objective.reinitialize();
     T maxcntol = -1;
     if (HOTSettings::useCN) {
-        // computeCharacteristicNorm :128-164 (the function-static first-step cache is per process there: evaluated afresh here)
-        double dPdFNorm = -1, dPdFNorm_max = -1;
-        for (int i = 0; i < s->count; ++i) {
-            auto model = s->model(i);
-            CorotatedIsotropicScratch<T, 3> sc;
-            Hessian9 firstPiolaDerivative;
-            model.updateScratch(TM::Identity(), sc);
-            model.firstPiolaDerivative(sc, firstPiolaDerivative);
-            double curdPdFNorm = firstPiolaDerivative.norm();
-            if (dPdFNorm < 0 || curdPdFNorm < dPdFNorm)
-                dPdFNorm = curdPdFNorm;
-            if (dPdFNorm_max < 0 || curdPdFNorm > dPdFNorm_max)
-                dPdFNorm_max = curdPdFNorm;
+        // computeCharacteristicNorm :128-164; its function-static first-step cache (`first`, dPdFNorm, dPdFNorm_max) lives in the simulation object
+        // here and is reset by implicit_ref_create, i.e. once per "process": later steps keep the first step's norms even when the snow model hardens
+        double& dPdFNorm = s->cn_dPdFNorm;
+        double& dPdFNorm_max = s->cn_dPdFNorm_max;
+        if (s->cn_first) {
+            for (int i = 0; i < s->count; ++i) {
+                auto model = s->model(i);
+                CorotatedIsotropicScratch<T, 3> sc;
+                Hessian9 firstPiolaDerivative;
+                model.updateScratch(TM::Identity(), sc);
+                model.firstPiolaDerivative(sc, firstPiolaDerivative);
+                double curdPdFNorm = firstPiolaDerivative.norm();
+                if (dPdFNorm < 0 || curdPdFNorm < dPdFNorm)
+                    dPdFNorm = curdPdFNorm;
+                if (dPdFNorm_max < 0 || curdPdFNorm > dPdFNorm_max)
+                    dPdFNorm_max = curdPdFNorm;
+            }
         }
+        if (dPdFNorm > 0)
+            s->cn_first = false;
         objective.evaluatePerNodeCNTolerance(HOTSettings::cneps, s->dt);
         if (dPdFNorm_max != -1)
             maxcntol = HOTSettings::cneps * s->dt * 24 * std::sqrt(s->dv.cols()) * s->dx * s->dx * dPdFNorm_max;
@@ -641,6 +654,54 @@ int implicit_ref_backward_euler_step(void* h, int lsolver, int levels, int smoot
         for (int d = 0; d < 3; ++d) dv_out[3 * i + d] = s->dv(d, i);
     s->force->restoreStrain();
     return 0;
+}
+
+// the second half of advanceOneTimeStep: gridToParticles(dt) = constructNewVelocityFromNewtonResult + the G2P of mpmgrid_ref_shim.cpp, then
+// force->evolveStrain(dt) (FBasedMpmForceHelper.cpp:100-114) and applyPlasticity (MpmSimulationBase.cpp:1039-1064) with the reference's return mappings:
+// model 0 none, 1 VonMisesFixedCorotated(q[0]), 2 SnowPlasticity(q[0..4]) carrying Jp and hardening mu / lambda per particle
+void implicit_ref_end_step(void* h, double dt, int plastic_model, const double* q, int* flags)
+{
+    MockSim* s = (MockSim*)h;
+    std::vector<double> dv(3 * (size_t)s->num_nodes);
+    for (int i = 0; i < s->num_nodes; ++i)
+        for (int d = 0; d < 3; ++d) dv[3 * i + d] = s->dv(d, i);
+    mpmgrid_ref_g2p(s, dv.data(), dt, flags);
+    for (int p = 0; p < s->count; ++p) {
+        auto& F = s->F[p];
+        F = (TM::Identity() + ((T)dt) * s->scratch_gradV[p]) * F;
+    }
+    for (int p = 0; p < s->count && plastic_model; ++p) {
+        CorotatedIsotropic<T, 3> c = s->model(p);
+        if (plastic_model == 2) {
+            SnowPlasticity<T> pl(q[0], q[1], q[2], q[3], q[4]);
+            pl.Jp = s->Jp[p];
+            pl.projectStrain(c, s->F[p]);
+            s->Jp[p] = pl.Jp;
+        }
+        else {
+            VonMisesFixedCorotated<T, 3> pl(q[0]);
+            pl.projectStrain(c, s->F[p]);
+        }
+        s->mu[p] = c.mu;
+        s->lam[p] = c.lambda;
+    }
+}
+
+void implicit_ref_get_state(void* h, double* X, double* V, double* C, double* F, double* Jp, double* mu, double* lam)
+{
+    MockSim* s = (MockSim*)h;
+    std::vector<double> G(9 * (size_t)s->count);
+    mpmgrid_ref_get_particles(s, X, V, C, G.data());
+    implicit_ref_get_F(h, F);
+    for (int i = 0; i < s->count; ++i) { Jp[i] = s->Jp[i]; mu[i] = s->mu[i]; lam[i] = s->lam[i]; }
+}
+
+void implicit_ref_get_id2coord(void* h, int* coord)
+{
+    MockSim* s = (MockSim*)h;
+    s->grid.iterateGrid([&](IV node, GridState<T, dim>& g) {
+        for (int d = 0; d < 3; ++d) coord[3 * g.idx + d] = node(d);
+    });
 }
 
 } // extern "C"

@@ -6,6 +6,7 @@
 #pragma once
 #include <string>
 #include <tuple>
+#include <vector>
 #include <Ziran/CS/DataStructure/DisjointRanges.h>
 namespace ZIRAN {
 template <class Type>
@@ -24,6 +25,11 @@ struct SubsetIterStandIn {
 };
 class DataManager {
 public:
+    // the two scalar attributes Projects/multigrid/ImplicitSolver.h reads through particles.DataManager::get(AttributeName<T>(..)) ("element measure" :500,618
+    // and "m" :676), served from the arrays of the stand-in simulation of oracle/implicit_ref_shim.cpp
+    std::vector<double>* measure = nullptr;
+    std::vector<double>* m = nullptr;
+    std::vector<double>& get(const AttributeName<double>& a) { return a.name == "m" ? *m : *measure; }
     template <class Type>
     bool exist(const AttributeName<Type>&) const { return false; }
     template <class... Types>

@@ -167,6 +167,25 @@ class Reference:
                                                   _p(dv), _p(out))
         return dict(iterations=int(out[0]), converged=int(out[1]), tolerance=float(out[2]), dv=dv)
 
+    def begin_step(self):
+        self.num_nodes = int(self.lib.implicit_ref_begin_step(self.h))
+        return self.num_nodes
+
+    def get_id2coord(self):
+        out = np.empty((self.num_nodes, 3), dtype=np.int32); self.lib.implicit_ref_get_id2coord(self.h, _p(out)); return out
+
+    def end_step(self, dt, plastic_model=0, params=()):
+        q = np.ascontiguousarray(list(params) + [0.0] * (5 - len(params)), dtype=np.float64)
+        flags = (C.c_int * 2)(0, 0)
+        self.lib.implicit_ref_end_step(self.h, C.c_double(dt), int(plastic_model), _p(q), flags)
+        return (flags[0], flags[1])
+
+    def get_state(self):
+        n = self.N
+        out = dict(X=np.empty((n, 3)), V=np.empty((n, 3)), C=np.empty((n, 9)), F=np.empty((n, 9)), Jp=np.empty(n), mu=np.empty(n), lam=np.empty(n))
+        self.lib.implicit_ref_get_state(self.h, *[_p(out[k]) for k in ("X", "V", "C", "F", "Jp", "mu", "lam")])
+        return out
+
     def shouldExitByCN(self, r, useCN, cneps):
         r = np.ascontiguousarray(r, dtype=np.float64)
         return int(self.lib.implicit_ref_should_exit_by_cn(self.h, _p(r), int(useCN), C.c_double(cneps)))
@@ -212,6 +231,72 @@ def reference_step(sc, bc, dv0, dt, opts):
                                  adaptive_h=opts.get("adaptive_h", 0), matfree=opts.get("matfree", 0), bcproject=opts.get("bcproject", 1), max_linear_iterations=opts.get("max_cg_iterations", 10000), mg_times=opts.get("mg_times", 1), mg_scale=opts.get("mg_scale", 0),
                                  topomega=opts.get("topomega", 0.1),
                                  max_iterations=opts.get("max_lbfgs_iterations", 10000) if lsolver == 3 else opts.get("max_newton_iterations", 3))
+
+
+# whole time steps (MultigridSimulation::advanceOneTimeStep, MultigridSimulation.h:235-297): sort, P2G, implicit solve, G2P, evolveStrain, plasticity
+RUNS = {
+    "elastic_hot": (dict(cells=(5, 6, 5), E=2e5, dt=4e-3, seed=3), dict(HOT), ("none", [])),
+    "snow_hot": (dict(cells=(5, 6, 5), E=2e5, dt=4e-3, seed=4), dict(HOT), ("snow", [10.0, 2e-2, 7.5e-3, 0.6, 20.0])),      # hardening: mu / lambda change every step
+    "von_mises_pn_mgpcg": (dict(cells=(5, 6, 5), E=2e5, dt=4e-3, seed=5), dict(HOT, lsolver=2, max_newton_iterations=10), ("von_mises", [300.0])),
+}
+RUN_STEPS = 3
+PLASTIC_CODE = {"none": 0, "von_mises": 1, "snow": 2}
+
+
+def floor_bc(coord):
+    return np.nonzero(coord[:, 1] <= coord[:, 1].min() + 1)[0].astype(np.int32)
+
+
+def run_scene(cells, E, dt, seed):
+    from hot_b200 import scenes
+    sc = scenes.block(cells, 1.0 / 32, ppc=6, seed=seed, E=E)
+    sc["F"] = sc["F"] + 0.05 * (np.random.default_rng(seed).random(sc["F"].shape) - 0.5)
+    sc["V"] = sc["V"] + np.array([0.0, -1.5, 0.0])                 # the block is pushed into its sticky floor
+    return sc
+
+
+def run_sim(make_sim, sc_args, opts, plastic, steps=RUN_STEPS):
+    """`steps` whole time steps through the interface the oracle and the CUDA object share; the state after every step"""
+    sc = run_scene(**sc_args)
+    dt = sc_args["dt"]
+    s = make_sim(sc["dx"])
+    s.set_particles(sc["X"], sc["V"], sc["mass"], sc["C"], sc["F"], sc["vol"], sc["mu"], sc["lam"])
+    s.set_dt_gravity(dt, GRAVITY)
+    s.set_plasticity(*plastic)
+    states, logs = [], []
+    for _ in range(steps):
+        s.sortParticlesAndPolluteGrid(); s.particlesToGrid()
+        bc = floor_bc(s.get_id2coord())
+        s.set_bc(bc, P=np.zeros((len(bc), 9)), dv_bc=np.zeros((len(bc), 3)))
+        logs.append(s.backwardEulerStep(**opts))
+        s.gridToParticles(dt)
+        p = s.get_particles()
+        Jp, mu, lam = s.get_plastic_state()
+        states.append(dict(X=p["X"], V=p["V"], C=p["C"], F=p["F"], Jp=Jp, mu=mu, lam=lam))
+    return states, [l["iterations"] for l in logs]
+
+
+def run_reference(sc_args, opts, plastic, steps=RUN_STEPS):
+    """the same time steps in the reference's code (oracle/implicit_ref_shim.cpp): one create() = one process, state carried inside"""
+    sc = run_scene(**sc_args)
+    dt = sc_args["dt"]
+    ref = Reference(sc["dx"], dt)
+    ref.setup({k: sc[k] for k in ("X", "V", "mass", "C", "F", "vol", "mu", "lam")}, opts.get("project", 1))
+    states, its = [], []
+    lsolver = opts.get("lsolver", 3)
+    for k in range(steps):
+        n = ref.num_nodes if k == 0 else ref.begin_step()
+        bc = floor_bc(ref.get_id2coord())
+        ref.set_bc(0, bc, np.zeros((len(bc), 9)), None, None, np.zeros(len(bc), dtype=np.int32))
+        dv0 = np.tile(dt * np.asarray(GRAVITY), (n, 1)); dv0[bc] = 0.0      # buildInitialDvAndVnForNewton with a sticky floor at rest
+        ref.set_dv(dv0)
+        r = ref.backwardEulerStep(lsolver=lsolver, mg_level=opts.get("mg_level", 3), smoother=opts.get("smoother", 5), coarse_solver=opts.get("coarse_solver", 2),
+                                  linesearch=opts.get("linesearch", 1), usecn=opts.get("usecn", 1), cneps=opts.get("cneps", 1e-7),
+                                  max_iterations=opts.get("max_lbfgs_iterations", 10000) if lsolver == 3 else opts.get("max_newton_iterations", 3))
+        its.append(r["iterations"])
+        ref.end_step(dt, PLASTIC_CODE[plastic[0]], plastic[1])
+        states.append(ref.get_state())
+    return states, its
 
 
 def vectors(n, seed):
@@ -272,5 +357,14 @@ if __name__ == "__main__":
         gold[f"step/{name}/iterations"] = np.int64(r["iterations"]); gold[f"step/{name}/converged"] = np.int64(r["converged"])
         gold[f"step/{name}/tolerance"] = np.float64(r["tolerance"]); gold[f"step/{name}/dv"] = r["dv"]
         print("step", name, "iterations", r["iterations"], "converged", r["converged"], "tolerance", r["tolerance"])
+    for name, (sc_args, opts, plastic) in RUNS.items():
+        states, its = run_reference(sc_args, opts, plastic)
+        gold[f"run/{name}/iterations"] = np.array(its, dtype=np.int64)
+        for k, st in enumerate(states):
+            for key, v in st.items():
+                if k == len(states) - 1 or key in ("Jp", "mu"):           # full state after the last step, the plastic history after every step
+                    gold[f"run/{name}/{k}/{key}"] = v
+        print("run", name, "iterations per step", its, "Jp range", states[-1]["Jp"].min(), states[-1]["Jp"].max(),
+              "mu range", states[-1]["mu"].min() / states[0]["mu"].max())
     np.savez_compressed(OUT, **gold)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

@@ -118,6 +118,27 @@ def test_whole_solve_golden_agrees_with_the_lbfgs_golden():
         assert np.abs(L[name + "_dv"] - G[f"step/{name}/dv"]).max() <= 1e-9 * np.abs(L[name + "_dv"]).max()
 
 
+def _check_run(make_sim, name, rtol):
+    """three whole time steps (sort, P2G, implicit solve, G2P, evolveStrain, return mapping) with the state carried through the re-sorts: the same
+    nonlinear iterations in every step, the same particle state at the end, the same plastic history after every step"""
+    sc_args, opts, plastic = gen.RUNS[name]
+    states, its = gen.run_sim(make_sim, sc_args, opts, plastic)
+    assert its == [int(x) for x in G[f"run/{name}/iterations"]], (name, its)
+    for k, st in enumerate(states):
+        for key, v in st.items():
+            gk = f"run/{name}/{k}/{key}"
+            if gk in G.files:
+                ref = G[gk]
+                assert np.abs(v - ref).max() <= rtol * max(np.abs(ref).max(), 1e-300), (name, k, key, np.abs(v - ref).max() / np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name", list(gen.RUNS))
+def test_oracle_time_steps_against_reference_code(oracle, name):
+    """MultigridSimulation::advanceOneTimeStep's sequence (MultigridSimulation.h:235-297) in the reference's grid / objective / solver / multigrid /
+    plasticity code against the oracle's, including the first-step cache of the characteristic norm while the snow model hardens"""
+    _check_run(oracle.OracleSim, name, 1e-8)
+
+
 @pytest.mark.skipif(not os.path.exists(gen.REF_LIB), reason="oracle/_ref/libimplicit_ref.so not built (needs /root/reference)")
 def test_reference_objective_reproduces_the_golden_vectors():
     name = "slip"
