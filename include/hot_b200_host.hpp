@@ -107,13 +107,17 @@ struct AnalyticLevelSet {
 };
 inline TV matVec(const TM& M, const TV& x) { return {M[0] * x[0] + M[3] * x[1] + M[6] * x[2], M[1] * x[0] + M[4] * x[1] + M[7] * x[2], M[2] * x[0] + M[5] * x[1] + M[8] * x[2]}; }
 inline TV matTVec(const TM& M, const TV& x) { return {M[0] * x[0] + M[1] * x[1] + M[2] * x[2], M[3] * x[0] + M[4] * x[1] + M[5] * x[2], M[6] * x[0] + M[7] * x[1] + M[8] * x[2]}; }
-// Eigen::Quaternion<T>(w, x, y, z).normalized().toRotationMatrix(), column-major
+// Eigen::Quaternion<T>(w, x, y, z).toRotationMatrix(), column-major, the quaternion taken as it is
+inline TM quaternionToMatrixRaw(double w, double x, double y, double z)
+{
+    return {1 - 2 * (y * y + z * z), 2 * (x * y + w * z), 2 * (x * z - w * y), 2 * (x * y - w * z), 1 - 2 * (x * x + z * z), 2 * (y * z + w * x),
+        2 * (x * z + w * y), 2 * (y * z - w * x), 1 - 2 * (x * x + y * y)};
+}
+// Eigen::Quaternion<T>(w, x, y, z).normalized().toRotationMatrix(): what AnalyticBox / CappedCylinder do with their own q (AnalyticLevelSet.h:340, .cpp:492,574)
 inline TM quaternionToMatrix(double w, double x, double y, double z)
 {
     const double l = std::sqrt(w * w + x * x + y * y + z * z);
-    w /= l; x /= l; y /= l; z /= l;
-    return {1 - 2 * (y * y + z * z), 2 * (x * y + w * z), 2 * (x * z - w * y), 2 * (x * y - w * z), 1 - 2 * (x * x + z * z), 2 * (y * z + w * x),
-        2 * (x * z + w * y), 2 * (y * z - w * x), 1 - 2 * (x * x + y * y)};
+    return quaternionToMatrixRaw(w / l, x / l, y / l, z / l);
 }
 struct HalfSpace : AnalyticLevelSet { // AnalyticLevelSet.cpp:259-304
     TV origin, outward_normal;
@@ -192,7 +196,10 @@ struct CappedCylinder : AnalyticLevelSet {
     double radius, height;
     TV b;
     TM R;
-    CappedCylinder(double r, double h, const std::array<double, 4>& q, const TV& b_in) : radius(r), height(h), b(b_in), R(quaternionToMatrix(q[0], q[1], q[2], q[3])) {}
+    // the reference normalises q = <w,x,y,z> as a 4-vector and hands THAT VECTOR to Eigen::Quaternion (AnalyticLevelSet.h:248-251), whose vector constructor
+    // reads coefficients in storage order (x, y, z, w): the rotation actually used is the one of the quaternion <w = q[3], x = q[0], y = q[1], z = q[2]>
+    // (for q = <1,0,0,0> a half turn about x, which maps the y-axis cylinder onto itself).  Replicated (tests/test_collider_ref.py).
+    CappedCylinder(double r, double h, const std::array<double, 4>& q, const TV& b_in) : radius(r), height(h), b(b_in), R(quaternionToMatrix(q[3], q[0], q[1], q[2])) {}
     bool query(const TV& X, double& phi, TV& n) const override
     {
         const TV Xp = matTVec(R, sub(X, b));
@@ -229,7 +236,7 @@ struct AnalyticCollisionObject {
     TV b{0, 0, 0}, dbdt{0, 0, 0}, omega{0, 0, 0};
     std::function<void(double, AnalyticCollisionObject&)> updateState; // collision_objects[k]->updateState(t + dt), MultigridSimulation.h:292-295
     AnalyticCollisionObject(std::shared_ptr<AnalyticLevelSet> l, COLLISION_OBJECT_TYPE t) : ls(std::move(l)), type(t) {}
-    void setRotation(const std::array<double, 4>& q) { R = quaternionToMatrix(q[0], q[1], q[2], q[3]); } // <w, x, y, z>
+    void setRotation(const std::array<double, 4>& q) { R = quaternionToMatrixRaw(q[0], q[1], q[2], q[3]); } // <w, x, y, z>, NOT normalised: Rotation(q), Rotation.h:51-56
     void setAngularVelocity(const TV& w) { omega = w; }
     void setTranslation(const TV& b_in, const TV& dbdt_in) { b = b_in; dbdt = dbdt_in; }
 
@@ -333,6 +340,29 @@ struct CollisionNode { // CollisionObject.h:16-45
     bool shouldRotate;
 };
 
+// the per-node body of buildInitialDvAndVnForNewton (MpmSimulationBase.cpp:1145-1176): collision test of the node at xi moving with old_v against
+// all objects; on a collision fills Z = {node_id, P = I - K K^T, R, R^-1, shouldRotate} and dv_bc = v_after - old_v and returns true
+inline bool collisionNodeAt(const std::vector<AnalyticCollisionObject>& objects, const TV& xi, const TV& old_v, int node_id, CollisionNode& Z, TV& dv_bc)
+{
+    TV vi = old_v, wn{0, 0, 0};
+    TM nb;
+    if (!multiObjectCollision(objects, xi, vi, nb, wn)) return false;
+    const bool isSlip = wn[0] != 0 || wn[1] != 0 || wn[2] != 0;
+    Z.node_id = node_id;
+    Z.shouldRotate = isSlip;
+    Z.R = isSlip ? rotateToX(wn) : identity();
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) Z.Rinv[r + 3 * c] = Z.R[c + 3 * r]; // rotation: inverse = transpose
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            double kk = 0;
+            for (int k = 0; k < 3; ++k) kk += nb[r + 3 * k] * nb[c + 3 * k];
+            Z.P[r + 3 * c] = (r == c ? 1.0 : 0.0) - kk;
+        }
+    for (int d = 0; d < 3; ++d) dv_bc[d] = vi[d] - old_v[d];
+    return true;
+}
+
 // ---- MpmSimulationBase surface -----------------------------------------------------------------------------------------------
 class MpmSimulationB200 {
 public:
@@ -435,29 +465,16 @@ public:
         for (int i = 0; i < num_nodes; ++i) {
             const TV xi{coord[3 * i] * dx, coord[3 * i + 1] * dx, coord[3 * i + 2] * dx};
             const TV old_v{vn[3 * i], vn[3 * i + 1], vn[3 * i + 2]};
-            TV vi = old_v, wn{0, 0, 0};
-            TM nb;
-            if (!multiObjectCollision(collision_objects, xi, vi, nb, wn)) continue;
-            const bool isSlip = wn[0] != 0 || wn[1] != 0 || wn[2] != 0;
             CollisionNode Z;
-            Z.node_id = i;
-            Z.shouldRotate = isSlip;
-            Z.R = isSlip ? rotateToX(wn) : identity();
-            for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 3; ++c) Z.Rinv[r + 3 * c] = Z.R[c + 3 * r]; // rotation: inverse = transpose
-            for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 3; ++c) {
-                    double kk = 0;
-                    for (int k = 0; k < 3; ++k) kk += nb[r + 3 * k] * nb[c + 3 * k];
-                    Z.P[r + 3 * c] = (r == c ? 1.0 : 0.0) - kk;
-                }
+            TV dvi;
+            if (!collisionNodeAt(collision_objects, xi, old_v, i, Z, dvi)) continue;
             collision_nodes.push_back(Z);
             node_id.push_back(i);
-            slip.push_back(isSlip);
+            slip.push_back(Z.shouldRotate);
             P.insert(P.end(), Z.P.begin(), Z.P.end());
             R.insert(R.end(), Z.R.begin(), Z.R.end());
             Rinv.insert(Rinv.end(), Z.Rinv.begin(), Z.Rinv.end());
-            for (int d = 0; d < 3; ++d) dv_bc.push_back(vi[d] - old_v[d]);
+            for (int d = 0; d < 3; ++d) dv_bc.push_back(dvi[d]);
         }
         const int mode = (HOTSettings::systemBCProject && HOTSettings::boundaryType == 1) ? 1 : 0; // MultigridSimulation.h:104-125
         check(hot_set_dt_gravity(h, dt, gravity.data()));

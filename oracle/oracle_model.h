@@ -13,10 +13,10 @@
 //   objective: state update, energy, residual, Hessian apply, CN tolerance, buildMatrix (+ BC projection), buildDiagonal, and whole
 //   implicit solves (Newton + PCG / MGPCG, HOT)                     ImplicitSolver.h, ExtendedNewtonsMethod.h, LBFGS.h, ...   libimplicit_ref.so
 //   snow / von Mises return mappings                                PlasticityApplier.cpp                       libplasticity_ref.so
+//   collision objects, buildInitialDvAndVnForNewton (host mirror)   AnalyticLevelSet.cpp, CollisionObject.cpp   libcollider_ref.so
 // The member functions of MpmSimulationBase / MpmForceBase / FBasedMpmForceHelper themselves cannot be compiled here (Scene / DataManager /
 // Particles / TBB containers / Partio absent): their particle loops are written out in the shims around the reference's grid, model and
-// objective code (each shim's header lists exactly which lines).  Still "parity unpinned" by reference code: collision objects /
-// buildInitialDvAndVnForNewton (a8, AnalyticLevelSet.cpp needs OpenVDB), Chebyshev's seeded 2-norm estimate,
+// objective code (each shim's header lists exactly which lines).  Still "parity unpinned" by reference code: Chebyshev's seeded 2-norm estimate,
 // and the extensions (Drucker-Prager, neo-Hookean) - those rest on the reference's in-code invariants and numpy / scipy checks.
 //
 // Section 1: SPGrid addressing restated from Lib/SPGrid/Core/SPGrid_Mask.h:22-52,59-128,150-189,237-245.

@@ -45,6 +45,8 @@ class VectorBlock; // declared only
 template <class M, int Q = 0>
 class JacobiSVD; // declared only
 
+template <class T, int R, int C>
+struct FixedArray;
 template <class D>
 struct traits;
 template <class T, int R, int C, int O, int MR, int MC>
@@ -188,7 +190,7 @@ public:
             for (int i = 0; i < rows(); ++i) s += (*this)(i, j) * (*this)(i, j);
         return s;
     }
-    Scalar norm() const { return std::sqrt(squaredNorm()); }
+    Scalar norm() const { using std::sqrt; return sqrt(squaredNorm()); }
     Scalar sum() const
     {
         Scalar s = 0;
@@ -244,8 +246,14 @@ public:
     // the first column, one multiplication by 1 / det per entry
     PlainObject inverse() const
     {
-        static_assert(RowsAtCompileTime == 3 && ColsAtCompileTime == 3, "mini_eigen: inverse() is implemented for 3 x 3 only");
+        static_assert((RowsAtCompileTime == 3 && ColsAtCompileTime == 3) || (RowsAtCompileTime == 2 && ColsAtCompileTime == 2), "mini_eigen: inverse() is implemented for 2 x 2 and 3 x 3 only");
         const MatrixBase& m = *this;
+        if (RowsAtCompileTime == 2) { // Eigen/src/LU/InverseImpl.h, compute_inverse<.., 2>: adjugate times 1 / det
+            const Scalar invdet2 = Scalar(1) / (m(0, 0) * m(1, 1) - m(1, 0) * m(0, 1));
+            PlainObject r2;
+            r2(0, 0) = m(1, 1) * invdet2; r2(1, 0) = -m(1, 0) * invdet2; r2(0, 1) = -m(0, 1) * invdet2; r2(1, 1) = m(0, 0) * invdet2;
+            return r2;
+        }
         auto cof = [&m](int i, int j) {
             const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
             return m(i1, j1) * m(i2, j2) - m(i1, j2) * m(i2, j1);
@@ -268,6 +276,28 @@ public:
         return r;
     }
     static PlainObject Zero() { PlainObject r; r.setZero(); return r; }
+    static PlainObject Zero(int, int) { return Zero(); }
+    template <class O> void resizeLike(const O&) {}
+    PlainObject normalized() const { PlainObject r = eval(); const Scalar n = norm(); if (n > Scalar(0)) { for (int k = 0; k < size(); ++k) r(k) = r(k) / n; } return r; }
+    void normalize() { derived() = normalized(); }
+    template <class O>
+    PlainObject cross(const MatrixBase<O>& o) const
+    {
+        static_assert(RowsAtCompileTime * ColsAtCompileTime == 3, "cross: 3-vectors");
+        PlainObject r;
+        const MatrixBase& a = *this;
+        r(0) = a(1) * o(2) - a(2) * o(1); r(1) = a(2) * o(0) - a(0) * o(2); r(2) = a(0) * o(1) - a(1) * o(0);
+        return r;
+    }
+    template <int BR, int BC> Block<Derived, BR, BC> topLeftCorner() const { return block<BR, BC>(0, 0); }
+    void transposeInPlace() { const PlainObject t = eval(); for (int j = 0; j < cols(); ++j) for (int i = 0; i < rows(); ++i) (*this)(i, j) = t(j, i); }
+    template <class O>
+    bool operator!=(const MatrixBase<O>& o) const { for (int j = 0; j < cols(); ++j) for (int i = 0; i < rows(); ++i) if ((*this)(i, j) != o(i, j)) return true; return false; }
+    template <int N> Block<Derived, N, 1> head() const { return Block<Derived, N, 1>(const_cast<Derived&>(derived()), 0, 0); }
+    FixedArray<Scalar, RowsAtCompileTime, ColsAtCompileTime> array() const;
+    template <int BR, int BC> Block<Derived, BR, BC> topRightCorner() const { return block<BR, BC>(0, ColsAtCompileTime - BC); }
+    Scalar maxCoeff() const { Scalar m = (*this)(0); for (int k = 1; k < size(); ++k) if ((*this)(k) > m) m = (*this)(k); return m; }
+    Scalar minCoeff() const { Scalar m = (*this)(0); for (int k = 1; k < size(); ++k) if ((*this)(k) < m) m = (*this)(k); return m; }
     static PlainObject Identity() { PlainObject r; r.setIdentity(); return r; }
     static PlainObject Constant(const Scalar& v) { PlainObject r; r.setConstant(v); return r; }
     static PlainObject Ones() { return Constant(Scalar(1)); }
@@ -319,6 +349,41 @@ public:
     T* data() { return m_; }
     const T* data() const { return m_; }
 };
+
+// coefficient-wise view of a fixed-size matrix: what the reference's geometry code uses of Eigen's Array (comparisons + any / all, min / max, abs,
+// maxCoeff, difference); converts back to a Matrix
+template <class T, int R, int C>
+struct FixedArray {
+    Matrix<T, R, C> m;
+    struct Mask {
+        bool b[(R > 0 ? R : 1) * (C > 0 ? C : 1)];
+        bool any() const { for (int k = 0; k < R * C; ++k) if (b[k]) return true; return false; }
+        bool all() const { for (int k = 0; k < R * C; ++k) if (!b[k]) return false; return true; }
+    };
+    Mask operator<(const FixedArray& o) const { Mask r; for (int k = 0; k < R * C; ++k) r.b[k] = m(k) < o.m(k); return r; }
+    Mask operator>(const FixedArray& o) const { Mask r; for (int k = 0; k < R * C; ++k) r.b[k] = m(k) > o.m(k); return r; }
+    Mask operator<=(const FixedArray& o) const { Mask r; for (int k = 0; k < R * C; ++k) r.b[k] = m(k) <= o.m(k); return r; }
+    Mask operator>=(const FixedArray& o) const { Mask r; for (int k = 0; k < R * C; ++k) r.b[k] = m(k) >= o.m(k); return r; }
+    FixedArray min(const FixedArray& o) const { FixedArray r; for (int k = 0; k < R * C; ++k) r.m(k) = o.m(k) < m(k) ? o.m(k) : m(k); return r; }
+    FixedArray max(const FixedArray& o) const { FixedArray r; for (int k = 0; k < R * C; ++k) r.m(k) = m(k) < o.m(k) ? o.m(k) : m(k); return r; }
+    FixedArray abs() const { using std::abs; FixedArray r; for (int k = 0; k < R * C; ++k) r.m(k) = abs(m(k)); return r; }
+    FixedArray operator-(const FixedArray& o) const { FixedArray r; for (int k = 0; k < R * C; ++k) r.m(k) = m(k) - o.m(k); return r; }
+    FixedArray operator+(const FixedArray& o) const { FixedArray r; for (int k = 0; k < R * C; ++k) r.m(k) = m(k) + o.m(k); return r; }
+    FixedArray operator*(const FixedArray& o) const { FixedArray r; for (int k = 0; k < R * C; ++k) r.m(k) = m(k) * o.m(k); return r; }
+    FixedArray operator/(const FixedArray& o) const { FixedArray r; for (int k = 0; k < R * C; ++k) r.m(k) = m(k) / o.m(k); return r; }
+    T maxCoeff() const { return m.maxCoeff(); }
+    T minCoeff() const { return m.minCoeff(); }
+    T sum() const { return m.sum(); }
+    operator Matrix<T, R, C>() const { return m; }
+    Matrix<T, R, C> matrix() const { return m; }
+};
+template <class Derived>
+FixedArray<typename MatrixBase<Derived>::Scalar, MatrixBase<Derived>::RowsAtCompileTime, MatrixBase<Derived>::ColsAtCompileTime> MatrixBase<Derived>::array() const
+{
+    FixedArray<Scalar, RowsAtCompileTime, ColsAtCompileTime> a;
+    a.m = eval();
+    return a;
+}
 
 template <class X, int BR, int BC>
 class Block : public MatrixBase<Block<X, BR, BC>> {
@@ -509,3 +574,4 @@ typedef Matrix<float, 3, 1> Vector3f;
 
 } // namespace Eigen
 #include "mini_eigen_dyn.h"
+#include "mini_eigen_geom.h"
