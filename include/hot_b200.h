@@ -205,7 +205,10 @@ typedef struct hot_collider {
     double friction;
     double p[8];        /* HalfSpace: origin[3], outward_normal[3] | Sphere: center[3], radius | AnalyticBox: half_edges[3] |
                            CappedCylinder (axis y): radius, height */
-    double shape_R[9];  /* AnalyticBox / CappedCylinder own rigid transform: X_primitive = shape_R^-1 (X - shape_b) */
+    double shape_R[9];  /* AnalyticBox / CappedCylinder own rigid transform: X_primitive = shape_R^-1 (X - shape_b).  From the reference's constructor
+                           argument q = <w,x,y,z>: AnalyticBox rotates by q normalised; CappedCylinder by the quaternion <w = q[3], x = q[0], y = q[1],
+                           z = q[2]> normalised (its 4-vector reaches Eigen::Quaternion in storage order, AnalyticLevelSet.h:248-251) - hot_b200_host.hpp
+                           builds both that way */
     double shape_b[3];
     double R[9], s, b[3];            /* object transform */
     double omega[3], dsdt, dbdt[3];  /* and its rates */
