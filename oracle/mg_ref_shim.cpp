@@ -9,6 +9,8 @@
 #include <array>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
+#include <cstdlib>
 #include <functional>
 #include <memory>
 #include <unordered_map>
@@ -123,6 +125,31 @@ int zr_mg_color_order(int level, int* out3)
 int zr_mg_two_norm(int level, double* lmax, double* lmin)
 {
     *lmax = g_mgp.sysmats[level]->_mat->lMax; *lmin = g_mgp.sysmats[level]->_mat->lMin;
+    return 0;
+}
+// SquareMatrix::estimate2norm (SquareMatrix.h:375-475) as the reference runs it: its start vector is seeded with srand(time(NULL)).  The call is
+// bracketed by time() reads (repeated if the second changed in between), so the seed is known afterwards and the +-1 start vector is regenerated with
+// the same rand() sequence (SquareMatrix.h:404-417: columns outer, components inner, (rand() & 7) >= 4 ? 1 : -1) and handed back.
+int zr_mg_estimate_two_norm(int level, double* start, double* lmax, double* lmin)
+{
+    auto& m = *g_mgp.sysmats[level]->_mat;
+    for (int attempt = 0; attempt < 100; ++attempt) {
+        const time_t t0 = time(NULL);
+        m.estimate2norm();
+        if (time(NULL) != t0) continue;
+        srand(t0);
+        const int n = g_mgp.dofs[level];
+        for (int i = 0; i < n; ++i)
+            for (int d = 0; d < dim; ++d) start[3 * i + d] = (rand() & 0x7) >= 4 ? 1.0 : -1.0;
+        *lmax = m.lMax; *lmin = m.lMin;
+        return 0;
+    }
+    return 1;
+}
+// lMax / lMin of a level set from outside (the Chebyshev smoother reads them)
+int zr_mg_set_two_norm(int level, double lmax, double lmin)
+{
+    g_mgp.sysmats[level]->_mat->lMax = lmax; g_mgp.sysmats[level]->_mat->lMin = lmin;
     return 0;
 }
 // SparseMPMMatrix::multiply of the level's system matrix

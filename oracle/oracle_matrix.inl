@@ -296,12 +296,12 @@ void chebyshev_smooth(Sim* s, MatrixState& M, int level, Vd& u, Vd& r, Vd& du, V
 // SquareMatrix::estimate2norm (SquareMatrix.h:375-475): power iteration on A A from a +-1 start vector.  The reference seeds the
 // start with srand(time(NULL)); any start converges to the same 2-norm within `tol`, here a fixed hash of the entry index.
 inline double sign_pattern(size_t t) { return ((uint32_t)(t * 2654435761u) >> 16) & 1u ? 1.0 : -1.0; }
-void estimate2norm(SqMat& A, double tol = 1e-6)
+void estimate2norm(SqMat& A, double tol = 1e-6, const double* start = nullptr /* the +-1 start vector (tests hand over the reference's own) */)
 {
     const int MaxIters = 512;
     const size_t m = 3 * (size_t)A.rows();
     Vd v(m), x(m);
-    for (size_t t = 0; t < m; ++t) v[t] = sign_pattern(t);
+    for (size_t t = 0; t < m; ++t) v[t] = start ? start[t] : sign_pattern(t);
     sq_multiply(A, v.data(), x.data());
     for (auto& a : x) a = std::fabs(a);
     double e = std::sqrt(vec_dot(x, x));
@@ -726,6 +726,15 @@ int orc_estimate_2norm(void* h, int level, double* lmax_lmin)
     MatrixState& M = matrix_of((Sim*)h);
     if (level < 0 || level >= (int)M.sysmats.size()) return -1;
     estimate2norm(M.sysmats[level]);
+    lmax_lmin[0] = M.sysmats[level].lMax; lmax_lmin[1] = M.sysmats[level].lMin;
+    return 0;
+}
+// the same from a given start vector (3 x dofs of the level): what tests/test_oracle_mg_ref.py uses to follow the reference's own seeded start
+int orc_estimate_2norm_from(void* h, int level, const double* start, double* lmax_lmin)
+{
+    MatrixState& M = matrix_of((Sim*)h);
+    if (level < 0 || level >= (int)M.sysmats.size()) return -1;
+    estimate2norm(M.sysmats[level], 1e-6, start);
     lmax_lmin[0] = M.sysmats[level].lMax; lmax_lmin[1] = M.sysmats[level].lMin;
     return 0;
 }

@@ -7,7 +7,7 @@
 //   SPGrid addressing (this header, section 1)                      SPGrid core                                 libspgrid_ref.so
 //   B-spline weights, QR-SVD, makePD, fixed-corotated psi / P / dP  BSplines.h, ImplicitQRSVD.h, CorotatedIsotropic.h ...   libziran_ref.so
 //   inexact PCG, MINRES                                             InexactConjugateGradient.h, Minres.h        libziran_ref.so
-//   Galerkin hierarchy, colouring, smoothers, V-cycle               MultigridPreconditioner.h, SquareMatrix.h   libziran_ref.so
+//   Galerkin hierarchy, colouring, smoothers (incl. Chebyshev + estimate2norm), V-cycle   MultigridPreconditioner.h, SquareMatrix.h   libziran_ref.so
 //   L-BFGS loop                                                     LBFGS.h                                     libhot_oracle_lbfgsref.so
 //   node record, sort + page activation, P2G, DOF numbering, G2P    MpmGrid.h over SPGrid_Page_Map              libmpmgrid_ref.so
 //   objective: state update, energy, residual, Hessian apply, CN tolerance, buildMatrix (+ BC projection), buildDiagonal, and whole
@@ -16,7 +16,7 @@
 //   collision objects, buildInitialDvAndVnForNewton (host mirror)   AnalyticLevelSet.cpp, CollisionObject.cpp   libcollider_ref.so
 // The member functions of MpmSimulationBase / MpmForceBase / FBasedMpmForceHelper themselves cannot be compiled here (Scene / DataManager /
 // Particles / TBB containers / Partio absent): their particle loops are written out in the shims around the reference's grid, model and
-// objective code (each shim's header lists exactly which lines).  Still "parity unpinned" by reference code: Chebyshev's seeded 2-norm estimate,
+// objective code (each shim's header lists exactly which lines).  Still "parity unpinned" by reference code: the restart-file layout
 // and the extensions (Drucker-Prager, neo-Hookean) - those rest on the reference's in-code invariants and numpy / scipy checks.
 //
 // Section 1: SPGrid addressing restated from Lib/SPGrid/Core/SPGrid_Mask.h:22-52,59-128,150-189,237-245.

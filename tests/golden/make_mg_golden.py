@@ -105,6 +105,13 @@ class Reference:
         self.lib.zr_mg_vcycle(_d(r), _d(out))
         return out
 
+    def estimate2norm(self, level):
+        """SquareMatrix::estimate2norm as the reference runs it (clock-seeded start): returns the start vector it used, lMax, lMin"""
+        start = np.empty((self.dofs[level], 3)); lmax = C.c_double(0); lmin = C.c_double(0)
+        rc = self.lib.zr_mg_estimate_two_norm(level, _d(start), C.byref(lmax), C.byref(lmin))
+        assert rc == 0
+        return start, lmax.value, lmin.value
+
 
 def main():
     import oracle_binding as orc
@@ -134,5 +141,31 @@ def main():
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "mg_ref.npz"), **out)
 
 
+CHEB_OUT = os.path.join(ROOT, "tests", "golden", "cheb_ref.npz")
+CHEB_ITERS = 4
+
+
+def main_chebyshev():
+    """tests/golden/cheb_ref.npz (f4: -smoother 6): the reference's estimate2norm with the start vector it drew (its seed is the clock: the vector is
+    recovered after the call, oracle/mg_ref_shim.cpp), chebyshev_smooth on every level and the V-cycle of the Chebyshev hierarchy"""
+    import oracle_binding as orc
+    o = scene(orc.OracleSim)
+    ref = Reference()
+    ref.build(o, 6, 2, 1)              # (the build estimates the norms once itself; the calls below redo it and keep the start vectors)
+    out = {"dofs": np.asarray(ref.dofs, dtype=np.int64)}
+    for l in range(LEVELS):
+        start, lmax, lmin = ref.estimate2norm(l)
+        out[f"start{l}"] = start.astype(np.int8); out[f"lmax{l}"] = np.float64(lmax); out[f"lmin{l}"] = np.float64(lmin)
+        x, u0 = vectors(ref.dofs[l], 10 + l)
+        out[f"cheb_l{l}_u"], out[f"cheb_l{l}_r"] = ref.smooth(l, 6, u0, x, CHEB_ITERS)
+        print("level", l, "dofs", ref.dofs[l], "lMax", lmax, "lMin", lmin)
+    b, _ = vectors(ref.dofs[0], 1)
+    out["vcycle"] = ref.vcycle(b)
+    np.savez_compressed(CHEB_OUT, **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "chebyshev":
+        main_chebyshev()
+    else:
+        main()

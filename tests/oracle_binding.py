@@ -284,6 +284,13 @@ def _add_matrix_methods(cls):
         self._check(_lib.orc_estimate_2norm(_vp(self._h), level, out))
         return float(out[0]), float(out[1])
 
+    def estimate2norm_from(self, level, start):
+        """the power iteration of estimate2norm from a given +-1 start vector; leaves lMax / lMin of the level set (the Chebyshev smoother reads them)"""
+        start = np.ascontiguousarray(start, dtype=np.float64)
+        out = (C.c_double * 2)()
+        self._check(_lib.orc_estimate_2norm_from(_vp(self._h), level, _p(start), out))
+        return float(out[0]), float(out[1])
+
     def level_dofs(self):
         L = _lib.orc_mg_levels(_vp(self._h))
         out = (C.c_int * L)()

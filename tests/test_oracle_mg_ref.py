@@ -76,6 +76,29 @@ def test_reference_multigrid_reproduces_the_golden_vectors(oracle):
     _close(ref.smooth(1, 5, u0, x, 2)[0], G["smooth5_l1_u"], 1e-13)
 
 
+def test_oracle_chebyshev_against_reference_code(oracle):
+    """f4, -smoother 6: SquareMatrix::estimate2norm (SquareMatrix.h:375-475) and chebyshev_smooth (MultigridPreconditioner.h:227-264) of the reference.
+    The reference seeds the start vector of the power iteration from the clock; cheb_ref.npz keeps the vector it drew (recovered after the call), and the
+    oracle's iteration started from the same vector must land on the same lMax / lMin; with them the Chebyshev sweeps and the V-cycle must agree."""
+    Cb = np.load(os.path.join(ROOT, "tests", "golden", "cheb_ref.npz"))
+    o = gen.scene(oracle.OracleSim)
+    o.buildMultigrid(levels=L, smoother=6, coarseSolver=2, Ainv=1, times=1)
+    dofs = o.level_dofs()
+    assert list(dofs) == [int(x) for x in Cb["dofs"]]
+    for l in range(L):
+        lmax, lmin = o.estimate2norm_from(l, Cb[f"start{l}"].astype(np.float64))
+        assert abs(lmax - float(Cb[f"lmax{l}"])) <= 1e-12 * float(Cb[f"lmax{l}"]) and abs(lmin - float(Cb[f"lmin{l}"])) <= 1e-12 * float(Cb[f"lmin{l}"])
+        lmax_own, _ = o.estimate2norm(l)                       # the oracle's own fixed start vector: the same norm to the iteration's tolerance
+        assert abs(lmax_own - lmax) <= 1e-4 * lmax
+        o.estimate2norm_from(l, Cb[f"start{l}"].astype(np.float64))
+    for l in range(L):
+        x, u0 = gen.vectors(dofs[l], 10 + l)
+        u, r = o.smooth(l, 6, u0, x, gen.CHEB_ITERS)
+        _close(u, Cb[f"cheb_l{l}_u"], 1e-10); _close(r, Cb[f"cheb_l{l}_r"], 1e-10)
+    b, _ = gen.vectors(dofs[0], 1)
+    _close(o.vcycle(b), Cb["vcycle"], 1e-9)
+
+
 @pytest.mark.gpu
 def test_cuda_multigrid_against_reference_code(hot):
     g = gen.scene(hot.MpmSimulationB200)
