@@ -363,6 +363,93 @@ inline bool collisionNodeAt(const std::vector<AnalyticCollisionObject>& objects,
     return true;
 }
 
+// the byte stream of the restart files (layout: see MpmSimulationB200::writeState), host arrays in and out; C (the APIC matrices) may be null on writing
+inline void writeRestart(std::ostream& out, long n, const double* X, const double* V, const double* mass, const double* vol, const double* F,
+    const double* mu, const double* lam, const double* C)
+{
+    auto w = [&](const void* p, size_t bytes) { out.write(reinterpret_cast<const char*>(p), (std::streamsize)bytes); };
+    auto u64 = [&](uint64_t v) { w(&v, 8); };
+    auto i32 = [&](int v) { w(&v, 4); };
+    auto header = [&](const char* name, uint64_t elem_bytes) {
+        const uint64_t len = std::strlen(name);
+        u64(len); w(name, len);
+        i32(7);                                  // DisjointRanges::lg2_grain_size
+        u64(1); u64(8); i32(0); i32((int)n);     // ranges = {[0, n)}
+        u64((uint64_t)n); u64(elem_bytes);
+    };
+    i32((int)n);
+    u64(6);
+    header("X", 24); w(X, (size_t)n * 24);
+    header("V", 24); w(V, (size_t)n * 24);
+    header("m", 8); w(mass, (size_t)n * 8);
+    header("element measure", 8); w(vol, (size_t)n * 8);
+    header("F", 72); w(F, (size_t)n * 72);
+    header("CorotatedIsotropic", 24);
+    // CorotatedIsotropic<T,3> {bool project; T mu, lambda} (CorotatedIsotropic.h:61-62) is trivially copyable and has no RW<> specialisation, so the
+    // reference writes each entry as the 24 raw bytes of the object (BinaryIO.h:41-43,102-108; its write() member is not used): the project flag,
+    // 7 bytes of padding, mu, lambda
+    const unsigned char head[8] = {(unsigned char)(HOTSettings::project ? 1 : 0), 0, 0, 0, 0, 0, 0, 0};
+    for (long i = 0; i < n; ++i) { w(head, 8); w(&mu[i], 8); w(&lam[i], 8); }
+    u64(0); u64(12);                             // trimesh_to_write.indices (Vector<int, 3>)
+    u64(0); u64(8);                              // segmesh_to_write.indices (Vector<int, 2>)
+    if (C) { u64((uint64_t)n); u64(72); w(C, (size_t)n * 72); }
+}
+struct RestartArrays {
+    int n = 0;
+    std::vector<double> X, V, m, vol, F, mu, lam, C;
+};
+inline RestartArrays readRestart(std::istream& in)
+{
+    RestartArrays A;
+    auto r = [&](void* p, size_t bytes) {
+        in.read(reinterpret_cast<char*>(p), (std::streamsize)bytes);
+        if (!in) throw HotError("readState: truncated restart file");
+    };
+    auto u64 = [&]() { uint64_t v; r(&v, 8); return v; };
+    auto i32 = [&]() { int v; r(&v, 4); return v; };
+    const int n = A.n = i32();
+    const uint64_t arrays = u64();
+    for (uint64_t a = 0; a < arrays; ++a) {
+        std::string name(u64(), '\0');
+        r(&name[0], name.size());
+        (void)i32();
+        const uint64_t nr = u64(), rb = u64();
+        if (rb != 8) throw HotError("readState: Range size mismatch");
+        std::vector<int> ranges(2 * nr);
+        r(ranges.data(), nr * 8);
+        const uint64_t size = u64(), bytes = u64();
+        if ((long)size != n) throw HotError("readState: array " + name + " does not cover all particles");
+        auto take = [&](std::vector<double>& dst, uint64_t expect) {
+            if (bytes != expect) throw HotError("Read error: The size of the types don't match (" + name + ")");
+            dst.resize(size * expect / 8);
+            r(dst.data(), size * expect);
+        };
+        if (name == "X") take(A.X, 24);
+        else if (name == "V") take(A.V, 24);
+        else if (name == "m") take(A.m, 8);
+        else if (name == "element measure") take(A.vol, 8);
+        else if (name == "F") take(A.F, 72);
+        else if (name == "CorotatedIsotropic") {
+            if (bytes != 24) throw HotError("Read error: The size of the types don't match (CorotatedIsotropic)");
+            A.mu.resize(size); A.lam.resize(size);
+            unsigned char head[8];
+            for (uint64_t i = 0; i < size; ++i) { r(head, 8); r(&A.mu[i], 8); r(&A.lam[i], 8); } // (project flag + padding first: the flag stays a run-time setting here)
+        }
+        else throw HotError("Array " + name + " was not initialized before reading.");
+    }
+    for (int k = 0; k < 2; ++k) { // mesh index vectors
+        const uint64_t size = u64(), bytes = u64();
+        in.ignore((std::streamsize)(size * bytes));
+    }
+    A.C.assign(9 * (size_t)n, 0.0);
+    if (in.peek() != std::char_traits<char>::eof()) { // trailing APIC matrices (see writeState)
+        const uint64_t size = u64(), bytes = u64();
+        if ((long)size == n && bytes == 72) r(A.C.data(), (size_t)n * 72);
+    }
+    if (A.X.empty() || A.V.empty() || A.m.empty() || A.vol.empty() || A.F.empty() || A.mu.empty()) throw HotError("readState: missing particle arrays");
+    return A;
+}
+
 // ---- MpmSimulationBase surface -----------------------------------------------------------------------------------------------
 class MpmSimulationB200 {
 public:
@@ -516,8 +603,9 @@ public:
     //   mesh index vectors; DataManager::writeData (DataManager.h:263-273) = int count, u64 #arrays, then per array its name
     //   (u64 length + bytes, BinaryIO.h:167-172) and DataArray::writeData (DataArray.h:100-105) = int lg2_grain_size (7),
     //   StdVector<Range{int lower, upper}>, StdVector<T> (u64 size, u64 sizeof(T), entries).  Arrays of this path: "X", "V" (TV),
-    //   "m", "element measure" (T), "F" (TM, column-major), "CorotatedIsotropic" (entries written as mu, lambda with sizeof 24,
-    //   CorotatedIsotropic.h:330-342).  The reader looks arrays up by NAME (DataManager.h:280-293), the order is free.
+    //   "m", "element measure" (T), "F" (TM, column-major), "CorotatedIsotropic" (the 24 raw bytes of the trivially copyable object: project flag,
+    //   padding, mu, lambda).  The reader looks arrays up by NAME (DataManager.h:280-293), the order is free.  Checked against the reference's own
+    //   DataManager / BinaryIO code in tests/test_restart_ref.py.
     //   The APIC matrix (scratch_gradV in the reference, written there only for interpolation_degree 1) follows as a trailing
     //   StdVector<TM>; a reader that does not expect it stops before it.
     void writeState(std::ostream& out)
@@ -526,78 +614,12 @@ public:
         std::vector<double> X(3 * n), V(3 * n), C(9 * n), F(9 * n), mu(n), lam(n);
         getParticles(X.data(), V.data(), C.data(), F.data());
         check(hot_get_plastic_state(h, nullptr, mu.data(), lam.data()));
-        auto w = [&](const void* p, size_t bytes) { out.write(reinterpret_cast<const char*>(p), (std::streamsize)bytes); };
-        auto u64 = [&](uint64_t v) { w(&v, 8); };
-        auto i32 = [&](int v) { w(&v, 4); };
-        auto header = [&](const char* name, uint64_t elem_bytes) {
-            const uint64_t len = std::strlen(name);
-            u64(len); w(name, len);
-            i32(7);                                  // DisjointRanges::lg2_grain_size
-            u64(1); u64(8); i32(0); i32((int)n);     // ranges = {[0, n)}
-            u64((uint64_t)n); u64(elem_bytes);
-        };
-        i32((int)n);
-        u64(6);
-        header("X", 24); w(X.data(), X.size() * 8);
-        header("V", 24); w(V.data(), V.size() * 8);
-        header("m", 8); w(mass_p.data(), (size_t)n * 8);
-        header("element measure", 8); w(vol_p.data(), (size_t)n * 8);
-        header("F", 72); w(F.data(), F.size() * 8);
-        header("CorotatedIsotropic", 24);
-        for (long i = 0; i < n; ++i) { w(&mu[i], 8); w(&lam[i], 8); }
-        u64(0); u64(12);                             // trimesh_to_write.indices (Vector<int, 3>)
-        u64(0); u64(8);                              // segmesh_to_write.indices (Vector<int, 2>)
-        u64((uint64_t)n); u64(72); w(C.data(), C.size() * 8);
+        writeRestart(out, n, X.data(), V.data(), mass_p.data(), vol_p.data(), F.data(), mu.data(), lam.data(), C.data());
     }
     void readState(std::istream& in)
     {
-        auto r = [&](void* p, size_t bytes) {
-            in.read(reinterpret_cast<char*>(p), (std::streamsize)bytes);
-            if (!in) throw HotError("readState: truncated restart file");
-        };
-        auto u64 = [&]() { uint64_t v; r(&v, 8); return v; };
-        auto i32 = [&]() { int v; r(&v, 4); return v; };
-        const int n = i32();
-        const uint64_t arrays = u64();
-        std::vector<double> X, V, m, vol, F, mu, lam, C;
-        for (uint64_t a = 0; a < arrays; ++a) {
-            std::string name(u64(), '\0');
-            r(&name[0], name.size());
-            (void)i32();
-            const uint64_t nr = u64(), rb = u64();
-            if (rb != 8) throw HotError("readState: Range size mismatch");
-            std::vector<int> ranges(2 * nr);
-            r(ranges.data(), nr * 8);
-            const uint64_t size = u64(), bytes = u64();
-            if ((long)size != n) throw HotError("readState: array " + name + " does not cover all particles");
-            auto take = [&](std::vector<double>& dst, uint64_t expect) {
-                if (bytes != expect) throw HotError("Read error: The size of the types don't match (" + name + ")");
-                dst.resize(size * expect / 8);
-                r(dst.data(), size * expect);
-            };
-            if (name == "X") take(X, 24);
-            else if (name == "V") take(V, 24);
-            else if (name == "m") take(m, 8);
-            else if (name == "element measure") take(vol, 8);
-            else if (name == "F") take(F, 72);
-            else if (name == "CorotatedIsotropic") {
-                if (bytes != 24) throw HotError("Read error: The size of the types don't match (CorotatedIsotropic)");
-                mu.resize(size); lam.resize(size);
-                for (uint64_t i = 0; i < size; ++i) { r(&mu[i], 8); r(&lam[i], 8); }
-            }
-            else throw HotError("Array " + name + " was not initialized before reading.");
-        }
-        for (int k = 0; k < 2; ++k) { // mesh index vectors
-            const uint64_t size = u64(), bytes = u64();
-            in.ignore((std::streamsize)(size * bytes));
-        }
-        C.assign(9 * (size_t)n, 0.0);
-        if (in.peek() != std::char_traits<char>::eof()) { // trailing APIC matrices (see writeState)
-            const uint64_t size = u64(), bytes = u64();
-            if ((long)size == n && bytes == 72) r(C.data(), (size_t)n * 72);
-        }
-        if (X.empty() || V.empty() || m.empty() || vol.empty() || F.empty() || mu.empty()) throw HotError("readState: missing particle arrays");
-        setParticles(n, X.data(), V.data(), m.data(), C.data(), F.data(), vol.data(), mu.data(), lam.data());
+        RestartArrays a = readRestart(in);
+        setParticles(a.n, a.X.data(), a.V.data(), a.m.data(), a.C.data(), a.F.data(), a.vol.data(), a.mu.data(), a.lam.data());
     }
 
     // One object over the GPUs of a box (include/hot_b200.h "one object over the GPUs of a box"; no counterpart in the single-process

@@ -14,10 +14,11 @@
 //   implicit solves (Newton + PCG / MGPCG, HOT)                     ImplicitSolver.h, ExtendedNewtonsMethod.h, LBFGS.h, ...   libimplicit_ref.so
 //   snow / von Mises return mappings                                PlasticityApplier.cpp                       libplasticity_ref.so
 //   collision objects, buildInitialDvAndVnForNewton (host mirror)   AnalyticLevelSet.cpp, CollisionObject.cpp   libcollider_ref.so
+//   restart files (host mirror)                                     DataManager.h, DataArray.h, BinaryIO.h      librestart_ref.so
 // The member functions of MpmSimulationBase / MpmForceBase / FBasedMpmForceHelper themselves cannot be compiled here (Scene / DataManager /
 // Particles / TBB containers / Partio absent): their particle loops are written out in the shims around the reference's grid, model and
-// objective code (each shim's header lists exactly which lines).  Still "parity unpinned" by reference code: the restart-file layout
-// and the extensions (Drucker-Prager, neo-Hookean) - those rest on the reference's in-code invariants and numpy / scipy checks.
+// objective code (each shim's header lists exactly which lines).  Not in the reference at all, hence without such a pin:
+// the extensions (Drucker-Prager, neo-Hookean) - those rest on closed forms, finite differences and numpy / scipy checks.
 //
 // Section 1: SPGrid addressing restated from Lib/SPGrid/Core/SPGrid_Mask.h:22-52,59-128,150-189,237-245.
 // Section 2: quadratic B-spline weights from Lib/Ziran/Math/Splines/BSplines.h:10-29,55-81 and

@@ -278,6 +278,7 @@ public:
     static PlainObject Zero() { PlainObject r; r.setZero(); return r; }
     static PlainObject Zero(int, int) { return Zero(); }
     template <class O> void resizeLike(const O&) {}
+    void resize(int, int) {}   // fixed size: Eigen accepts a resize to the same dimensions (BinaryIO.h:139)
     PlainObject normalized() const { PlainObject r = eval(); const Scalar n = norm(); if (n > Scalar(0)) { for (int k = 0; k < size(); ++k) r(k) = r(k) / n; } return r; }
     void normalize() { derived() = normalized(); }
     template <class O>

@@ -5,6 +5,7 @@
 #include <cstddef>
 #include <mutex>
 namespace tbb {
+struct split {};
 template <class T>
 class blocked_range {
     T b_, e_;
