@@ -41,15 +41,18 @@ inline double cneps = 1e-5;
 inline bool useAdaptiveHessian = false, useCN = false, matrixFree = false, project = false, systemBCProject = false, linesearch = false;
 inline int boundaryType = 0, lsolver = 0, Ainv = 0, smoother = 0, coarseSolver = 0, levelCnt = 1, times = 1, levelscale = 0, debugMode = 0;
 inline double omega = 1, topomega = 0.1;
+inline bool useBaselineMultigrid = false, topDownMGS = false; // accepted by the parser like the reference's; not implemented here: optionsFromSettings() refuses them
+inline bool revealJacobi = false, revealVcycle = false;       // timing printouts of the reference: accepted, without effect
 } // namespace HOTSettings
 
-// the flag subset of Projects/multigrid/main.cpp:40-84 that drives the hot path; unknown flags throw like
-// FLAGS::ParseFlags (Lib/Ziran/CS/Util/CommandLineFlags.h:185-206)
+// the flags of Projects/multigrid/main.cpp:40-84 (every registered flag is accepted, the ones outside the hot path are consumed and dropped); unknown
+// flags and flags without their value throw like FLAGS::ParseFlags (Lib/Ziran/CS/Util/CommandLineFlags.h:15-22,185-206).  Compared with the reference's
+// own parser in tests/test_flags_ref.py.
 inline void parseFlags(int argc, const char* const* argv)
 {
     using namespace HOTSettings;
     auto need = [&](int& i) -> const char* {
-        if (i + 1 >= argc) throw HotError(std::string("Missing value for flag ") + argv[i]);
+        if (i + 1 >= argc) throw HotError(std::string("Not enough arguments to ") + argv[i]);
         return argv[++i];
     };
     for (int i = 1; i < argc; ++i) {
@@ -60,7 +63,12 @@ inline void parseFlags(int argc, const char* const* argv)
         else if (f == "--project") project = true;
         else if (f == "--bcproject") systemBCProject = true;
         else if (f == "--linesearch") linesearch = true;
-        else if (f == "--3d" || f == "--double") {}
+        else if (f == "--baseline") useBaselineMultigrid = true;
+        else if (f == "--topDownMGS") topDownMGS = true;
+        else if (f == "--showresidual") revealJacobi = true;
+        else if (f == "--showvcycle") revealVcycle = true;
+        else if (f == "--3d" || f == "--double" || f == "--help" || f == "--run_diff_test") {}
+        else if (f == "-dbg") debugMode = std::stoi(need(i));
         else if (f == "-cneps") cneps = std::stod(need(i));
         else if (f == "-bc") boundaryType = std::stoi(need(i));
         else if (f == "-lsolver") lsolver = std::stoi(need(i));
@@ -72,13 +80,15 @@ inline void parseFlags(int argc, const char* const* argv)
         else if (f == "-mg_scale") levelscale = std::stoi(need(i));
         else if (f == "-mg_omega") omega = std::stod(need(i));
         else if (f == "-mg_jomega") topomega = std::stod(need(i));
-        else if (f == "-test" || f == "-o" || f == "-t" || f == "-cmd0" || f == "-cmd1" || f == "-dbg") need(i);
-        else throw HotError("Unknown flag: " + f);
+        else if (f == "-test" || f == "-o" || f == "-t" || f == "-cmd0" || f == "-cmd1" || f == "-script" || f == "-i" || f == "-dtps" || f == "-restart" || f == "-v_mu") need(i);
+        else throw HotError("Unknown flag " + f);
     }
 }
 
 inline hot_solver_options optionsFromSettings()
 {
+    if (HOTSettings::useBaselineMultigrid) throw HotError("--baseline: the geometric-multigrid baseline (MultigridSimulation.inl) is not part of this library");
+    if (HOTSettings::topDownMGS) throw HotError("--topDownMGS: the top-down multigrid schedule (MultigridPreconditioner.h:534-547) is not part of this library");
     hot_solver_options o;
     hot_default_options(&o);
     o.lsolver = HOTSettings::lsolver; o.matfree = HOTSettings::matrixFree; o.project = HOTSettings::project;

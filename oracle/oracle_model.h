@@ -15,6 +15,7 @@
 //   snow / von Mises return mappings                                PlasticityApplier.cpp                       libplasticity_ref.so
 //   collision objects, buildInitialDvAndVnForNewton (host mirror)   AnalyticLevelSet.cpp, CollisionObject.cpp   libcollider_ref.so
 //   restart files (host mirror)                                     DataManager.h, DataArray.h, BinaryIO.h      librestart_ref.so
+//   command-line flags (host mirror)                                CommandLineFlags.h, Configurations.h        libflags_ref.so
 // The member functions of MpmSimulationBase / MpmForceBase / FBasedMpmForceHelper themselves cannot be compiled here (Scene / DataManager /
 // Particles / TBB containers / Partio absent): their particle loops are written out in the shims around the reference's grid, model and
 // objective code (each shim's header lists exactly which lines).  Not in the reference at all, hence without such a pin:
