@@ -42,3 +42,23 @@ def test_exports_symbol_is_a_data_object():
 def test_backend_creates_a_handle(loader):
     f = _fields(subprocess.check_output([loader, PLUGIN, "create"], text=True))
     assert f["handle"] == "ok"
+
+
+REF_LOADER = os.path.join(ROOT, "oracle", "_ref", "plugin_ref_loader")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LOADER), reason="oracle/_ref/plugin_ref_loader not built (needs /root/reference)")
+def test_reference_plugin_manager_loads_the_plugin(tmp_path):
+    """the REFERENCE'S OWN loader - Lib/Ziran/CS/Util/{PluginManager.cpp, SharedLibrary.cpp} compiled where they lie (oracle/plugin_ref_loader.cpp) - runs
+    loadAllPlugins on a plugin directory holding hot_b200_plugin.so (a copy, like <build>/Plugins; libhot_b200.so on the library path), asserts the API
+    version, lets the plugin register its factory in the reference's PluginManager and retrieves it through the reference's getAll<Interface>()"""
+    import shutil
+    plugins = tmp_path / "Plugins"
+    plugins.mkdir()
+    shutil.copy(PLUGIN, plugins / "hot_b200_plugin.so")
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "hot_b200", "lib") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    f = _fields(subprocess.check_output([REF_LOADER, str(plugins)], text=True, env=env))
+    assert f["plugins"] == "1" and f["factories"] == "1"
+    assert f["apiVersion"] == "2" and f["className"] == "HotB200Plugin"
+    assert f["supported(double,3)"] == "1" and f["supported(float,3)"] == "0" and f["supported(double,2)"] == "0"
+    assert f["abi"] == "hot_b200.h"
