@@ -19,6 +19,7 @@
 #include <cstring>
 #include <functional>
 #include <istream>
+#include <limits>
 #include <memory>
 #include <ostream>
 #include <stdexcept>
@@ -114,6 +115,8 @@ struct AnalyticLevelSet {
     virtual ~AnalyticLevelSet() = default;
     virtual bool query(const TV& X, double& phi, TV& n) const = 0; // true when inside (phi <= 0)
     virtual void describe(hot_collider& c) const = 0;
+    // material-space bounding box (used by evalMaxSpeed); the reference's base class - and with it HalfSpace - has none (AnalyticLevelSet.cpp:121-125)
+    virtual void getBounds(TV&, TV&) const { throw HotError("No bounds available."); }
 };
 inline TV matVec(const TM& M, const TV& x) { return {M[0] * x[0] + M[3] * x[1] + M[6] * x[2], M[1] * x[0] + M[4] * x[1] + M[7] * x[2], M[2] * x[0] + M[5] * x[1] + M[8] * x[2]}; }
 inline TV matTVec(const TM& M, const TV& x) { return {M[0] * x[0] + M[1] * x[1] + M[2] * x[2], M[3] * x[0] + M[4] * x[1] + M[5] * x[2], M[6] * x[0] + M[7] * x[1] + M[8] * x[2]}; }
@@ -162,6 +165,10 @@ struct Sphere : AnalyticLevelSet { // Sphere::queryInside, AnalyticLevelSet.cpp:
         n = l < 1e-7 ? TV{1, 0, 0} : TV{d[0] / l, d[1] / l, d[2] / l};
         return true;
     }
+    void getBounds(TV& lo, TV& hi) const override // AnalyticLevelSet.cpp:464-469
+    {
+        for (int d = 0; d < 3; ++d) { lo[d] = center[d] - radius; hi[d] = center[d] + radius; }
+    }
     void describe(hot_collider& c) const override
     {
         c.shape = HOT_SHAPE_SPHERE;
@@ -174,10 +181,20 @@ struct Sphere : AnalyticLevelSet { // Sphere::queryInside, AnalyticLevelSet.cpp:
 struct AnalyticBox : AnalyticLevelSet {
     TV half_edges, b;
     TM R;
+    bool axis_aligned = false; // built by axisAligned(): stands for the reference's AxisAlignedAnalyticBox, whose bounds are its corners
+    TV aa_min{0, 0, 0}, aa_max{0, 0, 0};
     AnalyticBox(const TV& h, const std::array<double, 4>& q, const TV& b_in) : half_edges(h), b(b_in), R(quaternionToMatrix(q[0], q[1], q[2], q[3])) {}
     static AnalyticBox axisAligned(const TV& lo, const TV& hi)
     {
-        return AnalyticBox({(hi[0] - lo[0]) / 2, (hi[1] - lo[1]) / 2, (hi[2] - lo[2]) / 2}, {1, 0, 0, 0}, {(lo[0] + hi[0]) / 2, (lo[1] + hi[1]) / 2, (lo[2] + hi[2]) / 2});
+        AnalyticBox box({(hi[0] - lo[0]) / 2, (hi[1] - lo[1]) / 2, (hi[2] - lo[2]) / 2}, {1, 0, 0, 0}, {(lo[0] + hi[0]) / 2, (lo[1] + hi[1]) / 2, (lo[2] + hi[2]) / 2});
+        box.axis_aligned = true; box.aa_min = lo; box.aa_max = hi;
+        return box;
+    }
+    void getBounds(TV& lo, TV& hi) const override // AnalyticBox: bounding sphere around b (.cpp:541-548); AxisAlignedAnalyticBox: the box (.cpp:370-374)
+    {
+        if (axis_aligned) { lo = aa_min; hi = aa_max; return; }
+        const double r = norm(half_edges);
+        for (int d = 0; d < 3; ++d) { lo[d] = -r + b[d]; hi[d] = r + b[d]; }
     }
     bool query(const TV& X, double& phi, TV& n) const override
     {
@@ -227,6 +244,11 @@ struct CappedCylinder : AnalyticLevelSet {
         n = matVec(R, Np);
         return true;
     }
+    void getBounds(TV& lo, TV& hi) const override // AnalyticLevelSet.h:287-293: bounding sphere around b
+    {
+        const double r = std::sqrt(radius * radius + (0.5 * height) * (0.5 * height));
+        for (int d = 0; d < 3; ++d) { lo[d] = -r + b[d]; hi[d] = r + b[d]; }
+    }
     void describe(hot_collider& c) const override
     {
         c.shape = HOT_SHAPE_CAPPED_CYLINDER;
@@ -249,6 +271,41 @@ struct AnalyticCollisionObject {
     void setRotation(const std::array<double, 4>& q) { R = quaternionToMatrixRaw(q[0], q[1], q[2], q[3]); } // <w, x, y, z>, NOT normalised: Rotation(q), Rotation.h:51-56
     void setAngularVelocity(const TV& w) { omega = w; }
     void setTranslation(const TV& b_in, const TV& dbdt_in) { b = b_in; dbdt = dbdt_in; }
+
+    // evalMaxSpeed, CollisionObject.cpp:201-238: the largest object speed at the corners where the particles' box and the object's bounds meet
+    double evalMaxSpeed(const TV& p_min_corner, const TV& p_max_corner) const
+    {
+        const auto velocity = [&](const TV& x) {
+            const TV xb = sub(x, b);
+            const double k = dsdt * (1 / s);
+            return TV{omega[1] * xb[2] - omega[2] * xb[1] + k * xb[0] + dbdt[0], omega[2] * xb[0] - omega[0] * xb[2] + k * xb[1] + dbdt[1],
+                omega[0] * xb[1] - omega[1] * xb[0] + k * xb[2] + dbdt[2]};
+        };
+        if (dsdt != 0 || norm(omega) != 0) {
+            TV lo, hi;
+            ls->getBounds(lo, hi);
+            const auto overlaps = [](const TV& a_lo, const TV& y, const TV& a_hi) { // (lo < y).any() && (y < hi).any(), as the reference writes it
+                return (a_lo[0] < y[0] || a_lo[1] < y[1] || a_lo[2] < y[2]) && (y[0] < a_hi[0] || y[1] < a_hi[1] || y[2] < a_hi[2]);
+            };
+            double max_speed = 0;
+            for (int i = 0; i < 8; ++i) {
+                TV x;
+                for (int d = 0; d < 3; ++d) x[d] = (i & (1 << d)) ? p_min_corner[d] : p_max_corner[d];
+                TV X = matTVec(R, sub(x, b));
+                for (int d = 0; d < 3; ++d) X[d] *= 1 / s;
+                if (overlaps(lo, X, hi)) max_speed = std::max(max_speed, norm(velocity(x)));
+            }
+            for (int i = 0; i < 8; ++i) {
+                TV X;
+                for (int d = 0; d < 3; ++d) X[d] = ((i & (1 << d)) ? lo[d] : hi[d]) * s;
+                TV x = matVec(R, X);
+                for (int d = 0; d < 3; ++d) x[d] += b[d];
+                if (overlaps(p_min_corner, x, p_max_corner)) max_speed = std::max(max_speed, norm(velocity(x)));
+            }
+            return max_speed;
+        }
+        return norm(dbdt);
+    }
 
     // detectAndResolveCollision, CollisionObject.cpp:384-452 (material velocity 0)
     bool detectAndResolveCollision(const TV& x, TV& v, TV& n) const
@@ -371,6 +428,25 @@ inline bool collisionNodeAt(const std::vector<AnalyticCollisionObject>& objects,
         }
     for (int d = 0; d < 3; ++d) dv_bc[d] = vi[d] - old_v[d];
     return true;
+}
+
+// calculateDt (MpmSimulationBase.cpp:789-814) with evalMaxParticleSpeed (:1190-1217) on host arrays: dt = cfl dx / max(particle speed, object speed over
+// the particles' box grown by (degree + 2) dx), or max_dt when nothing moves
+inline double calculateDtFromArrays(long n, const double* X, const double* V, double dx, double cfl, double max_dt, const std::vector<AnalyticCollisionObject>& objects)
+{
+    const double Tmin = (double)std::numeric_limits<float>::lowest(); // the reference's initial value of the max reduction (:1196)
+    double speed = 0;
+    TV hi{Tmin, Tmin, Tmin}, neg_lo{Tmin, Tmin, Tmin};
+    for (long i = 0; i < n; ++i) {
+        speed = std::max(speed, std::sqrt(V[3 * i] * V[3 * i] + V[3 * i + 1] * V[3 * i + 1] + V[3 * i + 2] * V[3 * i + 2]));
+        for (int d = 0; d < 3; ++d) { hi[d] = std::max(hi[d], X[3 * i + d]); neg_lo[d] = std::max(neg_lo[d], -X[3 * i + d]); }
+    }
+    TV p_min, p_max;
+    for (int d = 0; d < 3; ++d) { p_min[d] = -neg_lo[d] - (2 + 2) * dx; p_max[d] = hi[d] + (2 + 2) * dx; } // interpolation_degree 2
+    double object_speed = 0;
+    for (const auto& o : objects) object_speed = std::max(o.evalMaxSpeed(p_min, p_max), object_speed);
+    const double m = std::max(speed, object_speed);
+    return m ? cfl * dx / m : max_dt;
 }
 
 // the byte stream of the restart files (layout: see MpmSimulationB200::writeState), host arrays in and out; C (the APIC matrices) may be null on writing
@@ -498,6 +574,15 @@ public:
     void getParticles(double* X, double* V, double* C, double* F) { check(hot_get_particles(h, X, V, C, F, nullptr)); }
     std::vector<double> mass_p, vol_p;
     long particleCount() const { return N; }
+
+    // calculateDt (MpmSimulationBase.cpp:789-814), the virtual the reference's frame loop calls between steps.  Reads X and V back (O(N) device -> host
+    // copy per call; a device-side reduction is the follow-up) and evaluates the rule on the host
+    double calculateDt(double max_dt)
+    {
+        std::vector<double> X(3 * (size_t)N), V(3 * (size_t)N);
+        getParticles(X.data(), V.data(), nullptr, nullptr);
+        return calculateDtFromArrays(N, X.data(), V.data(), dx, cfl, max_dt, collision_objects);
+    }
 
     void sortParticlesAndPolluteGrid() { check(hot_sort_and_activate(h)); } // MpmSimulationBase.cpp:1066-1137
     void particlesToGrid() { check(hot_p2g(h, &num_nodes)); } // :461-533

@@ -102,4 +102,21 @@ void zr_colliders_eval(int n_obj, const double* objs, long n, const double* xi_i
     }
 }
 
+// AnalyticCollisionObject::evalMaxSpeed (CollisionObject.cpp:201-238) of every object for the particle box [p_min, p_max] (what calculateDt,
+// MpmSimulationBase.cpp:802-804, asks for); NaN where the reference throws (a rotating / scaling object over a level set without bounds: HalfSpace)
+void zr_colliders_max_speed(int n_obj, const double* objs, const double* p_min, const double* p_max, double* out)
+{
+    StdVector<std::unique_ptr<Object>> collision_objects;
+    build(n_obj, objs, collision_objects);
+    const TV lo(p_min[0], p_min[1], p_min[2]), hi(p_max[0], p_max[1], p_max[2]);
+    for (int k = 0; k < n_obj; ++k) {
+        try {
+            out[k] = collision_objects[k]->evalMaxSpeed(lo, hi);
+        }
+        catch (...) {
+            out[k] = NAN;
+        }
+    }
+}
+
 } // extern "C"

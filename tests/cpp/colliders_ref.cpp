@@ -6,6 +6,7 @@
 #include "hot_b200_host.hpp"
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 using namespace hot_b200;
 
@@ -43,6 +44,23 @@ int main(int argc, char** argv)
     }
     FILE* out = std::fopen(argv[2], "wb");
     if (!out) return 6;
+    if (argc > 3 && std::string(argv[3]) == "speed") { // evalMaxSpeed of every object for the box [xi[0], xi[1]]; NaN where the mirror throws
+        const TV lo{xi[0], xi[1], xi[2]}, hi{xi[3], xi[4], xi[5]};
+        for (const auto& o : objects) {
+            double sp;
+            try { sp = o.evalMaxSpeed(lo, hi); }
+            catch (const HotError&) { sp = std::nan(""); }
+            std::fwrite(&sp, 8, 1, out);
+        }
+        // calculateDt of a particle set = the two box corners moving with v[0], v[1], among these objects (cfl 0.6, dx 1/32, max_dt 1e-2): skipping the
+        // objects the reference would throw on
+        std::vector<AnalyticCollisionObject> ok;
+        for (const auto& o : objects) { try { (void)o.evalMaxSpeed(lo, hi); ok.push_back(o); } catch (const HotError&) {} }
+        const double dtc = calculateDtFromArrays(2, xi.data(), v.data(), 1.0 / 32, 0.6, 1e-2, ok);
+        std::fwrite(&dtc, 8, 1, out);
+        std::fclose(out);
+        return 0;
+    }
     for (long long i = 0; i < n; ++i) {
         const TV x{xi[3 * i], xi[3 * i + 1], xi[3 * i + 2]}, old_v{v[3 * i], v[3 * i + 1], v[3 * i + 2]};
         CollisionNode Z;

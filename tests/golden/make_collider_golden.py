@@ -81,6 +81,19 @@ def reference(objs, xi, v):
     return dict(collide=collide, dv=dv, P=P, R=R, Rinv=Rinv, slip=slip)
 
 
+def reference_max_speed(objs, p_min, p_max):
+    lib = C.CDLL(REF_LIB)
+    o = np.ascontiguousarray(np.concatenate(objs))
+    lo = np.ascontiguousarray(p_min, dtype=np.float64); hi = np.ascontiguousarray(p_max, dtype=np.float64)
+    out = np.empty(len(objs))
+    lib.zr_colliders_max_speed(len(objs), _p(o), _p(lo), _p(hi), _p(out))
+    return out
+
+
+# particle boxes for evalMaxSpeed (calculateDt): around the objects, far from them, inside them
+BOXES = [((0.2, 0.2, 0.2), (0.9, 0.9, 0.9)), ((-0.3, 0.0, 0.1), (0.4, 1.4, 1.2)), ((3.0, 3.0, 3.0), (3.5, 3.2, 3.1)), ((0.45, 0.45, 0.45), (0.55, 0.55, 0.55))]
+
+
 if __name__ == "__main__":
     gold = {}
     for k, (name, objs) in enumerate(scenes().items()):
@@ -91,5 +104,10 @@ if __name__ == "__main__":
             gold[f"{name}/{key}"] = val
         two = int(((np.abs(out["P"]).sum(1) > 0) & (out["slip"] == 1) & (np.abs(np.linalg.det(out["P"].reshape(-1, 3, 3))) < 1e-12)).sum())
         print(name, "points", len(xi), "colliding", int(out["collide"].sum()), "slip", int(out["slip"].sum()), "sticky", int((out["collide"] - out["slip"]).sum()))
+    for name, objs in scenes().items():
+        gold[name + "/max_speed"] = np.stack([reference_max_speed(objs, lo, hi) for lo, hi in BOXES])
+        g = 4.0 / 32          # calculateDt grows the particles' box by (interpolation_degree + 2) dx, dx = 1/32 in the test
+        gold[name + "/max_speed_grown"] = np.stack([reference_max_speed(objs, np.asarray(lo) - g, np.asarray(hi) + g) for lo, hi in BOXES])
+        print(name, "max speeds", np.round(gold[name + "/max_speed"], 4).tolist())
     np.savez_compressed(OUT, **gold)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

@@ -58,6 +58,30 @@ def test_host_collision_objects_against_reference_code(mirror, tmp_path, name):
         assert err <= 1e-12 * max(1.0, np.abs(b).max()), (name, k, err)
 
 
+@pytest.mark.parametrize("name", SCENES)
+def test_host_max_speed_and_calculate_dt_against_reference_code(mirror, tmp_path, name):
+    """AnalyticCollisionObject::evalMaxSpeed (CollisionObject.cpp:201-238) of every object of the scene for four particle boxes - what calculateDt
+    (MpmSimulationBase.cpp:789-814) takes its object speed from - and the dt rule itself on a two-particle set"""
+    objs = G[name + "/objects"]
+    for k, (lo, hi) in enumerate(gen.BOXES):
+        inp, out = str(tmp_path / f"in{k}.bin"), str(tmp_path / f"out{k}.bin")
+        xi = np.array([lo, hi], dtype=np.float64); v = np.array([[0.3, -0.2, 0.1], [0.0, 0.5, 0.0]])
+        with open(inp, "wb") as f:
+            f.write(struct.pack("<qqd3d", len(objs), 2, gen.DT, *gen.GRAVITY))
+            for a in (objs, xi, v):
+                f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+        subprocess.check_call([mirror, inp, out, "speed"])
+        rec = np.fromfile(out, dtype=np.float64)
+        got, dt = rec[:len(objs)], rec[len(objs)]
+        ref = G[name + "/max_speed"][k]
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), (name, k)              # where the reference throws "No bounds available." the mirror throws
+        ok = ~np.isnan(ref)
+        assert np.abs(got[ok] - ref[ok]).max() <= 1e-12 * max(1.0, np.abs(ref[ok]).max()), (name, k, got, ref)
+        grown = G[name + "/max_speed_grown"][k]                      # calculateDt: cfl dx / max(particle speed, object speed over the box grown by 4 dx)
+        top = max(np.linalg.norm(v, axis=1).max(), np.nanmax(grown) if ok.any() else 0.0)
+        assert abs(dt - 0.6 * (1.0 / 32) / top) <= 1e-12 * dt
+
+
 def test_golden_scenes_exercise_the_branches():
     m, c = "mixed", "slip_corner"
     assert 0 < G[m + "/slip"].sum() < G[m + "/collide"].sum()                             # sticky and slip nodes
