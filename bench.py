@@ -173,29 +173,24 @@ def cpu_baseline(sc, reps, warmup=1):
 def reference_code_baseline(sc, max_particles=250000, reps=2):
     """P2G + G2P of the REFERENCE'S OWN grid code (Lib/MPM/MpmGrid.h over its SPGrid page map, compiled where it lies into
     oracle/_ref/libmpmgrid_ref.so; its TBB loops run serially because TBB is not in this image) on a bounded spatial slab of the workload:
-    reported beside the OpenMP port so the port can be judged against the code it restates.  None when the library is absent."""
+    reported beside the OpenMP port so the port can be judged against the code it restates.  None when the library is absent.
+    Runs in a CHILD PROCESS with a timeout: the reference's SPGrid allocator reserves its 4096^3 address range with one mmap and throws C++
+    exceptions on failure, which must not be able to take the bench line down with them."""
     try:
-        import importlib.util
-        path = os.path.join(ROOT, "tests", "golden", "make_mpmgrid_golden.py")
-        spec = importlib.util.spec_from_file_location("make_mpmgrid_golden", path)
-        gen = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(gen)
-        if not os.path.exists(gen.REF_LIB):
+        import subprocess
+        import tempfile
+        helper = os.path.join(ROOT, "tests", "golden", "make_mpmgrid_golden.py")
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libmpmgrid_ref.so")):
             return None
         n = len(sc["mass"])
         keep = np.argsort(sc["X"][:, 0], kind="stable")[:min(n, max_particles)]      # the lowest-x slab: a compact piece of the object
-        ref = gen.Reference(sc["dx"])
-        ref.set_particles(sc["X"][keep], sc["V"][keep], sc["mass"][keep], sc["C"][keep])
-        ref.sortParticlesAndPolluteGrid()
-        times = []
-        for it in range(1 + reps):
-            t0 = time.perf_counter()
-            nn = ref.particlesToGrid()
-            ref.set_dv(np.zeros((nn, 3)))
-            ref.gridToParticles(0.0)
-            if it >= 1:
-                times.append(time.perf_counter() - t0)
-        t = float(np.mean(times))
+        with tempfile.TemporaryDirectory() as tmp:
+            f = os.path.join(tmp, "slab.npz")
+            np.savez(f, X=sc["X"][keep], V=sc["V"][keep], mass=sc["mass"][keep], C=sc["C"][keep], dx=sc["dx"], reps=reps)
+            out = subprocess.run([sys.executable, helper, "time", f], capture_output=True, text=True, timeout=120)
+        if out.returncode != 0:
+            return {"error": f"child exited with {out.returncode}: {out.stderr.strip()[-200:]}"}
+        t = float(out.stdout.strip().splitlines()[-1])
         return {"value": len(keep) / t / 1e6, "unit": UNIT, "cores": 1, "kind": "reference",
                 "sample": f"lowest-x slab of {len(keep)} particles, {reps} timed P2G+G2P steps of the reference's MpmGrid / SPGrid code "
                           f"(oracle/_ref/libmpmgrid_ref.so; serial: TBB absent)"}

@@ -133,6 +133,28 @@ def run(sim, inp, dv=None):
     return out
 
 
+def time_slab(path):
+    """bench.py's cpu_baseline.reference_code leg (run as a child process): mean seconds of one P2G + G2P(dt = 0) pass over the particles of `path`"""
+    import time
+    d = np.load(path)
+    ref = Reference(float(d["dx"]))
+    ref.set_particles(d["X"], d["V"], d["mass"], d["C"])
+    ref.sortParticlesAndPolluteGrid()
+    times = []
+    for it in range(1 + int(d["reps"])):
+        t0 = time.perf_counter()
+        nn = ref.particlesToGrid()
+        ref.set_dv(np.zeros((nn, 3)))
+        ref.gridToParticles(0.0)
+        if it >= 1:
+            times.append(time.perf_counter() - t0)
+    print(repr(float(np.mean(times))))
+
+
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[1] == "time":
+    time_slab(sys.argv[2])
+    sys.exit(0)
+
 if __name__ == "__main__":
     gold = {}
     r0 = Reference(0.1)
