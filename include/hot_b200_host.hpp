@@ -892,6 +892,33 @@ private:
 };
 
 // ---- Krylov / Newton objective concept ---------------------------------------------------------------------------------------
+// ImplicitSolverObjective::shouldExitByCN (ImplicitSolver.h:171-215) on host arrays: without --usecn the l2 norm against cneps, with it the residual
+// scaled per node by the CN tolerance against the node count
+inline bool shouldExitByCN(const TVStack& residual, const std::vector<double>& nodeCNTol, int num_nodes)
+{
+    if (!HOTSettings::useCN) {
+        double s = 0;
+        for (double x : residual) s += x * x;
+        return std::sqrt(s) < HOTSettings::cneps;
+    }
+    double scaled = 0;
+    for (int i = 0; i < num_nodes; ++i)
+        scaled += (residual[3 * i] * residual[3 * i] + residual[3 * i + 1] * residual[3 * i + 1] + residual[3 * i + 2] * residual[3 * i + 2]) / (nodeCNTol[i] * nodeCNTol[i]);
+    if (num_nodes == 0) return true;
+    return scaled < num_nodes;
+}
+// transformResidual (R, :117-125) / recoverSolution (R^-1, :103-115): slip collision nodes live in their rotated frame when the system is BC-projected
+inline void rotateCollisionNodes(const std::vector<CollisionNode>& nodes, TVStack& v, bool inverse)
+{
+    if (!(HOTSettings::systemBCProject && HOTSettings::boundaryType == 1)) return;
+    for (const CollisionNode& c : nodes)
+        if (c.shouldRotate) {
+            const TV x{v[3 * c.node_id], v[3 * c.node_id + 1], v[3 * c.node_id + 2]};
+            const TV y = matVec(inverse ? c.Rinv : c.R, x);
+            for (int d = 0; d < 3; ++d) v[3 * c.node_id + d] = y[d];
+        }
+}
+
 class ImplicitSolverObjectiveB200 {
 public:
     using Scalar = double;
@@ -938,6 +965,61 @@ public:
         buildMatrix(true);
         simulation.check(hot_build_mg(simulation.handle(), HOTSettings::levelCnt, HOTSettings::smoother, HOTSettings::coarseSolver,
             HOTSettings::Ainv, HOTSettings::times, HOTSettings::levelscale, HOTSettings::topomega));
+    }
+    // the rest of the duck-typed objective the reference's Newton / L-BFGS templates call (ImplicitSolver.h); host logic over the C ABI.  The library
+    // runs the same sequence internally (hot_backward_euler_step), which is the tested path; these members exist so that an outer loop kept in the
+    // reference can drive the device operators one call at a time.
+    std::vector<double> nodeCNTol;
+    TVStack dv0;
+    double cg_tolerance = 1;      // cg.setTolerance(1) of the constructor (:86-88); backwardEulerStep sets maxcntol with --usecn (MultigridSimulation.h:207)
+    int cg_max_iterations = 10000;
+    void evaluatePerNodeCNTolerance(double eps, double dt) // :667-696
+    {
+        nodeCNTol.resize((size_t)simulation.num_nodes);
+        simulation.check(hot_eval_cn_tolerance(simulation.handle(), eps, dt, nodeCNTol.data()));
+    }
+    bool shouldExitByCN(const TVStack& residual) { return hot_b200::shouldExitByCN(residual, nodeCNTol, simulation.num_nodes); } // :171-215
+    void transformResidual(TVStack& r) { rotateCollisionNodes(simulation.collision_nodes, r, false); }                         // :117-125
+    void recoverSolution(TVStack& ddv) { rotateCollisionNodes(simulation.collision_nodes, ddv, true); }                        // :103-115
+    void resetLSFlag(const TVStack& dv) { dv0 = dv; }                                                                           // :277-282
+    double lineSearch(TVStack& ddv, TVStack& residual, double alpha) // :313-333 (capped at 60 halvings like the library: a NaN energy would loop forever)
+    {
+        TVStack dvnew(ddv.size());
+        recoverSolution(ddv);
+        const bool ls = HOTSettings::linesearch;
+        HOTSettings::linesearch = true; // updateState must return the energy
+        const double Ek0 = Ek;
+        int halvings = 0;
+        do {
+            for (size_t i = 0; i < ddv.size(); ++i) dvnew[i] = dv0[i] + ddv[i] * alpha;
+            updateState(dvnew, true);
+            alpha *= 0.5;
+        } while (Ek > Ek0 && ++halvings < 60);
+        HOTSettings::linesearch = ls;
+        alpha *= 2;
+        for (double& x : ddv) x *= alpha;
+        transformResidual(ddv);
+        computeResidual(residual, true);
+        dv0 = dvnew;
+        return alpha;
+    }
+    void computeStep(TVStack& ddv, const TVStack& residual, double /* linear_solve_relative_tolerance: the inexact CG derives its own */) // :355-432, -lsolver 2
+    {
+        ddv.assign(residual.size(), 0.0);
+        int preconditioner = 1, iters = 0;
+        if (!matrix_free) {
+            buildMatrix(HOTSettings::systemBCProject);
+            simulation.check(hot_build_mg(simulation.handle(), HOTSettings::levelCnt, HOTSettings::smoother, HOTSettings::coarseSolver, HOTSettings::Ainv,
+                HOTSettings::times, HOTSettings::levelscale, HOTSettings::topomega));
+            preconditioner = (HOTSettings::levelCnt == 1 && HOTSettings::times == 1) ? 1 : 2; // "force diagonal entry preconditioner", :381-396
+        }
+        else
+            simulation.check(hot_build_diagonal(simulation.handle(), HOTSettings::Ainv, nullptr));
+        simulation.check(hot_pcg(simulation.handle(), residual.data(), ddv.data(), cg_tolerance, cg_max_iterations, matrix_free ? 1 : 0, preconditioner, &iters));
+        if (HOTSettings::linesearch) {
+            TVStack r = residual;
+            lineSearch(ddv, r, 1.0);
+        }
     }
 };
 

@@ -88,6 +88,29 @@ def test_golden_exit_tests_bracket_the_threshold():
         assert abs(scaled.sum() / n - 1.0) < 1e-9
 
 
+def test_host_exit_test_against_reference_code(tmp_path):
+    """hot_b200::shouldExitByCN (the exit test of ImplicitSolverObjectiveB200, include/hot_b200_host.hpp; driver tests/cpp/objective_ref.cpp) takes the
+    decisions of the reference's ImplicitSolverObjective::shouldExitByCN on residuals scaled just below / above the threshold, with and without --usecn"""
+    import struct
+    import subprocess
+    exe = str(tmp_path / "objective_ref")
+    lib = os.path.join(ROOT, "hot_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "objective_ref.cpp"),
+                           "-o", exe, "-L", lib, "-lhot_b200", f"-Wl,-rpath,{lib}", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    for name in gen.CASES:
+        r, tol, f = G[f"{name}/residual"], G[f"{name}/cntol"], float(G[f"{name}/exit_scale"])
+        l2 = float(np.sqrt((r ** 2).sum()))
+        calls = [(1, 0.0, 0.99 * f), (1, 0.0, 1.01 * f), (0, 1.01 * l2, 1.0), (0, 0.99 * l2, 1.0)]      # (useCN, cneps, scale): make_implicit_golden.py
+        got = []
+        for k, (usecn, cneps, scale) in enumerate(calls):
+            inp = str(tmp_path / f"{name}{k}.bin")
+            with open(inp, "wb") as fh:
+                fh.write(struct.pack("<qqdd", len(tol), usecn, cneps, scale))
+                fh.write(np.ascontiguousarray(r, dtype=np.float64).tobytes()); fh.write(np.ascontiguousarray(tol, dtype=np.float64).tobytes())
+            got.append(int(subprocess.check_output([exe, inp], text=True).strip()))
+        assert got == [int(x) for x in G[f"{name}/exit"]], (name, got)
+
+
 def _check_step(make_sim, name, rtol_dv):
     """a whole implicit solve (row a24 + the Newton / L-BFGS outer loops a22): same number of nonlinear iterations, same tolerance, same dv"""
     sc_args, opts = gen.STEPS[name]
